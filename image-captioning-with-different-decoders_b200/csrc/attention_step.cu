@@ -1,0 +1,462 @@
+// Fused additive-attention step kernels (HBM-bound).  Reference: models/attention.py:55-60, 270-271.
+//
+// Forward, per decoder row r (image b = img_index ? img_index[r] : r):
+//   scores kernel : e[p] = sum_a relu(att_enc[b,p,a] + att_dec[r,a]) * w_full[a] + b_full     (:55-57)
+//                   alpha = softmax_p(e)                                                        (:58)
+//                   one CTA per row streams the 196x512 att_enc tile once (401 KB), warp-per-pixel rows,
+//                   128-bit coalesced loads, warp-shuffle dot, block softmax.
+//   weighted-sum  : awe[c] = sum_p alpha[p] * enc[b,p,c]; gate = sigmoid(fbeta_pre); gated = gate*awe
+//                   grid (C/256, rows): a CTA streams a 196 x 1 KB column panel of enc with 4 pixel
+//                   groups x 64 float4 lanes, 7 independent 128-bit loads in flight per thread,
+//                   cross-group reduce in shared memory, gate fused in the epilogue.   (:59-60, 270-271)
+// The (B,196,2048) `enc*alpha` temporary of the reference (:59) is never materialised.
+//
+// Backward, per row: d_awe = d_gated*gate, d_fbeta_pre = d_gated*awe_raw*gate*(1-gate),
+//   d_alpha[p] = <d_awe, enc[b,p,:]> (+ upstream), softmax backward in centred form,
+//   d_att_dec[a] = w_full[a] * sum_p d_e[p] * [att_enc[b,p,a]+att_dec[a] > 0].
+// d_att_enc is NOT read-modify-written per step: d_e is saved per step and one kernel after the time
+// loop (attention_proj_bwd) forms d_att_enc and d_w_full for all steps at once.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// scores + softmax.  grid = rows, block = 256 (8 warps).  smem: 2*A + P + 40 floats.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) att_scores_softmax_kernel(
+        int P, int A, const int* __restrict__ img_index,
+        const float* __restrict__ att_enc, const float* __restrict__ att_dec, long long ld_dec,
+        const float* __restrict__ w_full, const float* __restrict__ b_full,
+        float* __restrict__ alpha, long long ld_alpha) {
+    extern __shared__ __align__(16) float sm[];
+    float* s_dec = sm;            // A
+    float* s_wf = sm + A;         // A
+    float* s_e = sm + 2 * A;      // P
+    float* s_red = s_e + P;       // 40
+    const int r = blockIdx.x;
+    const int img = img_index ? img_index[r] : r;
+    const float* ae = att_enc + (long long)img * P * A;
+    const float* dec = att_dec + (long long)r * ld_dec;
+    for (int a = threadIdx.x; a < A; a += blockDim.x) { s_dec[a] = dec[a]; s_wf[a] = w_full[a]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const float bfull = b_full ? b_full[0] : 0.f;
+    const int A4 = A >> 2;
+    // two pixel rows per warp iteration => 2 * (A/128) independent 128-bit loads in flight per lane
+    for (int p = warp; p < P; p += 2 * nwarp) {
+        const int p2 = p + nwarp;
+        const bool has2 = p2 < P;
+        const float* row0 = ae + (long long)p * A;
+        const float* row1 = ae + (long long)(has2 ? p2 : p) * A;
+        float acc0 = 0.f, acc1 = 0.f;
+        for (int j = lane; j < A4; j += 32) {
+            const float4 x0 = ld_stream_f4(row0 + 4 * j);
+            const float4 x1 = ld_stream_f4(row1 + 4 * j);
+            const float4 d = *reinterpret_cast<const float4*>(s_dec + 4 * j);
+            const float4 w = *reinterpret_cast<const float4*>(s_wf + 4 * j);
+            acc0 = fmaf(fmaxf(x0.x + d.x, 0.f), w.x, acc0);
+            acc0 = fmaf(fmaxf(x0.y + d.y, 0.f), w.y, acc0);
+            acc0 = fmaf(fmaxf(x0.z + d.z, 0.f), w.z, acc0);
+            acc0 = fmaf(fmaxf(x0.w + d.w, 0.f), w.w, acc0);
+            acc1 = fmaf(fmaxf(x1.x + d.x, 0.f), w.x, acc1);
+            acc1 = fmaf(fmaxf(x1.y + d.y, 0.f), w.y, acc1);
+            acc1 = fmaf(fmaxf(x1.z + d.z, 0.f), w.z, acc1);
+            acc1 = fmaf(fmaxf(x1.w + d.w, 0.f), w.w, acc1);
+        }
+        acc0 = warp_sum(acc0);
+        acc1 = warp_sum(acc1);
+        if (lane == 0) { s_e[p] = acc0 + bfull; if (has2) s_e[p2] = acc1 + bfull; }
+    }
+    __syncthreads();
+    float m = -INFINITY;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) m = fmaxf(m, s_e[p]);
+    m = block_max(m, s_red);
+    float sum = 0.f;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) { const float ex = expf(s_e[p] - m); s_e[p] = ex; sum += ex; }
+    sum = block_sum(sum, s_red);
+    float* out = alpha + (long long)r * ld_alpha;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) out[p] = s_e[p] / sum;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weighted pixel sum + gate.  grid = (ceil(C/256), rows), block = 256 = 4 pixel groups x 64 float4 lanes.
+// alpha == NULL  => plain mean over pixels (init_hidden_state, models/attention.py:161).
+// ------------------------------------------------------------------------------------------------
+constexpr int WS_LANES = 64, WS_GROUPS = 4, WS_UNROLL = 7;
+
+__global__ void __launch_bounds__(256) weighted_pixel_sum_kernel(
+        int P, int C, const int* __restrict__ img_index, const float* __restrict__ enc,
+        const float* __restrict__ alpha, long long ld_alpha,
+        const float* __restrict__ fbeta_pre, long long ld_fb,
+        float* __restrict__ awe_raw, float* __restrict__ gate, float* __restrict__ gated) {
+    extern __shared__ __align__(16) float sm[];
+    float* s_alpha = sm;                                                  // P (padded to mult. of 4)
+    float4* s_part = reinterpret_cast<float4*>(sm + ((P + 3) & ~3));      // (WS_GROUPS-1) * WS_LANES float4
+    const int r = blockIdx.y;
+    const int img = img_index ? img_index[r] : r;
+    const int lane = threadIdx.x & (WS_LANES - 1), grp = threadIdx.x / WS_LANES;
+    const int c = blockIdx.x * (WS_LANES * 4) + lane * 4;
+    if (alpha) {
+        const float* al = alpha + (long long)r * ld_alpha;
+        for (int p = threadIdx.x; p < P; p += blockDim.x) s_alpha[p] = al[p];
+    } else {
+        for (int p = threadIdx.x; p < P; p += blockDim.x) s_alpha[p] = 1.f;
+    }
+    __syncthreads();
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) {
+        const float* base = enc + (long long)img * P * C + c;
+        int p = grp;
+        for (; p + (WS_UNROLL - 1) * WS_GROUPS < P; p += WS_UNROLL * WS_GROUPS) {
+            float4 x[WS_UNROLL];
+#pragma unroll
+            for (int u = 0; u < WS_UNROLL; ++u) x[u] = ld_stream_f4(base + (long long)(p + u * WS_GROUPS) * C);
+#pragma unroll
+            for (int u = 0; u < WS_UNROLL; ++u) {
+                const float a = s_alpha[p + u * WS_GROUPS];
+                acc.x = fmaf(a, x[u].x, acc.x); acc.y = fmaf(a, x[u].y, acc.y);
+                acc.z = fmaf(a, x[u].z, acc.z); acc.w = fmaf(a, x[u].w, acc.w);
+            }
+        }
+        for (; p < P; p += WS_GROUPS) {
+            const float4 x = ld_stream_f4(base + (long long)p * C);
+            const float a = s_alpha[p];
+            acc.x = fmaf(a, x.x, acc.x); acc.y = fmaf(a, x.y, acc.y);
+            acc.z = fmaf(a, x.z, acc.z); acc.w = fmaf(a, x.w, acc.w);
+        }
+    }
+    if (grp > 0) s_part[(grp - 1) * WS_LANES + lane] = acc;
+    __syncthreads();
+    if (grp == 0 && c < C) {
+#pragma unroll
+        for (int g = 0; g < WS_GROUPS - 1; ++g) {
+            const float4 o = s_part[g * WS_LANES + lane];
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        if (!alpha) { const float inv = (float)P; acc.x /= inv; acc.y /= inv; acc.z /= inv; acc.w /= inv; }
+        const long long o = (long long)r * C + c;
+        if (awe_raw) *reinterpret_cast<float4*>(awe_raw + o) = acc;
+        if (fbeta_pre) {
+            const float4 f = *reinterpret_cast<const float4*>(fbeta_pre + (long long)r * ld_fb + c);
+            const float4 g = make_float4(sigmoidf_(f.x), sigmoidf_(f.y), sigmoidf_(f.z), sigmoidf_(f.w));
+            if (gate) *reinterpret_cast<float4*>(gate + o) = g;
+            if (gated) *reinterpret_cast<float4*>(gated + o) =
+                    make_float4(g.x * acc.x, g.y * acc.y, g.z * acc.z, g.w * acc.w);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// step backward.  grid = rows, block = 256.  smem: C + 3*P + A + 40 floats + 2*... see launcher.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) att_step_bwd_kernel(
+        int P, int C, int A,
+        const float* __restrict__ enc, const float* __restrict__ att_enc,
+        const float* __restrict__ att_dec, long long ld_dec, const float* __restrict__ w_full,
+        const float* __restrict__ alpha, long long ld_alpha,
+        const float* __restrict__ d_alpha_ext, long long ld_dalpha,
+        const float* __restrict__ gate, const float* __restrict__ awe_raw, const float* __restrict__ d_gated,
+        float* __restrict__ d_att_dec, long long ld_ddec,
+        float* __restrict__ d_fbeta_pre, long long ld_dfb,
+        float* __restrict__ d_e, long long ld_de) {
+    extern __shared__ __align__(16) float sm[];
+    float* s_dawe = sm;                       // C
+    float* s_dec = s_dawe + C;                // A
+    float* s_alpha = s_dec + A;               // P
+    float* s_de = s_alpha + ((P + 3) & ~3);   // P   (d_alpha, then d_e)
+    float* s_red = s_de + ((P + 3) & ~3);     // 40
+    float* s_part = s_red + 40;               // A   (second pixel-group partial of d_att_dec)
+    const int r = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+
+    // (A) gate backward, elementwise over C
+    {
+        const long long o = (long long)r * C;
+        for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+            const float4 dg = *reinterpret_cast<const float4*>(d_gated + o + c);
+            const float4 g = *reinterpret_cast<const float4*>(gate + o + c);
+            const float4 aw = *reinterpret_cast<const float4*>(awe_raw + o + c);
+            const float4 da = make_float4(dg.x * g.x, dg.y * g.y, dg.z * g.z, dg.w * g.w);
+            *reinterpret_cast<float4*>(s_dawe + c) = da;
+            const float4 df = make_float4(dg.x * aw.x * g.x * (1.f - g.x), dg.y * aw.y * g.y * (1.f - g.y),
+                                          dg.z * aw.z * g.z * (1.f - g.z), dg.w * aw.w * g.w * (1.f - g.w));
+            *reinterpret_cast<float4*>(d_fbeta_pre + (long long)r * ld_dfb + c) = df;
+        }
+        const float* dec = att_dec + (long long)r * ld_dec;
+        for (int a = threadIdx.x; a < A; a += blockDim.x) s_dec[a] = dec[a];
+        const float* al = alpha + (long long)r * ld_alpha;
+        for (int p = threadIdx.x; p < P; p += blockDim.x) s_alpha[p] = al[p];
+    }
+    __syncthreads();
+
+    // (B) d_alpha[p] = <d_awe, enc[r,p,:]>   warp per pixel row, 8 x 128-bit loads in flight per lane
+    {
+        const float* eb = enc + (long long)r * P * C;
+        const int C4 = C >> 2;
+        for (int p = warp; p < P; p += nwarp) {
+            const float* row = eb + (long long)p * C;
+            float acc = 0.f;
+            int j = lane;
+            for (; j + 7 * 32 < C4; j += 8 * 32) {
+                float4 x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = ld_stream_f4(row + 4 * (j + u * 32));
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 d = *reinterpret_cast<const float4*>(s_dawe + 4 * (j + u * 32));
+                    acc = fmaf(x[u].x, d.x, acc); acc = fmaf(x[u].y, d.y, acc);
+                    acc = fmaf(x[u].z, d.z, acc); acc = fmaf(x[u].w, d.w, acc);
+                }
+            }
+            for (; j < C4; j += 32) {
+                const float4 x = ld_stream_f4(row + 4 * j);
+                const float4 d = *reinterpret_cast<const float4*>(s_dawe + 4 * j);
+                acc = fmaf(x.x, d.x, acc); acc = fmaf(x.y, d.y, acc);
+                acc = fmaf(x.z, d.z, acc); acc = fmaf(x.w, d.w, acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                if (d_alpha_ext) acc += d_alpha_ext[(long long)r * ld_dalpha + p];
+                s_de[p] = acc;
+            }
+        }
+    }
+    __syncthreads();
+
+    // (C) softmax backward, centred:  d_e = alpha * (d_alpha - sum_q alpha_q d_alpha_q)
+    {
+        float part = 0.f;
+        for (int p = threadIdx.x; p < P; p += blockDim.x) part = fmaf(s_alpha[p], s_de[p], part);
+        const float dot = block_sum(part, s_red);
+        float* out = d_e + (long long)r * ld_de;
+        for (int p = threadIdx.x; p < P; p += blockDim.x) {
+            const float v = s_alpha[p] * (s_de[p] - dot);
+            s_de[p] = v;
+            out[p] = v;
+        }
+    }
+    __syncthreads();
+
+    // (D) d_att_dec[a] = w_full[a] * sum_p d_e[p] * [att_enc[p,a] + att_dec[a] > 0]
+    {
+        const float* ab = att_enc + (long long)r * P * A;
+        const int A4 = A >> 2;
+        const int half = blockDim.x >> 1;                 // two pixel groups
+        const int grp = threadIdx.x / half, t = threadIdx.x % half;
+        for (int j0 = 0; j0 < A4; j0 += half) {
+            const int j = j0 + t;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < A4) {
+                const float4 d = *reinterpret_cast<const float4*>(s_dec + 4 * j);
+                int p = grp;
+                for (; p + 6 * 2 < P; p += 7 * 2) {
+                    float4 x[7];
+#pragma unroll
+                    for (int u = 0; u < 7; ++u) x[u] = ld_stream_f4(ab + (long long)(p + 2 * u) * A + 4 * j);
+#pragma unroll
+                    for (int u = 0; u < 7; ++u) {
+                        const float de = s_de[p + 2 * u];
+                        acc.x += (x[u].x + d.x > 0.f) ? de : 0.f;
+                        acc.y += (x[u].y + d.y > 0.f) ? de : 0.f;
+                        acc.z += (x[u].z + d.z > 0.f) ? de : 0.f;
+                        acc.w += (x[u].w + d.w > 0.f) ? de : 0.f;
+                    }
+                }
+                for (; p < P; p += 2) {
+                    const float4 x = ld_stream_f4(ab + (long long)p * A + 4 * j);
+                    const float de = s_de[p];
+                    acc.x += (x.x + d.x > 0.f) ? de : 0.f;
+                    acc.y += (x.y + d.y > 0.f) ? de : 0.f;
+                    acc.z += (x.z + d.z > 0.f) ? de : 0.f;
+                    acc.w += (x.w + d.w > 0.f) ? de : 0.f;
+                }
+            }
+            if (grp == 1 && j < A4) *reinterpret_cast<float4*>(s_part + 4 * j) = acc;
+            __syncthreads();
+            if (grp == 0 && j < A4) {
+                const float4 o = *reinterpret_cast<const float4*>(s_part + 4 * j);
+                const float4 w = *reinterpret_cast<const float4*>(w_full + 4 * j);
+                float4 res = make_float4((acc.x + o.x) * w.x, (acc.y + o.y) * w.y,
+                                         (acc.z + o.z) * w.z, (acc.w + o.w) * w.w);
+                *reinterpret_cast<float4*>(d_att_dec + (long long)r * ld_ddec + 4 * j) = res;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// After the loop: d_att_enc + full_att parameter gradients.
+// grid = (ceil(P/PB), B), block = A/4 threads (each 4 consecutive a).  smem: T*A (att_dec) + T*PB (d_e).
+// partial[(b*gridDim.x + chunk)*(A+4) + ...]: per-CTA d_w_full[A] and d_b_full.
+// ------------------------------------------------------------------------------------------------
+constexpr int PROJ_PB = 28;
+
+__global__ void att_proj_bwd_kernel(int B, int T, int P, int A, int len_b_unused,
+                                    const int* __restrict__ row_len,   // [B] number of active steps of row b
+                                    const float* __restrict__ att_enc, const float* __restrict__ att_dec_all,
+                                    long long ld_dec, const float* __restrict__ w_full,
+                                    const float* __restrict__ d_e, float* __restrict__ d_att_enc,
+                                    float* __restrict__ partial) {
+    extern __shared__ __align__(16) float sm[];
+    const int b = blockIdx.y, p0 = blockIdx.x * PROJ_PB;
+    const int np = min(PROJ_PB, P - p0);
+    const int Tb = row_len[b];
+    float* s_dec = sm;                  // Tb * A
+    float* s_de = sm + (size_t)T * A;   // Tb * PROJ_PB
+    float* s_red = s_de + (size_t)T * PROJ_PB;   // 40
+    for (int i = threadIdx.x; i < Tb * A; i += blockDim.x) {
+        const int t = i / A, a = i % A;
+        s_dec[i] = att_dec_all[((long long)t * B + b) * ld_dec + a];
+    }
+    float de_sum = 0.f;
+    for (int i = threadIdx.x; i < Tb * PROJ_PB; i += blockDim.x) {
+        const int t = i / PROJ_PB, pp = i % PROJ_PB;
+        const float v = (pp < np) ? d_e[((long long)b * T + t) * P + p0 + pp] : 0.f;
+        s_de[i] = v;
+        de_sum += v;
+    }
+    __syncthreads();
+    const int a = threadIdx.x * 4;
+    float4 wacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a < A) {
+        const float4 w = *reinterpret_cast<const float4*>(w_full + a);
+        for (int pp = 0; pp < np; ++pp) {
+            const long long o = ((long long)b * P + p0 + pp) * A + a;
+            const float4 x = *reinterpret_cast<const float4*>(att_enc + o);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int t = 0; t < Tb; ++t) {
+                const float de = s_de[t * PROJ_PB + pp];
+                const float4 d = *reinterpret_cast<const float4*>(s_dec + (size_t)t * A + a);
+                const float s0 = x.x + d.x, s1 = x.y + d.y, s2 = x.z + d.z, s3 = x.w + d.w;
+                acc.x += (s0 > 0.f) ? de : 0.f;  wacc.x = fmaf(de, fmaxf(s0, 0.f), wacc.x);
+                acc.y += (s1 > 0.f) ? de : 0.f;  wacc.y = fmaf(de, fmaxf(s1, 0.f), wacc.y);
+                acc.z += (s2 > 0.f) ? de : 0.f;  wacc.z = fmaf(de, fmaxf(s2, 0.f), wacc.z);
+                acc.w += (s3 > 0.f) ? de : 0.f;  wacc.w = fmaf(de, fmaxf(s3, 0.f), wacc.w);
+            }
+            *reinterpret_cast<float4*>(d_att_enc + o) =
+                    make_float4(acc.x * w.x, acc.y * w.y, acc.z * w.z, acc.w * w.w);
+        }
+    }
+    float* mine = partial + ((long long)b * gridDim.x + blockIdx.x) * (A + 4);
+    if (a < A) *reinterpret_cast<float4*>(mine + a) = wacc;
+    const float tot = block_sum(de_sum, s_red);
+    if (threadIdx.x == 0) { mine[A] = tot; mine[A + 1] = 0.f; mine[A + 2] = 0.f; mine[A + 3] = 0.f; }
+}
+
+__global__ void row_len_from_bt_kernel(int B, int T, const int* __restrict__ bt, int* __restrict__ row_len) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int n = 0;
+    for (int t = 0; t < T; ++t) n += (b < bt[t]) ? 1 : 0;    // bt is non-increasing, rows are a prefix
+    row_len[b] = n;
+}
+
+struct BtPack { int v[ICD_MAX_STEPS]; };
+__global__ void row_len_from_pack_kernel(int B, int T, const BtPack bt, int* __restrict__ row_len) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int n = 0;
+    for (int t = 0; t < T; ++t) n += (b < bt.v[t]) ? 1 : 0;
+    row_len[b] = n;
+}
+
+}  // namespace
+
+int icd_weighted_pixel_sum(int rows, int P, int C, const int32_t* img_index, const float* enc,
+                           const float* alpha, int64_t ld_alpha, const float* fbeta_pre, int64_t ld_fb,
+                           float* awe_raw, float* gate, float* gated, cudaStream_t s) {
+    if (rows == 0) return 0;
+    ICD_CHECK_ARG(C % 4 == 0, "attention: C=%d must be a multiple of 4", C);
+    ICD_CHECK_ARG(!fbeta_pre || ld_fb % 4 == 0, "attention: ld_fb must be a multiple of 4");
+    ICD_CHECK_ARG(rows <= 65535, "attention: rows=%d exceeds gridDim.y", rows);
+    dim3 grid((C + WS_LANES * 4 - 1) / (WS_LANES * 4), rows);
+    const size_t smem = (((P + 3) & ~3) + (WS_GROUPS - 1) * WS_LANES * 4) * sizeof(float);
+    weighted_pixel_sum_kernel<<<grid, 256, smem, s>>>(P, C, img_index, enc, alpha, ld_alpha, fbeta_pre, ld_fb,
+                                                      awe_raw, gate, gated);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int icd_attention_step_fwd(int rows, int P, int C, int A, const int32_t* img_index,
+                                      const float* enc, const float* att_enc,
+                                      const float* att_dec, int64_t ld_dec,
+                                      const float* w_full, const float* b_full,
+                                      const float* fbeta_pre, int64_t ld_fb,
+                                      float* alpha, int64_t ld_alpha,
+                                      float* awe_raw, float* gate, float* gated, void* stream) {
+    cudaStream_t s = icd_stream(stream);
+    if (rows == 0) return 0;
+    ICD_CHECK_ARG(rows > 0 && P > 0 && C > 0 && A > 0, "attention_step_fwd: bad dims");
+    ICD_CHECK_ARG(A % 4 == 0 && C % 4 == 0, "attention_step_fwd: A=%d and C=%d must be multiples of 4", A, C);
+    ICD_CHECK_ARG(ld_dec % 4 == 0, "attention_step_fwd: ld_dec must be a multiple of 4");
+    const size_t smem = (2 * (size_t)A + P + 40) * sizeof(float);
+    ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_fwd: A/P too large for shared memory");
+    if (smem > 48 * 1024)
+        ICD_CUDA(cudaFuncSetAttribute(att_scores_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    att_scores_softmax_kernel<<<rows, 256, smem, s>>>(P, A, img_index, att_enc, att_dec, ld_dec, w_full, b_full,
+                                                       alpha, ld_alpha);
+    ICD_LAUNCH_CHECK();
+    return icd_weighted_pixel_sum(rows, P, C, img_index, enc, alpha, ld_alpha, fbeta_pre, ld_fb,
+                                  awe_raw, gate, gated, s);
+}
+
+extern "C" int icd_attention_step_bwd(int rows, int P, int C, int A,
+                                      const float* enc, const float* att_enc,
+                                      const float* att_dec, int64_t ld_dec, const float* w_full,
+                                      const float* alpha, int64_t ld_alpha,
+                                      const float* d_alpha_ext, int64_t ld_dalpha,
+                                      const float* gate, const float* awe_raw, const float* d_gated,
+                                      float* d_att_dec, int64_t ld_ddec,
+                                      float* d_fbeta_pre, int64_t ld_dfb,
+                                      float* d_e, int64_t ld_de, void* stream) {
+    cudaStream_t s = icd_stream(stream);
+    if (rows == 0) return 0;
+    ICD_CHECK_ARG(A % 4 == 0 && C % 4 == 0, "attention_step_bwd: A and C must be multiples of 4");
+    ICD_CHECK_ARG(ld_dec % 4 == 0 && ld_ddec % 4 == 0 && ld_dfb % 4 == 0, "attention_step_bwd: row strides must be multiples of 4");
+    const size_t smem = ((size_t)C + 2 * (size_t)A + 2 * ((P + 3) & ~3) + 40) * sizeof(float);
+    ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_bwd: dims too large for shared memory");
+    if (smem > 48 * 1024)
+        ICD_CUDA(cudaFuncSetAttribute(att_step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    att_step_bwd_kernel<<<rows, 256, smem, s>>>(P, C, A, enc, att_enc, att_dec, ld_dec, w_full, alpha, ld_alpha,
+                                                 d_alpha_ext, ld_dalpha, gate, awe_raw, d_gated,
+                                                 d_att_dec, ld_ddec, d_fbeta_pre, ld_dfb, d_e, ld_de);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int64_t icd_attention_proj_bwd_ws_floats(int B, int P, int A) {
+    const int64_t chunks = (P + PROJ_PB - 1) / PROJ_PB;
+    // per-CTA partials + [B] int row lengths (stored as 4-byte words at the end)
+    return (int64_t)B * chunks * (A + 4) + B + 8;
+}
+
+extern "C" int icd_attention_proj_bwd(int B, int T, int P, int A, const int32_t* bt_host,
+                                      const float* att_enc, const float* att_dec_all, int64_t ld_dec,
+                                      const float* w_full, const float* d_e,
+                                      float* d_att_enc, float* d_w_full, float* d_b_full,
+                                      float* partial, void* stream) {
+    cudaStream_t s = icd_stream(stream);
+    ICD_CHECK_ARG(T > 0 && T <= ICD_MAX_STEPS, "attention_proj_bwd: T=%d out of range", T);
+    ICD_CHECK_ARG(A % 4 == 0 && A / 4 <= 1024, "attention_proj_bwd: A=%d unsupported", A);
+    ICD_CHECK_ARG(B <= 65535, "attention_proj_bwd: B too large");
+    const int chunks = (P + PROJ_PB - 1) / PROJ_PB;
+    int* row_len = reinterpret_cast<int*>(partial + (int64_t)B * chunks * (A + 4));
+    BtPack pack;
+    for (int t = 0; t < ICD_MAX_STEPS; ++t) pack.v[t] = t < T ? bt_host[t] : 0;
+    row_len_from_pack_kernel<<<(B + 127) / 128, 128, 0, s>>>(B, T, pack, row_len);
+    ICD_LAUNCH_CHECK();
+    const size_t smem = ((size_t)T * A + (size_t)T * PROJ_PB + 40) * sizeof(float);
+    ICD_CHECK_ARG(smem <= 220 * 1024, "attention_proj_bwd: T*A too large for shared memory");
+    if (smem > 48 * 1024)
+        ICD_CUDA(cudaFuncSetAttribute(att_proj_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int threads = ((A / 4 + 31) / 32) * 32;
+    dim3 grid(chunks, B);
+    att_proj_bwd_kernel<<<grid, threads, smem, s>>>(B, T, P, A, 0, row_len, att_enc, att_dec_all, ld_dec, w_full,
+                                                     d_e, d_att_enc, partial);
+    ICD_LAUNCH_CHECK();
+    // reduce the per-CTA partials: columns [0,A) -> d_w_full, column A -> d_b_full
+    ICD_TRY(icd_colsum(partial, A + 4, (int64_t)B * chunks, A, nullptr, d_w_full, s));
+    ICD_TRY(icd_colsum(partial + A, A + 4, (int64_t)B * chunks, 1, nullptr, d_b_full, s));
+    return 0;
+}

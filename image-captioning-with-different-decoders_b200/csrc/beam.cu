@@ -1,0 +1,297 @@
+// Batched, device-side beam search (gen_captions.py:16-131; state machine of SURVEY.md Appendix C).
+//
+// n_img independent images x k beam slots are decoded together: every step is one round of
+//   embedding gather -> [W_dec;W_fbeta;W_hh] contraction -> fused attention step (features indexed per image,
+//   never gathered/copied as at gen_captions.py:111, enc_att computed once per image instead of per beam per
+//   step) -> LSTMCell -> fc -> per-image warp/block top-k over the (live beams x V) candidates -> beam reorder.
+// No host synchronisation inside the loop; sequences and alpha frames are reconstructed at the end by
+// back-tracking parent pointers, so no per-step copy of the growing (k, step, 14, 14) alpha tensor (:89).
+//
+// Reference semantics kept: step 1 candidates come from beam 0 only (:78-79); later steps take the top
+// k_live (= remaining beams) of the flattened (k_live * V) scores, sorted descending (:82); scores are raw
+// summed log-probs (:74-76); beams that emit <end> leave the beam and are never replaced (:93-104); the winner is
+// the first completed beam with the maximal score (:127); the loop body runs for step = 1..max_steps+1 (:119).
+#include "common.cuh"
+
+namespace {
+
+constexpr int KMAX = 8;          // beam slots per image supported by the top-k kernel
+
+struct BeamWs {
+    float *att_enc, *mean, *h0, *c0, *h, *c, *h_tmp, *c_tmp, *w_cat, *b_cat, *emb_x, *z, *gated, *gates_pre,
+          *gates_act_unused, *logits, *alpha_steps, *score, *best_score;
+    int *img_index, *prev_word, *k_live, *src, *parent, *word, *best_step, *best_parent;
+    long long* tok64;
+};
+
+size_t carve(const icd_beam_desc_t* d, BeamWs* w, char* base) {
+    const size_t R = (size_t)d->n_img * d->k, S = (size_t)d->max_steps + 1;
+    const int P = d->P, C = d->C, A = d->A, D = d->D, E = d->E, V = d->V, NZ = A + C + 4 * D;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return base ? base + o : (char*)nullptr; };
+    float* f;
+#define TAKE_F(name, n) f = (float*)take(sizeof(float) * (n)); if (w) w->name = f;
+    TAKE_F(att_enc, (size_t)d->n_img * P * A)
+    TAKE_F(mean, (size_t)d->n_img * C)
+    TAKE_F(h0, (size_t)d->n_img * D)
+    TAKE_F(c0, (size_t)d->n_img * D)
+    TAKE_F(h, R * D) TAKE_F(c, R * D) TAKE_F(h_tmp, R * D) TAKE_F(c_tmp, R * D)
+    TAKE_F(w_cat, (size_t)NZ * D) TAKE_F(b_cat, (size_t)NZ)
+    TAKE_F(emb_x, R * E) TAKE_F(z, R * NZ) TAKE_F(gated, R * C) TAKE_F(gates_pre, R * 4 * D)
+    TAKE_F(logits, R * V)
+    TAKE_F(alpha_steps, S * R * P)
+    TAKE_F(score, R) TAKE_F(best_score, (size_t)d->n_img)
+#undef TAKE_F
+    int* ip;
+#define TAKE_I(name, n) ip = (int*)take(sizeof(int) * (n)); if (w) w->name = ip;
+    TAKE_I(img_index, R) TAKE_I(prev_word, R) TAKE_I(k_live, (size_t)d->n_img) TAKE_I(src, R)
+    TAKE_I(parent, S * R) TAKE_I(word, S * R) TAKE_I(best_step, (size_t)d->n_img) TAKE_I(best_parent, (size_t)d->n_img)
+#undef TAKE_I
+    long long* lp = (long long*)take(sizeof(long long) * R); if (w) w->tok64 = lp;
+    return off;
+}
+
+__global__ void beam_init_kernel(int n_img, int k, int D, int start_id, const float* __restrict__ h0,
+                                 const float* __restrict__ c0, float* __restrict__ h, float* __restrict__ c,
+                                 int* __restrict__ img_index, int* __restrict__ prev_word, long long* __restrict__ tok64,
+                                 float* __restrict__ score, int* __restrict__ k_live, float* __restrict__ best_score,
+                                 int* __restrict__ best_step, int* __restrict__ best_parent) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long R = (long long)n_img * k;
+    if (i < R * D) {
+        const long long r = i / D; const int dd = (int)(i % D);
+        const long long img = r / k;
+        h[i] = h0[img * D + dd];
+        c[i] = c0[img * D + dd];
+    }
+    if (i < R) { img_index[i] = (int)(i / k); prev_word[i] = start_id; tok64[i] = start_id; score[i] = 0.f; }   // :47-52
+    if (i < n_img) { k_live[i] = k; best_score[i] = -INFINITY; best_step[i] = 0; best_parent[i] = 0; }
+}
+
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
+    return v > bv || (v == bv && i < bi);
+}
+
+// One CTA per image.  log_softmax over V for each live row, add the running score, top-k_live over the
+// flattened candidates (ties: lower flat index first), then the beam bookkeeping of gen_captions.py:85-116.
+__global__ void __launch_bounds__(256) beam_topk_kernel(
+        int k, int V, int step, int end_id, const float* __restrict__ logits,
+        float* __restrict__ score, int* __restrict__ prev_word, long long* __restrict__ tok64,
+        int* __restrict__ k_live, int* __restrict__ src,
+        int* __restrict__ parent_s, int* __restrict__ word_s, int* __restrict__ trace_s,
+        float* __restrict__ best_score, int* __restrict__ best_step, int* __restrict__ best_parent) {
+    __shared__ float s_red[40];
+    __shared__ float s_off[KMAX];            // per-row additive constant: score_i - max_i - log(sum_i)
+    __shared__ float s_max[KMAX], s_lsum[KMAX], s_score[KMAX];
+    __shared__ float s_cv[256 * KMAX];
+    __shared__ int s_ci[256 * KMAX];
+    __shared__ float s_topv[KMAX];
+    __shared__ int s_topi[KMAX];
+    const int img = blockIdx.x;
+    const int kl = k_live[img];
+    if (trace_s) for (int j = threadIdx.x; j < k; j += blockDim.x) trace_s[img * k + j] = -1;
+    if (kl == 0) return;
+    const int nrows = (step == 1) ? 1 : kl;                                                  // :78-82
+    const float* lg = logits + (long long)img * k * V;
+    for (int i = 0; i < nrows; ++i) {                                                        // :74 log_softmax
+        const float* x = lg + (long long)i * V;
+        float m = -INFINITY;
+        for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, x[v]);
+        m = block_max(m, s_red);
+        float sum = 0.f;
+        for (int v = threadIdx.x; v < V; v += blockDim.x) sum += expf(x[v] - m);
+        sum = block_sum(sum, s_red);
+        if (threadIdx.x == 0) { s_max[i] = m; s_lsum[i] = logf(sum); s_score[i] = score[img * k + i]; }
+    }
+    __syncthreads();
+    // thread-local top-kl over a strided slice of the flattened (nrows*V) candidates
+    float tv[KMAX]; int ti[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
+    const int total = nrows * V;
+    for (int f = threadIdx.x; f < total; f += blockDim.x) {
+        const int i = f / V;
+        const float lp = (lg[f] - s_max[i]) - s_lsum[i];            // log_softmax value
+        const float v = s_score[i] + lp;                            // :76
+        if (better(v, f, tv[KMAX - 1], ti[KMAX - 1])) {
+            tv[KMAX - 1] = v; ti[KMAX - 1] = f;
+#pragma unroll
+            for (int j = KMAX - 1; j > 0; --j) {
+                if (better(tv[j], ti[j], tv[j - 1], ti[j - 1])) {
+                    const float a = tv[j]; tv[j] = tv[j - 1]; tv[j - 1] = a;
+                    const int b = ti[j]; ti[j] = ti[j - 1]; ti[j - 1] = b;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) { s_cv[threadIdx.x * KMAX + j] = tv[j]; s_ci[threadIdx.x * KMAX + j] = ti[j]; }
+    __syncthreads();
+    if (threadIdx.x < 32) {                                          // warp 0: kl rounds of arg-best
+        const int lane = threadIdx.x;
+        for (int round = 0; round < kl; ++round) {
+            float bv = -INFINITY; int bi = 0x7fffffff, bpos = -1;
+            for (int q = lane; q < 256 * KMAX; q += 32)
+                if (better(s_cv[q], s_ci[q], bv, bi)) { bv = s_cv[q]; bi = s_ci[q]; bpos = q; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+                if (better(ov, oi, bv, bi)) { bv = ov; bi = oi; bpos = op; }
+            }
+            if (lane == 0) { s_topv[round] = bv; s_topi[round] = bi; if (bpos >= 0) { s_cv[bpos] = -INFINITY; s_ci[bpos] = 0x7fffffff; } }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nlive = 0;
+        float bs = best_score[img];
+        for (int j = 0; j < kl; ++j) {
+            const int idx = s_topi[j];
+            const float val = s_topv[j];
+            const int prev = idx / V, next = idx % V;                                        // :85-86
+            if (trace_s) trace_s[img * k + j] = next;                                        // :91
+            if (next == end_id) {                                                            // :93-103
+                if (val > bs) { bs = val; best_score[img] = val; best_step[img] = step; best_parent[img] = prev; }
+            } else {                                                                         // :109-116
+                const int r = img * k + nlive;
+                src[r] = prev; parent_s[r] = prev; word_s[r] = next;
+                prev_word[r] = next; tok64[r] = next; score[r] = val;
+                ++nlive;
+            }
+        }
+        k_live[img] = nlive;                                                                 // :104
+    }
+}
+
+__global__ void beam_reorder_kernel(int k, int D, const int* __restrict__ k_live, const int* __restrict__ src,
+                                    const float* __restrict__ h_tmp, const float* __restrict__ c_tmp,
+                                    float* __restrict__ h, float* __restrict__ c) {
+    const int r = blockIdx.x;                       // destination row
+    const int img = r / k, j = r % k;
+    if (j >= k_live[img]) return;
+    const long long so = ((long long)img * k + src[r]) * D, dst = (long long)r * D;
+    for (int dd = threadIdx.x; dd < D; dd += blockDim.x) { h[dst + dd] = h_tmp[so + dd]; c[dst + dd] = c_tmp[so + dd]; }
+}
+
+// Back-track the winner of each image.
+__global__ void beam_finalize_kernel(int k, int P, int S1 /* max_steps+1 */, long long R, int start_id, int end_id,
+                                     const float* __restrict__ best_score, const int* __restrict__ best_step,
+                                     const int* __restrict__ best_parent, const int* __restrict__ parent,
+                                     const int* __restrict__ word, const float* __restrict__ alpha_steps,
+                                     int* __restrict__ out_len, int* __restrict__ out_seq, float* __restrict__ out_score,
+                                     float* __restrict__ out_alpha) {
+    const int img = blockIdx.x;
+    const int S = best_step[img];
+    const int W = S1 + 1;                           // out_seq row width = max_steps + 2
+    __shared__ int s_slot[ICD_MAX_STEPS + 2];       // s_slot[s] = row (within image) whose alpha is frame s
+    if (threadIdx.x == 0) {
+        out_score[img] = best_score[img];
+        if (S == 0) { out_len[img] = 0; }
+        else {
+            out_len[img] = S + 1;
+            int* seq = out_seq + (long long)img * W;
+            seq[0] = start_id; seq[S] = end_id;
+            int cur = best_parent[img];             // slot (step S-1 numbering) the winner extended
+            s_slot[S] = cur;
+            for (int s = S - 1; s >= 1; --s) {
+                const long long o = (long long)(s - 1) * R + (long long)img * k + cur;
+                seq[s] = word[o];
+                cur = parent[o];
+                s_slot[s] = cur;
+            }
+        }
+    }
+    __syncthreads();
+    if (S == 0 || !out_alpha) return;
+    float* oa = out_alpha + (long long)img * W * P;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) oa[p] = 1.f;                           // :54 frame of ones
+    for (int s = 1; s <= S; ++s) {
+        const float* a = alpha_steps + ((long long)(s - 1) * R + (long long)img * k + s_slot[s]) * P;
+        for (int p = threadIdx.x; p < P; p += blockDim.x) oa[(long long)s * P + p] = a[p];
+    }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ table_f32, const double* __restrict__ table_f64,
+                                   const long long* __restrict__ tok, int E, float* __restrict__ out) {
+    const long long r = blockIdx.x;
+    const long long t = tok[r];
+    for (int e = threadIdx.x; e < E; e += blockDim.x)
+        out[r * E + e] = table_f64 ? (float)table_f64[t * E + e] : table_f32[t * E + e];
+}
+
+}  // namespace
+
+extern "C" int64_t icd_beam_search_ws_bytes(const icd_beam_desc_t* d) {
+    if (!d) return -1;
+    return (int64_t)carve(d, nullptr, nullptr);
+}
+
+extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
+    ICD_CHECK_ARG(d != nullptr, "beam_search: null descriptor");
+    ICD_CHECK_ARG(d->n_img > 0 && d->k >= 1 && d->k <= KMAX, "beam_search: n_img=%d k=%d (k <= %d)", d->n_img, d->k, KMAX);
+    ICD_CHECK_ARG(d->max_steps >= 1 && d->max_steps + 1 <= ICD_MAX_STEPS, "beam_search: max_steps=%d out of range", d->max_steps);
+    ICD_CHECK_ARG(d->V >= d->k, "beam_search: vocabulary smaller than the beam");
+    ICD_CHECK_ARG(d->A % 4 == 0 && d->C % 4 == 0 && d->D % 4 == 0 && d->E % 4 == 0, "beam_search: dims must be multiples of 4");
+    ICD_CHECK_ARG(d->ws && d->ws_bytes >= icd_beam_search_ws_bytes(d), "beam_search: workspace too small");
+    cudaStream_t s = icd_stream(stream);
+    BeamWs w;
+    carve(d, &w, (char*)d->ws);
+    const int n_img = d->n_img, k = d->k, P = d->P, C = d->C, A = d->A, D = d->D, E = d->E, V = d->V;
+    const int NZ = A + C + 4 * D, prec = d->precision;
+    const long long R = (long long)n_img * k;
+    ICD_CHECK_ARG(R <= 65535, "beam_search: n_img*k=%lld exceeds 65535 rows per call (chunk the images)", R);
+    const int S1 = d->max_steps + 1;
+
+    ICD_CUDA(cudaMemcpyAsync(w.w_cat, d->dec_att_w, sizeof(float) * (size_t)A * D, cudaMemcpyDeviceToDevice, s));
+    ICD_CUDA(cudaMemcpyAsync(w.w_cat + (size_t)A * D, d->f_beta_w, sizeof(float) * (size_t)C * D, cudaMemcpyDeviceToDevice, s));
+    ICD_CUDA(cudaMemcpyAsync(w.w_cat + (size_t)(A + C) * D, d->w_hh, sizeof(float) * (size_t)4 * D * D, cudaMemcpyDeviceToDevice, s));
+    ICD_CUDA(cudaMemcpyAsync(w.b_cat, d->dec_att_b, sizeof(float) * A, cudaMemcpyDeviceToDevice, s));
+    ICD_CUDA(cudaMemcpyAsync(w.b_cat + A, d->f_beta_b, sizeof(float) * C, cudaMemcpyDeviceToDevice, s));
+    ICD_CUDA(cudaMemcpyAsync(w.b_cat + A + C, d->b_hh, sizeof(float) * 4 * D, cudaMemcpyDeviceToDevice, s));
+
+    // once per image: enc_att projection and the initial state (:62)
+    ICD_TRY(icd_gemm_simple(prec, d->enc, C, 1, d->enc_att_w, C, 1, w.att_enc, A, n_img * P, A, C, d->enc_att_b, nullptr,
+                            nullptr, 0, nullptr, 0, nullptr, 0.f, s));
+    ICD_TRY(icd_init_hidden_state(n_img, P, C, D, prec, d->enc, d->h_lin_w, d->h_lin_b, d->c_lin_w, d->c_lin_b,
+                                  w.mean, w.h0, w.c0, stream));
+    {
+        const long long n = R * D;
+        beam_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n_img, k, D, d->start_id, w.h0, w.c0, w.h, w.c,
+                                                                      w.img_index, w.prev_word, w.tok64, w.score, w.k_live,
+                                                                      w.best_score, w.best_step, w.best_parent);
+        ICD_LAUNCH_CHECK();
+    }
+    for (int step = 1; step <= S1; ++step) {
+        float* alpha_s = w.alpha_steps + (size_t)(step - 1) * R * P;
+        gather_rows_kernel<<<(unsigned)R, 128, 0, s>>>(d->emb_is_f64 ? nullptr : (const float*)d->emb_w,
+                                                       d->emb_is_f64 ? (const double*)d->emb_w : nullptr,
+                                                       w.tok64, E, w.emb_x);                 // :65
+        ICD_LAUNCH_CHECK();
+        ICD_TRY(icd_gemm_simple(prec, w.h, D, 1, w.w_cat, D, 1, w.z, NZ, (int)R, NZ, D, w.b_cat, nullptr,
+                                nullptr, 0, nullptr, 0, nullptr, 0.f, s));
+        ICD_TRY(icd_attention_step_fwd((int)R, P, C, A, w.img_index, d->enc, w.att_enc, w.z, NZ, d->full_att_w,
+                                       d->full_att_b, w.z + A, NZ, alpha_s, P, nullptr, nullptr, w.gated, stream));  // :66-69
+        ICD_TRY(icd_gemm_simple(prec, w.emb_x, E, 1, d->w_ih, E + C, 1, w.gates_pre, 4 * D, (int)R, 4 * D, E,
+                                d->b_ih, nullptr, w.z + A + C, NZ, nullptr, 0, nullptr, 0.f, s));
+        ICD_TRY(icd_gemm_simple(prec, w.gated, C, 1, d->w_ih + E, E + C, 1, w.gates_pre, 4 * D, (int)R, 4 * D, C,
+                                nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 1.f, s)); // :70-71
+        ICD_TRY(icd_lstm_pointwise_fwd((int)R, D, w.gates_pre, w.c, nullptr, w.c_tmp, w.h_tmp, nullptr, 0, nullptr, 1.f, s));
+        ICD_TRY(icd_gemm_simple(prec, w.h_tmp, D, 1, d->fc_w, D, 1, w.logits, V, (int)R, V, D, d->fc_b, nullptr,
+                                nullptr, 0, nullptr, 0, nullptr, 0.f, s));                   // :72 (no dropout)
+        beam_topk_kernel<<<n_img, 256, 0, s>>>(k, V, step, d->end_id, w.logits, w.score, w.prev_word, w.tok64, w.k_live,
+                                               w.src, w.parent + (size_t)(step - 1) * R, w.word + (size_t)(step - 1) * R,
+                                               d->trace_words ? d->trace_words + (size_t)(step - 1) * R : nullptr,
+                                               w.best_score, w.best_step, w.best_parent);
+        ICD_LAUNCH_CHECK();
+        beam_reorder_kernel<<<(unsigned)R, 128, 0, s>>>(k, D, w.k_live, w.src, w.h_tmp, w.c_tmp, w.h, w.c);
+        ICD_LAUNCH_CHECK();
+    }
+    beam_finalize_kernel<<<n_img, 128, 0, s>>>(k, P, S1, R, d->start_id, d->end_id, w.best_score, w.best_step,
+                                               w.best_parent, w.parent, w.word, w.alpha_steps, d->out_len, d->out_seq,
+                                               d->out_score, d->out_alpha);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}

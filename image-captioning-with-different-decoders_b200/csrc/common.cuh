@@ -1,0 +1,95 @@
+// Shared helpers for libicd_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/icd_b200.h"
+
+#ifndef ICD_NUM_SMS
+#define ICD_NUM_SMS 148          // B200: 2 dies x 74 SMs
+#endif
+
+void icd_set_error(const char* fmt, ...);
+
+#define ICD_CHECK_ARG(cond, ...)                         \
+    do { if (!(cond)) { icd_set_error(__VA_ARGS__); return -1; } } while (0)
+
+#define ICD_CUDA(call)                                                                 \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                             \
+        icd_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+        return (int)e_; } } while (0)
+
+#define ICD_LAUNCH_CHECK()  ICD_CUDA(cudaGetLastError())
+
+#define ICD_TRY(call) do { int r_ = (call); if (r_ != 0) return r_; } while (0)
+
+static inline cudaStream_t icd_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+    // streaming 128-bit load: read-only path, do not allocate in L1 (each byte is used once per CTA)
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// block-wide reductions for blockDim.x <= 1024 (multiple of 32); scratch: >= 33 floats of smem.
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();                 // protect scratch reuse
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    float r = (threadIdx.x < nw) ? scratch[threadIdx.x] : 0.f;
+    if (w == 0) { r = warp_sum(r); if (lane == 0) scratch[32] = r; }
+    __syncthreads();
+    return scratch[32];
+}
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    float r = (threadIdx.x < nw) ? scratch[threadIdx.x] : -INFINITY;
+    if (w == 0) { r = warp_max(r); if (lane == 0) scratch[32] = r; }
+    __syncthreads();
+    return scratch[32];
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---- internal (non-exported) launchers shared between translation units -----------------------
+int icd_colsum(const float* X, int64_t ld, int64_t M, int N, const uint8_t* row_mask, float* out, cudaStream_t s);
+int icd_embed_gather(const void* table, int is_f64, const int64_t* captions, int B, int L, int T, int E,
+                     float* out /* (T,B,E) */, cudaStream_t s);
+int icd_embed_scatter_add(void* d_table, int is_f64, const int64_t* captions, int B, int L, int T, int E,
+                          const int32_t* bt_host, const float* d_x /* (T,B,E) */, cudaStream_t s);
+int icd_lstm_pointwise_fwd(int rows, int D, const float* gates_pre, const float* c_prev,
+                           float* gates_act, float* c_new, float* h_new,
+                           float* hdrop, int64_t hdrop_row_stride, const uint8_t* mask, float scale,
+                           cudaStream_t s);
+int icd_lstm_pointwise_bwd(int rows, int D, const float* dh_in, const float* d_hdrop, int64_t hdrop_row_stride,
+                           const uint8_t* mask, float scale, float* dc_inout,
+                           const float* gates_act, const float* c_prev, const float* c_new,
+                           float* dgates_pre, int64_t ld_dg, cudaStream_t s);
+int icd_weighted_pixel_sum(int rows, int P, int C, const int32_t* img_index, const float* enc,
+                           const float* alpha, int64_t ld_alpha, const float* fbeta_pre, int64_t ld_fb,
+                           float* awe_raw, float* gate, float* gated, cudaStream_t s);
+int icd_gemm_simple(int prec, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
+                    float* C, int64_t ldc, int M, int N, int K, const float* bias1, const float* bias2,
+                    const float* add1, int64_t ld1, const float* add2, int64_t ld2, const uint8_t* row_mask,
+                    float beta, cudaStream_t s);

@@ -1,0 +1,277 @@
+// Small fused pointwise / reduction kernels around the contractions:
+//   LSTMCell gate math fwd/bwd (torch.nn.LSTMCell semantics, gate order i,f,g,o — models/attention.py:277-278,
+//   models/baseline.py:106) with the nn.Dropout keep-mask of models/attention.py:279 fused into the h store,
+//   masked column sums (bias gradients), embedding gather / scatter-add (models/attention.py:247),
+//   Philox keep-mask generation, clamp+Adam (train_utils.py:2-12, models/attention.py:423-428),
+//   row-wise cross-entropy forward+backward (models/attention.py:411).
+#include "common.cuh"
+
+namespace {
+
+__global__ void lstm_pointwise_fwd_kernel(int rows, int D, const float* __restrict__ gates_pre,
+                                          const float* __restrict__ c_prev, float* __restrict__ gates_act,
+                                          float* __restrict__ c_new, float* __restrict__ h_new,
+                                          float* __restrict__ hdrop, long long hdrop_row_stride,
+                                          const unsigned char* __restrict__ mask, float scale) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)rows * D) return;
+    const int r = (int)(idx / D), d = (int)(idx % D);
+    const float* g = gates_pre + (long long)r * 4 * D;
+    const float i = sigmoidf_(g[d]);
+    const float f = sigmoidf_(g[D + d]);
+    const float gg = tanhf(g[2 * D + d]);
+    const float o = sigmoidf_(g[3 * D + d]);
+    const float c = f * c_prev[idx] + i * gg;
+    const float h = o * tanhf(c);
+    if (gates_act) {
+        float* ga = gates_act + (long long)r * 4 * D;
+        ga[d] = i; ga[D + d] = f; ga[2 * D + d] = gg; ga[3 * D + d] = o;
+    }
+    c_new[idx] = c;
+    h_new[idx] = h;
+    if (hdrop) {
+        float hd = h;
+        if (mask) hd = mask[idx] ? h * scale : 0.f;
+        hdrop[(long long)r * hdrop_row_stride + d] = hd;
+    }
+}
+
+__global__ void lstm_pointwise_bwd_kernel(int rows, int D, const float* __restrict__ dh_in,
+                                          const float* __restrict__ d_hdrop, long long hdrop_row_stride,
+                                          const unsigned char* __restrict__ mask, float scale,
+                                          float* __restrict__ dc_inout, const float* __restrict__ gates_act,
+                                          const float* __restrict__ c_prev, const float* __restrict__ c_new,
+                                          float* __restrict__ dgates_pre, long long ld_dg) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)rows * D) return;
+    const int r = (int)(idx / D), d = (int)(idx % D);
+    const float* ga = gates_act + (long long)r * 4 * D;
+    const float i = ga[d], f = ga[D + d], g = ga[2 * D + d], o = ga[3 * D + d];
+    float dh = dh_in ? dh_in[idx] : 0.f;
+    if (d_hdrop) {
+        float u = d_hdrop[(long long)r * hdrop_row_stride + d];
+        if (mask) u = mask[idx] ? u * scale : 0.f;
+        dh += u;
+    }
+    const float tc = tanhf(c_new[idx]);
+    const float d_o = dh * tc;
+    const float dc = dc_inout[idx] + dh * o * (1.f - tc * tc);
+    const float d_i = dc * g, d_g = dc * i, d_f = dc * c_prev[idx];
+    dc_inout[idx] = dc * f;
+    float* dg = dgates_pre + (long long)r * ld_dg;
+    dg[d] = d_i * i * (1.f - i);
+    dg[D + d] = d_f * f * (1.f - f);
+    dg[2 * D + d] = d_g * (1.f - g * g);
+    dg[3 * D + d] = d_o * o * (1.f - o);
+}
+
+// out[n] = sum_m mask[m] * X[m*ld + n].  block (32,32): x -> column, y -> row phase.  deterministic.
+__global__ void colsum_kernel(const float* __restrict__ X, long long ld, long long M, int N,
+                              const unsigned char* __restrict__ row_mask, float* __restrict__ out) {
+    __shared__ float s[32][33];
+    const int n = blockIdx.x * 32 + threadIdx.x;
+    float acc = 0.f;
+    if (n < N) {
+        for (long long m = threadIdx.y; m < M; m += 32)
+            if (!row_mask || row_mask[m]) acc += X[m * ld + n];
+    }
+    s[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int y = 0; y < 32; ++y) t += s[y][threadIdx.x];
+        out[n] = t;
+    }
+}
+
+template <typename TT>
+__global__ void embed_gather_kernel(const TT* __restrict__ table, const long long* __restrict__ captions,
+                                    int B, int L, int T, int E, float* __restrict__ out) {
+    const int row = blockIdx.x;                  // row = t*B + b
+    const int t = row / B, b = row % B;
+    const long long tok = captions[(long long)b * L + t];
+    const TT* src = table + tok * E;
+    float* dst = out + (long long)row * E;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = (float)src[e];
+}
+
+struct BtPack { int v[ICD_MAX_STEPS]; };
+
+template <typename TT>
+__global__ void embed_scatter_add_kernel(TT* __restrict__ d_table, const long long* __restrict__ captions,
+                                         int B, int L, int T, int E, const BtPack bt,
+                                         const float* __restrict__ d_x) {
+    const int row = blockIdx.x;
+    const int t = row / B, b = row % B;
+    if (b >= bt.v[t]) return;
+    const long long tok = captions[(long long)b * L + t];
+    TT* dst = d_table + tok * E;
+    const float* src = d_x + (long long)row * E;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) atomicAdd(dst + e, (TT)src[e]);
+}
+
+// Philox4x32-10 counter-based generator (Salmon et al. 2011).
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+__global__ void dropout_mask_kernel(unsigned char* __restrict__ out, long long n, float p,
+                                    unsigned long long seed, unsigned long long offset) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread -> 4 outputs
+    if (q * 4 >= n) return;
+    const unsigned long long ctr = offset + (unsigned long long)q;
+    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const long long i = q * 4 + j;
+        if (i < n) {
+            const float u = (float)(c[j] >> 8) * (1.0f / 16777216.0f);   // [0,1)
+            out[i] = (u >= p) ? 1 : 0;
+        }
+    }
+}
+
+__global__ void clip_adam_kernel(float* __restrict__ param, const float* __restrict__ grad,
+                                 float* __restrict__ m, float* __restrict__ v, long long n,
+                                 float grad_scale, float clip, float lr, float b1, float b2, float eps,
+                                 float bias_c1, float bias_c2_sqrt) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        float g = grad[i] * grad_scale;
+        g = fminf(fmaxf(g, -clip), clip);                         // train_utils.py:12 clamp_(-c, c)
+        const float mi = b1 * m[i] + (1.f - b1) * g;              // torch.optim.Adam (single-tensor form)
+        const float vi = b2 * v[i] + (1.f - b2) * g * g;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / bias_c2_sqrt + eps;
+        param[i] -= (lr / bias_c1) * (mi / denom);
+    }
+}
+
+// Row-wise softmax cross-entropy forward + backward in one pass over the logits row held in smem/regs.
+// grid = R rows, block = 256.  row_loss[r] = lse - logit[target] (0 for ignored rows);
+// d_logits[r,:] = (softmax - onehot) * inv_count  (0 for ignored rows).
+__global__ void __launch_bounds__(256) cross_entropy_kernel(int V, const float* __restrict__ logits,
+                                                            const long long* __restrict__ targets,
+                                                            float* __restrict__ row_loss,
+                                                            float* __restrict__ d_logits, float inv_count) {
+    __shared__ float s_red[40];
+    const long long r = blockIdx.x;
+    const float* x = logits + r * V;
+    const long long tgt = targets[r];
+    if (tgt < 0) {
+        if (threadIdx.x == 0 && row_loss) row_loss[r] = 0.f;
+        if (d_logits) for (int v = threadIdx.x; v < V; v += blockDim.x) d_logits[r * V + v] = 0.f;
+        return;
+    }
+    float m = -INFINITY;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, x[v]);
+    m = block_max(m, s_red);
+    float sum = 0.f;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) sum += expf(x[v] - m);
+    sum = block_sum(sum, s_red);
+    const float lse = m + logf(sum);
+    if (threadIdx.x == 0 && row_loss) row_loss[r] = lse - x[tgt];
+    if (d_logits) {
+        float* dx = d_logits + r * V;
+        for (int v = threadIdx.x; v < V; v += blockDim.x) {
+            const float pr = expf(x[v] - lse);
+            dx[v] = (pr - (v == tgt ? 1.f : 0.f)) * inv_count;
+        }
+    }
+}
+
+}  // namespace
+
+int icd_lstm_pointwise_fwd(int rows, int D, const float* gates_pre, const float* c_prev,
+                           float* gates_act, float* c_new, float* h_new,
+                           float* hdrop, int64_t hdrop_row_stride, const uint8_t* mask, float scale,
+                           cudaStream_t s) {
+    if (rows == 0) return 0;
+    const long long n = (long long)rows * D;
+    lstm_pointwise_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rows, D, gates_pre, c_prev, gates_act,
+                                                                           c_new, h_new, hdrop, hdrop_row_stride,
+                                                                           mask, scale);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+int icd_lstm_pointwise_bwd(int rows, int D, const float* dh_in, const float* d_hdrop, int64_t hdrop_row_stride,
+                           const uint8_t* mask, float scale, float* dc_inout,
+                           const float* gates_act, const float* c_prev, const float* c_new,
+                           float* dgates_pre, int64_t ld_dg, cudaStream_t s) {
+    if (rows == 0) return 0;
+    const long long n = (long long)rows * D;
+    lstm_pointwise_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rows, D, dh_in, d_hdrop, hdrop_row_stride,
+                                                                           mask, scale, dc_inout, gates_act, c_prev,
+                                                                           c_new, dgates_pre, ld_dg);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+int icd_colsum(const float* X, int64_t ld, int64_t M, int N, const uint8_t* row_mask, float* out, cudaStream_t s) {
+    if (N == 0) return 0;
+    colsum_kernel<<<(N + 31) / 32, dim3(32, 32), 0, s>>>(X, ld, M, N, row_mask, out);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+int icd_embed_gather(const void* table, int is_f64, const int64_t* captions, int B, int L, int T, int E,
+                     float* out, cudaStream_t s) {
+    if (B * T == 0) return 0;
+    if (is_f64) embed_gather_kernel<double><<<B * T, 128, 0, s>>>((const double*)table, (const long long*)captions, B, L, T, E, out);
+    else        embed_gather_kernel<float><<<B * T, 128, 0, s>>>((const float*)table, (const long long*)captions, B, L, T, E, out);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+int icd_embed_scatter_add(void* d_table, int is_f64, const int64_t* captions, int B, int L, int T, int E,
+                          const int32_t* bt_host, const float* d_x, cudaStream_t s) {
+    if (B * T == 0) return 0;
+    ICD_CHECK_ARG(T <= ICD_MAX_STEPS, "embed_scatter_add: T too large");
+    BtPack pack;
+    for (int t = 0; t < ICD_MAX_STEPS; ++t) pack.v[t] = t < T ? bt_host[t] : 0;
+    if (is_f64) embed_scatter_add_kernel<double><<<B * T, 128, 0, s>>>((double*)d_table, (const long long*)captions, B, L, T, E, pack, d_x);
+    else        embed_scatter_add_kernel<float><<<B * T, 128, 0, s>>>((float*)d_table, (const long long*)captions, B, L, T, E, pack, d_x);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int icd_dropout_mask(uint8_t* out, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
+    if (n <= 0) return 0;
+    const long long q = (n + 3) / 4;
+    dropout_mask_kernel<<<(unsigned)((q + 255) / 256), 256, 0, icd_stream(stream)>>>(out, n, p, seed, offset);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int icd_clip_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                                  int64_t n, float grad_scale, float grad_clip, float lr, float beta1, float beta2,
+                                  float eps, int32_t step, void* stream) {
+    if (n <= 0) return 0;
+    ICD_CHECK_ARG(step >= 1, "clip_adam_step: step must be >= 1");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    long long blocks = (n + 255) / 256;
+    if (blocks > ICD_NUM_SMS * 16) blocks = ICD_NUM_SMS * 16;
+    clip_adam_kernel<<<(unsigned)blocks, 256, 0, icd_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n,
+                                                                       grad_scale, grad_clip, lr, beta1, beta2, eps,
+                                                                       (float)bc1, (float)sqrt(bc2));
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int icd_cross_entropy_fwd_bwd(int64_t R, int V, const float* logits, const int64_t* targets,
+                                         float* row_loss, float* d_logits, float inv_count, void* stream) {
+    if (R <= 0) return 0;
+    cross_entropy_kernel<<<(unsigned)R, 256, 0, icd_stream(stream)>>>(V, logits, (const long long*)targets,
+                                                                      row_loss, d_logits, inv_count);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,161 @@
+"""Tensor-level wrappers over the C-ABI entry points (include/icd_b200.h).
+
+torch is used here only for device memory, the current stream and dtype bookkeeping; every computation is a
+kernel of libicd_b200.so.  All functions require CUDA tensors and raise otherwise — there is no CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import PREC_BF16, PREC_FP32, check, fill, lib, ptr, stream_ptr
+
+_PREC = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+
+
+def precision_id(p):
+    if isinstance(p, int):
+        return p
+    return _PREC[p]
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.IcdError("icd_b200 ops need CUDA tensors (got %s); there is no CPU fallback" % t.device)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def gemm(a, b, *, a_strides=None, b_strides=None, out=None, ldc=None, M=None, N=None, K=None,
+         bias1=None, bias2=None, add1=None, ld1=0, add2=None, ld2=0, row_mask=None, beta=0.0,
+         precision="fp32"):
+    """C[M,N] = A[M,K] * B[N,K]^T + epilogue.  By default A is (M,K) row-major and B is (N,K) row-major
+    (the nn.Linear layout: y = x W^T).  Explicit element strides (sam, sak)/(sbn, sbk) select the
+    transposed forms used by the backward contractions."""
+    _need_cuda(a, b)
+    if a_strides is None:
+        M_, K_ = a.shape
+        a_strides = (a.stride(0), a.stride(1))
+    if b_strides is None:
+        N_, K2 = b.shape
+        b_strides = (b.stride(0), b.stride(1))
+    M = a.shape[0] if M is None else M
+    N = b.shape[0] if N is None else N
+    K = a.shape[1] if K is None else K
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+        ldc = N
+    elif ldc is None:
+        ldc = out.stride(0)
+    d = _lib.GemmDesc()
+    fill(d, A=a, sam=a_strides[0], sak=a_strides[1], B=b, sbn=b_strides[0], sbk=b_strides[1], C=out, ldc=ldc,
+         M=M, N=N, K=K, bias1=bias1, bias2=bias2, add1=add1, ld1=ld1, add2=add2, ld2=ld2, row_mask=row_mask,
+         beta=float(beta), precision=precision_id(precision))
+    check(lib().icd_gemm(ctypes.byref(d), stream_ptr()), "icd_gemm")
+    return out
+
+
+def attention_step_fwd(enc, att_enc, att_dec, w_full, b_full, fbeta_pre=None, img_index=None):
+    """-> (alpha (R,P), awe_raw (R,C), gate, gated)   [gate/gated None when fbeta_pre is None]"""
+    _need_cuda(enc, att_enc, att_dec)
+    n_img, P, C = enc.shape
+    A = att_enc.shape[2]
+    R = att_dec.shape[0]
+    dev = enc.device
+    alpha = torch.empty(R, P, device=dev, dtype=torch.float32)
+    awe = torch.empty(R, C, device=dev, dtype=torch.float32)
+    gate = gated = None
+    if fbeta_pre is not None:
+        gate = torch.empty(R, C, device=dev, dtype=torch.float32)
+        gated = torch.empty(R, C, device=dev, dtype=torch.float32)
+    check(lib().icd_attention_step_fwd(
+        R, P, C, A, ptr(img_index), ptr(enc), ptr(att_enc), ptr(att_dec), ctypes.c_int64(att_dec.stride(0)),
+        ptr(w_full), ptr(b_full), ptr(fbeta_pre), ctypes.c_int64(fbeta_pre.stride(0) if fbeta_pre is not None else 0),
+        ptr(alpha), ctypes.c_int64(P), ptr(awe), ptr(gate), ptr(gated), stream_ptr()), "icd_attention_step_fwd")
+    return alpha, awe, gate, gated
+
+
+def attention_step_bwd(enc, att_enc, att_dec, w_full, alpha, gate, awe_raw, d_gated, d_alpha_ext=None):
+    """-> (d_att_dec (R,A), d_fbeta_pre (R,C), d_e (R,P))"""
+    _need_cuda(enc, att_enc, att_dec, d_gated)
+    n_img, P, C = enc.shape
+    A = att_enc.shape[2]
+    R = att_dec.shape[0]
+    dev = enc.device
+    d_att_dec = torch.empty(R, A, device=dev, dtype=torch.float32)
+    d_fb = torch.empty(R, C, device=dev, dtype=torch.float32)
+    d_e = torch.empty(R, P, device=dev, dtype=torch.float32)
+    check(lib().icd_attention_step_bwd(
+        R, P, C, A, ptr(enc), ptr(att_enc), ptr(att_dec), ctypes.c_int64(att_dec.stride(0)), ptr(w_full),
+        ptr(alpha), ctypes.c_int64(alpha.stride(0)),
+        ptr(d_alpha_ext), ctypes.c_int64(d_alpha_ext.stride(0) if d_alpha_ext is not None else 0),
+        ptr(gate), ptr(awe_raw), ptr(d_gated),
+        ptr(d_att_dec), ctypes.c_int64(A), ptr(d_fb), ctypes.c_int64(C), ptr(d_e), ctypes.c_int64(P),
+        stream_ptr()), "icd_attention_step_bwd")
+    return d_att_dec, d_fb, d_e
+
+
+def attention_proj_bwd(att_enc, att_dec_all, w_full, d_e, bt):
+    """att_dec_all (T,B,A) [row stride may exceed A], d_e (B,T,P), bt list[T] -> (d_att_enc, d_w_full, d_b_full)"""
+    B, P, A = att_enc.shape
+    T = len(bt)
+    dev = att_enc.device
+    d_att_enc = torch.empty_like(att_enc)
+    d_wf = torch.empty(A, device=dev, dtype=torch.float32)
+    d_bf = torch.empty(1, device=dev, dtype=torch.float32)
+    ws = torch.empty(int(lib().icd_attention_proj_bwd_ws_floats(B, P, A)), device=dev, dtype=torch.float32)
+    bt_arr = (ctypes.c_int32 * T)(*bt)
+    check(lib().icd_attention_proj_bwd(B, T, P, A, bt_arr, ptr(att_enc), ptr(att_dec_all),
+                                       ctypes.c_int64(att_dec_all.stride(1)), ptr(w_full), ptr(d_e),
+                                       ptr(d_att_enc), ptr(d_wf), ptr(d_bf), ptr(ws), stream_ptr()),
+          "icd_attention_proj_bwd")
+    return d_att_enc, d_wf, d_bf
+
+
+def init_hidden_state(enc, h_w, h_b, c_w, c_b, precision="fp32"):
+    _need_cuda(enc)
+    B, P, C = enc.shape
+    D = h_w.shape[0]
+    dev = enc.device
+    mean = torch.empty(B, C, device=dev, dtype=torch.float32)
+    h = torch.empty(B, D, device=dev, dtype=torch.float32)
+    c = torch.empty(B, D, device=dev, dtype=torch.float32)
+    check(lib().icd_init_hidden_state(B, P, C, D, precision_id(precision), ptr(enc), ptr(h_w), ptr(h_b),
+                                      ptr(c_w), ptr(c_b), ptr(mean), ptr(h), ptr(c), stream_ptr()),
+          "icd_init_hidden_state")
+    return h, c, mean
+
+
+def dropout_mask(shape, p, seed, offset=0, device="cuda"):
+    out = torch.empty(shape, device=device, dtype=torch.uint8)
+    check(lib().icd_dropout_mask(ptr(out), ctypes.c_int64(out.numel()), ctypes.c_float(p),
+                                 ctypes.c_uint64(seed), ctypes.c_uint64(offset), stream_ptr()), "icd_dropout_mask")
+    return out
+
+
+def clip_adam_step(param, grad, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-8,
+                   grad_clip=5.0, grad_scale=1.0):
+    _need_cuda(param, grad, exp_avg, exp_avg_sq)
+    check(lib().icd_clip_adam_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq),
+                                   ctypes.c_int64(param.numel()), ctypes.c_float(grad_scale),
+                                   ctypes.c_float(grad_clip), ctypes.c_float(lr), ctypes.c_float(betas[0]),
+                                   ctypes.c_float(betas[1]), ctypes.c_float(eps), ctypes.c_int32(step),
+                                   stream_ptr()), "icd_clip_adam_step")
+
+
+def cross_entropy_fwd_bwd(logits, targets, inv_count, want_grad=True):
+    """logits (R,V) fp32 contiguous, targets (R) int64 (<0 = ignored row).
+    -> (row_loss (R), d_logits (R,V) = (softmax - onehot) * inv_count)"""
+    _need_cuda(logits, targets)
+    R, V = logits.shape
+    row_loss = torch.empty(R, device=logits.device, dtype=torch.float32)
+    d_logits = torch.empty_like(logits) if want_grad else None
+    check(lib().icd_cross_entropy_fwd_bwd(ctypes.c_int64(R), V, ptr(logits), ptr(targets), ptr(row_loss),
+                                          ptr(d_logits), ctypes.c_float(inv_count), stream_ptr()),
+          "icd_cross_entropy_fwd_bwd")
+    return row_loss, d_logits

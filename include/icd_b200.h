@@ -1,0 +1,297 @@
+/*
+ * icd_b200.h — C ABI of libicd_b200.so: the B200 (sm_100a) captioning-decoder hot path.
+ *
+ * The reference (SarahAlkhateeb/Image-Captioning-with-Different-Decoders) is pure Python/PyTorch and
+ * has no FFI of its own; the "operator interface" of this path is the nn.Module surface
+ *   models/attention.py:18-61   SoftAttention.forward
+ *   models/attention.py:151-164 AttentionDecoder.init_hidden_state
+ *   models/attention.py:218-284 AttentionDecoder.forward (+ its autograd backward)
+ *   models/baseline.py:81-111   BaselineDecoder.forward  (+ its autograd backward)
+ *   gen_captions.py:16-131      attention_caption_image_beam_search
+ *   train_utils.py:2-12 + models/attention.py:417-430   clamp(+-grad_clip) + Adam step
+ * Each entry point below names the reference lines it replaces.  A reference maintainer binds
+ * them with ctypes; no torch types cross this boundary.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host;
+ *   - row-major, element strides given explicitly where a tensor may be a slice;
+ *   - `stream` is a cudaStream_t passed as void*; every call is stream-ordered and asynchronous,
+ *     never synchronises the device, never allocates: all workspace is caller-provided;
+ *   - return value: 0 ok; <0 bad argument / unsupported shape (see icd_last_error_string);
+ *     >0 a cudaError_t;
+ *   - thread-compatible: no global mutable state except the per-thread last-error string.
+ */
+#ifndef ICD_B200_H
+#define ICD_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define ICD_API __attribute__((visibility("default")))
+#else
+#define ICD_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICD_B200_ABI_VERSION 3
+#define ICD_MAX_STEPS 256
+
+ICD_API int icd_version(void);                       /* ICD_B200_ABI_VERSION the library was built with */
+ICD_API const char* icd_last_error_string(void);     /* per-thread, valid until the next failing call     */
+ICD_API int icd_sizeof_att_desc(void);               /* sizeof(icd_att_desc_t)  — struct-layout self check */
+ICD_API int icd_sizeof_base_desc(void);
+ICD_API int icd_sizeof_beam_desc(void);
+ICD_API int icd_has_tensor_core_gemm(void);          /* 1 if the tcgen05/TMA GEMM path was compiled in     */
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense contraction  C[M,N] = A[M,K] * B[N,K]^T (+ epilogue), fp32 storage.
+ *   A(m,k) = A[m*sam + k*sak], B(n,k) = B[n*sbn + k*sbk]  (one stride of each operand must be 1)
+ *   C(m,n) = C[m*ldc + n]
+ *   epilogue: v = acc + bias1[n] + bias2[n] + add1[m*ld1+n] + add2[m*ld2+n]; (any may be NULL)
+ *             if (row_mask && !row_mask[m]) v = 0;   C = v + beta*C
+ *   precision: ICD_PREC_FP32  — fp32 FMA (parity tier),
+ *              ICD_PREC_BF16  — bf16 operands on tcgen05 tensor cores, fp32 accumulate (fast tier)
+ * Replaces every nn.Linear / LSTMCell matmul on the path (models/attention.py:54,55,161-163,
+ * 270,277-279; models/baseline.py:106,109).
+ * ---------------------------------------------------------------------------------------------- */
+#define ICD_PREC_FP32 0
+#define ICD_PREC_BF16 1
+
+typedef struct {
+    const float* A; int64_t sam, sak;
+    const float* B; int64_t sbn, sbk;
+    float* C; int64_t ldc;
+    int32_t M, N, K;
+    const float* bias1; const float* bias2;
+    const float* add1; int64_t ld1;
+    const float* add2; int64_t ld2;
+    const uint8_t* row_mask;
+    float beta;
+    int32_t precision;
+} icd_gemm_desc_t;
+
+ICD_API int icd_gemm(const icd_gemm_desc_t* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SoftAttention step, forward (models/attention.py:55-60 with att_enc hoisted, + :270-271 gate).
+ *   rows      : number of decoder rows processed (batch_size_t, or images*beams)
+ *   img_index : optional [rows] int32 — row r attends over image img_index[r] (beam search);
+ *               NULL => row r uses image r
+ *   enc       : (n_img, P, C) fp32 channel-last feature maps
+ *   att_enc   : (n_img, P, A) fp32  = enc_att(enc)            (models/attention.py:54)
+ *   att_dec   : row r at att_dec + r*ld_dec, A floats         (dec_att(h), :55)
+ *   fbeta_pre : row r at fbeta_pre + r*ld_fb, C floats        (f_beta(h) before sigmoid, :270)
+ *   alpha     : out, row r at alpha + r*ld_alpha, P floats    (softmax over pixels, :58)
+ *   awe_raw, gate, gated : out (rows, C) each, any may be NULL:
+ *        awe_raw = sum_p alpha*enc (:59-60), gate = sigmoid(fbeta_pre), gated = gate*awe_raw (:271)
+ * ---------------------------------------------------------------------------------------------- */
+ICD_API int icd_attention_step_fwd(int rows, int P, int C, int A,
+                           const int32_t* img_index,
+                           const float* enc, const float* att_enc,
+                           const float* att_dec, int64_t ld_dec,
+                           const float* w_full, const float* b_full,
+                           const float* fbeta_pre, int64_t ld_fb,
+                           float* alpha, int64_t ld_alpha,
+                           float* awe_raw, float* gate, float* gated,
+                           void* stream);
+
+/* Backward of the step above for the recurrent path.
+ *   in : d_gated (rows,C); gate, awe_raw (rows,C) and alpha saved by the forward;
+ *        d_alpha_ext: optional upstream gradient on alpha itself (row stride ld_dalpha)
+ *   out: d_att_dec row r at d_att_dec + r*ld_ddec (A floats)
+ *        d_fbeta_pre row r at d_fbeta_pre + r*ld_dfb (C floats)
+ *        d_e row r at d_e + r*ld_de (P floats)  — gradient w.r.t. the pre-softmax scores; consumed
+ *        after the time loop by icd_attention_proj_bwd (d_att_enc is NOT read-modify-written per step)
+ */
+ICD_API int icd_attention_step_bwd(int rows, int P, int C, int A,
+                           const float* enc, const float* att_enc,
+                           const float* att_dec, int64_t ld_dec,
+                           const float* w_full,
+                           const float* alpha, int64_t ld_alpha,
+                           const float* d_alpha_ext, int64_t ld_dalpha,
+                           const float* gate, const float* awe_raw, const float* d_gated,
+                           float* d_att_dec, int64_t ld_ddec,
+                           float* d_fbeta_pre, int64_t ld_dfb,
+                           float* d_e, int64_t ld_de,
+                           void* stream);
+
+/* After the time loop: d_att_enc[b,p,a] = w_full[a] * sum_t d_e[b,t,p] * [att_enc[b,p,a]+att_dec[t,b,a] > 0]
+ * plus the full_att parameter gradients (d_w_full[A], d_b_full[1]).
+ *   att_dec_all: (T, B, *) with row (t,b) at att_dec_all + (t*B+b)*ld_dec ; d_e: (B, T, P)
+ *   bt_host[T]: rows active at step t;   partial: workspace of icd_attention_proj_bwd_ws_floats() floats
+ */
+ICD_API int64_t icd_attention_proj_bwd_ws_floats(int B, int P, int A);
+ICD_API int icd_attention_proj_bwd(int B, int T, int P, int A, const int32_t* bt_host,
+                           const float* att_enc, const float* att_dec_all, int64_t ld_dec,
+                           const float* w_full, const float* d_e,
+                           float* d_att_enc, float* d_w_full, float* d_b_full,
+                           float* partial, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * AttentionDecoder.forward / backward, teacher-forced (models/attention.py:218-284).
+ * One descriptor carries inputs, weights, outputs, tensors saved for backward and scratch.
+ * Shapes: B batch, T = max(decode_lengths), L caption columns, P pixels, C encoder dim,
+ *         A attention dim, D decoder dim, E embed size, V vocab, NZ = A + C + 4*D.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t B, T, L, P, C, A, D, E, V;
+    int32_t precision;            /* ICD_PREC_* for the dense contractions                      */
+    int32_t emb_is_f64;           /* embedding table (and its gradient) are float64 (GloVe path)  */
+    int32_t bt_host[ICD_MAX_STEPS]; /* batch_size_t = sum(l > t), first-rows semantics (:261-265)  */
+    /* inputs */
+    const float* enc;             /* (B,P,C) */
+    const int64_t* captions;      /* (B,L)   */
+    const uint8_t* drop_mask;     /* (T,B,D) keep-mask or NULL (eval / p=0)   (:279)              */
+    float drop_scale;             /* 1/(1-p) */
+    /* weights, state_dict order of SURVEY.md 8b */
+    const float *enc_att_w, *enc_att_b, *dec_att_w, *dec_att_b, *full_att_w, *full_att_b;
+    const float *w_ih, *w_hh, *b_ih, *b_hh;
+    const float *h_lin_w, *h_lin_b, *c_lin_w, *c_lin_b;
+    const float *f_beta_w, *f_beta_b, *fc_w, *fc_b;
+    const void* emb_w;            /* (V,E) fp32 or fp64 */
+    /* outputs */
+    float* predictions;           /* (B,T,V) rows >= batch_size_t are exactly 0 (:253,280)        */
+    float* alphas;                /* (B,T,P)                                    (:257,281)        */
+    /* saved for backward (fwd writes, bwd reads) */
+    float* att_enc;               /* (B,P,A)  */
+    float* mean_enc;              /* (B,C)    */
+    float* emb_x;                 /* (T,B,E)  */
+    float* xg;                    /* (T,B,4D) */
+    float* w_cat;                 /* (NZ,D) = [dec_att_w; f_beta_w; w_hh] */
+    float* b_cat;                 /* (NZ)   = [dec_att_b; f_beta_b; 0]    */
+    float* z;                     /* (T,B,NZ) */
+    float* awe_raw;               /* (T,B,C)  */
+    float* gate;                  /* (T,B,C)  */
+    float* gated;                 /* (T,B,C)  */
+    float* gates_act;             /* (T,B,4D) */
+    float* h_all;                 /* (T+1,B,D) */
+    float* c_all;                 /* (T+1,B,D) */
+    float* hdrop;                 /* (B,T,D)  */
+    uint8_t* row_valid;           /* (B*T)    */
+    float* gates_pre;             /* (B,4D) scratch */
+    /* ---- backward only ---- */
+    const float* d_predictions;   /* (B,T,V) */
+    const float* d_alphas;        /* (B,T,P) or NULL */
+    float *d_enc_att_w, *d_enc_att_b;
+    float *d_w_cat, *d_b_cat;     /* (NZ,D),(NZ): rows [0,A) dec_att, [A,A+C) f_beta, [A+C,NZ) w_hh / b_hh(=b_ih) */
+    float *d_full_att_w, *d_full_att_b;
+    float *d_w_ih;                /* (4D,E+C) */
+    float *d_h_lin_w, *d_h_lin_b, *d_c_lin_w, *d_c_lin_b;
+    float *d_fc_w, *d_fc_b;
+    void* d_emb_w;                /* (V,E) fp32/fp64, pre-zeroed by this call; NULL => embedding frozen */
+    /* backward scratch */
+    float* d_hdrop;               /* (B,T,D)  */
+    float* dz;                    /* (T,B,NZ) */
+    float* d_e;                   /* (B,T,P)  */
+    float* dh;                    /* (B,D)    */
+    float* dc;                    /* (B,D)    */
+    float* d_gated;               /* (B,C)    */
+    float* d_att_enc;             /* (B,P,A)  */
+    float* d_emb_x;               /* (T,B,E)  */
+    float* proj_partial;          /* icd_attention_proj_bwd_ws_floats(B,P,A) floats */
+} icd_att_desc_t;
+
+ICD_API int icd_attention_decoder_fwd(const icd_att_desc_t* d, void* stream);
+ICD_API int icd_attention_decoder_bwd(const icd_att_desc_t* d, void* stream);
+
+/* init_hidden_state (models/attention.py:151-164): mean over pixels, h_lin, c_lin.  h, c: (B,D). */
+ICD_API int icd_init_hidden_state(int B, int P, int C, int D, int precision, const float* enc,
+                          const float* h_lin_w, const float* h_lin_b,
+                          const float* c_lin_w, const float* c_lin_b,
+                          float* mean_enc, float* h, float* c, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BaselineDecoder.forward / backward (models/baseline.py:81-111): embedding of captions[:, :-1],
+ * image feature prepended as step 0, 1-layer LSTM from zero state (gate order i,f,g,o), vocab linear.
+ * B batch, L caption columns (= LSTM steps), E embed, H hidden, V vocab.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t B, L, E, H, V;
+    int32_t precision;
+    int32_t emb_is_f64;
+    const float* img_features;    /* (B,E)   */
+    const int64_t* captions;      /* (B,L)   */
+    const void* emb_w;            /* (V,E)   */
+    const float *w_ih, *w_hh, *b_ih, *b_hh;   /* (4H,E) (4H,H) (4H) (4H) */
+    const float *lin_w, *lin_b;   /* (V,H) (V) */
+    float* outputs;               /* (B,L,V) */
+    /* saved */
+    float* x;                     /* (L,B,E)  step-major LSTM input  */
+    float* xg;                    /* (L,B,4H) */
+    float* gates_act;             /* (L,B,4H) */
+    float* h_all;                 /* (L+1,B,H) */
+    float* c_all;                 /* (L+1,B,H) */
+    float* hout;                  /* (B,L,H)  */
+    float* gates_pre;             /* (B,4H) scratch */
+    /* backward */
+    const float* d_outputs;       /* (B,L,V) */
+    float *d_w_ih, *d_w_hh, *d_b, *d_lin_w, *d_lin_b;   /* d_b = d_b_ih = d_b_hh */
+    void* d_emb_w;                /* (V,E) or NULL */
+    float* d_img_features;        /* (B,E) or NULL */
+    float* d_hout;                /* (B,L,H) */
+    float* dg;                    /* (L,B,4H) */
+    float* dh;                    /* (B,H) */
+    float* dc;                    /* (B,H) */
+    float* d_x;                   /* (L,B,E) */
+} icd_base_desc_t;
+
+ICD_API int icd_baseline_decoder_fwd(const icd_base_desc_t* d, void* stream);
+ICD_API int icd_baseline_decoder_bwd(const icd_base_desc_t* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched beam search (gen_captions.py:16-131; state machine in SURVEY.md Appendix C), n_img
+ * independent images x k beam slots, fully device-side (no per-step host sync).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_img, k, max_steps;  /* loop body runs for step = 1 .. max_steps+1 (gen_captions.py:119) */
+    int32_t P, C, A, D, E, V;
+    int32_t precision, emb_is_f64;
+    int32_t start_id, end_id;
+    const float* enc;             /* (n_img,P,C) */
+    const float *enc_att_w, *enc_att_b, *dec_att_w, *dec_att_b, *full_att_w, *full_att_b;
+    const float *w_ih, *w_hh, *b_ih, *b_hh;
+    const float *h_lin_w, *h_lin_b, *c_lin_w, *c_lin_b;
+    const float *f_beta_w, *f_beta_b, *fc_w, *fc_b;
+    const void* emb_w;
+    /* results (device) */
+    int32_t* out_len;             /* (n_img)   length of best completed caption incl. <start>/<end>; 0 => none completed */
+    int32_t* out_seq;             /* (n_img, max_steps+2) */
+    float* out_score;             /* (n_img)   raw summed log-prob of the winner */
+    float* out_alpha;             /* (n_img, max_steps+2, P) frame 0 = ones; may be NULL */
+    int32_t* trace_words;         /* (max_steps+1, n_img, k) next-word ids per step, -1 = empty slot; may be NULL */
+    /* workspace (device) */
+    void* ws; int64_t ws_bytes;   /* >= icd_beam_search_ws_bytes(desc) */
+} icd_beam_desc_t;
+
+ICD_API int64_t icd_beam_search_ws_bytes(const icd_beam_desc_t* d);
+ICD_API int icd_beam_search(const icd_beam_desc_t* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser glue: element-wise gradient clamp to +-grad_clip (train_utils.py:2-12) fused with the
+ * torch.optim.Adam(lr, betas=(0.9,0.999), eps=1e-8, weight_decay=0) update (models/attention.py:352-355,
+ * 423-428) over a flat fp32 buffer; grad_scale multiplies the gradient first (1/world_size after all-reduce).
+ * step is the 1-based Adam step count.
+ * ---------------------------------------------------------------------------------------------- */
+ICD_API int icd_clip_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                       int64_t n, float grad_scale, float grad_clip, float lr, float beta1, float beta2,
+                       float eps, int32_t step, void* stream);
+
+/* Keep-mask generator for nn.Dropout (Philox4x32-10, counter-based): out[i] = uniform > p ? 1 : 0 */
+ICD_API int icd_dropout_mask(uint8_t* out, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+
+/* Token-level loss glue (models/attention.py:401-411; models/baseline.py:224-225) fused:
+ * mean cross-entropy over the valid rows of logits (R,V) and its gradient written in place of a
+ * separate softmax pass.  targets[r] < 0 => row ignored.  loss_sum/count are device scalars (pre-zeroed
+ * by the call); d_logits may be NULL (loss only); grad_scale = upstream grad / count is applied by the
+ * second entry point once count is known.
+ */
+ICD_API int icd_cross_entropy_fwd_bwd(int64_t R, int V, const float* logits, const int64_t* targets,
+                              float* row_loss, float* d_logits, float inv_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICD_B200_H */

@@ -1,0 +1,144 @@
+"""CPU tier: the C-ABI library loads without a GPU and exports every symbol include/icd_b200.h declares; host-side
+logic of the drop-in modules (constructor contract, state_dict keys, batch_size_t schedule, synthetic inputs)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import helpers as H
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from icd_b200 import _lib
+    L = _lib.lib()
+    header = open(_lib.HEADER).read()
+    declared = re.findall(r"ICD_API\s+[\w\s\*]+?\b(icd_\w+)\s*\(", header)
+    assert len(declared) >= 20 and sorted(declared) == sorted(_lib.FUNCTIONS)
+    for name in declared:
+        assert hasattr(L, name), "libicd_b200.so does not export " + name
+    assert L.icd_version() == _lib.DEFINES["ICD_B200_ABI_VERSION"]
+    assert L.icd_sizeof_att_desc() == ctypes.sizeof(_lib.AttDesc)
+    assert L.icd_sizeof_base_desc() == ctypes.sizeof(_lib.BaseDesc)
+    assert L.icd_sizeof_beam_desc() == ctypes.sizeof(_lib.BeamDesc)
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    from icd_b200 import _lib
+    L = _lib.lib()
+    d = _lib.GemmDesc()
+    _lib.fill(d, M=4, N=4, K=4, sam=3, sak=2, sbn=4, sbk=1, ldc=4, precision=_lib.PREC_FP32)
+    rc = L.icd_gemm(ctypes.byref(d), None)
+    assert rc < 0 and b"unit stride" in L.icd_last_error_string()
+    d.precision = 77
+    assert L.icd_gemm(ctypes.byref(d), None) < 0
+    with pytest.raises(_lib.IcdError):
+        _lib.check(rc, "icd_gemm")
+
+
+def test_product_path_refuses_cpu_tensors():
+    """No CPU / eager fallback: the modules must fail loudly off-GPU."""
+    import icd_b200.models.attention as my_att
+    import icd_b200.models.baseline as my_base
+    from icd_b200 import _lib
+    from icd_b200.vocabulary import synthetic_vocab
+    case = H.ATT_CASES["att_small_ragged"]
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams,
+                                   synthetic_vocab(case["V"]))
+    enc, caps, lens = H.att_inputs(case)
+    with pytest.raises(_lib.IcdError):
+        dec(enc, caps, lens)
+    bcase = H.BASE_CASES["base_small"]
+    bdec = H.build_baseline_module(bcase, my_base.BaselineDecoder, my_base.BaselineDecoderParams)
+    img, bcaps, _ = H.base_inputs(bcase)
+    with pytest.raises(_lib.IcdError):
+        bdec(img, bcaps)
+
+
+def test_no_product_module_imports_the_oracle():
+    pkg = os.path.join(H.ROOT, "image-captioning-with-different-decoders_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "/root/reference" not in src, f
+
+
+def test_constructor_contract_and_state_dict_keys():
+    import icd_b200.models.attention as my_att
+    import icd_b200.models.baseline as my_base
+    from icd_b200.vocabulary import Vocabulary, synthetic_vocab
+    from oracle import decoders as O
+    p = my_att.AttentionDecoderParams()
+    assert (p.attention_dim, p.decoder_dim, p.embed_size, p.dropout, p.use_bert, p.vocab) == (512, 512, 512, 0.5, False, None)
+    with pytest.raises(AssertionError):
+        my_att.AttentionDecoder(torch.device("cpu"), object())
+    with pytest.raises(AssertionError):
+        my_att.AttentionDecoder(torch.device("cpu"), p)            # vocab must be a Vocabulary
+    p.vocab = synthetic_vocab(50)
+    p.attention_dim, p.decoder_dim, p.embed_size = 16, 12, 8
+    dec = my_att.AttentionDecoder(torch.device("cpu"), p)
+    assert list(dec.state_dict().keys()) == O.ATT_KEYS
+    assert dec.vocab_size == 50 and dec.encoder_dim == 2048 and isinstance(dec.vocab, Vocabulary)
+    assert dec.decode_step.weight_ih.shape == (48, 8 + 2048)
+    assert torch.all(dec.fc.bias == 0) and float(dec.fc.weight.abs().max()) <= 0.1
+    assert dec.embedding.weight.requires_grad
+    dec.fine_tune_embeddings(False)
+    assert not dec.embedding.weight.requires_grad
+    tbl = torch.zeros(50, 8, dtype=torch.float64)
+    dec.load_pretrained_embeddins(tbl)
+    assert dec.embedding.weight.dtype == torch.float64 and dec.embedding.weight.requires_grad
+    for attr in ("attention", "embedding", "decode_step", "h_lin", "c_lin", "f_beta", "sigmoid", "fc", "dropout"):
+        assert hasattr(dec, attr)
+    bp = my_base.BaselineDecoderParams()
+    assert (bp.hidden_size, bp.embed_size, bp.vocab_size) == (512, 512, None)
+    with pytest.raises(AssertionError):
+        my_base.BaselineDecoder(bp)
+    bp.vocab_size = 50
+    bp.hidden_size = bp.embed_size = 8
+    b = my_base.BaselineDecoder(bp)
+    assert list(b.state_dict().keys()) == O.BASE_KEYS
+    assert (b.embed_size, b.hidden_size) == (8, 8)
+
+
+def test_vocabulary_layout_and_unknown_fallback():
+    from icd_b200.vocabulary import END_TOKEN, PAD_TOKEN, START_TOKEN, UNK_TOKEN, synthetic_vocab
+    v = synthetic_vocab(9490)
+    assert len(v) == 9490
+    assert (v(PAD_TOKEN), v(START_TOKEN), v(END_TOKEN), v(UNK_TOKEN)) == (0, 9487, 9488, 9489)
+    assert v("never-seen-word") == v(UNK_TOKEN)
+    assert v.i2w[v("w3")] == "w3"
+
+
+def test_synthetic_inputs_shapes_and_schedule():
+    from icd_b200 import synthetic
+    enc = synthetic.features(3)
+    assert enc.shape == (3, 14, 14, 2048) and float(enc.min()) == 0.0 and 0.3 < float(enc.mean()) < 0.5
+    caps, lens = synthetic.captions(6, 100, max_len=12, lengths="ragged")
+    assert caps.shape == (6, 12) and lens == sorted(lens, reverse=True) and lens[0] == 12
+    for b, l in enumerate(lens):
+        assert caps[b, 0] == 97 and caps[b, l - 1] == 98 and torch.all(caps[b, l:] == 0)
+        assert torch.all((caps[b, 1:l - 1] >= 1) & (caps[b, 1:l - 1] <= 96))
+    # batch_size_t schedule of models/attention.py:261 for unsorted lengths: a COUNT, rows taken positionally
+    dl = [l - 1 for l in [5, 8, 3, 8]]
+    bt = [sum(l > t for l in dl) for t in range(max(dl))]
+    assert bt == [4, 4, 3, 3, 2, 2, 2]
+    t = synthetic.glove_like_table(20)
+    assert t.dtype == torch.float64 and t.shape == (20, 300)
+
+
+def test_flat_param_buffer_views_share_storage():
+    from icd_b200.parallel import FlatParamBuffer
+    m = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    want = [p.detach().clone() for p in m.parameters()]
+    buf = FlatParamBuffer(m)
+    assert buf.flat.numel() == sum(p.numel() for p in m.parameters())
+    for p, w in zip(m.parameters(), want):
+        assert torch.equal(p.data, w)
+    buf.flat.zero_()
+    assert all(float(p.abs().sum()) == 0 for p in m.parameters())
+    m(torch.ones(1, 4)).sum().backward()
+    g = buf.gather_grads()
+    assert torch.equal(g, torch.cat([p.grad.reshape(-1) for p in m.parameters()]))

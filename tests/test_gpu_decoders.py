@@ -1,0 +1,336 @@
+"""GPU tier, module level: the drop-in modules (CUDA kernels through the C ABI) against
+  (a) the golden vectors produced by the unmodified reference (tests/golden/*.npz), and
+  (b) the oracle (oracle/decoders.py) run on the CPU on the same seeded inputs, fp32 and fp64.
+
+Tolerances, fp32 tier (BASELINE.json north_star: 1e-3 relative on logits, alphas, loss, gradients):
+  logits / alphas / loss          1e-4 norm-wise (measured ~1e-6; pure re-association of fp32 sums)
+  gradients                       1e-3 norm-wise per tensor, with the SURVEY.md Appendix B caveat: the four
+                                  attention-projection gradients are ill-conditioned (the reference itself is ~5e-4
+                                  from fp64 truth), so they are judged by distance to the fp64 oracle as well
+  attention.full_att.bias.grad    absolute 1e-5 (true value identically 0)
+  greedy ids                      identical wherever the reference's top-2 logit margin exceeds 1e-4
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle import decoders as O
+
+pytestmark = pytest.mark.gpu
+
+ILL_CONDITIONED = ("attention.enc_att.weight", "attention.enc_att.bias", "attention.dec_att.weight",
+                   "attention.dec_att.bias")
+
+
+def load(name):
+    return np.load(os.path.join(H.GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+
+
+def golden_tensor(case, g, name):
+    return torch.from_numpy(g[name]) if case["store"] == "full" else None
+
+
+def compare(case, g, name, t, tol, atol=0.0):
+    if case["store"] == "full":
+        H.assert_close_norm(t, torch.from_numpy(g[name]), tol, name, atol)
+    else:
+        H.assert_digest_close(name, t, dict(norm=g[name + "@norm"], samples=g[name + "@samples"]), tol, atol)
+
+
+def run_attention(case, cuda, dtype_oracle=None):
+    import icd_b200.models.attention as my_att
+    from icd_b200.vocabulary import synthetic_vocab
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams,
+                                   synthetic_vocab(case["V"]))
+    sd = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    dec = dec.to(cuda)
+    enc, caps, lens = H.att_inputs(case)
+    dl = [l - 1 for l in lens]
+    masks = None
+    if case["train"]:
+        masks = H.dropout_masks_like_reference(case, dl, case["D"])
+        dec._dropout_mask_override = H.stack_masks(masks, case["B"], case["D"])
+    caps_dev = caps.to(cuda)
+    preds, caps_out, odl, alphas = dec(enc.to(cuda), caps_dev, lens)
+    assert caps_out is caps_dev and odl == dl
+    if case.get("loss", True):
+        loss = O.attention_loss(preds, caps_dev, odl, alphas)       # the reference's loss glue, torch ops on GPU
+    else:
+        gen = torch.Generator().manual_seed(case["iseed"] + 1000)
+        g1 = torch.randn(preds.shape, generator=gen).to(cuda)
+        g2 = torch.randn(alphas.shape, generator=gen).to(cuda)
+        loss = (preds * g1).sum() + (alphas * g2).sum()
+    loss.backward()
+    grads = {k: p.grad for k, p in dec.named_parameters()}
+    return dec, sd, (enc, caps, lens, dl, masks), preds, alphas, loss, grads
+
+
+@pytest.mark.parametrize("name", list(H.ATT_CASES))
+def test_attention_decoder_matches_reference_golden(cuda, name):
+    case = H.ATT_CASES[name]
+    g = load(name)
+    dec, sd, (enc, caps, lens, dl, masks), preds, alphas, loss, grads = run_attention(case, cuda)
+    cs = {k: H.checksum(v) for k, v in sd.items()}
+    assert list(cs.values()) == [str(v) for v in g["weight_checksums"]], "seeded init differs from the reference"
+    assert list(g["decode_lengths"]) == dl
+    compare(case, g, "predictions", preds, 1e-4)
+    compare(case, g, "alphas", alphas, 1e-4)
+    # rows >= batch_size_t are exactly zero (models/attention.py:253-258)
+    for b, l in enumerate(dl):
+        assert torch.all(preds[b, l:] == 0) and torch.all(alphas[b, l:] == 0)
+    if case.get("loss", True):
+        assert abs(loss.item() - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+        ids = O.teacher_forced_ids(preds.cpu(), dl)
+        gold, margin = g["greedy_ids"], g["greedy_margin"]
+        for j, row in enumerate(ids):
+            for t, tok in enumerate(row):
+                if margin[j, t] > 1e-4:
+                    assert tok == gold[j, t], "greedy id differs at (%d,%d) with margin %.2e" % (j, t, margin[j, t])
+    # fp64 oracle as the arbiter for the ill-conditioned tensors
+    frozen = () if case["fine_tune_embedding"] else ("embedding.weight",)
+    w64 = {k: v.double().requires_grad_(k not in frozen) for k, v in sd.items()}
+    p64, _, dl64, a64 = O.attention_decoder_forward(w64, enc.double(), caps, lens, dropout_p=case["dropout"],
+                                                    dropout_masks=masks)
+    if case.get("loss", True):
+        l64 = O.attention_loss(p64, caps, dl64, a64)
+    else:
+        gen = torch.Generator().manual_seed(case["iseed"] + 1000)
+        g1 = torch.randn(p64.shape, generator=gen).double()
+        g2 = torch.randn(a64.shape, generator=gen).double()
+        l64 = (p64 * g1).sum() + (a64 * g2).sum()
+    l64.backward()
+    names = [str(x) for x in g["grad_names"]]
+    for k in names:
+        gr = grads[k]
+        assert gr is not None, k
+        assert gr.dtype == sd[k].dtype, "gradient dtype of %s" % k
+        if k == "attention.full_att.bias":
+            assert float(gr.abs().max()) < 1e-5
+            continue
+        H.assert_close_norm(gr, w64[k].grad, 1e-3, "grad vs fp64 oracle: " + k)
+        tol = 2e-3 if k in ILL_CONDITIONED else 1e-3
+        compare(case, g, "grad:" + k, gr, tol)
+    for k, gr in grads.items():
+        if k not in names:
+            assert gr is None, "unexpected gradient for " + k
+
+
+def test_attention_decoder_eval_has_no_dropout_and_is_deterministic(cuda):
+    import icd_b200.models.attention as my_att
+    from icd_b200.vocabulary import synthetic_vocab
+    case = dict(H.ATT_CASES["att_small_dropout"], train=False)
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams,
+                                   synthetic_vocab(case["V"])).to(cuda)
+    enc, caps, lens = H.att_inputs(case)
+    with torch.no_grad():
+        p1, _, _, a1 = dec(enc.to(cuda), caps.to(cuda), lens)
+        p2, _, _, a2 = dec(enc.to(cuda), caps.to(cuda), lens)
+    assert torch.equal(p1, p2) and torch.equal(a1, a2)
+    w = O.cast_weights(dec.state_dict(), torch.float32)
+    po, _, _, ao = O.attention_decoder_forward(w, enc, caps, lens)
+    H.assert_close_norm(p1, po, 1e-4, "eval predictions")
+    # train mode with the built-in Philox mask: seeded by torch's generator, drops ~p of fc inputs
+    dec.train()
+    torch.manual_seed(3)
+    with torch.no_grad():
+        t1, _, _, _ = dec(enc.to(cuda), caps.to(cuda), lens)
+        torch.manual_seed(3)
+        t2, _, _, _ = dec(enc.to(cuda), caps.to(cuda), lens)
+        t3, _, _, _ = dec(enc.to(cuda), caps.to(cuda), lens)
+    assert torch.equal(t1, t2) and not torch.equal(t1, t3) and not torch.equal(t1, p1)
+
+
+def test_attention_decoder_accepts_permuted_encoder_view(cuda):
+    """EncoderAttention returns an NCHW tensor permuted to (B,14,14,2048) (models/encoder.py:107-110)."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.vocabulary import synthetic_vocab
+    case = H.ATT_CASES["att_small_ragged"]
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams,
+                                   synthetic_vocab(case["V"])).to(cuda)
+    enc, caps, lens = H.att_inputs(case)
+    nchw = enc.permute(0, 3, 1, 2).contiguous().to(cuda)
+    view = nchw.permute(0, 2, 3, 1)
+    assert not view.is_contiguous()
+    with torch.no_grad():
+        p1, _, _, a1 = dec(enc.to(cuda), caps.to(cuda), lens)
+        p2, _, _, a2 = dec(view, caps.to(cuda), lens)
+    assert torch.equal(p1, p2) and torch.equal(a1, a2)
+
+
+def test_soft_attention_module_matches_oracle(cuda):
+    import icd_b200.models.attention as my_att
+    torch.manual_seed(0)
+    att = my_att.SoftAttention(2048, 64, 48)
+    w = {"attention." + k: v.detach().clone().double().requires_grad_(True) for k, v in att.state_dict().items()}
+    att = att.to(cuda)
+    g = torch.Generator().manual_seed(1)
+    enc = torch.randn(4, 196, 2048, generator=g).clamp_min_(0)
+    h = torch.randn(4, 64, generator=g)
+    h_dev = h.to(cuda).requires_grad_(True)
+    awe, alpha = att(enc.to(cuda), h_dev)
+    h64 = h.double().requires_grad_(True)
+    awe64, alpha64 = O.soft_attention(w, enc.double(), h64)
+    H.assert_close_norm(awe, awe64, 1e-5, "awe")
+    H.assert_close_norm(alpha, alpha64, 1e-5, "alpha")
+    ga = torch.randn(awe.shape, generator=g)
+    gb = torch.randn(alpha.shape, generator=g)
+    ((awe * ga.to(cuda)).sum() + (alpha * gb.to(cuda)).sum()).backward()
+    ((awe64 * ga.double()).sum() + (alpha64 * gb.double()).sum()).backward()
+    H.assert_close_norm(h_dev.grad, h64.grad, 1e-4, "d hidden")
+    for k, p in att.named_parameters():
+        if k == "full_att.bias":
+            assert float(p.grad.abs().max()) < 1e-4
+            continue
+        H.assert_close_norm(p.grad, w["attention." + k].grad, 1e-4, "grad " + k)
+
+
+@pytest.mark.parametrize("name", list(H.BASE_CASES))
+def test_baseline_decoder_matches_reference_golden(cuda, name):
+    import icd_b200.models.baseline as my_base
+    case = H.BASE_CASES[name]
+    g = load(name)
+    dec = H.build_baseline_module(case, my_base.BaselineDecoder, my_base.BaselineDecoderParams)
+    cs = H.state_checksums(dec)
+    assert list(cs.values()) == [str(v) for v in g["weight_checksums"]]
+    dec = dec.to(cuda)
+    img, caps, lens = H.base_inputs(case)
+    img_dev = img.to(cuda).requires_grad_(True)
+    outs = dec(img_dev, caps.to(cuda))
+    assert outs.shape == (case["B"], case["L"], case["V"])
+    compare(case, g, "outputs", outs, 1e-4)
+    loss = O.baseline_loss(outs, caps.to(cuda))
+    assert abs(loss.item() - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
+    loss.backward()
+    for k in [str(x) for x in g["grad_names"]]:
+        gr = img_dev.grad if k == "img_features" else dict(dec.named_parameters())[k].grad
+        compare(case, g, "grad:" + k, gr, 1e-3)
+    ids = outs.argmax(dim=2).cpu().numpy()
+    margin = g["greedy_margin"]
+    assert np.all((ids == g["greedy_ids"]) | (margin <= 1e-4))
+
+
+@pytest.mark.parametrize("name", list(H.BEAM_CASES))
+def test_beam_search_matches_reference_golden(cuda, name, capsys):
+    import icd_b200.models.attention as my_att
+    from icd_b200.gen_captions import attention_caption_image_beam_search, beam_search_batched
+    from icd_b200.vocabulary import synthetic_vocab
+    case = H.BEAM_CASES[name]
+    g = load(name)
+    vocab = synthetic_vocab(case["V"])
+    acase = dict(case, dropout=0.5, train=False, fine_tune_embedding=True)
+    dec = H.build_attention_module(acase, my_att.AttentionDecoder, my_att.AttentionDecoderParams, vocab)
+    H.apply_beam_recipe(dec, case)
+    assert list(H.state_checksums(dec).values()) == [str(v) for v in g["weight_checksums"]]
+    dec = dec.to(cuda)
+    feats = H.beam_features(case).to(cuda)
+    V, k = case["V"], case["k"]
+    with torch.no_grad():
+        res = beam_search_batched(dec, feats, k, V - 3, V - 2, max_steps=50, want_alphas=True, want_trace=True)
+    lens = res["len"].cpu().tolist()
+    for i in range(case["n_img"]):
+        if not bool(g["stable_%d" % i]):
+            continue        # caption of the reference flips under fp64 re-evaluation: not a meaningful target
+        gold = list(g["seq_%d" % i])
+        if bool(g["ended_%d" % i]):
+            assert lens[i] == len(gold)
+            assert res["seq"][i, :lens[i]].cpu().tolist() == gold
+            a = res["alpha"][i, :lens[i]].cpu().numpy().reshape(lens[i], 14, 14)
+            assert np.abs(a - g["alphas_%d" % i]).max() < 1e-4
+        else:
+            assert lens[i] == 0
+        gt = g["trace_%d" % i]
+        tr = res["trace"][:gt.shape[0], i].cpu().numpy()
+        assert np.array_equal(tr, gt), "per-step next-word trace differs for image %d" % i
+        if gt.shape[0] < 51:
+            assert np.all(res["trace"][gt.shape[0]:, i].cpu().numpy() == -1)
+
+    # the drop-in single-image function: same signature / return tuple / per-step print as gen_captions.py:16-131
+    class Args:
+        beam_size = k
+
+    class Identity(torch.nn.Module):
+        def forward(self, x):
+            return x
+    i = 0
+    seq, alphas, ended = attention_caption_image_beam_search(cuda, Args, feats[i:i + 1], Identity(), dec, vocab)
+    printed = [ln for ln in capsys.readouterr().out.strip().split("\n") if ln]
+    assert ended == bool(g["ended_%d" % i]) and seq == list(g["seq_%d" % i])
+    gt = g["trace_%d" % i]
+    assert printed == [str([vocab.i2w[int(x)] for x in row if x >= 0]) for row in gt]
+    assert isinstance(alphas, list) and len(alphas) == len(seq) and len(alphas[0]) == 14 and len(alphas[0][0]) == 14
+    assert alphas[0][0][0] == 1.0
+
+
+def test_beam_search_failure_tuple_when_no_end(cuda):
+    """Default random init never emits <end> within 51 steps => ([start, end], [], False) (gen_captions.py:123-125)."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.gen_captions import attention_caption_image_beam_search
+    from icd_b200.vocabulary import synthetic_vocab
+    case = dict(H.BEAM_CASES["beam_small"], dropout=0.5, train=False, fine_tune_embedding=True)
+    vocab = synthetic_vocab(case["V"])
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams, vocab)
+    with torch.no_grad():
+        dec.fc.bias[case["V"] - 2] = -50.0
+    dec = dec.to(cuda)
+
+    class Args:
+        beam_size = 3
+
+    class Identity(torch.nn.Module):
+        def forward(self, x):
+            return x
+    feats = H.beam_features(case)[:1].to(cuda)
+    seq, alphas, ended = attention_caption_image_beam_search(cuda, Args, feats, Identity(), dec, vocab)
+    assert (seq, alphas, ended) == ([case["V"] - 3, case["V"] - 2], [], False)
+
+
+def test_full_size_properties_config3_shape(cuda):
+    """BASELINE config-3 shape (B=64 slice of the 512 batch to bound test time), properties that do not need the
+    oracle: softmax rows sum to 1, masked rows are zero, batch rows are independent (a row's outputs do not depend on
+    which other rows share the batch), the gradient of a sum over a split batch adds up."""
+    import icd_b200.models.attention as my_att
+    from icd_b200 import synthetic
+    from icd_b200.vocabulary import synthetic_vocab
+    V = 9490
+    p = my_att.AttentionDecoderParams()
+    p.vocab = synthetic_vocab(V)
+    p.dropout = 0.0
+    torch.manual_seed(0)
+    dec = my_att.AttentionDecoder(cuda, p).to(cuda)
+    dec.fine_tune_embeddings(False)
+    B = 64
+    enc = synthetic.features(B).to(cuda)
+    caps, lens = synthetic.captions(B, V, max_len=25, lengths="ragged")
+    caps = caps.to(cuda)
+    preds, _, dl, alphas = dec(enc, caps, lens)
+    assert preds.shape == (B, 24, V) and alphas.shape == (B, 24, 196)
+    for b, l in enumerate(dl):
+        assert torch.all(preds[b, l:] == 0) and torch.all(alphas[b, l:] == 0)
+        assert torch.allclose(alphas[b, :l].sum(-1), torch.ones(l, device=cuda), atol=1e-5)
+    loss = O.attention_loss(preds, caps, dl, alphas)
+    loss.backward()
+    g_full = {k: v.grad.clone() for k, v in dec.named_parameters() if v.grad is not None}
+    # row independence: first 16 rows alone give the same logits
+    with torch.no_grad():
+        p16, _, dl16, a16 = dec(enc[:16], caps[:16], lens[:16])
+    H.assert_close_norm(p16, preds[:16, :max(dl16)], 1e-5, "row independence (predictions)")
+    H.assert_close_norm(a16, alphas[:16, :max(dl16)], 1e-5, "row independence (alphas)")
+    # additivity over a batch split (what data parallelism relies on): sum-reduced losses
+    dec.zero_grad()
+    parts = []
+    for sl in (slice(0, 32), slice(32, 64)):
+        pp, _, dd, aa = dec(enc[sl], caps[sl], lens[sl])
+        parts.append((pp * pp).sum() + (aa * aa).sum())
+        parts[-1].backward()
+    g_split = {k: v.grad.clone() for k, v in dec.named_parameters() if v.grad is not None}
+    dec.zero_grad()
+    pp, _, dd, aa = dec(enc, caps, lens)
+    ((pp * pp).sum() + (aa * aa).sum()).backward()
+    for k, v in dec.named_parameters():
+        if v.grad is None or k == "attention.full_att.bias":
+            continue
+        H.assert_close_norm(g_split[k], v.grad, 1e-3, "split-batch additivity " + k)
+    assert set(g_full) == set(g_split)

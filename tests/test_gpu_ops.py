@@ -1,0 +1,185 @@
+"""GPU tier, op level: every C-ABI kernel entry point against the oracle / an fp64 torch restatement of the same op.
+Tolerances (fp32 tier): 1e-5 norm-wise for contractions and pointwise ops unless stated."""
+import pytest
+import torch
+
+import helpers as H
+from oracle import decoders as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from icd_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (37, 131, 77), (128, 128, 16), (200, 9490, 512), (5, 2048, 300),
+                                   (513, 259, 1030)])
+def test_gemm_nt_matches_fp64(cuda, M, N, K):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g).to(cuda)
+    b = torch.randn(N, K, generator=g).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    c = ops.gemm(a, b, bias1=bias)
+    ref = a.double() @ b.double().t() + bias.double()
+    H.assert_close_norm(c, ref, 1e-5, "gemm NT %dx%dx%d" % (M, N, K))
+
+
+def test_gemm_transposed_operand_forms(cuda):
+    """The three layouts the backward uses: dX = dY W (B n-contiguous), dW = dY^T X (both row-contiguous)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 150, 70, 260
+    dy = torch.randn(M, N, generator=g).to(cuda)
+    w = torch.randn(N, K, generator=g).to(cuda)
+    x = torch.randn(M, K, generator=g).to(cuda)
+    # dX[M,K] = dY[M,N] W[N,K]:  A = dY (k-contig), B(n=k_in, k=n_out) = W[n_out*K + k_in] -> (sbn, sbk) = (1, K)
+    dx = ops.gemm(dy, w, b_strides=(1, K), M=M, N=K, K=N)
+    H.assert_close_norm(dx, dy.double() @ w.double(), 1e-5, "gemm NN")
+    # dW[N,K] = dY^T X: A(m=n_out, k=row) = dY[row*N + n_out] -> (1, N); B(n=k_in, k=row) = X[row*K + k_in] -> (1, K)
+    dw = ops.gemm(dy, x, a_strides=(1, N), b_strides=(1, K), M=N, N=K, K=M)
+    H.assert_close_norm(dw, dy.double().t() @ x.double(), 1e-5, "gemm TN")
+    # A row-contiguous with B k-contiguous
+    at = torch.randn(K, M, generator=g).to(cuda)           # A(m,k) = at[k*M + m]
+    c = ops.gemm(at, w, a_strides=(1, M), M=M, N=N, K=K)
+    H.assert_close_norm(c, at.double().t() @ w.double().t(), 1e-5, "gemm TN' ")
+
+
+def test_gemm_split_k_and_epilogue(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    M, N, K = 96, 200, 8192                      # few tiles, long K -> split-K path with atomics
+    a = torch.randn(M, K, generator=g).to(cuda)
+    b = torch.randn(N, K, generator=g).to(cuda)
+    b1 = torch.randn(N, generator=g).to(cuda)
+    b2 = torch.randn(N, generator=g).to(cuda)
+    add1 = torch.randn(M, N + 8, generator=g).to(cuda)
+    add2 = torch.randn(M, N, generator=g).to(cuda)
+    mask = (torch.rand(M, generator=g) > 0.3).to(torch.uint8).to(cuda)
+    c = ops.gemm(a, b, bias1=b1, bias2=b2, add1=add1, ld1=N + 8, add2=add2, ld2=N, row_mask=mask)
+    ref = a.double() @ b.double().t() + b1.double() + b2.double() + add1[:, :N].double() + add2.double()
+    ref = ref * mask.double().unsqueeze(1)
+    H.assert_close_norm(c, ref, 1e-5, "gemm split-k epilogue")
+    assert torch.all(c[mask == 0] == 0)
+    # beta accumulate into a strided output slice, unaligned N
+    Ms, Ns, Ks = 33, 45, 64
+    a = torch.randn(Ms, Ks, generator=g).to(cuda)
+    b = torch.randn(Ns, Ks, generator=g).to(cuda)
+    big = torch.randn(Ms, 101, generator=g).to(cuda)
+    want = big.double().clone()
+    want[:, 7:7 + Ns] += a.double() @ b.double().t()
+    ops.gemm(a, b, out=big[:, 7:], ldc=101, M=Ms, N=Ns, K=Ks, beta=1.0)
+    H.assert_close_norm(big, want, 1e-5, "gemm beta/ldc")
+
+
+@pytest.mark.parametrize("R,A,Cdim,use_index", [(3, 48, 2048, False), (7, 512, 2048, True), (1, 64, 256, False)])
+def test_attention_step_fwd_bwd_matches_oracle_autograd(cuda, R, A, Cdim, use_index):
+    ops = _ops()
+    g = torch.Generator().manual_seed(R * 11 + A)
+    P = 196
+    n_img = 3 if use_index else R
+    enc = torch.randn(n_img, P, Cdim, generator=g).clamp_min_(0)
+    att_enc = torch.randn(n_img, P, A, generator=g) * 0.5
+    att_dec = (torch.randn(R, A, generator=g) * 0.5).requires_grad_(True)
+    wf = (torch.randn(A, generator=g) * 0.2).requires_grad_(True)
+    bf = torch.randn(1, generator=g).requires_grad_(True)
+    fb = torch.randn(R, Cdim, generator=g).requires_grad_(True)
+    idx = torch.randint(0, n_img, (R,), generator=g) if use_index else torch.arange(R)
+    # oracle (fp64): models/attention.py:56-60, 270-271 with att_enc / att_dec given
+    e64, ae64 = enc.double()[idx], att_enc.double()[idx].requires_grad_(True)
+    ad64, wf64, bf64, fb64 = (t.detach().double().requires_grad_(True) for t in (att_dec, wf, bf, fb))
+    att = (torch.relu(ae64 + ad64.unsqueeze(1)) * wf64).sum(-1) + bf64
+    alpha64 = torch.softmax(att, dim=1)
+    awe64 = (e64 * alpha64.unsqueeze(2)).sum(1)
+    gate64 = torch.sigmoid(fb64)
+    gated64 = gate64 * awe64
+    img_index = idx.to(torch.int32).to(cuda) if use_index else None
+    alpha, awe, gate, gated = ops.attention_step_fwd(enc.to(cuda), att_enc.to(cuda), att_dec.detach().to(cuda),
+                                                     wf.detach().to(cuda), bf.detach().to(cuda),
+                                                     fb.detach().to(cuda), img_index)
+    H.assert_close_norm(alpha, alpha64, 1e-5, "alpha")
+    H.assert_close_norm(awe, awe64, 1e-5, "awe")
+    H.assert_close_norm(gate, gate64, 1e-5, "gate")
+    H.assert_close_norm(gated, gated64, 1e-5, "gated")
+    assert torch.allclose(alpha.sum(1).cpu(), torch.ones(R), atol=1e-5)
+    if use_index:
+        return
+    # backward: upstream gradients on gated and directly on alpha
+    d_gated = torch.randn(R, Cdim, generator=g)
+    d_alpha = torch.randn(R, P, generator=g)
+    ((gated64 * d_gated.double()).sum() + (alpha64 * d_alpha.double()).sum()).backward()
+    d_att_dec, d_fb, d_e = ops.attention_step_bwd(enc.to(cuda), att_enc.to(cuda), att_dec.detach().to(cuda),
+                                                  wf.detach().to(cuda), alpha, gate, awe, d_gated.to(cuda),
+                                                  d_alpha.to(cuda))
+    H.assert_close_norm(d_att_dec, ad64.grad, 2e-5, "d_att_dec")
+    H.assert_close_norm(d_fb, fb64.grad, 2e-5, "d_fbeta_pre")
+    d_att_enc, d_wf, d_bf = ops.attention_proj_bwd(att_enc.to(cuda), att_dec.detach().to(cuda).view(1, R, A),
+                                                   wf.detach().to(cuda), d_e.view(R, 1, P), [R])
+    H.assert_close_norm(d_att_enc, ae64.grad, 2e-5, "d_att_enc")
+    H.assert_close_norm(d_wf, wf64.grad, 2e-5, "d_w_full")
+    H.assert_close_norm(d_bf, bf64.grad, 1e-4, "d_b_full", atol=1e-5)
+
+
+def test_init_hidden_state_matches_oracle(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    B, P, C, D = 5, 196, 2048, 64
+    enc = torch.randn(B, P, C, generator=g).clamp_min_(0)
+    w = {"h_lin.weight": torch.randn(D, C, generator=g) * 0.02, "h_lin.bias": torch.randn(D, generator=g),
+         "c_lin.weight": torch.randn(D, C, generator=g) * 0.02, "c_lin.bias": torch.randn(D, generator=g)}
+    h64, c64 = O.init_hidden_state({k: v.double() for k, v in w.items()}, enc.double())
+    h, c, mean = ops.init_hidden_state(enc.to(cuda), *(w[k].to(cuda) for k in
+                                                        ("h_lin.weight", "h_lin.bias", "c_lin.weight", "c_lin.bias")))
+    H.assert_close_norm(mean, enc.double().mean(1), 1e-6, "mean")
+    H.assert_close_norm(h, h64, 1e-5, "h0")
+    H.assert_close_norm(c, c64, 1e-5, "c0")
+
+
+def test_dropout_mask_statistics_and_determinism(cuda):
+    ops = _ops()
+    m1 = ops.dropout_mask((24, 64, 512), 0.5, seed=1234, device=cuda)
+    m2 = ops.dropout_mask((24, 64, 512), 0.5, seed=1234, device=cuda)
+    m3 = ops.dropout_mask((24, 64, 512), 0.5, seed=1235, device=cuda)
+    assert torch.equal(m1, m2) and not torch.equal(m1, m3)
+    assert set(m1.unique().tolist()) <= {0, 1}
+    assert abs(m1.float().mean().item() - 0.5) < 5e-3
+    keep = ops.dropout_mask((1 << 20,), 0.2, seed=7, device=cuda).float().mean().item()
+    assert abs(keep - 0.8) < 5e-3
+
+
+def test_clip_adam_matches_torch_adam_with_clamp(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(2)
+    p0 = torch.randn(10007, generator=g)
+    p_ref = torch.nn.Parameter(p0.clone().double())
+    opt = torch.optim.Adam([p_ref], lr=1e-3)
+    p = p0.clone().to(cuda)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    for step in range(1, 6):
+        grad = torch.randn(10007, generator=g) * 10.0            # many entries beyond +-5
+        p_ref.grad = grad.double().clamp(-5, 5)                  # train_utils.py:12
+        opt.step()
+        ops.clip_adam_step(p, grad.to(cuda), m, v, step, lr=1e-3, grad_clip=5.0)
+    H.assert_close_norm(p, p_ref.data, 1e-6, "adam params")
+
+
+def test_cross_entropy_matches_torch(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    R, V = 37, 9490
+    x = torch.randn(R, V, generator=g) * 3
+    t = torch.randint(0, V, (R,), generator=g)
+    t[5] = -1
+    t[11] = -1
+    x64 = x.double().requires_grad_(True)
+    valid = t >= 0
+    loss64 = torch.nn.functional.cross_entropy(x64[valid], t[valid], reduction="sum")
+    n = int(valid.sum())
+    (loss64 / n).backward()
+    row_loss, dx = ops.cross_entropy_fwd_bwd(x.to(cuda), t.to(cuda), 1.0 / n)
+    assert abs(row_loss.sum().item() - loss64.item()) < 1e-5 * abs(loss64.item())
+    H.assert_close_norm(dx, x64.grad, 1e-5, "d_logits")
+    assert torch.all(dx[5] == 0) and torch.all(dx[11] == 0)

@@ -1,0 +1,151 @@
+"""CPU tier: the oracle (oracle/decoders.py) against the golden vectors generated from the unmodified reference
+(tests/golden/make_golden.py).  Also checks that the icd_b200 module constructors reproduce the reference's
+seeded initialisation (weight checksums stored with every golden)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle import decoders as O
+
+import icd_b200.models.attention as my_att
+import icd_b200.models.baseline as my_base
+from icd_b200.vocabulary import synthetic_vocab
+
+
+def load(name):
+    return np.load(os.path.join(H.GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+
+
+def check_weights(module, g):
+    cs = H.state_checksums(module)
+    assert list(cs.keys()) == [str(k) for k in g["weight_keys"]]
+    assert list(cs.values()) == [str(v) for v in g["weight_checksums"]]
+
+
+def compare(case, g, name, t, tol, atol=0.0):
+    if case["store"] == "full":
+        H.assert_close_norm(t, torch.from_numpy(g[name]), tol, name, atol)
+    else:
+        H.assert_digest_close(name, t, dict(norm=g[name + "@norm"], samples=g[name + "@samples"]), tol, atol)
+
+
+@pytest.mark.parametrize("name", list(H.ATT_CASES))
+def test_attention_oracle_matches_reference_golden(name):
+    case = H.ATT_CASES[name]
+    if name == "att_cfg1":
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+    g = load(name)
+    mine = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams,
+                                    synthetic_vocab(case["V"]))
+    check_weights(mine, g)
+    enc, caps, lens = H.att_inputs(case)
+    frozen = () if case["fine_tune_embedding"] else ("embedding.weight",)
+    w = {k: v.detach().clone().requires_grad_(k not in frozen) for k, v in mine.state_dict().items()}
+    masks = None
+    dl = [l - 1 for l in lens]
+    if case["train"]:
+        masks = H.dropout_masks_like_reference(case, dl, case["D"])
+    preds, caps_out, odl, alphas = O.attention_decoder_forward(w, enc, caps, lens, dropout_p=case["dropout"],
+                                                               dropout_masks=masks)
+    assert caps_out is caps and odl == list(g["decode_lengths"])
+    compare(case, g, "predictions", preds, 1e-6)
+    compare(case, g, "alphas", alphas, 1e-6)
+    if case.get("loss", True):
+        loss = O.attention_loss(preds, caps, odl, alphas)
+        assert abs(loss.item() - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+        ids = O.teacher_forced_ids(preds, odl)
+        gold = g["greedy_ids"]
+        for j, row in enumerate(ids):
+            assert row == list(gold[j, :len(row)])
+    else:
+        gen = torch.Generator().manual_seed(case["iseed"] + 1000)
+        g1 = torch.randn(preds.shape, generator=gen)
+        g2 = torch.randn(alphas.shape, generator=gen)
+        loss = (preds * g1).sum() + (alphas * g2).sum()
+    loss.backward()
+    for k in [str(x) for x in g["grad_names"]]:
+        tol, atol = (1e-5, 0.0)
+        if k == "attention.full_att.bias":
+            tol, atol = (0.0, 1e-6)          # true value is identically 0
+        compare(case, g, "grad:" + k, w[k].grad, tol, atol)
+    if not case["fine_tune_embedding"]:
+        assert "embedding.weight" not in [str(x) for x in g["grad_names"]]
+
+
+def test_hoisted_restatement_equals_per_step_recompute():
+    """enc_att(encoder_out) hoisted out of the loop (what the kernels do) == per-step recompute (reference)."""
+    case = H.ATT_CASES["att_small_ragged"]
+    mine = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams,
+                                    synthetic_vocab(case["V"]))
+    enc, caps, lens = H.att_inputs(case)
+    w = O.cast_weights(mine.state_dict(), torch.float32)
+    p1, _, _, a1 = O.attention_decoder_forward(w, enc, caps, lens)
+    p2, _, _, a2 = O.attention_decoder_forward(w, enc, caps, lens, hoist=True)
+    H.assert_close_norm(p2, p1, 1e-6, "hoisted predictions")
+    H.assert_close_norm(a2, a1, 1e-6, "hoisted alphas")
+
+
+def test_fp64_oracle_is_close_to_fp32_reference():
+    case = H.ATT_CASES["att_small_ragged"]
+    g = load("att_small_ragged")
+    mine = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams,
+                                    synthetic_vocab(case["V"]))
+    enc, caps, lens = H.att_inputs(case)
+    w64 = O.cast_weights(mine.state_dict(), torch.float64)
+    preds, _, _, alphas = O.attention_decoder_forward(w64, enc.double(), caps, lens)
+    H.assert_close_norm(preds, torch.from_numpy(g["predictions"]), 1e-5, "fp64 vs reference fp32 predictions")
+    H.assert_close_norm(alphas, torch.from_numpy(g["alphas"]), 1e-5, "fp64 vs reference fp32 alphas")
+
+
+@pytest.mark.parametrize("name", list(H.BASE_CASES))
+def test_baseline_oracle_matches_reference_golden(name):
+    case = H.BASE_CASES[name]
+    g = load(name)
+    mine = H.build_baseline_module(case, my_base.BaselineDecoder, my_base.BaselineDecoderParams)
+    check_weights(mine, g)
+    img, caps, lens = H.base_inputs(case)
+    w = {k: v.detach().clone().requires_grad_(True) for k, v in mine.state_dict().items()}
+    img = img.clone().requires_grad_(True)
+    outs = O.baseline_decoder_forward(w, img, caps)
+    compare(case, g, "outputs", outs, 2e-6)
+    loss = O.baseline_loss(outs, caps)
+    assert abs(loss.item() - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    loss.backward()
+    for k in [str(x) for x in g["grad_names"]]:
+        gr = img.grad if k == "img_features" else w[k].grad
+        compare(case, g, "grad:" + k, gr, 2e-5)
+
+
+@pytest.mark.parametrize("name", list(H.BEAM_CASES))
+def test_beam_oracle_matches_reference_golden(name):
+    case = H.BEAM_CASES[name]
+    g = load(name)
+    acase = dict(case, dropout=0.5, train=False, fine_tune_embedding=True)
+    mine = H.build_attention_module(acase, my_att.AttentionDecoder, my_att.AttentionDecoderParams,
+                                    synthetic_vocab(case["V"]))
+    H.apply_beam_recipe(mine, case)
+    check_weights(mine, g)
+    feats = H.beam_features(case)
+    V = case["V"]
+    w = O.cast_weights(mine.state_dict(), torch.float32)
+    n = case["n_img"] if name == "beam_small" else 3          # full-size case: a subset keeps the CPU tier fast
+    for i in range(n):
+        trace = []
+        seq, alphas, ended = O.beam_search(w, feats[i:i + 1], case["k"], V - 3, V - 2, trace=trace)
+        assert seq == list(g["seq_%d" % i]) and ended == bool(g["ended_%d" % i])
+        gt = g["trace_%d" % i]
+        assert len(trace) == gt.shape[0]
+        for s, words in enumerate(trace):
+            assert words == [x for x in gt[s] if x >= 0]
+        if alphas:
+            assert np.abs(np.asarray(alphas, dtype=np.float32) - g["alphas_%d" % i]).max() < 1e-6
+
+
+def test_pinning_report_present():
+    rep = json.load(open(os.path.join(H.GOLDEN_DIR, "PINNING.json")))
+    for name in list(H.ATT_CASES) + list(H.BASE_CASES) + list(H.BEAM_CASES):
+        assert name in rep
