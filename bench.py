@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py — attention-decoder train-step throughput (captions/s) on N B200 of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision fp32|bf16|auto]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): basic_att AttentionDecoder,
+A = D = E = 512, V = 9490, batch 512 captions PER GPU, all captions 25 tokens (T = 24 decode steps — the reference's
+own training regime), synthetic 14x14x2048 features, random-init weights, embedding frozen,
+dropout 0.5 in train mode.  One step = forward + loss (models/attention.py:401-414) + backward + gradient
+all-reduce (N > 1) + clamp(+-5) + Adam(1e-4).  Weak scaling: per-GPU work is fixed.
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM; `e2e`: the same step driven from pinned HOST
+buffers through the public module API, H2D copies of features+captions and the D2H read of the loss inside the timed
+region.  `roofline`: the fused attention-step forward kernel (HBM-bound), algorithmic bytes / live CUDA-event time.
+`cpu_baseline` / `--impl reference`: the reference algorithm (oracle/decoders.py, per-step enc_att recompute as at
+models/attention.py:54) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+V, A, D, E, P, C, MAXLEN = 9490, 512, 512, 512, 196, 2048, 25
+B_PER_GPU = 512
+CPU_SAMPLE_B = 32
+# fused attention step, forward, fp32 features: P*C*4 + P*A*4 + (A + C + C + P)*4 per (image, step)
+ATT_FWD_BYTES_PER_ROW = P * C * 4 + P * A * 4 + (A + C + C + P) * 4        # = 2 026 256
+ATT_BWD_BYTES_PER_ROW = P * C * 4 + P * A * 4 + (3 * C + 2 * A + 3 * P + C) * 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="icd_b200", choices=["icd_b200", "reference"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="captions per GPU (default: the benchmark config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference algorithm on the host cores (oracle port)
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps, warmup, sample_b=CPU_SAMPLE_B):
+    """Time `steps` train steps of the reference algorithm on a `sample_b`-caption slice of the benchmark batch."""
+    import torch
+    from icd_b200 import synthetic
+    from icd_b200.vocabulary import synthetic_vocab
+    import icd_b200.models.attention as my_att
+    from oracle import decoders as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p = my_att.AttentionDecoderParams()
+    p.vocab = synthetic_vocab(V)
+    torch.manual_seed(0)
+    dec = my_att.AttentionDecoder(torch.device("cpu"), p)       # used as a seeded weight container only
+    dec.fine_tune_embeddings(False)
+    w = {k: v.detach().clone().requires_grad_(k != "embedding.weight") for k, v in dec.state_dict().items()}
+    params = [t for t in w.values() if t.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-4)
+    enc = synthetic.features(sample_b)
+    caps, lens = synthetic.captions(sample_b, V, max_len=MAXLEN)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        dl = [l - 1 for l in lens]
+        masks = [(torch.rand(sum(x > t for x in dl), D) >= 0.5).float() for t in range(max(dl))]
+        preds, _, dl, alphas = O.attention_decoder_forward(w, enc, caps, lens, dropout_p=0.5, dropout_masks=masks)
+        loss = O.attention_loss(preds, caps, dl, alphas)
+        opt.zero_grad()
+        loss.backward()
+        for t in params:
+            t.grad.clamp_(-5.0, 5.0)
+        opt.step()
+        loss.item()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return dict(value=sample_b * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores,
+                sample="%d-caption slice of the %d-caption batch, T=24, V=%d, %d timed steps" %
+                       (sample_b, B_PER_GPU, V, len(times)))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_steps(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "attention-decoder train-step captions/s", "value": r["value"],
+        "unit": "captions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, "fp32", B_PER_GPU),
+        "cpu_baseline": {"value": r["value"], "unit": "captions/s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n, precision, batch):
+    return {"workload": "configs[2]: basic_att attention decoder train step, batch %d/GPU, T=24 (25-token captions), "
+                        "V=9490, A=D=E=512, 14x14x2048 synthetic features, embedding frozen, dropout 0.5" % batch,
+            "global_batch": batch * n, "per_gpu_batch": batch, "decode_steps": 24, "vocab": V,
+            "gemm_precision": precision, "parallelism": "dp%d" % n,
+            "l2": "inputs_exceed_l2 (822 MB of features per step vs 126 MB L2; no explicit flush)"}
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def window(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        for t, ln in self.rows:
+            if t < t0 or t > t1:
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes read+write per launch of the fused attention-step forward kernel from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get("att_step_fwd_kernel_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    assert torch.cuda.is_available(), "bench.py needs a GPU (the decoder has no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+
+    from icd_b200 import ops, synthetic
+    from icd_b200._lib import lib
+    from icd_b200.losses import attention_caption_loss
+    from icd_b200.parallel import DataParallelClipAdam
+    from icd_b200.vocabulary import synthetic_vocab
+    import icd_b200.models.attention as my_att
+
+    precision = args.precision
+    if precision == "auto":
+        precision = "bf16" if lib().icd_has_tensor_core_gemm() else "fp32"
+    B = args.batch
+    p = my_att.AttentionDecoderParams()
+    p.vocab = synthetic_vocab(V)
+    torch.manual_seed(0)
+    dec = my_att.AttentionDecoder(dev, p)
+    dec.fine_tune_embeddings(False)                      # basic_att: --fine_tune_embedding defaults to False
+    dec = dec.to(dev)
+    dec.precision = precision
+    dec.train()
+    opt = DataParallelClipAdam(dec, lr=1e-4, grad_clip=5.0)
+    torch.manual_seed(1234 + rank)
+
+    # pinned host copies of this rank's shard (synthetic; each rank a different seed) + resident device copies
+    enc_h = synthetic.features(B, seed=1234 + rank).pin_memory()
+    caps_h, lens = synthetic.captions(B, V, max_len=MAXLEN, seed=1234 + rank)
+    caps_h = caps_h.pin_memory()
+    enc_d = enc_h.to(dev, non_blocking=True)
+    caps_d = caps_h.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+
+    def train_step(enc, caps):
+        preds, caps_sorted, dl, alphas = dec(enc, caps, lens)
+        loss = attention_caption_loss(preds, caps_sorted, dl, alphas, alpha_c=1.0)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    for _ in range(max(args.warmup, 3)):
+        train_step(enc_d, caps_d)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.3)
+    ops.prof_enable(True)
+    launches0 = ops.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        loss = train_step(enc_d, caps_d)
+    ev1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = ops.launch_count() - launches0
+    prof = ops.prof_collect()
+    ops.prof_enable(False)
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    last_loss = float(loss.item())
+
+    # ---- end-to-end timing: host buffers -> H2D -> step -> D2H loss, copies inside the timed region,
+    #      next batch prefetched on a side stream while the current step computes ----
+    e2e = None
+    if not args.no_e2e:
+        copy_stream = torch.cuda.Stream()
+        bufs = [(torch.empty_like(enc_d), torch.empty_like(caps_d)) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[i % 2])            # buffer free again?
+                bufs[i % 2][0].copy_(enc_h, non_blocking=True)
+                bufs[i % 2][1].copy_(caps_h, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        def e2e_loop(n):
+            for d_ in done:
+                d_.record()
+            prefetch(0)
+            out = 0.0
+            for i in range(n):
+                if i + 1 < n:
+                    prefetch(i + 1)
+                torch.cuda.current_stream().wait_event(ready[i % 2])
+                l = train_step(*bufs[i % 2])
+                done[i % 2].record()
+                out = l.item()                                   # D2H read of the step's loss (sync, as the reference does)
+            return out
+        e2e_loop(2)
+        barrier()
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev2.record()
+        e2e_loop(args.steps)
+        ev3.record()
+        barrier()
+        ms2 = torch.tensor([ev2.elapsed_time(ev3)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        e2e = {"value": B * world * args.steps / (float(ms2.item()) / 1e3), "unit": "captions/s",
+               "h2d_bytes_per_step": int(enc_h.numel() * 4 + caps_h.numel() * 8), "d2h_bytes_per_step": 4,
+               "ms_per_step": float(ms2.item()) / args.steps,
+               "note": "per GPU: pinned fp32 features + int64 captions copied H2D every step on a side stream "
+                       "(double-buffered), loss.item() every step"}
+
+    clocks = sampler.window(t_wall0, t_wall1) if sampler else None
+    if sampler:
+        sampler.stop()
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        fwd_s = prof["fwd_ms"] / 1e3
+        achieved = (ATT_FWD_BYTES_PER_ROW * prof["fwd_rows"] / fwd_s / 1e9) if fwd_s > 0 else None
+        bwd_s = prof["bwd_ms"] / 1e3
+        achieved_bwd = (ATT_BWD_BYTES_PER_ROW * prof["bwd_rows"] / bwd_s / 1e9) if bwd_s > 0 else None
+        line = {
+            "metric": "attention-decoder train-step captions/s",
+            "value": B * world * args.steps / (ms_total / 1e3), "unit": "captions/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+            "config": workload_config(world, precision, B),
+            "loss": last_loss,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {
+                "kernel": "att_step_fwd_kernel (fused additive-attention step, forward)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(),
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_row": ATT_FWD_BYTES_PER_ROW,
+                "launches": prof["fwd_launches"], "avg_launch_ms": (prof["fwd_ms"] / prof["fwd_launches"]) if prof["fwd_launches"] else None,
+                "share_of_step": (prof["fwd_ms"] / ms_total) if ms_total else None,
+                "bwd": {"kernel": "att_step_bwd_kernel", "achieved": achieved_bwd,
+                        "frac": (achieved_bwd / peak) if achieved_bwd else None,
+                        "algorithmic_bytes_per_row": ATT_BWD_BYTES_PER_ROW,
+                        "share_of_step": (prof["bwd_ms"] / ms_total) if ms_total else None},
+            },
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_steps(steps=2, warmup=1)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "captions/s", "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

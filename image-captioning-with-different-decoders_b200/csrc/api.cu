@@ -10,7 +10,60 @@ void icd_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+long long g_icd_launches = 0;
+
+// ---- attention-step profiling: cudaEvent pairs recorded on the launching stream ---------------------
+namespace {
+constexpr int PROF_MAX = 8192;
+struct ProfRec { cudaEvent_t a, b; int dir, rows; };
+bool g_prof_on = false;
+ProfRec g_prof[PROF_MAX];
+int g_prof_n = 0, g_prof_created = 0;
+bool g_prof_open = false;
+}
+
+void icd_prof_mark_begin(int dir, int rows, cudaStream_t s) {
+    g_prof_open = false;
+    if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+    if (g_prof_n >= g_prof_created) {
+        if (cudaEventCreate(&g_prof[g_prof_n].a) != cudaSuccess || cudaEventCreate(&g_prof[g_prof_n].b) != cudaSuccess) return;
+        g_prof_created = g_prof_n + 1;
+    }
+    g_prof[g_prof_n].dir = dir; g_prof[g_prof_n].rows = rows;
+    cudaEventRecord(g_prof[g_prof_n].a, s);
+    g_prof_open = true;
+}
+
+void icd_prof_mark_end(int dir, cudaStream_t s) {
+    (void)dir;
+    if (!g_prof_open) return;
+    cudaEventRecord(g_prof[g_prof_n].b, s);
+    ++g_prof_n;
+    g_prof_open = false;
+}
+
 extern "C" {
+int64_t icd_launch_count(void) { return (int64_t)g_icd_launches; }
+
+int icd_prof_enable(int on) { g_prof_on = on != 0; if (!on) g_prof_n = 0; return 0; }
+
+int icd_prof_collect(double* fwd_ms, int64_t* fwd_launches, int64_t* fwd_rows,
+                     double* bwd_ms, int64_t* bwd_launches, int64_t* bwd_rows) {
+    double ms[2] = {0, 0}; int64_t n[2] = {0, 0}, rows[2] = {0, 0};
+    for (int i = 0; i < g_prof_n; ++i) {
+        cudaError_t e = cudaEventSynchronize(g_prof[i].b);
+        if (e != cudaSuccess) { icd_set_error("prof_collect: %s", cudaGetErrorString(e)); g_prof_n = 0; return (int)e; }
+        float t = 0.f;
+        e = cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b);
+        if (e != cudaSuccess) { icd_set_error("prof_collect: %s", cudaGetErrorString(e)); g_prof_n = 0; return (int)e; }
+        ms[g_prof[i].dir] += t; n[g_prof[i].dir] += 1; rows[g_prof[i].dir] += g_prof[i].rows;
+    }
+    g_prof_n = 0;
+    if (fwd_ms) *fwd_ms = ms[0]; if (fwd_launches) *fwd_launches = n[0]; if (fwd_rows) *fwd_rows = rows[0];
+    if (bwd_ms) *bwd_ms = ms[1]; if (bwd_launches) *bwd_launches = n[1]; if (bwd_rows) *bwd_rows = rows[1];
+    return 0;
+}
+
 int icd_version(void) { return ICD_B200_ABI_VERSION; }
 const char* icd_last_error_string(void) { return g_err; }
 int icd_sizeof_att_desc(void) { return (int)sizeof(icd_att_desc_t); }

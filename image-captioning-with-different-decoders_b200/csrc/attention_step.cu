@@ -21,18 +21,31 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// scores + softmax.  grid = rows, block = 256 (8 warps).  smem: 2*A + P + 40 floats.
+// Fused attention step, forward: ONE kernel per decode step.  grid = rows, block = 256 (8 warps).
+//   phase 1  scores: warp per pixel row of att_enc (A floats), two rows per iteration => 2*(A/128) independent
+//            128-bit loads in flight per lane; relu(att_enc + att_dec) . w_full via warp shuffle
+//   phase 2  softmax over the P scores in shared memory (expf, block reductions); alpha written out
+//   phase 3  awe[c] = sum_p alpha[p] * enc[p, c]: thread t owns float4 columns t and t+256 (C = 2048 => two
+//            columns), 2 x 4 independent 128-bit loads in flight, each pixel row read as two contiguous 4 KB runs
+//   epilogue gate = sigmoid(fbeta_pre), gated = gate * awe
+// Algorithmic bytes per row: P*A*4 (att_enc) + P*C*4 (enc) + small = 2 026 256 B for P=196, A=512, C=2048.
+// smem: 2*A + P + 40 floats.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) att_scores_softmax_kernel(
-        int P, int A, const int* __restrict__ img_index,
-        const float* __restrict__ att_enc, const float* __restrict__ att_dec, long long ld_dec,
+constexpr int FW_UNROLL = 4;
+
+__global__ void __launch_bounds__(256, 4) att_step_fwd_kernel(
+        int P, int C, int A, const int* __restrict__ img_index,
+        const float* __restrict__ enc, const float* __restrict__ att_enc,
+        const float* __restrict__ att_dec, long long ld_dec,
         const float* __restrict__ w_full, const float* __restrict__ b_full,
-        float* __restrict__ alpha, long long ld_alpha) {
+        const float* __restrict__ fbeta_pre, long long ld_fb,
+        float* __restrict__ alpha, long long ld_alpha,
+        float* __restrict__ awe_raw, float* __restrict__ gate, float* __restrict__ gated) {
     extern __shared__ __align__(16) float sm[];
     float* s_dec = sm;            // A
     float* s_wf = sm + A;         // A
-    float* s_e = sm + 2 * A;      // P
-    float* s_red = s_e + P;       // 40
+    float* s_e = sm + 2 * A;      // P  (scores, then alpha)
+    float* s_red = s_e + ((P + 3) & ~3);       // 40
     const int r = blockIdx.x;
     const int img = img_index ? img_index[r] : r;
     const float* ae = att_enc + (long long)img * P * A;
@@ -42,7 +55,6 @@ __global__ void __launch_bounds__(256) att_scores_softmax_kernel(
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const float bfull = b_full ? b_full[0] : 0.f;
     const int A4 = A >> 2;
-    // two pixel rows per warp iteration => 2 * (A/128) independent 128-bit loads in flight per lane
     for (int p = warp; p < P; p += 2 * nwarp) {
         const int p2 = p + nwarp;
         const bool has2 = p2 < P;
@@ -74,8 +86,63 @@ __global__ void __launch_bounds__(256) att_scores_softmax_kernel(
     float sum = 0.f;
     for (int p = threadIdx.x; p < P; p += blockDim.x) { const float ex = expf(s_e[p] - m); s_e[p] = ex; sum += ex; }
     sum = block_sum(sum, s_red);
-    float* out = alpha + (long long)r * ld_alpha;
-    for (int p = threadIdx.x; p < P; p += blockDim.x) out[p] = s_e[p] / sum;
+    {
+        float* out = alpha + (long long)r * ld_alpha;
+        for (int p = threadIdx.x; p < P; p += blockDim.x) { const float al = s_e[p] / sum; s_e[p] = al; out[p] = al; }
+    }
+    __syncthreads();
+
+    // phase 3: alpha-weighted sum over pixels, two float4 columns per thread per pass
+    const float* eb = enc + (long long)img * P * C;
+    const int stride = blockDim.x * 4;                         // 1024 floats between a thread's two columns
+    for (int c0 = threadIdx.x * 4; c0 < C; c0 += 2 * stride) {
+        const int c1 = c0 + stride;
+        const bool has1 = c1 < C;
+        const float* b0 = eb + c0;
+        const float* b1 = eb + (has1 ? c1 : c0);
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        int p = 0;
+        for (; p + FW_UNROLL <= P; p += FW_UNROLL) {
+            float4 x0[FW_UNROLL], x1[FW_UNROLL];
+#pragma unroll
+            for (int u = 0; u < FW_UNROLL; ++u) {
+                x0[u] = ld_stream_f4(b0 + (long long)(p + u) * C);
+                x1[u] = ld_stream_f4(b1 + (long long)(p + u) * C);
+            }
+#pragma unroll
+            for (int u = 0; u < FW_UNROLL; ++u) {
+                const float al = s_e[p + u];
+                a0.x = fmaf(al, x0[u].x, a0.x); a0.y = fmaf(al, x0[u].y, a0.y);
+                a0.z = fmaf(al, x0[u].z, a0.z); a0.w = fmaf(al, x0[u].w, a0.w);
+                a1.x = fmaf(al, x1[u].x, a1.x); a1.y = fmaf(al, x1[u].y, a1.y);
+                a1.z = fmaf(al, x1[u].z, a1.z); a1.w = fmaf(al, x1[u].w, a1.w);
+            }
+        }
+        for (; p < P; ++p) {
+            const float4 x0 = ld_stream_f4(b0 + (long long)p * C);
+            const float4 x1 = ld_stream_f4(b1 + (long long)p * C);
+            const float al = s_e[p];
+            a0.x = fmaf(al, x0.x, a0.x); a0.y = fmaf(al, x0.y, a0.y);
+            a0.z = fmaf(al, x0.z, a0.z); a0.w = fmaf(al, x0.w, a0.w);
+            a1.x = fmaf(al, x1.x, a1.x); a1.y = fmaf(al, x1.y, a1.y);
+            a1.z = fmaf(al, x1.z, a1.z); a1.w = fmaf(al, x1.w, a1.w);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !has1) break;
+            const int c = h ? c1 : c0;
+            const float4 acc = h ? a1 : a0;
+            const long long o = (long long)r * C + c;
+            if (awe_raw) *reinterpret_cast<float4*>(awe_raw + o) = acc;
+            if (fbeta_pre) {
+                const float4 f = *reinterpret_cast<const float4*>(fbeta_pre + (long long)r * ld_fb + c);
+                const float4 g = make_float4(sigmoidf_(f.x), sigmoidf_(f.y), sigmoidf_(f.z), sigmoidf_(f.w));
+                if (gate) *reinterpret_cast<float4*>(gate + o) = g;
+                if (gated) *reinterpret_cast<float4*>(gated + o) =
+                        make_float4(g.x * acc.x, g.y * acc.y, g.z * acc.z, g.w * acc.w);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -344,14 +411,6 @@ __global__ void att_proj_bwd_kernel(int B, int T, int P, int A, int len_b_unused
     if (threadIdx.x == 0) { mine[A] = tot; mine[A + 1] = 0.f; mine[A + 2] = 0.f; mine[A + 3] = 0.f; }
 }
 
-__global__ void row_len_from_bt_kernel(int B, int T, const int* __restrict__ bt, int* __restrict__ row_len) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    int n = 0;
-    for (int t = 0; t < T; ++t) n += (b < bt[t]) ? 1 : 0;    // bt is non-increasing, rows are a prefix
-    row_len[b] = n;
-}
-
 struct BtPack { int v[ICD_MAX_STEPS]; };
 __global__ void row_len_from_pack_kernel(int B, int T, const BtPack bt, int* __restrict__ row_len) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -390,15 +449,17 @@ extern "C" int icd_attention_step_fwd(int rows, int P, int C, int A, const int32
     ICD_CHECK_ARG(rows > 0 && P > 0 && C > 0 && A > 0, "attention_step_fwd: bad dims");
     ICD_CHECK_ARG(A % 4 == 0 && C % 4 == 0, "attention_step_fwd: A=%d and C=%d must be multiples of 4", A, C);
     ICD_CHECK_ARG(ld_dec % 4 == 0, "attention_step_fwd: ld_dec must be a multiple of 4");
-    const size_t smem = (2 * (size_t)A + P + 40) * sizeof(float);
+    ICD_CHECK_ARG(!fbeta_pre || ld_fb % 4 == 0, "attention_step_fwd: ld_fb must be a multiple of 4");
+    const size_t smem = (2 * (size_t)A + ((P + 3) & ~3) + 40) * sizeof(float);
     ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_fwd: A/P too large for shared memory");
     if (smem > 48 * 1024)
-        ICD_CUDA(cudaFuncSetAttribute(att_scores_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    att_scores_softmax_kernel<<<rows, 256, smem, s>>>(P, A, img_index, att_enc, att_dec, ld_dec, w_full, b_full,
-                                                       alpha, ld_alpha);
+        ICD_CUDA(cudaFuncSetAttribute(att_step_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    icd_prof_mark_begin(0, rows, s);
+    att_step_fwd_kernel<<<rows, 256, smem, s>>>(P, C, A, img_index, enc, att_enc, att_dec, ld_dec, w_full, b_full,
+                                                 fbeta_pre, ld_fb, alpha, ld_alpha, awe_raw, gate, gated);
+    icd_prof_mark_end(0, s);
     ICD_LAUNCH_CHECK();
-    return icd_weighted_pixel_sum(rows, P, C, img_index, enc, alpha, ld_alpha, fbeta_pre, ld_fb,
-                                  awe_raw, gate, gated, s);
+    return 0;
 }
 
 extern "C" int icd_attention_step_bwd(int rows, int P, int C, int A,
@@ -418,9 +479,11 @@ extern "C" int icd_attention_step_bwd(int rows, int P, int C, int A,
     ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_bwd: dims too large for shared memory");
     if (smem > 48 * 1024)
         ICD_CUDA(cudaFuncSetAttribute(att_step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    icd_prof_mark_begin(1, rows, s);
     att_step_bwd_kernel<<<rows, 256, smem, s>>>(P, C, A, enc, att_enc, att_dec, ld_dec, w_full, alpha, ld_alpha,
                                                  d_alpha_ext, ld_dalpha, gate, awe_raw, d_gated,
                                                  d_att_dec, ld_ddec, d_fbeta_pre, ld_dfb, d_e, ld_de);
+    icd_prof_mark_end(1, s);
     ICD_LAUNCH_CHECK();
     return 0;
 }

@@ -47,7 +47,7 @@ extern "C" int icd_baseline_decoder_bwd(const icd_base_desc_t* d, void* stream) 
     ICD_TRY(icd_gemm_simple(prec, d->d_outputs, V, 1, d->lin_w, 1, H, d->d_hout, H, B * L, H, V,
                             nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s));
     ICD_TRY(icd_gemm_simple(prec, d->d_outputs, 1, V, d->hout, 1, H, d->d_lin_w, H, V, H, B * L,
-                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s));
+                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s, ICD_GEMM_ALLOW_SPLITK));
     ICD_TRY(icd_colsum(d->d_outputs, V, (int64_t)B * L, V, nullptr, d->d_lin_b, s));
     // BPTT (:106)
     ICD_CUDA(cudaMemsetAsync(d->dh, 0, sizeof(float) * BH, s));
@@ -62,9 +62,9 @@ extern "C" int icd_baseline_decoder_bwd(const icd_base_desc_t* d, void* stream) 
     }
     // hoisted weight gradients
     ICD_TRY(icd_gemm_simple(prec, d->dg, 1, 4 * H, d->h_all, 1, H, d->d_w_hh, H, 4 * H, H, LB,
-                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s));
+                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s, ICD_GEMM_ALLOW_SPLITK));
     ICD_TRY(icd_gemm_simple(prec, d->dg, 1, 4 * H, d->x, 1, E, d->d_w_ih, E, 4 * H, E, LB,
-                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s));
+                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s, ICD_GEMM_ALLOW_SPLITK));
     ICD_TRY(icd_colsum(d->dg, 4 * H, LB, 4 * H, nullptr, d->d_b, s));
     if (d->d_img_features || d->d_emb_w) {
         ICD_TRY(icd_gemm_simple(prec, d->dg, 4 * H, 1, d->w_ih, 1, E, d->d_x, E, LB, E, 4 * H,

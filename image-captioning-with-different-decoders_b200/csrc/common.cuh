@@ -20,7 +20,8 @@ void icd_set_error(const char* fmt, ...);
         icd_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
         return (int)e_; } } while (0)
 
-#define ICD_LAUNCH_CHECK()  ICD_CUDA(cudaGetLastError())
+extern long long g_icd_launches;      // api.cu: kernels launched by this library (bench.py reports it)
+#define ICD_LAUNCH_CHECK()  do { ++g_icd_launches; ICD_CUDA(cudaGetLastError()); } while (0)
 
 #define ICD_TRY(call) do { int r_ = (call); if (r_ != 0) return r_; } while (0)
 
@@ -72,6 +73,10 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
+// attention-step profiling hooks (api.cu)
+void icd_prof_mark_begin(int dir, int rows, cudaStream_t s);
+void icd_prof_mark_end(int dir, cudaStream_t s);
+
 // ---- internal (non-exported) launchers shared between translation units -----------------------
 int icd_colsum(const float* X, int64_t ld, int64_t M, int N, const uint8_t* row_mask, float* out, cudaStream_t s);
 int icd_embed_gather(const void* table, int is_f64, const int64_t* captions, int B, int L, int T, int E,
@@ -92,4 +97,4 @@ int icd_weighted_pixel_sum(int rows, int P, int C, const int32_t* img_index, con
 int icd_gemm_simple(int prec, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
                     float* C, int64_t ldc, int M, int N, int K, const float* bias1, const float* bias2,
                     const float* add1, int64_t ld1, const float* add2, int64_t ld2, const uint8_t* row_mask,
-                    float beta, cudaStream_t s);
+                    float beta, cudaStream_t s, int flags = 0);

@@ -143,7 +143,7 @@ extern "C" int icd_attention_decoder_bwd(const icd_att_desc_t* d, void* stream) 
     ICD_TRY(icd_gemm_simple(prec, d->d_predictions, V, 1, d->fc_w, 1, D, d->d_hdrop, D, B * T, D, V,
                             nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s));
     ICD_TRY(icd_gemm_simple(prec, d->d_predictions, 1, V, d->hdrop, 1, D, d->d_fc_w, D, V, D, B * T,
-                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s));
+                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s, ICD_GEMM_ALLOW_SPLITK));
     ICD_TRY(icd_colsum(d->d_predictions, V, (int64_t)B * T, V, d->row_valid, d->d_fc_b, s));
 
     // ---- BPTT ----
@@ -174,23 +174,23 @@ extern "C" int icd_attention_decoder_bwd(const icd_att_desc_t* d, void* stream) 
 
     // ---- init_hidden_state (:161-163): dh, dc now hold d h0, d c0 ----
     ICD_TRY(icd_gemm_simple(prec, d->dh, 1, D, d->mean_enc, 1, C, d->d_h_lin_w, C, D, C, B,
-                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s));
+                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s, ICD_GEMM_ALLOW_SPLITK));
     ICD_TRY(icd_colsum(d->dh, D, B, D, nullptr, d->d_h_lin_b, s));
     ICD_TRY(icd_gemm_simple(prec, d->dc, 1, D, d->mean_enc, 1, C, d->d_c_lin_w, C, D, C, B,
-                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s));
+                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s, ICD_GEMM_ALLOW_SPLITK));
     ICD_TRY(icd_colsum(d->dc, D, B, D, nullptr, d->d_c_lin_b, s));
 
     // ---- hoisted weight gradients over the T*B stacked rows ----
     // d[W_dec; W_fbeta; W_hh] = dz^T * h_prev_all ; d[b_dec; b_fbeta; b_hh] = colsum(dz)
     ICD_TRY(icd_gemm_simple(prec, d->dz, 1, NZ, d->h_all, 1, D, d->d_w_cat, D, NZ, D, TB,
-                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s));
+                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s, ICD_GEMM_ALLOW_SPLITK));
     ICD_TRY(icd_colsum(d->dz, NZ, TB, NZ, nullptr, d->d_b_cat, s));
     // dW_ih = [dG^T * emb_x | dG^T * gated]
     const float* dG = d->dz + A + C;
     ICD_TRY(icd_gemm_simple(prec, dG, 1, NZ, d->emb_x, 1, E, d->d_w_ih, E + C, 4 * D, E, TB,
-                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s));
+                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s, ICD_GEMM_ALLOW_SPLITK));
     ICD_TRY(icd_gemm_simple(prec, dG, 1, NZ, d->gated, 1, C, d->d_w_ih + E, E + C, 4 * D, C, TB,
-                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s));
+                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s, ICD_GEMM_ALLOW_SPLITK));
     // embedding gradient (:247) when fine-tuned: d_emb_x = dG * W_ih[:, :E], scatter-added by token id
     if (d->d_emb_w) {
         ICD_TRY(icd_gemm_simple(prec, dG, NZ, 1, d->w_ih, 1, E + C, d->d_emb_x, E, TB, E, 4 * D,
@@ -203,6 +203,6 @@ extern "C" int icd_attention_decoder_bwd(const icd_att_desc_t* d, void* stream) 
                                    d->d_att_enc, d->d_full_att_w, d->d_full_att_b, d->proj_partial, stream));
     ICD_TRY(icd_colsum(d->d_att_enc, A, (int64_t)B * P, A, nullptr, d->d_enc_att_b, s));
     ICD_TRY(icd_gemm_simple(prec, d->d_att_enc, 1, A, d->enc, 1, C, d->d_enc_att_w, C, A, C, B * P,
-                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s));
+                            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s, ICD_GEMM_ALLOW_SPLITK));
     return 0;
 }

@@ -16,8 +16,9 @@ extern "C" int icd_gemm(const icd_gemm_desc_t* d, void* stream) {
 int icd_gemm_simple(int prec, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
                     float* C, int64_t ldc, int M, int N, int K, const float* bias1, const float* bias2,
                     const float* add1, int64_t ld1, const float* add2, int64_t ld2, const uint8_t* row_mask,
-                    float beta, cudaStream_t s) {
+                    float beta, cudaStream_t s, int flags) {
     icd_gemm_desc_t d;
+    d.flags = flags;
     d.A = A; d.sam = sam; d.sak = sak; d.B = B; d.sbn = sbn; d.sbk = sbk; d.C = C; d.ldc = ldc;
     d.M = M; d.N = N; d.K = K; d.bias1 = bias1; d.bias2 = bias2; d.add1 = add1; d.ld1 = ld1;
     d.add2 = add2; d.ld2 = ld2; d.row_mask = row_mask; d.beta = beta; d.precision = prec;

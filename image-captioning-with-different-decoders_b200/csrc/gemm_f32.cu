@@ -210,7 +210,7 @@ int icd_gemm_f32_launch(const icd_gemm_desc_t* d, cudaStream_t s) {
     const int gm = (d->M + BM - 1) / BM, gn = (d->N + BN - 1) / BN;
     int splitk = 1;
     const long long tiles = (long long)gm * gn;
-    if (d->beta == 0.f && d->K >= 2048 && tiles < ICD_NUM_SMS) {
+    if ((d->flags & ICD_GEMM_ALLOW_SPLITK) && d->beta == 0.f && d->K >= 2048 && tiles < ICD_NUM_SMS) {
         splitk = (int)((2 * ICD_NUM_SMS + tiles - 1) / tiles);
         const int maxs = d->K / 512;
         if (splitk > maxs) splitk = maxs;

@@ -33,7 +33,7 @@ def _f32c(t):
 
 def gemm(a, b, *, a_strides=None, b_strides=None, out=None, ldc=None, M=None, N=None, K=None,
          bias1=None, bias2=None, add1=None, ld1=0, add2=None, ld2=0, row_mask=None, beta=0.0,
-         precision="fp32"):
+         precision="fp32", flags=0):
     """C[M,N] = A[M,K] * B[N,K]^T + epilogue.  By default A is (M,K) row-major and B is (N,K) row-major
     (the nn.Linear layout: y = x W^T).  Explicit element strides (sam, sak)/(sbn, sbk) select the
     transposed forms used by the backward contractions."""
@@ -55,7 +55,7 @@ def gemm(a, b, *, a_strides=None, b_strides=None, out=None, ldc=None, M=None, N=
     d = _lib.GemmDesc()
     fill(d, A=a, sam=a_strides[0], sak=a_strides[1], B=b, sbn=b_strides[0], sbk=b_strides[1], C=out, ldc=ldc,
          M=M, N=N, K=K, bias1=bias1, bias2=bias2, add1=add1, ld1=ld1, add2=add2, ld2=ld2, row_mask=row_mask,
-         beta=float(beta), precision=precision_id(precision))
+         beta=float(beta), precision=precision_id(precision), flags=int(flags))
     check(lib().icd_gemm(ctypes.byref(d), stream_ptr()), "icd_gemm")
     return out
 
@@ -159,3 +159,22 @@ def cross_entropy_fwd_bwd(logits, targets, inv_count, want_grad=True):
                                           ptr(d_logits), ctypes.c_float(inv_count), stream_ptr()),
           "icd_cross_entropy_fwd_bwd")
     return row_loss, d_logits
+
+
+def launch_count():
+    """Kernels launched by libicd_b200.so in this process so far."""
+    return int(lib().icd_launch_count())
+
+
+def prof_enable(on):
+    check(lib().icd_prof_enable(int(bool(on))), "icd_prof_enable")
+
+
+def prof_collect():
+    """-> dict(fwd_ms, fwd_launches, fwd_rows, bwd_ms, bwd_launches, bwd_rows) for the attention-step kernels."""
+    f_ms, b_ms = ctypes.c_double(0), ctypes.c_double(0)
+    f_n, f_r, b_n, b_r = (ctypes.c_int64(0) for _ in range(4))
+    check(lib().icd_prof_collect(ctypes.byref(f_ms), ctypes.byref(f_n), ctypes.byref(f_r),
+                                 ctypes.byref(b_ms), ctypes.byref(b_n), ctypes.byref(b_r)), "icd_prof_collect")
+    return dict(fwd_ms=f_ms.value, fwd_launches=f_n.value, fwd_rows=f_r.value,
+                bwd_ms=b_ms.value, bwd_launches=b_n.value, bwd_rows=b_r.value)

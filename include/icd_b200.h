@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ICD_B200_ABI_VERSION 3
+#define ICD_B200_ABI_VERSION 4
 #define ICD_MAX_STEPS 256
 
 ICD_API int icd_version(void);                       /* ICD_B200_ABI_VERSION the library was built with */
@@ -45,6 +45,14 @@ ICD_API int icd_sizeof_att_desc(void);               /* sizeof(icd_att_desc_t)  
 ICD_API int icd_sizeof_base_desc(void);
 ICD_API int icd_sizeof_beam_desc(void);
 ICD_API int icd_has_tensor_core_gemm(void);          /* 1 if the tcgen05/TMA GEMM path was compiled in     */
+ICD_API int64_t icd_launch_count(void);              /* kernels launched by this library so far (process-wide) */
+
+/* Optional device-side timing of the attention-step kernels (bench.py's roofline line).  When enabled every
+ * icd_attention_step_fwd / _bwd launch is bracketed by a cudaEvent pair on its own stream; icd_prof_collect
+ * waits for the recorded events, sums elapsed milliseconds / launches / rows per direction and resets. */
+ICD_API int icd_prof_enable(int on);
+ICD_API int icd_prof_collect(double* fwd_ms, int64_t* fwd_launches, int64_t* fwd_rows,
+                     double* bwd_ms, int64_t* bwd_launches, int64_t* bwd_rows);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense contraction  C[M,N] = A[M,K] * B[N,K]^T (+ epilogue), fp32 storage.
@@ -59,6 +67,9 @@ ICD_API int icd_has_tensor_core_gemm(void);          /* 1 if the tcgen05/TMA GEM
  * ---------------------------------------------------------------------------------------------- */
 #define ICD_PREC_FP32 0
 #define ICD_PREC_BF16 1
+/* allow split-K with atomic accumulation (run-to-run summation order not fixed): used only for the weight-gradient
+ * contractions whose M x N is small and K = B*T or B*196; every forward contraction is deterministic */
+#define ICD_GEMM_ALLOW_SPLITK 1
 
 typedef struct {
     const float* A; int64_t sam, sak;
@@ -71,6 +82,7 @@ typedef struct {
     const uint8_t* row_mask;
     float beta;
     int32_t precision;
+    int32_t flags;                /* ICD_GEMM_* bits */
 } icd_gemm_desc_t;
 
 ICD_API int icd_gemm(const icd_gemm_desc_t* d, void* stream);

@@ -79,8 +79,10 @@ def test_attention_decoder_matches_reference_golden(cuda, name):
     compare(case, g, "predictions", preds, 1e-4)
     compare(case, g, "alphas", alphas, 1e-4)
     # rows >= batch_size_t are exactly zero (models/attention.py:253-258)
-    for b, l in enumerate(dl):
-        assert torch.all(preds[b, l:] == 0) and torch.all(alphas[b, l:] == 0)
+    # (the first batch_size_t rows are active at step t, whatever their own length — :261-265)
+    for t in range(max(dl)):
+        bt = sum(l > t for l in dl)
+        assert torch.all(preds[bt:, t] == 0) and torch.all(alphas[bt:, t] == 0)
     if case.get("loss", True):
         assert abs(loss.item() - float(g["loss"])) <= 1e-4 * abs(float(g["loss"]))
         ids = O.teacher_forced_ids(preds.cpu(), dl)
@@ -254,14 +256,16 @@ def test_beam_search_matches_reference_golden(cuda, name, capsys):
     class Identity(torch.nn.Module):
         def forward(self, x):
             return x
-    i = 0
+    i = [j for j in range(case["n_img"]) if bool(g["ended_%d" % j])][0]
+    capsys.readouterr()
     seq, alphas, ended = attention_caption_image_beam_search(cuda, Args, feats[i:i + 1], Identity(), dec, vocab)
     printed = [ln for ln in capsys.readouterr().out.strip().split("\n") if ln]
-    assert ended == bool(g["ended_%d" % i]) and seq == list(g["seq_%d" % i])
+    assert ended is True and seq == list(g["seq_%d" % i])
     gt = g["trace_%d" % i]
     assert printed == [str([vocab.i2w[int(x)] for x in row if x >= 0]) for row in gt]
     assert isinstance(alphas, list) and len(alphas) == len(seq) and len(alphas[0]) == 14 and len(alphas[0][0]) == 14
     assert alphas[0][0][0] == 1.0
+    assert np.abs(np.asarray(alphas, dtype=np.float32) - g["alphas_%d" % i]).max() < 1e-4
 
 
 def test_beam_search_failure_tuple_when_no_end(cuda):
