@@ -1,8 +1,13 @@
 // Dispatcher for the dense contraction entry point icd_gemm (include/icd_b200.h).
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 int icd_gemm_f32_launch(const icd_gemm_desc_t* d, cudaStream_t s);   // gemm_f32.cu
 int icd_gemm_tc_launch(const icd_gemm_desc_t* d, cudaStream_t s);    // gemm_tc.cu (tcgen05 / TMA, bf16)
+
+extern "C" int64_t icd_gemm_ws_bytes(int32_t M, int32_t N, int32_t K, int32_t precision) {
+    return precision == ICD_PREC_BF16 ? icd_gemm_tc_ws_bytes(M, N, K) : 0;
+}
 
 extern "C" int icd_gemm(const icd_gemm_desc_t* d, void* stream) {
     ICD_CHECK_ARG(d != nullptr, "gemm: null descriptor");
@@ -18,7 +23,7 @@ int icd_gemm_simple(int prec, const float* A, int64_t sam, int64_t sak, const fl
                     const float* add1, int64_t ld1, const float* add2, int64_t ld2, const uint8_t* row_mask,
                     float beta, cudaStream_t s, int flags) {
     icd_gemm_desc_t d;
-    d.flags = flags;
+    d.flags = flags; d.ws = nullptr; d.ws_bytes = 0;
     d.A = A; d.sam = sam; d.sak = sak; d.B = B; d.sbn = sbn; d.sbk = sbk; d.C = C; d.ldc = ldc;
     d.M = M; d.N = N; d.K = K; d.bias1 = bias1; d.bias2 = bias2; d.add1 = add1; d.ld1 = ld1;
     d.add2 = add2; d.ld2 = ld2; d.row_mask = row_mask; d.beta = beta; d.precision = prec;

@@ -1,0 +1,13 @@
+// Internal interface of the bf16 tensor-core tier (gemm_tc.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// dst[r*ldd + c] = bf16(src[r*s_r + c*s_c]);  one of s_r / s_c must be 1; ldd multiple of 8.
+int icd_convert_bf16(const float* src, int64_t s_r, int64_t s_c, int rows, int cols, void* dst, int64_t ldd,
+                     cudaStream_t s);
+// C[M,N] = A16[M,K] * B16[N,K]^T + epilogue; A16/B16 bf16 K-major with leading dimensions lda/ldb (multiples of 8).
+int icd_gemm_bf16(const void* A16, int64_t lda, const void* B16, int64_t ldb, float* C, int64_t ldc,
+                  int M, int N, int K, const float* bias1, const float* bias2, const float* add1, int64_t ld1,
+                  const float* add2, int64_t ld2, const uint8_t* row_mask, float beta, cudaStream_t s);
+int64_t icd_gemm_tc_ws_bytes(int M, int N, int K);

@@ -53,6 +53,11 @@ def gemm(a, b, *, a_strides=None, b_strides=None, out=None, ldc=None, M=None, N=
     elif ldc is None:
         ldc = out.stride(0)
     d = _lib.GemmDesc()
+    ws = None
+    need = int(lib().icd_gemm_ws_bytes(M, N, K, precision_id(precision)))
+    if need:
+        ws = torch.empty(need, device=a.device, dtype=torch.uint8)
+    fill(d, ws=ws, ws_bytes=need)
     fill(d, A=a, sam=a_strides[0], sak=a_strides[1], B=b, sbn=b_strides[0], sbk=b_strides[1], C=out, ldc=ldc,
          M=M, N=N, K=K, bias1=bias1, bias2=bias2, add1=add1, ld1=ld1, add2=add2, ld2=ld2, row_mask=row_mask,
          beta=float(beta), precision=precision_id(precision), flags=int(flags))

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ICD_B200_ABI_VERSION 4
+#define ICD_B200_ABI_VERSION 5
 #define ICD_MAX_STEPS 256
 
 ICD_API int icd_version(void);                       /* ICD_B200_ABI_VERSION the library was built with */
@@ -83,8 +83,10 @@ typedef struct {
     float beta;
     int32_t precision;
     int32_t flags;                /* ICD_GEMM_* bits */
+    void* ws; int64_t ws_bytes;   /* ICD_PREC_BF16 only: >= icd_gemm_ws_bytes(M,N,K) bytes for the bf16 operand copies */
 } icd_gemm_desc_t;
 
+ICD_API int64_t icd_gemm_ws_bytes(int32_t M, int32_t N, int32_t K, int32_t precision);
 ICD_API int icd_gemm(const icd_gemm_desc_t* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -183,3 +183,37 @@ def test_cross_entropy_matches_torch(cuda):
     assert abs(row_loss.sum().item() - loss64.item()) < 1e-5 * abs(loss64.item())
     H.assert_close_norm(dx, x64.grad, 1e-5, "d_logits")
     assert torch.all(dx[5] == 0) and torch.all(dx[11] == 0)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 128), (512, 4608, 512), (300, 9490, 512),
+                                   (77, 200, 300), (1000, 136, 2048), (12288, 512, 9490)])
+def test_gemm_bf16_tensor_core_matches_bf16_rounded_fp64(cuda, M, N, K):
+    """tcgen05/TMA tier: operands rounded to bf16, fp32 accumulation => compare with the fp64 product of the
+    bf16-rounded operands (tolerance 2e-5 norm-wise: only the accumulation order differs)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(cuda)
+    b = torch.randn(N, K, generator=g).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    add = torch.randn(M, N, generator=g).to(cuda)
+    mask = (torch.rand(M, generator=g) > 0.2).to(torch.uint8).to(cuda)
+    c = ops.gemm(a, b, bias1=bias, add1=add, ld1=N, row_mask=mask, precision="bf16")
+    ref = a.bfloat16().double() @ b.bfloat16().double().t() + bias.double() + add.double()
+    ref = ref * mask.double().unsqueeze(1)
+    H.assert_close_norm(c, ref, 2e-5, "tc gemm %dx%dx%d" % (M, N, K))
+    # and against the unrounded fp64 product at bf16 tolerance
+    full = (a.double() @ b.double().t() + bias.double() + add.double()) * mask.double().unsqueeze(1)
+    H.assert_close_norm(c, full, 1e-2, "tc gemm vs fp64")
+
+
+def test_gemm_bf16_transposed_forms_and_beta(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(8)
+    M, N, K = 260, 150, 700
+    dy = torch.randn(K, M, generator=g).to(cuda)          # A(m,k) = dy[k*M + m]  (row-contiguous source)
+    x = torch.randn(K, N, generator=g).to(cuda)           # B(n,k) = x[k*N + n]
+    c0 = torch.randn(M, N, generator=g).to(cuda)
+    c = c0.clone()
+    ops.gemm(dy, x, a_strides=(1, M), b_strides=(1, N), out=c, ldc=N, M=M, N=N, K=K, beta=1.0, precision="bf16")
+    ref = c0.double() + dy.bfloat16().double().t() @ x.bfloat16().double()
+    H.assert_close_norm(c, ref, 2e-5, "tc gemm TN beta")
