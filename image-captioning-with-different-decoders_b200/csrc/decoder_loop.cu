@@ -52,9 +52,20 @@ extern "C" int icd_init_hidden_state(int B, int P, int C, int D, int precision, 
     return 0;
 }
 
+int64_t icd_att_tc_ws_bytes(const icd_att_desc_t* d);                         // decoder_loop_bf16.cu
+int icd_attention_decoder_fwd_bf16(const icd_att_desc_t* d, cudaStream_t s);
+int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s);
+
+extern "C" int64_t icd_attention_decoder_ws_bytes(const icd_att_desc_t* d) {
+    if (!d || d->precision != ICD_PREC_BF16) return 0;
+    return icd_att_tc_ws_bytes(d);
+}
+
 extern "C" int icd_attention_decoder_fwd(const icd_att_desc_t* d, void* stream) {
     ICD_TRY(check_common(d));
     cudaStream_t s = icd_stream(stream);
+    if (d->precision == ICD_PREC_BF16) return icd_attention_decoder_fwd_bf16(d, s);
+    ICD_CHECK_ARG(d->precision == ICD_PREC_FP32, "attention_decoder: unknown precision %d", d->precision);
     const int B = d->B, T = d->T, P = d->P, C = d->C, A = d->A, D = d->D, E = d->E, V = d->V;
     const int NZ = A + C + 4 * D;
     const int prec = d->precision;
@@ -128,6 +139,7 @@ extern "C" int icd_attention_decoder_fwd(const icd_att_desc_t* d, void* stream) 
 extern "C" int icd_attention_decoder_bwd(const icd_att_desc_t* d, void* stream) {
     ICD_TRY(check_common(d));
     cudaStream_t s = icd_stream(stream);
+    if (d->precision == ICD_PREC_BF16) return icd_attention_decoder_bwd_bf16(d, s);
     const int B = d->B, T = d->T, P = d->P, C = d->C, A = d->A, D = d->D, E = d->E, V = d->V;
     const int NZ = A + C + 4 * D;
     const int prec = d->precision;

@@ -22,7 +22,8 @@ def beam_search_batched(decoder, features, beam_size, start_id, end_id, max_step
          score  (n_img,) float32 raw summed log-prob of the winner (gen_captions.py:127)
          alpha  (n_img, max_steps+2, P) float32, frame 0 all ones (gen_captions.py:54)      [want_alphas]
          trace  (max_steps+1, n_img, k) int32 next-word ids per step, -1 = empty slot        [want_trace]
-    The loop body runs for step = 1 .. max_steps+1, like ``step > 50`` at gen_captions.py:119 for max_steps=50."""
+    The loop body runs for step = 1 .. max_steps+1, like ``step > 50`` at gen_captions.py:119 for max_steps=50.
+    Caption generation always runs the fp32 tier (identical captions need fp32-grade logits)."""
     if not features.is_cuda:
         raise _lib.IcdError("beam_search_batched needs CUDA tensors; there is no CPU fallback")
     n_img = features.shape[0]
@@ -50,7 +51,7 @@ def beam_search_batched(decoder, features, beam_size, start_id, end_id, max_step
         d = _lib.BeamDesc()
         trace = torch.empty(max_steps + 1, n, k, device=dev, dtype=torch.int32) if want_trace else None
         fill(d, n_img=n, k=k, max_steps=max_steps, P=P, C=C, A=A, D=D, E=E, V=V,
-             precision=ops.precision_id(decoder.precision), emb_is_f64=int(emb_w.dtype == torch.float64),
+             precision=ops.precision_id("fp32"), emb_is_f64=int(emb_w.dtype == torch.float64),
              start_id=start_id, end_id=end_id, enc=enc[i0:i0 + n],
              enc_att_w=a.enc_att.weight, enc_att_b=a.enc_att.bias, dec_att_w=a.dec_att.weight,
              dec_att_b=a.dec_att.bias, full_att_w=a.full_att.weight, full_att_b=a.full_att.bias,

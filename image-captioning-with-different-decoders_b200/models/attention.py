@@ -146,7 +146,7 @@ class AttentionDecoder(nn.Module):
         generation); training goes through ``forward`` whose autograd Function covers this step."""
         enc = encoder_out.contiguous().float()
         h, c, _ = ops.init_hidden_state(enc, self.h_lin.weight, self.h_lin.bias, self.c_lin.weight,
-                                        self.c_lin.bias, precision=self.precision)
+                                        self.c_lin.bias, precision="fp32")
         return h, c
 
     def forward(self, encoder_out, encoded_captions, caption_lengths):
@@ -224,11 +224,14 @@ class _AttentionDecoderFn(torch.autograd.Function):
              emb_w=emb_w.contiguous(), **dict(zip(_W_NAMES, weights)), **bufs)
         for t in range(T):
             d.bt_host[t] = bt[t]
+        need = int(lib().icd_attention_decoder_ws_bytes(ctypes.byref(d)))
+        tc_ws = torch.empty(need, device=dev, dtype=torch.uint8) if need else None
+        fill(d, tc_ws=tc_ws, tc_ws_bytes=need)
+        bufs["tc_ws"] = tc_ws
         check(lib().icd_attention_decoder_fwd(ctypes.byref(d), stream_ptr()), "icd_attention_decoder_fwd")
         ctx.desc = d
         ctx.keep = (enc, captions, emb_w, weights, mask, bufs)      # keeps every device buffer alive
         ctx.dims = (B, T, L, P, C, A, D, E, V, NZ, emb_is_f64)
-        ctx.mark_non_differentiable()
         return bufs["predictions"], bufs["alphas"]
 
     @staticmethod

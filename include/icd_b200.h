@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ICD_B200_ABI_VERSION 5
+#define ICD_B200_ABI_VERSION 6
 #define ICD_MAX_STEPS 256
 
 ICD_API int icd_version(void);                       /* ICD_B200_ABI_VERSION the library was built with */
@@ -206,8 +206,11 @@ typedef struct {
     float* d_att_enc;             /* (B,P,A)  */
     float* d_emb_x;               /* (T,B,E)  */
     float* proj_partial;          /* icd_attention_proj_bwd_ws_floats(B,P,A) floats */
+    /* ICD_PREC_BF16 only: arena for the bf16 operand copies, shared by fwd and bwd of the same step */
+    void* tc_ws; int64_t tc_ws_bytes;   /* >= icd_attention_decoder_ws_bytes(desc) */
 } icd_att_desc_t;
 
+ICD_API int64_t icd_attention_decoder_ws_bytes(const icd_att_desc_t* d);
 ICD_API int icd_attention_decoder_fwd(const icd_att_desc_t* d, void* stream);
 ICD_API int icd_attention_decoder_bwd(const icd_att_desc_t* d, void* stream);
 

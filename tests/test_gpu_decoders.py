@@ -338,3 +338,44 @@ def test_full_size_properties_config3_shape(cuda):
             continue
         H.assert_close_norm(g_split[k], v.grad, 1e-3, "split-batch additivity " + k)
     assert set(g_full) == set(g_split)
+
+
+@pytest.mark.parametrize("name", ["att_small_ragged", "att_small_dropout", "att_cfg1"])
+def test_attention_decoder_bf16_tier_matches_reference_golden(cuda, name):
+    """bf16 tensor-core tier (tcgen05 GEMMs, fp32 everything else).  Stated tolerances (measured
+    bf16-operand emulation): logits / alphas 5e-3, loss 1e-3, gradients 1e-2, the four ill-conditioned
+    attention-projection gradients 8e-2; greedy ids must agree wherever the reference's top-2 margin exceeds 2e-2."""
+    case = dict(H.ATT_CASES[name])
+    g = load(name)
+    import icd_b200.models.attention as my_att
+    from icd_b200.vocabulary import synthetic_vocab
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams,
+                                   synthetic_vocab(case["V"])).to(cuda)
+    dec.precision = "bf16"
+    enc, caps, lens = H.att_inputs(case)
+    dl = [l - 1 for l in lens]
+    if case["train"]:
+        masks = H.dropout_masks_like_reference(case, dl, case["D"])
+        dec._dropout_mask_override = H.stack_masks(masks, case["B"], case["D"])
+    caps_dev = caps.to(cuda)
+    preds, _, odl, alphas = dec(enc.to(cuda), caps_dev, lens)
+    loss = O.attention_loss(preds, caps_dev, odl, alphas)
+    loss.backward()
+    compare(case, g, "predictions", preds, 5e-3)
+    compare(case, g, "alphas", alphas, 5e-3)
+    assert abs(loss.item() - float(g["loss"])) <= 1e-3 * abs(float(g["loss"]))
+    for t in range(max(dl)):
+        bt = sum(l > t for l in dl)
+        assert torch.all(preds[bt:, t] == 0) and torch.all(alphas[bt:, t] == 0)
+    ids = O.teacher_forced_ids(preds.cpu(), dl)
+    gold, margin = g["greedy_ids"], g["greedy_margin"]
+    for j, row in enumerate(ids):
+        for t, tok in enumerate(row):
+            if margin[j, t] > 2e-2:
+                assert tok == gold[j, t]
+    grads = {k: p.grad for k, p in dec.named_parameters()}
+    for k in [str(x) for x in g["grad_names"]]:
+        if k == "attention.full_att.bias":
+            assert float(grads[k].abs().max()) < 1e-4
+            continue
+        compare(case, g, "grad:" + k, grads[k], 8e-2 if k in ILL_CONDITIONED else 1e-2)
