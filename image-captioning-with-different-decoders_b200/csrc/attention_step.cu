@@ -452,8 +452,13 @@ extern "C" int icd_attention_step_fwd(int rows, int P, int C, int A, const int32
     ICD_CHECK_ARG(!fbeta_pre || ld_fb % 4 == 0, "attention_step_fwd: ld_fb must be a multiple of 4");
     const size_t smem = (2 * (size_t)A + ((P + 3) & ~3) + 40) * sizeof(float);
     ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_fwd: A/P too large for shared memory");
-    if (smem > 48 * 1024)
-        ICD_CUDA(cudaFuncSetAttribute(att_step_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        static size_t configured = 48 * 1024;
+        if (smem > configured) {
+            ICD_CUDA(cudaFuncSetAttribute(att_step_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+    }
     icd_prof_mark_begin(0, rows, s);
     att_step_fwd_kernel<<<rows, 256, smem, s>>>(P, C, A, img_index, enc, att_enc, att_dec, ld_dec, w_full, b_full,
                                                  fbeta_pre, ld_fb, alpha, ld_alpha, awe_raw, gate, gated);
@@ -477,8 +482,13 @@ extern "C" int icd_attention_step_bwd(int rows, int P, int C, int A,
     ICD_CHECK_ARG(ld_dec % 4 == 0 && ld_ddec % 4 == 0 && ld_dfb % 4 == 0, "attention_step_bwd: row strides must be multiples of 4");
     const size_t smem = ((size_t)C + 2 * (size_t)A + 2 * ((P + 3) & ~3) + 40) * sizeof(float);
     ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_bwd: dims too large for shared memory");
-    if (smem > 48 * 1024)
-        ICD_CUDA(cudaFuncSetAttribute(att_step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        static size_t configured = 48 * 1024;
+        if (smem > configured) {
+            ICD_CUDA(cudaFuncSetAttribute(att_step_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+    }
     icd_prof_mark_begin(1, rows, s);
     att_step_bwd_kernel<<<rows, 256, smem, s>>>(P, C, A, enc, att_enc, att_dec, ld_dec, w_full, alpha, ld_alpha,
                                                  d_alpha_ext, ld_dalpha, gate, awe_raw, d_gated,
@@ -511,8 +521,13 @@ extern "C" int icd_attention_proj_bwd(int B, int T, int P, int A, const int32_t*
     ICD_LAUNCH_CHECK();
     const size_t smem = ((size_t)T * A + (size_t)T * PROJ_PB + 40) * sizeof(float);
     ICD_CHECK_ARG(smem <= 220 * 1024, "attention_proj_bwd: T*A too large for shared memory");
-    if (smem > 48 * 1024)
-        ICD_CUDA(cudaFuncSetAttribute(att_proj_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        static size_t configured = 48 * 1024;
+        if (smem > configured) {
+            ICD_CUDA(cudaFuncSetAttribute(att_proj_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+    }
     int threads = ((A / 4 + 31) / 32) * 32;
     dim3 grid(chunks, B);
     att_proj_bwd_kernel<<<grid, threads, smem, s>>>(B, T, P, A, 0, row_len, att_enc, att_dec_all, ld_dec, w_full,

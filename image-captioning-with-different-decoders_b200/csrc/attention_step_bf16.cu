@@ -1,0 +1,491 @@
+// Fused additive-attention step kernels for bf16-STORED features (the tensor-core tier; BASELINE.json configs[2] allows
+// the 14x14x2048 features and their enc_att projection to be stored in bf16).  Arithmetic is fp32 throughout; only the
+// two big HBM streams — enc (P x C) and att_enc (P x A) per image — are read as bf16, halving the bytes of the
+// HBM-bound step: 196*2048*2 + 196*512*2 + small = 1 022 736 B per (image, step) forward.
+// Same math and same reference lines as attention_step.cu (models/attention.py:55-60, 270-271).
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace {
+
+__device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ld_stream_u2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+// 8 packed bf16 -> 8 floats (element 2i in the low half of word i)
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+    f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+    f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: one kernel per decode step, grid = rows, block = 256.
+// ------------------------------------------------------------------------------------------------
+constexpr int FW16_ROWS = 4;      // pixel rows per warp iteration in the score phase
+constexpr int FW16_UNROLL = 8;    // pixel rows in flight per thread in the weighted-sum phase
+
+__global__ void __launch_bounds__(256, 4) att_step_fwd_bf16_kernel(
+        int P, int C, int A, const int* __restrict__ img_index,
+        const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* __restrict__ att_enc,
+        const float* __restrict__ att_dec, long long ld_dec,
+        const float* __restrict__ w_full, const float* __restrict__ b_full,
+        const float* __restrict__ fbeta_pre, long long ld_fb,
+        float* __restrict__ alpha, long long ld_alpha,
+        float* __restrict__ awe_raw, float* __restrict__ gate, float* __restrict__ gated,
+        __nv_bfloat16* __restrict__ gated16) {
+    extern __shared__ __align__(16) float sm[];
+    float* s_dec = sm;
+    float* s_wf = sm + A;
+    float* s_e = sm + 2 * A;
+    float* s_red = s_e + ((P + 3) & ~3);
+    const int r = blockIdx.x;
+    const int img = img_index ? img_index[r] : r;
+    const __nv_bfloat16* ae = att_enc + (long long)img * P * A;
+    const float* dec = att_dec + (long long)r * ld_dec;
+    for (int a = threadIdx.x; a < A; a += blockDim.x) { s_dec[a] = dec[a]; s_wf[a] = w_full[a]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const float bfull = b_full ? b_full[0] : 0.f;
+    const int A8 = A >> 3;
+    // phase 1: scores; FW16_ROWS pixel rows per warp iteration, 16 B per lane per row chunk
+    for (int p0 = warp; p0 < P; p0 += FW16_ROWS * nwarp) {
+        float acc[FW16_ROWS];
+#pragma unroll
+        for (int u = 0; u < FW16_ROWS; ++u) acc[u] = 0.f;
+        for (int j = lane; j < A8; j += 32) {
+            uint4 x[FW16_ROWS];
+#pragma unroll
+            for (int u = 0; u < FW16_ROWS; ++u) {
+                const int p = min(p0 + u * nwarp, P - 1);
+                x[u] = ld_stream_u4(ae + (long long)p * A + 8 * j);
+            }
+            const float4 d0 = *reinterpret_cast<const float4*>(s_dec + 8 * j);
+            const float4 d1 = *reinterpret_cast<const float4*>(s_dec + 8 * j + 4);
+            const float4 w0 = *reinterpret_cast<const float4*>(s_wf + 8 * j);
+            const float4 w1 = *reinterpret_cast<const float4*>(s_wf + 8 * j + 4);
+            const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int u = 0; u < FW16_ROWS; ++u) {
+                float f[8];
+                unpack8(x[u], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[u] = fmaf(fmaxf(f[i] + dd[i], 0.f), ww[i], acc[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < FW16_ROWS; ++u) {
+            const float v = warp_sum(acc[u]);
+            const int p = p0 + u * nwarp;
+            if (lane == 0 && p < P) s_e[p] = v + bfull;
+        }
+    }
+    __syncthreads();
+    // phase 2: softmax over pixels
+    float m = -INFINITY;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) m = fmaxf(m, s_e[p]);
+    m = block_max(m, s_red);
+    float sum = 0.f;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) { const float ex = expf(s_e[p] - m); s_e[p] = ex; sum += ex; }
+    sum = block_sum(sum, s_red);
+    {
+        float* out = alpha + (long long)r * ld_alpha;
+        for (int p = threadIdx.x; p < P; p += blockDim.x) { const float al = s_e[p] / sum; s_e[p] = al; out[p] = al; }
+    }
+    __syncthreads();
+    // phase 3: alpha-weighted sum; thread owns 8 consecutive channels (16 B), FW16_UNROLL pixel rows in flight
+    const __nv_bfloat16* eb = enc + (long long)img * P * C;
+    for (int c = threadIdx.x * 8; c < C; c += blockDim.x * 8) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        int p = 0;
+        for (; p + FW16_UNROLL <= P; p += FW16_UNROLL) {
+            uint4 x[FW16_UNROLL];
+#pragma unroll
+            for (int u = 0; u < FW16_UNROLL; ++u) x[u] = ld_stream_u4(eb + (long long)(p + u) * C + c);
+#pragma unroll
+            for (int u = 0; u < FW16_UNROLL; ++u) {
+                const float al = s_e[p + u];
+                float f[8];
+                unpack8(x[u], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(al, f[i], acc[i]);
+            }
+        }
+        for (; p < P; ++p) {
+            const uint4 x = ld_stream_u4(eb + (long long)p * C + c);
+            const float al = s_e[p];
+            float f[8];
+            unpack8(x, f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(al, f[i], acc[i]);
+        }
+        const long long o = (long long)r * C + c;
+        if (awe_raw) {
+            *reinterpret_cast<float4*>(awe_raw + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4*>(awe_raw + o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+        if (fbeta_pre) {
+            const float4 f0 = *reinterpret_cast<const float4*>(fbeta_pre + (long long)r * ld_fb + c);
+            const float4 f1 = *reinterpret_cast<const float4*>(fbeta_pre + (long long)r * ld_fb + c + 4);
+            const float g[8] = {sigmoidf_(f0.x), sigmoidf_(f0.y), sigmoidf_(f0.z), sigmoidf_(f0.w),
+                                sigmoidf_(f1.x), sigmoidf_(f1.y), sigmoidf_(f1.z), sigmoidf_(f1.w)};
+            float gd[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gd[i] = g[i] * acc[i];
+            if (gate) {
+                *reinterpret_cast<float4*>(gate + o) = make_float4(g[0], g[1], g[2], g[3]);
+                *reinterpret_cast<float4*>(gate + o + 4) = make_float4(g[4], g[5], g[6], g[7]);
+            }
+            if (gated) {
+                *reinterpret_cast<float4*>(gated + o) = make_float4(gd[0], gd[1], gd[2], gd[3]);
+                *reinterpret_cast<float4*>(gated + o + 4) = make_float4(gd[4], gd[5], gd[6], gd[7]);
+            }
+            if (gated16) {
+                uint4 pk = make_uint4(pack2(gd[0], gd[1]), pack2(gd[2], gd[3]), pack2(gd[4], gd[5]), pack2(gd[6], gd[7]));
+                *reinterpret_cast<uint4*>(gated16 + o) = pk;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward: grid = rows, block = 256.  smem: C + 2*A + 2*Ppad + 40 + 3*8*(A/8) floats
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 3) att_step_bwd_bf16_kernel(
+        int P, int C, int A,
+        const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* __restrict__ att_enc,
+        const float* __restrict__ att_dec, long long ld_dec, const float* __restrict__ w_full,
+        const float* __restrict__ alpha, long long ld_alpha,
+        const float* __restrict__ d_alpha_ext, long long ld_dalpha,
+        const float* __restrict__ gate, const float* __restrict__ awe_raw, const float* __restrict__ d_gated,
+        float* __restrict__ d_att_dec, long long ld_ddec,
+        float* __restrict__ d_fbeta_pre, long long ld_dfb,
+        float* __restrict__ d_e, long long ld_de,
+        __nv_bfloat16* __restrict__ dz16, long long ld_dz16) {
+    extern __shared__ __align__(16) float sm[];
+    float* s_dawe = sm;                       // C
+    float* s_dec = s_dawe + C;                // A
+    float* s_alpha = s_dec + A;               // Ppad
+    float* s_de = s_alpha + ((P + 3) & ~3);   // Ppad
+    float* s_red = s_de + ((P + 3) & ~3);     // 40
+    float* s_part = s_red + 40;               // 3 * A
+    const int r = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+
+    // (A) gate backward (elementwise over C)
+    {
+        const long long o = (long long)r * C;
+        for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+            const float4 dg = *reinterpret_cast<const float4*>(d_gated + o + c);
+            const float4 g = *reinterpret_cast<const float4*>(gate + o + c);
+            const float4 aw = *reinterpret_cast<const float4*>(awe_raw + o + c);
+            *reinterpret_cast<float4*>(s_dawe + c) = make_float4(dg.x * g.x, dg.y * g.y, dg.z * g.z, dg.w * g.w);
+            const float4 df = make_float4(dg.x * aw.x * g.x * (1.f - g.x), dg.y * aw.y * g.y * (1.f - g.y),
+                                          dg.z * aw.z * g.z * (1.f - g.z), dg.w * aw.w * g.w * (1.f - g.w));
+            *reinterpret_cast<float4*>(d_fbeta_pre + (long long)r * ld_dfb + c) = df;
+            if (dz16) {
+                uint2 pk = make_uint2(pack2(df.x, df.y), pack2(df.z, df.w));
+                *reinterpret_cast<uint2*>(dz16 + (long long)r * ld_dz16 + A + c) = pk;
+            }
+        }
+        const float* dec = att_dec + (long long)r * ld_dec;
+        for (int a = threadIdx.x; a < A; a += blockDim.x) s_dec[a] = dec[a];
+        const float* al = alpha + (long long)r * ld_alpha;
+        for (int p = threadIdx.x; p < P; p += blockDim.x) s_alpha[p] = al[p];
+    }
+    __syncthreads();
+
+    // (B) d_alpha[p] = <d_awe, enc[r,p,:]>: warp per pixel row, 8 x 16 B loads in flight per lane
+    {
+        const __nv_bfloat16* eb = enc + (long long)r * P * C;
+        const int C8 = C >> 3;
+        for (int p = warp; p < P; p += nwarp) {
+            const __nv_bfloat16* row = eb + (long long)p * C;
+            float acc = 0.f;
+            int j = lane;
+            for (; j + 7 * 32 < C8; j += 8 * 32) {
+                uint4 x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = ld_stream_u4(row + 8 * (j + u * 32));
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    float f[8];
+                    unpack8(x[u], f);
+                    const float4 d0 = *reinterpret_cast<const float4*>(s_dawe + 8 * (j + u * 32));
+                    const float4 d1 = *reinterpret_cast<const float4*>(s_dawe + 8 * (j + u * 32) + 4);
+                    acc = fmaf(f[0], d0.x, acc); acc = fmaf(f[1], d0.y, acc); acc = fmaf(f[2], d0.z, acc); acc = fmaf(f[3], d0.w, acc);
+                    acc = fmaf(f[4], d1.x, acc); acc = fmaf(f[5], d1.y, acc); acc = fmaf(f[6], d1.z, acc); acc = fmaf(f[7], d1.w, acc);
+                }
+            }
+            for (; j < C8; j += 32) {
+                const uint4 x = ld_stream_u4(row + 8 * j);
+                float f[8];
+                unpack8(x, f);
+                const float4 d0 = *reinterpret_cast<const float4*>(s_dawe + 8 * j);
+                const float4 d1 = *reinterpret_cast<const float4*>(s_dawe + 8 * j + 4);
+                acc = fmaf(f[0], d0.x, acc); acc = fmaf(f[1], d0.y, acc); acc = fmaf(f[2], d0.z, acc); acc = fmaf(f[3], d0.w, acc);
+                acc = fmaf(f[4], d1.x, acc); acc = fmaf(f[5], d1.y, acc); acc = fmaf(f[6], d1.z, acc); acc = fmaf(f[7], d1.w, acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                if (d_alpha_ext) acc += d_alpha_ext[(long long)r * ld_dalpha + p];
+                s_de[p] = acc;
+            }
+        }
+    }
+    __syncthreads();
+
+    // (C) softmax backward, centred
+    {
+        float part = 0.f;
+        for (int p = threadIdx.x; p < P; p += blockDim.x) part = fmaf(s_alpha[p], s_de[p], part);
+        const float dot = block_sum(part, s_red);
+        float* out = d_e + (long long)r * ld_de;
+        for (int p = threadIdx.x; p < P; p += blockDim.x) {
+            const float v = s_alpha[p] * (s_de[p] - dot);
+            s_de[p] = v;
+            out[p] = v;
+        }
+    }
+    __syncthreads();
+
+    // (D) d_att_dec[a] = w_full[a] * sum_p d_e[p] * [att_enc[p,a] + att_dec[a] > 0]
+    //     thread = (pixel group g of 4, 8-channel column j); loops over column chunks of 64 * 8 channels
+    {
+        const __nv_bfloat16* ab = att_enc + (long long)r * P * A;
+        const int A8 = A >> 3;
+        const int grp = threadIdx.x >> 6, t = threadIdx.x & 63;
+        for (int j0 = 0; j0 < A8; j0 += 64) {
+            const int j = j0 + t;
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+            if (j < A8) {
+                const float4 d0 = *reinterpret_cast<const float4*>(s_dec + 8 * j);
+                const float4 d1 = *reinterpret_cast<const float4*>(s_dec + 8 * j + 4);
+                const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                int p = grp;
+                for (; p + 6 * 4 < P; p += 7 * 4) {
+                    uint4 x[7];
+#pragma unroll
+                    for (int u = 0; u < 7; ++u) x[u] = ld_stream_u4(ab + (long long)(p + 4 * u) * A + 8 * j);
+#pragma unroll
+                    for (int u = 0; u < 7; ++u) {
+                        const float de = s_de[p + 4 * u];
+                        float f[8];
+                        unpack8(x[u], f);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[i] += (f[i] + dd[i] > 0.f) ? de : 0.f;
+                    }
+                }
+                for (; p < P; p += 4) {
+                    const uint4 x = ld_stream_u4(ab + (long long)p * A + 8 * j);
+                    const float de = s_de[p];
+                    float f[8];
+                    unpack8(x, f);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] += (f[i] + dd[i] > 0.f) ? de : 0.f;
+                }
+            }
+            if (grp > 0 && j < A8) {
+                float* dst = s_part + (size_t)(grp - 1) * A + 8 * j;
+                *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            }
+            __syncthreads();
+            if (grp == 0 && j < A8) {
+                float res[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    res[i] = (acc[i] + s_part[8 * j + i] + s_part[A + 8 * j + i] + s_part[2 * A + 8 * j + i]) * w_full[8 * j + i];
+                float* o = d_att_dec + (long long)r * ld_ddec + 8 * j;
+                *reinterpret_cast<float4*>(o) = make_float4(res[0], res[1], res[2], res[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(res[4], res[5], res[6], res[7]);
+                if (dz16) {
+                    uint4 pk = make_uint4(pack2(res[0], res[1]), pack2(res[2], res[3]), pack2(res[4], res[5]), pack2(res[6], res[7]));
+                    *reinterpret_cast<uint4*>(dz16 + (long long)r * ld_dz16 + 8 * j) = pk;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// after the loop: d_att_enc + full_att parameter gradients, att_enc stored as bf16
+// ------------------------------------------------------------------------------------------------
+constexpr int PROJ_PB = 28;
+
+__global__ void att_proj_bwd_bf16_kernel(int B, int T, int P, int A, const int* __restrict__ row_len,
+                                         const __nv_bfloat16* __restrict__ att_enc,
+                                         const float* __restrict__ att_dec_all, long long ld_dec,
+                                         const float* __restrict__ w_full, const float* __restrict__ d_e,
+                                         float* __restrict__ d_att_enc, float* __restrict__ partial) {
+    extern __shared__ __align__(16) float sm[];
+    const int b = blockIdx.y, p0 = blockIdx.x * PROJ_PB;
+    const int np = min(PROJ_PB, P - p0);
+    const int Tb = row_len[b];
+    float* s_dec = sm;
+    float* s_de = sm + (size_t)T * A;
+    float* s_red = s_de + (size_t)T * PROJ_PB;
+    for (int i = threadIdx.x; i < Tb * A; i += blockDim.x) {
+        const int t = i / A, a = i % A;
+        s_dec[i] = att_dec_all[((long long)t * B + b) * ld_dec + a];
+    }
+    float de_sum = 0.f;
+    for (int i = threadIdx.x; i < Tb * PROJ_PB; i += blockDim.x) {
+        const int t = i / PROJ_PB, pp = i % PROJ_PB;
+        const float v = (pp < np) ? d_e[((long long)b * T + t) * P + p0 + pp] : 0.f;
+        s_de[i] = v;
+        de_sum += v;
+    }
+    __syncthreads();
+    const int a = threadIdx.x * 4;
+    float4 wacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a < A) {
+        const float4 w = *reinterpret_cast<const float4*>(w_full + a);
+        for (int pp = 0; pp < np; ++pp) {
+            const long long o = ((long long)b * P + p0 + pp) * A + a;
+            const uint2 raw = ld_stream_u2(att_enc + o);
+            const float x0 = __uint_as_float(raw.x << 16), x1 = __uint_as_float(raw.x & 0xffff0000u);
+            const float x2 = __uint_as_float(raw.y << 16), x3 = __uint_as_float(raw.y & 0xffff0000u);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int t = 0; t < Tb; ++t) {
+                const float de = s_de[t * PROJ_PB + pp];
+                const float4 d = *reinterpret_cast<const float4*>(s_dec + (size_t)t * A + a);
+                const float s0 = x0 + d.x, s1 = x1 + d.y, s2 = x2 + d.z, s3 = x3 + d.w;
+                acc.x += (s0 > 0.f) ? de : 0.f;  wacc.x = fmaf(de, fmaxf(s0, 0.f), wacc.x);
+                acc.y += (s1 > 0.f) ? de : 0.f;  wacc.y = fmaf(de, fmaxf(s1, 0.f), wacc.y);
+                acc.z += (s2 > 0.f) ? de : 0.f;  wacc.z = fmaf(de, fmaxf(s2, 0.f), wacc.z);
+                acc.w += (s3 > 0.f) ? de : 0.f;  wacc.w = fmaf(de, fmaxf(s3, 0.f), wacc.w);
+            }
+            *reinterpret_cast<float4*>(d_att_enc + o) = make_float4(acc.x * w.x, acc.y * w.y, acc.z * w.z, acc.w * w.w);
+        }
+    }
+    float* mine = partial + ((long long)b * gridDim.x + blockIdx.x) * (A + 4);
+    if (a < A) *reinterpret_cast<float4*>(mine + a) = wacc;
+    const float tot = block_sum(de_sum, s_red);
+    if (threadIdx.x == 0) { mine[A] = tot; mine[A + 1] = 0.f; mine[A + 2] = 0.f; mine[A + 3] = 0.f; }
+}
+
+struct BtPack { int v[ICD_MAX_STEPS]; };
+__global__ void row_len_from_pack_kernel16(int B, int T, const BtPack bt, int* __restrict__ row_len) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int n = 0;
+    for (int t = 0; t < T; ++t) n += (b < bt.v[t]) ? 1 : 0;
+    row_len[b] = n;
+}
+
+}  // namespace
+
+extern "C" int icd_attention_step_fwd_bf16(int rows, int P, int C, int A, const int32_t* img_index,
+                                           const void* enc16, const void* att_enc16,
+                                           const float* att_dec, int64_t ld_dec,
+                                           const float* w_full, const float* b_full,
+                                           const float* fbeta_pre, int64_t ld_fb,
+                                           float* alpha, int64_t ld_alpha,
+                                           float* awe_raw, float* gate, float* gated, void* gated16, void* stream) {
+    cudaStream_t s = icd_stream(stream);
+    if (rows == 0) return 0;
+    ICD_CHECK_ARG(rows > 0 && P > 0, "attention_step_fwd_bf16: bad dims");
+    ICD_CHECK_ARG(A % 8 == 0 && C % 8 == 0, "attention_step_fwd_bf16: A=%d and C=%d must be multiples of 8", A, C);
+    ICD_CHECK_ARG(ld_dec % 4 == 0 && (!fbeta_pre || ld_fb % 4 == 0), "attention_step_fwd_bf16: row strides must be multiples of 4");
+    const size_t smem = (2 * (size_t)A + ((P + 3) & ~3) + 40) * sizeof(float);
+    ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_fwd_bf16: A/P too large for shared memory");
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        ICD_CUDA(cudaFuncSetAttribute(att_step_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    icd_prof_mark_begin(0, rows, s);
+    att_step_fwd_bf16_kernel<<<rows, 256, smem, s>>>(P, C, A, img_index,
+                                                      reinterpret_cast<const __nv_bfloat16*>(enc16),
+                                                      reinterpret_cast<const __nv_bfloat16*>(att_enc16),
+                                                      att_dec, ld_dec, w_full, b_full, fbeta_pre, ld_fb, alpha, ld_alpha,
+                                                      awe_raw, gate, gated, reinterpret_cast<__nv_bfloat16*>(gated16));
+    icd_prof_mark_end(0, s);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
+                                           const void* enc16, const void* att_enc16,
+                                           const float* att_dec, int64_t ld_dec, const float* w_full,
+                                           const float* alpha, int64_t ld_alpha,
+                                           const float* d_alpha_ext, int64_t ld_dalpha,
+                                           const float* gate, const float* awe_raw, const float* d_gated,
+                                           float* d_att_dec, int64_t ld_ddec,
+                                           float* d_fbeta_pre, int64_t ld_dfb,
+                                           float* d_e, int64_t ld_de,
+                                           void* dz16, int64_t ld_dz16, void* stream) {
+    cudaStream_t s = icd_stream(stream);
+    if (rows == 0) return 0;
+    ICD_CHECK_ARG(A % 8 == 0 && C % 8 == 0, "attention_step_bwd_bf16: A and C must be multiples of 8");
+    ICD_CHECK_ARG(ld_dec % 4 == 0 && ld_ddec % 4 == 0 && ld_dfb % 4 == 0 && (!dz16 || ld_dz16 % 8 == 0),
+                  "attention_step_bwd_bf16: row strides misaligned");
+    const size_t smem = ((size_t)C + 4 * (size_t)A + 2 * ((P + 3) & ~3) + 40) * sizeof(float);
+    ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_bwd_bf16: dims too large for shared memory");
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        ICD_CUDA(cudaFuncSetAttribute(att_step_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    icd_prof_mark_begin(1, rows, s);
+    att_step_bwd_bf16_kernel<<<rows, 256, smem, s>>>(P, C, A, reinterpret_cast<const __nv_bfloat16*>(enc16),
+                                                      reinterpret_cast<const __nv_bfloat16*>(att_enc16),
+                                                      att_dec, ld_dec, w_full, alpha, ld_alpha, d_alpha_ext, ld_dalpha,
+                                                      gate, awe_raw, d_gated, d_att_dec, ld_ddec, d_fbeta_pre, ld_dfb,
+                                                      d_e, ld_de, reinterpret_cast<__nv_bfloat16*>(dz16), ld_dz16);
+    icd_prof_mark_end(1, s);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int icd_attention_proj_bwd_bf16(int B, int T, int P, int A, const int32_t* bt_host,
+                                           const void* att_enc16, const float* att_dec_all, int64_t ld_dec,
+                                           const float* w_full, const float* d_e,
+                                           float* d_att_enc, float* d_w_full, float* d_b_full,
+                                           float* partial, void* stream) {
+    cudaStream_t s = icd_stream(stream);
+    ICD_CHECK_ARG(T > 0 && T <= ICD_MAX_STEPS, "attention_proj_bwd_bf16: T=%d out of range", T);
+    ICD_CHECK_ARG(A % 4 == 0 && A / 4 <= 1024, "attention_proj_bwd_bf16: A=%d unsupported", A);
+    ICD_CHECK_ARG(B <= 65535, "attention_proj_bwd_bf16: B too large");
+    const int chunks = (P + PROJ_PB - 1) / PROJ_PB;
+    int* row_len = reinterpret_cast<int*>(partial + (int64_t)B * chunks * (A + 4));
+    BtPack pack;
+    for (int t = 0; t < ICD_MAX_STEPS; ++t) pack.v[t] = t < T ? bt_host[t] : 0;
+    row_len_from_pack_kernel16<<<(B + 127) / 128, 128, 0, s>>>(B, T, pack, row_len);
+    ICD_LAUNCH_CHECK();
+    const size_t smem = ((size_t)T * A + (size_t)T * PROJ_PB + 40) * sizeof(float);
+    ICD_CHECK_ARG(smem <= 220 * 1024, "attention_proj_bwd_bf16: T*A too large for shared memory");
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        ICD_CUDA(cudaFuncSetAttribute(att_proj_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int threads = ((A / 4 + 31) / 32) * 32;
+    dim3 grid(chunks, B);
+    att_proj_bwd_bf16_kernel<<<grid, threads, smem, s>>>(B, T, P, A, row_len,
+                                                          reinterpret_cast<const __nv_bfloat16*>(att_enc16),
+                                                          att_dec_all, ld_dec, w_full, d_e, d_att_enc, partial);
+    ICD_LAUNCH_CHECK();
+    ICD_TRY(icd_colsum(partial, A + 4, (int64_t)B * chunks, A, nullptr, d_w_full, s));
+    ICD_TRY(icd_colsum(partial + A, A + 4, (int64_t)B * chunks, 1, nullptr, d_b_full, s));
+    return 0;
+}

@@ -86,11 +86,11 @@ int icd_embed_scatter_add(void* d_table, int is_f64, const int64_t* captions, in
 int icd_lstm_pointwise_fwd(int rows, int D, const float* gates_pre, const float* c_prev,
                            float* gates_act, float* c_new, float* h_new,
                            float* hdrop, int64_t hdrop_row_stride, const uint8_t* mask, float scale,
-                           cudaStream_t s);
+                           cudaStream_t s, void* h16 = nullptr, void* hdrop16 = nullptr);
 int icd_lstm_pointwise_bwd(int rows, int D, const float* dh_in, const float* d_hdrop, int64_t hdrop_row_stride,
                            const uint8_t* mask, float scale, float* dc_inout,
                            const float* gates_act, const float* c_prev, const float* c_new,
-                           float* dgates_pre, int64_t ld_dg, cudaStream_t s);
+                           float* dgates_pre, int64_t ld_dg, cudaStream_t s, void* dg16 = nullptr, int64_t ld_dg16 = 0);
 int icd_weighted_pixel_sum(int rows, int P, int C, const int32_t* img_index, const float* enc,
                            const float* alpha, int64_t ld_alpha, const float* fbeta_pre, int64_t ld_fb,
                            float* awe_raw, float* gate, float* gated, cudaStream_t s);

@@ -41,7 +41,7 @@ struct Arena {
 // every bf16 buffer of the tier, carved in a fixed order so forward and backward agree on the layout
 struct Bufs {
     void *We, *Wcat, *WihE, *WihC, *Wh, *Wc, *Wfc;                 // weights, K-major
-    void *enc, *mean, *embx, *h, *gated, *hdrop;                   // forward activations, K-major
+    void *enc, *att_enc, *mean, *embx, *h, *gated, *hdrop;         // forward activations, K-major
     void *WcatT, *WihCT, *WihET, *WfcT;                            // backward: transposed weights
     void *dY, *dYT, *hdropT, *dz, *dzT, *hT, *embxT, *gatedT, *dhT, *dcT, *meanT, *daeT, *encT;
     int64_t ldE, ldV, ldTB, ldB, ldBP, ldBT;
@@ -53,7 +53,8 @@ void carve(const icd_att_desc_t* d, Arena& a, Bufs& b) {
     b.ldE = up8(E); b.ldV = up8(V); b.ldTB = up8(TB); b.ldB = up8(B); b.ldBP = up8(B * P); b.ldBT = up8(B * T);
     b.We = a.take(A, C); b.Wcat = a.take(NZ, D); b.WihE = a.take(4 * D, b.ldE); b.WihC = a.take(4 * D, C);
     b.Wh = a.take(D, C); b.Wc = a.take(D, C); b.Wfc = a.take(V, D);
-    b.enc = a.take(B * P, C); b.mean = a.take(B, C); b.embx = a.take(TB, b.ldE); b.h = a.take(TB, D);
+    b.enc = a.take(B * P, C); b.att_enc = a.take(B * P, A); b.mean = a.take(B, C); b.embx = a.take(TB, b.ldE);
+    b.h = a.take(TB + B, D);
     b.gated = a.take(TB, C); b.hdrop = a.take(B * T, D);
     b.WcatT = a.take(D, NZ); b.WihCT = a.take(C, 4 * D); b.WihET = a.take(E, 4 * D); b.WfcT = a.take(D, b.ldV);
     b.dY = a.take(B * T, b.ldV); b.dYT = a.take(V, b.ldBT); b.hdropT = a.take(D, b.ldBT);
@@ -100,12 +101,13 @@ int icd_attention_decoder_fwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
     ICD_LAUNCH_CHECK();
     ICD_CUDA(cudaMemsetAsync(d->alphas, 0, sizeof(float) * (size_t)B * T * P, s));
     ICD_CUDA(cudaMemsetAsync(d->hdrop, 0, sizeof(float) * (size_t)B * T * D, s));
+    ICD_CUDA(cudaMemsetAsync(u.hdrop, 0, (size_t)B * T * D * 2, s));
     if (d->bt_host[T - 1] < B) {
         ICD_CUDA(cudaMemsetAsync(d->h_all, 0, sizeof(float) * (size_t)(T + 1) * BD, s));
         ICD_CUDA(cudaMemsetAsync(d->c_all, 0, sizeof(float) * (size_t)(T + 1) * BD, s));
         ICD_CUDA(cudaMemsetAsync(d->gated, 0, sizeof(float) * (size_t)T * B * C, s));
         ICD_CUDA(cudaMemsetAsync(d->z, 0, sizeof(float) * (size_t)T * B * NZ, s));
-        ICD_CUDA(cudaMemsetAsync(u.h, 0, (size_t)TB * D * 2, s));
+        ICD_CUDA(cudaMemsetAsync(u.h, 0, (size_t)(TB + B) * D * 2, s));
         ICD_CUDA(cudaMemsetAsync(u.gated, 0, (size_t)TB * C * 2, s));
     }
     ICD_CUDA(cudaMemcpyAsync(d->w_cat, d->dec_att_w, sizeof(float) * (size_t)A * D, cudaMemcpyDeviceToDevice, s));
@@ -126,12 +128,14 @@ int icd_attention_decoder_fwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
     CVT(d->enc, C, 1, B * P, C, u.enc, C);
 
     // K1: att_enc = enc_att(encoder_out), once per batch (models/attention.py:54)
-    MM(u.enc, C, u.We, C, d->att_enc, A, B * P, A, C, d->enc_att_b, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);
+    ICD_TRY(icd_gemm_bf16(u.enc, C, u.We, C, nullptr, 0, B * P, A, C, d->enc_att_b, nullptr, nullptr, 0, nullptr, 0,
+                          nullptr, 0.f, s, u.att_enc, A));
     // K7: init_hidden_state (:161-163)
     ICD_TRY(icd_weighted_pixel_sum(B, P, C, nullptr, d->enc, nullptr, 0, nullptr, 0, d->mean_enc, nullptr, nullptr, s));
     CVT(d->mean_enc, C, 1, B, C, u.mean, C);
     MM(u.mean, C, u.Wh, C, d->h_all, D, B, D, C, d->h_lin_b, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);
     MM(u.mean, C, u.Wc, C, d->c_all, D, B, D, C, d->c_lin_b, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);
+    CVT(d->h_all, D, 1, B, D, u.h, D);                              // h_0 (bf16); h_t, t >= 1, is emitted by the gate kernel
     // K5: embedding lookup (:247) + hoisted input contraction
     ICD_TRY(icd_embed_gather(d->emb_w, d->emb_is_f64, d->captions, B, d->L, T, E, d->emb_x, s));
     CVT(d->emb_x, E, 1, TB, E, u.embx, u.ldE);
@@ -145,22 +149,20 @@ int icd_attention_decoder_fwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
         float* zt = d->z + (size_t)t * B * NZ;
         char* h16 = at16(u.h, (int64_t)t * B * D);
         char* g16 = at16(u.gated, (int64_t)t * B * C);
-        CVT(h_prev, D, 1, bt, D, h16, D);
         MM(h16, D, u.Wcat, D, zt, NZ, bt, NZ, D, d->b_cat, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);       // K2
-        ICD_TRY(icd_attention_step_fwd(bt, P, C, A, nullptr, d->enc, d->att_enc, zt, NZ, d->full_att_w, d->full_att_b,
-                                       zt + A, NZ, d->alphas + (size_t)t * P, (int64_t)T * P,
-                                       d->awe_raw + (size_t)t * B * C, d->gate + (size_t)t * B * C,
-                                       d->gated + (size_t)t * B * C, (void*)s));                                    // K3
-        CVT(d->gated + (size_t)t * B * C, C, 1, bt, C, g16, C);
+        ICD_TRY(icd_attention_step_fwd_bf16(bt, P, C, A, nullptr, u.enc, u.att_enc, zt, NZ, d->full_att_w, d->full_att_b,
+                                            zt + A, NZ, d->alphas + (size_t)t * P, (int64_t)T * P,
+                                            d->awe_raw + (size_t)t * B * C, d->gate + (size_t)t * B * C,
+                                            d->gated + (size_t)t * B * C, g16, (void*)s));                         // K3
         MM(g16, C, u.WihC, C, d->gates_pre, 4 * D, bt, 4 * D, C, nullptr, nullptr,
            d->xg + (size_t)t * B * 4 * D, 4 * D, zt + A + C, NZ, nullptr, 0.f);                                   // K4
         ICD_TRY(icd_lstm_pointwise_fwd(bt, D, d->gates_pre, c_prev, d->gates_act + (size_t)t * B * 4 * D,
                                        d->c_all + (size_t)(t + 1) * BD, d->h_all + (size_t)(t + 1) * BD,
                                        d->hdrop + (size_t)t * D, (int64_t)T * D,
-                                       d->drop_mask ? d->drop_mask + (size_t)t * BD : nullptr, d->drop_scale, s));
+                                       d->drop_mask ? d->drop_mask + (size_t)t * BD : nullptr, d->drop_scale, s,
+                                       at16(u.h, (int64_t)(t + 1) * B * D), at16(u.hdrop, (int64_t)t * D)));
     }
     // K6: predictions = fc(dropout(h)) for every (b,t) at once (:279-280); inactive rows exactly 0 (:253)
-    CVT(d->hdrop, D, 1, B * T, D, u.hdrop, D);
     MM(u.hdrop, D, u.Wfc, D, d->predictions, V, B * T, V, D, d->fc_b, nullptr, nullptr, 0, nullptr, 0, d->row_valid, 0.f);
     return 0;
 }
@@ -202,16 +204,15 @@ int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
                                        d->drop_mask ? d->drop_mask + (size_t)t * BD : nullptr, d->drop_scale,
                                        d->dc, d->gates_act + (size_t)t * B * 4 * D,
                                        d->c_all + (size_t)t * BD, d->c_all + (size_t)(t + 1) * BD,
-                                       dzt + A + C, NZ, s));
-        CVT(dzt + A + C, NZ, 1, bt, 4 * D, at16(dz16, A + C), NZ);                 // dG (bf16) into its slice of dz16
+                                       dzt + A + C, NZ, s, at16(dz16, A + C), NZ));     // dG also emitted as bf16
         MM(at16(dz16, A + C), NZ, u.WihCT, 4 * D, d->d_gated, C, bt, C, 4 * D,
            nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);                // d_gated = dG W_ih[:, E:]
-        ICD_TRY(icd_attention_step_bwd(bt, P, C, A, d->enc, d->att_enc, zt, NZ, d->full_att_w,
-                                       d->alphas + (size_t)t * P, (int64_t)T * P,
-                                       d->d_alphas ? d->d_alphas + (size_t)t * P : nullptr, (int64_t)T * P,
-                                       d->gate + (size_t)t * B * C, d->awe_raw + (size_t)t * B * C, d->d_gated,
-                                       dzt, NZ, dzt + A, NZ, d->d_e + (size_t)t * P, (int64_t)T * P, (void*)s));
-        CVT(dzt, NZ, 1, bt, A + C, dz16, NZ);                                      // d att_dec | d fbeta_pre (bf16)
+        ICD_TRY(icd_attention_step_bwd_bf16(bt, P, C, A, u.enc, u.att_enc, zt, NZ, d->full_att_w,
+                                            d->alphas + (size_t)t * P, (int64_t)T * P,
+                                            d->d_alphas ? d->d_alphas + (size_t)t * P : nullptr, (int64_t)T * P,
+                                            d->gate + (size_t)t * B * C, d->awe_raw + (size_t)t * B * C, d->d_gated,
+                                            dzt, NZ, dzt + A, NZ, d->d_e + (size_t)t * P, (int64_t)T * P,
+                                            dz16, NZ, (void*)s));                   // d att_dec | d fbeta_pre (+ bf16)
         MM(dz16, NZ, u.WcatT, NZ, d->dh, D, bt, D, NZ, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);
     }
 
@@ -242,8 +243,8 @@ int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
         ICD_TRY(icd_embed_scatter_add(d->d_emb_w, d->emb_is_f64, d->captions, B, d->L, T, E, d->bt_host, d->d_emb_x, s));
     }
     // attention projections: d_att_enc for all steps at once, full_att grads, then enc_att grads (:54)
-    ICD_TRY(icd_attention_proj_bwd(B, T, P, A, d->bt_host, d->att_enc, d->z, NZ, d->full_att_w, d->d_e,
-                                   d->d_att_enc, d->d_full_att_w, d->d_full_att_b, d->proj_partial, (void*)s));
+    ICD_TRY(icd_attention_proj_bwd_bf16(B, T, P, A, d->bt_host, u.att_enc, d->z, NZ, d->full_att_w, d->d_e,
+                                        d->d_att_enc, d->d_full_att_w, d->d_full_att_b, d->proj_partial, (void*)s));
     ICD_TRY(icd_colsum(d->d_att_enc, A, (int64_t)BP, A, nullptr, d->d_enc_att_b, s));
     CVT(d->d_att_enc, 1, A, A, BP, u.daeT, u.ldBP);                // [A x BP]
     CVT(d->enc, 1, C, C, BP, u.encT, u.ldBP);                      // [C x BP]

@@ -34,6 +34,7 @@ struct EpiArgs {
     const float* add2; long long ld2;
     const unsigned char* row_mask;
     float beta;
+    __nv_bfloat16* C16; long long ldc16;      // optional bf16 copy of the result (C may then be NULL)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -215,9 +216,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (e.add1) x += e.add1[(long long)m * e.ld1 + n];
                         if (e.add2) x += e.add2[(long long)m * e.ld2 + n];
                         if (e.row_mask && !e.row_mask[m]) x = 0.f;
-                        float* cp = e.C + (long long)m * e.ldc + n;
-                        if (e.beta != 0.f) x += e.beta * (*cp);
-                        *cp = x;
+                        if (e.C) {
+                            float* cp = e.C + (long long)m * e.ldc + n;
+                            if (e.beta != 0.f) x += e.beta * (*cp);
+                            *cp = x;
+                        }
+                        if (e.C16) e.C16[(long long)m * e.ldc16 + n] = __float2bfloat16_rn(x);
                     }
                 }
                 __syncwarp();
@@ -345,9 +349,11 @@ int icd_convert_bf16(const float* src, int64_t s_r, int64_t s_c, int rows, int c
 
 int icd_gemm_bf16(const void* A16, int64_t lda, const void* B16, int64_t ldb, float* C, int64_t ldc,
                   int M, int N, int K, const float* bias1, const float* bias2, const float* add1, int64_t ld1,
-                  const float* add2, int64_t ld2, const uint8_t* row_mask, float beta, cudaStream_t s) {
+                  const float* add2, int64_t ld2, const uint8_t* row_mask, float beta, cudaStream_t s,
+                  void* C16, int64_t ldc16) {
     if (M == 0 || N == 0) return 0;
     ICD_CHECK_ARG(K > 0, "gemm_tc: K must be positive");
+    ICD_CHECK_ARG(C != nullptr || C16 != nullptr, "gemm_tc: no output");
     const int tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256);
     const bool use256 = (N > 128) && tiles256 >= ICD_NUM_SMS;
     const int BN = use256 ? 256 : 128;
@@ -357,6 +363,7 @@ int icd_gemm_bf16(const void* A16, int64_t lda, const void* B16, int64_t ldb, fl
     EpiArgs e;
     e.C = C; e.ldc = ldc; e.M = M; e.N = N; e.K = K; e.bias1 = bias1; e.bias2 = bias2;
     e.add1 = add1; e.ld1 = ld1; e.add2 = add2; e.ld2 = ld2; e.row_mask = row_mask; e.beta = beta;
+    e.C16 = reinterpret_cast<__nv_bfloat16*>(C16); e.ldc16 = ldc16;
     return use256 ? launch<256>(tmA, tmB, e, s) : launch<128>(tmA, tmB, e, s);
 }
 
@@ -378,5 +385,5 @@ int icd_gemm_tc_launch(const icd_gemm_desc_t* d, cudaStream_t s) {
     ICD_TRY(icd_convert_bf16(d->A, d->sam, d->sak, d->M, d->K, a16, ldk, s));
     ICD_TRY(icd_convert_bf16(d->B, d->sbn, d->sbk, d->N, d->K, b16, ldk, s));
     return icd_gemm_bf16(a16, ldk, b16, ldk, d->C, d->ldc, d->M, d->N, d->K, d->bias1, d->bias2, d->add1, d->ld1,
-                         d->add2, d->ld2, d->row_mask, d->beta, s);
+                         d->add2, d->ld2, d->row_mask, d->beta, s, nullptr, 0);
 }

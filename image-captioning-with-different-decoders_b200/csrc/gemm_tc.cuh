@@ -9,5 +9,6 @@ int icd_convert_bf16(const float* src, int64_t s_r, int64_t s_c, int rows, int c
 // C[M,N] = A16[M,K] * B16[N,K]^T + epilogue; A16/B16 bf16 K-major with leading dimensions lda/ldb (multiples of 8).
 int icd_gemm_bf16(const void* A16, int64_t lda, const void* B16, int64_t ldb, float* C, int64_t ldc,
                   int M, int N, int K, const float* bias1, const float* bias2, const float* add1, int64_t ld1,
-                  const float* add2, int64_t ld2, const uint8_t* row_mask, float beta, cudaStream_t s);
+                  const float* add2, int64_t ld2, const uint8_t* row_mask, float beta, cudaStream_t s,
+                  void* C16 = nullptr, int64_t ldc16 = 0);   // optional bf16 copy of the result; C may be NULL then
 int64_t icd_gemm_tc_ws_bytes(int M, int N, int K);

@@ -5,6 +5,7 @@
 //   Philox keep-mask generation, clamp+Adam (train_utils.py:2-12, models/attention.py:423-428),
 //   row-wise cross-entropy forward+backward (models/attention.py:411).
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -12,7 +13,8 @@ __global__ void lstm_pointwise_fwd_kernel(int rows, int D, const float* __restri
                                           const float* __restrict__ c_prev, float* __restrict__ gates_act,
                                           float* __restrict__ c_new, float* __restrict__ h_new,
                                           float* __restrict__ hdrop, long long hdrop_row_stride,
-                                          const unsigned char* __restrict__ mask, float scale) {
+                                          const unsigned char* __restrict__ mask, float scale,
+                                          __nv_bfloat16* __restrict__ h16, __nv_bfloat16* __restrict__ hdrop16) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)rows * D) return;
     const int r = (int)(idx / D), d = (int)(idx % D);
@@ -33,7 +35,9 @@ __global__ void lstm_pointwise_fwd_kernel(int rows, int D, const float* __restri
         float hd = h;
         if (mask) hd = mask[idx] ? h * scale : 0.f;
         hdrop[(long long)r * hdrop_row_stride + d] = hd;
+        if (hdrop16) hdrop16[(long long)r * hdrop_row_stride + d] = __float2bfloat16_rn(hd);
     }
+    if (h16) h16[idx] = __float2bfloat16_rn(h);
 }
 
 __global__ void lstm_pointwise_bwd_kernel(int rows, int D, const float* __restrict__ dh_in,
@@ -41,7 +45,8 @@ __global__ void lstm_pointwise_bwd_kernel(int rows, int D, const float* __restri
                                           const unsigned char* __restrict__ mask, float scale,
                                           float* __restrict__ dc_inout, const float* __restrict__ gates_act,
                                           const float* __restrict__ c_prev, const float* __restrict__ c_new,
-                                          float* __restrict__ dgates_pre, long long ld_dg) {
+                                          float* __restrict__ dgates_pre, long long ld_dg,
+                                          __nv_bfloat16* __restrict__ dg16, long long ld_dg16) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)rows * D) return;
     const int r = (int)(idx / D), d = (int)(idx % D);
@@ -59,10 +64,13 @@ __global__ void lstm_pointwise_bwd_kernel(int rows, int D, const float* __restri
     const float d_i = dc * g, d_g = dc * i, d_f = dc * c_prev[idx];
     dc_inout[idx] = dc * f;
     float* dg = dgates_pre + (long long)r * ld_dg;
-    dg[d] = d_i * i * (1.f - i);
-    dg[D + d] = d_f * f * (1.f - f);
-    dg[2 * D + d] = d_g * (1.f - g * g);
-    dg[3 * D + d] = d_o * o * (1.f - o);
+    const float p_i = d_i * i * (1.f - i), p_f = d_f * f * (1.f - f), p_g = d_g * (1.f - g * g), p_o = d_o * o * (1.f - o);
+    dg[d] = p_i; dg[D + d] = p_f; dg[2 * D + d] = p_g; dg[3 * D + d] = p_o;
+    if (dg16) {
+        __nv_bfloat16* q = dg16 + (long long)r * ld_dg16;
+        q[d] = __float2bfloat16_rn(p_i); q[D + d] = __float2bfloat16_rn(p_f);
+        q[2 * D + d] = __float2bfloat16_rn(p_g); q[3 * D + d] = __float2bfloat16_rn(p_o);
+    }
 }
 
 // out[n] = sum_m mask[m] * X[m*ld + n].  block (32,32): x -> column, y -> row phase.  deterministic.
@@ -192,12 +200,13 @@ __global__ void __launch_bounds__(256) cross_entropy_kernel(int V, const float* 
 int icd_lstm_pointwise_fwd(int rows, int D, const float* gates_pre, const float* c_prev,
                            float* gates_act, float* c_new, float* h_new,
                            float* hdrop, int64_t hdrop_row_stride, const uint8_t* mask, float scale,
-                           cudaStream_t s) {
+                           cudaStream_t s, void* h16, void* hdrop16) {
     if (rows == 0) return 0;
     const long long n = (long long)rows * D;
     lstm_pointwise_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rows, D, gates_pre, c_prev, gates_act,
                                                                            c_new, h_new, hdrop, hdrop_row_stride,
-                                                                           mask, scale);
+                                                                           mask, scale, (__nv_bfloat16*)h16,
+                                                                           (__nv_bfloat16*)hdrop16);
     ICD_LAUNCH_CHECK();
     return 0;
 }
@@ -205,12 +214,13 @@ int icd_lstm_pointwise_fwd(int rows, int D, const float* gates_pre, const float*
 int icd_lstm_pointwise_bwd(int rows, int D, const float* dh_in, const float* d_hdrop, int64_t hdrop_row_stride,
                            const uint8_t* mask, float scale, float* dc_inout,
                            const float* gates_act, const float* c_prev, const float* c_new,
-                           float* dgates_pre, int64_t ld_dg, cudaStream_t s) {
+                           float* dgates_pre, int64_t ld_dg, cudaStream_t s, void* dg16, int64_t ld_dg16) {
     if (rows == 0) return 0;
     const long long n = (long long)rows * D;
     lstm_pointwise_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rows, D, dh_in, d_hdrop, hdrop_row_stride,
                                                                            mask, scale, dc_inout, gates_act, c_prev,
-                                                                           c_new, dgates_pre, ld_dg);
+                                                                           c_new, dgates_pre, ld_dg,
+                                                                           (__nv_bfloat16*)dg16, ld_dg16);
     ICD_LAUNCH_CHECK();
     return 0;
 }

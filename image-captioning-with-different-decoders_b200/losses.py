@@ -14,6 +14,7 @@ reads each logits row once and writes loss and gradient; rows with t >= batch_si
 (CrossEntropyLoss(ignore_index=<pad>) over all (b, t)).
 The doubly-stochastic regulariser touches only the (B,T,196) alphas and stays a torch expression.
 """
+import numpy as np
 import torch
 
 from . import ops
@@ -32,19 +33,25 @@ class _FusedCE(torch.autograd.Function):
         return d_logits * g, None, None
 
 
-def packed_targets(encoded_captions, decode_lengths, T):
-    """targets[b, t] = captions[b, t+1] where row b is active at step t (b < batch_size_t), else -1."""
+def packed_targets(encoded_captions, decode_lengths, T, row_valid=None):
+    """targets[b, t] = captions[b, t+1] where row b is active at step t (b < batch_size_t), else -1.
+    ``row_valid``: the (B*T) uint8 activity mask the decoder forward already built on the device (no host->device
+    copy, no sync); rebuilt from ``decode_lengths`` when absent."""
     B = encoded_captions.shape[0]
-    bt = torch.tensor([sum(l > t for l in decode_lengths) for t in range(T)], device=encoded_captions.device)
-    rows = torch.arange(B, device=encoded_captions.device).unsqueeze(1)
-    active = rows < bt.unsqueeze(0)                                   # (B,T): first batch_size_t rows
+    dev = encoded_captions.device
+    if row_valid is not None:
+        active = row_valid.view(B, T).bool()
+    else:
+        dl = np.asarray(decode_lengths, dtype=np.int64)
+        bt = (dl[None, :] > np.arange(T)[:, None]).sum(axis=1)                       # batch_size_t
+        active = torch.from_numpy(np.arange(B)[:, None] < bt[None, :]).to(dev, non_blocking=True)
     tgt = encoded_captions[:, 1:T + 1]
     return torch.where(active, tgt, torch.full_like(tgt, -1)), int(sum(decode_lengths))
 
 
 def attention_caption_loss(predictions, encoded_captions, decode_lengths, alphas, alpha_c=1.0):
     B, T, V = predictions.shape
-    tgt, n_valid = packed_targets(encoded_captions, decode_lengths, T)
+    tgt, n_valid = packed_targets(encoded_captions, decode_lengths, T, getattr(predictions, "_icd_row_valid", None))
     ce = _FusedCE.apply(predictions.reshape(B * T, V), tgt.reshape(-1).contiguous(), n_valid)
     return ce + ((alpha_c - alphas.sum(dim=1)) ** 2).mean()
 

@@ -11,6 +11,7 @@ Not yet supported: gradients w.r.t. ``encoder_out`` (``-
 """
 import ctypes
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -156,7 +157,8 @@ class AttentionDecoder(nn.Module):
         enc = encoder_out.reshape(batch_size, -1, encoder_dim)                         # :230
         decode_lengths = [caption_length - 1 for caption_length in caption_lengths]    # :236
         T = max(decode_lengths)
-        bt = [sum(l > t for l in decode_lengths) for t in range(T)]                    # :261
+        dl_np = np.asarray(decode_lengths, dtype=np.int64)
+        bt = (dl_np[None, :] > np.arange(T)[:, None]).sum(axis=1).tolist()             # :261 batch_size_t
         D = self.decoder_dim
         mask = None
         p = self.dropout.p
@@ -229,10 +231,16 @@ class _AttentionDecoderFn(torch.autograd.Function):
         fill(d, tc_ws=tc_ws, tc_ws_bytes=need)
         bufs["tc_ws"] = tc_ws
         check(lib().icd_attention_decoder_fwd(ctypes.byref(d), stream_ptr()), "icd_attention_decoder_fwd")
+        predictions, alphas = bufs.pop("predictions"), bufs.pop("alphas")
+        # the returned tensors get this node as grad_fn: keeping them in ctx would create a reference cycle (and
+        # leak ~3 GB of activations per step until the cyclic GC runs) — keep a detached alias of alphas instead
+        bufs["alphas_saved"] = alphas.detach()
         ctx.desc = d
         ctx.keep = (enc, captions, emb_w, weights, mask, bufs)      # keeps every device buffer alive
         ctx.dims = (B, T, L, P, C, A, D, E, V, NZ, emb_is_f64)
-        return bufs["predictions"], bufs["alphas"]
+        ctx.row_valid = bufs["row_valid"]
+        predictions._icd_row_valid = bufs["row_valid"]               # (B*T) uint8, reused by the fused loss
+        return predictions, alphas
 
     @staticmethod
     def backward(ctx, d_pred, d_alphas):

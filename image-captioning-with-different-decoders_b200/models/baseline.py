@@ -76,10 +76,11 @@ class _BaselineDecoderFn(torch.autograd.Function):
              img_features=img, captions=captions, emb_w=emb_w.contiguous(), w_ih=ws[0], w_hh=ws[1], b_ih=ws[2],
              b_hh=ws[3], lin_w=ws[4], lin_b=ws[5], **bufs)
         check(lib().icd_baseline_decoder_fwd(ctypes.byref(d), stream_ptr()), "icd_baseline_decoder_fwd")
+        outputs = bufs.pop("outputs")          # not kept in ctx: it carries this node as grad_fn (reference cycle)
         ctx.desc = d
         ctx.keep = (img, captions, emb_w, ws, bufs)
         ctx.dims = (B, L, E, H, V)
-        return bufs["outputs"]
+        return outputs
 
     @staticmethod
     def backward(ctx, d_out):

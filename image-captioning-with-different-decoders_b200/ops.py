@@ -183,3 +183,63 @@ def prof_collect():
                                  ctypes.byref(b_ms), ctypes.byref(b_n), ctypes.byref(b_r)), "icd_prof_collect")
     return dict(fwd_ms=f_ms.value, fwd_launches=f_n.value, fwd_rows=f_r.value,
                 bwd_ms=b_ms.value, bwd_launches=b_n.value, bwd_rows=b_r.value)
+
+
+# ---- bf16-stored-feature variants (tensor-core tier) ---------------------------------------------------
+def attention_step_fwd_bf16(enc16, att_enc16, att_dec, w_full, b_full, fbeta_pre=None, img_index=None):
+    """enc16 (n_img,P,C) / att_enc16 (n_img,P,A) torch.bfloat16 -> (alpha, awe_raw, gate, gated, gated16)"""
+    _need_cuda(enc16, att_enc16, att_dec)
+    assert enc16.dtype == torch.bfloat16 and att_enc16.dtype == torch.bfloat16
+    n_img, P, C = enc16.shape
+    A = att_enc16.shape[2]
+    R = att_dec.shape[0]
+    dev = enc16.device
+    alpha = torch.empty(R, P, device=dev, dtype=torch.float32)
+    awe = torch.empty(R, C, device=dev, dtype=torch.float32)
+    gate = gated = gated16 = None
+    if fbeta_pre is not None:
+        gate = torch.empty(R, C, device=dev, dtype=torch.float32)
+        gated = torch.empty(R, C, device=dev, dtype=torch.float32)
+        gated16 = torch.empty(R, C, device=dev, dtype=torch.bfloat16)
+    check(lib().icd_attention_step_fwd_bf16(
+        R, P, C, A, ptr(img_index), ptr(enc16), ptr(att_enc16), ptr(att_dec), ctypes.c_int64(att_dec.stride(0)),
+        ptr(w_full), ptr(b_full), ptr(fbeta_pre), ctypes.c_int64(fbeta_pre.stride(0) if fbeta_pre is not None else 0),
+        ptr(alpha), ctypes.c_int64(P), ptr(awe), ptr(gate), ptr(gated), ptr(gated16), stream_ptr()),
+        "icd_attention_step_fwd_bf16")
+    return alpha, awe, gate, gated, gated16
+
+
+def attention_step_bwd_bf16(enc16, att_enc16, att_dec, w_full, alpha, gate, awe_raw, d_gated, d_alpha_ext=None):
+    """-> (d_att_dec (R,A), d_fbeta_pre (R,C), d_e (R,P), dz16 (R, A+C) bf16 copy of [d_att_dec | d_fbeta_pre])"""
+    n_img, P, C = enc16.shape
+    A = att_enc16.shape[2]
+    R = att_dec.shape[0]
+    dev = enc16.device
+    d_att_dec = torch.empty(R, A, device=dev, dtype=torch.float32)
+    d_fb = torch.empty(R, C, device=dev, dtype=torch.float32)
+    d_e = torch.empty(R, P, device=dev, dtype=torch.float32)
+    dz16 = torch.empty(R, A + C, device=dev, dtype=torch.bfloat16)
+    check(lib().icd_attention_step_bwd_bf16(
+        R, P, C, A, ptr(enc16), ptr(att_enc16), ptr(att_dec), ctypes.c_int64(att_dec.stride(0)), ptr(w_full),
+        ptr(alpha), ctypes.c_int64(alpha.stride(0)),
+        ptr(d_alpha_ext), ctypes.c_int64(d_alpha_ext.stride(0) if d_alpha_ext is not None else 0),
+        ptr(gate), ptr(awe_raw), ptr(d_gated),
+        ptr(d_att_dec), ctypes.c_int64(A), ptr(d_fb), ctypes.c_int64(C), ptr(d_e), ctypes.c_int64(P),
+        ptr(dz16), ctypes.c_int64(A + C), stream_ptr()), "icd_attention_step_bwd_bf16")
+    return d_att_dec, d_fb, d_e, dz16
+
+
+def attention_proj_bwd_bf16(att_enc16, att_dec_all, w_full, d_e, bt):
+    B, P, A = att_enc16.shape
+    T = len(bt)
+    dev = att_enc16.device
+    d_att_enc = torch.empty(B, P, A, device=dev, dtype=torch.float32)
+    d_wf = torch.empty(A, device=dev, dtype=torch.float32)
+    d_bf = torch.empty(1, device=dev, dtype=torch.float32)
+    ws = torch.empty(int(lib().icd_attention_proj_bwd_ws_floats(B, P, A)), device=dev, dtype=torch.float32)
+    bt_arr = (ctypes.c_int32 * T)(*bt)
+    check(lib().icd_attention_proj_bwd_bf16(B, T, P, A, bt_arr, ptr(att_enc16), ptr(att_dec_all),
+                                            ctypes.c_int64(att_dec_all.stride(1)), ptr(w_full), ptr(d_e),
+                                            ptr(d_att_enc), ptr(d_wf), ptr(d_bf), ptr(ws), stream_ptr()),
+          "icd_attention_proj_bwd_bf16")
+    return d_att_enc, d_wf, d_bf

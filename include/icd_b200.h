@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ICD_B200_ABI_VERSION 6
+#define ICD_B200_ABI_VERSION 7
 #define ICD_MAX_STEPS 256
 
 ICD_API int icd_version(void);                       /* ICD_B200_ABI_VERSION the library was built with */
@@ -143,6 +143,33 @@ ICD_API int icd_attention_proj_bwd(int B, int T, int P, int A, const int32_t* bt
                            const float* w_full, const float* d_e,
                            float* d_att_enc, float* d_w_full, float* d_b_full,
                            float* partial, void* stream);
+
+/* bf16-STORED feature variants of the three entry points above (tensor-core tier): enc16 (n_img,P,C) and att_enc16
+ * (n_img,P,A) are bf16, all arithmetic and every other tensor stay fp32.  Optional bf16 copies of results that feed
+ * the next tensor-core contraction: gated16 (rows,C); dz16 row r at dz16 + r*ld_dz16: [d_att_dec (A) | d_fbeta_pre (C)].
+ */
+ICD_API int icd_attention_step_fwd_bf16(int rows, int P, int C, int A, const int32_t* img_index,
+                                const void* enc16, const void* att_enc16,
+                                const float* att_dec, int64_t ld_dec,
+                                const float* w_full, const float* b_full,
+                                const float* fbeta_pre, int64_t ld_fb,
+                                float* alpha, int64_t ld_alpha,
+                                float* awe_raw, float* gate, float* gated, void* gated16, void* stream);
+ICD_API int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
+                                const void* enc16, const void* att_enc16,
+                                const float* att_dec, int64_t ld_dec, const float* w_full,
+                                const float* alpha, int64_t ld_alpha,
+                                const float* d_alpha_ext, int64_t ld_dalpha,
+                                const float* gate, const float* awe_raw, const float* d_gated,
+                                float* d_att_dec, int64_t ld_ddec,
+                                float* d_fbeta_pre, int64_t ld_dfb,
+                                float* d_e, int64_t ld_de,
+                                void* dz16, int64_t ld_dz16, void* stream);
+ICD_API int icd_attention_proj_bwd_bf16(int B, int T, int P, int A, const int32_t* bt_host,
+                                const void* att_enc16, const float* att_dec_all, int64_t ld_dec,
+                                const float* w_full, const float* d_e,
+                                float* d_att_enc, float* d_w_full, float* d_b_full,
+                                float* partial, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * AttentionDecoder.forward / backward, teacher-forced (models/attention.py:218-284).

@@ -217,3 +217,51 @@ def test_gemm_bf16_transposed_forms_and_beta(cuda):
     ops.gemm(dy, x, a_strides=(1, M), b_strides=(1, N), out=c, ldc=N, M=M, N=N, K=K, beta=1.0, precision="bf16")
     ref = c0.double() + dy.bfloat16().double().t() @ x.bfloat16().double()
     H.assert_close_norm(c, ref, 2e-5, "tc gemm TN beta")
+
+
+@pytest.mark.parametrize("R,A,Cdim,use_index", [(3, 48, 2048, False), (6, 512, 2048, True), (2, 64, 512, False)])
+def test_attention_step_bf16_features_matches_oracle_on_rounded_features(cuda, R, A, Cdim, use_index):
+    """bf16-STORED features, fp32 arithmetic: feeding the oracle the same bf16-rounded features must agree to fp32
+    accuracy (1e-5) — the only approximation of this variant is the storage rounding of enc / att_enc."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(R * 13 + A)
+    P = 196
+    n_img = 3 if use_index else R
+    enc16 = torch.randn(n_img, P, Cdim, generator=g).clamp_min_(0).bfloat16()
+    att_enc16 = (torch.randn(n_img, P, A, generator=g) * 0.5).bfloat16()
+    att_dec = torch.randn(R, A, generator=g) * 0.5
+    wf = torch.randn(A, generator=g) * 0.2
+    bf = torch.randn(1, generator=g)
+    fb = torch.randn(R, Cdim, generator=g)
+    idx = torch.randint(0, n_img, (R,), generator=g) if use_index else torch.arange(R)
+    e64 = enc16.double()[idx]
+    ae64 = att_enc16.double()[idx].requires_grad_(True)
+    ad64, wf64, bf64, fb64 = (t.double().requires_grad_(True) for t in (att_dec, wf, bf, fb))
+    att = (torch.relu(ae64 + ad64.unsqueeze(1)) * wf64).sum(-1) + bf64
+    alpha64 = torch.softmax(att, dim=1)
+    awe64 = (e64 * alpha64.unsqueeze(2)).sum(1)
+    gate64 = torch.sigmoid(fb64)
+    gated64 = gate64 * awe64
+    img_index = idx.to(torch.int32).to(cuda) if use_index else None
+    alpha, awe, gate, gated, gated16 = ops.attention_step_fwd_bf16(
+        enc16.to(cuda), att_enc16.to(cuda), att_dec.to(cuda), wf.to(cuda), bf.to(cuda), fb.to(cuda), img_index)
+    H.assert_close_norm(alpha, alpha64, 1e-5, "alpha")
+    H.assert_close_norm(awe, awe64, 1e-5, "awe")
+    H.assert_close_norm(gated, gated64, 1e-5, "gated")
+    H.assert_close_norm(gated16.float(), gated64, 4e-3, "gated16")
+    if use_index:
+        return
+    d_gated = torch.randn(R, Cdim, generator=g)
+    d_alpha = torch.randn(R, P, generator=g)
+    ((gated64 * d_gated.double()).sum() + (alpha64 * d_alpha.double()).sum()).backward()
+    d_att_dec, d_fb, d_e, dz16 = ops.attention_step_bwd_bf16(enc16.to(cuda), att_enc16.to(cuda), att_dec.to(cuda),
+                                                            wf.to(cuda), alpha, gate, awe, d_gated.to(cuda),
+                                                            d_alpha.to(cuda))
+    H.assert_close_norm(d_att_dec, ad64.grad, 2e-5, "d_att_dec")
+    H.assert_close_norm(d_fb, fb64.grad, 2e-5, "d_fbeta_pre")
+    H.assert_close_norm(dz16[:, :A].float(), ad64.grad, 4e-3, "dz16[:, :A]")
+    H.assert_close_norm(dz16[:, A:].float(), fb64.grad, 4e-3, "dz16[:, A:]")
+    d_att_enc, d_wf, d_bf = ops.attention_proj_bwd_bf16(att_enc16.to(cuda), att_dec.to(cuda).view(1, R, A),
+                                                        wf.to(cuda), d_e.view(R, 1, P), [R])
+    H.assert_close_norm(d_att_enc, ae64.grad, 2e-5, "d_att_enc")
+    H.assert_close_norm(d_wf, wf64.grad, 2e-5, "d_w_full")
