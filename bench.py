@@ -33,8 +33,12 @@ V, A, D, E, P, C, MAXLEN = 9490, 512, 512, 512, 196, 2048, 25
 B_PER_GPU = 512
 CPU_SAMPLE_B = 32
 # fused attention step, forward, fp32 features: P*C*4 + P*A*4 + (A + C + C + P)*4 per (image, step)
-ATT_FWD_BYTES_PER_ROW = P * C * 4 + P * A * 4 + (A + C + C + P) * 4        # = 2 026 256
-ATT_BWD_BYTES_PER_ROW = P * C * 4 + P * A * 4 + (3 * C + 2 * A + 3 * P + C) * 4
+# (= 2 026 256 B); with bf16-STORED features (the bf16 tier) the two big streams halve: 1 022 736 B.
+def att_bytes_per_row(precision):
+    s = 2 if precision == "bf16" else 4
+    fwd = P * C * s + P * A * s + (A + C + C + P) * 4
+    bwd = P * C * s + P * A * s + (3 * C + 2 * A + 3 * P + C) * 4
+    return fwd, bwd
 
 
 def parse():
@@ -129,7 +133,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -252,11 +256,10 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None     # started before warm-up: NVML start-up stalls launches
     for _ in range(max(args.warmup, 3)):
         train_step(enc_d, caps_d)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    time.sleep(0.3)
     ops.prof_enable(True)
     launches0 = ops.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -327,6 +330,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
+        ATT_FWD_BYTES_PER_ROW, ATT_BWD_BYTES_PER_ROW = att_bytes_per_row(precision)
         fwd_s = prof["fwd_ms"] / 1e3
         achieved = (ATT_FWD_BYTES_PER_ROW * prof["fwd_rows"] / fwd_s / 1e9) if fwd_s > 0 else None
         bwd_s = prof["bwd_ms"] / 1e3
@@ -342,14 +346,16 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {
-                "kernel": "att_step_fwd_kernel (fused additive-attention step, forward)",
+                "kernel": ("att_step_fwd_bf16_kernel" if precision == "bf16" else "att_step_fwd_kernel") +
+                          " (fused additive-attention step, forward)",
+                "feature_storage": "bf16" if precision == "bf16" else "fp32",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(),
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_row": ATT_FWD_BYTES_PER_ROW,
                 "launches": prof["fwd_launches"], "avg_launch_ms": (prof["fwd_ms"] / prof["fwd_launches"]) if prof["fwd_launches"] else None,
                 "share_of_step": (prof["fwd_ms"] / ms_total) if ms_total else None,
-                "bwd": {"kernel": "att_step_bwd_kernel", "achieved": achieved_bwd,
+                "bwd": {"kernel": "att_step_bwd_bf16_kernel" if precision == "bf16" else "att_step_bwd_kernel", "achieved": achieved_bwd,
                         "frac": (achieved_bwd / peak) if achieved_bwd else None,
                         "algorithmic_bytes_per_row": ATT_BWD_BYTES_PER_ROW,
                         "share_of_step": (prof["bwd_ms"] / ms_total) if ms_total else None},

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256, 4) att_step_fwd_bf16_kernel(
 // ------------------------------------------------------------------------------------------------
 // backward: grid = rows, block = 256.  smem: C + 2*A + 2*Ppad + 40 + 3*8*(A/8) floats
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3) att_step_bwd_bf16_kernel(
+__global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
         int P, int C, int A,
         const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* __restrict__ att_enc,
         const float* __restrict__ att_dec, long long ld_dec, const float* __restrict__ w_full,
