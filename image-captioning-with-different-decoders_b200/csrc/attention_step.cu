@@ -353,13 +353,15 @@ __global__ void __launch_bounds__(256) att_step_bwd_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
-// After the loop: d_att_enc + full_att parameter gradients.
-// grid = (ceil(P/PB), B), block = A/4 threads (each 4 consecutive a).  smem: T*A (att_dec) + T*PB (d_e).
-// partial[(b*gridDim.x + chunk)*(A+4) + ...]: per-CTA d_w_full[A] and d_b_full.
+// After the loop: d_att_enc + full_att / enc_att-bias parameter gradients.
+//   d_att_enc[b,p,a] = w_full[a] * sum_t d_e[b,t,p] * [att_enc[b,p,a] + att_dec[t,b,a] > 0]
+// grid = (ceil(P/PB), B), block = A/4 threads (each 4 consecutive a), 4 pixels per pass so that one 128-bit
+// shared-memory read of att_dec[t, a..a+3] feeds 16 updates.  smem: T*A (att_dec) + T*PB (d_e).
+// partial[(b*gridDim.x + chunk)*(2A+4)] = { d_w_full[A], colsum_p d_att_enc[A] (-> d enc_att.bias), sum d_e, 0,0,0 }.
 // ------------------------------------------------------------------------------------------------
 constexpr int PROJ_PB = 28;
 
-__global__ void att_proj_bwd_kernel(int B, int T, int P, int A, int len_b_unused,
+__global__ void att_proj_bwd_kernel(int B, int T, int P, int A,
                                     const int* __restrict__ row_len,   // [B] number of active steps of row b
                                     const float* __restrict__ att_enc, const float* __restrict__ att_dec_all,
                                     long long ld_dec, const float* __restrict__ w_full,
@@ -372,9 +374,10 @@ __global__ void att_proj_bwd_kernel(int B, int T, int P, int A, int len_b_unused
     float* s_dec = sm;                  // Tb * A
     float* s_de = sm + (size_t)T * A;   // Tb * PROJ_PB
     float* s_red = s_de + (size_t)T * PROJ_PB;   // 40
-    for (int i = threadIdx.x; i < Tb * A; i += blockDim.x) {
-        const int t = i / A, a = i % A;
-        s_dec[i] = att_dec_all[((long long)t * B + b) * ld_dec + a];
+    for (int i = threadIdx.x; i < Tb * (A >> 2); i += blockDim.x) {
+        const int t = i / (A >> 2), a4 = (i % (A >> 2)) * 4;
+        *reinterpret_cast<float4*>(s_dec + (size_t)t * A + a4) =
+            *reinterpret_cast<const float4*>(att_dec_all + ((long long)t * B + b) * ld_dec + a4);
     }
     float de_sum = 0.f;
     for (int i = threadIdx.x; i < Tb * PROJ_PB; i += blockDim.x) {
@@ -385,30 +388,53 @@ __global__ void att_proj_bwd_kernel(int B, int T, int P, int A, int len_b_unused
     }
     __syncthreads();
     const int a = threadIdx.x * 4;
-    float4 wacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 wacc = make_float4(0.f, 0.f, 0.f, 0.f), bacc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a < A) {
         const float4 w = *reinterpret_cast<const float4*>(w_full + a);
-        for (int pp = 0; pp < np; ++pp) {
-            const long long o = ((long long)b * P + p0 + pp) * A + a;
-            const float4 x = *reinterpret_cast<const float4*>(att_enc + o);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int t = 0; t < Tb; ++t) {
-                const float de = s_de[t * PROJ_PB + pp];
-                const float4 d = *reinterpret_cast<const float4*>(s_dec + (size_t)t * A + a);
-                const float s0 = x.x + d.x, s1 = x.y + d.y, s2 = x.z + d.z, s3 = x.w + d.w;
-                acc.x += (s0 > 0.f) ? de : 0.f;  wacc.x = fmaf(de, fmaxf(s0, 0.f), wacc.x);
-                acc.y += (s1 > 0.f) ? de : 0.f;  wacc.y = fmaf(de, fmaxf(s1, 0.f), wacc.y);
-                acc.z += (s2 > 0.f) ? de : 0.f;  wacc.z = fmaf(de, fmaxf(s2, 0.f), wacc.z);
-                acc.w += (s3 > 0.f) ? de : 0.f;  wacc.w = fmaf(de, fmaxf(s3, 0.f), wacc.w);
+        for (int pq = 0; pq < np; pq += 4) {                          // PROJ_PB % 4 == 0; rows >= np carry d_e = 0
+            float x[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int pp = min(pq + u, np - 1);
+                const float4 raw = ld_stream_f4(att_enc + ((long long)b * P + p0 + pp) * A + a);
+                x[u][0] = raw.x; x[u][1] = raw.y; x[u][2] = raw.z; x[u][3] = raw.w;
             }
-            *reinterpret_cast<float4*>(d_att_enc + o) =
-                    make_float4(acc.x * w.x, acc.y * w.y, acc.z * w.z, acc.w * w.w);
+            float acc[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[u][i] = 0.f;
+            for (int t = 0; t < Tb; ++t) {
+                const float4 de4 = *reinterpret_cast<const float4*>(s_de + t * PROJ_PB + pq);
+                const float4 d = *reinterpret_cast<const float4*>(s_dec + (size_t)t * A + a);
+                const float de[4] = {de4.x, de4.y, de4.z, de4.w};
+                const float dd[4] = {d.x, d.y, d.z, d.w};
+                float wl[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float sv = x[u][i] + dd[i];
+                        acc[u][i] += (sv > 0.f) ? de[u] : 0.f;
+                        wl[i] = fmaf(de[u], fmaxf(sv, 0.f), wl[i]);
+                    }
+                }
+                wacc.x += wl[0]; wacc.y += wl[1]; wacc.z += wl[2]; wacc.w += wl[3];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (pq + u >= np) break;
+                const long long o = ((long long)b * P + p0 + pq + u) * A + a;
+                const float4 r = make_float4(acc[u][0] * w.x, acc[u][1] * w.y, acc[u][2] * w.z, acc[u][3] * w.w);
+                bacc.x += r.x; bacc.y += r.y; bacc.z += r.z; bacc.w += r.w;
+                *reinterpret_cast<float4*>(d_att_enc + o) = r;
+            }
         }
     }
-    float* mine = partial + ((long long)b * gridDim.x + blockIdx.x) * (A + 4);
-    if (a < A) *reinterpret_cast<float4*>(mine + a) = wacc;
+    float* mine = partial + ((long long)b * gridDim.x + blockIdx.x) * (2 * A + 4);
+    if (a < A) { *reinterpret_cast<float4*>(mine + a) = wacc; *reinterpret_cast<float4*>(mine + A + a) = bacc; }
     const float tot = block_sum(de_sum, s_red);
-    if (threadIdx.x == 0) { mine[A] = tot; mine[A + 1] = 0.f; mine[A + 2] = 0.f; mine[A + 3] = 0.f; }
+    if (threadIdx.x == 0) { mine[2 * A] = tot; mine[2 * A + 1] = 0.f; mine[2 * A + 2] = 0.f; mine[2 * A + 3] = 0.f; }
 }
 
 struct BtPack { int v[ICD_MAX_STEPS]; };
@@ -500,21 +526,23 @@ extern "C" int icd_attention_step_bwd(int rows, int P, int C, int A,
 
 extern "C" int64_t icd_attention_proj_bwd_ws_floats(int B, int P, int A) {
     const int64_t chunks = (P + PROJ_PB - 1) / PROJ_PB;
-    // per-CTA partials + [B] int row lengths (stored as 4-byte words at the end)
-    return (int64_t)B * chunks * (A + 4) + B + 8;
+    // per-CTA partials (d_w_full[A] | d_b_enc[A] | sum d_e + pad) + [B] int row lengths (4-byte words at the end)
+    return (int64_t)B * chunks * (2 * A + 4) + B + 8;
 }
 
 extern "C" int icd_attention_proj_bwd(int B, int T, int P, int A, const int32_t* bt_host,
                                       const float* att_enc, const float* att_dec_all, int64_t ld_dec,
                                       const float* w_full, const float* d_e,
-                                      float* d_att_enc, float* d_w_full, float* d_b_full,
+                                      float* d_att_enc, float* d_w_full, float* d_b_full, float* d_b_enc,
                                       float* partial, void* stream) {
     cudaStream_t s = icd_stream(stream);
     ICD_CHECK_ARG(T > 0 && T <= ICD_MAX_STEPS, "attention_proj_bwd: T=%d out of range", T);
     ICD_CHECK_ARG(A % 4 == 0 && A / 4 <= 1024, "attention_proj_bwd: A=%d unsupported", A);
+    ICD_CHECK_ARG(ld_dec % 4 == 0, "attention_proj_bwd: ld_dec must be a multiple of 4");
     ICD_CHECK_ARG(B <= 65535, "attention_proj_bwd: B too large");
     const int chunks = (P + PROJ_PB - 1) / PROJ_PB;
-    int* row_len = reinterpret_cast<int*>(partial + (int64_t)B * chunks * (A + 4));
+    const int W = 2 * A + 4;
+    int* row_len = reinterpret_cast<int*>(partial + (int64_t)B * chunks * W);
     BtPack pack;
     for (int t = 0; t < ICD_MAX_STEPS; ++t) pack.v[t] = t < T ? bt_host[t] : 0;
     row_len_from_pack_kernel<<<(B + 127) / 128, 128, 0, s>>>(B, T, pack, row_len);
@@ -530,11 +558,12 @@ extern "C" int icd_attention_proj_bwd(int B, int T, int P, int A, const int32_t*
     }
     int threads = ((A / 4 + 31) / 32) * 32;
     dim3 grid(chunks, B);
-    att_proj_bwd_kernel<<<grid, threads, smem, s>>>(B, T, P, A, 0, row_len, att_enc, att_dec_all, ld_dec, w_full,
+    att_proj_bwd_kernel<<<grid, threads, smem, s>>>(B, T, P, A, row_len, att_enc, att_dec_all, ld_dec, w_full,
                                                      d_e, d_att_enc, partial);
     ICD_LAUNCH_CHECK();
-    // reduce the per-CTA partials: columns [0,A) -> d_w_full, column A -> d_b_full
-    ICD_TRY(icd_colsum(partial, A + 4, (int64_t)B * chunks, A, nullptr, d_w_full, s));
-    ICD_TRY(icd_colsum(partial + A, A + 4, (int64_t)B * chunks, 1, nullptr, d_b_full, s));
+    // reduce the per-CTA partials: [0,A) -> d_w_full, [A,2A) -> d enc_att.bias, column 2A -> d_b_full
+    ICD_TRY(icd_colsum(partial, W, (int64_t)B * chunks, A, nullptr, d_w_full, s));
+    if (d_b_enc) ICD_TRY(icd_colsum(partial + A, W, (int64_t)B * chunks, A, nullptr, d_b_enc, s));
+    ICD_TRY(icd_colsum(partial + 2 * A, W, (int64_t)B * chunks, 1, nullptr, d_b_full, s));
     return 0;
 }

@@ -327,7 +327,13 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
-// after the loop: d_att_enc + full_att parameter gradients, att_enc stored as bf16
+// after the loop: d_att_enc + full_att / enc_att-bias parameter gradients, att_enc stored as bf16.
+//   d_att_enc[b,p,a] = w_full[a] * sum_t d_e[b,t,p] * [att_enc[b,p,a] + att_dec[t,b,a] > 0]
+// grid = (ceil(P/PROJ_PB), B), block = A/4 threads (each 4 consecutive a), 4 pixels per pass so that one 128-bit
+// shared-memory read of att_dec[t, a..a+3] feeds 16 updates.  smem: T*A (att_dec) + T*PROJ_PB (d_e).
+// Outputs: d_att_enc fp32 and / or bf16 (either may be NULL: the bf16 tier only needs the bf16 copy, which is the
+// MN-major A operand of the enc_att weight-gradient contraction) and per-CTA partials
+//   partial[(b*gridDim.x + chunk)*(2A+4)] = { d_w_full[A], colsum_p d_att_enc[A] (-> d enc_att.bias), sum d_e, 0,0,0 }.
 // ------------------------------------------------------------------------------------------------
 constexpr int PROJ_PB = 28;
 
@@ -335,7 +341,8 @@ __global__ void att_proj_bwd_bf16_kernel(int B, int T, int P, int A, const int* 
                                          const __nv_bfloat16* __restrict__ att_enc,
                                          const float* __restrict__ att_dec_all, long long ld_dec,
                                          const float* __restrict__ w_full, const float* __restrict__ d_e,
-                                         float* __restrict__ d_att_enc, float* __restrict__ partial) {
+                                         float* __restrict__ d_att_enc, __nv_bfloat16* __restrict__ d_att_enc16,
+                                         float* __restrict__ partial) {
     extern __shared__ __align__(16) float sm[];
     const int b = blockIdx.y, p0 = blockIdx.x * PROJ_PB;
     const int np = min(PROJ_PB, P - p0);
@@ -343,9 +350,10 @@ __global__ void att_proj_bwd_bf16_kernel(int B, int T, int P, int A, const int* 
     float* s_dec = sm;
     float* s_de = sm + (size_t)T * A;
     float* s_red = s_de + (size_t)T * PROJ_PB;
-    for (int i = threadIdx.x; i < Tb * A; i += blockDim.x) {
-        const int t = i / A, a = i % A;
-        s_dec[i] = att_dec_all[((long long)t * B + b) * ld_dec + a];
+    for (int i = threadIdx.x; i < Tb * (A >> 2); i += blockDim.x) {
+        const int t = i / (A >> 2), a4 = (i % (A >> 2)) * 4;
+        *reinterpret_cast<float4*>(s_dec + (size_t)t * A + a4) =
+            *reinterpret_cast<const float4*>(att_dec_all + ((long long)t * B + b) * ld_dec + a4);
     }
     float de_sum = 0.f;
     for (int i = threadIdx.x; i < Tb * PROJ_PB; i += blockDim.x) {
@@ -356,31 +364,100 @@ __global__ void att_proj_bwd_bf16_kernel(int B, int T, int P, int A, const int* 
     }
     __syncthreads();
     const int a = threadIdx.x * 4;
-    float4 wacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 wacc = make_float4(0.f, 0.f, 0.f, 0.f), bacc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a < A) {
         const float4 w = *reinterpret_cast<const float4*>(w_full + a);
-        for (int pp = 0; pp < np; ++pp) {
-            const long long o = ((long long)b * P + p0 + pp) * A + a;
-            const uint2 raw = ld_stream_u2(att_enc + o);
-            const float x0 = __uint_as_float(raw.x << 16), x1 = __uint_as_float(raw.x & 0xffff0000u);
-            const float x2 = __uint_as_float(raw.y << 16), x3 = __uint_as_float(raw.y & 0xffff0000u);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int t = 0; t < Tb; ++t) {
-                const float de = s_de[t * PROJ_PB + pp];
-                const float4 d = *reinterpret_cast<const float4*>(s_dec + (size_t)t * A + a);
-                const float s0 = x0 + d.x, s1 = x1 + d.y, s2 = x2 + d.z, s3 = x3 + d.w;
-                acc.x += (s0 > 0.f) ? de : 0.f;  wacc.x = fmaf(de, fmaxf(s0, 0.f), wacc.x);
-                acc.y += (s1 > 0.f) ? de : 0.f;  wacc.y = fmaf(de, fmaxf(s1, 0.f), wacc.y);
-                acc.z += (s2 > 0.f) ? de : 0.f;  wacc.z = fmaf(de, fmaxf(s2, 0.f), wacc.z);
-                acc.w += (s3 > 0.f) ? de : 0.f;  wacc.w = fmaf(de, fmaxf(s3, 0.f), wacc.w);
+        for (int pq = 0; pq < np; pq += 4) {                          // PROJ_PB is a multiple of 4; rows >= np carry d_e = 0
+            float x[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int pp = min(pq + u, np - 1);
+                const uint2 raw = ld_stream_u2(att_enc + ((long long)b * P + p0 + pp) * A + a);
+                x[u][0] = __uint_as_float(raw.x << 16); x[u][1] = __uint_as_float(raw.x & 0xffff0000u);
+                x[u][2] = __uint_as_float(raw.y << 16); x[u][3] = __uint_as_float(raw.y & 0xffff0000u);
             }
-            *reinterpret_cast<float4*>(d_att_enc + o) = make_float4(acc.x * w.x, acc.y * w.y, acc.z * w.z, acc.w * w.w);
+            float acc[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[u][i] = 0.f;
+            for (int t = 0; t < Tb; ++t) {
+                const float4 de4 = *reinterpret_cast<const float4*>(s_de + t * PROJ_PB + pq);
+                const float4 d = *reinterpret_cast<const float4*>(s_dec + (size_t)t * A + a);
+                const float de[4] = {de4.x, de4.y, de4.z, de4.w};
+                const float dd[4] = {d.x, d.y, d.z, d.w};
+                float wl[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float sv = x[u][i] + dd[i];
+                        acc[u][i] += (sv > 0.f) ? de[u] : 0.f;
+                        wl[i] = fmaf(de[u], fmaxf(sv, 0.f), wl[i]);
+                    }
+                }
+                wacc.x += wl[0]; wacc.y += wl[1]; wacc.z += wl[2]; wacc.w += wl[3];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (pq + u >= np) break;
+                const long long o = ((long long)b * P + p0 + pq + u) * A + a;
+                const float4 r = make_float4(acc[u][0] * w.x, acc[u][1] * w.y, acc[u][2] * w.z, acc[u][3] * w.w);
+                bacc.x += r.x; bacc.y += r.y; bacc.z += r.z; bacc.w += r.w;
+                if (d_att_enc) *reinterpret_cast<float4*>(d_att_enc + o) = r;
+                if (d_att_enc16) *reinterpret_cast<uint2*>(d_att_enc16 + o) = make_uint2(pack2(r.x, r.y), pack2(r.z, r.w));
+            }
         }
     }
-    float* mine = partial + ((long long)b * gridDim.x + blockIdx.x) * (A + 4);
-    if (a < A) *reinterpret_cast<float4*>(mine + a) = wacc;
+    float* mine = partial + ((long long)b * gridDim.x + blockIdx.x) * (2 * A + 4);
+    if (a < A) { *reinterpret_cast<float4*>(mine + a) = wacc; *reinterpret_cast<float4*>(mine + A + a) = bacc; }
     const float tot = block_sum(de_sum, s_red);
-    if (threadIdx.x == 0) { mine[A] = tot; mine[A + 1] = 0.f; mine[A + 2] = 0.f; mine[A + 3] = 0.f; }
+    if (threadIdx.x == 0) { mine[2 * A] = tot; mine[2 * A + 1] = 0.f; mine[2 * A + 2] = 0.f; mine[2 * A + 3] = 0.f; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 features -> bf16 features + pixel mean in ONE pass over encoder_out (models/attention.py:161 mean(dim=1)).
+// grid = (ceil(C/256), B), block = 256 = 4 pixel groups x 64 float4 lanes.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) convert_features_kernel(int P, int C, const float* __restrict__ enc,
+                                                               __nv_bfloat16* __restrict__ enc16,
+                                                               float* __restrict__ mean, __nv_bfloat16* __restrict__ mean16) {
+    __shared__ float4 s_part[3 * 64];
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int c = blockIdx.x * 256 + lane * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) {
+        const float* base = enc + (long long)b * P * C + c;
+        __nv_bfloat16* ob = enc16 + (long long)b * P * C + c;
+        int p = grp;
+        for (; p + 6 * 4 < P; p += 7 * 4) {
+            float4 x[7];
+#pragma unroll
+            for (int u = 0; u < 7; ++u) x[u] = ld_stream_f4(base + (long long)(p + 4 * u) * C);
+#pragma unroll
+            for (int u = 0; u < 7; ++u) {
+                acc.x += x[u].x; acc.y += x[u].y; acc.z += x[u].z; acc.w += x[u].w;
+                *reinterpret_cast<uint2*>(ob + (long long)(p + 4 * u) * C) = make_uint2(pack2(x[u].x, x[u].y), pack2(x[u].z, x[u].w));
+            }
+        }
+        for (; p < P; p += 4) {
+            const float4 x = ld_stream_f4(base + (long long)p * C);
+            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+            *reinterpret_cast<uint2*>(ob + (long long)p * C) = make_uint2(pack2(x.x, x.y), pack2(x.z, x.w));
+        }
+    }
+    if (grp > 0) s_part[(grp - 1) * 64 + lane] = acc;
+    __syncthreads();
+    if (grp == 0 && c < C) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) { const float4 o = s_part[g * 64 + lane]; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+        const float inv = (float)P;
+        acc.x /= inv; acc.y /= inv; acc.z /= inv; acc.w /= inv;
+        const long long o = (long long)b * C + c;
+        if (mean) *reinterpret_cast<float4*>(mean + o) = acc;
+        if (mean16) *reinterpret_cast<uint2*>(mean16 + o) = make_uint2(pack2(acc.x, acc.y), pack2(acc.z, acc.w));
+    }
 }
 
 struct BtPack { int v[ICD_MAX_STEPS]; };
@@ -460,14 +537,16 @@ extern "C" int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
 extern "C" int icd_attention_proj_bwd_bf16(int B, int T, int P, int A, const int32_t* bt_host,
                                            const void* att_enc16, const float* att_dec_all, int64_t ld_dec,
                                            const float* w_full, const float* d_e,
-                                           float* d_att_enc, float* d_w_full, float* d_b_full,
-                                           float* partial, void* stream) {
+                                           float* d_att_enc, void* d_att_enc16, float* d_w_full, float* d_b_full,
+                                           float* d_b_enc, float* partial, void* stream) {
     cudaStream_t s = icd_stream(stream);
     ICD_CHECK_ARG(T > 0 && T <= ICD_MAX_STEPS, "attention_proj_bwd_bf16: T=%d out of range", T);
     ICD_CHECK_ARG(A % 4 == 0 && A / 4 <= 1024, "attention_proj_bwd_bf16: A=%d unsupported", A);
+    ICD_CHECK_ARG(ld_dec % 4 == 0, "attention_proj_bwd_bf16: ld_dec must be a multiple of 4");
     ICD_CHECK_ARG(B <= 65535, "attention_proj_bwd_bf16: B too large");
     const int chunks = (P + PROJ_PB - 1) / PROJ_PB;
-    int* row_len = reinterpret_cast<int*>(partial + (int64_t)B * chunks * (A + 4));
+    const int W = 2 * A + 4;
+    int* row_len = reinterpret_cast<int*>(partial + (int64_t)B * chunks * W);
     BtPack pack;
     for (int t = 0; t < ICD_MAX_STEPS; ++t) pack.v[t] = t < T ? bt_host[t] : 0;
     row_len_from_pack_kernel16<<<(B + 127) / 128, 128, 0, s>>>(B, T, pack, row_len);
@@ -483,9 +562,20 @@ extern "C" int icd_attention_proj_bwd_bf16(int B, int T, int P, int A, const int
     dim3 grid(chunks, B);
     att_proj_bwd_bf16_kernel<<<grid, threads, smem, s>>>(B, T, P, A, row_len,
                                                           reinterpret_cast<const __nv_bfloat16*>(att_enc16),
-                                                          att_dec_all, ld_dec, w_full, d_e, d_att_enc, partial);
+                                                          att_dec_all, ld_dec, w_full, d_e, d_att_enc,
+                                                          reinterpret_cast<__nv_bfloat16*>(d_att_enc16), partial);
     ICD_LAUNCH_CHECK();
-    ICD_TRY(icd_colsum(partial, A + 4, (int64_t)B * chunks, A, nullptr, d_w_full, s));
-    ICD_TRY(icd_colsum(partial + A, A + 4, (int64_t)B * chunks, 1, nullptr, d_b_full, s));
+    ICD_TRY(icd_colsum(partial, W, (int64_t)B * chunks, A, nullptr, d_w_full, s));
+    if (d_b_enc) ICD_TRY(icd_colsum(partial + A, W, (int64_t)B * chunks, A, nullptr, d_b_enc, s));
+    ICD_TRY(icd_colsum(partial + 2 * A, W, (int64_t)B * chunks, 1, nullptr, d_b_full, s));
+    return 0;
+}
+
+int icd_convert_features_bf16(int B, int P, int C, const float* enc, void* enc16, float* mean, void* mean16, cudaStream_t s) {
+    ICD_CHECK_ARG(C % 4 == 0 && B <= 65535, "convert_features: C=%d must be a multiple of 4, B <= 65535", C);
+    dim3 grid((C + 255) / 256, B);
+    convert_features_kernel<<<grid, 256, 0, s>>>(P, C, enc, reinterpret_cast<__nv_bfloat16*>(enc16), mean,
+                                                 reinterpret_cast<__nv_bfloat16*>(mean16));
+    ICD_LAUNCH_CHECK();
     return 0;
 }

@@ -212,8 +212,8 @@ extern "C" int icd_attention_decoder_bwd(const icd_att_desc_t* d, void* stream) 
     }
     // attention projections: d_att_enc for all steps at once, full_att grads, then enc_att grads (:54)
     ICD_TRY(icd_attention_proj_bwd(B, T, P, A, d->bt_host, d->att_enc, d->z, NZ, d->full_att_w, d->d_e,
-                                   d->d_att_enc, d->d_full_att_w, d->d_full_att_b, d->proj_partial, stream));
-    ICD_TRY(icd_colsum(d->d_att_enc, A, (int64_t)B * P, A, nullptr, d->d_enc_att_b, s));
+                                   d->d_att_enc, d->d_full_att_w, d->d_full_att_b, d->d_enc_att_b, d->proj_partial,
+                                   stream));
     ICD_TRY(icd_gemm_simple(prec, d->d_att_enc, 1, A, d->enc, 1, C, d->d_enc_att_w, C, A, C, B * P,
                             nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s, ICD_GEMM_ALLOW_SPLITK));
     return 0;

@@ -26,41 +26,60 @@ __global__ void row_valid_kernel16(int B, int T, const BtPack bt, unsigned char*
 
 inline int64_t up8(int64_t x) { return (x + 7) / 8 * 8; }
 
-// bump allocator over the caller's arena; element type is bf16 (2 bytes)
+// bump allocator over the caller's arena
 struct Arena {
     char* base; int64_t cap, off; bool ok;
-    void* take(int64_t rows, int64_t ld) {
-        const int64_t bytes = (rows * ld * 2 + 255) / 256 * 256;
+    void* take_bytes(int64_t bytes) {
+        bytes = (bytes + 255) / 256 * 256;
         void* p = base ? base + off : nullptr;
         off += bytes;
         if (base && off > cap) ok = false;
         return p;
     }
+    void* take(int64_t rows, int64_t ld) { return take_bytes(rows * ld * 2); }      // bf16 elements
 };
 
-// every bf16 buffer of the tier, carved in a fixed order so forward and backward agree on the layout
+// every bf16 buffer of the tier, carved in a fixed order so forward and backward agree on the layout.
+// No transposed copies exist: the tensor-core kernel consumes MN-major operands directly (gemm_tc.cu).
 struct Bufs {
-    void *We, *Wcat, *WihE, *WihC, *Wh, *Wc, *Wfc;                 // weights, K-major
-    void *enc, *att_enc, *mean, *embx, *h, *gated, *hdrop;         // forward activations, K-major
-    void *WcatT, *WihCT, *WihET, *WfcT;                            // backward: transposed weights
-    void *dY, *dYT, *hdropT, *dz, *dzT, *hT, *embxT, *gatedT, *dhT, *dcT, *meanT, *daeT, *encT;
-    int64_t ldE, ldV, ldTB, ldB, ldBP, ldBT;
+    void *We, *Wcat, *WihE, *WihC, *Wh, *Wc, *Wfc;                 // weights [out, in] (K-major for y = x W^T, MN-major B for dX = dY W)
+    void *enc, *att_enc, *mean, *embx, *h, *gated, *hdrop;         // forward activations [rows, features]
+    void *dY, *dz, *dh, *dc, *dae;                                 // backward: [rows, features]
+    float* splitk; int64_t splitk_floats;                          // deterministic split-K slices
+    int64_t ldE, ldV;
 };
 
 void carve(const icd_att_desc_t* d, Arena& a, Bufs& b) {
     const int64_t B = d->B, T = d->T, P = d->P, C = d->C, A = d->A, D = d->D, E = d->E, V = d->V;
     const int64_t NZ = A + C + 4 * D, TB = T * B;
-    b.ldE = up8(E); b.ldV = up8(V); b.ldTB = up8(TB); b.ldB = up8(B); b.ldBP = up8(B * P); b.ldBT = up8(B * T);
+    b.ldE = up8(E); b.ldV = up8(V);
     b.We = a.take(A, C); b.Wcat = a.take(NZ, D); b.WihE = a.take(4 * D, b.ldE); b.WihC = a.take(4 * D, C);
     b.Wh = a.take(D, C); b.Wc = a.take(D, C); b.Wfc = a.take(V, D);
     b.enc = a.take(B * P, C); b.att_enc = a.take(B * P, A); b.mean = a.take(B, C); b.embx = a.take(TB, b.ldE);
     b.h = a.take(TB + B, D);
     b.gated = a.take(TB, C); b.hdrop = a.take(B * T, D);
-    b.WcatT = a.take(D, NZ); b.WihCT = a.take(C, 4 * D); b.WihET = a.take(E, 4 * D); b.WfcT = a.take(D, b.ldV);
-    b.dY = a.take(B * T, b.ldV); b.dYT = a.take(V, b.ldBT); b.hdropT = a.take(D, b.ldBT);
-    b.dz = a.take(TB, NZ); b.dzT = a.take(NZ, b.ldTB); b.hT = a.take(D, b.ldTB); b.embxT = a.take(E, b.ldTB);
-    b.gatedT = a.take(C, b.ldTB); b.dhT = a.take(D, b.ldB); b.dcT = a.take(D, b.ldB); b.meanT = a.take(C, b.ldB);
-    b.daeT = a.take(A, b.ldBP); b.encT = a.take(C, b.ldBP);
+    b.dY = a.take(B * T, b.ldV); b.dz = a.take(TB, NZ); b.dh = a.take(B, D); b.dc = a.take(B, D);
+    b.dae = a.take(B * P, A);
+    // split-K workspace: the largest request among the contractions that may split
+    const int shapes[][3] = {
+        {(int)B, (int)D, (int)C},            // h_lin / c_lin
+        {(int)B, (int)NZ, (int)D},           // z = h W_cat^T
+        {(int)B, (int)(4 * D), (int)C},      // gates
+        {(int)B, (int)C, (int)(4 * D)},      // d_gated
+        {(int)B, (int)D, (int)NZ},           // dh
+        {(int)D, (int)C, (int)B},            // d h_lin / c_lin weights
+        {(int)NZ, (int)D, (int)TB},          // d W_cat
+        {(int)(4 * D), (int)E, (int)TB},     // d W_ih (embedding part)
+        {(int)(4 * D), (int)C, (int)TB},     // d W_ih (awe part)
+        {(int)TB, (int)E, (int)(4 * D)},     // d emb_x
+        {(int)A, (int)C, (int)(B * P)},      // d enc_att.weight
+        {(int)V, (int)D, (int)(B * T)},      // d fc.weight
+        {(int)(B * T), (int)D, (int)V},      // d hdrop
+    };
+    int64_t f = 0;
+    for (const auto& sh : shapes) { const int64_t n = icd_gemm_bf16_splitk_floats(sh[0], sh[1], sh[2]); if (n > f) f = n; }
+    b.splitk_floats = f;
+    b.splitk = reinterpret_cast<float*>(a.take_bytes(f * 4));
 }
 
 int check16(const icd_att_desc_t* d, Arena& a, Bufs& b) {
@@ -73,13 +92,17 @@ int check16(const icd_att_desc_t* d, Arena& a, Bufs& b) {
     return 0;
 }
 
-#define CVT(src, sr, sc, rows, cols, dst, ld) ICD_TRY(icd_convert_bf16((src), (sr), (sc), (rows), (cols), (dst), (ld), s))
-#define MM(A16, lda, B16, ldb, Cp, ldc, M, N, K, b1, b2, a1, l1, a2, l2, mask, beta) \
-    ICD_TRY(icd_gemm_bf16((A16), (lda), (B16), (ldb), (Cp), (ldc), (M), (N), (K), (b1), (b2), (a1), (l1), (a2), (l2), (mask), (beta), s))
+#define CVT(src, sr, rows, cols, dst, ld) ICD_TRY(icd_convert_bf16((src), (sr), 1, (rows), (cols), (dst), (ld), s))
+// C[M,N] (+ optional bf16 copy) = A * B^T + epilogue; amn / bmn: operand stored [K][M] / [K][N] (MN-major)
+#define MMX(A16, lda, amn, B16, ldb, bmn, Cp, ldc, M, N, K, b1, b2, a1, l1, a2, l2, mask, C16, ldc16) \
+    ICD_TRY(icd_gemm_bf16_ex((A16), (lda), (amn), (B16), (ldb), (bmn), (Cp), (ldc), (M), (N), (K), (b1), (b2), (a1), (l1), \
+                             (a2), (l2), (mask), 0.f, s, (C16), (ldc16), u.splitk, u.splitk_floats))
 
 inline char* at16(void* p, int64_t elem_off) { return reinterpret_cast<char*>(p) + elem_off * 2; }
 
 }  // namespace
+
+int icd_convert_features_bf16(int B, int P, int C, const float* enc, void* enc16, float* mean, void* mean16, cudaStream_t s);
 
 int64_t icd_att_tc_ws_bytes(const icd_att_desc_t* d) {
     Arena a; a.base = nullptr; a.cap = 0; a.off = 0; a.ok = true;
@@ -100,9 +123,9 @@ int icd_attention_decoder_fwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
     row_valid_kernel16<<<(B * T + 255) / 256, 256, 0, s>>>(B, T, pack, d->row_valid);
     ICD_LAUNCH_CHECK();
     ICD_CUDA(cudaMemsetAsync(d->alphas, 0, sizeof(float) * (size_t)B * T * P, s));
-    ICD_CUDA(cudaMemsetAsync(d->hdrop, 0, sizeof(float) * (size_t)B * T * D, s));
-    ICD_CUDA(cudaMemsetAsync(u.hdrop, 0, (size_t)B * T * D * 2, s));
-    if (d->bt_host[T - 1] < B) {
+    if (d->bt_host[T - 1] < B) {          // ragged batch: rows that go inactive must read as zeros later
+        ICD_CUDA(cudaMemsetAsync(d->hdrop, 0, sizeof(float) * (size_t)B * T * D, s));
+        ICD_CUDA(cudaMemsetAsync(u.hdrop, 0, (size_t)B * T * D * 2, s));
         ICD_CUDA(cudaMemsetAsync(d->h_all, 0, sizeof(float) * (size_t)(T + 1) * BD, s));
         ICD_CUDA(cudaMemsetAsync(d->c_all, 0, sizeof(float) * (size_t)(T + 1) * BD, s));
         ICD_CUDA(cudaMemsetAsync(d->gated, 0, sizeof(float) * (size_t)T * B * C, s));
@@ -110,52 +133,49 @@ int icd_attention_decoder_fwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
         ICD_CUDA(cudaMemsetAsync(u.h, 0, (size_t)(TB + B) * D * 2, s));
         ICD_CUDA(cudaMemsetAsync(u.gated, 0, (size_t)TB * C * 2, s));
     }
-    ICD_CUDA(cudaMemcpyAsync(d->w_cat, d->dec_att_w, sizeof(float) * (size_t)A * D, cudaMemcpyDeviceToDevice, s));
-    ICD_CUDA(cudaMemcpyAsync(d->w_cat + (size_t)A * D, d->f_beta_w, sizeof(float) * (size_t)C * D, cudaMemcpyDeviceToDevice, s));
-    ICD_CUDA(cudaMemcpyAsync(d->w_cat + (size_t)(A + C) * D, d->w_hh, sizeof(float) * (size_t)4 * D * D, cudaMemcpyDeviceToDevice, s));
+    // fp32 [b_dec; b_fbeta; 0] (b_hh rides with the hoisted embedding term); the fp32 w_cat copy is kept for callers
+    // that inspect it but the tier itself only needs the bf16 stack
     ICD_CUDA(cudaMemcpyAsync(d->b_cat, d->dec_att_b, sizeof(float) * A, cudaMemcpyDeviceToDevice, s));
     ICD_CUDA(cudaMemcpyAsync(d->b_cat + A, d->f_beta_b, sizeof(float) * C, cudaMemcpyDeviceToDevice, s));
     ICD_CUDA(cudaMemsetAsync(d->b_cat + A + C, 0, sizeof(float) * 4 * D, s));
 
-    // ---- bf16 K-major copies of the weights (they change every optimiser step) and of the features ----
-    CVT(d->enc_att_w, C, 1, A, C, u.We, C);
-    CVT(d->w_cat, D, 1, NZ, D, u.Wcat, D);
-    CVT(d->w_ih, E + C, 1, 4 * D, E, u.WihE, u.ldE);
-    CVT(d->w_ih + E, E + C, 1, 4 * D, C, u.WihC, C);
-    CVT(d->h_lin_w, C, 1, D, C, u.Wh, C);
-    CVT(d->c_lin_w, C, 1, D, C, u.Wc, C);
-    CVT(d->fc_w, D, 1, V, D, u.Wfc, D);
-    CVT(d->enc, C, 1, B * P, C, u.enc, C);
+    // ---- bf16 copies of the weights (they change every optimiser step) ----
+    CVT(d->enc_att_w, C, A, C, u.We, C);
+    CVT(d->dec_att_w, D, A, D, u.Wcat, D);                                   // [W_dec; W_fbeta; W_hh]
+    CVT(d->f_beta_w, D, C, D, at16(u.Wcat, (int64_t)A * D), D);
+    CVT(d->w_hh, D, 4 * D, D, at16(u.Wcat, (int64_t)(A + C) * D), D);
+    CVT(d->w_ih, E + C, 4 * D, E, u.WihE, u.ldE);
+    CVT(d->w_ih + E, E + C, 4 * D, C, u.WihC, C);
+    CVT(d->h_lin_w, C, D, C, u.Wh, C);
+    CVT(d->c_lin_w, C, D, C, u.Wc, C);
+    CVT(d->fc_w, D, V, D, u.Wfc, D);
+    // ---- features: fp32 -> bf16 and the pixel mean (:161) in one pass over encoder_out ----
+    ICD_TRY(icd_convert_features_bf16(B, P, C, d->enc, u.enc, d->mean_enc, u.mean, s));
 
-    // K1: att_enc = enc_att(encoder_out), once per batch (models/attention.py:54)
-    ICD_TRY(icd_gemm_bf16(u.enc, C, u.We, C, nullptr, 0, B * P, A, C, d->enc_att_b, nullptr, nullptr, 0, nullptr, 0,
-                          nullptr, 0.f, s, u.att_enc, A));
-    // K7: init_hidden_state (:161-163)
-    ICD_TRY(icd_weighted_pixel_sum(B, P, C, nullptr, d->enc, nullptr, 0, nullptr, 0, d->mean_enc, nullptr, nullptr, s));
-    CVT(d->mean_enc, C, 1, B, C, u.mean, C);
-    MM(u.mean, C, u.Wh, C, d->h_all, D, B, D, C, d->h_lin_b, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);
-    MM(u.mean, C, u.Wc, C, d->c_all, D, B, D, C, d->c_lin_b, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);
-    CVT(d->h_all, D, 1, B, D, u.h, D);                              // h_0 (bf16); h_t, t >= 1, is emitted by the gate kernel
+    // K1: att_enc = enc_att(encoder_out), once per batch (models/attention.py:54); stored bf16 only
+    MMX(u.enc, C, 0, u.We, C, 0, nullptr, 0, B * P, A, C, d->enc_att_b, nullptr, nullptr, 0, nullptr, 0, nullptr, u.att_enc, A);
+    // K7: init_hidden_state (:162-163); h_0 also emitted as bf16 (operand of the first step)
+    MMX(u.mean, C, 0, u.Wh, C, 0, d->h_all, D, B, D, C, d->h_lin_b, nullptr, nullptr, 0, nullptr, 0, nullptr, u.h, D);
+    MMX(u.mean, C, 0, u.Wc, C, 0, d->c_all, D, B, D, C, d->c_lin_b, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, 0);
     // K5: embedding lookup (:247) + hoisted input contraction
     ICD_TRY(icd_embed_gather(d->emb_w, d->emb_is_f64, d->captions, B, d->L, T, E, d->emb_x, s));
-    CVT(d->emb_x, E, 1, TB, E, u.embx, u.ldE);
-    MM(u.embx, u.ldE, u.WihE, u.ldE, d->xg, 4 * D, TB, 4 * D, E, d->b_ih, d->b_hh, nullptr, 0, nullptr, 0, nullptr, 0.f);
+    CVT(d->emb_x, E, TB, E, u.embx, u.ldE);
+    MMX(u.embx, u.ldE, 0, u.WihE, u.ldE, 0, d->xg, 4 * D, TB, 4 * D, E, d->b_ih, d->b_hh, nullptr, 0, nullptr, 0, nullptr, nullptr, 0);
 
     for (int t = 0; t < T; ++t) {
         const int bt = d->bt_host[t];
         if (bt == 0) break;
-        const float* h_prev = d->h_all + (size_t)t * BD;
         const float* c_prev = d->c_all + (size_t)t * BD;
         float* zt = d->z + (size_t)t * B * NZ;
         char* h16 = at16(u.h, (int64_t)t * B * D);
         char* g16 = at16(u.gated, (int64_t)t * B * C);
-        MM(h16, D, u.Wcat, D, zt, NZ, bt, NZ, D, d->b_cat, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);       // K2
+        MMX(h16, D, 0, u.Wcat, D, 0, zt, NZ, bt, NZ, D, d->b_cat, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, 0);   // K2
         ICD_TRY(icd_attention_step_fwd_bf16(bt, P, C, A, nullptr, u.enc, u.att_enc, zt, NZ, d->full_att_w, d->full_att_b,
                                             zt + A, NZ, d->alphas + (size_t)t * P, (int64_t)T * P,
                                             d->awe_raw + (size_t)t * B * C, d->gate + (size_t)t * B * C,
                                             d->gated + (size_t)t * B * C, g16, (void*)s));                         // K3
-        MM(g16, C, u.WihC, C, d->gates_pre, 4 * D, bt, 4 * D, C, nullptr, nullptr,
-           d->xg + (size_t)t * B * 4 * D, 4 * D, zt + A + C, NZ, nullptr, 0.f);                                   // K4
+        MMX(g16, C, 0, u.WihC, C, 0, d->gates_pre, 4 * D, bt, 4 * D, C, nullptr, nullptr,
+            d->xg + (size_t)t * B * 4 * D, 4 * D, zt + A + C, NZ, nullptr, nullptr, 0);                            // K4
         ICD_TRY(icd_lstm_pointwise_fwd(bt, D, d->gates_pre, c_prev, d->gates_act + (size_t)t * B * 4 * D,
                                        d->c_all + (size_t)(t + 1) * BD, d->h_all + (size_t)(t + 1) * BD,
                                        d->hdrop + (size_t)t * D, (int64_t)T * D,
@@ -163,7 +183,7 @@ int icd_attention_decoder_fwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
                                        at16(u.h, (int64_t)(t + 1) * B * D), at16(u.hdrop, (int64_t)t * D)));
     }
     // K6: predictions = fc(dropout(h)) for every (b,t) at once (:279-280); inactive rows exactly 0 (:253)
-    MM(u.hdrop, D, u.Wfc, D, d->predictions, V, B * T, V, D, d->fc_b, nullptr, nullptr, 0, nullptr, 0, d->row_valid, 0.f);
+    MMX(u.hdrop, D, 0, u.Wfc, D, 0, d->predictions, V, B * T, V, D, d->fc_b, nullptr, nullptr, 0, nullptr, 0, d->row_valid, nullptr, 0);
     return 0;
 }
 
@@ -173,24 +193,22 @@ int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
     const int B = d->B, T = d->T, P = d->P, C = d->C, A = d->A, D = d->D, E = d->E, V = d->V;
     const int NZ = A + C + 4 * D, TB = T * B, BT = B * T, BP = B * P;
     const long long BD = (long long)B * D;
+    const float* NF = nullptr;
 
-    ICD_CUDA(cudaMemsetAsync(d->dz, 0, sizeof(float) * (size_t)TB * NZ, s));
-    ICD_CUDA(cudaMemsetAsync(d->d_e, 0, sizeof(float) * (size_t)B * T * P, s));
+    if (d->bt_host[T - 1] < B) {          // ragged batch: inactive rows of the stacked gradients contribute zeros
+        ICD_CUDA(cudaMemsetAsync(d->dz, 0, sizeof(float) * (size_t)TB * NZ, s));
+        ICD_CUDA(cudaMemsetAsync(u.dz, 0, (size_t)TB * NZ * 2, s));
+        ICD_CUDA(cudaMemsetAsync(d->d_e, 0, sizeof(float) * (size_t)B * T * P, s));
+    }
     ICD_CUDA(cudaMemsetAsync(d->dh, 0, sizeof(float) * (size_t)BD, s));
     ICD_CUDA(cudaMemsetAsync(d->dc, 0, sizeof(float) * (size_t)BD, s));
-    ICD_CUDA(cudaMemsetAsync(u.dz, 0, (size_t)TB * NZ * 2, s));
-
-    // transposed bf16 weights for the dX contractions (B operand must be K-major: B[n, k] = W[k, n])
-    CVT(d->w_cat, 1, D, D, NZ, u.WcatT, NZ);                       // [D x NZ]
-    CVT(d->w_ih + E, 1, E + C, C, 4 * D, u.WihCT, 4 * D);          // [C x 4D]
-    CVT(d->fc_w, 1, D, D, V, u.WfcT, u.ldV);                       // [D x V]
 
     // ---- fc (:279): d_hdrop = dY W_fc ; dW_fc = dY^T hdrop ; db_fc = masked column sum of dY ----
-    CVT(d->d_predictions, V, 1, BT, V, u.dY, u.ldV);
-    CVT(d->d_predictions, 1, V, V, BT, u.dYT, u.ldBT);
-    CVT(d->hdrop, 1, D, D, BT, u.hdropT, u.ldBT);
-    MM(u.dY, u.ldV, u.WfcT, u.ldV, d->d_hdrop, D, BT, D, V, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);
-    MM(u.dYT, u.ldBT, u.hdropT, u.ldBT, d->d_fc_w, D, V, D, BT, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);
+    const void* dY16 = d->d_predictions16;
+    int64_t ldY = d->ld_dpred16;
+    if (!dY16) { CVT(d->d_predictions, V, BT, V, u.dY, u.ldV); dY16 = u.dY; ldY = u.ldV; }
+    MMX(dY16, ldY, 0, u.Wfc, D, 1, d->d_hdrop, D, BT, D, V, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
+    MMX(dY16, ldY, 1, u.hdrop, D, 1, d->d_fc_w, D, V, D, BT, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
     ICD_TRY(icd_colsum(d->d_predictions, V, (int64_t)BT, V, d->row_valid, d->d_fc_b, s));
 
     // ---- BPTT ----
@@ -205,49 +223,42 @@ int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
                                        d->dc, d->gates_act + (size_t)t * B * 4 * D,
                                        d->c_all + (size_t)t * BD, d->c_all + (size_t)(t + 1) * BD,
                                        dzt + A + C, NZ, s, at16(dz16, A + C), NZ));     // dG also emitted as bf16
-        MM(at16(dz16, A + C), NZ, u.WihCT, 4 * D, d->d_gated, C, bt, C, 4 * D,
-           nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);                // d_gated = dG W_ih[:, E:]
+        // d_gated = dG W_ih[:, E:]           (W_ih[:, E:] stored [4D, C] = MN-major B, N = C, K = 4D)
+        MMX(at16(dz16, A + C), NZ, 0, u.WihC, C, 1, d->d_gated, C, bt, C, 4 * D, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
         ICD_TRY(icd_attention_step_bwd_bf16(bt, P, C, A, u.enc, u.att_enc, zt, NZ, d->full_att_w,
                                             d->alphas + (size_t)t * P, (int64_t)T * P,
                                             d->d_alphas ? d->d_alphas + (size_t)t * P : nullptr, (int64_t)T * P,
                                             d->gate + (size_t)t * B * C, d->awe_raw + (size_t)t * B * C, d->d_gated,
                                             dzt, NZ, dzt + A, NZ, d->d_e + (size_t)t * P, (int64_t)T * P,
                                             dz16, NZ, (void*)s));                   // d att_dec | d fbeta_pre (+ bf16)
-        MM(dz16, NZ, u.WcatT, NZ, d->dh, D, bt, D, NZ, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);
+        // dh_t = dz [W_dec; W_fbeta; W_hh]    (stack stored [NZ, D] = MN-major B, N = D, K = NZ)
+        MMX(dz16, NZ, 0, u.Wcat, D, 1, d->dh, D, bt, D, NZ, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
     }
 
     // ---- init_hidden_state (:161-163): dh, dc now hold d h0, d c0 ----
-    CVT(d->dh, 1, D, D, B, u.dhT, u.ldB);
-    CVT(d->dc, 1, D, D, B, u.dcT, u.ldB);
-    CVT(d->mean_enc, 1, C, C, B, u.meanT, u.ldB);
-    MM(u.dhT, u.ldB, u.meanT, u.ldB, d->d_h_lin_w, C, D, C, B, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);
+    CVT(d->dh, D, B, D, u.dh, D);
+    CVT(d->dc, D, B, D, u.dc, D);
+    MMX(u.dh, D, 1, u.mean, C, 1, d->d_h_lin_w, C, D, C, B, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
     ICD_TRY(icd_colsum(d->dh, D, B, D, nullptr, d->d_h_lin_b, s));
-    MM(u.dcT, u.ldB, u.meanT, u.ldB, d->d_c_lin_w, C, D, C, B, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);
+    MMX(u.dc, D, 1, u.mean, C, 1, d->d_c_lin_w, C, D, C, B, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
     ICD_TRY(icd_colsum(d->dc, D, B, D, nullptr, d->d_c_lin_b, s));
 
-    // ---- hoisted weight gradients over the T*B stacked rows ----
-    CVT(d->dz, 1, NZ, NZ, TB, u.dzT, u.ldTB);                      // [NZ x TB]
-    CVT(d->h_all, 1, D, D, TB, u.hT, u.ldTB);                      // [D x TB]   (h_0 .. h_{T-1})
-    CVT(d->emb_x, 1, E, E, TB, u.embxT, u.ldTB);                   // [E x TB]
-    CVT(d->gated, 1, C, C, TB, u.gatedT, u.ldTB);                  // [C x TB]
-    MM(u.dzT, u.ldTB, u.hT, u.ldTB, d->d_w_cat, D, NZ, D, TB, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);
+    // ---- hoisted weight gradients over the T*B stacked rows: dW = dY^T X, both operands MN-major as stored ----
+    MMX(u.dz, NZ, 1, u.h, D, 1, d->d_w_cat, D, NZ, D, TB, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
     ICD_TRY(icd_colsum(d->dz, NZ, TB, NZ, nullptr, d->d_b_cat, s));
-    char* dGT = at16(u.dzT, (int64_t)(A + C) * u.ldTB);           // rows [A+C, NZ) of dz^T = dG^T  [4D x TB]
-    MM(dGT, u.ldTB, u.embxT, u.ldTB, d->d_w_ih, E + C, 4 * D, E, TB, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);
-    MM(dGT, u.ldTB, u.gatedT, u.ldTB, d->d_w_ih + E, E + C, 4 * D, C, TB, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);
+    char* dG16 = at16(u.dz, A + C);                                // columns [A+C, NZ) of dz = dG  [TB x 4D], ld NZ
+    MMX(dG16, NZ, 1, u.embx, u.ldE, 1, d->d_w_ih, E + C, 4 * D, E, TB, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
+    MMX(dG16, NZ, 1, u.gated, C, 1, d->d_w_ih + E, E + C, 4 * D, C, TB, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
     if (d->d_emb_w) {
-        CVT(d->w_ih, 1, E + C, E, 4 * D, u.WihET, 4 * D);          // [E x 4D]
-        MM(at16(u.dz, A + C), NZ, u.WihET, 4 * D, d->d_emb_x, E, TB, E, 4 * D,
-           nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);
+        MMX(dG16, NZ, 0, u.WihE, u.ldE, 1, d->d_emb_x, E, TB, E, 4 * D, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
         ICD_CUDA(cudaMemsetAsync(d->d_emb_w, 0, (d->emb_is_f64 ? sizeof(double) : sizeof(float)) * (size_t)V * E, s));
         ICD_TRY(icd_embed_scatter_add(d->d_emb_w, d->emb_is_f64, d->captions, B, d->L, T, E, d->bt_host, d->d_emb_x, s));
     }
-    // attention projections: d_att_enc for all steps at once, full_att grads, then enc_att grads (:54)
+    // attention projections: d_att_enc for all steps at once (bf16 only: it is just the A operand of the next
+    // contraction), full_att grads and the enc_att bias grad from the same pass, then the enc_att weight grad (:54)
     ICD_TRY(icd_attention_proj_bwd_bf16(B, T, P, A, d->bt_host, u.att_enc, d->z, NZ, d->full_att_w, d->d_e,
-                                        d->d_att_enc, d->d_full_att_w, d->d_full_att_b, d->proj_partial, (void*)s));
-    ICD_TRY(icd_colsum(d->d_att_enc, A, (int64_t)BP, A, nullptr, d->d_enc_att_b, s));
-    CVT(d->d_att_enc, 1, A, A, BP, u.daeT, u.ldBP);                // [A x BP]
-    CVT(d->enc, 1, C, C, BP, u.encT, u.ldBP);                      // [C x BP]
-    MM(u.daeT, u.ldBP, u.encT, u.ldBP, d->d_enc_att_w, C, A, C, BP, nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f);
+                                        nullptr, u.dae, d->d_full_att_w, d->d_full_att_b, d->d_enc_att_b,
+                                        d->proj_partial, (void*)s));
+    MMX(u.dae, A, 1, u.enc, C, 1, d->d_enc_att_w, C, A, C, BP, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
     return 0;
 }

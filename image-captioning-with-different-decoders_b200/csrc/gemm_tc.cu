@@ -1,18 +1,22 @@
 // bf16 tensor-core tier of the dense contraction:  C[M,N] = A[M,K] * B[N,K]^T + epilogue   (fp32 accumulate/out)
 //
 // Blackwell-native (sm_100a) kernel, hand-written PTX:
-//   * operands: bf16, K-major, staged by TMA (cp.async.bulk.tensor.2d, 128B swizzle) into a 4-stage shared-memory ring;
-//   * math: tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x BN x 16 (BN = 256 or 128), issued by ONE elected thread,
-//     accumulators in TMEM (2 stages x BN fp32 columns, so the epilogue of tile i overlaps the MMAs of tile i+1);
+//   * operands: bf16, staged by TMA (cp.async.bulk.tensor.2d, 128B swizzle) into a shared-memory ring.  Each operand is
+//     either K-major (rows of K contiguous elements: activations x, weights W of y = x W^T) or MN-major (rows of M / N
+//     contiguous elements, one row per k: the operands of every weight-gradient contraction dW = dY^T X and of every
+//     dX = dY W contraction).  The UMMA shared-memory / instruction descriptors carry the major-ness, so NO operand is
+//     ever transposed in memory;
+//   * math: tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x BN x 16 (BN = 256 / 128 / 64), issued by ONE elected
+//     thread, accumulators in TMEM (2 stages x BN fp32 columns: the epilogue of tile i overlaps the MMAs of tile i+1);
 //   * sync: mbarrier full/empty ring (TMA <-> MMA), tcgen05.commit -> mbarrier (MMA -> TMA slot release and
 //     MMA -> epilogue), tmem_empty barrier (epilogue -> MMA);
-//   * warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5 epilogue
-//     (tcgen05.ld 32x32b.x32 -> registers -> padded smem transpose -> coalesced fp32 stores with the fused epilogue:
-//     bias1 + bias2 + add1 + add2, row mask, beta);
-//   * persistent: grid = min(#tiles, #SMs), static round-robin tile schedule.
-// fp32 sources are converted to K-major bf16 (optionally transposing) by convert_bf16_kernel into caller-provided
-// workspace, so the kernel only ever sees K-major operands (the weight-gradient contractions dW = dY^T X are fed
-// transposed copies, which the conversion pass produces at no extra traffic).
+//   * warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-9 epilogue
+//     (tcgen05.ld 32x32b.x32 -> registers -> padded smem transpose -> coalesced 128-bit loads/stores with the fused
+//     epilogue: bias1 + bias2 + add1 + add2, row mask, beta, optional bf16 copy of the result);
+//   * persistent: grid = min(#work units, #SMs), static round-robin schedule;
+//   * small problems (the per-time-step contractions with M = batch): narrower BN and deterministic split-K
+//     (work unit = tile x K-slice, raw partial tiles to workspace, a second kernel sums the slices in fixed order
+//     and applies the epilogue) so that one wave still covers the 148 SMs.
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include <cuda.h>
@@ -21,10 +25,12 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
 constexpr int EPI_LD = 33;                           // padded row of the per-warp 32x32 transpose buffer
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS; // 320
+constexpr int MN_BLOCK_BYTES = BK * 128;             // one 64-element MN block of an MN-major tile: BK rows x 128 B
 
 struct EpiArgs {
     float* C; long long ldc;
@@ -35,6 +41,14 @@ struct EpiArgs {
     const unsigned char* row_mask;
     float beta;
     __nv_bfloat16* C16; long long ldc16;      // optional bf16 copy of the result (C may then be NULL)
+    int vec4;                                 // every row start of C / add1 / add2 / C16 is 16-byte (8 for C16) aligned
+};
+
+struct KArgs {
+    EpiArgs e;
+    int a_mn, b_mn;                           // 1: operand is MN-major in memory
+    int splits, kb_per_split;                 // split-K: work unit = (tile, slice)
+    float* partial;                           // [splits][M][N] raw accumulators when splits > 1
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -58,7 +72,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                      "selp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) break;
-        if (++spins > (1ull << 22)) __trap();        // a protocol bug must fault, never hang the GPU
+        if (++spins > (1ull << 24)) __trap();        // a protocol bug must fault, never hang the GPU
     }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
@@ -87,30 +101,110 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[3
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (ignored for swizzled K-major; 1)
-//   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = SWIZZLE_128B (2)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
-    return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+// 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
+//   [46,48) version = 1 | [61,64) layout = SWIZZLE_128B (2)
+// K-major tile  (rows of 64 bf16 = 128 B, 8-row swizzle atoms of 1024 B): LBO unused (1), SBO = 1024 B between
+//                8-row groups; the next UMMA_K = 16 slice starts 32 B further inside the 128 B span.
+// MN-major tile (BK rows of 64 MN-elements = 128 B each, one row per k; 64-wide MN blocks MN_BLOCK_BYTES apart):
+//                canonical ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units: LBO = MN-block stride, SBO = 1024 B
+//                between groups of 8 k-rows; the next UMMA_K = 16 slice starts 2 k-groups = 2048 B further.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, int mn_major) {
+    const uint64_t lbo = mn_major ? (uint64_t)(MN_BLOCK_BYTES >> 4) : 1ull;
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | (lbo << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
 template <int BN>
 struct Cfg {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;
+    static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr int EPI_BYTES = NUM_EPI_WARPS * 32 * EPI_LD * 4;
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
-    static constexpr int TMEM_COLS = 2 * BN;         // two accumulator stages (power of two: 256 or 512)
-    // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), K-major both,
+    static constexpr int TMEM_COLS = 2 * BN;         // two accumulator stages (power of two: 128, 256 or 512)
+    // cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b format BF16 (1<<7, 1<<10), a_major bit 15, b_major bit 16,
     // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
 
+// One 32x32 sub-tile of the accumulator, already transposed into sE (row stride EPI_LD): apply the fused epilogue and
+// write it out with coalesced accesses.  vec4: lane -> 4 consecutive columns, 8 lanes per row, 4 rows per instruction.
+__device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ sE, int lane, int mrow0, int nb,
+                                                     const EpiArgs& e) {
+    if (e.vec4 && nb + 32 <= e.N) {
+        const int cc = (lane & 7) * 4, n = nb + cc;
+        float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e.bias1) { const float4 b = *reinterpret_cast<const float4*>(e.bias1 + n); bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w; }
+        if (e.bias2) { const float4 b = *reinterpret_cast<const float4*>(e.bias2 + n); bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w; }
+        float4 a1[8], a2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = mrow0 + i * 4 + (lane >> 3);
+            a1[i] = make_float4(0.f, 0.f, 0.f, 0.f); a2[i] = a1[i];
+            if (m < e.M) {
+                if (e.add1) a1[i] = *reinterpret_cast<const float4*>(e.add1 + (long long)m * e.ld1 + n);
+                if (e.add2) a2[i] = *reinterpret_cast<const float4*>(e.add2 + (long long)m * e.ld2 + n);
+                if (e.beta != 0.f && e.C) {
+                    const float4 o = *reinterpret_cast<const float4*>(e.C + (long long)m * e.ldc + n);
+                    a1[i].x += e.beta * o.x; a1[i].y += e.beta * o.y; a1[i].z += e.beta * o.z; a1[i].w += e.beta * o.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3), m = mrow0 + rr;
+            if (m >= e.M) continue;
+            const float* s = sE + rr * EPI_LD + cc;
+            float4 x = make_float4(s[0] + bsum.x + a1[i].x + a2[i].x, s[1] + bsum.y + a1[i].y + a2[i].y,
+                                   s[2] + bsum.z + a1[i].z + a2[i].z, s[3] + bsum.w + a1[i].w + a2[i].w);
+            if (e.row_mask && !e.row_mask[m]) x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e.C) *reinterpret_cast<float4*>(e.C + (long long)m * e.ldc + n) = x;
+            if (e.C16) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(e.C16 + (long long)m * e.ldc16 + n) = pk;
+            }
+        }
+    } else {
+        // generic path: lane -> one column, one row per instruction (still 128 B coalesced); handles the N tail and
+        // row strides that are not multiples of 4 (the (B,T,V) logits with V = 9490)
+        const int n = nb + lane;
+        const bool nok = n < e.N;
+        float bsum = 0.f;
+        if (nok) { if (e.bias1) bsum += e.bias1[n]; if (e.bias2) bsum += e.bias2[n]; }
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += 8) {
+            float a[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int m = mrow0 + r0 + u;
+                a[u] = 0.f;
+                if (nok && m < e.M) {
+                    if (e.add1) a[u] += e.add1[(long long)m * e.ld1 + n];
+                    if (e.add2) a[u] += e.add2[(long long)m * e.ld2 + n];
+                    if (e.beta != 0.f && e.C) a[u] += e.beta * e.C[(long long)m * e.ldc + n];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int m = mrow0 + r0 + u;
+                if (!nok || m >= e.M) continue;
+                float x = sE[(r0 + u) * EPI_LD + lane] + bsum + a[u];
+                if (e.row_mask && !e.row_mask[m]) x = 0.f;
+                if (e.C) e.C[(long long)m * e.ldc + n] = x;
+                if (e.C16) e.C16[(long long)m * e.ldc16 + n] = __float2bfloat16_rn(x);
+            }
+        }
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiArgs e) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KArgs p) {
     using C_ = Cfg<BN>;
+    constexpr int STAGES = C_::STAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024 B alignment
     uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -120,16 +214,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + STAGES * C_::STAGE_BYTES + C_::EPI_BYTES + 16 * STAGES + 32);
 
+    const EpiArgs& e = p.e;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (e.M + BM - 1) / BM, tiles_n = (e.N + BN - 1) / BN;
     const int num_tiles = tiles_m * tiles_n;
     const int nkb = (e.K + BK - 1) / BK;
+    const int num_units = num_tiles * p.splits;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB) : "memory");
         for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -146,13 +242,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // =================================== TMA producer ===================================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+                const int tile = unit % num_tiles, slice = unit / num_tiles;
                 const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
-                for (int kb = 0; kb < nkb; ++kb) {
+                const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                    mbar_arrive_expect_tx(full0 + 8 * stage, C_::STAGE_BYTES);
-                    tma_load_2d(sA + stage * A_BYTES, &tmA, kb * BK, m0, full0 + 8 * stage);
-                    tma_load_2d(sB + stage * C_::B_BYTES, &tmB, kb * BK, n0, full0 + 8 * stage);
+                    const uint32_t fb = full0 + 8 * stage;
+                    mbar_arrive_expect_tx(fb, C_::STAGE_BYTES);
+                    const uint32_t a_dst = sA + stage * A_BYTES, b_dst = sB + stage * C_::B_BYTES;
+                    if (!p.a_mn) tma_load_2d(a_dst, &tmA, kb * BK, m0, fb);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * MN_BLOCK_BYTES, &tmA, m0 + 64 * j, kb * BK, fb);
+                    }
+                    if (!p.b_mn) tma_load_2d(b_dst, &tmB, kb * BK, n0, fb);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < (BN + 63) / 64; ++j) tma_load_2d(b_dst + j * MN_BLOCK_BYTES, &tmB, n0 + 64 * j, kb * BK, fb);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -161,22 +269,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // =================================== MMA issuer ===================================
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const uint32_t idesc = C_::IDESC | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16);
+        const uint64_t a_kstep = p.a_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);   // descriptor units of 16 B
+        const uint64_t b_kstep = p.b_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+            const int slice = unit / num_tiles;
+            const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);              // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(full0 + 8 * stage, phase);                  // TMA bytes have landed
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint64_t adesc = make_smem_desc(sA + stage * A_BYTES);
-                    const uint64_t bdesc = make_smem_desc(sB + stage * C_::B_BYTES);
+                    const uint64_t adesc = make_smem_desc(sA + stage * A_BYTES, p.a_mn);
+                    const uint64_t bdesc = make_smem_desc(sB + stage * C_::B_BYTES, p.b_mn);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)              // +32 B per K slice inside the 128 B swizzle span
-                        tc_mma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), C_::IDESC,
-                                   (kb > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        tc_mma_f16(d_tmem, adesc + (uint64_t)k * a_kstep, bdesc + (uint64_t)k * b_kstep, idesc,
+                                   (kb > kb0 || k > 0) ? 1u : 0u);
                     tc_commit(empty0 + 8 * stage);                    // smem slot reusable once these MMAs retire
-                    if (kb == nkb - 1) tc_commit(tfull0 + 8 * acc);   // accumulator complete -> epilogue
+                    if (kb == kb1 - 1) tc_commit(tfull0 + 8 * acc);   // accumulator complete -> epilogue
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -184,50 +297,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
-        // =================================== epilogue warps 2..5 ===================================
+        // =================================== epilogue warps 2..9 ===================================
         const int q = warp & 3;                                       // TMEM lane quarter this warp may access
+        const int cg = (warp - 2) >> 2;                               // column group: chunks cg, cg+2, ...
         float* sE = sEpi + (warp - 2) * 32 * EPI_LD;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        constexpr int NCHUNK = BN / 32;
+        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+            const int tile = unit % num_tiles, slice = unit / num_tiles;
             const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+            EpiArgs ee = e;
+            if (p.splits > 1) {                                       // raw partial tile, epilogue deferred
+                ee.C = p.partial + (long long)slice * e.M * e.N; ee.ldc = e.N;
+                ee.bias1 = ee.bias2 = ee.add1 = ee.add2 = nullptr; ee.row_mask = nullptr; ee.beta = 0.f; ee.C16 = nullptr;
+                ee.vec4 = (e.N % 4 == 0);
+            }
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             const int mrow0 = m0 + q * 32;
+            bool released = false;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = cg; c < NCHUNK; c += 2) {
                 const int nb = n0 + c * 32;
-                if (nb >= e.N) break;                                 // warp-uniform
-                uint32_t v[32];
-                tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
-                tc_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sE[lane * EPI_LD + j] = __uint_as_float(v[j]);
-                __syncwarp();
-                const int n = nb + lane;
-                const bool nok = n < e.N;
-                float bsum = 0.f;
-                if (nok) { if (e.bias1) bsum += e.bias1[n]; if (e.bias2) bsum += e.bias2[n]; }
-#pragma unroll 4
-                for (int r = 0; r < 32; ++r) {
-                    const int m = mrow0 + r;
-                    if (m >= e.M) break;                              // warp-uniform
-                    if (nok) {
-                        float x = sE[r * EPI_LD + lane] + bsum;
-                        if (e.add1) x += e.add1[(long long)m * e.ld1 + n];
-                        if (e.add2) x += e.add2[(long long)m * e.ld2 + n];
-                        if (e.row_mask && !e.row_mask[m]) x = 0.f;
-                        if (e.C) {
-                            float* cp = e.C + (long long)m * e.ldc + n;
-                            if (e.beta != 0.f) x += e.beta * (*cp);
-                            *cp = x;
-                        }
-                        if (e.C16) e.C16[(long long)m * e.ldc16 + n] = __float2bfloat16_rn(x);
+                const bool last = (c + 2 >= NCHUNK);
+                if (nb < e.N && mrow0 < e.M) {                        // warp-uniform
+                    uint32_t v[32];
+                    tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+                    tc_wait_ld();
+                    if (last) {                                       // all of this warp's TMEM reads are done
+                        tc_fence_before();
+                        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+                        released = true;
                     }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sE[lane * EPI_LD + j] = __uint_as_float(v[j]);
+                    __syncwarp();
+                    epilogue_store_chunk(sE, lane, mrow0, nb, ee);
+                    __syncwarp();
                 }
-                __syncwarp();
             }
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            if (!released) {
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -241,10 +353,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// split-K second pass: C = epilogue(sum_s partial[s]) with the slices summed in fixed order (deterministic).
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, const EpiArgs e) {
+    const long long MN = (long long)e.M * e.N;
+    if (e.vec4 && e.N % 4 == 0) {
+        const long long total = MN / 4;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const long long o = i * 4;
+            const int m = (int)(o / e.N), n = (int)(o % e.N);
+            float4 x = *reinterpret_cast<const float4*>(partial + o);
+            for (int s = 1; s < splits; ++s) {
+                const float4 y = *reinterpret_cast<const float4*>(partial + (long long)s * MN + o);
+                x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+            }
+            if (e.bias1) { const float4 b = *reinterpret_cast<const float4*>(e.bias1 + n); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
+            if (e.bias2) { const float4 b = *reinterpret_cast<const float4*>(e.bias2 + n); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
+            if (e.add1) { const float4 b = *reinterpret_cast<const float4*>(e.add1 + (long long)m * e.ld1 + n); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
+            if (e.add2) { const float4 b = *reinterpret_cast<const float4*>(e.add2 + (long long)m * e.ld2 + n); x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w; }
+            if (e.row_mask && !e.row_mask[m]) x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e.C) {
+                float* c = e.C + (long long)m * e.ldc + n;
+                if (e.beta != 0.f) { const float4 o4 = *reinterpret_cast<const float4*>(c); x.x += e.beta * o4.x; x.y += e.beta * o4.y; x.z += e.beta * o4.z; x.w += e.beta * o4.w; }
+                *reinterpret_cast<float4*>(c) = x;
+            }
+            if (e.C16) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(e.C16 + (long long)m * e.ldc16 + n) = pk;
+            }
+        }
+    } else {
+        for (long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x; o < MN; o += (long long)gridDim.x * blockDim.x) {
+            const int m = (int)(o / e.N), n = (int)(o % e.N);
+            float x = partial[o];
+            for (int s = 1; s < splits; ++s) x += partial[(long long)s * MN + o];
+            if (e.bias1) x += e.bias1[n];
+            if (e.bias2) x += e.bias2[n];
+            if (e.add1) x += e.add1[(long long)m * e.ld1 + n];
+            if (e.add2) x += e.add2[(long long)m * e.ld2 + n];
+            if (e.row_mask && !e.row_mask[m]) x = 0.f;
+            if (e.C) { float* c = e.C + (long long)m * e.ldc + n; if (e.beta != 0.f) x += e.beta * (*c); *c = x; }
+            if (e.C16) e.C16[(long long)m * e.ldc16 + n] = __float2bfloat16_rn(x);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- fp32 -> bf16 staging
-// dst[r*ldd + c] = bf16(src[r*s_r + c*s_c]), r < rows, c < cols.  One of s_r / s_c is 1.
+// dst[r*ldd + c] = bf16(src[r*s_r + c]), r < rows, c < cols (source rows contiguous).
 __global__ void convert_rows_kernel(const float* __restrict__ src, long long s_r, int rows, int cols,
-                                    __nv_bfloat16* __restrict__ dst, long long ldd) {
+                                    __nv_bfloat16* __restrict__ dst, long long ldd, int vec) {
+    if (vec) {                                          // cols % 4 == 0, rows 16 B aligned: 128-bit loads, 64-bit stores
+        const long long n4 = cols >> 2, total = (long long)rows * n4;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+             i += (long long)gridDim.x * blockDim.x) {
+            const long long r = i / n4; const int c = (int)(i % n4) * 4;
+            const float4 x = ld_stream_f4(src + r * s_r + c);
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(dst + r * ldd + c) = pk;
+        }
+        return;
+    }
     const long long n2 = ((long long)cols + 1) / 2;
     const long long total = (long long)rows * n2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -293,15 +464,17 @@ int get_encode(EncodeTiledFn* out) {
     return 0;
 }
 
-int make_tmap(CUtensorMap* tm, const __nv_bfloat16* p, long long ld, int rows, int K, int box_rows) {
+// K-major operand:  memory [rows][K] (ld elements between rows)  -> dims {K, rows}, box {BK, box_rows}
+// MN-major operand: memory [K][rows] (ld elements between k rows) -> dims {rows, K}, box {64, BK}
+int make_tmap(CUtensorMap* tm, const __nv_bfloat16* p, long long ld, int rows, int K, int box_rows, int mn_major) {
     EncodeTiledFn enc;
     ICD_TRY(get_encode(&enc));
     ICD_CHECK_ARG((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld % 8) == 0,
                   "gemm_tc: bf16 operand must be 16-byte aligned with a leading dimension multiple of 8 (ld=%lld)", ld);
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
+    cuuint64_t dims[2], strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2], estr[2] = {1, 1};
+    if (!mn_major) { dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows; box[0] = BK; box[1] = (cuuint32_t)box_rows; }
+    else           { dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K; box[0] = 64; box[1] = BK; }
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(p), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -310,17 +483,46 @@ int make_tmap(CUtensorMap* tm, const __nv_bfloat16* p, long long ld, int rows, i
 }
 
 template <int BN>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiArgs& e, cudaStream_t s) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KArgs& k, int units, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
         ICD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
         attr_set = true;
     }
-    const int tiles = ((e.M + BM - 1) / BM) * ((e.N + BN - 1) / BN);
-    const int grid = tiles < ICD_NUM_SMS ? tiles : ICD_NUM_SMS;
-    gemm_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM, s>>>(tmA, tmB, e);
+    const int grid = units < ICD_NUM_SMS ? units : ICD_NUM_SMS;
+    gemm_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM, s>>>(tmA, tmB, k);
     ICD_LAUNCH_CHECK();
     return 0;
+}
+
+// tile width / split-K plan from a small cost model (SM clocks): one persistent wave of work units should cover the
+// 148 SMs; narrower tiles pay more shared-memory / L2 traffic per flop, split-K pays a second (reduce) kernel.
+struct Plan { int bn, splits, kb_per_split; };
+
+Plan make_plan(int M, int N, int K, bool allow_split) {
+    const int tm = (M + BM - 1) / BM, nkb = (K + BK - 1) / BK;
+    const int cand[3] = {256, 128, 64};
+    const double clk_per_kb[3] = {512.0, 256.0 * 1.15, 192.0 * 1.3};
+    Plan best; best.bn = 64; best.splits = 1; best.kb_per_split = nkb;
+    double best_cost = 1e300;
+    for (int i = 0; i < 3; ++i) {
+        const int bn = cand[i];
+        if (i < 2 && N <= cand[i + 1]) continue;                 // a narrower tile already covers N
+        const int tiles = tm * ((N + bn - 1) / bn);
+        int splits = 1, kbs = nkb;
+        if (allow_split && tiles * 2 <= ICD_NUM_SMS && nkb >= 8) {
+            int s = ICD_NUM_SMS / tiles;
+            if (s > nkb / 4) s = nkb / 4;
+            if (s > 32) s = 32;
+            if (s >= 2) { kbs = (nkb + s - 1) / s; splits = (nkb + kbs - 1) / kbs; }
+        }
+        const double units = (double)tiles * splits;
+        double waves = units / ICD_NUM_SMS;
+        if (waves < 1.0) waves = 1.0;
+        const double cost = waves * kbs * clk_per_kb[i] + 3000.0 + (splits > 1 ? 6000.0 : 0.0);
+        if (cost < best_cost) { best_cost = cost; best.bn = bn; best.splits = splits; best.kb_per_split = kbs; }
+    }
+    return best;
 }
 
 }  // namespace
@@ -334,10 +536,11 @@ int icd_convert_bf16(const float* src, int64_t s_r, int64_t s_c, int rows, int c
     ICD_CHECK_ARG(ldd % 8 == 0 && ldd >= cols, "convert_bf16: ldd=%lld must be a multiple of 8 and >= cols", (long long)ldd);
     __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
     if (s_c == 1) {
-        const long long total = (long long)rows * ((cols + 1) / 2);
+        const int vec = (cols % 4 == 0) && (s_r % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+        const long long total = vec ? (long long)rows * (cols / 4) : (long long)rows * ((cols + 1) / 2);
         long long blocks = (total + 255) / 256;
-        if (blocks > ICD_NUM_SMS * 32) blocks = ICD_NUM_SMS * 32;
-        convert_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, s_r, rows, cols, d, ldd);
+        if (blocks > ICD_NUM_SMS * 16) blocks = ICD_NUM_SMS * 16;
+        convert_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, s_r, rows, cols, d, ldd, vec);
     } else {
         dim3 grid((rows + 31) / 32, (cols + 31) / 32);
         ICD_CHECK_ARG(grid.y <= 65535, "convert_bf16: too many columns for the transposing path");
@@ -347,29 +550,72 @@ int icd_convert_bf16(const float* src, int64_t s_r, int64_t s_c, int rows, int c
     return 0;
 }
 
+int64_t icd_gemm_bf16_splitk_floats(int M, int N, int K) {
+    const Plan p = make_plan(M, N, K, true);
+    return p.splits > 1 ? (int64_t)p.splits * M * N : 0;
+}
+
+int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, int64_t ldb, int b_mn,
+                     float* C, int64_t ldc, int M, int N, int K,
+                     const float* bias1, const float* bias2, const float* add1, int64_t ld1,
+                     const float* add2, int64_t ld2, const uint8_t* row_mask, float beta, cudaStream_t s,
+                     void* C16, int64_t ldc16, float* splitk_ws, int64_t splitk_ws_floats) {
+    if (M == 0 || N == 0) return 0;
+    ICD_CHECK_ARG(K > 0, "gemm_tc: K must be positive");
+    ICD_CHECK_ARG(C != nullptr || C16 != nullptr, "gemm_tc: no output");
+    Plan pl = make_plan(M, N, K, splitk_ws != nullptr);
+    if (pl.splits > 1 && (int64_t)pl.splits * M * N > splitk_ws_floats) {
+        pl.splits = 1; pl.kb_per_split = (K + BK - 1) / BK;
+    }
+    CUtensorMap tmA, tmB;
+    ICD_TRY(make_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(A16), lda, M, K, BM, a_mn));
+    ICD_TRY(make_tmap(&tmB, reinterpret_cast<const __nv_bfloat16*>(B16), ldb, N, K, pl.bn, b_mn));
+    KArgs k;
+    EpiArgs& e = k.e;
+    e.C = C; e.ldc = ldc; e.M = M; e.N = N; e.K = K; e.bias1 = bias1; e.bias2 = bias2;
+    e.add1 = add1; e.ld1 = ld1; e.add2 = add2; e.ld2 = ld2; e.row_mask = row_mask; e.beta = beta;
+    e.C16 = reinterpret_cast<__nv_bfloat16*>(C16); e.ldc16 = ldc16;
+    auto al = [](const void* q, uintptr_t a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
+    e.vec4 = (!C || (al(C, 16) && ldc % 4 == 0)) && (!add1 || (al(add1, 16) && ld1 % 4 == 0)) &&
+             (!add2 || (al(add2, 16) && ld2 % 4 == 0)) && (!C16 || (al(C16, 8) && ldc16 % 4 == 0)) &&
+             (!bias1 || al(bias1, 16)) && (!bias2 || al(bias2, 16));
+    k.a_mn = a_mn ? 1 : 0; k.b_mn = b_mn ? 1 : 0;
+    k.splits = pl.splits; k.kb_per_split = pl.kb_per_split; k.partial = splitk_ws;
+    const int tiles = ((M + BM - 1) / BM) * ((N + pl.bn - 1) / pl.bn);
+    const int units = tiles * pl.splits;
+    switch (pl.bn) {
+        case 256: ICD_TRY(launch<256>(tmA, tmB, k, units, s)); break;
+        case 128: ICD_TRY(launch<128>(tmA, tmB, k, units, s)); break;
+        default:  ICD_TRY(launch<64>(tmA, tmB, k, units, s)); break;
+    }
+    if (pl.splits > 1) {
+        const long long work = ((long long)M * N + 3) / 4;
+        long long blocks = (work + 255) / 256;
+        if (blocks > ICD_NUM_SMS * 8) blocks = ICD_NUM_SMS * 8;
+        splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(splitk_ws, pl.splits, e);
+        ICD_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 int icd_gemm_bf16(const void* A16, int64_t lda, const void* B16, int64_t ldb, float* C, int64_t ldc,
                   int M, int N, int K, const float* bias1, const float* bias2, const float* add1, int64_t ld1,
                   const float* add2, int64_t ld2, const uint8_t* row_mask, float beta, cudaStream_t s,
                   void* C16, int64_t ldc16) {
-    if (M == 0 || N == 0) return 0;
-    ICD_CHECK_ARG(K > 0, "gemm_tc: K must be positive");
-    ICD_CHECK_ARG(C != nullptr || C16 != nullptr, "gemm_tc: no output");
-    const int tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256);
-    const bool use256 = (N > 128) && tiles256 >= ICD_NUM_SMS;
-    const int BN = use256 ? 256 : 128;
-    CUtensorMap tmA, tmB;
-    ICD_TRY(make_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(A16), lda, M, K, BM));
-    ICD_TRY(make_tmap(&tmB, reinterpret_cast<const __nv_bfloat16*>(B16), ldb, N, K, BN));
-    EpiArgs e;
-    e.C = C; e.ldc = ldc; e.M = M; e.N = N; e.K = K; e.bias1 = bias1; e.bias2 = bias2;
-    e.add1 = add1; e.ld1 = ld1; e.add2 = add2; e.ld2 = ld2; e.row_mask = row_mask; e.beta = beta;
-    e.C16 = reinterpret_cast<__nv_bfloat16*>(C16); e.ldc16 = ldc16;
-    return use256 ? launch<256>(tmA, tmB, e, s) : launch<128>(tmA, tmB, e, s);
+    return icd_gemm_bf16_ex(A16, lda, 0, B16, ldb, 0, C, ldc, M, N, K, bias1, bias2, add1, ld1, add2, ld2, row_mask,
+                            beta, s, C16, ldc16, nullptr, 0);
 }
 
+namespace {
+inline int64_t up8(int64_t x) { return (x + 7) / 8 * 8; }
+inline int64_t up256(int64_t x) { return (x + 255) / 256 * 256; }
+}
+
+// workspace of the public fp32-in entry point: bf16 copies of both operands (in their own orientation) + split-K slices
 int64_t icd_gemm_tc_ws_bytes(int M, int N, int K) {
-    const int64_t ldk = ((int64_t)K + 7) / 8 * 8;
-    return ((int64_t)M * ldk * 2 + 255) / 256 * 256 + ((int64_t)N * ldk * 2 + 255) / 256 * 256;
+    const int64_t a = up256(std::max((int64_t)M * up8(K), (int64_t)K * up8(M)) * 2);
+    const int64_t b = up256(std::max((int64_t)N * up8(K), (int64_t)K * up8(N)) * 2);
+    return a + b + up256(icd_gemm_bf16_splitk_floats(M, N, K) * 4);
 }
 
 int icd_gemm_tc_launch(const icd_gemm_desc_t* d, cudaStream_t s) {
@@ -379,11 +625,19 @@ int icd_gemm_tc_launch(const icd_gemm_desc_t* d, cudaStream_t s) {
     const int64_t need = icd_gemm_tc_ws_bytes(d->M, d->N, d->K);
     ICD_CHECK_ARG(d->ws && d->ws_bytes >= need, "gemm: ICD_PREC_BF16 needs %lld bytes of workspace (icd_gemm_ws_bytes), got %lld",
                   (long long)need, (long long)d->ws_bytes);
-    const int64_t ldk = ((int64_t)d->K + 7) / 8 * 8;
+    const int M = d->M, N = d->N, K = d->K;
+    const int a_mn = (d->sak != 1), b_mn = (d->sbk != 1);          // row-contiguous source => MN-major operand, no transpose
+    const int64_t a_bytes = up256(std::max((int64_t)M * up8(K), (int64_t)K * up8(M)) * 2);
+    const int64_t b_bytes = up256(std::max((int64_t)N * up8(K), (int64_t)K * up8(N)) * 2);
     char* a16 = reinterpret_cast<char*>(d->ws);
-    char* b16 = a16 + ((int64_t)d->M * ldk * 2 + 255) / 256 * 256;
-    ICD_TRY(icd_convert_bf16(d->A, d->sam, d->sak, d->M, d->K, a16, ldk, s));
-    ICD_TRY(icd_convert_bf16(d->B, d->sbn, d->sbk, d->N, d->K, b16, ldk, s));
-    return icd_gemm_bf16(a16, ldk, b16, ldk, d->C, d->ldc, d->M, d->N, d->K, d->bias1, d->bias2, d->add1, d->ld1,
-                         d->add2, d->ld2, d->row_mask, d->beta, s, nullptr, 0);
+    char* b16 = a16 + a_bytes;
+    float* sk = reinterpret_cast<float*>(b16 + b_bytes);
+    const int64_t lda = a_mn ? up8(M) : up8(K), ldb = b_mn ? up8(N) : up8(K);
+    if (!a_mn) ICD_TRY(icd_convert_bf16(d->A, d->sam, 1, M, K, a16, lda, s));
+    else       ICD_TRY(icd_convert_bf16(d->A, d->sak, 1, K, M, a16, lda, s));
+    if (!b_mn) ICD_TRY(icd_convert_bf16(d->B, d->sbn, 1, N, K, b16, ldb, s));
+    else       ICD_TRY(icd_convert_bf16(d->B, d->sbk, 1, K, N, b16, ldb, s));
+    return icd_gemm_bf16_ex(a16, lda, a_mn, b16, ldb, b_mn, d->C, d->ldc, M, N, K, d->bias1, d->bias2, d->add1, d->ld1,
+                            d->add2, d->ld2, d->row_mask, d->beta, s, nullptr, 0, sk,
+                            icd_gemm_bf16_splitk_floats(M, N, K));
 }

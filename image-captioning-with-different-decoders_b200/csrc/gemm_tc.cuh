@@ -6,9 +6,18 @@
 // dst[r*ldd + c] = bf16(src[r*s_r + c*s_c]);  one of s_r / s_c must be 1; ldd multiple of 8.
 int icd_convert_bf16(const float* src, int64_t s_r, int64_t s_c, int rows, int cols, void* dst, int64_t ldd,
                      cudaStream_t s);
-// C[M,N] = A16[M,K] * B16[N,K]^T + epilogue; A16/B16 bf16 K-major with leading dimensions lda/ldb (multiples of 8).
+// C[M,N] = A[M,K] * B[N,K]^T + epilogue; A16/B16 bf16 K-major with leading dimensions lda/ldb (multiples of 8).
 int icd_gemm_bf16(const void* A16, int64_t lda, const void* B16, int64_t ldb, float* C, int64_t ldc,
                   int M, int N, int K, const float* bias1, const float* bias2, const float* add1, int64_t ld1,
                   const float* add2, int64_t ld2, const uint8_t* row_mask, float beta, cudaStream_t s,
                   void* C16 = nullptr, int64_t ldc16 = 0);   // optional bf16 copy of the result; C may be NULL then
+// General form.  a_mn / b_mn = 1: the operand is MN-major in memory, i.e. stored as [K][M] (resp. [K][N]) with lda
+// (ldb) elements between consecutive k rows — the layout of every dW = dY^T X and dX = dY W operand, consumed without
+// a transpose.  splitk_ws (optional, icd_gemm_bf16_splitk_floats(M,N,K) floats) enables deterministic split-K.
+int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, int64_t ldb, int b_mn,
+                     float* C, int64_t ldc, int M, int N, int K,
+                     const float* bias1, const float* bias2, const float* add1, int64_t ld1,
+                     const float* add2, int64_t ld2, const uint8_t* row_mask, float beta, cudaStream_t s,
+                     void* C16, int64_t ldc16, float* splitk_ws, int64_t splitk_ws_floats);
+int64_t icd_gemm_bf16_splitk_floats(int M, int N, int K);
 int64_t icd_gemm_tc_ws_bytes(int M, int N, int K);

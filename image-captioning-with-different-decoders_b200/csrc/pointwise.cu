@@ -162,20 +162,18 @@ __global__ void clip_adam_kernel(float* __restrict__ param, const float* __restr
     }
 }
 
-// Row-wise softmax cross-entropy forward + backward in one pass over the logits row held in smem/regs.
-// grid = R rows, block = 256.  row_loss[r] = lse - logit[target] (0 for ignored rows);
-// d_logits[r,:] = (softmax - onehot) * inv_count  (0 for ignored rows).
-__global__ void __launch_bounds__(256) cross_entropy_kernel(int V, const float* __restrict__ logits,
-                                                            const long long* __restrict__ targets,
-                                                            float* __restrict__ row_loss,
-                                                            float* __restrict__ d_logits, float inv_count) {
+// Row-wise softmax cross-entropy.  Forward: grid = R rows, block = 256: row_loss[r] = lse - logit[target] (0 for ignored
+// rows), lse[r] saved.  Backward: one CTA per row again, pure streaming: d = (exp(x - lse) - onehot) * scale with
+// scale = inv_count * upstream[0] read from device memory; optional bf16 copy (row stride ld16, tail columns zeroed).
+__global__ void __launch_bounds__(256) cross_entropy_fwd_kernel(int V, const float* __restrict__ logits,
+                                                                const long long* __restrict__ targets,
+                                                                float* __restrict__ row_loss, float* __restrict__ lse_out) {
     __shared__ float s_red[40];
     const long long r = blockIdx.x;
     const float* x = logits + r * V;
     const long long tgt = targets[r];
     if (tgt < 0) {
-        if (threadIdx.x == 0 && row_loss) row_loss[r] = 0.f;
-        if (d_logits) for (int v = threadIdx.x; v < V; v += blockDim.x) d_logits[r * V + v] = 0.f;
+        if (threadIdx.x == 0) { row_loss[r] = 0.f; lse_out[r] = 0.f; }
         return;
     }
     float m = -INFINITY;
@@ -185,12 +183,46 @@ __global__ void __launch_bounds__(256) cross_entropy_kernel(int V, const float* 
     for (int v = threadIdx.x; v < V; v += blockDim.x) sum += expf(x[v] - m);
     sum = block_sum(sum, s_red);
     const float lse = m + logf(sum);
-    if (threadIdx.x == 0 && row_loss) row_loss[r] = lse - x[tgt];
-    if (d_logits) {
-        float* dx = d_logits + r * V;
+    if (threadIdx.x == 0) { row_loss[r] = lse - x[tgt]; lse_out[r] = lse; }
+}
+
+__global__ void __launch_bounds__(256) cross_entropy_bwd_kernel(int V, const float* __restrict__ logits,
+                                                                const long long* __restrict__ targets,
+                                                                const float* __restrict__ lse_in,
+                                                                const float* __restrict__ upstream, float inv_count,
+                                                                float* __restrict__ d_logits,
+                                                                __nv_bfloat16* __restrict__ d16, long long ld16) {
+    const long long r = blockIdx.x;
+    const float* x = logits + r * V;
+    const long long tgt = targets[r];
+    float* dx = d_logits ? d_logits + r * V : nullptr;
+    __nv_bfloat16* d16r = d16 ? d16 + r * ld16 : nullptr;
+    if (d16r) for (int v = V + threadIdx.x; v < ld16; v += blockDim.x) d16r[v] = __float2bfloat16_rn(0.f);
+    if (tgt < 0) {
         for (int v = threadIdx.x; v < V; v += blockDim.x) {
-            const float pr = expf(x[v] - lse);
-            dx[v] = (pr - (v == tgt ? 1.f : 0.f)) * inv_count;
+            if (dx) dx[v] = 0.f;
+            if (d16r) d16r[v] = __float2bfloat16_rn(0.f);
+        }
+        return;
+    }
+    const float lse = lse_in[r];
+    const float scale = inv_count * (upstream ? upstream[0] : 1.f);
+    // V even and rows 8-byte aligned (V = 9490): 64-bit loads / stores; otherwise scalar
+    if ((V & 1) == 0) {
+        const int V2 = V >> 1;
+        for (int j = threadIdx.x; j < V2; j += blockDim.x) {
+            const float2 xv = *reinterpret_cast<const float2*>(x + 2 * j);
+            float2 g;
+            g.x = (expf(xv.x - lse) - ((2 * j) == tgt ? 1.f : 0.f)) * scale;
+            g.y = (expf(xv.y - lse) - ((2 * j + 1) == tgt ? 1.f : 0.f)) * scale;
+            if (dx) *reinterpret_cast<float2*>(dx + 2 * j) = g;
+            if (d16r) *reinterpret_cast<__nv_bfloat162*>(d16r + 2 * j) = __floats2bfloat162_rn(g.x, g.y);
+        }
+    } else {
+        for (int v = threadIdx.x; v < V; v += blockDim.x) {
+            const float g = (expf(x[v] - lse) - (v == tgt ? 1.f : 0.f)) * scale;
+            if (dx) dx[v] = g;
+            if (d16r) d16r[v] = __float2bfloat16_rn(g);
         }
     }
 }
@@ -277,11 +309,22 @@ extern "C" int icd_clip_adam_step(float* param, const float* grad, float* exp_av
     return 0;
 }
 
-extern "C" int icd_cross_entropy_fwd_bwd(int64_t R, int V, const float* logits, const int64_t* targets,
-                                         float* row_loss, float* d_logits, float inv_count, void* stream) {
+extern "C" int icd_cross_entropy_fwd(int64_t R, int V, const float* logits, const int64_t* targets,
+                                     float* row_loss, float* lse, void* stream) {
     if (R <= 0) return 0;
-    cross_entropy_kernel<<<(unsigned)R, 256, 0, icd_stream(stream)>>>(V, logits, (const long long*)targets,
-                                                                      row_loss, d_logits, inv_count);
+    ICD_CHECK_ARG(row_loss && lse, "cross_entropy_fwd: row_loss and lse are required");
+    cross_entropy_fwd_kernel<<<(unsigned)R, 256, 0, icd_stream(stream)>>>(V, logits, (const long long*)targets, row_loss, lse);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int icd_cross_entropy_bwd(int64_t R, int V, const float* logits, const int64_t* targets, const float* lse,
+                                     const float* upstream, float inv_count, float* d_logits, void* d_logits16,
+                                     int64_t ld16, void* stream) {
+    if (R <= 0) return 0;
+    ICD_CHECK_ARG(!d_logits16 || (ld16 % 8 == 0 && ld16 >= V), "cross_entropy_bwd: ld16=%lld must be a multiple of 8 and >= V", (long long)ld16);
+    cross_entropy_bwd_kernel<<<(unsigned)R, 256, 0, icd_stream(stream)>>>(V, logits, (const long long*)targets, lse, upstream,
+                                                                          inv_count, d_logits, (__nv_bfloat16*)d_logits16, ld16);
     ICD_LAUNCH_CHECK();
     return 0;
 }

@@ -8,8 +8,9 @@
     loss = CrossEntropyLoss()(scores, targets) + ((alpha_c - alphas.sum(dim=1)) ** 2).mean()
 
 The mean cross-entropy over the packed rows does not depend on their order, so the 466 MB packed copy and the
-separate log-softmax / NLL / softmax-backward passes are replaced by ONE kernel (icd_cross_entropy_fwd_bwd) that
-reads each logits row once and writes loss and gradient; rows with t >= batch_size_t carry target -1 and are skipped
+separate log-softmax / NLL / softmax-backward passes are replaced by two streaming kernels (icd_cross_entropy_fwd:
+per-row loss + log-sum-exp; icd_cross_entropy_bwd: gradient, scaled by the upstream gradient read on the device, plus
+a bf16 copy for the tensor-core tier); rows with t >= batch_size_t carry target -1 and are skipped
 (they are the rows pack_padded_sequence drops).  ``baseline_caption_loss`` == models/baseline.py:194-195,224-225
 (CrossEntropyLoss(ignore_index=<pad>) over all (b, t)).
 The doubly-stochastic regulariser touches only the (B,T,196) alphas and stays a torch expression.
@@ -20,17 +21,44 @@ import torch
 from . import ops
 
 
+# bf16 side-channel between the fused loss and the bf16 tier of the decoder backward: the loss backward already streams
+# every logit once, so it also emits the bf16 copy of d(loss)/d(logits) that the vocabulary-layer backward contractions
+# consume — the decoder backward then skips its own fp32 -> bf16 pass over the (B*T, V) gradient.  Keyed by the device
+# address of the fp32 gradient, consumed once, and only honoured if that tensor has not been modified in place since
+# (autograd accumulating a second gradient into it bumps its version counter).
+_BF16_SIDECAR = {}
+
+
+def take_bf16_sidecar(grad):
+    """-> bf16 tensor (R, ld16) matching the fp32 gradient ``grad`` if the fused loss produced one, else None."""
+    ent = _BF16_SIDECAR.pop(grad.data_ptr(), None)
+    _BF16_SIDECAR.clear()
+    if ent is None:
+        return None
+    d16, d32, version = ent
+    if d32.numel() != grad.numel() or d32._version != version or grad._version != version:
+        return None
+    return d16
+
+
 class _FusedCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits2d, targets, n_valid):
-        row_loss, d_logits = ops.cross_entropy_fwd_bwd(logits2d, targets, 1.0 / n_valid, want_grad=True)
-        ctx.save_for_backward(d_logits)
+    def forward(ctx, logits2d, targets, n_valid, want_bf16):
+        row_loss, lse = ops.cross_entropy_fwd(logits2d, targets)
+        ctx.save_for_backward(logits2d, targets, lse)
+        ctx.n_valid, ctx.want_bf16 = n_valid, want_bf16
         return row_loss.sum() / n_valid
 
     @staticmethod
     def backward(ctx, g):
-        (d_logits,) = ctx.saved_tensors
-        return d_logits * g, None, None
+        logits2d, targets, lse = ctx.saved_tensors
+        g = g.reshape(1).float().contiguous()
+        d_logits, d16 = ops.cross_entropy_bwd(logits2d, targets, lse, 1.0 / ctx.n_valid, upstream=g,
+                                              want_bf16=ctx.want_bf16)
+        _BF16_SIDECAR.clear()
+        if d16 is not None:
+            _BF16_SIDECAR[d_logits.data_ptr()] = (d16, d_logits, d_logits._version)
+        return d_logits, None, None, None
 
 
 def packed_targets(encoded_captions, decode_lengths, T, row_valid=None):
@@ -52,7 +80,8 @@ def packed_targets(encoded_captions, decode_lengths, T, row_valid=None):
 def attention_caption_loss(predictions, encoded_captions, decode_lengths, alphas, alpha_c=1.0):
     B, T, V = predictions.shape
     tgt, n_valid = packed_targets(encoded_captions, decode_lengths, T, getattr(predictions, "_icd_row_valid", None))
-    ce = _FusedCE.apply(predictions.reshape(B * T, V), tgt.reshape(-1).contiguous(), n_valid)
+    want_bf16 = bool(getattr(predictions, "_icd_bf16_tier", False))
+    ce = _FusedCE.apply(predictions.reshape(B * T, V), tgt.reshape(-1).contiguous(), n_valid, want_bf16)
     return ce + ((alpha_c - alphas.sum(dim=1)) ** 2).mean()
 
 
@@ -60,4 +89,4 @@ def baseline_caption_loss(outputs, captions, pad_id=0):
     B, L, V = outputs.shape
     tgt = torch.where(captions == pad_id, torch.full_like(captions, -1), captions).reshape(-1).contiguous()
     n_valid = int((tgt >= 0).sum().item())
-    return _FusedCE.apply(outputs.reshape(B * L, V), tgt, max(n_valid, 1))
+    return _FusedCE.apply(outputs.reshape(B * L, V), tgt, max(n_valid, 1), False)

@@ -65,12 +65,11 @@ class _SoftAttentionFn(torch.autograd.Function):
         ones = torch.ones_like(awe)
         d_att_dec, _, d_e = ops.attention_step_bwd(enc, att_enc, att_dec, wf.reshape(-1), alpha, ones, awe, d_awe,
                                                    None if d_alpha is None else d_alpha.contiguous())
-        d_att_enc, d_wf, d_bf = ops.attention_proj_bwd(att_enc, att_dec.view(1, B, A), wf.reshape(-1),
-                                                       d_e.view(B, 1, P), [B])
+        d_att_enc, d_wf, d_bf, d_be = ops.attention_proj_bwd(att_enc, att_dec.view(1, B, A), wf.reshape(-1),
+                                                             d_e.view(B, 1, P), [B])
         dae = d_att_enc.view(B * P, A)
         encf = enc.view(B * P, C)
         d_We = ops.gemm(dae, encf, a_strides=(1, A), b_strides=(1, C), M=A, N=C, K=B * P, precision=prec)
-        d_be = dae.sum(0)
         d_Wd = ops.gemm(d_att_dec, h, a_strides=(1, A), b_strides=(1, h.shape[1]), M=A, N=h.shape[1], K=B,
                         precision=prec)
         d_bd = d_att_dec.sum(0)
@@ -240,6 +239,8 @@ class _AttentionDecoderFn(torch.autograd.Function):
         ctx.dims = (B, T, L, P, C, A, D, E, V, NZ, emb_is_f64)
         ctx.row_valid = bufs["row_valid"]
         predictions._icd_row_valid = bufs["row_valid"]               # (B*T) uint8, reused by the fused loss
+        predictions._icd_bf16_tier = precision == "bf16"             # the fused loss then also emits a bf16 gradient
+        ctx.precision = precision
         return predictions, alphas
 
     @staticmethod
@@ -253,6 +254,10 @@ class _AttentionDecoderFn(torch.autograd.Function):
         if d_pred is None:
             d_pred = torch.zeros(B, T, V, **f32)
         d_pred = d_pred.contiguous().float()
+        d_pred16 = None
+        if ctx.precision == "bf16":
+            from ..losses import take_bf16_sidecar
+            d_pred16 = take_bf16_sidecar(d_pred)
         if d_alphas is not None:
             d_alphas = d_alphas.contiguous().float()
         want_emb = ctx.needs_input_grad[2]
@@ -268,11 +273,12 @@ class _AttentionDecoderFn(torch.autograd.Function):
         scratch = dict(
             d_hdrop=torch.empty(B, T, D, **f32), dz=torch.empty(T, B, NZ, **f32), d_e=torch.empty(B, T, P, **f32),
             dh=torch.empty(B, D, **f32), dc=torch.empty(B, D, **f32), d_gated=torch.empty(B, C, **f32),
-            d_att_enc=torch.empty(B, P, A, **f32),
+            d_att_enc=(torch.empty(B, P, A, **f32) if ctx.precision != "bf16" else None),
             d_emb_x=(torch.empty(T, B, E, **f32) if want_emb else None),
             proj_partial=torch.empty(int(lib().icd_attention_proj_bwd_ws_floats(B, P, A)), **f32))
         d = ctx.desc
-        fill(d, d_predictions=d_pred, d_alphas=d_alphas, **g, **scratch)
+        fill(d, d_predictions=d_pred, d_predictions16=d_pred16,
+             ld_dpred16=(d_pred16.stride(0) if d_pred16 is not None else 0), d_alphas=d_alphas, **g, **scratch)
         check(lib().icd_attention_decoder_bwd(ctypes.byref(d), stream_ptr()), "icd_attention_decoder_bwd")
         dwc, dbc = g["d_w_cat"], g["d_b_cat"]
         d_b_lstm = dbc[A + C:]

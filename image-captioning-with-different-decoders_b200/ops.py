@@ -106,20 +106,22 @@ def attention_step_bwd(enc, att_enc, att_dec, w_full, alpha, gate, awe_raw, d_ga
 
 
 def attention_proj_bwd(att_enc, att_dec_all, w_full, d_e, bt):
-    """att_dec_all (T,B,A) [row stride may exceed A], d_e (B,T,P), bt list[T] -> (d_att_enc, d_w_full, d_b_full)"""
+    """att_dec_all (T,B,A) [row stride may exceed A], d_e (B,T,P), bt list[T]
+    -> (d_att_enc, d_w_full, d_b_full, d_b_enc)   [d_b_enc = d_att_enc summed over (b, p): the enc_att bias gradient]"""
     B, P, A = att_enc.shape
     T = len(bt)
     dev = att_enc.device
     d_att_enc = torch.empty_like(att_enc)
     d_wf = torch.empty(A, device=dev, dtype=torch.float32)
     d_bf = torch.empty(1, device=dev, dtype=torch.float32)
+    d_be = torch.empty(A, device=dev, dtype=torch.float32)
     ws = torch.empty(int(lib().icd_attention_proj_bwd_ws_floats(B, P, A)), device=dev, dtype=torch.float32)
     bt_arr = (ctypes.c_int32 * T)(*bt)
     check(lib().icd_attention_proj_bwd(B, T, P, A, bt_arr, ptr(att_enc), ptr(att_dec_all),
                                        ctypes.c_int64(att_dec_all.stride(1)), ptr(w_full), ptr(d_e),
-                                       ptr(d_att_enc), ptr(d_wf), ptr(d_bf), ptr(ws), stream_ptr()),
+                                       ptr(d_att_enc), ptr(d_wf), ptr(d_bf), ptr(d_be), ptr(ws), stream_ptr()),
           "icd_attention_proj_bwd")
-    return d_att_enc, d_wf, d_bf
+    return d_att_enc, d_wf, d_bf, d_be
 
 
 def init_hidden_state(enc, h_w, h_b, c_w, c_b, precision="fp32"):
@@ -153,16 +155,37 @@ def clip_adam_step(param, grad, exp_avg, exp_avg_sq, step, lr=1e-4, betas=(0.9, 
                                    stream_ptr()), "icd_clip_adam_step")
 
 
-def cross_entropy_fwd_bwd(logits, targets, inv_count, want_grad=True):
-    """logits (R,V) fp32 contiguous, targets (R) int64 (<0 = ignored row).
-    -> (row_loss (R), d_logits (R,V) = (softmax - onehot) * inv_count)"""
+def cross_entropy_fwd(logits, targets):
+    """logits (R,V) fp32 contiguous, targets (R) int64 (<0 = ignored row) -> (row_loss (R), lse (R))"""
     _need_cuda(logits, targets)
     R, V = logits.shape
     row_loss = torch.empty(R, device=logits.device, dtype=torch.float32)
-    d_logits = torch.empty_like(logits) if want_grad else None
-    check(lib().icd_cross_entropy_fwd_bwd(ctypes.c_int64(R), V, ptr(logits), ptr(targets), ptr(row_loss),
-                                          ptr(d_logits), ctypes.c_float(inv_count), stream_ptr()),
-          "icd_cross_entropy_fwd_bwd")
+    lse = torch.empty(R, device=logits.device, dtype=torch.float32)
+    check(lib().icd_cross_entropy_fwd(ctypes.c_int64(R), V, ptr(logits), ptr(targets), ptr(row_loss), ptr(lse),
+                                      stream_ptr()), "icd_cross_entropy_fwd")
+    return row_loss, lse
+
+
+def cross_entropy_bwd(logits, targets, lse, inv_count, upstream=None, want_bf16=False):
+    """-> (d_logits (R,V) fp32 = (softmax - onehot) * inv_count * upstream, d_logits16 (R, up8(V)) bf16 or None);
+    ``upstream`` is a 0-dim / 1-element CUDA fp32 tensor read on the device (no host sync)."""
+    _need_cuda(logits, targets, lse)
+    R, V = logits.shape
+    d_logits = torch.empty_like(logits)
+    d16, ld16 = None, 0
+    if want_bf16:
+        ld16 = (V + 7) // 8 * 8
+        d16 = torch.empty(R, ld16, device=logits.device, dtype=torch.bfloat16)
+    check(lib().icd_cross_entropy_bwd(ctypes.c_int64(R), V, ptr(logits), ptr(targets), ptr(lse), ptr(upstream),
+                                      ctypes.c_float(inv_count), ptr(d_logits), ptr(d16), ctypes.c_int64(ld16),
+                                      stream_ptr()), "icd_cross_entropy_bwd")
+    return d_logits, d16
+
+
+def cross_entropy_fwd_bwd(logits, targets, inv_count, want_grad=True):
+    """Convenience: -> (row_loss (R), d_logits (R,V) = (softmax - onehot) * inv_count)"""
+    row_loss, lse = cross_entropy_fwd(logits, targets)
+    d_logits = cross_entropy_bwd(logits, targets, lse, inv_count)[0] if want_grad else None
     return row_loss, d_logits
 
 
@@ -230,16 +253,20 @@ def attention_step_bwd_bf16(enc16, att_enc16, att_dec, w_full, alpha, gate, awe_
 
 
 def attention_proj_bwd_bf16(att_enc16, att_dec_all, w_full, d_e, bt):
+    """-> (d_att_enc fp32, d_att_enc16 bf16, d_w_full, d_b_full, d_b_enc)"""
     B, P, A = att_enc16.shape
     T = len(bt)
     dev = att_enc16.device
     d_att_enc = torch.empty(B, P, A, device=dev, dtype=torch.float32)
+    d_att_enc16 = torch.empty(B, P, A, device=dev, dtype=torch.bfloat16)
     d_wf = torch.empty(A, device=dev, dtype=torch.float32)
     d_bf = torch.empty(1, device=dev, dtype=torch.float32)
+    d_be = torch.empty(A, device=dev, dtype=torch.float32)
     ws = torch.empty(int(lib().icd_attention_proj_bwd_ws_floats(B, P, A)), device=dev, dtype=torch.float32)
     bt_arr = (ctypes.c_int32 * T)(*bt)
     check(lib().icd_attention_proj_bwd_bf16(B, T, P, A, bt_arr, ptr(att_enc16), ptr(att_dec_all),
                                             ctypes.c_int64(att_dec_all.stride(1)), ptr(w_full), ptr(d_e),
-                                            ptr(d_att_enc), ptr(d_wf), ptr(d_bf), ptr(ws), stream_ptr()),
+                                            ptr(d_att_enc), ptr(d_att_enc16), ptr(d_wf), ptr(d_bf), ptr(d_be), ptr(ws),
+                                            stream_ptr()),
           "icd_attention_proj_bwd_bf16")
-    return d_att_enc, d_wf, d_bf
+    return d_att_enc, d_att_enc16, d_wf, d_bf, d_be

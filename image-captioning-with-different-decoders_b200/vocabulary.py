@@ -13,7 +13,19 @@ END_TOKEN = '<end>'
 UNK_TOKEN = '<unk>'
 
 
-class Vocabulary(object):
+class _VocabularyMeta(type):
+    """``isinstance(v, Vocabulary)`` also accepts the reference's own ``vocabulary.Vocabulary`` (a distinct class
+    object with the same surface), so a checkpointed / pickled reference vocabulary passes the constructor assert
+    of the drop-in decoders (models/attention.py:84)."""
+
+    def __instancecheck__(cls, obj):
+        if type.__instancecheck__(cls, obj):
+            return True
+        return (type(obj).__name__ == "Vocabulary" and hasattr(obj, "w2i") and hasattr(obj, "i2w")
+                and callable(obj) and hasattr(obj, "__len__"))
+
+
+class Vocabulary(object, metaclass=_VocabularyMeta):
     def __init__(self):
         self.w2i = {}
         self.i2w = {}

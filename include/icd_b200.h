@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ICD_B200_ABI_VERSION 7
+#define ICD_B200_ABI_VERSION 8
 #define ICD_MAX_STEPS 256
 
 ICD_API int icd_version(void);                       /* ICD_B200_ABI_VERSION the library was built with */
@@ -133,7 +133,8 @@ ICD_API int icd_attention_step_bwd(int rows, int P, int C, int A,
                            void* stream);
 
 /* After the time loop: d_att_enc[b,p,a] = w_full[a] * sum_t d_e[b,t,p] * [att_enc[b,p,a]+att_dec[t,b,a] > 0]
- * plus the full_att parameter gradients (d_w_full[A], d_b_full[1]).
+ * plus the full_att parameter gradients (d_w_full[A], d_b_full[1]) and, from the same pass, the enc_att bias
+ * gradient d_b_enc[A] = sum_{b,p} d_att_enc[b,p,:] (may be NULL).
  *   att_dec_all: (T, B, *) with row (t,b) at att_dec_all + (t*B+b)*ld_dec ; d_e: (B, T, P)
  *   bt_host[T]: rows active at step t;   partial: workspace of icd_attention_proj_bwd_ws_floats() floats
  */
@@ -141,7 +142,7 @@ ICD_API int64_t icd_attention_proj_bwd_ws_floats(int B, int P, int A);
 ICD_API int icd_attention_proj_bwd(int B, int T, int P, int A, const int32_t* bt_host,
                            const float* att_enc, const float* att_dec_all, int64_t ld_dec,
                            const float* w_full, const float* d_e,
-                           float* d_att_enc, float* d_w_full, float* d_b_full,
+                           float* d_att_enc, float* d_w_full, float* d_b_full, float* d_b_enc,
                            float* partial, void* stream);
 
 /* bf16-STORED feature variants of the three entry points above (tensor-core tier): enc16 (n_img,P,C) and att_enc16
@@ -165,11 +166,12 @@ ICD_API int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
                                 float* d_fbeta_pre, int64_t ld_dfb,
                                 float* d_e, int64_t ld_de,
                                 void* dz16, int64_t ld_dz16, void* stream);
+/* d_att_enc (fp32) and d_att_enc16 (bf16) are both optional outputs (at least one should be given) */
 ICD_API int icd_attention_proj_bwd_bf16(int B, int T, int P, int A, const int32_t* bt_host,
                                 const void* att_enc16, const float* att_dec_all, int64_t ld_dec,
                                 const float* w_full, const float* d_e,
-                                float* d_att_enc, float* d_w_full, float* d_b_full,
-                                float* partial, void* stream);
+                                float* d_att_enc, void* d_att_enc16, float* d_w_full, float* d_b_full,
+                                float* d_b_enc, float* partial, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * AttentionDecoder.forward / backward, teacher-forced (models/attention.py:218-284).
@@ -215,6 +217,9 @@ typedef struct {
     float* gates_pre;             /* (B,4D) scratch */
     /* ---- backward only ---- */
     const float* d_predictions;   /* (B,T,V) */
+    const void* d_predictions16;  /* optional bf16 copy of d_predictions, row stride ld_dpred16 (multiple of 8), as written
+                                     by icd_cross_entropy_bwd; ICD_PREC_BF16 only; NULL => converted internally */
+    int64_t ld_dpred16;
     const float* d_alphas;        /* (B,T,P) or NULL */
     float *d_enc_att_w, *d_enc_att_b;
     float *d_w_cat, *d_b_cat;     /* (NZ,D),(NZ): rows [0,A) dec_att, [A,A+C) f_beta, [A+C,NZ) w_hh / b_hh(=b_ih) */
@@ -230,7 +235,7 @@ typedef struct {
     float* dh;                    /* (B,D)    */
     float* dc;                    /* (B,D)    */
     float* d_gated;               /* (B,C)    */
-    float* d_att_enc;             /* (B,P,A)  */
+    float* d_att_enc;             /* (B,P,A)  ICD_PREC_FP32 only (the bf16 tier keeps a bf16 copy in tc_ws) */
     float* d_emb_x;               /* (T,B,E)  */
     float* proj_partial;          /* icd_attention_proj_bwd_ws_floats(B,P,A) floats */
     /* ICD_PREC_BF16 only: arena for the bf16 operand copies, shared by fwd and bwd of the same step */
@@ -327,13 +332,17 @@ ICD_API int icd_clip_adam_step(float* param, const float* grad, float* exp_avg, 
 ICD_API int icd_dropout_mask(uint8_t* out, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
 
 /* Token-level loss glue (models/attention.py:401-411; models/baseline.py:224-225) fused:
- * mean cross-entropy over the valid rows of logits (R,V) and its gradient written in place of a
- * separate softmax pass.  targets[r] < 0 => row ignored.  loss_sum/count are device scalars (pre-zeroed
- * by the call); d_logits may be NULL (loss only); grad_scale = upstream grad / count is applied by the
- * second entry point once count is known.
+ * forward : row_loss[r] = logsumexp(logits[r,:]) - logits[r, targets[r]], lse[r] saved; targets[r] < 0 => row ignored
+ *           (row_loss 0) — these are the rows pack_padded_sequence drops / ignore_index skips;
+ * backward: d_logits[r,v] = (exp(logits[r,v] - lse[r]) - [v == targets[r]]) * inv_count * (*upstream)  (0 for ignored
+ *           rows); `upstream` is a DEVICE scalar (d loss, read by the kernel: no host sync); d_logits16 is an optional
+ *           bf16 copy with row stride ld16 (multiple of 8) — the A operand of the vocabulary-layer backward contractions.
  */
-ICD_API int icd_cross_entropy_fwd_bwd(int64_t R, int V, const float* logits, const int64_t* targets,
-                              float* row_loss, float* d_logits, float inv_count, void* stream);
+ICD_API int icd_cross_entropy_fwd(int64_t R, int V, const float* logits, const int64_t* targets,
+                          float* row_loss, float* lse, void* stream);
+ICD_API int icd_cross_entropy_bwd(int64_t R, int V, const float* logits, const int64_t* targets, const float* lse,
+                          const float* upstream, float inv_count, float* d_logits, void* d_logits16, int64_t ld16,
+                          void* stream);
 
 #ifdef __cplusplus
 }

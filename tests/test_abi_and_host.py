@@ -142,3 +142,34 @@ def test_flat_param_buffer_views_share_storage():
     m(torch.ones(1, 4)).sum().backward()
     g = buf.gather_grads()
     assert torch.equal(g, torch.cat([p.grad.reshape(-1) for p in m.parameters()]))
+
+
+def test_constructor_accepts_a_foreign_vocabulary_class_with_the_reference_surface():
+    """A maintainer swapping imports (INTEGRATION.md level 1) passes the reference's own ``vocabulary.Vocabulary``."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.vocabulary import Vocabulary as MyVocab
+
+    class Vocabulary(object):          # same surface as the reference's vocabulary.py:8-35, different class object
+        def __init__(self):
+            self.w2i, self.i2w = {}, {}
+
+        def add_word(self, w):
+            if w not in self.w2i:
+                self.i2w[len(self.w2i)] = w
+                self.w2i[w] = len(self.w2i)
+
+        def __call__(self, w):
+            return self.w2i.get(w, self.w2i["<unk>"])
+
+        def __len__(self):
+            return len(self.w2i)
+
+    v = Vocabulary()
+    for w in ["<pad>", "a", "b", "<start>", "<end>", "<unk>"]:
+        v.add_word(w)
+    assert isinstance(v, MyVocab) and not isinstance(object(), MyVocab) and not isinstance({}, MyVocab)
+    p = my_att.AttentionDecoderParams()
+    p.vocab = v
+    p.attention_dim = p.decoder_dim = p.embed_size = 8
+    dec = my_att.AttentionDecoder(torch.device("cpu"), p)
+    assert dec.vocab_size == 6

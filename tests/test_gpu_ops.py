@@ -115,11 +115,12 @@ def test_attention_step_fwd_bwd_matches_oracle_autograd(cuda, R, A, Cdim, use_in
                                                   d_alpha.to(cuda))
     H.assert_close_norm(d_att_dec, ad64.grad, 2e-5, "d_att_dec")
     H.assert_close_norm(d_fb, fb64.grad, 2e-5, "d_fbeta_pre")
-    d_att_enc, d_wf, d_bf = ops.attention_proj_bwd(att_enc.to(cuda), att_dec.detach().to(cuda).view(1, R, A),
+    d_att_enc, d_wf, d_bf, d_be = ops.attention_proj_bwd(att_enc.to(cuda), att_dec.detach().to(cuda).view(1, R, A),
                                                    wf.detach().to(cuda), d_e.view(R, 1, P), [R])
     H.assert_close_norm(d_att_enc, ae64.grad, 2e-5, "d_att_enc")
     H.assert_close_norm(d_wf, wf64.grad, 2e-5, "d_w_full")
     H.assert_close_norm(d_bf, bf64.grad, 1e-4, "d_b_full", atol=1e-5)
+    H.assert_close_norm(d_be, ae64.grad.sum(dim=(0, 1)), 2e-5, "d_b_enc (enc_att bias gradient)")
 
 
 def test_init_hidden_state_matches_oracle(cuda):
@@ -183,6 +184,14 @@ def test_cross_entropy_matches_torch(cuda):
     assert abs(row_loss.sum().item() - loss64.item()) < 1e-5 * abs(loss64.item())
     H.assert_close_norm(dx, x64.grad, 1e-5, "d_logits")
     assert torch.all(dx[5] == 0) and torch.all(dx[11] == 0)
+    # split entry points: upstream gradient read on the device + bf16 copy for the tensor-core tier
+    rl, lse = ops.cross_entropy_fwd(x.to(cuda), t.to(cuda))
+    up = torch.tensor([0.37], device=cuda)
+    d32, d16 = ops.cross_entropy_bwd(x.to(cuda), t.to(cuda), lse, 1.0 / n, upstream=up, want_bf16=True)
+    H.assert_close_norm(d32, x64.grad * 0.37, 1e-5, "d_logits * upstream")
+    assert d16.shape[1] % 8 == 0 and d16.shape[1] >= x.shape[1]
+    H.assert_close_norm(d16[:, :x.shape[1]].float(), x64.grad * 0.37, 4e-3, "d_logits16")
+    assert torch.all(d16[:, x.shape[1]:] == 0)
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 128), (512, 4608, 512), (300, 9490, 512),
@@ -261,7 +270,35 @@ def test_attention_step_bf16_features_matches_oracle_on_rounded_features(cuda, R
     H.assert_close_norm(d_fb, fb64.grad, 2e-5, "d_fbeta_pre")
     H.assert_close_norm(dz16[:, :A].float(), ad64.grad, 4e-3, "dz16[:, :A]")
     H.assert_close_norm(dz16[:, A:].float(), fb64.grad, 4e-3, "dz16[:, A:]")
-    d_att_enc, d_wf, d_bf = ops.attention_proj_bwd_bf16(att_enc16.to(cuda), att_dec.to(cuda).view(1, R, A),
+    d_att_enc, d_att_enc16, d_wf, d_bf, d_be = ops.attention_proj_bwd_bf16(att_enc16.to(cuda), att_dec.to(cuda).view(1, R, A),
                                                         wf.to(cuda), d_e.view(R, 1, P), [R])
     H.assert_close_norm(d_att_enc, ae64.grad, 2e-5, "d_att_enc")
+    H.assert_close_norm(d_att_enc16.float(), ae64.grad, 4e-3, "d_att_enc16")
+    H.assert_close_norm(d_be, ae64.grad.sum(dim=(0, 1)), 2e-5, "d_b_enc")
     H.assert_close_norm(d_wf, wf64.grad, 2e-5, "d_w_full")
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(512, 2048, 2048), (512, 512, 4608), (300, 200, 1000), (128, 64, 64),
+                                   (2048, 520, 12288), (96, 9490, 136), (512, 2048, 40000)])
+def test_gemm_bf16_operand_majors_tiles_and_split_k(cuda, M, N, K, a_mn, b_mn):
+    """Every operand-major combination of the tcgen05 kernel (K-major = rows of K, MN-major = rows of M/N, consumed
+    without a transpose), across the BN = 256/128/64 tile plans and the deterministic split-K plans the shapes select
+    (per-step contractions with M = batch, weight-gradient contractions with K = tokens)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K + a_mn * 2 + b_mn)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g).to(cuda)
+    a_dev = (a.t().contiguous() if a_mn else a).to(cuda)       # MN-major: stored [K][M]
+    b_dev = (b.t().contiguous() if b_mn else b).to(cuda)
+    kw = dict(M=M, N=N, K=K, bias1=bias, precision="bf16")
+    if a_mn:
+        kw["a_strides"] = (1, M)
+    if b_mn:
+        kw["b_strides"] = (1, N)
+    c = ops.gemm(a_dev, b_dev, **kw)
+    ref = a.bfloat16().double() @ b.bfloat16().double().t() + bias.double().cpu()
+    H.assert_close_norm(c, ref, 2e-5, "tc gemm majors (%d,%d) %dx%dx%d" % (a_mn, b_mn, M, N, K))
+    c2 = ops.gemm(a_dev, b_dev, **kw)
+    assert torch.equal(c, c2), "tensor-core contraction (incl. split-K) must be run-to-run deterministic"
