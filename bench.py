@@ -125,43 +125,90 @@ def workload_config(n, precision, batch):
 
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / power / throttle reasons sampled DURING the timed region, in-process through NVML (nvidia_ml_py):
+    a background thread polls every 50 ms with true timestamps.  NVML is initialised before warm-up (its start-up
+    stalls kernel launches for tens of ms, which must not land inside the timed region).  Falls back to an
+    `nvidia-smi -lms` child process when the NVML bindings are unavailable."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows, self.proc = [], None
+    def __init__(self, index, uuid=None):
+        self.rows, self.proc, self.nvml, self.stop_flag = [], None, None, False
+        self.period = float(os.environ.get("ICD_BENCH_SAMPLER_PERIOD", "0.05"))
+        try:
+            if os.environ.get("ICD_BENCH_SAMPLER", "on") == "smi":
+                raise RuntimeError("forced nvidia-smi sampler")
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if uuid:
+                for cand in (uuid, "GPU-" + uuid):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml, self.h = pynvml, h
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        names = (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap),
+                 ("hw_power_brake", n.nvmlClocksEventReasonHwPowerBrakeSlowdown))
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                pw = n.nvmlDeviceGetPowerUsage(self.h) / 1e3
+                self.rows.append((time.perf_counter(), sm, self.max_sm, pw, [k for k, bit in names if mask & bit]))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
     def _read(self):
         for ln in self.proc.stdout:
-            self.rows.append((time.perf_counter(), ln.strip()))
-
-    def window(self, t0, t1):
-        sm, mx, reasons = [], [], set()
-        for t, ln in self.rows:
-            if t < t0 or t > t1:
-                continue
-            f = [x.strip() for x in ln.split(",")]
+            f = [x.strip() for x in ln.strip().split(",")]
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                reasons = [name for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7])
+                           if val.lower().startswith("active")]
+                self.rows.append((time.perf_counter(), float(f[0]), float(f[1]), float(f[2]), reasons))
             except Exception:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+
+    def wait_ready(self, timeout=20.0):
+        t0 = time.perf_counter()
+        while (self.nvml or self.proc) and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.05)
+
+    def window(self, t0, t1):
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        if not rows:      # a timed region shorter than one polling period: take the nearest sample
+            rows = sorted(self.rows, key=lambda r: abs(r[0] - 0.5 * (t0 + t1)))[:1]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        reasons = sorted({x for r in rows for x in r[4]})
+        return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": max(r[2] for r in rows),
+                "power_w_max": max(r[3] for r in rows), "reasons": reasons, "samples": len(rows),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
     def stop(self):
+        self.stop_flag = True
         if self.proc:
             self.proc.terminate()
 
@@ -256,20 +303,31 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ----
-    sampler = ClockSampler(local_rank) if rank == 0 else None     # started before warm-up: NVML start-up stalls launches
+    uuid = None
+    try:
+        uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        pass
+    sampler = ClockSampler(local_rank, uuid) if (rank == 0 and os.environ.get("ICD_BENCH_SAMPLER", "on") != "off") else None
+    if sampler:
+        sampler.wait_ready()
     for _ in range(max(args.warmup, 3)):
         train_step(enc_d, caps_d)
     barrier()
     ops.prof_enable(True)
     launches0 = ops.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
     ev0.record()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         loss = train_step(enc_d, caps_d)
+        step_ev[i].record()
     ev1.record()
+    t_issue = time.perf_counter() - t_wall0                      # host time to ISSUE the K steps (no sync inside)
     barrier()
     t_wall1 = time.perf_counter()
+    per_step_ms = [round((ev0 if i == 0 else step_ev[i - 1]).elapsed_time(step_ev[i]), 3) for i in range(args.steps)]
     launches = ops.launch_count() - launches0
     prof = ops.prof_collect()
     ops.prof_enable(False)
@@ -284,45 +342,61 @@ def main():
     e2e = None
     if not args.no_e2e:
         copy_stream = torch.cuda.Stream()
-        bufs = [(torch.empty_like(enc_d), torch.empty_like(caps_d)) for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        done = [torch.cuda.Event() for _ in range(2)]
 
-        def prefetch(i):
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(done[i % 2])            # buffer free again?
-                bufs[i % 2][0].copy_(enc_h, non_blocking=True)
-                bufs[i % 2][1].copy_(caps_h, non_blocking=True)
-                ready[i % 2].record(copy_stream)
+        def e2e_run(enc_host, n_steps):
+            bufs = [(torch.empty(enc_host.shape, dtype=enc_host.dtype, device=dev), torch.empty_like(caps_d)) for _ in range(2)]
+            ready = [torch.cuda.Event() for _ in range(2)]
+            done = [torch.cuda.Event() for _ in range(2)]
 
-        def e2e_loop(n):
-            for d_ in done:
-                d_.record()
-            prefetch(0)
-            out = 0.0
-            for i in range(n):
-                if i + 1 < n:
-                    prefetch(i + 1)
-                torch.cuda.current_stream().wait_event(ready[i % 2])
-                l = train_step(*bufs[i % 2])
-                done[i % 2].record()
-                out = l.item()                                   # D2H read of the step's loss (sync, as the reference does)
-            return out
-        e2e_loop(2)
-        barrier()
-        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev2.record()
-        e2e_loop(args.steps)
-        ev3.record()
-        barrier()
-        ms2 = torch.tensor([ev2.elapsed_time(ev3)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        e2e = {"value": B * world * args.steps / (float(ms2.item()) / 1e3), "unit": "captions/s",
-               "h2d_bytes_per_step": int(enc_h.numel() * 4 + caps_h.numel() * 8), "d2h_bytes_per_step": 4,
-               "ms_per_step": float(ms2.item()) / args.steps,
-               "note": "per GPU: pinned fp32 features + int64 captions copied H2D every step on a side stream "
+            def prefetch(i):
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(done[i % 2])            # buffer free again?
+                    bufs[i % 2][0].copy_(enc_host, non_blocking=True)
+                    bufs[i % 2][1].copy_(caps_h, non_blocking=True)
+                    ready[i % 2].record(copy_stream)
+
+            def loop(n):
+                for d_ in done:
+                    d_.record()
+                prefetch(0)
+                out = 0.0
+                for i in range(n):
+                    if i + 1 < n:
+                        prefetch(i + 1)
+                    torch.cuda.current_stream().wait_event(ready[i % 2])
+                    l = train_step(*bufs[i % 2])
+                    done[i % 2].record()
+                    out = l.item()                               # D2H read of the step's loss (sync, as the reference does)
+                return out
+            loop(2)
+            barrier()
+            ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev2.record()
+            loop(n_steps)
+            ev3.record()
+            barrier()
+            ms2 = torch.tensor([ev2.elapsed_time(ev3)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+            del bufs
+            return float(ms2.item())
+
+        # headline: features stored bf16 on the host (BASELINE.json configs[2] allows bf16-stored features; the bf16 tier
+        # consumes them in place).  The fp32-host variant (exactly the reference's feature dtype) is reported beside it.
+        host16 = precision == "bf16"
+        enc_h16 = enc_h.to(torch.bfloat16).pin_memory() if host16 else None
+        ms_main = e2e_run(enc_h16 if host16 else enc_h, args.steps)
+        main_bytes = (enc_h16.numel() * 2 if host16 else enc_h.numel() * 4) + caps_h.numel() * 8
+        e2e = {"value": B * world * args.steps / (ms_main / 1e3), "unit": "captions/s",
+               "h2d_bytes_per_step": int(main_bytes), "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_main / args.steps,
+               "host_feature_dtype": "bf16" if host16 else "fp32",
+               "note": "per GPU: pinned host features + int64 captions copied H2D every step on a side stream "
                        "(double-buffered), loss.item() every step"}
+        if host16:
+            ms_f32 = e2e_run(enc_h, args.steps)
+            e2e["fp32_host_features"] = {"value": B * world * args.steps / (ms_f32 / 1e3), "ms_per_step": ms_f32 / args.steps,
+                                         "h2d_bytes_per_step": int(enc_h.numel() * 4 + caps_h.numel() * 8)}
 
     clocks = sampler.window(t_wall0, t_wall1) if sampler else None
     if sampler:
@@ -343,6 +417,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
             "config": workload_config(world, precision, B),
             "loss": last_loss,
+            "per_step_ms": per_step_ms, "host_issue_ms_per_step": 1e3 * t_issue / args.steps,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {

@@ -469,6 +469,63 @@ __global__ void row_len_from_pack_kernel16(int B, int T, const BtPack bt, int* _
     row_len[b] = n;
 }
 
+// pixel mean of bf16-stored features (models/attention.py:161) when the caller hands the features over in bf16.
+// grid = (ceil(C/512), B), block = 256 = 4 pixel groups x 64 lanes of 8 channels (16 B).
+__global__ void __launch_bounds__(256) feature_mean_bf16_kernel(int P, int C, const __nv_bfloat16* __restrict__ enc16,
+                                                                float* __restrict__ mean, __nv_bfloat16* __restrict__ mean16) {
+    __shared__ float s_part[3 * 64 * 8];
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int c = blockIdx.x * 512 + lane * 8;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if (c < C) {
+        const __nv_bfloat16* base = enc16 + (long long)b * P * C + c;
+        int p = grp;
+        for (; p + 6 * 4 < P; p += 7 * 4) {
+            uint4 x[7];
+#pragma unroll
+            for (int u = 0; u < 7; ++u) x[u] = ld_stream_u4(base + (long long)(p + 4 * u) * C);
+#pragma unroll
+            for (int u = 0; u < 7; ++u) {
+                float f[8];
+                unpack8(x[u], f);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] += f[i];
+            }
+        }
+        for (; p < P; p += 4) {
+            const uint4 x = ld_stream_u4(base + (long long)p * C);
+            float f[8];
+            unpack8(x, f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += f[i];
+        }
+    }
+    if (grp > 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_part[((grp - 1) * 64 + lane) * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    if (grp == 0 && c < C) {
+        const float inv = (float)P;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            acc[i] += s_part[(0 * 64 + lane) * 8 + i] + s_part[(1 * 64 + lane) * 8 + i] + s_part[(2 * 64 + lane) * 8 + i];
+            acc[i] /= inv;
+        }
+        const long long o = (long long)b * C + c;
+        if (mean) {
+            *reinterpret_cast<float4*>(mean + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4*>(mean + o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+        if (mean16)
+            *reinterpret_cast<uint4*>(mean16 + o) = make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]),
+                                                               pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
+    }
+}
+
 }  // namespace
 
 extern "C" int icd_attention_step_fwd_bf16(int rows, int P, int C, int A, const int32_t* img_index,
@@ -576,6 +633,15 @@ int icd_convert_features_bf16(int B, int P, int C, const float* enc, void* enc16
     dim3 grid((C + 255) / 256, B);
     convert_features_kernel<<<grid, 256, 0, s>>>(P, C, enc, reinterpret_cast<__nv_bfloat16*>(enc16), mean,
                                                  reinterpret_cast<__nv_bfloat16*>(mean16));
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+int icd_feature_mean_bf16(int B, int P, int C, const void* enc16, float* mean, void* mean16, cudaStream_t s) {
+    ICD_CHECK_ARG(C % 8 == 0 && B <= 65535, "feature_mean_bf16: C=%d must be a multiple of 8, B <= 65535", C);
+    dim3 grid((C + 511) / 512, B);
+    feature_mean_bf16_kernel<<<grid, 256, 0, s>>>(P, C, reinterpret_cast<const __nv_bfloat16*>(enc16), mean,
+                                                  reinterpret_cast<__nv_bfloat16*>(mean16));
     ICD_LAUNCH_CHECK();
     return 0;
 }

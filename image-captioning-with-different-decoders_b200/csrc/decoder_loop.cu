@@ -66,6 +66,7 @@ extern "C" int icd_attention_decoder_fwd(const icd_att_desc_t* d, void* stream) 
     cudaStream_t s = icd_stream(stream);
     if (d->precision == ICD_PREC_BF16) return icd_attention_decoder_fwd_bf16(d, s);
     ICD_CHECK_ARG(d->precision == ICD_PREC_FP32, "attention_decoder: unknown precision %d", d->precision);
+    ICD_CHECK_ARG(d->enc != nullptr, "attention_decoder(fp32): enc is required (bf16-stored features need ICD_PREC_BF16)");
     const int B = d->B, T = d->T, P = d->P, C = d->C, A = d->A, D = d->D, E = d->E, V = d->V;
     const int NZ = A + C + 4 * D;
     const int prec = d->precision;

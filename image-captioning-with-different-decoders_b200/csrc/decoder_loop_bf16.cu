@@ -55,7 +55,8 @@ void carve(const icd_att_desc_t* d, Arena& a, Bufs& b) {
     b.ldE = up8(E); b.ldV = up8(V);
     b.We = a.take(A, C); b.Wcat = a.take(NZ, D); b.WihE = a.take(4 * D, b.ldE); b.WihC = a.take(4 * D, C);
     b.Wh = a.take(D, C); b.Wc = a.take(D, C); b.Wfc = a.take(V, D);
-    b.enc = a.take(B * P, C); b.att_enc = a.take(B * P, A); b.mean = a.take(B, C); b.embx = a.take(TB, b.ldE);
+    b.enc = d->enc16 ? const_cast<void*>(d->enc16) : a.take(B * P, C);      // caller-provided bf16 features are used in place
+    b.att_enc = a.take(B * P, A); b.mean = a.take(B, C); b.embx = a.take(TB, b.ldE);
     b.h = a.take(TB + B, D);
     b.gated = a.take(TB, C); b.hdrop = a.take(B * T, D);
     b.dY = a.take(B * T, b.ldV); b.dz = a.take(TB, NZ); b.dh = a.take(B, D); b.dc = a.take(B, D);
@@ -103,6 +104,7 @@ inline char* at16(void* p, int64_t elem_off) { return reinterpret_cast<char*>(p)
 }  // namespace
 
 int icd_convert_features_bf16(int B, int P, int C, const float* enc, void* enc16, float* mean, void* mean16, cudaStream_t s);
+int icd_feature_mean_bf16(int B, int P, int C, const void* enc16, float* mean, void* mean16, cudaStream_t s);
 
 int64_t icd_att_tc_ws_bytes(const icd_att_desc_t* d) {
     Arena a; a.base = nullptr; a.cap = 0; a.off = 0; a.ok = true;
@@ -150,7 +152,11 @@ int icd_attention_decoder_fwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
     CVT(d->c_lin_w, C, D, C, u.Wc, C);
     CVT(d->fc_w, D, V, D, u.Wfc, D);
     // ---- features: fp32 -> bf16 and the pixel mean (:161) in one pass over encoder_out ----
-    ICD_TRY(icd_convert_features_bf16(B, P, C, d->enc, u.enc, d->mean_enc, u.mean, s));
+    if (d->enc16) ICD_TRY(icd_feature_mean_bf16(B, P, C, d->enc16, d->mean_enc, u.mean, s));
+    else {
+        ICD_CHECK_ARG(d->enc != nullptr, "attention_decoder(bf16): neither enc nor enc16 given");
+        ICD_TRY(icd_convert_features_bf16(B, P, C, d->enc, u.enc, d->mean_enc, u.mean, s));
+    }
 
     // K1: att_enc = enc_att(encoder_out), once per batch (models/attention.py:54); stored bf16 only
     MMX(u.enc, C, 0, u.We, C, 0, nullptr, 0, B * P, A, C, d->enc_att_b, nullptr, nullptr, 0, nullptr, 0, nullptr, u.att_enc, A);

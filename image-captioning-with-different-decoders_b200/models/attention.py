@@ -194,10 +194,17 @@ class _AttentionDecoderFn(torch.autograd.Function):
         if not enc.is_cuda:
             raise _lib.IcdError("AttentionDecoder.forward needs CUDA tensors; there is no CPU fallback")
         dev = enc.device
-        enc = enc.contiguous().float()
+        # bf16 tier: features that already arrive in bf16 (an encoder under autocast, or a bf16 feature store) are used in
+        # place — no fp32 round trip; every other dtype is read as fp32 like the reference's .float() path
+        enc16 = None
+        if precision == "bf16" and enc.dtype == torch.bfloat16:
+            enc16 = enc.contiguous()
+            enc = None
+        else:
+            enc = enc.contiguous().float()
         captions = captions.contiguous()
         assert captions.dtype == torch.int64
-        B, P, C = enc.shape
+        B, P, C = (enc16 if enc is None else enc).shape
         T = len(bt)
         L = captions.shape[1]
         A = weights[0].shape[0]
@@ -221,7 +228,8 @@ class _AttentionDecoderFn(torch.autograd.Function):
             row_valid=torch.empty(B * T, device=dev, dtype=torch.uint8), gates_pre=torch.empty(B, 4 * D, **f32))
         d = _lib.AttDesc()
         fill(d, B=B, T=T, L=L, P=P, C=C, A=A, D=D, E=E, V=V, precision=ops.precision_id(precision),
-             emb_is_f64=int(emb_is_f64), enc=enc, captions=captions, drop_mask=mask, drop_scale=float(drop_scale),
+             emb_is_f64=int(emb_is_f64), enc=enc, enc16=enc16, captions=captions, drop_mask=mask,
+             drop_scale=float(drop_scale),
              emb_w=emb_w.contiguous(), **dict(zip(_W_NAMES, weights)), **bufs)
         for t in range(T):
             d.bt_host[t] = bt[t]
@@ -235,7 +243,7 @@ class _AttentionDecoderFn(torch.autograd.Function):
         # leak ~3 GB of activations per step until the cyclic GC runs) — keep a detached alias of alphas instead
         bufs["alphas_saved"] = alphas.detach()
         ctx.desc = d
-        ctx.keep = (enc, captions, emb_w, weights, mask, bufs)      # keeps every device buffer alive
+        ctx.keep = (enc if enc is not None else enc16, captions, emb_w, weights, mask, bufs)   # keeps buffers alive
         ctx.dims = (B, T, L, P, C, A, D, E, V, NZ, emb_is_f64)
         ctx.row_valid = bufs["row_valid"]
         predictions._icd_row_valid = bufs["row_valid"]               # (B*T) uint8, reused by the fused loss
@@ -248,6 +256,9 @@ class _AttentionDecoderFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             raise NotImplementedError("icd_b200: gradient w.r.t. encoder_out (fine-tuned encoder) is not supported yet")
         B, T, L, P, C, A, D, E, V, NZ, emb_is_f64 = ctx.dims
+        if ctx.keep is None:
+            raise RuntimeError("icd_b200: AttentionDecoder backward called a second time; its saved activations were "
+                               "released after the first backward (like autograd's saved tensors without retain_graph)")
         enc, captions, emb_w, weights, mask, bufs = ctx.keep
         dev = enc.device
         f32 = dict(device=dev, dtype=torch.float32)
@@ -280,6 +291,11 @@ class _AttentionDecoderFn(torch.autograd.Function):
         fill(d, d_predictions=d_pred, d_predictions16=d_pred16,
              ld_dpred16=(d_pred16.stride(0) if d_pred16 is not None else 0), d_alphas=d_alphas, **g, **scratch)
         check(lib().icd_attention_decoder_bwd(ctypes.byref(d), stream_ptr()), "icd_attention_decoder_bwd")
+        # release the ~GBs of saved activations now (stream-ordered: the caching allocator only hands them to later
+        # work on this stream), not when the last reference to the loss tensor dies — otherwise two steps' worth of
+        # activations coexist whenever the caller keeps `loss` across iterations
+        ctx.keep = None
+        ctx.desc = None
         dwc, dbc = g["d_w_cat"], g["d_b_cat"]
         d_b_lstm = dbc[A + C:]
         grads = [

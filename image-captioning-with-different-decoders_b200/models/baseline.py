@@ -85,6 +85,9 @@ class _BaselineDecoderFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_out):
         B, L, E, H, V = ctx.dims
+        if ctx.keep is None:
+            raise RuntimeError("icd_b200: BaselineDecoder backward called a second time; its saved activations were "
+                               "released after the first backward")
         img, captions, emb_w, ws, bufs = ctx.keep
         dev = img.device
         f32 = dict(device=dev, dtype=torch.float32)
@@ -100,5 +103,7 @@ class _BaselineDecoderFn(torch.autograd.Function):
         d = ctx.desc
         fill(d, d_outputs=d_out, **g, **scratch)
         check(lib().icd_baseline_decoder_bwd(ctypes.byref(d), stream_ptr()), "icd_baseline_decoder_bwd")
+        ctx.keep = None          # release the saved activations now, not when the loss tensor dies
+        ctx.desc = None
         return (g["d_img_features"], None, g["d_emb_w"], g["d_w_ih"], g["d_w_hh"], g["d_b"], g["d_b"].clone(),
                 g["d_lin_w"], g["d_lin_b"], None)

@@ -186,6 +186,8 @@ typedef struct {
     int32_t bt_host[ICD_MAX_STEPS]; /* batch_size_t = sum(l > t), first-rows semantics (:261-265)  */
     /* inputs */
     const float* enc;             /* (B,P,C) */
+    const void* enc16;            /* optional, ICD_PREC_BF16 only: the features already stored as bf16 (B,P,C), e.g. the
+                                     output of an encoder run under autocast; `enc` may then be NULL */
     const int64_t* captions;      /* (B,L)   */
     const uint8_t* drop_mask;     /* (T,B,D) keep-mask or NULL (eval / p=0)   (:279)              */
     float drop_scale;             /* 1/(1-p) */

@@ -379,3 +379,28 @@ def test_attention_decoder_bf16_tier_matches_reference_golden(cuda, name):
             assert float(grads[k].abs().max()) < 1e-4
             continue
         compare(case, g, "grad:" + k, grads[k], 1.5e-1 if k in ILL_CONDITIONED else 1e-2)
+
+
+def test_bf16_tier_accepts_bf16_stored_features_in_place(cuda):
+    """Features handed over in bf16 (encoder under autocast / bf16 feature store) are consumed without an fp32 round
+    trip; the result must equal the fp32-input path fed the same (bf16-representable) values."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.vocabulary import synthetic_vocab
+    case = dict(H.ATT_CASES["att_small_ragged"])
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams,
+                                   synthetic_vocab(case["V"])).to(cuda)
+    dec.precision = "bf16"
+    enc, caps, lens = H.att_inputs(case)
+    enc16 = enc.bfloat16()
+    outs = []
+    for feats in (enc16.float().to(cuda), enc16.to(cuda)):
+        dec.zero_grad()
+        preds, _, dl, alphas = dec(feats, caps.to(cuda), lens)
+        loss = O.attention_loss(preds, caps.to(cuda), dl, alphas)
+        loss.backward()
+        outs.append((preds.detach().clone(), alphas.detach().clone(),
+                     {k: p.grad.detach().clone() for k, p in dec.named_parameters()}))
+    H.assert_close_norm(outs[1][0], outs[0][0], 1e-5, "predictions (bf16-stored features)")
+    H.assert_close_norm(outs[1][1], outs[0][1], 1e-5, "alphas (bf16-stored features)")
+    for k in outs[0][2]:
+        H.assert_close_norm(outs[1][2][k], outs[0][2][k], 1e-4, "grad " + k, atol=1e-7)
