@@ -79,6 +79,9 @@ void icd_prof_mark_end(int dir, cudaStream_t s);
 
 // ---- internal (non-exported) launchers shared between translation units -----------------------
 int icd_colsum(const float* X, int64_t ld, int64_t M, int N, const uint8_t* row_mask, float* out, cudaStream_t s);
+int64_t icd_colsum_bf16_ws_floats(int64_t M, int N);
+int icd_colsum_bf16(const void* X16, int64_t ld, int64_t M, int N, const uint8_t* row_mask, float* out, float* ws,
+                    cudaStream_t s);
 int icd_embed_gather(const void* table, int is_f64, const int64_t* captions, int B, int L, int T, int E,
                      float* out /* (T,B,E) */, cudaStream_t s);
 int icd_embed_scatter_add(void* d_table, int is_f64, const int64_t* captions, int B, int L, int T, int E,

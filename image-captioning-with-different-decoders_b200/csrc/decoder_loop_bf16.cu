@@ -46,6 +46,7 @@ struct Bufs {
     void *enc, *att_enc, *mean, *embx, *h, *gated, *hdrop;         // forward activations [rows, features]
     void *dY, *dz, *dh, *dc, *dae;                                 // backward: [rows, features]
     float* splitk; int64_t splitk_floats;                          // deterministic split-K slices
+    float* colsum_ws;                                              // partial column sums of the bf16 dY
     int64_t ldE, ldV;
 };
 
@@ -81,6 +82,7 @@ void carve(const icd_att_desc_t* d, Arena& a, Bufs& b) {
     for (const auto& sh : shapes) { const int64_t n = icd_gemm_bf16_splitk_floats(sh[0], sh[1], sh[2]); if (n > f) f = n; }
     b.splitk_floats = f;
     b.splitk = reinterpret_cast<float*>(a.take_bytes(f * 4));
+    b.colsum_ws = reinterpret_cast<float*>(a.take_bytes(icd_colsum_bf16_ws_floats(B * T, (int)V) * 4));
 }
 
 int check16(const icd_att_desc_t* d, Arena& a, Bufs& b) {
@@ -215,7 +217,7 @@ int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
     if (!dY16) { CVT(d->d_predictions, V, BT, V, u.dY, u.ldV); dY16 = u.dY; ldY = u.ldV; }
     MMX(dY16, ldY, 0, u.Wfc, D, 1, d->d_hdrop, D, BT, D, V, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
     MMX(dY16, ldY, 1, u.hdrop, D, 1, d->d_fc_w, D, V, D, BT, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
-    ICD_TRY(icd_colsum(d->d_predictions, V, (int64_t)BT, V, d->row_valid, d->d_fc_b, s));
+    ICD_TRY(icd_colsum_bf16(dY16, ldY, (int64_t)BT, V, d->row_valid, d->d_fc_b, u.colsum_ws, s));
 
     // ---- BPTT ----
     for (int t = T - 1; t >= 0; --t) {

@@ -29,3 +29,17 @@ int icd_gemm_simple(int prec, const float* A, int64_t sam, int64_t sak, const fl
     d.add2 = add2; d.ld2 = ld2; d.row_mask = row_mask; d.beta = beta; d.precision = prec;
     return icd_gemm(&d, (void*)s);
 }
+
+extern "C" int64_t icd_gemm_bf16_splitk_ws_floats(int32_t M, int32_t N, int32_t K) {
+    return icd_gemm_bf16_splitk_floats(M, N, K);
+}
+
+extern "C" int icd_gemm_bf16_operands(const void* A16, int64_t lda, int32_t a_mn, const void* B16, int64_t ldb, int32_t b_mn,
+                                      float* C, int64_t ldc, void* C16, int64_t ldc16, int32_t M, int32_t N, int32_t K,
+                                      const float* bias1, const float* add1, int64_t ld1, const uint8_t* row_mask,
+                                      float* splitk_ws, int64_t splitk_ws_floats, void* stream) {
+    ICD_CHECK_ARG(A16 && B16, "gemm_bf16_operands: null operand");
+    ICD_CHECK_ARG(M >= 0 && N >= 0 && K > 0, "gemm_bf16_operands: bad dims");
+    return icd_gemm_bf16_ex(A16, lda, a_mn, B16, ldb, b_mn, C, ldc, M, N, K, bias1, nullptr, add1, ld1, nullptr, 0, row_mask,
+                            0.f, icd_stream(stream), C16, ldc16, splitk_ws, splitk_ws_floats);
+}

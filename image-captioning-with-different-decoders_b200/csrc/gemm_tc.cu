@@ -21,6 +21,7 @@
 #include "gemm_tc.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cmath>
 #include <mutex>
 
 namespace {
@@ -41,7 +42,7 @@ struct EpiArgs {
     const unsigned char* row_mask;
     float beta;
     __nv_bfloat16* C16; long long ldc16;      // optional bf16 copy of the result (C may then be NULL)
-    int vec4;                                 // every row start of C / add1 / add2 / C16 is 16-byte (8 for C16) aligned
+    int vec;                                  // 4 / 2 / 1: widest vector (in floats) every row start of C / add / C16 allows
 };
 
 struct KArgs {
@@ -129,10 +130,18 @@ struct Cfg {
 };
 
 // One 32x32 sub-tile of the accumulator, already transposed into sE (row stride EPI_LD): apply the fused epilogue and
-// write it out with coalesced accesses.  vec4: lane -> 4 consecutive columns, 8 lanes per row, 4 rows per instruction.
+// write it out with coalesced accesses.  rowbits: bit r set <=> row mrow0 + r is inside M and not masked out (the row
+// mask is read ONCE per sub-tile, one coalesced byte load + a warp ballot, never in the store loop).
+//   vec4 : lane -> 4 consecutive columns, 8 lanes per row, 4 rows per instruction (128-bit accesses)
+//   vec2 : lane -> 2 consecutive columns, 16 lanes per row, 2 rows per instruction (64-bit; row stride even, e.g. V = 9490)
+//   else : lane -> 1 column, 1 row per instruction (still 128 B coalesced); also the N tail of the other two
 __device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ sE, int lane, int mrow0, int nb,
                                                      const EpiArgs& e) {
-    if (e.vec4 && nb + 32 <= e.N) {
+    unsigned inb = (mrow0 + lane < e.M) ? 1u : 0u;
+    unsigned keep = inb;
+    if (e.row_mask && inb) keep = e.row_mask[mrow0 + lane] ? 1u : 0u;
+    const unsigned rows_in = __ballot_sync(0xffffffffu, inb != 0), rows_keep = __ballot_sync(0xffffffffu, keep != 0);
+    if (e.vec >= 4 && nb + 32 <= e.N) {
         const int cc = (lane & 7) * 4, n = nb + cc;
         float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e.bias1) { const float4 b = *reinterpret_cast<const float4*>(e.bias1 + n); bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w; }
@@ -140,9 +149,9 @@ __device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ s
         float4 a1[8], a2[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int m = mrow0 + i * 4 + (lane >> 3);
+            const int rr = i * 4 + (lane >> 3), m = mrow0 + rr;
             a1[i] = make_float4(0.f, 0.f, 0.f, 0.f); a2[i] = a1[i];
-            if (m < e.M) {
+            if ((rows_keep >> rr) & 1u) {
                 if (e.add1) a1[i] = *reinterpret_cast<const float4*>(e.add1 + (long long)m * e.ld1 + n);
                 if (e.add2) a2[i] = *reinterpret_cast<const float4*>(e.add2 + (long long)m * e.ld2 + n);
                 if (e.beta != 0.f && e.C) {
@@ -154,11 +163,11 @@ __device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ s
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int rr = i * 4 + (lane >> 3), m = mrow0 + rr;
-            if (m >= e.M) continue;
+            if (!((rows_in >> rr) & 1u)) continue;
             const float* s = sE + rr * EPI_LD + cc;
             float4 x = make_float4(s[0] + bsum.x + a1[i].x + a2[i].x, s[1] + bsum.y + a1[i].y + a2[i].y,
                                    s[2] + bsum.z + a1[i].z + a2[i].z, s[3] + bsum.w + a1[i].w + a2[i].w);
-            if (e.row_mask && !e.row_mask[m]) x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!((rows_keep >> rr) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
             if (e.C) *reinterpret_cast<float4*>(e.C + (long long)m * e.ldc + n) = x;
             if (e.C16) {
                 const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
@@ -167,9 +176,36 @@ __device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ s
                 *reinterpret_cast<uint2*>(e.C16 + (long long)m * e.ldc16 + n) = pk;
             }
         }
+    } else if (e.vec >= 2 && nb + 32 <= e.N) {
+        const int cc = (lane & 15) * 2, n = nb + cc;
+        float2 bsum = make_float2(0.f, 0.f);
+        if (e.bias1) { const float2 b = *reinterpret_cast<const float2*>(e.bias1 + n); bsum.x += b.x; bsum.y += b.y; }
+        if (e.bias2) { const float2 b = *reinterpret_cast<const float2*>(e.bias2 + n); bsum.x += b.x; bsum.y += b.y; }
+#pragma unroll 1
+        for (int i0 = 0; i0 < 16; i0 += 8) {
+            float2 a[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int rr = (i0 + u) * 2 + (lane >> 4), m = mrow0 + rr;
+                a[u] = make_float2(0.f, 0.f);
+                if ((rows_keep >> rr) & 1u) {
+                    if (e.add1) { const float2 t = *reinterpret_cast<const float2*>(e.add1 + (long long)m * e.ld1 + n); a[u].x += t.x; a[u].y += t.y; }
+                    if (e.add2) { const float2 t = *reinterpret_cast<const float2*>(e.add2 + (long long)m * e.ld2 + n); a[u].x += t.x; a[u].y += t.y; }
+                    if (e.beta != 0.f && e.C) { const float2 t = *reinterpret_cast<const float2*>(e.C + (long long)m * e.ldc + n); a[u].x += e.beta * t.x; a[u].y += e.beta * t.y; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int rr = (i0 + u) * 2 + (lane >> 4), m = mrow0 + rr;
+                if (!((rows_in >> rr) & 1u)) continue;
+                const float* s = sE + rr * EPI_LD + cc;
+                float2 x = make_float2(s[0] + bsum.x + a[u].x, s[1] + bsum.y + a[u].y);
+                if (!((rows_keep >> rr) & 1u)) x = make_float2(0.f, 0.f);
+                if (e.C) *reinterpret_cast<float2*>(e.C + (long long)m * e.ldc + n) = x;
+                if (e.C16) *reinterpret_cast<__nv_bfloat162*>(e.C16 + (long long)m * e.ldc16 + n) = __floats2bfloat162_rn(x.x, x.y);
+            }
+        }
     } else {
-        // generic path: lane -> one column, one row per instruction (still 128 B coalesced); handles the N tail and
-        // row strides that are not multiples of 4 (the (B,T,V) logits with V = 9490)
         const int n = nb + lane;
         const bool nok = n < e.N;
         float bsum = 0.f;
@@ -179,9 +215,9 @@ __device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ s
             float a[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int m = mrow0 + r0 + u;
+                const int rr = r0 + u, m = mrow0 + rr;
                 a[u] = 0.f;
-                if (nok && m < e.M) {
+                if (nok && ((rows_keep >> rr) & 1u)) {
                     if (e.add1) a[u] += e.add1[(long long)m * e.ld1 + n];
                     if (e.add2) a[u] += e.add2[(long long)m * e.ld2 + n];
                     if (e.beta != 0.f && e.C) a[u] += e.beta * e.C[(long long)m * e.ldc + n];
@@ -189,10 +225,10 @@ __device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ s
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int m = mrow0 + r0 + u;
-                if (!nok || m >= e.M) continue;
-                float x = sE[(r0 + u) * EPI_LD + lane] + bsum + a[u];
-                if (e.row_mask && !e.row_mask[m]) x = 0.f;
+                const int rr = r0 + u, m = mrow0 + rr;
+                if (!nok || !((rows_in >> rr) & 1u)) continue;
+                float x = sE[rr * EPI_LD + lane] + bsum + a[u];
+                if (!((rows_keep >> rr) & 1u)) x = 0.f;
                 if (e.C) e.C[(long long)m * e.ldc + n] = x;
                 if (e.C16) e.C16[(long long)m * e.ldc16 + n] = __float2bfloat16_rn(x);
             }
@@ -310,7 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.splits > 1) {                                       // raw partial tile, epilogue deferred
                 ee.C = p.partial + (long long)slice * e.M * e.N; ee.ldc = e.N;
                 ee.bias1 = ee.bias2 = ee.add1 = ee.add2 = nullptr; ee.row_mask = nullptr; ee.beta = 0.f; ee.C16 = nullptr;
-                ee.vec4 = (e.N % 4 == 0);
+                ee.vec = (e.N % 4 == 0) ? 4 : ((e.N % 2 == 0) ? 2 : 1);
             }
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
@@ -356,7 +392,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // split-K second pass: C = epilogue(sum_s partial[s]) with the slices summed in fixed order (deterministic).
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, const EpiArgs e) {
     const long long MN = (long long)e.M * e.N;
-    if (e.vec4 && e.N % 4 == 0) {
+    if (e.vec >= 4 && e.N % 4 == 0) {
         const long long total = MN / 4;
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
             const long long o = i * 4;
@@ -517,8 +553,9 @@ Plan make_plan(int M, int N, int K, bool allow_split) {
             if (s >= 2) { kbs = (nkb + s - 1) / s; splits = (nkb + kbs - 1) / kbs; }
         }
         const double units = (double)tiles * splits;
-        double waves = units / ICD_NUM_SMS;
-        if (waves < 1.0) waves = 1.0;
+        double waves = units / ICD_NUM_SMS;                      // static round-robin: the busiest CTA does ceil() units,
+        if (waves < 1.0) waves = 1.0;                            // but short tiles overlap their epilogues: blend
+        else waves = 0.5 * (waves + std::ceil(waves));
         const double cost = waves * kbs * clk_per_kb[i] + 3000.0 + (splits > 1 ? 6000.0 : 0.0);
         if (cost < best_cost) { best_cost = cost; best.bn = bn; best.splits = splits; best.kb_per_split = kbs; }
     }
@@ -576,9 +613,12 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
     e.add1 = add1; e.ld1 = ld1; e.add2 = add2; e.ld2 = ld2; e.row_mask = row_mask; e.beta = beta;
     e.C16 = reinterpret_cast<__nv_bfloat16*>(C16); e.ldc16 = ldc16;
     auto al = [](const void* q, uintptr_t a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
-    e.vec4 = (!C || (al(C, 16) && ldc % 4 == 0)) && (!add1 || (al(add1, 16) && ld1 % 4 == 0)) &&
-             (!add2 || (al(add2, 16) && ld2 % 4 == 0)) && (!C16 || (al(C16, 8) && ldc16 % 4 == 0)) &&
-             (!bias1 || al(bias1, 16)) && (!bias2 || al(bias2, 16));
+    auto fits = [&](int v) {     // v floats per access: fp32 rows aligned to 4v bytes, bf16 rows to 2v bytes
+        return (!C || (al(C, 4 * v) && ldc % v == 0)) && (!add1 || (al(add1, 4 * v) && ld1 % v == 0)) &&
+               (!add2 || (al(add2, 4 * v) && ld2 % v == 0)) && (!C16 || (al(C16, 2 * v) && ldc16 % v == 0)) &&
+               (!bias1 || al(bias1, 4 * v)) && (!bias2 || al(bias2, 4 * v));
+    };
+    e.vec = fits(4) ? 4 : (fits(2) ? 2 : 1);
     k.a_mn = a_mn ? 1 : 0; k.b_mn = b_mn ? 1 : 0;
     k.splits = pl.splits; k.kb_per_split = pl.kb_per_split; k.partial = splitk_ws;
     const int tiles = ((M + BM - 1) / BM) * ((N + pl.bn - 1) / pl.bn);

@@ -93,6 +93,44 @@ __global__ void colsum_kernel(const float* __restrict__ X, long long ld, long lo
     }
 }
 
+// partial[chunk][n] = sum over the rows of `chunk` of mask[m] * X16[m*ld + n]   (bf16 source, fp32 accumulate).
+// grid = (ceil(N/256), chunks), block = 128 threads x 2 columns; rows of a chunk are streamed with 32-bit loads.
+__global__ void __launch_bounds__(128) colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ X, long long ld,
+                                                                  long long M, int N, int rows_per_chunk,
+                                                                  const unsigned char* __restrict__ row_mask,
+                                                                  float* __restrict__ partial) {
+    const int n = blockIdx.x * 256 + threadIdx.x * 2;
+    const long long m0 = (long long)blockIdx.y * rows_per_chunk;
+    const long long m1 = min(M, m0 + rows_per_chunk);
+    float a0 = 0.f, a1 = 0.f;
+    if (n < N) {
+        const bool pair = (n + 1 < N);
+        long long m = m0;
+        for (; m + 3 < m1; m += 4) {
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const __nv_bfloat16* p = X + (m + u) * ld + n;
+                v[u] = pair ? *reinterpret_cast<const uint32_t*>(p) : (uint32_t)(*reinterpret_cast<const unsigned short*>(p));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (row_mask && !row_mask[m + u]) continue;
+                a0 += __uint_as_float(v[u] << 16); a1 += __uint_as_float(v[u] & 0xffff0000u);
+            }
+        }
+        for (; m < m1; ++m) {
+            if (row_mask && !row_mask[m]) continue;
+            const __nv_bfloat16* p = X + m * ld + n;
+            const uint32_t v = pair ? *reinterpret_cast<const uint32_t*>(p) : (uint32_t)(*reinterpret_cast<const unsigned short*>(p));
+            a0 += __uint_as_float(v << 16); a1 += __uint_as_float(v & 0xffff0000u);
+        }
+        float* o = partial + (long long)blockIdx.y * N + n;
+        o[0] = a0;
+        if (pair) o[1] = a1;
+    }
+}
+
 template <typename TT>
 __global__ void embed_gather_kernel(const TT* __restrict__ table, const long long* __restrict__ captions,
                                     int B, int L, int T, int E, float* __restrict__ out) {
@@ -165,10 +203,23 @@ __global__ void clip_adam_kernel(float* __restrict__ param, const float* __restr
 // Row-wise softmax cross-entropy.  Forward: grid = R rows, block = 256: row_loss[r] = lse - logit[target] (0 for ignored
 // rows), lse[r] saved.  Backward: one CTA per row again, pure streaming: d = (exp(x - lse) - onehot) * scale with
 // scale = inv_count * upstream[0] read from device memory; optional bf16 copy (row stride ld16, tail columns zeroed).
+__device__ __forceinline__ void online_add(float& m, float& s, float x) {       // running (max, sum exp(x - max))
+    const float mn = fmaxf(m, x);
+    s = s * __expf(m - mn) + __expf(x - mn);
+    m = mn;
+}
+__device__ __forceinline__ void online_merge(float& m, float& s, float m2, float s2) {
+    const float mn = fmaxf(m, m2);
+    const float a = (m == -INFINITY) ? 0.f : s * __expf(m - mn);
+    const float b = (m2 == -INFINITY) ? 0.f : s2 * __expf(m2 - mn);
+    s = a + b; m = mn;
+}
+
+// single pass over the row: online log-sum-exp, 64-bit loads (rows are 8-byte aligned when V is even), 4 loads in flight
 __global__ void __launch_bounds__(256) cross_entropy_fwd_kernel(int V, const float* __restrict__ logits,
                                                                 const long long* __restrict__ targets,
                                                                 float* __restrict__ row_loss, float* __restrict__ lse_out) {
-    __shared__ float s_red[40];
+    __shared__ float s_m[8], s_s[8];
     const long long r = blockIdx.x;
     const float* x = logits + r * V;
     const long long tgt = targets[r];
@@ -176,14 +227,41 @@ __global__ void __launch_bounds__(256) cross_entropy_fwd_kernel(int V, const flo
         if (threadIdx.x == 0) { row_loss[r] = 0.f; lse_out[r] = 0.f; }
         return;
     }
-    float m = -INFINITY;
-    for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, x[v]);
-    m = block_max(m, s_red);
-    float sum = 0.f;
-    for (int v = threadIdx.x; v < V; v += blockDim.x) sum += expf(x[v] - m);
-    sum = block_sum(sum, s_red);
-    const float lse = m + logf(sum);
-    if (threadIdx.x == 0) { row_loss[r] = lse - x[tgt]; lse_out[r] = lse; }
+    float m = -INFINITY, s = 0.f;
+    if ((V & 1) == 0) {
+        const int V2 = V >> 1;
+        const float2* x2 = reinterpret_cast<const float2*>(x);
+        int j = threadIdx.x;
+        for (; j + 3 * 256 < V2; j += 4 * 256) {
+            float2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = x2[j + u * 256];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float mx = fmaxf(v[u].x, v[u].y), mn = fmaxf(m, mx);
+                s = s * __expf(m - mn) + __expf(v[u].x - mn) + __expf(v[u].y - mn);
+                m = mn;
+            }
+        }
+        for (; j < V2; j += 256) { const float2 v = x2[j]; online_add(m, s, v.x); online_add(m, s, v.y); }
+    } else {
+        for (int v = threadIdx.x; v < V; v += 256) online_add(m, s, x[v]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        online_merge(m, s, m2, s2);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { s_m[w] = m; s_s[w] = s; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float M = s_m[0], S = s_s[0];
+        for (int i = 1; i < 8; ++i) online_merge(M, S, s_m[i], s_s[i]);
+        const float lse = M + logf(S);
+        row_loss[r] = lse - x[tgt];
+        lse_out[r] = lse;
+    }
 }
 
 __global__ void __launch_bounds__(256) cross_entropy_bwd_kernel(int V, const float* __restrict__ logits,
@@ -262,6 +340,25 @@ int icd_colsum(const float* X, int64_t ld, int64_t M, int N, const uint8_t* row_
     colsum_kernel<<<(N + 31) / 32, dim3(32, 32), 0, s>>>(X, ld, M, N, row_mask, out);
     ICD_LAUNCH_CHECK();
     return 0;
+}
+
+int64_t icd_colsum_bf16_ws_floats(int64_t M, int N) {
+    const int64_t chunks = (M + 511) / 512;
+    return chunks * N;
+}
+
+// out[n] = sum_m mask[m] * X16[m*ld + n] over a tall bf16 matrix; deterministic (fixed chunking, fixed order).
+int icd_colsum_bf16(const void* X16, int64_t ld, int64_t M, int N, const uint8_t* row_mask, float* out, float* ws,
+                    cudaStream_t s) {
+    if (N == 0) return 0;
+    ICD_CHECK_ARG(ld % 2 == 0, "colsum_bf16: ld must be even");
+    const int rows_per_chunk = 512;
+    const int chunks = (int)((M + rows_per_chunk - 1) / rows_per_chunk);
+    dim3 grid((N + 255) / 256, chunks);
+    colsum_bf16_partial_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(X16), ld, M, N, rows_per_chunk,
+                                                    row_mask, ws);
+    ICD_LAUNCH_CHECK();
+    return icd_colsum(ws, N, chunks, N, nullptr, out, s);
 }
 
 int icd_embed_gather(const void* table, int is_f64, const int64_t* captions, int B, int L, int T, int E,

@@ -65,6 +65,32 @@ def gemm(a, b, *, a_strides=None, b_strides=None, out=None, ldc=None, M=None, N=
     return out
 
 
+def gemm_bf16(a16, b16, M, N, K, *, a_mn=False, b_mn=False, out=None, out16=None, bias1=None, add1=None, row_mask=None,
+              split_k=True, want_fp32=True, ldc=None):
+    """Tensor-core contraction on operands already stored in bf16 (no staging pass).  a16: (M,K) [a_mn=False] or (K,M)
+    [a_mn=True] torch.bfloat16 (row stride = leading dimension, multiple of 8); b16 likewise with N.
+    -> (C fp32 (M,N) or None, C16 bf16 or None)"""
+    _need_cuda(a16, b16)
+    assert a16.dtype == torch.bfloat16 and b16.dtype == torch.bfloat16
+    dev = a16.device
+    if out is None and want_fp32:
+        out = torch.empty(M, N, device=dev, dtype=torch.float32)
+    if ldc is None:
+        ldc = out.stride(0) if out is not None else 0
+    ws, nws = None, 0
+    if split_k:
+        nws = int(lib().icd_gemm_bf16_splitk_ws_floats(M, N, K))
+        if nws:
+            ws = torch.empty(nws, device=dev, dtype=torch.float32)
+    check(lib().icd_gemm_bf16_operands(ptr(a16), ctypes.c_int64(a16.stride(0)), int(a_mn), ptr(b16),
+                                       ctypes.c_int64(b16.stride(0)), int(b_mn), ptr(out), ctypes.c_int64(ldc),
+                                       ptr(out16), ctypes.c_int64(out16.stride(0) if out16 is not None else 0),
+                                       M, N, K, ptr(bias1), ptr(add1),
+                                       ctypes.c_int64(add1.stride(0) if add1 is not None else 0), ptr(row_mask),
+                                       ptr(ws), ctypes.c_int64(nws), stream_ptr()), "icd_gemm_bf16_operands")
+    return out, out16
+
+
 def attention_step_fwd(enc, att_enc, att_dec, w_full, b_full, fbeta_pre=None, img_index=None):
     """-> (alpha (R,P), awe_raw (R,C), gate, gated)   [gate/gated None when fbeta_pre is None]"""
     _need_cuda(enc, att_enc, att_dec)

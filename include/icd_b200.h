@@ -89,6 +89,19 @@ typedef struct {
 ICD_API int64_t icd_gemm_ws_bytes(int32_t M, int32_t N, int32_t K, int32_t precision);
 ICD_API int icd_gemm(const icd_gemm_desc_t* d, void* stream);
 
+/* The tensor-core contraction on operands that are ALREADY bf16 (no staging pass): C[M,N] (fp32, optional) and / or
+ * C16[M,N] (bf16, optional) = A * B^T + bias1[n] + add1[m,n], rows with row_mask[m] == 0 forced to 0.
+ *   a_mn = 0: A is K-major, stored [M][K] with lda elements between rows;  a_mn = 1: MN-major, stored [K][M] with lda
+ *   elements between k rows (a row-major activation used as the dY^T operand of dW = dY^T X).  Same for B / b_mn.
+ *   lda / ldb multiples of 8, operands 16-byte aligned.  splitk_ws: optional icd_gemm_bf16_splitk_ws_floats(M,N,K)
+ *   floats enabling deterministic split-K for small M x N.
+ */
+ICD_API int64_t icd_gemm_bf16_splitk_ws_floats(int32_t M, int32_t N, int32_t K);
+ICD_API int icd_gemm_bf16_operands(const void* A16, int64_t lda, int32_t a_mn, const void* B16, int64_t ldb, int32_t b_mn,
+                           float* C, int64_t ldc, void* C16, int64_t ldc16, int32_t M, int32_t N, int32_t K,
+                           const float* bias1, const float* add1, int64_t ld1, const uint8_t* row_mask,
+                           float* splitk_ws, int64_t splitk_ws_floats, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * SoftAttention step, forward (models/attention.py:55-60 with att_enc hoisted, + :270-271 gate).
  *   rows      : number of decoder rows processed (batch_size_t, or images*beams)

@@ -1,0 +1,58 @@
+"""Isolated timing of the tcgen05 contraction on the shapes of the train step (CUDA events, warm L2).
+    python tools/gemm_bench.py            # on the GPU box
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import __graft_entry__  # noqa: E402
+
+__graft_entry__.build()
+from icd_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+B, T, P, C, A, D, E, V = 512, 24, 196, 2048, 512, 512, 512, 9490
+NZ = A + C + 4 * D
+
+
+def run(name, M, N, K, a_mn=False, b_mn=False, fp32=True, bf16=False, mask=False, bias=False, add=False, ldc=None, iters=20):
+    a = torch.randn((K, M) if a_mn else (M, K), device=dev).bfloat16()
+    b = torch.randn((K, N) if b_mn else (N, K), device=dev).bfloat16()
+    ldc = ldc or N
+    out = torch.empty(M, ldc, device=dev) if fp32 else None
+    out16 = torch.empty(M, (N + 7) // 8 * 8, device=dev, dtype=torch.bfloat16) if bf16 else None
+    kw = dict(a_mn=a_mn, b_mn=b_mn, out=out, out16=out16, want_fp32=fp32, ldc=ldc,
+              bias1=torch.randn(N, device=dev) if bias else None,
+              add1=torch.randn(M, N, device=dev) if add else None,
+              row_mask=torch.ones(M, device=dev, dtype=torch.uint8) if mask else None)
+    for _ in range(3):
+        ops.gemm_bf16(a, b, M, N, K, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ops.gemm_bf16(a, b, M, N, K, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    print("%-34s M=%6d N=%5d K=%6d  %8.1f us  %7.1f TF/s" % (name, M, N, K, us, 2.0 * M * N * K / us / 1e6), flush=True)
+
+
+run("K1 enc_att (bf16 out)", B * P, A, C, fp32=False, bf16=True, bias=True)
+run("K5 emb*W_ih (fp32 out)", T * B, 4 * D, E, bias=True)
+run("K6 fc fwd (ldc=V, mask)", B * T, V, D, bias=True, mask=True)
+run("K6 fc fwd (ldc=V, no mask)", B * T, V, D, bias=True)
+run("K6 fc fwd (ldc=9496)", B * T, V, D, bias=True, mask=True, ldc=9496)
+run("d_hdrop dY*Wfc", B * T, D, V - 2, b_mn=True)
+run("d_fc_w dY^T*hdrop", V - 2, D, B * T, a_mn=True, b_mn=True)
+run("d_w_cat", NZ, D, T * B, a_mn=True, b_mn=True)
+run("d_w_ih(C)", 4 * D, C, T * B, a_mn=True, b_mn=True)
+run("dW_e", A, C, B * P, a_mn=True, b_mn=True)
+run("K2 z (step)", B, NZ, D, bias=True, iters=100)
+run("K4 gates (step)", B, 4 * D, C, add=True, iters=100)
+run("d_gated (step)", B, C, 4 * D, b_mn=True, iters=100)
+run("dh (step)", B, D, NZ, b_mn=True, iters=100)
+run("h_lin", B, D, C, bias=True, bf16=True, iters=100)
