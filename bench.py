@@ -253,6 +253,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("ICD_BENCH_KEEP_NCCL_DEBUG") is None:
+            os.environ["NCCL_DEBUG"] = "WARN"       # the NCCL version banner goes to stdout: keep stdout = ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
         __graft_entry__.build()
