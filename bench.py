@@ -49,6 +49,11 @@ def parse():
     ap.add_argument("--impl", default="icd_b200", choices=["icd_b200", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="captions per GPU (default: the benchmark config)")
+    ap.add_argument("--workload", default="train", choices=["train", "beam", "baseline", "glove"],
+                    help="train = BASELINE.json configs[2] (the metric's configuration, default); the others time the "
+                         "remaining configs and print their own JSON line")
+    ap.add_argument("--beam-images", type=int, default=1024, help="images per GPU for the beam-search measurement")
+    ap.add_argument("--no-beam", action="store_true", help="skip the beam-5 side measurement of the default run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -234,8 +239,129 @@ def ncu_traffic():
     return None
 
 
+def beam_measure(dev, n_img, k=5, max_steps=24, reps=2):
+    """BASELINE.json configs[4]: beam search k = 5 over synthetic features, caption cap 25 tokens (loop body runs for step
+    = 1 .. max_steps + 1), weights from the beam fixture recipe so that captions terminate.  Timed region:
+    the whole batched decode (icd_beam_search, fp32 tier) + the device->host read of lengths and token ids."""
+    import torch
+    from icd_b200.gen_captions import beam_search_batched
+    from icd_b200.vocabulary import synthetic_vocab
+    import icd_b200.models.attention as my_att
+    p = my_att.AttentionDecoderParams()
+    p.vocab = synthetic_vocab(V)
+    torch.manual_seed(0)
+    dec = my_att.AttentionDecoder(dev, p)
+    with torch.no_grad():
+        dec.embedding.weight *= 30.0
+        dec.fc.weight[V - 2] *= 30.0
+        dec.fc.bias[V - 2] = -4.0
+    dec = dec.to(dev).eval()
+    g = torch.Generator().manual_seed(77)
+    feats = torch.randn(n_img, 14, 14, C, generator=g).abs_().to(dev)
+    times, res = [], None
+    with torch.no_grad():
+        for i in range(reps + 1):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = beam_search_batched(dec, feats, k, V - 3, V - 2, max_steps=max_steps, want_alphas=False)
+            lens = res["len"].cpu()
+            seqs = res["seq"].cpu()
+            e1.record()
+            torch.cuda.synchronize()
+            if i > 0:
+                times.append(e0.elapsed_time(e1))
+    ms = min(times)
+    done = int((lens > 0).sum())
+    return {"metric": "beam-5 captions/s", "value": n_img / (ms / 1e3), "unit": "captions/s", "images": n_img, "beam": k,
+            "max_caption_tokens": max_steps + 1, "ms": ms, "completed": done, "precision": "fp32",
+            "mean_len": float(lens[lens > 0].float().mean()) if done else 0.0}
+
+
+def side_workload(args):
+    """configs[1] (baseline LSTM decoder B=128, L=25), configs[3] (glove_att: E=300, fp64 fine-tuned table, B=512) and
+    configs[4] (beam search) on one GPU: fwd + loss + bwd + clamp + Adam, CUDA-event timed."""
+    import torch
+    import __graft_entry__
+    __graft_entry__.build()
+    from icd_b200 import synthetic
+    from icd_b200.losses import attention_caption_loss, baseline_caption_loss
+    from icd_b200.parallel import DataParallelClipAdam
+    from icd_b200.vocabulary import synthetic_vocab
+    import icd_b200.models.attention as my_att
+    import icd_b200.models.baseline as my_base
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if args.workload == "beam":
+        line = beam_measure(dev, args.beam_images)
+        line.update({"n_gpus": 1, "data": "synthetic", "config": {"workload": "configs[4]: beam search k=5, %d images" % args.beam_images}})
+        print(json.dumps(line), flush=True)
+        return
+    if args.workload == "baseline":
+        Bb, L = 128, MAXLEN
+        p = my_base.BaselineDecoderParams()
+        p.vocab_size = V
+        torch.manual_seed(0)
+        dec = my_base.BaselineDecoder(p).to(dev)
+        dec.precision = "bf16" if args.precision in ("auto", "bf16") else "fp32"
+        opt = DataParallelClipAdam(dec, lr=1e-4, grad_clip=5.0)
+        img = torch.randn(Bb, E, device=dev, requires_grad=True)
+        caps, _ = synthetic.captions(Bb, V, max_len=L)
+        caps = caps.to(dev)
+
+        def step():
+            out = dec(img, caps)
+            loss = baseline_caption_loss(out, caps)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return loss
+        name, batch = "configs[1]: baseline LSTM decoder, batch 128, L=25, V=9490, E=H=512", Bb
+    else:
+        Bb = args.batch
+        p = my_att.AttentionDecoderParams()
+        p.vocab = synthetic_vocab(V)
+        p.embed_size = 300
+        torch.manual_seed(0)
+        dec = my_att.AttentionDecoder(dev, p)
+        dec.load_pretrained_embeddins(synthetic.glove_like_table(V, 300))
+        dec.fine_tune_embeddings(True)
+        dec = dec.to(dev)
+        dec.precision = "bf16" if args.precision in ("auto", "bf16") else "fp32"
+        dec.train()
+        opt = DataParallelClipAdam(dec, lr=1e-4, grad_clip=5.0)
+        enc = synthetic.features(Bb).to(dev)
+        caps, lens = synthetic.captions(Bb, V, max_len=MAXLEN)
+        caps = caps.to(dev)
+
+        def step():
+            preds, cs, dl, alphas = dec(enc, caps, lens)
+            loss = attention_caption_loss(preds, cs, dl, alphas)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            return loss
+        name, batch = "configs[3]: glove_att, embed 300, fp64 fine-tuned embedding table, batch %d, T=24, V=9490" % Bb, Bb
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    print(json.dumps({"metric": "train-step captions/s", "value": batch / (ms / 1e3), "unit": "captions/s", "n_gpus": 1,
+                      "steps": args.steps, "ms_per_step": ms, "loss": float(loss.item()), "data": "synthetic",
+                      "dtype": dec.precision, "config": {"workload": name}}), flush=True)
+
+
 def main():
     args = parse()
+    if args.workload != "train" and args.impl != "reference":
+        side_workload(args)
+        return
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -357,19 +483,33 @@ def main():
                     bufs[i % 2][1].copy_(caps_h, non_blocking=True)
                     ready[i % 2].record(copy_stream)
 
+            loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()       # pinned landing buffer for the step losses
+            loss_ready = [torch.cuda.Event() for _ in range(2)]
+
             def loop(n):
+                """Every step: H2D of its inputs (prefetched one step ahead on the side stream) and a D2H read of its
+                loss.  The loss is copied to pinned memory asynchronously and READ one step later, after the next step
+                has been issued — the launch queue never drains (the reference's loss.item() right after backward
+                stalls the pipeline every step)."""
                 for d_ in done:
                     d_.record()
                 prefetch(0)
-                out = 0.0
+                out = []
                 for i in range(n):
                     if i + 1 < n:
                         prefetch(i + 1)
                     torch.cuda.current_stream().wait_event(ready[i % 2])
                     l = train_step(*bufs[i % 2])
                     done[i % 2].record()
-                    out = l.item()                               # D2H read of the step's loss (sync, as the reference does)
-                return out
+                    if i >= 1:                                   # read the PREVIOUS step's loss (its slot is reused at i+1)
+                        loss_ready[(i - 1) % 2].synchronize()
+                        out.append(float(loss_host[(i - 1) % 2]))
+                    loss_host[i % 2:i % 2 + 1].copy_(l.detach().reshape(1), non_blocking=True)
+                    loss_ready[i % 2].record()
+                loss_ready[(n - 1) % 2].synchronize()
+                out.append(float(loss_host[(n - 1) % 2]))
+                assert len(out) == n
+                return out[-1]
             loop(2)
             barrier()
             ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -394,7 +534,8 @@ def main():
                "ms_per_step": ms_main / args.steps,
                "host_feature_dtype": "bf16" if host16 else "fp32",
                "note": "per GPU: pinned host features + int64 captions copied H2D every step on a side stream "
-                       "(double-buffered), loss.item() every step"}
+                       "(double-buffered); every step's loss copied D2H to pinned memory and read on the host one step "
+                       "later (pipelined read-back)"}
         if host16:
             ms_f32 = e2e_run(enc_h, args.steps)
             e2e["fp32_host_features"] = {"value": B * world * args.steps / (ms_f32 / 1e3), "ms_per_step": ms_f32 / args.steps,
@@ -440,6 +581,12 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
+        if not args.no_beam:
+            try:
+                line["beam5"] = beam_measure(dev, args.beam_images)
+                line["beam5"]["note"] = "configs[4] on this GPU alone (images shard over GPUs with no collective)"
+            except Exception as ex:          # never lose the headline line over the side measurement
+                line["beam5"] = {"error": repr(ex)[:200]}
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_steps(steps=2, warmup=1)
             line["cpu_baseline"] = {"value": r["value"], "unit": "captions/s", "cores": r["cores"], "kind": "port",

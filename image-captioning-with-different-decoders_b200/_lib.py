@@ -98,6 +98,7 @@ def lib():
     L.icd_gemm_ws_bytes.restype = ctypes.c_int64
     L.icd_gemm_bf16_splitk_ws_floats.restype = ctypes.c_int64
     L.icd_attention_decoder_ws_bytes.restype = ctypes.c_int64
+    L.icd_baseline_decoder_ws_bytes.restype = ctypes.c_int64
     if L.icd_version() != DEFINES["ICD_B200_ABI_VERSION"]:
         raise IcdError("libicd_b200.so ABI %d != header ABI %d — rebuild" %
                        (L.icd_version(), DEFINES["ICD_B200_ABI_VERSION"]))

@@ -75,6 +75,10 @@ class _BaselineDecoderFn(torch.autograd.Function):
         fill(d, B=B, L=L, E=E, H=H, V=V, precision=ops.precision_id(precision), emb_is_f64=int(emb_is_f64),
              img_features=img, captions=captions, emb_w=emb_w.contiguous(), w_ih=ws[0], w_hh=ws[1], b_ih=ws[2],
              b_hh=ws[3], lin_w=ws[4], lin_b=ws[5], **bufs)
+        need = int(lib().icd_baseline_decoder_ws_bytes(ctypes.byref(d)))
+        tc_ws = torch.empty(need, device=dev, dtype=torch.uint8) if need else None
+        fill(d, tc_ws=tc_ws, tc_ws_bytes=need)
+        bufs["tc_ws"] = tc_ws
         check(lib().icd_baseline_decoder_fwd(ctypes.byref(d), stream_ptr()), "icd_baseline_decoder_fwd")
         outputs = bufs.pop("outputs")          # not kept in ctx: it carries this node as grad_fn (reference cycle)
         ctx.desc = d

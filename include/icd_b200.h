@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ICD_B200_ABI_VERSION 8
+#define ICD_B200_ABI_VERSION 9
 #define ICD_MAX_STEPS 256
 
 ICD_API int icd_version(void);                       /* ICD_B200_ABI_VERSION the library was built with */
@@ -300,8 +300,11 @@ typedef struct {
     float* dh;                    /* (B,H) */
     float* dc;                    /* (B,H) */
     float* d_x;                   /* (L,B,E) */
+    /* ICD_PREC_BF16 only: arena for the bf16 operand copies, shared by fwd and bwd of the same step */
+    void* tc_ws; int64_t tc_ws_bytes;   /* >= icd_baseline_decoder_ws_bytes(desc) */
 } icd_base_desc_t;
 
+ICD_API int64_t icd_baseline_decoder_ws_bytes(const icd_base_desc_t* d);
 ICD_API int icd_baseline_decoder_fwd(const icd_base_desc_t* d, void* stream);
 ICD_API int icd_baseline_decoder_bwd(const icd_base_desc_t* d, void* stream);
 

@@ -404,3 +404,26 @@ def test_bf16_tier_accepts_bf16_stored_features_in_place(cuda):
     H.assert_close_norm(outs[1][1], outs[0][1], 1e-5, "alphas (bf16-stored features)")
     for k in outs[0][2]:
         H.assert_close_norm(outs[1][2][k], outs[0][2][k], 1e-4, "grad " + k, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", list(H.BASE_CASES))
+def test_baseline_decoder_bf16_tier_matches_reference_golden(cuda, name):
+    """bf16 tensor-core tier of the baseline decoder (BASELINE.json configs[1] on B200): stated tolerances — logits 5e-3,
+    loss 1e-3, gradients 2e-2 norm-wise; greedy ids equal wherever the reference's top-2 margin exceeds 2e-2."""
+    import icd_b200.models.baseline as my_base
+    case = H.BASE_CASES[name]
+    g = load(name)
+    dec = H.build_baseline_module(case, my_base.BaselineDecoder, my_base.BaselineDecoderParams).to(cuda)
+    dec.precision = "bf16"
+    img, caps, lens = H.base_inputs(case)
+    img_dev = img.to(cuda).requires_grad_(True)
+    outs = dec(img_dev, caps.to(cuda))
+    compare(case, g, "outputs", outs, 5e-3)
+    loss = O.baseline_loss(outs, caps.to(cuda))
+    assert abs(loss.item() - float(g["loss"])) <= 1e-3 * abs(float(g["loss"]))
+    loss.backward()
+    for k in [str(x) for x in g["grad_names"]]:
+        gr = img_dev.grad if k == "img_features" else dict(dec.named_parameters())[k].grad
+        compare(case, g, "grad:" + k, gr, 2e-2)
+    ids = outs.argmax(dim=2).cpu().numpy()
+    assert np.all((ids == g["greedy_ids"]) | (g["greedy_margin"] <= 2e-2))
