@@ -72,6 +72,7 @@ BeamDesc = _make_struct("icd_beam_desc_t")
 
 PREC_FP32 = DEFINES["ICD_PREC_FP32"]
 PREC_BF16 = DEFINES["ICD_PREC_BF16"]
+PREC_FP32X3 = DEFINES["ICD_PREC_FP32X3"]
 MAX_STEPS = DEFINES["ICD_MAX_STEPS"]
 
 _lib = None

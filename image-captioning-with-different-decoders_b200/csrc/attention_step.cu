@@ -146,6 +146,125 @@ __global__ void __launch_bounds__(256, 4) att_step_fwd_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------
+// Grouped forward for caption generation: the K beam rows of ONE image share its feature map, so one CTA serves all
+// live beams of an image and reads att_enc / enc ONCE per step instead of once per beam (gen_captions.py:44 expands the
+// features to k copies and :111 re-gathers them every step).  grid = n_img, block = 256; rows img*k + j, j < k_live[img];
+// images with no live beam exit immediately.  Per row the arithmetic (lane partition of the score dot, sequential pixel
+// order of the weighted sum) is that of att_step_fwd_kernel, so results are bit-identical to the per-row kernel.
+// smem: K*A (att_dec) + A (w_full) + K*Ppad (scores / alpha) floats.
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256, 2) att_step_fwd_grouped_kernel(
+        int k, int P, int C, int A, const int* __restrict__ k_live,
+        const float* __restrict__ enc, const float* __restrict__ att_enc,
+        const float* __restrict__ att_dec, long long ld_dec,
+        const float* __restrict__ w_full, const float* __restrict__ b_full,
+        const float* __restrict__ fbeta_pre, long long ld_fb,
+        float* __restrict__ alpha, long long ld_alpha, float* __restrict__ gated) {
+    extern __shared__ __align__(16) float sm[];
+    const int img = blockIdx.x;
+    const int kl = k_live ? min(k_live[img], K) : min(k, K);
+    if (kl <= 0) return;
+    const int Pp = (P + 3) & ~3;
+    float* s_dec = sm;                 // K * A
+    float* s_wf = sm + K * A;          // A
+    float* s_e = s_wf + A;             // K * Pp
+    const long long r0 = (long long)img * k;
+    for (int i = threadIdx.x; i < kl * A; i += blockDim.x) s_dec[i] = att_dec[(r0 + i / A) * ld_dec + (i % A)];
+    for (int a = threadIdx.x; a < A; a += blockDim.x) s_wf[a] = w_full[a];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const float bfull = b_full ? b_full[0] : 0.f;
+    const int A4 = A >> 2;
+    const float* ae = att_enc + (long long)img * P * A;
+    for (int p = warp; p < P; p += nwarp) {
+        float acc[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[j] = 0.f;
+        const float* row = ae + (long long)p * A;
+        for (int q = lane; q < A4; q += 32) {
+            const float4 x = ld_stream_f4(row + 4 * q);
+            const float4 w = *reinterpret_cast<const float4*>(s_wf + 4 * q);
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                if (j < kl) {
+                    const float4 d = *reinterpret_cast<const float4*>(s_dec + j * A + 4 * q);
+                    acc[j] = fmaf(fmaxf(x.x + d.x, 0.f), w.x, acc[j]);
+                    acc[j] = fmaf(fmaxf(x.y + d.y, 0.f), w.y, acc[j]);
+                    acc[j] = fmaf(fmaxf(x.z + d.z, 0.f), w.z, acc[j]);
+                    acc[j] = fmaf(fmaxf(x.w + d.w, 0.f), w.w, acc[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (j < kl) {
+                const float v = warp_sum(acc[j]);
+                if (lane == 0) s_e[j * Pp + p] = v + bfull;
+            }
+        }
+    }
+    __syncthreads();
+    // softmax over pixels: warp j handles row j (kl <= K <= 8 = number of warps)
+    for (int j = warp; j < kl; j += nwarp) {
+        float* e = s_e + j * Pp;
+        float m = -INFINITY;
+        for (int p = lane; p < P; p += 32) m = fmaxf(m, e[p]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int p = lane; p < P; p += 32) { const float ex = expf(e[p] - m); e[p] = ex; sum += ex; }
+        sum = warp_sum(sum);
+        float* out = alpha + (r0 + j) * ld_alpha;
+        for (int p = lane; p < P; p += 32) { const float al = e[p] / sum; e[p] = al; out[p] = al; }
+    }
+    __syncthreads();
+    // weighted sums for all live rows: each enc row is loaded once and feeds kl accumulators
+    const float* eb = enc + (long long)img * P * C;
+    for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+        float4 acc[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int p = 0;
+        for (; p + 4 <= P; p += 4) {
+            float4 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) x[u] = ld_stream_f4(eb + (long long)(p + u) * C + c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    if (j < kl) {
+                        const float al = s_e[j * Pp + p + u];
+                        acc[j].x = fmaf(al, x[u].x, acc[j].x); acc[j].y = fmaf(al, x[u].y, acc[j].y);
+                        acc[j].z = fmaf(al, x[u].z, acc[j].z); acc[j].w = fmaf(al, x[u].w, acc[j].w);
+                    }
+                }
+            }
+        }
+        for (; p < P; ++p) {
+            const float4 x = ld_stream_f4(eb + (long long)p * C + c);
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                if (j < kl) {
+                    const float al = s_e[j * Pp + p];
+                    acc[j].x = fmaf(al, x.x, acc[j].x); acc[j].y = fmaf(al, x.y, acc[j].y);
+                    acc[j].z = fmaf(al, x.z, acc[j].z); acc[j].w = fmaf(al, x.w, acc[j].w);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (j < kl) {
+                const float4 f = *reinterpret_cast<const float4*>(fbeta_pre + (r0 + j) * ld_fb + c);
+                const float4 g = make_float4(sigmoidf_(f.x), sigmoidf_(f.y), sigmoidf_(f.z), sigmoidf_(f.w));
+                *reinterpret_cast<float4*>(gated + (r0 + j) * C + c) =
+                    make_float4(g.x * acc[j].x, g.y * acc[j].y, g.z * acc[j].z, g.w * acc[j].w);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // weighted pixel sum + gate.  grid = (ceil(C/256), rows), block = 256 = 4 pixel groups x 64 float4 lanes.
 // alpha == NULL  => plain mean over pixels (init_hidden_state, models/attention.py:161).
 // ------------------------------------------------------------------------------------------------
@@ -566,4 +685,44 @@ extern "C" int icd_attention_proj_bwd(int B, int T, int P, int A, const int32_t*
     if (d_b_enc) ICD_TRY(icd_colsum(partial + A, W, (int64_t)B * chunks, A, nullptr, d_b_enc, s));
     ICD_TRY(icd_colsum(partial + 2 * A, W, (int64_t)B * chunks, 1, nullptr, d_b_full, s));
     return 0;
+}
+
+// Caption-generation variant (internal): rows img*k + j, j < k_live[img], of image img are served by one CTA.
+template <int K>
+static int launch_grouped(int n_img, int k, int P, int C, int A, const int* k_live, const float* enc, const float* att_enc,
+                          const float* att_dec, int64_t ld_dec, const float* w_full, const float* b_full,
+                          const float* fbeta_pre, int64_t ld_fb, float* alpha, int64_t ld_alpha, float* gated,
+                          cudaStream_t s) {
+    const size_t smem = ((size_t)K * A + A + (size_t)K * ((P + 3) & ~3)) * sizeof(float);
+    ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_fwd_grouped: K*A too large for shared memory");
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        ICD_CUDA(cudaFuncSetAttribute(att_step_fwd_grouped_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    att_step_fwd_grouped_kernel<K><<<n_img, 256, smem, s>>>(k, P, C, A, k_live, enc, att_enc, att_dec, ld_dec, w_full, b_full,
+                                                            fbeta_pre, ld_fb, alpha, ld_alpha, gated);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+int icd_attention_step_fwd_grouped(int n_img, int k, int P, int C, int A, const int* k_live, const float* enc,
+                                   const float* att_enc, const float* att_dec, int64_t ld_dec, const float* w_full,
+                                   const float* b_full, const float* fbeta_pre, int64_t ld_fb, float* alpha,
+                                   int64_t ld_alpha, float* gated, cudaStream_t s) {
+    if (n_img == 0) return 0;
+    ICD_CHECK_ARG(k >= 1 && k <= 8, "attention_step_fwd_grouped: k=%d (1..8)", k);
+    ICD_CHECK_ARG(A % 4 == 0 && C % 4 == 0 && ld_dec % 4 == 0 && ld_fb % 4 == 0, "attention_step_fwd_grouped: misaligned dims");
+#define ICD_GROUPED(KK) return launch_grouped<KK>(n_img, k, P, C, A, k_live, enc, att_enc, att_dec, ld_dec, w_full, b_full, \
+                                                  fbeta_pre, ld_fb, alpha, ld_alpha, gated, s)
+    switch (k) {
+        case 1: ICD_GROUPED(1);
+        case 2: ICD_GROUPED(2);
+        case 3: ICD_GROUPED(3);
+        case 4: ICD_GROUPED(4);
+        case 5: ICD_GROUPED(5);
+        case 6: ICD_GROUPED(6);
+        default: ICD_GROUPED(8);
+    }
+#undef ICD_GROUPED
 }

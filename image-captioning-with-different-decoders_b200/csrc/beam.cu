@@ -12,6 +12,7 @@
 // summed log-probs (:74-76); beams that emit <end> leave the beam and are never replaced (:93-104); the winner is
 // the first completed beam with the maximal score (:127); the loop body runs for step = 1..max_steps+1 (:119).
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace {
 
@@ -22,7 +23,13 @@ struct BeamWs {
           *gates_act_unused, *logits, *alpha_steps, *score, *best_score;
     int *img_index, *prev_word, *k_live, *src, *parent, *word, *best_step, *best_parent;
     long long* tok64;
+    // ICD_PREC_FP32X3: 3-term bf16 splits (gemm_tc.cu) of the weights (once per call) and of the step activations
+    void *x3_We, *x3_Wcat, *x3_WihE, *x3_WihC, *x3_Wh, *x3_Wc, *x3_Wfc, *x3_act;
+    float* x3_splitk; long long x3_splitk_floats;
 };
+
+inline long long up8ll(long long x) { return (x + 7) / 8 * 8; }
+constexpr int X3_IMG_CHUNK = 64;          // images per enc_att projection pass (bounds the split activation scratch)
 
 size_t carve(const icd_beam_desc_t* d, BeamWs* w, char* base) {
     const size_t R = (size_t)d->n_img * d->k, S = (size_t)d->max_steps + 1;
@@ -48,6 +55,23 @@ size_t carve(const icd_beam_desc_t* d, BeamWs* w, char* base) {
     TAKE_I(parent, S * R) TAKE_I(word, S * R) TAKE_I(best_step, (size_t)d->n_img) TAKE_I(best_parent, (size_t)d->n_img)
 #undef TAKE_I
     long long* lp = (long long*)take(sizeof(long long) * R); if (w) w->tok64 = lp;
+    if (d->precision == ICD_PREC_FP32X3) {
+        auto takev = [&](size_t bytes) { return (void*)take(bytes); };
+        void* v;
+#define TAKE_X3(name, rows, K) v = takev((size_t)(rows) * 6 * up8ll(K) * 2); if (w) w->name = v;
+        TAKE_X3(x3_We, A, C) TAKE_X3(x3_Wcat, NZ, D) TAKE_X3(x3_WihE, 4 * D, E) TAKE_X3(x3_WihC, 4 * D, C)
+        TAKE_X3(x3_Wh, D, C) TAKE_X3(x3_Wc, D, C) TAKE_X3(x3_Wfc, V, D)
+#undef TAKE_X3
+        const size_t act_rows = R > (size_t)X3_IMG_CHUNK * P ? R : (size_t)X3_IMG_CHUNK * P;
+        v = takev(act_rows * 6 * up8ll(C) * 2); if (w) w->x3_act = v;
+        long long f = 0;
+        const long long shapes[][3] = {{(long long)X3_IMG_CHUNK * P, A, 6 * up8ll(C)}, {(long long)d->n_img, D, 6 * up8ll(C)},
+                                       {(long long)R, NZ, 6 * up8ll(D)}, {(long long)R, 4 * D, 6 * up8ll(E)},
+                                       {(long long)R, 4 * D, 6 * up8ll(C)}, {(long long)R, V, 6 * up8ll(D)}};
+        for (const auto& sh : shapes) { const long long n = icd_gemm_bf16_splitk_floats((int)sh[0], (int)sh[1], (int)sh[2]); if (n > f) f = n; }
+        float* fp = (float*)take(sizeof(float) * (size_t)f);
+        if (w) { w->x3_splitk = fp; w->x3_splitk_floats = f; }
+    }
     return off;
 }
 
@@ -224,6 +248,20 @@ __global__ void gather_rows_kernel(const float* __restrict__ table_f32, const do
 
 }  // namespace
 
+// y[rows, N] = x[rows, K] * W[N, K]^T (+ bias + add + beta*y): fp32 FMA kernel, or the fp32-grade tensor-core tier with the
+// activation split on the fly and the weight split `w16x3` prepared once per call.
+int beam_mm(int prec, const BeamWs& w, const float* x, long long ldx, int rows, int K, const float* W, long long ldw,
+            const void* w16x3, float* y, long long ldy, int N, const float* bias, const float* add, long long ldadd,
+            float beta, cudaStream_t s) {
+    if (prec != ICD_PREC_FP32X3)
+        return icd_gemm_simple(ICD_PREC_FP32, x, ldx, 1, W, ldw, 1, y, ldy, rows, N, K, bias, nullptr, add, ldadd, nullptr, 0,
+                               nullptr, beta, s);
+    const long long seg = up8ll(K);
+    ICD_TRY(icd_split3_bf16(x, ldx, rows, K, w.x3_act, 0, s));
+    return icd_gemm_bf16_ex(w.x3_act, 6 * seg, 0, w16x3, 6 * seg, 0, y, ldy, rows, N, (int)(6 * seg), bias, nullptr, add, ldadd,
+                            nullptr, 0, nullptr, beta, s, nullptr, 0, w.x3_splitk, w.x3_splitk_floats);
+}
+
 extern "C" int64_t icd_beam_search_ws_bytes(const icd_beam_desc_t* d) {
     if (!d) return -1;
     return (int64_t)carve(d, nullptr, nullptr);
@@ -253,10 +291,25 @@ extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
     ICD_CUDA(cudaMemcpyAsync(w.b_cat + A + C, d->b_hh, sizeof(float) * 4 * D, cudaMemcpyDeviceToDevice, s));
 
     // once per image: enc_att projection and the initial state (:62)
-    ICD_TRY(icd_gemm_simple(prec, d->enc, C, 1, d->enc_att_w, C, 1, w.att_enc, A, n_img * P, A, C, d->enc_att_b, nullptr,
-                            nullptr, 0, nullptr, 0, nullptr, 0.f, s));
-    ICD_TRY(icd_init_hidden_state(n_img, P, C, D, prec, d->enc, d->h_lin_w, d->h_lin_b, d->c_lin_w, d->c_lin_b,
-                                  w.mean, w.h0, w.c0, stream));
+    ICD_CHECK_ARG(prec == ICD_PREC_FP32 || prec == ICD_PREC_FP32X3, "beam_search: precision must be ICD_PREC_FP32 or ICD_PREC_FP32X3");
+    if (prec == ICD_PREC_FP32X3) {            // weights are constant over the whole search: split them once
+        ICD_TRY(icd_split3_bf16(d->enc_att_w, C, A, C, w.x3_We, 1, s));
+        ICD_TRY(icd_split3_bf16(w.w_cat, D, NZ, D, w.x3_Wcat, 1, s));
+        ICD_TRY(icd_split3_bf16(d->w_ih, E + C, 4 * D, E, w.x3_WihE, 1, s));
+        ICD_TRY(icd_split3_bf16(d->w_ih + E, E + C, 4 * D, C, w.x3_WihC, 1, s));
+        ICD_TRY(icd_split3_bf16(d->h_lin_w, C, D, C, w.x3_Wh, 1, s));
+        ICD_TRY(icd_split3_bf16(d->c_lin_w, C, D, C, w.x3_Wc, 1, s));
+        ICD_TRY(icd_split3_bf16(d->fc_w, D, V, D, w.x3_Wfc, 1, s));
+    }
+    for (int i0 = 0; i0 < n_img; i0 += X3_IMG_CHUNK) {       // att_enc = enc_att(enc), once per image
+        const int ni = n_img - i0 < X3_IMG_CHUNK ? n_img - i0 : X3_IMG_CHUNK;
+        ICD_TRY(beam_mm(prec, w, d->enc + (size_t)i0 * P * C, C, ni * P, C, d->enc_att_w, C, w.x3_We,
+                        w.att_enc + (size_t)i0 * P * A, A, A, d->enc_att_b, nullptr, 0, 0.f, s));
+    }
+    // initial state (:62): pixel mean, h_lin, c_lin
+    ICD_TRY(icd_weighted_pixel_sum(n_img, P, C, nullptr, d->enc, nullptr, 0, nullptr, 0, w.mean, nullptr, nullptr, s));
+    ICD_TRY(beam_mm(prec, w, w.mean, C, n_img, C, d->h_lin_w, C, w.x3_Wh, w.h0, D, D, d->h_lin_b, nullptr, 0, 0.f, s));
+    ICD_TRY(beam_mm(prec, w, w.mean, C, n_img, C, d->c_lin_w, C, w.x3_Wc, w.c0, D, D, d->c_lin_b, nullptr, 0, 0.f, s));
     {
         const long long n = R * D;
         beam_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n_img, k, D, d->start_id, w.h0, w.c0, w.h, w.c,
@@ -270,17 +323,16 @@ extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
                                                        d->emb_is_f64 ? (const double*)d->emb_w : nullptr,
                                                        w.tok64, E, w.emb_x);                 // :65
         ICD_LAUNCH_CHECK();
-        ICD_TRY(icd_gemm_simple(prec, w.h, D, 1, w.w_cat, D, 1, w.z, NZ, (int)R, NZ, D, w.b_cat, nullptr,
-                                nullptr, 0, nullptr, 0, nullptr, 0.f, s));
-        ICD_TRY(icd_attention_step_fwd((int)R, P, C, A, w.img_index, d->enc, w.att_enc, w.z, NZ, d->full_att_w,
-                                       d->full_att_b, w.z + A, NZ, alpha_s, P, nullptr, nullptr, w.gated, stream));  // :66-69
-        ICD_TRY(icd_gemm_simple(prec, w.emb_x, E, 1, d->w_ih, E + C, 1, w.gates_pre, 4 * D, (int)R, 4 * D, E,
-                                d->b_ih, nullptr, w.z + A + C, NZ, nullptr, 0, nullptr, 0.f, s));
-        ICD_TRY(icd_gemm_simple(prec, w.gated, C, 1, d->w_ih + E, E + C, 1, w.gates_pre, 4 * D, (int)R, 4 * D, C,
-                                nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 1.f, s)); // :70-71
+        ICD_TRY(beam_mm(prec, w, w.h, D, (int)R, D, w.w_cat, D, w.x3_Wcat, w.z, NZ, NZ, w.b_cat, nullptr, 0, 0.f, s));
+        // :66-69 — one CTA per image serves all of its live beams (features read once per image, finished images skipped)
+        ICD_TRY(icd_attention_step_fwd_grouped(n_img, k, P, C, A, w.k_live, d->enc, w.att_enc, w.z, NZ, d->full_att_w,
+                                               d->full_att_b, w.z + A, NZ, alpha_s, P, w.gated, s));
+        ICD_TRY(beam_mm(prec, w, w.emb_x, E, (int)R, E, d->w_ih, E + C, w.x3_WihE, w.gates_pre, 4 * D, 4 * D,
+                        d->b_ih, w.z + A + C, NZ, 0.f, s));
+        ICD_TRY(beam_mm(prec, w, w.gated, C, (int)R, C, d->w_ih + E, E + C, w.x3_WihC, w.gates_pre, 4 * D, 4 * D,
+                        nullptr, nullptr, 0, 1.f, s));                                       // :70-71
         ICD_TRY(icd_lstm_pointwise_fwd((int)R, D, w.gates_pre, w.c, nullptr, w.c_tmp, w.h_tmp, nullptr, 0, nullptr, 1.f, s));
-        ICD_TRY(icd_gemm_simple(prec, w.h_tmp, D, 1, d->fc_w, D, 1, w.logits, V, (int)R, V, D, d->fc_b, nullptr,
-                                nullptr, 0, nullptr, 0, nullptr, 0.f, s));                   // :72 (no dropout)
+        ICD_TRY(beam_mm(prec, w, w.h_tmp, D, (int)R, D, d->fc_w, D, w.x3_Wfc, w.logits, V, V, d->fc_b, nullptr, 0, 0.f, s));   // :72
         beam_topk_kernel<<<n_img, 256, 0, s>>>(k, V, step, d->end_id, w.logits, w.score, w.prev_word, w.tok64, w.k_live,
                                                w.src, w.parent + (size_t)(step - 1) * R, w.word + (size_t)(step - 1) * R,
                                                d->trace_words ? d->trace_words + (size_t)(step - 1) * R : nullptr,

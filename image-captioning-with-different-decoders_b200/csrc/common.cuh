@@ -97,6 +97,10 @@ int icd_lstm_pointwise_bwd(int rows, int D, const float* dh_in, const float* d_h
 int icd_weighted_pixel_sum(int rows, int P, int C, const int32_t* img_index, const float* enc,
                            const float* alpha, int64_t ld_alpha, const float* fbeta_pre, int64_t ld_fb,
                            float* awe_raw, float* gate, float* gated, cudaStream_t s);
+int icd_attention_step_fwd_grouped(int n_img, int k, int P, int C, int A, const int* k_live, const float* enc,
+                                   const float* att_enc, const float* att_dec, int64_t ld_dec, const float* w_full,
+                                   const float* b_full, const float* fbeta_pre, int64_t ld_fb, float* alpha,
+                                   int64_t ld_alpha, float* gated, cudaStream_t s);
 int icd_gemm_simple(int prec, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
                     float* C, int64_t ldc, int M, int N, int K, const float* bias1, const float* bias2,
                     const float* add1, int64_t ld1, const float* add2, int64_t ld2, const uint8_t* row_mask,

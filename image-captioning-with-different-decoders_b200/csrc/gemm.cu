@@ -4,8 +4,10 @@
 
 int icd_gemm_f32_launch(const icd_gemm_desc_t* d, cudaStream_t s);   // gemm_f32.cu
 int icd_gemm_tc_launch(const icd_gemm_desc_t* d, cudaStream_t s);    // gemm_tc.cu (tcgen05 / TMA, bf16)
+int icd_gemm_x3_launch(const icd_gemm_desc_t* d, cudaStream_t s);    // gemm_tc.cu (3-term bf16 split, fp32-grade)
 
 extern "C" int64_t icd_gemm_ws_bytes(int32_t M, int32_t N, int32_t K, int32_t precision) {
+    if (precision == ICD_PREC_FP32X3) return icd_gemm_x3_ws_bytes(M, N, K);
     return precision == ICD_PREC_BF16 ? icd_gemm_tc_ws_bytes(M, N, K) : 0;
 }
 
@@ -14,6 +16,7 @@ extern "C" int icd_gemm(const icd_gemm_desc_t* d, void* stream) {
     cudaStream_t s = icd_stream(stream);
     if (d->precision == ICD_PREC_FP32) return icd_gemm_f32_launch(d, s);
     if (d->precision == ICD_PREC_BF16) return icd_gemm_tc_launch(d, s);
+    if (d->precision == ICD_PREC_FP32X3) return icd_gemm_x3_launch(d, s);
     icd_set_error("gemm: unknown precision %d", d->precision);
     return -1;
 }

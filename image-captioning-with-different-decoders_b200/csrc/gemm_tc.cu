@@ -481,6 +481,46 @@ __global__ void convert_transpose_kernel(const float* __restrict__ src, long lon
     }
 }
 
+// ---------------------------------------------------------------------------------------------- fp32 -> 3 x bf16 split
+// x = b1 + b2 + b3 with b1 = bf16(x), b2 = bf16(x - b1), b3 = bf16(x - b1 - b2)  (24 mantissa bits kept).
+// The six significant cross terms of a product are laid out along K so that ONE bf16 contraction over K' = 6 * seg sums
+//   A': [a1 | a1 | a2 | a1 | a3 | a2]      B': [b1 | b2 | b1 | b3 | b1 | b2]
+// which: 0 = A pattern, 1 = B pattern.
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& b1, __nv_bfloat16& b2, __nv_bfloat16& b3) {
+    b1 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(b1);
+    b2 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(b2);
+    b3 = __float2bfloat16_rn(r2);
+}
+// K-major source rows: dst[r*ldd + s*seg + c] = term_s(src[r*s_r + c]), c < cols; pad columns [cols, seg) zeroed.
+__global__ void split3_rows_kernel(const float* __restrict__ src, long long s_r, int rows, int cols, int seg,
+                                   __nv_bfloat16* __restrict__ dst, long long ldd, int which) {
+    const long long total = (long long)rows * seg;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / seg; const int c = (int)(i % seg);
+        __nv_bfloat16 t[3];
+        if (c < cols) split3(src[r * s_r + c], t[0], t[1], t[2]);
+        else t[0] = t[1] = t[2] = __float2bfloat16_rn(0.f);
+        __nv_bfloat16* d = dst + r * ldd + c;
+        if (which == 0) { d[0] = t[0]; d[seg] = t[0]; d[2 * seg] = t[1]; d[3 * seg] = t[0]; d[4 * seg] = t[2]; d[5 * seg] = t[1]; }
+        else            { d[0] = t[0]; d[seg] = t[1]; d[2 * seg] = t[0]; d[3 * seg] = t[2]; d[4 * seg] = t[0]; d[5 * seg] = t[1]; }
+    }
+}
+// MN-major source ([K][MN] rows): dst[(s*K + k)*ldd + m] = term_s(src[k*s_k + m])
+__global__ void split3_mn_kernel(const float* __restrict__ src, long long s_k, int K, int mn,
+                                 __nv_bfloat16* __restrict__ dst, long long ldd, int which) {
+    const long long total = (long long)K * mn;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long k = i / mn; const int m = (int)(i % mn);
+        __nv_bfloat16 t[3];
+        split3(src[k * s_k + m], t[0], t[1], t[2]);
+        const int pa[6] = {0, 0, 1, 0, 2, 1}, pb[6] = {0, 1, 0, 2, 0, 1};
+#pragma unroll
+        for (int sgm = 0; sgm < 6; ++sgm) dst[((long long)sgm * K + k) * ldd + m] = t[which == 0 ? pa[sgm] : pb[sgm]];
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -680,4 +720,70 @@ int icd_gemm_tc_launch(const icd_gemm_desc_t* d, cudaStream_t s) {
     return icd_gemm_bf16_ex(a16, lda, a_mn, b16, ldb, b_mn, d->C, d->ldc, M, N, K, d->bias1, d->bias2, d->add1, d->ld1,
                             d->add2, d->ld2, d->row_mask, d->beta, s, nullptr, 0, sk,
                             icd_gemm_bf16_splitk_floats(M, N, K));
+}
+
+// ---------------------------------------------------------------------------------------------- fp32-grade (3-term) tier
+// K-major operand [rows][K] -> bf16 [rows][6*seg], seg = up8(K); returns the leading dimension.
+int icd_split3_bf16(const float* src, int64_t s_r, int rows, int cols, void* dst, int which, cudaStream_t s) {
+    if (rows == 0 || cols == 0) return 0;
+    const int seg = (int)up8(cols);
+    const long long total = (long long)rows * seg;
+    long long blocks = (total + 255) / 256;
+    if (blocks > ICD_NUM_SMS * 16) blocks = ICD_NUM_SMS * 16;
+    split3_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, s_r, rows, cols, seg, reinterpret_cast<__nv_bfloat16*>(dst),
+                                                        6LL * seg, which);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t icd_gemm_x3_ws_bytes(int M, int N, int K) {
+    const int64_t a = up256(std::max((int64_t)M * 6 * up8(K), (int64_t)6 * K * up8(M)) * 2);
+    const int64_t b = up256(std::max((int64_t)N * 6 * up8(K), (int64_t)6 * K * up8(N)) * 2);
+    return a + b + up256(icd_gemm_bf16_splitk_floats(M, N, 6 * (int)up8(K)) * 4);
+}
+
+int icd_gemm_x3_launch(const icd_gemm_desc_t* d, cudaStream_t s) {
+    if (d->M == 0 || d->N == 0) return 0;
+    ICD_CHECK_ARG(d->sak == 1 || d->sam == 1, "gemm: A needs a unit stride");
+    ICD_CHECK_ARG(d->sbk == 1 || d->sbn == 1, "gemm: B needs a unit stride");
+    const int M = d->M, N = d->N, K = d->K;
+    const int64_t need = icd_gemm_x3_ws_bytes(M, N, K);
+    ICD_CHECK_ARG(d->ws && d->ws_bytes >= need, "gemm: ICD_PREC_FP32X3 needs %lld bytes of workspace (icd_gemm_ws_bytes), got %lld",
+                  (long long)need, (long long)d->ws_bytes);
+    const int a_mn = (d->sak != 1), b_mn = (d->sbk != 1);
+    const int64_t a_bytes = up256(std::max((int64_t)M * 6 * up8(K), (int64_t)6 * K * up8(M)) * 2);
+    const int64_t b_bytes = up256(std::max((int64_t)N * 6 * up8(K), (int64_t)6 * K * up8(N)) * 2);
+    char* a16 = reinterpret_cast<char*>(d->ws);
+    char* b16 = a16 + a_bytes;
+    float* sk = reinterpret_cast<float*>(b16 + b_bytes);
+    const int seg = (int)up8(K);
+    int64_t lda, ldb; int Kx;
+    auto split_mn = [&](const float* src, int64_t s_k, int mn, void* dst, int64_t ldd, int which) -> int {
+        const long long total = (long long)K * mn;
+        long long blocks = (total + 255) / 256;
+        if (blocks > ICD_NUM_SMS * 16) blocks = ICD_NUM_SMS * 16;
+        split3_mn_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, s_k, K, mn, reinterpret_cast<__nv_bfloat16*>(dst), ldd, which);
+        ICD_LAUNCH_CHECK();
+        return 0;
+    };
+    // both operands must agree on the K' layout: K-major segments are padded to seg = up8(K), MN-major ones are not, so
+    // when the majors differ the MN-major operand is also laid out with seg-row segments (pad rows zeroed)
+    const bool mixed = (a_mn != b_mn);
+    if (!a_mn && !b_mn) Kx = 6 * seg; else if (a_mn && b_mn) Kx = 6 * K; else Kx = 6 * seg;
+    if (!a_mn) { lda = 6LL * seg; ICD_TRY(icd_split3_bf16(d->A, d->sam, M, K, a16, 0, s)); }
+    else {
+        lda = up8(M);
+        if (mixed) ICD_CUDA(cudaMemsetAsync(a16, 0, (size_t)6 * seg * lda * 2, s));
+        ICD_TRY(split_mn(d->A, d->sak, M, a16, lda, 0));
+    }
+    if (!b_mn) { ldb = 6LL * seg; ICD_TRY(icd_split3_bf16(d->B, d->sbn, N, K, b16, 1, s)); }
+    else {
+        ldb = up8(N);
+        if (mixed) ICD_CUDA(cudaMemsetAsync(b16, 0, (size_t)6 * seg * ldb * 2, s));
+        ICD_TRY(split_mn(d->B, d->sbk, N, b16, ldb, 1));
+    }
+    ICD_CHECK_ARG(!mixed || seg == K, "gemm(FP32X3): mixed operand majors need K %% 8 == 0 (K=%d)", K);
+    return icd_gemm_bf16_ex(a16, lda, a_mn, b16, ldb, b_mn, d->C, d->ldc, M, N, Kx, d->bias1, d->bias2, d->add1, d->ld1,
+                            d->add2, d->ld2, d->row_mask, d->beta, s, nullptr, 0, sk,
+                            icd_gemm_bf16_splitk_floats(M, N, 6 * seg));
 }

@@ -21,3 +21,7 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
                      void* C16, int64_t ldc16, float* splitk_ws, int64_t splitk_ws_floats);
 int64_t icd_gemm_bf16_splitk_floats(int M, int N, int K);
 int64_t icd_gemm_tc_ws_bytes(int M, int N, int K);
+// fp32-grade tier (ICD_PREC_FP32X3): 3-term bf16 split laid out along K (A pattern which = 0, B pattern which = 1):
+// K-major fp32 [rows][cols] (row stride s_r) -> bf16 [rows][6 * up8(cols)]
+int icd_split3_bf16(const float* src, int64_t s_r, int rows, int cols, void* dst, int which, cudaStream_t s);
+int64_t icd_gemm_x3_ws_bytes(int M, int N, int K);

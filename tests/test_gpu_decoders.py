@@ -214,8 +214,9 @@ def test_baseline_decoder_matches_reference_golden(cuda, name):
     assert np.all((ids == g["greedy_ids"]) | (margin <= 1e-4))
 
 
+@pytest.mark.parametrize("precision", ["fp32x3", "fp32"])
 @pytest.mark.parametrize("name", list(H.BEAM_CASES))
-def test_beam_search_matches_reference_golden(cuda, name, capsys):
+def test_beam_search_matches_reference_golden(cuda, name, precision, capsys):
     import icd_b200.models.attention as my_att
     from icd_b200.gen_captions import attention_caption_image_beam_search, beam_search_batched
     from icd_b200.vocabulary import synthetic_vocab
@@ -230,7 +231,8 @@ def test_beam_search_matches_reference_golden(cuda, name, capsys):
     feats = H.beam_features(case).to(cuda)
     V, k = case["V"], case["k"]
     with torch.no_grad():
-        res = beam_search_batched(dec, feats, k, V - 3, V - 2, max_steps=50, want_alphas=True, want_trace=True)
+        res = beam_search_batched(dec, feats, k, V - 3, V - 2, max_steps=50, want_alphas=True, want_trace=True,
+                                  precision=precision)
     lens = res["len"].cpu().tolist()
     for i in range(case["n_img"]):
         if not bool(g["stable_%d" % i]):

@@ -302,3 +302,30 @@ def test_gemm_bf16_operand_majors_tiles_and_split_k(cuda, M, N, K, a_mn, b_mn):
     H.assert_close_norm(c, ref, 2e-5, "tc gemm majors (%d,%d) %dx%dx%d" % (a_mn, b_mn, M, N, K))
     c2 = ops.gemm(a_dev, b_dev, **kw)
     assert torch.equal(c, c2), "tensor-core contraction (incl. split-K) must be run-to-run deterministic"
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 1), (0, 1)])
+@pytest.mark.parametrize("M,N,K", [(200, 9490, 512), (64, 300, 2048), (5120, 2048, 520)])
+def test_gemm_fp32x3_is_fp32_grade(cuda, M, N, K, a_mn, b_mn):
+    """ICD_PREC_FP32X3: fp32 operands split into three bf16 terms, six cross terms summed by one tcgen05 contraction.
+    Operand rounding is gone (24 mantissa bits kept); what remains is the tensor core's truncating fp32 accumulator:
+    measured ~6e-6 norm-wise at K = 512, i.e. ~70x tighter than single-pass TF32 (4e-4) and ~500x tighter than bf16
+    operands (3e-3).  Bound asserted: 2e-5."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + 3 * N + 7 * K)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g).to(cuda)
+    a_dev = (a.t().contiguous() if a_mn else a).to(cuda)
+    b_dev = (b.t().contiguous() if b_mn else b).to(cuda)
+    kw = dict(M=M, N=N, K=K, bias1=bias, precision="fp32x3")
+    if a_mn:
+        kw["a_strides"] = (1, M)
+    if b_mn:
+        kw["b_strides"] = (1, N)
+    c = ops.gemm(a_dev, b_dev, **kw)
+    ref = a.double() @ b.double().t() + bias.double().cpu()
+    H.assert_close_norm(c, ref, 2e-5, "fp32x3 gemm %dx%dx%d majors (%d,%d)" % (M, N, K, a_mn, b_mn))
+    c16 = ops.gemm(a_dev, b_dev, **dict(kw, precision="bf16"))
+    assert H.rel_err(c, ref) * 50 < H.rel_err(c16, ref), "fp32x3 must be far tighter than bf16 operands"
+    print("fp32x3 rel err %.2e, bf16 rel err %.2e" % (H.rel_err(c, ref), H.rel_err(c16, ref)))
