@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(256) att_step_bwd_kernel(
         const float* __restrict__ gate, const float* __restrict__ awe_raw, const float* __restrict__ d_gated,
         float* __restrict__ d_att_dec, long long ld_ddec,
         float* __restrict__ d_fbeta_pre, long long ld_dfb,
-        float* __restrict__ d_e, long long ld_de) {
+        float* __restrict__ d_e, long long ld_de, float* __restrict__ d_awe_out) {
     extern __shared__ __align__(16) float sm[];
     float* s_dawe = sm;                       // C
     float* s_dec = s_dawe + C;                // A
@@ -364,6 +364,7 @@ __global__ void __launch_bounds__(256) att_step_bwd_kernel(
             const float4 aw = *reinterpret_cast<const float4*>(awe_raw + o + c);
             const float4 da = make_float4(dg.x * g.x, dg.y * g.y, dg.z * g.z, dg.w * g.w);
             *reinterpret_cast<float4*>(s_dawe + c) = da;
+            if (d_awe_out) *reinterpret_cast<float4*>(d_awe_out + o + c) = da;     // kept for the encoder gradient
             const float4 df = make_float4(dg.x * aw.x * g.x * (1.f - g.x), dg.y * aw.y * g.y * (1.f - g.y),
                                           dg.z * aw.z * g.z * (1.f - g.z), dg.w * aw.w * g.w * (1.f - g.w));
             *reinterpret_cast<float4*>(d_fbeta_pre + (long long)r * ld_dfb + c) = df;
@@ -620,7 +621,7 @@ extern "C" int icd_attention_step_bwd(int rows, int P, int C, int A,
                                       const float* gate, const float* awe_raw, const float* d_gated,
                                       float* d_att_dec, int64_t ld_ddec,
                                       float* d_fbeta_pre, int64_t ld_dfb,
-                                      float* d_e, int64_t ld_de, void* stream) {
+                                      float* d_e, int64_t ld_de, float* d_awe_out, void* stream) {
     cudaStream_t s = icd_stream(stream);
     if (rows == 0) return 0;
     ICD_CHECK_ARG(A % 4 == 0 && C % 4 == 0, "attention_step_bwd: A and C must be multiples of 4");
@@ -637,7 +638,7 @@ extern "C" int icd_attention_step_bwd(int rows, int P, int C, int A,
     icd_prof_mark_begin(1, rows, s);
     att_step_bwd_kernel<<<rows, 256, smem, s>>>(P, C, A, enc, att_enc, att_dec, ld_dec, w_full, alpha, ld_alpha,
                                                  d_alpha_ext, ld_dalpha, gate, awe_raw, d_gated,
-                                                 d_att_dec, ld_ddec, d_fbeta_pre, ld_dfb, d_e, ld_de);
+                                                 d_att_dec, ld_ddec, d_fbeta_pre, ld_dfb, d_e, ld_de, d_awe_out);
     icd_prof_mark_end(1, s);
     ICD_LAUNCH_CHECK();
     return 0;
@@ -725,4 +726,85 @@ int icd_attention_step_fwd_grouped(int n_img, int k, int P, int C, int A, const 
         default: ICD_GROUPED(8);
     }
 #undef ICD_GROUPED
+}
+
+// ------------------------------------------------------------------------------------------------
+// Encoder gradient, attention + initial-state part (models/attention.py:59-60 and :161):
+//   d_enc[b,p,c] = sum_{t < len_b} alpha[b,t,p] * d_awe[t,b,c]  +  d_mean[b,c] / P          (written, not accumulated)
+// The enc_att part, d_att_enc W_e, is added afterwards by a contraction with beta = 1.
+// grid = (ceil(C/1024), B), block = 256 threads x 4 channels; d_awe of up to 32 steps lives in registers, alphas in smem.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int EG_TCH = 32;
+__global__ void __launch_bounds__(256, 1) enc_grad_kernel(int B, int T, int P, int C, const int* __restrict__ row_len,
+                                                          const float* __restrict__ alphas,      // (B,T,P)
+                                                          const float* __restrict__ d_awe_all,   // (T,B,C)
+                                                          const float* __restrict__ d_mean,      // (B,C) or NULL
+                                                          float* __restrict__ d_enc) {           // (B,P,C)
+    extern __shared__ __align__(16) float sm[];     // EG_TCH * P alphas of the current step chunk
+    const int b = blockIdx.y;
+    const int c = blockIdx.x * 1024 + threadIdx.x * 4;
+    const int Tb = row_len ? row_len[b] : T;
+    const float invP = 1.f / (float)P;
+    for (int t0 = 0; t0 < max(Tb, 1); t0 += EG_TCH) {
+        const int nt = min(EG_TCH, Tb - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < max(nt, 0) * P; i += blockDim.x)
+            sm[i] = alphas[((long long)b * T + t0 + i / P) * P + (i % P)];
+        __syncthreads();
+        if (c >= C) continue;
+        float4 da[EG_TCH];
+#pragma unroll
+        for (int u = 0; u < EG_TCH; ++u)
+            da[u] = (u < nt) ? *reinterpret_cast<const float4*>(d_awe_all + ((long long)(t0 + u) * B + b) * C + c)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 base = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t0 == 0 && d_mean) {
+            const float4 m = *reinterpret_cast<const float4*>(d_mean + (long long)b * C + c);
+            base = make_float4(m.x * invP, m.y * invP, m.z * invP, m.w * invP);
+        }
+        for (int p = 0; p < P; ++p) {
+            float4 acc = base;
+            float* o = d_enc + ((long long)b * P + p) * C + c;
+            if (t0 > 0) acc = *reinterpret_cast<const float4*>(o);
+#pragma unroll
+            for (int u = 0; u < EG_TCH; ++u) {
+                if (u < nt) {
+                    const float al = sm[u * P + p];
+                    acc.x = fmaf(al, da[u].x, acc.x); acc.y = fmaf(al, da[u].y, acc.y);
+                    acc.z = fmaf(al, da[u].z, acc.z); acc.w = fmaf(al, da[u].w, acc.w);
+                }
+            }
+            *reinterpret_cast<float4*>(o) = acc;
+        }
+    }
+}
+}  // namespace
+
+extern "C" int icd_attention_enc_grad(int B, int T, int P, int C, const int32_t* bt_host,
+                                      const float* alphas, const float* d_awe_all, const float* d_mean,
+                                      float* d_enc, int32_t* row_len_ws, void* stream) {
+    cudaStream_t s = icd_stream(stream);
+    ICD_CHECK_ARG(B > 0 && T > 0 && T <= ICD_MAX_STEPS && C % 4 == 0 && B <= 65535, "attention_enc_grad: bad dims");
+    ICD_CHECK_ARG(alphas && d_awe_all && d_enc, "attention_enc_grad: null argument");
+    int* row_len = nullptr;
+    if (bt_host) {
+        ICD_CHECK_ARG(row_len_ws != nullptr, "attention_enc_grad: row_len_ws (B ints) required with bt_host");
+        BtPack pack;
+        for (int t = 0; t < ICD_MAX_STEPS; ++t) pack.v[t] = t < T ? bt_host[t] : 0;
+        row_len_from_pack_kernel<<<(B + 127) / 128, 128, 0, s>>>(B, T, pack, row_len_ws);
+        ICD_LAUNCH_CHECK();
+        row_len = row_len_ws;
+    }
+    const size_t smem = (size_t)EG_TCH * P * sizeof(float);
+    ICD_CHECK_ARG(smem <= 200 * 1024, "attention_enc_grad: P too large");
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        ICD_CUDA(cudaFuncSetAttribute(enc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((C + 1023) / 1024, B);
+    enc_grad_kernel<<<grid, 256, smem, s>>>(B, T, P, C, row_len, alphas, d_awe_all, d_mean, d_enc);
+    ICD_LAUNCH_CHECK();
+    return 0;
 }

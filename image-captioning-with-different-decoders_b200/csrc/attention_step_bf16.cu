@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
         float* __restrict__ d_att_dec, long long ld_ddec,
         float* __restrict__ d_fbeta_pre, long long ld_dfb,
         float* __restrict__ d_e, long long ld_de,
-        __nv_bfloat16* __restrict__ dz16, long long ld_dz16) {
+        __nv_bfloat16* __restrict__ dz16, long long ld_dz16, float* __restrict__ d_awe_out) {
     extern __shared__ __align__(16) float sm[];
     float* s_dawe = sm;                       // C
     float* s_dec = s_dawe + C;                // A
@@ -194,7 +194,9 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
             const float4 dg = *reinterpret_cast<const float4*>(d_gated + o + c);
             const float4 g = *reinterpret_cast<const float4*>(gate + o + c);
             const float4 aw = *reinterpret_cast<const float4*>(awe_raw + o + c);
-            *reinterpret_cast<float4*>(s_dawe + c) = make_float4(dg.x * g.x, dg.y * g.y, dg.z * g.z, dg.w * g.w);
+            const float4 da = make_float4(dg.x * g.x, dg.y * g.y, dg.z * g.z, dg.w * g.w);
+            *reinterpret_cast<float4*>(s_dawe + c) = da;
+            if (d_awe_out) *reinterpret_cast<float4*>(d_awe_out + o + c) = da;     // kept for the encoder gradient
             const float4 df = make_float4(dg.x * aw.x * g.x * (1.f - g.x), dg.y * aw.y * g.y * (1.f - g.y),
                                           dg.z * aw.z * g.z * (1.f - g.z), dg.w * aw.w * g.w * (1.f - g.w));
             *reinterpret_cast<float4*>(d_fbeta_pre + (long long)r * ld_dfb + c) = df;
@@ -567,7 +569,7 @@ extern "C" int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
                                            float* d_att_dec, int64_t ld_ddec,
                                            float* d_fbeta_pre, int64_t ld_dfb,
                                            float* d_e, int64_t ld_de,
-                                           void* dz16, int64_t ld_dz16, void* stream) {
+                                           void* dz16, int64_t ld_dz16, float* d_awe_out, void* stream) {
     cudaStream_t s = icd_stream(stream);
     if (rows == 0) return 0;
     ICD_CHECK_ARG(A % 8 == 0 && C % 8 == 0, "attention_step_bwd_bf16: A and C must be multiples of 8");
@@ -585,7 +587,7 @@ extern "C" int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
                                                       reinterpret_cast<const __nv_bfloat16*>(att_enc16),
                                                       att_dec, ld_dec, w_full, alpha, ld_alpha, d_alpha_ext, ld_dalpha,
                                                       gate, awe_raw, d_gated, d_att_dec, ld_ddec, d_fbeta_pre, ld_dfb,
-                                                      d_e, ld_de, reinterpret_cast<__nv_bfloat16*>(dz16), ld_dz16);
+                                                      d_e, ld_de, reinterpret_cast<__nv_bfloat16*>(dz16), ld_dz16, d_awe_out);
     icd_prof_mark_end(1, s);
     ICD_LAUNCH_CHECK();
     return 0;

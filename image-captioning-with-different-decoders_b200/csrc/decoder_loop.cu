@@ -179,7 +179,8 @@ extern "C" int icd_attention_decoder_bwd(const icd_att_desc_t* d, void* stream) 
                                        d->alphas + (size_t)t * P, (int64_t)T * P,
                                        d->d_alphas ? d->d_alphas + (size_t)t * P : nullptr, (int64_t)T * P,
                                        d->gate + (size_t)t * B * C, d->awe_raw + (size_t)t * B * C, d->d_gated,
-                                       dzt, NZ, dzt + A, NZ, d->d_e + (size_t)t * P, (int64_t)T * P, s));
+                                       dzt, NZ, dzt + A, NZ, d->d_e + (size_t)t * P, (int64_t)T * P,
+                                       d->d_enc ? d->d_awe_all + (size_t)t * B * C : nullptr, s));
         // dh_{t} = dz * [W_dec; W_fbeta; W_hh]
         ICD_TRY(icd_gemm_simple(prec, dzt, NZ, 1, d->w_cat, 1, D, d->dh, D, bt, D, NZ,
                                 nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s));
@@ -217,5 +218,19 @@ extern "C" int icd_attention_decoder_bwd(const icd_att_desc_t* d, void* stream) 
                                    stream));
     ICD_TRY(icd_gemm_simple(prec, d->d_att_enc, 1, A, d->enc, 1, C, d->d_enc_att_w, C, A, C, B * P,
                             nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s, ICD_GEMM_ALLOW_SPLITK));
+    // ---- optional: gradient w.r.t. the encoder features (--fine_tune_encoder) ----
+    if (d->d_enc) {
+        ICD_CHECK_ARG(d->d_awe_all && d->d_mean, "attention_decoder: d_enc needs the d_awe_all and d_mean scratch buffers");
+        // d_mean = d h0 W_h + d c0 W_c  (:161-163)
+        ICD_TRY(icd_gemm_simple(prec, d->dh, D, 1, d->h_lin_w, 1, C, d->d_mean, C, B, C, D,
+                                nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s));
+        ICD_TRY(icd_gemm_simple(prec, d->dc, D, 1, d->c_lin_w, 1, C, d->d_mean, C, B, C, D,
+                                nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 1.f, s));
+        int32_t* row_len_ws = reinterpret_cast<int32_t*>(d->proj_partial);       // free again after the projection pass
+        ICD_TRY(icd_attention_enc_grad(B, T, P, C, d->bt_host, d->alphas, d->d_awe_all, d->d_mean, d->d_enc, row_len_ws, stream));
+        // + d_att_enc W_e  (:54)
+        ICD_TRY(icd_gemm_simple(prec, d->d_att_enc, A, 1, d->enc_att_w, 1, C, d->d_enc, C, B * P, C, A,
+                                nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 1.f, s));
+    }
     return 0;
 }

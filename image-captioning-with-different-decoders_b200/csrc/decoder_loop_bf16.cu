@@ -238,7 +238,8 @@ int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
                                             d->d_alphas ? d->d_alphas + (size_t)t * P : nullptr, (int64_t)T * P,
                                             d->gate + (size_t)t * B * C, d->awe_raw + (size_t)t * B * C, d->d_gated,
                                             dzt, NZ, dzt + A, NZ, d->d_e + (size_t)t * P, (int64_t)T * P,
-                                            dz16, NZ, (void*)s));                   // d att_dec | d fbeta_pre (+ bf16)
+                                            dz16, NZ, d->d_enc ? d->d_awe_all + (size_t)t * B * C : nullptr,
+                                            (void*)s));                             // d att_dec | d fbeta_pre (+ bf16)
         // dh_t = dz [W_dec; W_fbeta; W_hh]    (stack stored [NZ, D] = MN-major B, N = D, K = NZ)
         MMX(dz16, NZ, 0, u.Wcat, D, 1, d->dh, D, bt, D, NZ, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
     }
@@ -268,5 +269,18 @@ int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
                                         nullptr, u.dae, d->d_full_att_w, d->d_full_att_b, d->d_enc_att_b,
                                         d->proj_partial, (void*)s));
     MMX(u.dae, A, 1, u.enc, C, 1, d->d_enc_att_w, C, A, C, BP, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
+    // ---- optional: gradient w.r.t. the encoder features (--fine_tune_encoder) ----
+    if (d->d_enc) {
+        ICD_CHECK_ARG(d->d_awe_all && d->d_mean, "attention_decoder: d_enc needs the d_awe_all and d_mean scratch buffers");
+        // d_mean = d h0 W_h + d c0 W_c (:161-163): W_h / W_c stored [D, C] = MN-major B (N = C, K = D); u.dh / u.dc hold d h0 / d c0
+        MMX(u.dh, D, 0, u.Wh, C, 1, d->d_mean, C, B, C, D, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
+        ICD_TRY(icd_gemm_bf16_ex(u.dc, D, 0, u.Wc, C, 1, d->d_mean, C, B, C, D, NF, NF, NF, 0, NF, 0, nullptr, 1.f, s,
+                                 nullptr, 0, u.splitk, u.splitk_floats));
+        int32_t* row_len_ws = reinterpret_cast<int32_t*>(d->proj_partial);       // free again after the projection pass
+        ICD_TRY(icd_attention_enc_grad(B, T, P, C, d->bt_host, d->alphas, d->d_awe_all, d->d_mean, d->d_enc, row_len_ws, (void*)s));
+        // + d_att_enc W_e (:54): W_e stored [A, C] = MN-major B (N = C, K = A)
+        ICD_TRY(icd_gemm_bf16_ex(u.dae, A, 0, u.We, C, 1, d->d_enc, C, BP, C, A, NF, NF, NF, 0, NF, 0, nullptr, 1.f, s,
+                                 nullptr, 0, nullptr, 0));
+    }
     return 0;
 }

@@ -7,7 +7,8 @@ reference (models/attention.py:18-284); same parameter initialisation order, so 
 never calls them — it runs the CUDA kernels through the C ABI (include/icd_b200.h).
 
 Out of scope: the BERT-embedding branch (``use_bert=True``, models/attention.py:166-215).
-Not yet supported: gradients w.r.t. ``encoder_out`` (``--fine_tune_encoder``).
+``encoder_out.requires_grad`` (``--fine_tune_encoder``, train.py:39) is honoured: the backward also returns the gradient
+w.r.t. the encoder features (attention-weighted sum, ``enc_att`` projection and initial-state mean paths).
 """
 import ctypes
 
@@ -56,12 +57,10 @@ class _SoftAttentionFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_awe, d_alpha):
         enc, h, We, Wd, wf, att_enc, att_dec, alpha, awe = ctx.saved_tensors
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("icd_b200: gradient w.r.t. encoder_out is not supported yet")
         B, P, C = enc.shape
         A = We.shape[0]
         prec = ctx.precision
-        d_awe = torch.zeros_like(awe) if d_awe is None else d_awe.contiguous()
+        d_awe = torch.zeros_like(awe) if d_awe is None else d_awe.contiguous().float()
         ones = torch.ones_like(awe)
         d_att_dec, _, d_e = ops.attention_step_bwd(enc, att_enc, att_dec, wf.reshape(-1), alpha, ones, awe, d_awe,
                                                    None if d_alpha is None else d_alpha.contiguous())
@@ -74,7 +73,12 @@ class _SoftAttentionFn(torch.autograd.Function):
                         precision=prec)
         d_bd = d_att_dec.sum(0)
         d_h = ops.gemm(d_att_dec, Wd, b_strides=(1, Wd.shape[1]), M=B, N=Wd.shape[1], K=A, precision=prec)
-        return None, d_h, d_We, d_be, d_Wd, d_bd, d_wf.view(1, A), d_bf, None
+        d_enc = None
+        if ctx.needs_input_grad[0]:        # d_enc = alpha (x) d_awe + d_att_enc W_e   (:54, :59-60)
+            d_enc = ops.attention_enc_grad(alpha.view(B, 1, P), d_awe.view(1, B, C))
+            ops.gemm(dae, We, b_strides=(1, C), out=d_enc.view(B * P, C), ldc=C, M=B * P, N=C, K=A, beta=1.0,
+                     precision=prec)
+        return d_enc, d_h, d_We, d_be, d_Wd, d_bd, d_wf.view(1, A), d_bf, None
 
 
 class AttentionDecoderParams:
@@ -194,6 +198,7 @@ class _AttentionDecoderFn(torch.autograd.Function):
         if not enc.is_cuda:
             raise _lib.IcdError("AttentionDecoder.forward needs CUDA tensors; there is no CPU fallback")
         dev = enc.device
+        ctx.in_dtype = enc.dtype
         # bf16 tier: features that already arrive in bf16 (an encoder under autocast, or a bf16 feature store) are used in
         # place — no fp32 round trip; every other dtype is read as fp32 like the reference's .float() path
         enc16 = None
@@ -253,8 +258,6 @@ class _AttentionDecoderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_pred, d_alphas):
-        if ctx.needs_input_grad[0]:
-            raise NotImplementedError("icd_b200: gradient w.r.t. encoder_out (fine-tuned encoder) is not supported yet")
         B, T, L, P, C, A, D, E, V, NZ, emb_is_f64 = ctx.dims
         if ctx.keep is None:
             raise RuntimeError("icd_b200: AttentionDecoder backward called a second time; its saved activations were "
@@ -272,6 +275,7 @@ class _AttentionDecoderFn(torch.autograd.Function):
         if d_alphas is not None:
             d_alphas = d_alphas.contiguous().float()
         want_emb = ctx.needs_input_grad[2]
+        want_enc = ctx.needs_input_grad[0]           # encoder_out.requires_grad (--fine_tune_encoder, train.py:39)
         g = dict(
             d_enc_att_w=torch.empty(A, C, **f32), d_enc_att_b=torch.empty(A, **f32),
             d_w_cat=torch.empty(NZ, D, **f32), d_b_cat=torch.empty(NZ, **f32),
@@ -286,6 +290,9 @@ class _AttentionDecoderFn(torch.autograd.Function):
             dh=torch.empty(B, D, **f32), dc=torch.empty(B, D, **f32), d_gated=torch.empty(B, C, **f32),
             d_att_enc=(torch.empty(B, P, A, **f32) if ctx.precision != "bf16" else None),
             d_emb_x=(torch.empty(T, B, E, **f32) if want_emb else None),
+            d_enc=(torch.empty(B, P, C, **f32) if want_enc else None),
+            d_awe_all=(torch.empty(T, B, C, **f32) if want_enc else None),
+            d_mean=(torch.empty(B, C, **f32) if want_enc else None),
             proj_partial=torch.empty(int(lib().icd_attention_proj_bwd_ws_floats(B, P, A)), **f32))
         d = ctx.desc
         fill(d, d_predictions=d_pred, d_predictions16=d_pred16,
@@ -303,4 +310,7 @@ class _AttentionDecoderFn(torch.autograd.Function):
             g["d_w_ih"], dwc[A + C:], d_b_lstm, d_b_lstm.clone(),
             g["d_h_lin_w"], g["d_h_lin_b"], g["d_c_lin_w"], g["d_c_lin_b"],
             dwc[A:A + C], dbc[A:A + C], g["d_fc_w"], g["d_fc_b"]]
-        return (None, None, g["d_emb_w"], *grads, None, None, None, None)
+        d_enc = scratch["d_enc"]
+        if d_enc is not None and ctx.in_dtype != torch.float32:
+            d_enc = d_enc.to(ctx.in_dtype)
+        return (d_enc, None, g["d_emb_w"], *grads, None, None, None, None)

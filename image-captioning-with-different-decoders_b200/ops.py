@@ -111,8 +111,8 @@ def attention_step_fwd(enc, att_enc, att_dec, w_full, b_full, fbeta_pre=None, im
     return alpha, awe, gate, gated
 
 
-def attention_step_bwd(enc, att_enc, att_dec, w_full, alpha, gate, awe_raw, d_gated, d_alpha_ext=None):
-    """-> (d_att_dec (R,A), d_fbeta_pre (R,C), d_e (R,P))"""
+def attention_step_bwd(enc, att_enc, att_dec, w_full, alpha, gate, awe_raw, d_gated, d_alpha_ext=None, d_awe_out=None):
+    """-> (d_att_dec (R,A), d_fbeta_pre (R,C), d_e (R,P)); d_awe_out: optional (R,C) output d_gated*gate"""
     _need_cuda(enc, att_enc, att_dec, d_gated)
     n_img, P, C = enc.shape
     A = att_enc.shape[2]
@@ -127,7 +127,7 @@ def attention_step_bwd(enc, att_enc, att_dec, w_full, alpha, gate, awe_raw, d_ga
         ptr(d_alpha_ext), ctypes.c_int64(d_alpha_ext.stride(0) if d_alpha_ext is not None else 0),
         ptr(gate), ptr(awe_raw), ptr(d_gated),
         ptr(d_att_dec), ctypes.c_int64(A), ptr(d_fb), ctypes.c_int64(C), ptr(d_e), ctypes.c_int64(P),
-        stream_ptr()), "icd_attention_step_bwd")
+        ptr(d_awe_out), stream_ptr()), "icd_attention_step_bwd")
     return d_att_dec, d_fb, d_e
 
 
@@ -148,6 +148,23 @@ def attention_proj_bwd(att_enc, att_dec_all, w_full, d_e, bt):
                                        ptr(d_att_enc), ptr(d_wf), ptr(d_bf), ptr(d_be), ptr(ws), stream_ptr()),
           "icd_attention_proj_bwd")
     return d_att_enc, d_wf, d_bf, d_be
+
+
+def attention_enc_grad(alphas, d_awe_all, d_mean=None, bt=None):
+    """alphas (B,T,P), d_awe_all (T,B,C), d_mean (B,C) or None, bt list[T] or None
+    -> d_enc (B,P,C) = sum_t alpha[b,t,p] * d_awe[t,b,c] + d_mean[b,c] / P"""
+    _need_cuda(alphas, d_awe_all)
+    B, T, P = alphas.shape
+    C = d_awe_all.shape[2]
+    dev = alphas.device
+    d_enc = torch.empty(B, P, C, device=dev, dtype=torch.float32)
+    bt_arr, ws = None, None
+    if bt is not None:
+        bt_arr = (ctypes.c_int32 * T)(*bt)
+        ws = torch.empty(B, device=dev, dtype=torch.int32)
+    check(lib().icd_attention_enc_grad(B, T, P, C, bt_arr, ptr(alphas.contiguous()), ptr(d_awe_all.contiguous()),
+                                       ptr(d_mean), ptr(d_enc), ptr(ws), stream_ptr()), "icd_attention_enc_grad")
+    return d_enc
 
 
 def init_hidden_state(enc, h_w, h_b, c_w, c_b, precision="fp32"):
@@ -274,7 +291,7 @@ def attention_step_bwd_bf16(enc16, att_enc16, att_dec, w_full, alpha, gate, awe_
         ptr(d_alpha_ext), ctypes.c_int64(d_alpha_ext.stride(0) if d_alpha_ext is not None else 0),
         ptr(gate), ptr(awe_raw), ptr(d_gated),
         ptr(d_att_dec), ctypes.c_int64(A), ptr(d_fb), ctypes.c_int64(C), ptr(d_e), ctypes.c_int64(P),
-        ptr(dz16), ctypes.c_int64(A + C), stream_ptr()), "icd_attention_step_bwd_bf16")
+        ptr(dz16), ctypes.c_int64(A + C), None, stream_ptr()), "icd_attention_step_bwd_bf16")
     return d_att_dec, d_fb, d_e, dz16
 
 

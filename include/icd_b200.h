@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ICD_B200_ABI_VERSION 9
+#define ICD_B200_ABI_VERSION 10
 #define ICD_MAX_STEPS 256
 
 ICD_API int icd_version(void);                       /* ICD_B200_ABI_VERSION the library was built with */
@@ -140,6 +140,8 @@ ICD_API int icd_attention_step_fwd(int rows, int P, int C, int A,
  *        d_fbeta_pre row r at d_fbeta_pre + r*ld_dfb (C floats)
  *        d_e row r at d_e + r*ld_de (P floats)  — gradient w.r.t. the pre-softmax scores; consumed
  *        after the time loop by icd_attention_proj_bwd (d_att_enc is NOT read-modify-written per step)
+ *        d_awe_out (rows,C), optional: d(loss)/d(awe_raw) = d_gated*gate, kept when the gradient w.r.t. the encoder
+ *        features is wanted (icd_attention_enc_grad)
  */
 ICD_API int icd_attention_step_bwd(int rows, int P, int C, int A,
                            const float* enc, const float* att_enc,
@@ -150,8 +152,18 @@ ICD_API int icd_attention_step_bwd(int rows, int P, int C, int A,
                            const float* gate, const float* awe_raw, const float* d_gated,
                            float* d_att_dec, int64_t ld_ddec,
                            float* d_fbeta_pre, int64_t ld_dfb,
-                           float* d_e, int64_t ld_de,
+                           float* d_e, int64_t ld_de, float* d_awe_out,
                            void* stream);
+
+/* Encoder-feature gradient, attention + initial-state part (models/attention.py:59-60, :161; the reference reaches it
+ * when --fine_tune_encoder unfreezes ResNet blocks, train.py:39):
+ *   d_enc[b,p,c] = sum_t alpha[b,t,p] * d_awe[t,b,c] + d_mean[b,c] / P        (d_enc is WRITTEN; d_mean may be NULL)
+ * alphas (B,T,P), d_awe_all (T,B,C) as saved by icd_attention_step_bwd, bt_host[T] optional (NULL => all rows active in
+ * all steps) with row_len_ws = B ints of scratch.  The enc_att part d_att_enc * W_e is added by a contraction (beta 1).
+ */
+ICD_API int icd_attention_enc_grad(int B, int T, int P, int C, const int32_t* bt_host,
+                           const float* alphas, const float* d_awe_all, const float* d_mean,
+                           float* d_enc, int32_t* row_len_ws, void* stream);
 
 /* After the time loop: d_att_enc[b,p,a] = w_full[a] * sum_t d_e[b,t,p] * [att_enc[b,p,a]+att_dec[t,b,a] > 0]
  * plus the full_att parameter gradients (d_w_full[A], d_b_full[1]) and, from the same pass, the enc_att bias
@@ -186,7 +198,7 @@ ICD_API int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
                                 float* d_att_dec, int64_t ld_ddec,
                                 float* d_fbeta_pre, int64_t ld_dfb,
                                 float* d_e, int64_t ld_de,
-                                void* dz16, int64_t ld_dz16, void* stream);
+                                void* dz16, int64_t ld_dz16, float* d_awe_out, void* stream);
 /* d_att_enc (fp32) and d_att_enc16 (bf16) are both optional outputs (at least one should be given) */
 ICD_API int icd_attention_proj_bwd_bf16(int B, int T, int P, int A, const int32_t* bt_host,
                                 const void* att_enc16, const float* att_dec_all, int64_t ld_dec,
@@ -260,6 +272,10 @@ typedef struct {
     float* d_gated;               /* (B,C)    */
     float* d_att_enc;             /* (B,P,A)  ICD_PREC_FP32 only (the bf16 tier keeps a bf16 copy in tc_ws) */
     float* d_emb_x;               /* (T,B,E)  */
+    /* optional: gradient w.r.t. the encoder features (encoder_out.requires_grad, --fine_tune_encoder) */
+    float* d_enc;                 /* (B,P,C) output; NULL => not computed                          */
+    float* d_awe_all;             /* (T,B,C) scratch, required with d_enc                          */
+    float* d_mean;                /* (B,C)   scratch, required with d_enc                          */
     float* proj_partial;          /* icd_attention_proj_bwd_ws_floats(B,P,A) floats */
     /* ICD_PREC_BF16 only: arena for the bf16 operand copies, shared by fwd and bwd of the same step */
     void* tc_ws; int64_t tc_ws_bytes;   /* >= icd_attention_decoder_ws_bytes(desc) */

@@ -162,6 +162,26 @@ def test_attention_decoder_accepts_permuted_encoder_view(cuda):
     assert torch.equal(p1, p2) and torch.equal(a1, a2)
 
 
+def test_soft_attention_module_encoder_gradient(cuda):
+    """SoftAttention used standalone (beam search / custom loops) also back-propagates into the features."""
+    import icd_b200.models.attention as my_att
+    torch.manual_seed(3)
+    att = my_att.SoftAttention(2048, 32, 48)
+    w = {"attention." + k: v.detach().clone().double() for k, v in att.state_dict().items()}
+    att = att.to(cuda)
+    g = torch.Generator().manual_seed(5)
+    enc = torch.randn(3, 196, 2048, generator=g).clamp_min_(0)
+    h = torch.randn(3, 32, generator=g)
+    ga, gb = torch.randn(3, 2048, generator=g), torch.randn(3, 196, generator=g)
+    enc_dev = enc.to(cuda).requires_grad_(True)
+    awe, alpha = att(enc_dev, h.to(cuda))
+    ((awe * ga.to(cuda)).sum() + (alpha * gb.to(cuda)).sum()).backward()
+    e64 = enc.double().requires_grad_(True)
+    awe64, alpha64 = O.soft_attention(w, e64, h.double())
+    ((awe64 * ga.double()).sum() + (alpha64 * gb.double()).sum()).backward()
+    H.assert_close_norm(enc_dev.grad, e64.grad, 1e-4, "SoftAttention d encoder_out")
+
+
 def test_soft_attention_module_matches_oracle(cuda):
     import icd_b200.models.attention as my_att
     torch.manual_seed(0)
@@ -429,3 +449,31 @@ def test_baseline_decoder_bf16_tier_matches_reference_golden(cuda, name):
         compare(case, g, "grad:" + k, gr, 2e-2)
     ids = outs.argmax(dim=2).cpu().numpy()
     assert np.all((ids == g["greedy_ids"]) | (g["greedy_margin"] <= 2e-2))
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 3e-2)])
+def test_encoder_feature_gradient_matches_oracle(cuda, precision, tol):
+    """encoder_out.requires_grad (the reference reaches this with --fine_tune_encoder, train.py:39): the gradient w.r.t.
+    the features — attention-weighted sum (models/attention.py:59-60), enc_att projection (:54) and initial-state mean
+    (:161) paths — against autograd over the fp64 oracle, for a ragged batch fed as the encoder's permuted NCHW view."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.vocabulary import synthetic_vocab
+    case = dict(H.ATT_CASES["att_small_ragged"])
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams,
+                                   synthetic_vocab(case["V"]))
+    sd = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    dec = dec.to(cuda)
+    dec.precision = precision
+    enc, caps, lens = H.att_inputs(case)
+    nchw = enc.permute(0, 3, 1, 2).contiguous().to(cuda).requires_grad_(True)       # what ResNet produces
+    preds, _, dl, alphas = dec(nchw.permute(0, 2, 3, 1), caps.to(cuda), lens)       # models/encoder.py:109 view
+    loss = O.attention_loss(preds, caps.to(cuda), dl, alphas)
+    loss.backward()
+    w64 = {k: v.double() for k, v in sd.items()}
+    e64 = enc.double().requires_grad_(True)
+    p64, _, dl64, a64 = O.attention_decoder_forward(w64, e64, caps, lens)
+    O.attention_loss(p64, caps, dl64, a64).backward()
+    assert nchw.grad is not None and nchw.grad.shape == nchw.shape and nchw.grad.dtype == torch.float32
+    H.assert_close_norm(nchw.grad.permute(0, 2, 3, 1), e64.grad, tol, "d loss / d encoder_out (%s)" % precision)
+    # rows are independent: a caption's feature gradient only depends on its own row
+    assert float(nchw.grad[0].abs().max()) > 0
