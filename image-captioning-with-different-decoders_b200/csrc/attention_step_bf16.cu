@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(256, 4) att_step_fwd_bf16_kernel(
     float* s_e = sm + 2 * A;
     float* s_red = s_e + ((P + 3) & ~3);
     const int r = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     const int img = img_index ? img_index[r] : r;
     const __nv_bfloat16* ae = att_enc + (long long)img * P * A;
     const float* dec = att_dec + (long long)r * ld_dec;
@@ -186,6 +188,8 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
     float* s_part = s_red + 40;               // 3 * A
     const int r = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    pdl_trigger();
+    pdl_wait();
 
     // (A) gate backward (elementwise over C)
     {
@@ -550,11 +554,10 @@ extern "C" int icd_attention_step_fwd_bf16(int rows, int P, int C, int A, const 
         configured = smem;
     }
     icd_prof_mark_begin(0, rows, s);
-    att_step_fwd_bf16_kernel<<<rows, 256, smem, s>>>(P, C, A, img_index,
-                                                      reinterpret_cast<const __nv_bfloat16*>(enc16),
-                                                      reinterpret_cast<const __nv_bfloat16*>(att_enc16),
-                                                      att_dec, ld_dec, w_full, b_full, fbeta_pre, ld_fb, alpha, ld_alpha,
-                                                      awe_raw, gate, gated, reinterpret_cast<__nv_bfloat16*>(gated16));
+    ICD_CUDA(icd_launch_pdl(att_step_fwd_bf16_kernel, dim3(rows), dim3(256), smem, s, P, C, A, (const int*)img_index,
+                            reinterpret_cast<const __nv_bfloat16*>(enc16), reinterpret_cast<const __nv_bfloat16*>(att_enc16),
+                            att_dec, (long long)ld_dec, w_full, b_full, fbeta_pre, (long long)ld_fb, alpha, (long long)ld_alpha,
+                            awe_raw, gate, gated, reinterpret_cast<__nv_bfloat16*>(gated16)));
     icd_prof_mark_end(0, s);
     ICD_LAUNCH_CHECK();
     return 0;
@@ -583,11 +586,11 @@ extern "C" int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
         configured = smem;
     }
     icd_prof_mark_begin(1, rows, s);
-    att_step_bwd_bf16_kernel<<<rows, 256, smem, s>>>(P, C, A, reinterpret_cast<const __nv_bfloat16*>(enc16),
-                                                      reinterpret_cast<const __nv_bfloat16*>(att_enc16),
-                                                      att_dec, ld_dec, w_full, alpha, ld_alpha, d_alpha_ext, ld_dalpha,
-                                                      gate, awe_raw, d_gated, d_att_dec, ld_ddec, d_fbeta_pre, ld_dfb,
-                                                      d_e, ld_de, reinterpret_cast<__nv_bfloat16*>(dz16), ld_dz16, d_awe_out);
+    ICD_CUDA(icd_launch_pdl(att_step_bwd_bf16_kernel, dim3(rows), dim3(256), smem, s, P, C, A,
+                            reinterpret_cast<const __nv_bfloat16*>(enc16), reinterpret_cast<const __nv_bfloat16*>(att_enc16),
+                            att_dec, (long long)ld_dec, w_full, alpha, (long long)ld_alpha, d_alpha_ext, (long long)ld_dalpha,
+                            gate, awe_raw, d_gated, d_att_dec, (long long)ld_ddec, d_fbeta_pre, (long long)ld_dfb,
+                            d_e, (long long)ld_de, reinterpret_cast<__nv_bfloat16*>(dz16), (long long)ld_dz16, d_awe_out));
     icd_prof_mark_end(1, s);
     ICD_LAUNCH_CHECK();
     return 0;

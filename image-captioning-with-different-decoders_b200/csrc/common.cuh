@@ -27,6 +27,21 @@ extern long long g_icd_launches;      // api.cu: kernels launched by this librar
 
 static inline cudaStream_t icd_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+#ifdef __CUDACC__
+// launch with the programmatic-stream-serialization attribute (see pdl_trigger / pdl_wait below)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t icd_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                         Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- device helpers -------------------------------------------------------------------------
 __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
     // streaming 128-bit load: read-only path, do not allocate in L1 (each byte is used once per CTA)
@@ -72,6 +87,16 @@ __device__ __forceinline__ float block_max(float v, float* scratch) {
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------
+// The kernels of the per-time-step chain (contraction -> attention step -> contraction -> LSTM gate math) are short and
+// strictly dependent; launched with cudaLaunchAttributeProgrammaticStreamSerialization the next kernel's CTAs become
+// resident, run their prologue (barrier init, TMEM allocation, tensor-map prefetch) and then block in pdl_wait() until
+// the previous grid has completed and flushed — launch latency and prologue leave the critical path.  Every kernel of
+// the chain executes pdl_trigger() at its top and pdl_wait() before its first dependent global access (reads of
+// upstream results AND writes: a buffer the previous kernel still reads must not be overwritten early).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // attention-step profiling hooks (api.cu)
 void icd_prof_mark_begin(int dir, int rows, cudaStream_t s);

@@ -273,6 +273,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // PDL: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail;
+    // from here on operands / epilogue inputs produced upstream are read and C is written
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         // =================================== TMA producer ===================================
@@ -391,6 +395,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // split-K second pass: C = epilogue(sum_s partial[s]) with the slices summed in fixed order (deterministic).
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits, const EpiArgs e) {
+    pdl_trigger();
+    pdl_wait();
     const long long MN = (long long)e.M * e.N;
     if (e.vec >= 4 && e.N % 4 == 0) {
         const long long total = MN / 4;
@@ -566,7 +572,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KArgs& k, int u
         attr_set = true;
     }
     const int grid = units < ICD_NUM_SMS ? units : ICD_NUM_SMS;
-    gemm_tc_kernel<BN><<<grid, NUM_THREADS, Cfg<BN>::SMEM, s>>>(tmA, tmB, k);
+    ICD_CUDA(icd_launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), (size_t)Cfg<BN>::SMEM, s, tmA, tmB, k));
     ICD_LAUNCH_CHECK();
     return 0;
 }
@@ -672,7 +678,8 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
         const long long work = ((long long)M * N + 3) / 4;
         long long blocks = (work + 255) / 256;
         if (blocks > ICD_NUM_SMS * 8) blocks = ICD_NUM_SMS * 8;
-        splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, s>>>(splitk_ws, pl.splits, e);
+        ICD_CUDA(icd_launch_pdl(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, s,
+                                (const float*)splitk_ws, pl.splits, e));
         ICD_LAUNCH_CHECK();
     }
     return 0;

@@ -15,6 +15,8 @@ __global__ void lstm_pointwise_fwd_kernel(int rows, int D, const float* __restri
                                           float* __restrict__ hdrop, long long hdrop_row_stride,
                                           const unsigned char* __restrict__ mask, float scale,
                                           __nv_bfloat16* __restrict__ h16, __nv_bfloat16* __restrict__ hdrop16) {
+    pdl_trigger();
+    pdl_wait();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)rows * D) return;
     const int r = (int)(idx / D), d = (int)(idx % D);
@@ -47,6 +49,8 @@ __global__ void lstm_pointwise_bwd_kernel(int rows, int D, const float* __restri
                                           const float* __restrict__ c_prev, const float* __restrict__ c_new,
                                           float* __restrict__ dgates_pre, long long ld_dg,
                                           __nv_bfloat16* __restrict__ dg16, long long ld_dg16) {
+    pdl_trigger();
+    pdl_wait();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)rows * D) return;
     const int r = (int)(idx / D), d = (int)(idx % D);
@@ -313,10 +317,9 @@ int icd_lstm_pointwise_fwd(int rows, int D, const float* gates_pre, const float*
                            cudaStream_t s, void* h16, void* hdrop16) {
     if (rows == 0) return 0;
     const long long n = (long long)rows * D;
-    lstm_pointwise_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rows, D, gates_pre, c_prev, gates_act,
-                                                                           c_new, h_new, hdrop, hdrop_row_stride,
-                                                                           mask, scale, (__nv_bfloat16*)h16,
-                                                                           (__nv_bfloat16*)hdrop16);
+    ICD_CUDA(icd_launch_pdl(lstm_pointwise_fwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, s, rows, D,
+                            gates_pre, c_prev, gates_act, c_new, h_new, hdrop, (long long)hdrop_row_stride,
+                            (const unsigned char*)mask, scale, (__nv_bfloat16*)h16, (__nv_bfloat16*)hdrop16));
     ICD_LAUNCH_CHECK();
     return 0;
 }
@@ -327,10 +330,9 @@ int icd_lstm_pointwise_bwd(int rows, int D, const float* dh_in, const float* d_h
                            float* dgates_pre, int64_t ld_dg, cudaStream_t s, void* dg16, int64_t ld_dg16) {
     if (rows == 0) return 0;
     const long long n = (long long)rows * D;
-    lstm_pointwise_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rows, D, dh_in, d_hdrop, hdrop_row_stride,
-                                                                           mask, scale, dc_inout, gates_act, c_prev,
-                                                                           c_new, dgates_pre, ld_dg,
-                                                                           (__nv_bfloat16*)dg16, ld_dg16);
+    ICD_CUDA(icd_launch_pdl(lstm_pointwise_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, s, rows, D,
+                            dh_in, d_hdrop, (long long)hdrop_row_stride, (const unsigned char*)mask, scale, dc_inout, gates_act,
+                            c_prev, c_new, dgates_pre, (long long)ld_dg, (__nv_bfloat16*)dg16, (long long)ld_dg16));
     ICD_LAUNCH_CHECK();
     return 0;
 }
