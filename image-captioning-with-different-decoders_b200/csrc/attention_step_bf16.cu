@@ -31,6 +31,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// m16n8k16 bf16 x bf16 -> fp32 warp MMA (legacy tensor path; used here as a batched matrix-vector product: the k index of
+// A and B may be ANY consistent permutation of the contraction index, which lets A fragments come straight from 128-bit
+// global loads of row-major bf16 features with no shuffles or shared-memory transposes)
+__device__ __forceinline__ void mma_bf16_16816(float& d0, float& d1, float& d2, float& d3,
+                                               uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward: one kernel per decode step, grid = rows, block = 256.
 // ------------------------------------------------------------------------------------------------
@@ -178,7 +187,7 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
         float* __restrict__ d_att_dec, long long ld_ddec,
         float* __restrict__ d_fbeta_pre, long long ld_dfb,
         float* __restrict__ d_e, long long ld_de,
-        __nv_bfloat16* __restrict__ dz16, long long ld_dz16, float* __restrict__ d_awe_out) {
+        __nv_bfloat16* __restrict__ dz16, long long ld_dz16, float* __restrict__ d_awe_out, int use_mma) {
     extern __shared__ __align__(16) float sm[];
     float* s_dawe = sm;                       // C
     float* s_dec = s_dawe + C;                // A
@@ -186,6 +195,8 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
     float* s_de = s_alpha + ((P + 3) & ~3);   // Ppad
     float* s_red = s_de + ((P + 3) & ~3);     // 40
     float* s_part = s_red + 40;               // 3 * A
+    float* s_pb = s_part + 3 * A;             // nwarp * Pp16   (tensor-core path: per-warp partial d_alpha)
+    __nv_bfloat16* s_hl = reinterpret_cast<__nv_bfloat16*>(s_pb + (blockDim.x >> 5) * (((P + 15) >> 4) << 4));   // 3 * C bf16
     const int r = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     pdl_trigger();
@@ -216,8 +227,67 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
     }
     __syncthreads();
 
-    // (B) d_alpha[p] = <d_awe, enc[r,p,:]>: warp per pixel row, 8 x 16 B loads in flight per lane
-    {
+    // (B) d_alpha[p] = <d_awe, enc[r,p,:]>
+    if (use_mma) {
+        // Tensor-core path.  d_awe (fp32) is split into three bf16 terms (24 mantissa bits: hi, mid, lo = columns n = 0, 1, 2
+        // of the B operand), enc rows are the A operand: D[16 pixels x 8] += A[16 pixels x 16 ch] * B[16 ch x 8].
+        // Warp w owns the channel strip [w*CW, (w+1)*CW) of every pixel row; lane (g = lane/4, t = lane%4) loads 16 B
+        // (channels 8t..8t+7 of a 32-channel block) of rows g and g+8 of the pixel block: those two 128-bit loads are
+        // the A fragments of two MMAs (k-slots 2t,2t+1 <-> channels 8t+0,1; 2t+8,2t+9 <-> 8t+2,3; second MMA: 8t+4..7).
+        // ~5 instructions per KB of features instead of ~38 for the unpack + FMA loop.
+        __nv_bfloat16* s_h0 = s_hl; __nv_bfloat16* s_h1 = s_hl + C; __nv_bfloat16* s_h2 = s_hl + 2 * C;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const float v = s_dawe[c];
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v);
+            const float r1 = v - __bfloat162float(h0);
+            const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+            s_h0[c] = h0; s_h1[c] = h1; s_h2[c] = __float2bfloat16_rn(r1 - __bfloat162float(h1));
+        }
+        __syncthreads();
+        const int g = lane >> 2, t = lane & 3;
+        const int CW = C / nwarp, NB = CW >> 5;
+        const int cb0 = warp * CW;
+        const int Pp16 = ((P + 15) >> 4) << 4;
+        const __nv_bfloat16* eb = enc + (long long)r * P * C + cb0 + 8 * t;
+        const __nv_bfloat16* bsrc = (g < 3) ? (s_hl + g * C + cb0 + 8 * t) : s_hl;
+        for (int pb = 0; pb < (Pp16 >> 4); ++pb) {
+            const int p0 = pb * 16 + g, p1 = p0 + 8;
+            const __nv_bfloat16* rowA = eb + (long long)min(p0, P - 1) * C;
+            const __nv_bfloat16* rowB = eb + (long long)min(p1, P - 1) * C;
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+            for (int nb0 = 0; nb0 < NB; nb0 += 4) {
+                uint4 xa[4], xb[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (nb0 + u < NB) { xa[u] = ld_stream_u4(rowA + 32 * (nb0 + u)); xb[u] = ld_stream_u4(rowB + 32 * (nb0 + u)); }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (nb0 + u < NB) {
+                        uint4 bq = make_uint4(0u, 0u, 0u, 0u);
+                        if (g < 3) bq = *reinterpret_cast<const uint4*>(bsrc + 32 * (nb0 + u));
+                        mma_bf16_16816(d0, d1, d2, d3, xa[u].x, xb[u].x, xa[u].y, xb[u].y, bq.x, bq.y);
+                        mma_bf16_16816(d0, d1, d2, d3, xa[u].z, xb[u].z, xa[u].w, xb[u].w, bq.z, bq.w);
+                    }
+                }
+            }
+            // D columns 0,1 (hi, mid) sit on the t == 0 lane of each quad, column 2 (lo) on the t == 1 lane
+            float s0 = (t == 0) ? d0 + d1 : ((t == 1) ? d0 : 0.f);
+            float s1 = (t == 0) ? d2 + d3 : ((t == 1) ? d2 : 0.f);
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+            if (t == 0) {
+                if (p0 < P) s_pb[warp * Pp16 + p0] = s0;
+                if (p1 < P) s_pb[warp * Pp16 + p1] = s1;
+            }
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < P; p += blockDim.x) {
+            float acc = 0.f;
+            for (int w = 0; w < nwarp; ++w) acc += s_pb[w * Pp16 + p];
+            if (d_alpha_ext) acc += d_alpha_ext[(long long)r * ld_dalpha + p];
+            s_de[p] = acc;
+        }
+    } else {
         const __nv_bfloat16* eb = enc + (long long)r * P * C;
         const int C8 = C >> 3;
         for (int p = warp; p < P; p += nwarp) {
@@ -578,7 +648,10 @@ extern "C" int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
     ICD_CHECK_ARG(A % 8 == 0 && C % 8 == 0, "attention_step_bwd_bf16: A and C must be multiples of 8");
     ICD_CHECK_ARG(ld_dec % 4 == 0 && ld_ddec % 4 == 0 && ld_dfb % 4 == 0 && (!dz16 || ld_dz16 % 8 == 0),
                   "attention_step_bwd_bf16: row strides misaligned");
-    const size_t smem = ((size_t)C + 4 * (size_t)A + 2 * ((P + 3) & ~3) + 40) * sizeof(float);
+    // tensor-core d_alpha path: 8 warps x channel strips of whole 32-channel blocks
+    const int use_mma = (C % 256 == 0) ? 1 : 0;
+    const size_t smem = ((size_t)C + 4 * (size_t)A + 2 * ((P + 3) & ~3) + 40 + 8 * (((P + 15) >> 4) << 4)) * sizeof(float)
+                        + 3 * (size_t)C * 2;
     ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_bwd_bf16: dims too large for shared memory");
     static size_t configured = 48 * 1024;
     if (smem > configured) {
@@ -590,7 +663,8 @@ extern "C" int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
                             reinterpret_cast<const __nv_bfloat16*>(enc16), reinterpret_cast<const __nv_bfloat16*>(att_enc16),
                             att_dec, (long long)ld_dec, w_full, alpha, (long long)ld_alpha, d_alpha_ext, (long long)ld_dalpha,
                             gate, awe_raw, d_gated, d_att_dec, (long long)ld_ddec, d_fbeta_pre, (long long)ld_dfb,
-                            d_e, (long long)ld_de, reinterpret_cast<__nv_bfloat16*>(dz16), (long long)ld_dz16, d_awe_out));
+                            d_e, (long long)ld_de, reinterpret_cast<__nv_bfloat16*>(dz16), (long long)ld_dz16, d_awe_out,
+                            use_mma));
     icd_prof_mark_end(1, s);
     ICD_LAUNCH_CHECK();
     return 0;
