@@ -358,6 +358,31 @@ def side_workload(args):
                       "dtype": dec.precision, "config": {"workload": name}}), flush=True)
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this rank's threads (and hence its first-touched pinned host buffers) to the NUMA node its GPU hangs off: with
+    one process per GPU the eight ranks otherwise all stage their H2D traffic through whichever node the OS picked."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        return None
+    return None
+
+
 def main():
     args = parse()
     if args.workload != "train" and args.impl != "reference":
@@ -378,6 +403,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (the decoder has no CPU path)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("ICD_BENCH_KEEP_NCCL_DEBUG") is None:
@@ -533,7 +559,7 @@ def main():
         e2e = {"value": B * world * args.steps / (ms_main / 1e3), "unit": "captions/s",
                "h2d_bytes_per_step": int(main_bytes), "d2h_bytes_per_step": 4,
                "ms_per_step": ms_main / args.steps,
-               "host_feature_dtype": "bf16" if host16 else "fp32",
+               "host_feature_dtype": "bf16" if host16 else "fp32", "numa_node_rank0": numa_node,
                "note": "per GPU: pinned host features + int64 captions copied H2D every step on a side stream "
                        "(double-buffered); every step's loss copied D2H to pinned memory and read on the host one step "
                        "later (pipelined read-back)"}
