@@ -477,3 +477,85 @@ def test_encoder_feature_gradient_matches_oracle(cuda, precision, tol):
     H.assert_close_norm(nchw.grad.permute(0, 2, 3, 1), e64.grad, tol, "d loss / d encoder_out (%s)" % precision)
     # rows are independent: a caption's feature gradient only depends on its own row
     assert float(nchw.grad[0].abs().max()) > 0
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 8e-3)])
+@pytest.mark.parametrize("B,lengths", [(1, [2]), (1, [9]), (3, [6, 1, 4]), (4, [2, 2, 2, 2]), (2, [40, 37])])
+def test_attention_decoder_edge_shapes(cuda, precision, tol, B, lengths):
+    """Edges of the teacher-forced loop against the oracle: a single caption, a single decode step (length-2 captions),
+    a caption of length 1 (zero decode steps: its rows stay exactly 0), long captions (T = 39 steps)."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.vocabulary import synthetic_vocab
+    case = dict(B=B, V=61, A=48, D=32, E=24, max_len=max(lengths), lengths=lengths, wseed=9, iseed=31 + B,
+                dropout=0.0, train=False, fine_tune_embedding=True)
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams,
+                                   synthetic_vocab(case["V"]))
+    w = {k: v.detach().clone().requires_grad_(True) for k, v in dec.state_dict().items()}
+    dec = dec.to(cuda)
+    dec.precision = precision
+    enc = synthetic_features(B, case["iseed"])
+    caps, lens = synthetic_caps(case)
+    preds, _, dl, alphas = dec(enc.to(cuda), caps.to(cuda), lens)
+    o_preds, _, o_dl, o_alphas = O.attention_decoder_forward(w, enc, caps, lens)
+    assert dl == o_dl and preds.shape == o_preds.shape and alphas.shape == o_alphas.shape
+    H.assert_close_norm(preds, o_preds, tol, "predictions")
+    H.assert_close_norm(alphas, o_alphas, tol, "alphas")
+    for t in range(max(dl)):                      # rows beyond batch_size_t stay exactly 0 (models/attention.py:253-258)
+        bt = sum(l > t for l in dl)
+        assert torch.all(preds[bt:, t] == 0) and torch.all(alphas[bt:, t] == 0)
+    g = torch.Generator().manual_seed(5)
+    gp, ga = torch.randn(preds.shape, generator=g), torch.randn(alphas.shape, generator=g)
+    ((preds * gp.to(cuda)).sum() + (alphas * ga.to(cuda)).sum()).backward()
+    ((o_preds * gp).sum() + (o_alphas * ga).sum()).backward()
+    gtol = 2e-3 if precision == "fp32" else 1.5e-1
+    for k, p in dec.named_parameters():
+        if k == "attention.full_att.bias":
+            continue
+        H.assert_close_norm(p.grad, w[k].grad, gtol, "grad " + k, atol=1e-6)
+
+
+def synthetic_features(B, seed):
+    from icd_b200 import synthetic
+    return synthetic.features(B, seed=seed)
+
+
+def synthetic_caps(case):
+    from icd_b200 import synthetic
+    return synthetic.captions(case["B"], case["V"], max_len=case["max_len"], seed=case["iseed"], lengths=case["lengths"])
+
+
+@pytest.mark.parametrize("k,n_img", [(1, 3), (8, 2), (5, 1)])
+def test_beam_search_edge_beam_widths_match_oracle(cuda, k, n_img):
+    """Beam widths 1 and 8 (the kernel's maximum) and a single image, against the oracle's per-image state machine."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.gen_captions import beam_search_batched
+    from icd_b200.vocabulary import synthetic_vocab
+    case = dict(H.BEAM_CASES["beam_small"], dropout=0.5, train=False, fine_tune_embedding=True, k=k, n_img=n_img)
+    vocab = synthetic_vocab(case["V"])
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams, vocab)
+    H.apply_beam_recipe(dec, case)
+    w = {kk: v.detach().clone() for kk, v in dec.state_dict().items()}
+    w64 = {kk: v.double() for kk, v in w.items()}
+    dec = dec.to(cuda)
+    feats = H.beam_features(case)[:n_img]
+    V = case["V"]
+    with torch.no_grad():
+        res = beam_search_batched(dec, feats.to(cuda), k, V - 3, V - 2, max_steps=50, want_alphas=True, want_trace=True)
+    lens = res["len"].cpu().tolist()
+    checked = 0
+    for i in range(n_img):
+        tr32, tr64 = [], []
+        seq, alphas, ended = O.beam_search(w, feats[i:i + 1], k, V - 3, V - 2, trace=tr32)
+        seq64, _, ended64 = O.beam_search(w64, feats[i:i + 1].double(), k, V - 3, V - 2, trace=tr64)
+        if (seq, ended) != (seq64, ended64) or tr32 != tr64:
+            continue            # the reference's own outcome is not stable under fp64 re-evaluation: not a target
+        checked += 1
+        if ended:
+            assert lens[i] == len(seq) and res["seq"][i, :lens[i]].cpu().tolist() == seq
+            a = res["alpha"][i, :lens[i]].cpu().numpy().reshape(lens[i], 14, 14)
+            assert np.abs(a - np.asarray(alphas, dtype=np.float32)).max() < 1e-4
+        else:
+            assert lens[i] == 0
+        got = [[x for x in row if x >= 0] for row in res["trace"][:len(tr32), i].cpu().tolist()]
+        assert got == tr32
+    assert checked >= 1
