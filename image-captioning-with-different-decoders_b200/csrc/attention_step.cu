@@ -182,17 +182,29 @@ __global__ void __launch_bounds__(256, 2) att_step_fwd_grouped_kernel(
 #pragma unroll
         for (int j = 0; j < K; ++j) acc[j] = 0.f;
         const float* row = ae + (long long)p * A;
-        for (int q = lane; q < A4; q += 32) {
-            const float4 x = ld_stream_f4(row + 4 * q);
-            const float4 w = *reinterpret_cast<const float4*>(s_wf + 4 * q);
+        for (int q0 = lane; q0 < A4; q0 += 4 * 32) {                 // 4 independent 128-bit loads in flight per lane
+            float4 xs[4];
 #pragma unroll
-            for (int j = 0; j < K; ++j) {
-                if (j < kl) {
-                    const float4 d = *reinterpret_cast<const float4*>(s_dec + j * A + 4 * q);
-                    acc[j] = fmaf(fmaxf(x.x + d.x, 0.f), w.x, acc[j]);
-                    acc[j] = fmaf(fmaxf(x.y + d.y, 0.f), w.y, acc[j]);
-                    acc[j] = fmaf(fmaxf(x.z + d.z, 0.f), w.z, acc[j]);
-                    acc[j] = fmaf(fmaxf(x.w + d.w, 0.f), w.w, acc[j]);
+            for (int u = 0; u < 4; ++u) {
+                const int q = q0 + 32 * u;
+                xs[u] = (q < A4) ? ld_stream_f4(row + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int q = q0 + 32 * u;
+                if (q < A4) {
+                    const float4 x = xs[u];
+                    const float4 w = *reinterpret_cast<const float4*>(s_wf + 4 * q);
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        if (j < kl) {
+                            const float4 d = *reinterpret_cast<const float4*>(s_dec + j * A + 4 * q);
+                            acc[j] = fmaf(fmaxf(x.x + d.x, 0.f), w.x, acc[j]);
+                            acc[j] = fmaf(fmaxf(x.y + d.y, 0.f), w.y, acc[j]);
+                            acc[j] = fmaf(fmaxf(x.z + d.z, 0.f), w.z, acc[j]);
+                            acc[j] = fmaf(fmaxf(x.w + d.w, 0.f), w.w, acc[j]);
+                        }
+                    }
                 }
             }
         }
@@ -225,12 +237,12 @@ __global__ void __launch_bounds__(256, 2) att_step_fwd_grouped_kernel(
 #pragma unroll
         for (int j = 0; j < K; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         int p = 0;
-        for (; p + 4 <= P; p += 4) {
-            float4 x[4];
+        for (; p + 8 <= P; p += 8) {                                  // 8 independent 128-bit loads in flight per thread
+            float4 x[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) x[u] = ld_stream_f4(eb + (long long)(p + u) * C + c);
+            for (int u = 0; u < 8; ++u) x[u] = ld_stream_f4(eb + (long long)(p + u) * C + c);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
 #pragma unroll
                 for (int j = 0; j < K; ++j) {
                     if (j < kl) {

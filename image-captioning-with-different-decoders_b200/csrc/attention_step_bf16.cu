@@ -80,8 +80,8 @@ __global__ void __launch_bounds__(256, 4) att_step_fwd_bf16_kernel(
             uint4 x[FW16_ROWS];
 #pragma unroll
             for (int u = 0; u < FW16_ROWS; ++u) {
-                const int p = min(p0 + u * nwarp, P - 1);
-                x[u] = ld_stream_u4(ae + (long long)p * A + 8 * j);
+                const int p = p0 + u * nwarp;                     // warp-uniform: rows past P are not loaded at all
+                x[u] = (p < P) ? ld_stream_u4(ae + (long long)p * A + 8 * j) : make_uint4(0u, 0u, 0u, 0u);
             }
             const float4 d0 = *reinterpret_cast<const float4*>(s_dec + 8 * j);
             const float4 d1 = *reinterpret_cast<const float4*>(s_dec + 8 * j + 4);
@@ -259,7 +259,10 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
                 uint4 xa[4], xb[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    if (nb0 + u < NB) { xa[u] = ld_stream_u4(rowA + 32 * (nb0 + u)); xb[u] = ld_stream_u4(rowB + 32 * (nb0 + u)); }
+                    if (nb0 + u < NB) {                           // rows past P (last pixel block) are zero, not re-read
+                        xa[u] = (p0 < P) ? ld_stream_u4(rowA + 32 * (nb0 + u)) : make_uint4(0u, 0u, 0u, 0u);
+                        xb[u] = (p1 < P) ? ld_stream_u4(rowB + 32 * (nb0 + u)) : make_uint4(0u, 0u, 0u, 0u);
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {

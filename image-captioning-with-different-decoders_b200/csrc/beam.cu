@@ -117,26 +117,52 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
     if (kl == 0) return;
     const int nrows = (step == 1) ? 1 : kl;                                                  // :78-82
     const float* lg = logits + (long long)img * k * V;
+    // rows are streamed with 64-bit loads, 4 in flight per thread (rows are 8-byte aligned when V is even)
+    const bool even = (V & 1) == 0;
+    const int V2 = V >> 1;
     for (int i = 0; i < nrows; ++i) {                                                        // :74 log_softmax
         const float* x = lg + (long long)i * V;
+        const float2* x2 = reinterpret_cast<const float2*>(x);
         float m = -INFINITY;
-        for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, x[v]);
+        if (even) {
+            int j = threadIdx.x;
+            for (; j + 3 * 256 < V2; j += 4 * 256) {
+                float2 a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = x2[j + u * 256];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) m = fmaxf(m, fmaxf(a[u].x, a[u].y));
+            }
+            for (; j < V2; j += 256) { const float2 a = x2[j]; m = fmaxf(m, fmaxf(a.x, a.y)); }
+        } else {
+            for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, x[v]);
+        }
         m = block_max(m, s_red);
         float sum = 0.f;
-        for (int v = threadIdx.x; v < V; v += blockDim.x) sum += expf(x[v] - m);
+        if (even) {
+            int j = threadIdx.x;
+            for (; j + 3 * 256 < V2; j += 4 * 256) {
+                float2 a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = x2[j + u * 256];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) sum += expf(a[u].x - m) + expf(a[u].y - m);
+            }
+            for (; j < V2; j += 256) { const float2 a = x2[j]; sum += expf(a.x - m) + expf(a.y - m); }
+        } else {
+            for (int v = threadIdx.x; v < V; v += blockDim.x) sum += expf(x[v] - m);
+        }
         sum = block_sum(sum, s_red);
         if (threadIdx.x == 0) { s_max[i] = m; s_lsum[i] = logf(sum); s_score[i] = score[img * k + i]; }
     }
     __syncthreads();
-    // thread-local top-kl over a strided slice of the flattened (nrows*V) candidates
+    // thread-local top-KMAX over this thread's slice of the flattened (nrows*V) candidates (flat index f = i*V + v)
     float tv[KMAX]; int ti[KMAX];
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
-    const int total = nrows * V;
-    for (int f = threadIdx.x; f < total; f += blockDim.x) {
-        const int i = f / V;
-        const float lp = (lg[f] - s_max[i]) - s_lsum[i];            // log_softmax value
-        const float v = s_score[i] + lp;                            // :76
+    auto consider = [&](float xv, float rmax, float rlsum, float rscore, int f) {
+        const float lp = (xv - rmax) - rlsum;                       // log_softmax value
+        const float v = rscore + lp;                                // :76
         if (better(v, f, tv[KMAX - 1], ti[KMAX - 1])) {
             tv[KMAX - 1] = v; ti[KMAX - 1] = f;
 #pragma unroll
@@ -146,6 +172,32 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
                     const int b = ti[j]; ti[j] = ti[j - 1]; ti[j - 1] = b;
                 }
             }
+        }
+    };
+    for (int i = 0; i < nrows; ++i) {
+        const float* x = lg + (long long)i * V;
+        const float2* x2 = reinterpret_cast<const float2*>(x);
+        const float rmax = s_max[i], rlsum = s_lsum[i], rscore = s_score[i];
+        const int f0 = i * V;
+        if (even) {
+            int j = threadIdx.x;
+            for (; j + 3 * 256 < V2; j += 4 * 256) {
+                float2 a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = x2[j + u * 256];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    consider(a[u].x, rmax, rlsum, rscore, f0 + 2 * (j + u * 256));
+                    consider(a[u].y, rmax, rlsum, rscore, f0 + 2 * (j + u * 256) + 1);
+                }
+            }
+            for (; j < V2; j += 256) {
+                const float2 a = x2[j];
+                consider(a.x, rmax, rlsum, rscore, f0 + 2 * j);
+                consider(a.y, rmax, rlsum, rscore, f0 + 2 * j + 1);
+            }
+        } else {
+            for (int v = threadIdx.x; v < V; v += blockDim.x) consider(x[v], rmax, rlsum, rscore, f0 + v);
         }
     }
 #pragma unroll
