@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="icd_b200", choices=["icd_b200", "reference"])
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp32x3", "bf16"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="captions per GPU (default: the benchmark config)")
     ap.add_argument("--workload", default="train", choices=["train", "beam", "baseline", "glove"],
                     help="train = BASELINE.json configs[2] (the metric's configuration, default); the others time the "
@@ -304,7 +304,7 @@ def side_workload(args):
         p.vocab_size = V
         torch.manual_seed(0)
         dec = my_base.BaselineDecoder(p).to(dev)
-        dec.precision = "bf16" if args.precision in ("auto", "bf16") else "fp32"
+        dec.precision = "bf16" if args.precision in ("auto", "bf16") else args.precision
         opt = DataParallelClipAdam(dec, lr=1e-4, grad_clip=5.0)
         img = torch.randn(Bb, E, device=dev, requires_grad=True)
         caps, _ = synthetic.captions(Bb, V, max_len=L)
@@ -328,7 +328,7 @@ def side_workload(args):
         dec.load_pretrained_embeddins(synthetic.glove_like_table(V, 300))
         dec.fine_tune_embeddings(True)
         dec = dec.to(dev)
-        dec.precision = "bf16" if args.precision in ("auto", "bf16") else "fp32"
+        dec.precision = "bf16" if args.precision in ("auto", "bf16") else args.precision
         dec.train()
         opt = DataParallelClipAdam(dec, lr=1e-4, grad_clip=5.0)
         enc = synthetic.features(Bb).to(dev)

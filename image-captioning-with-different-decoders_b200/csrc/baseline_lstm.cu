@@ -4,6 +4,7 @@
 // h * W_hh^T (+ fused gate pointwise) per step, and the vocabulary contraction runs once over all (b, t).
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include <algorithm>
 
 namespace {
 int check(const icd_base_desc_t* d) {
@@ -136,6 +137,14 @@ int baseline_bwd_bf16(const icd_base_desc_t* d, cudaStream_t s) {
 }  // namespace
 
 extern "C" int64_t icd_baseline_decoder_ws_bytes(const icd_base_desc_t* d) {
+    if (d && d->precision == ICD_PREC_FP32X3) {
+        const int64_t B = d->B, L = d->L, E = d->E, H = d->H, V = d->V, LB = L * B;
+        const int64_t shapes[][3] = {{LB, 4 * H, E}, {B, 4 * H, H}, {LB, V, H}, {LB, H, V}, {V, H, LB}, {B, H, 4 * H},
+                                     {4 * H, H, LB}, {4 * H, E, LB}, {LB, E, 4 * H}};
+        int64_t need = 0;
+        for (const auto& sh : shapes) need = std::max(need, icd_gemm_ws_bytes((int)sh[0], (int)sh[1], (int)sh[2], ICD_PREC_FP32X3));
+        return need;
+    }
     if (!d || d->precision != ICD_PREC_BF16) return 0;
     Arena16 a; a.base = nullptr; a.cap = 0; a.off = 0; a.ok = true;
     BaseBufs b;
@@ -147,7 +156,8 @@ extern "C" int icd_baseline_decoder_fwd(const icd_base_desc_t* d, void* stream) 
     ICD_TRY(check(d));
     cudaStream_t s = icd_stream(stream);
     if (d->precision == ICD_PREC_BF16) return baseline_fwd_bf16(d, s);
-    ICD_CHECK_ARG(d->precision == ICD_PREC_FP32, "baseline_decoder: unknown precision %d", d->precision);
+    ICD_CHECK_ARG(d->precision == ICD_PREC_FP32 || d->precision == ICD_PREC_FP32X3, "baseline_decoder: unknown precision %d", d->precision);
+    IcdSimpleWsScope ws_scope(d->tc_ws, d->tc_ws_bytes);
     const int B = d->B, L = d->L, E = d->E, H = d->H, V = d->V, prec = d->precision;
     const size_t BH = (size_t)B * H;
     // x[0] = img_features, x[t] = embedding(captions[:, t-1])   (:93-101)
@@ -173,6 +183,7 @@ extern "C" int icd_baseline_decoder_bwd(const icd_base_desc_t* d, void* stream) 
     ICD_TRY(check(d));
     cudaStream_t s = icd_stream(stream);
     if (d->precision == ICD_PREC_BF16) return baseline_bwd_bf16(d, s);
+    IcdSimpleWsScope ws_scope(d->tc_ws, d->tc_ws_bytes);
     const int B = d->B, L = d->L, E = d->E, H = d->H, V = d->V, prec = d->precision;
     const size_t BH = (size_t)B * H;
     const int LB = L * B;

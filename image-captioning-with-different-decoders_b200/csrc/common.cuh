@@ -126,6 +126,11 @@ int icd_attention_step_fwd_grouped(int n_img, int k, int P, int C, int A, const 
                                    const float* att_enc, const float* att_dec, int64_t ld_dec, const float* w_full,
                                    const float* b_full, const float* fbeta_pre, int64_t ld_fb, float* alpha,
                                    int64_t ld_alpha, float* gated, cudaStream_t s);
+void icd_gemm_simple_set_ws(void* ws, int64_t bytes);
+struct IcdSimpleWsScope {          // RAII: workspace for icd_gemm_simple's tensor-core tiers during one entry-point call
+    IcdSimpleWsScope(void* ws, int64_t bytes) { icd_gemm_simple_set_ws(ws, bytes); }
+    ~IcdSimpleWsScope() { icd_gemm_simple_set_ws(nullptr, 0); }
+};
 int icd_gemm_simple(int prec, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
                     float* C, int64_t ldc, int M, int N, int K, const float* bias1, const float* bias2,
                     const float* add1, int64_t ld1, const float* add2, int64_t ld2, const uint8_t* row_mask,

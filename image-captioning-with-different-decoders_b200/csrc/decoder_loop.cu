@@ -11,6 +11,7 @@
 // Backward is the hand-derived adjoint of the same graph (BPTT), with all weight-gradient contractions hoisted
 // out of the loop (one per weight over the T*B stacked rows).
 #include "common.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -57,16 +58,27 @@ int icd_attention_decoder_fwd_bf16(const icd_att_desc_t* d, cudaStream_t s);
 int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s);
 
 extern "C" int64_t icd_attention_decoder_ws_bytes(const icd_att_desc_t* d) {
-    if (!d || d->precision != ICD_PREC_BF16) return 0;
-    return icd_att_tc_ws_bytes(d);
+    if (!d) return 0;
+    if (d->precision == ICD_PREC_BF16) return icd_att_tc_ws_bytes(d);
+    if (d->precision != ICD_PREC_FP32X3) return 0;
+    // fp32-grade tensor-core tier: every contraction splits its two operands on the fly (gemm_tc.cu); size for the largest
+    const int64_t B = d->B, T = d->T, P = d->P, C = d->C, A = d->A, D = d->D, E = d->E, V = d->V, NZ = A + C + 4 * D, TB = T * B;
+    const int64_t shapes[][3] = {
+        {B * P, A, C}, {B, D, C}, {TB, 4 * D, E}, {B, NZ, D}, {B, 4 * D, C}, {B * T, V, D},
+        {B * T, D, V}, {V, D, B * T}, {B, C, 4 * D}, {B, D, NZ}, {D, C, B}, {NZ, D, TB}, {4 * D, E, TB}, {4 * D, C, TB},
+        {TB, E, 4 * D}, {A, C, B * P}, {B, C, D}, {B * P, C, A}};
+    int64_t need = 0;
+    for (const auto& sh : shapes) need = std::max(need, icd_gemm_ws_bytes((int)sh[0], (int)sh[1], (int)sh[2], ICD_PREC_FP32X3));
+    return need;
 }
 
 extern "C" int icd_attention_decoder_fwd(const icd_att_desc_t* d, void* stream) {
     ICD_TRY(check_common(d));
     cudaStream_t s = icd_stream(stream);
     if (d->precision == ICD_PREC_BF16) return icd_attention_decoder_fwd_bf16(d, s);
-    ICD_CHECK_ARG(d->precision == ICD_PREC_FP32, "attention_decoder: unknown precision %d", d->precision);
+    ICD_CHECK_ARG(d->precision == ICD_PREC_FP32 || d->precision == ICD_PREC_FP32X3, "attention_decoder: unknown precision %d", d->precision);
     ICD_CHECK_ARG(d->enc != nullptr, "attention_decoder(fp32): enc is required (bf16-stored features need ICD_PREC_BF16)");
+    IcdSimpleWsScope ws_scope(d->tc_ws, d->tc_ws_bytes);        // ICD_PREC_FP32X3: operand splits live in the caller's arena
     const int B = d->B, T = d->T, P = d->P, C = d->C, A = d->A, D = d->D, E = d->E, V = d->V;
     const int NZ = A + C + 4 * D;
     const int prec = d->precision;
@@ -141,6 +153,7 @@ extern "C" int icd_attention_decoder_bwd(const icd_att_desc_t* d, void* stream) 
     ICD_TRY(check_common(d));
     cudaStream_t s = icd_stream(stream);
     if (d->precision == ICD_PREC_BF16) return icd_attention_decoder_bwd_bf16(d, s);
+    IcdSimpleWsScope ws_scope(d->tc_ws, d->tc_ws_bytes);
     const int B = d->B, T = d->T, P = d->P, C = d->C, A = d->A, D = d->D, E = d->E, V = d->V;
     const int NZ = A + C + 4 * D;
     const int prec = d->precision;

@@ -21,12 +21,18 @@ extern "C" int icd_gemm(const icd_gemm_desc_t* d, void* stream) {
     return -1;
 }
 
+// workspace the internal helper hands to the tensor-core tiers (set by the decoder entry points from desc->tc_ws for the
+// duration of one call; thread-local, so concurrent callers on different host threads do not interfere)
+static thread_local void* g_simple_ws = nullptr;
+static thread_local int64_t g_simple_ws_bytes = 0;
+void icd_gemm_simple_set_ws(void* ws, int64_t bytes) { g_simple_ws = ws; g_simple_ws_bytes = bytes; }
+
 int icd_gemm_simple(int prec, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
                     float* C, int64_t ldc, int M, int N, int K, const float* bias1, const float* bias2,
                     const float* add1, int64_t ld1, const float* add2, int64_t ld2, const uint8_t* row_mask,
                     float beta, cudaStream_t s, int flags) {
     icd_gemm_desc_t d;
-    d.flags = flags; d.ws = nullptr; d.ws_bytes = 0;
+    d.flags = flags; d.ws = g_simple_ws; d.ws_bytes = g_simple_ws_bytes;
     d.A = A; d.sam = sam; d.sak = sak; d.B = B; d.sbn = sbn; d.sbk = sbk; d.C = C; d.ldc = ldc;
     d.M = M; d.N = N; d.K = K; d.bias1 = bias1; d.bias2 = bias2; d.add1 = add1; d.ld1 = ld1;
     d.add2 = add2; d.ld2 = ld2; d.row_mask = row_mask; d.beta = beta; d.precision = prec;

@@ -513,8 +513,8 @@ __global__ void split3_rows_kernel(const float* __restrict__ src, long long s_r,
         else            { d[0] = t[0]; d[seg] = t[1]; d[2 * seg] = t[0]; d[3 * seg] = t[2]; d[4 * seg] = t[0]; d[5 * seg] = t[1]; }
     }
 }
-// MN-major source ([K][MN] rows): dst[(s*K + k)*ldd + m] = term_s(src[k*s_k + m])
-__global__ void split3_mn_kernel(const float* __restrict__ src, long long s_k, int K, int mn,
+// MN-major source ([K][MN] rows): dst[(s*seg + k)*ldd + m] = term_s(src[k*s_k + m])   (seg >= K: rows per segment)
+__global__ void split3_mn_kernel(const float* __restrict__ src, long long s_k, int K, int mn, int seg,
                                  __nv_bfloat16* __restrict__ dst, long long ldd, int which) {
     const long long total = (long long)K * mn;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -523,7 +523,7 @@ __global__ void split3_mn_kernel(const float* __restrict__ src, long long s_k, i
         split3(src[k * s_k + m], t[0], t[1], t[2]);
         const int pa[6] = {0, 0, 1, 0, 2, 1}, pb[6] = {0, 1, 0, 2, 0, 1};
 #pragma unroll
-        for (int sgm = 0; sgm < 6; ++sgm) dst[((long long)sgm * K + k) * ldd + m] = t[which == 0 ? pa[sgm] : pb[sgm]];
+        for (int sgm = 0; sgm < 6; ++sgm) dst[((long long)sgm * seg + k) * ldd + m] = t[which == 0 ? pa[sgm] : pb[sgm]];
     }
 }
 
@@ -744,9 +744,9 @@ int icd_split3_bf16(const float* src, int64_t s_r, int rows, int cols, void* dst
 }
 
 int64_t icd_gemm_x3_ws_bytes(int M, int N, int K) {
-    const int64_t a = up256(std::max((int64_t)M * 6 * up8(K), (int64_t)6 * K * up8(M)) * 2);
-    const int64_t b = up256(std::max((int64_t)N * 6 * up8(K), (int64_t)6 * K * up8(N)) * 2);
-    return a + b + up256(icd_gemm_bf16_splitk_floats(M, N, 6 * (int)up8(K)) * 4);
+    const int64_t a = up256((int64_t)up8(M) * 6 * up8(K) * 2);
+    const int64_t b = up256((int64_t)up8(N) * 6 * up8(K) * 2);
+    return a + b + up256(std::max(icd_gemm_bf16_splitk_floats(M, N, 6 * (int)up8(K)), icd_gemm_bf16_splitk_floats(M, N, 6 * K)) * 4);
 }
 
 int icd_gemm_x3_launch(const icd_gemm_desc_t* d, cudaStream_t s) {
@@ -758,39 +758,32 @@ int icd_gemm_x3_launch(const icd_gemm_desc_t* d, cudaStream_t s) {
     ICD_CHECK_ARG(d->ws && d->ws_bytes >= need, "gemm: ICD_PREC_FP32X3 needs %lld bytes of workspace (icd_gemm_ws_bytes), got %lld",
                   (long long)need, (long long)d->ws_bytes);
     const int a_mn = (d->sak != 1), b_mn = (d->sbk != 1);
-    const int64_t a_bytes = up256(std::max((int64_t)M * 6 * up8(K), (int64_t)6 * K * up8(M)) * 2);
-    const int64_t b_bytes = up256(std::max((int64_t)N * 6 * up8(K), (int64_t)6 * K * up8(N)) * 2);
+    const int64_t a_bytes = up256((int64_t)up8(M) * 6 * up8(K) * 2);
+    const int64_t b_bytes = up256((int64_t)up8(N) * 6 * up8(K) * 2);
     char* a16 = reinterpret_cast<char*>(d->ws);
     char* b16 = a16 + a_bytes;
     float* sk = reinterpret_cast<float*>(b16 + b_bytes);
     const int seg = (int)up8(K);
-    int64_t lda, ldb; int Kx;
+    // both operands must agree on the K' layout: K-major segments are padded to seg = up8(K) columns; an MN-major operand
+    // uses K rows per segment when its partner is MN-major too, and seg rows (pad rows zeroed) when the majors differ
+    const bool mixed = (a_mn != b_mn);
+    const int mn_seg = mixed ? seg : K;
+    const int Kx = (a_mn && b_mn) ? 6 * K : 6 * seg;
+    int64_t lda, ldb;
     auto split_mn = [&](const float* src, int64_t s_k, int mn, void* dst, int64_t ldd, int which) -> int {
+        if (mn_seg != K) ICD_CUDA(cudaMemsetAsync(dst, 0, (size_t)6 * mn_seg * ldd * 2, s));
         const long long total = (long long)K * mn;
         long long blocks = (total + 255) / 256;
         if (blocks > ICD_NUM_SMS * 16) blocks = ICD_NUM_SMS * 16;
-        split3_mn_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, s_k, K, mn, reinterpret_cast<__nv_bfloat16*>(dst), ldd, which);
+        split3_mn_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, s_k, K, mn, mn_seg, reinterpret_cast<__nv_bfloat16*>(dst), ldd, which);
         ICD_LAUNCH_CHECK();
         return 0;
     };
-    // both operands must agree on the K' layout: K-major segments are padded to seg = up8(K), MN-major ones are not, so
-    // when the majors differ the MN-major operand is also laid out with seg-row segments (pad rows zeroed)
-    const bool mixed = (a_mn != b_mn);
-    if (!a_mn && !b_mn) Kx = 6 * seg; else if (a_mn && b_mn) Kx = 6 * K; else Kx = 6 * seg;
     if (!a_mn) { lda = 6LL * seg; ICD_TRY(icd_split3_bf16(d->A, d->sam, M, K, a16, 0, s)); }
-    else {
-        lda = up8(M);
-        if (mixed) ICD_CUDA(cudaMemsetAsync(a16, 0, (size_t)6 * seg * lda * 2, s));
-        ICD_TRY(split_mn(d->A, d->sak, M, a16, lda, 0));
-    }
+    else { lda = up8(M); ICD_TRY(split_mn(d->A, d->sak, M, a16, lda, 0)); }
     if (!b_mn) { ldb = 6LL * seg; ICD_TRY(icd_split3_bf16(d->B, d->sbn, N, K, b16, 1, s)); }
-    else {
-        ldb = up8(N);
-        if (mixed) ICD_CUDA(cudaMemsetAsync(b16, 0, (size_t)6 * seg * ldb * 2, s));
-        ICD_TRY(split_mn(d->B, d->sbk, N, b16, ldb, 1));
-    }
-    ICD_CHECK_ARG(!mixed || seg == K, "gemm(FP32X3): mixed operand majors need K %% 8 == 0 (K=%d)", K);
+    else { ldb = up8(N); ICD_TRY(split_mn(d->B, d->sbk, N, b16, ldb, 1)); }
     return icd_gemm_bf16_ex(a16, lda, a_mn, b16, ldb, b_mn, d->C, d->ldc, M, N, Kx, d->bias1, d->bias2, d->add1, d->ld1,
                             d->add2, d->ld2, d->row_mask, d->beta, s, nullptr, 0, sk,
-                            icd_gemm_bf16_splitk_floats(M, N, 6 * seg));
+                            icd_gemm_bf16_splitk_floats(M, N, Kx));
 }
