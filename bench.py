@@ -467,9 +467,11 @@ def main():
     if sampler:
         sampler.wait_ready()
     n_warm = max(args.warmup, 6)                        # >= 3 required; 6 lets the caching allocator reach its steady state
+    ops.prof_enable(True)                               # the library creates its timing events lazily: do that during warm-up
     for _ in range(n_warm):
         train_step(enc_d, caps_d)
     barrier()
+    ops.prof_collect()                                  # discard the warm-up samples (the events stay allocated)
     import gc
     gc.collect()
     gc.disable()                    # a cyclic-GC pause of the launching thread inside the timed region starves the GPU queue

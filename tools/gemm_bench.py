@@ -14,6 +14,7 @@ __graft_entry__.build()
 from icd_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda:0")
+PROFILE = "--profile" in sys.argv          # one warm-up + one launch per shape (for ncu --set full)
 B, T, P, C, A, D, E, V = 512, 24, 196, 2048, 512, 512, 512, 9490
 NZ = A + C + 4 * D
 
@@ -28,7 +29,9 @@ def run(name, M, N, K, a_mn=False, b_mn=False, fp32=True, bf16=False, mask=False
               bias1=torch.randn(N, device=dev) if bias else None,
               add1=torch.randn(M, N, device=dev) if add else None,
               row_mask=torch.ones(M, device=dev, dtype=torch.uint8) if mask else None)
-    for _ in range(3):
+    if PROFILE:
+        iters = 1
+    for _ in range(1 if PROFILE else 3):
         ops.gemm_bf16(a, b, M, N, K, **kw)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
