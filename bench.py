@@ -509,11 +509,18 @@ def main():
             ready = [torch.cuda.Event() for _ in range(2)]
             done = [torch.cuda.Event() for _ in range(2)]
 
+            h2d_ev = []
+            trace = []
+
             def prefetch(i):
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(done[i % 2])            # buffer free again?
+                    e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e_a.record(copy_stream)
                     bufs[i % 2][0].copy_(enc_host, non_blocking=True)
                     bufs[i % 2][1].copy_(caps_h, non_blocking=True)
+                    e_b.record(copy_stream)
+                    h2d_ev.append((e_a, e_b))
                     ready[i % 2].record(copy_stream)
 
             loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()       # pinned landing buffer for the step losses
@@ -534,6 +541,8 @@ def main():
                     torch.cuda.current_stream().wait_event(ready[i % 2])
                     l = train_step(*bufs[i % 2])
                     done[i % 2].record()
+                    if os.environ.get("ICD_BENCH_E2E_TRACE"):
+                        ev = torch.cuda.Event(enable_timing=True); ev.record(); trace.append((time.perf_counter(), ev))
                     if i >= 1:                                   # read the PREVIOUS step's loss (its slot is reused at i+1)
                         loss_ready[(i - 1) % 2].synchronize()
                         out.append(float(loss_host[(i - 1) % 2]))
@@ -554,6 +563,13 @@ def main():
             if world > 1:
                 dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
             del bufs
+            if trace:
+                tr = trace[-n_steps:]
+                print("e2e trace: gpu step deltas (ms)", [round(tr[j][1].elapsed_time(tr[j + 1][1]), 2) for j in range(len(tr) - 1)],
+                      "host issue deltas (ms)", [round(1e3 * (tr[j + 1][0] - tr[j][0]), 2) for j in range(len(tr) - 1)],
+                      "ev2->first", round(ev2.elapsed_time(tr[0][1]), 2), "last->ev3", round(tr[-1][1].elapsed_time(ev3), 2), file=sys.stderr)
+            h2d_ms = [a.elapsed_time(b) for a, b in h2d_ev[-n_steps:]]
+            e2e_run.last_h2d_ms = sum(h2d_ms) / max(len(h2d_ms), 1)
             return float(ms2.item())
 
         # headline: features stored bf16 on the host (BASELINE.json configs[2] allows bf16-stored features; the bf16 tier
@@ -566,6 +582,7 @@ def main():
                "h2d_bytes_per_step": int(main_bytes), "d2h_bytes_per_step": 4,
                "ms_per_step": ms_main / args.steps,
                "host_feature_dtype": "bf16" if host16 else "fp32", "numa_node_rank0": numa_node,
+               "h2d_ms_per_step": e2e_run.last_h2d_ms,
                "note": "per GPU: pinned host features + int64 captions copied H2D every step on a side stream "
                        "(double-buffered); every step's loss copied D2H to pinned memory and read on the host one step "
                        "later (pipelined read-back)"}
