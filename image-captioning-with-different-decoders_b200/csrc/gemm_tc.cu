@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 
 namespace {
@@ -50,6 +51,8 @@ struct KArgs {
     int a_mn, b_mn;                           // 1: operand is MN-major in memory
     int splits, kb_per_split;                 // split-K: work unit = (tile, slice)
     float* partial;                           // [splits][M][N] raw accumulators when splits > 1
+    int cluster;                              // 1, or 2: CTA pairs (thread-block cluster of 2 along M) share every B tile —
+                                              // each CTA fetches half of it and TMA-multicasts it into both shared memories
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -79,6 +82,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 :: "r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -252,15 +272,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const EpiArgs& e = p.e;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // cluster = 2: the pair works on m-tiles (2*mp, 2*mp + 1) of the same n-tile ("super tile"); both CTAs walk the same
+    // unit sequence, so their pipelines run in lock step through the shared empty barriers
+    const int CL = p.cluster;
+    const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
     const int tiles_m = (e.M + BM - 1) / BM, tiles_n = (e.N + BN - 1) / BN;
-    const int num_tiles = tiles_m * tiles_n;
+    const int tiles_mc = (tiles_m + CL - 1) / CL;
+    const int num_tiles = tiles_mc * tiles_n;                            // super tiles
     const int nkb = (e.K + BK - 1) / BK;
     const int num_units = num_tiles * p.splits;
+    const int unit0 = blockIdx.x / CL, unit_stride = gridDim.x / CL;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB) : "memory");
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, (uint32_t)CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -271,6 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // the peer's barriers must be initialised before any multicast can target them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     // PDL: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail;
@@ -282,12 +309,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // =================================== TMA producer ===================================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+            for (int unit = unit0; unit < num_units; unit += unit_stride) {
                 const int tile = unit % num_tiles, slice = unit / num_tiles;
-                const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+                const int m0 = ((tile % tiles_mc) * CL + (int)crank) * BM, n0 = (tile / tiles_mc) * BN;
                 const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);        // cluster = 2: BOTH CTAs have consumed this slot
                     const uint32_t fb = full0 + 8 * stage;
                     mbar_arrive_expect_tx(fb, C_::STAGE_BYTES);
                     const uint32_t a_dst = sA + stage * A_BYTES, b_dst = sB + stage * C_::B_BYTES;
@@ -296,10 +323,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * MN_BLOCK_BYTES, &tmA, m0 + 64 * j, kb * BK, fb);
                     }
-                    if (!p.b_mn) tma_load_2d(b_dst, &tmB, kb * BK, n0, fb);
-                    else {
+                    if (CL == 1) {
+                        if (!p.b_mn) tma_load_2d(b_dst, &tmB, kb * BK, n0, fb);
+                        else {
 #pragma unroll
-                        for (int j = 0; j < (BN + 63) / 64; ++j) tma_load_2d(b_dst + j * MN_BLOCK_BYTES, &tmB, n0 + 64 * j, kb * BK, fb);
+                            for (int j = 0; j < (BN + 63) / 64; ++j) tma_load_2d(b_dst + j * MN_BLOCK_BYTES, &tmB, n0 + 64 * j, kb * BK, fb);
+                        }
+                    } else {
+                        // this CTA fetches its half of the B tile and multicasts it into both CTAs' shared memory; the
+                        // transaction bytes land on the full barrier at the same offset in each CTA
+                        if (!p.b_mn) tma_load_2d_mc(b_dst + crank * (C_::B_BYTES / 2), &tmB, kb * BK, n0 + (int)crank * (BN / 2), fb, (uint16_t)0x3);
+                        else {
+#pragma unroll
+                            for (int j = 0; j < BN / 128; ++j) {
+                                const int blk = (int)crank * (BN / 128) + j;
+                                tma_load_2d_mc(b_dst + blk * MN_BLOCK_BYTES, &tmB, n0 + 64 * blk, kb * BK, fb, (uint16_t)0x3);
+                            }
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -312,7 +352,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t idesc = C_::IDESC | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16);
         const uint64_t a_kstep = p.a_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);   // descriptor units of 16 B
         const uint64_t b_kstep = p.b_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
-        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        for (int unit = unit0; unit < num_units; unit += unit_stride) {
             const int slice = unit / num_tiles;
             const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);              // epilogue has drained this accumulator
@@ -328,7 +368,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int k = 0; k < BK / UMMA_K; ++k)
                         tc_mma_f16(d_tmem, adesc + (uint64_t)k * a_kstep, bdesc + (uint64_t)k * b_kstep, idesc,
                                    (kb > kb0 || k > 0) ? 1u : 0u);
-                    tc_commit(empty0 + 8 * stage);                    // smem slot reusable once these MMAs retire
+                    if (CL == 1) tc_commit(empty0 + 8 * stage);       // smem slot reusable once these MMAs retire
+                    else tc_commit_mc(empty0 + 8 * stage, (uint16_t)0x3);   // ... signalled to both producers of the pair
                     if (kb == kb1 - 1) tc_commit(tfull0 + 8 * acc);   // accumulator complete -> epilogue
                 }
                 __syncwarp();
@@ -343,9 +384,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* sE = sEpi + (warp - 2) * 32 * EPI_LD;
         int acc = 0; uint32_t acc_phase = 0;
         constexpr int NCHUNK = BN / 32;
-        for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        for (int unit = unit0; unit < num_units; unit += unit_stride) {
             const int tile = unit % num_tiles, slice = unit / num_tiles;
-            const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+            const int m0 = ((tile % tiles_mc) * CL + (int)crank) * BM, n0 = (tile / tiles_mc) * BN;
             EpiArgs ee = e;
             if (p.splits > 1) {                                       // raw partial tile, epilogue deferred
                 ee.C = p.partial + (long long)slice * e.M * e.N; ee.ldc = e.N;
@@ -386,9 +427,222 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // the peer may still multicast into this CTA's shared memory / barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                     :: "r"(tmem_base), "r"((uint32_t)C_::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant: tcgen05.mma.cta_group::2.  Two CTAs of a thread-block cluster (same TPC) compute ONE 256 x BN tile:
+// each CTA stages its own 128 rows of A and only HALF of the B tile (BN/2 rows of N); the MMA, issued by one thread of
+// the leader CTA (cluster rank 0), reads A and B from both shared memories and writes rows 0-127 of the accumulator into
+// the leader's TMEM and rows 128-255 into the peer's.  Per SM and k-block this moves 16 KB (A) + BN/2 * 128 B (B half)
+// instead of 16 KB + BN * 128 B — the single-CTA kernel saturates the SM's L2 ingress at ~65 % tensor-pipe utilisation.
+//   * TMA loads of BOTH CTAs complete on the LEADER's full barrier (cp.async.bulk.tensor ... cta_group::2, barrier
+//     address mapped into the leader with mapa); the leader's producer arms it with the bytes of both CTAs;
+//   * tcgen05.commit.cta_group::2 ... multicast::cluster releases the smem slot in both CTAs (each producer waits on its
+//     own empty barrier) and announces the finished accumulator on both CTAs' tmem-full barriers;
+//   * every epilogue warp of both CTAs arrives on the LEADER's tmem-empty barrier (remote mbarrier.arrive), which the MMA
+//     thread waits on before reusing an accumulator stage.
+// Everything else (roles, epilogue, split-K, operand majors, PDL) is as in gemm_tc_kernel.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar_cluster_addr) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+template <int BN>
+struct Cfg2 {
+    static constexpr int BH_BYTES = (BN / 2) * BK * 2;                  // this CTA's half of the B tile
+    static constexpr int STAGE_BYTES = A_BYTES + BH_BYTES;              // per CTA
+    static constexpr int STAGES = BN == 256 ? 6 : 8;
+    static constexpr int EPI_BYTES = NUM_EPI_WARPS * 32 * EPI_LD * 4;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+    static constexpr int TMEM_COLS = 2 * BN;
+    // UMMA M = 256 (m_dim = 16), N = BN
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KArgs p) {
+    using C_ = Cfg2<BN>;
+    constexpr int STAGES = C_::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sA = base, sB = base + STAGES * A_BYTES;
+    float* sEpi = reinterpret_cast<float*>(gbase + STAGES * C_::STAGE_BYTES);
+    const uint32_t bars = base + STAGES * C_::STAGE_BYTES + C_::EPI_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + STAGES * C_::STAGE_BYTES + C_::EPI_BYTES + 16 * STAGES + 32);
+
+    const EpiArgs& e = p.e;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_ctarank();                           // 0 = leader
+    const int tiles_m = (e.M + BM - 1) / BM, tiles_n = (e.N + BN - 1) / BN;
+    const int tiles_mc = (tiles_m + 1) / 2;
+    const int num_tiles = tiles_mc * tiles_n;                            // 256 x BN super tiles
+    const int nkb = (e.K + BK - 1) / BK;
+    const int num_units = num_tiles * p.splits;
+    const int unit0 = blockIdx.x / 2, unit_stride = gridDim.x / 2;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB) : "memory");
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 2 * NUM_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)C_::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();
+
+    if (warp == 0) {
+        // =================================== TMA producer (both CTAs) ===================================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int unit = unit0; unit < num_units; unit += unit_stride) {
+                const int tile = unit % num_tiles, slice = unit / num_tiles;
+                const int m0 = ((tile % tiles_mc) * 2 + (int)crank) * BM, n0 = (tile / tiles_mc) * BN + (int)crank * (BN / 2);
+                const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t fb_leader = mapa_u32(full0 + 8 * stage, 0);
+                    if (crank == 0) mbar_arrive_expect_tx(full0 + 8 * stage, 2 * C_::STAGE_BYTES);   // bytes of BOTH CTAs
+                    const uint32_t a_dst = sA + stage * A_BYTES, b_dst = sB + stage * C_::BH_BYTES;
+                    if (!p.a_mn) tma_load_2d_2sm(a_dst, &tmA, kb * BK, m0, fb_leader);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(a_dst + j * MN_BLOCK_BYTES, &tmA, m0 + 64 * j, kb * BK, fb_leader);
+                    }
+                    if (!p.b_mn) tma_load_2d_2sm(b_dst, &tmB, kb * BK, n0, fb_leader);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(b_dst + j * MN_BLOCK_BYTES, &tmB, n0 + 64 * j, kb * BK, fb_leader);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =================================== MMA issuer (leader CTA only) ===================================
+        if (crank == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            const uint32_t idesc = C_::IDESC | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16);
+            const uint64_t a_kstep = p.a_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
+            const uint64_t b_kstep = p.b_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
+            for (int unit = unit0; unit < num_units; unit += unit_stride) {
+                const int slice = unit / num_tiles;
+                const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);          // the epilogues of BOTH CTAs have drained this stage
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);              // both CTAs' tiles have landed
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint64_t adesc = make_smem_desc(sA + stage * A_BYTES, p.a_mn);
+                        const uint64_t bdesc = make_smem_desc(sB + stage * C_::BH_BYTES, p.b_mn);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            tc_mma_f16_2sm(d_tmem, adesc + (uint64_t)k * a_kstep, bdesc + (uint64_t)k * b_kstep, idesc,
+                                           (kb > kb0 || k > 0) ? 1u : 0u);
+                        tc_commit_2sm(empty0 + 8 * stage, (uint16_t)0x3);                 // slot free in both CTAs
+                        if (kb == kb1 - 1) tc_commit_2sm(tfull0 + 8 * acc, (uint16_t)0x3);   // accumulator ready in both
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // =================================== epilogue warps 2..9 (both CTAs, own TMEM half) ===================================
+        const int q = warp & 3;
+        const int cg = (warp - 2) >> 2;
+        float* sE = sEpi + (warp - 2) * 32 * EPI_LD;
+        int acc = 0; uint32_t acc_phase = 0;
+        constexpr int NCHUNK = BN / 32;
+        for (int unit = unit0; unit < num_units; unit += unit_stride) {
+            const int tile = unit % num_tiles, slice = unit / num_tiles;
+            const int m0 = ((tile % tiles_mc) * 2 + (int)crank) * BM, n0 = (tile / tiles_mc) * BN;
+            EpiArgs ee = e;
+            if (p.splits > 1) {
+                ee.C = p.partial + (long long)slice * e.M * e.N; ee.ldc = e.N;
+                ee.bias1 = ee.bias2 = ee.add1 = ee.add2 = nullptr; ee.row_mask = nullptr; ee.beta = 0.f; ee.C16 = nullptr;
+                ee.vec = (e.N % 4 == 0) ? 4 : ((e.N % 2 == 0) ? 2 : 1);
+            }
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            tc_fence_after();
+            const int mrow0 = m0 + q * 32;
+            const uint32_t tempty_leader = mapa_u32(tempty0 + 8 * acc, 0);
+            bool released = false;
+#pragma unroll 1
+            for (int c = cg; c < NCHUNK; c += 2) {
+                const int nb = n0 + c * 32;
+                const bool last = (c + 2 >= NCHUNK);
+                if (nb < e.N && mrow0 < e.M) {
+                    uint32_t v[32];
+                    tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+                    tc_wait_ld();
+                    if (last) {
+                        tc_fence_before();
+                        if (lane == 0) mbar_arrive_remote(tempty_leader);
+                        released = true;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sE[lane * EPI_LD + j] = __uint_as_float(v[j]);
+                    __syncwarp();
+                    epilogue_store_chunk(sE, lane, mrow0, nb, ee);
+                    __syncwarp();
+                }
+            }
+            if (!released) {
+                tc_fence_before();
+                if (lane == 0) mbar_arrive_remote(tempty_leader);
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;"
                      :: "r"(tmem_base), "r"((uint32_t)C_::TMEM_COLS) : "memory");
     }
 }
@@ -571,10 +825,39 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KArgs& k, int u
         ICD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
         attr_set = true;
     }
-    const int grid = units < ICD_NUM_SMS ? units : ICD_NUM_SMS;
-    ICD_CUDA(icd_launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), (size_t)Cfg<BN>::SMEM, s, tmA, tmB, k));
+    if (k.cluster > 1) {                       // units = super tiles x slices; one CTA pair per unit slot
+        const int pairs = units < ICD_NUM_SMS / 2 ? units : ICD_NUM_SMS / 2;
+        ICD_CUDA(icd_launch_pdl_cluster(gemm_tc_kernel<BN>, dim3(2 * pairs), dim3(NUM_THREADS), (size_t)Cfg<BN>::SMEM, s, 2u,
+                                        tmA, tmB, k));
+    } else {
+        const int grid = units < ICD_NUM_SMS ? units : ICD_NUM_SMS;
+        ICD_CUDA(icd_launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), (size_t)Cfg<BN>::SMEM, s, tmA, tmB, k));
+    }
     ICD_LAUNCH_CHECK();
     return 0;
+}
+
+template <int BN>
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const KArgs& k, int units, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        ICD_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<BN>::SMEM));
+        attr_set = true;
+    }
+    const int pairs = units < ICD_NUM_SMS / 2 ? units : ICD_NUM_SMS / 2;
+    ICD_CUDA(icd_launch_pdl_cluster(gemm_tc2_kernel<BN>, dim3(2 * pairs), dim3(NUM_THREADS), (size_t)Cfg2<BN>::SMEM, s, 2u,
+                                    tmA, tmB, k));
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+// Pairing mode of the contraction (ICD_GEMM_PAIR / icd_gemm_set_pair_mode):
+//   0 = single-CTA tiles only; 1 = CTA pairs sharing the B tile by TMA multicast (cta_group::1 MMAs);
+//   2 = CTA pairs computing one 256 x BN tile with tcgen05.mma.cta_group::2 (default where the shape allows it)
+int g_pair_mode = -1;
+int pair_mode() {
+    if (g_pair_mode < 0) { const char* e = getenv("ICD_GEMM_PAIR"); g_pair_mode = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
+    return g_pair_mode;
 }
 
 // tile width / split-K plan from a small cost model (SM clocks): one persistent wave of work units should cover the
@@ -611,6 +894,7 @@ Plan make_plan(int M, int N, int K, bool allow_split) {
 }  // namespace
 
 extern "C" int icd_has_tensor_core_gemm(void) { return 1; }
+extern "C" int icd_gemm_set_pair_mode(int mode) { const int old = pair_mode(); if (mode >= 0 && mode <= 2) g_pair_mode = mode; return old; }
 
 int icd_convert_bf16(const float* src, int64_t s_r, int64_t s_c, int rows, int cols, void* dst, int64_t ldd,
                      cudaStream_t s) {
@@ -650,9 +934,12 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
     if (pl.splits > 1 && (int64_t)pl.splits * M * N > splitk_ws_floats) {
         pl.splits = 1; pl.kb_per_split = (K + BK - 1) / BK;
     }
+    const int tiles_m = (M + BM - 1) / BM;
+    const int mode = (pl.bn >= 128 && tiles_m >= 2) ? pair_mode() : 0;
+    const int cluster = mode ? 2 : 1;
     CUtensorMap tmA, tmB;
     ICD_TRY(make_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(A16), lda, M, K, BM, a_mn));
-    ICD_TRY(make_tmap(&tmB, reinterpret_cast<const __nv_bfloat16*>(B16), ldb, N, K, pl.bn, b_mn));
+    ICD_TRY(make_tmap(&tmB, reinterpret_cast<const __nv_bfloat16*>(B16), ldb, N, K, pl.bn / cluster, b_mn));
     KArgs k;
     EpiArgs& e = k.e;
     e.C = C; e.ldc = ldc; e.M = M; e.N = N; e.K = K; e.bias1 = bias1; e.bias2 = bias2;
@@ -667,12 +954,17 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
     e.vec = fits(4) ? 4 : (fits(2) ? 2 : 1);
     k.a_mn = a_mn ? 1 : 0; k.b_mn = b_mn ? 1 : 0;
     k.splits = pl.splits; k.kb_per_split = pl.kb_per_split; k.partial = splitk_ws;
-    const int tiles = ((M + BM - 1) / BM) * ((N + pl.bn - 1) / pl.bn);
+    k.cluster = cluster;
+    const int tiles = ((tiles_m + cluster - 1) / cluster) * ((N + pl.bn - 1) / pl.bn);      // super tiles when paired
     const int units = tiles * pl.splits;
-    switch (pl.bn) {
-        case 256: ICD_TRY(launch<256>(tmA, tmB, k, units, s)); break;
-        case 128: ICD_TRY(launch<128>(tmA, tmB, k, units, s)); break;
-        default:  ICD_TRY(launch<64>(tmA, tmB, k, units, s)); break;
+    if (mode == 2) {
+        if (pl.bn == 256) ICD_TRY(launch2<256>(tmA, tmB, k, units, s)); else ICD_TRY(launch2<128>(tmA, tmB, k, units, s));
+    } else {
+        switch (pl.bn) {
+            case 256: ICD_TRY(launch<256>(tmA, tmB, k, units, s)); break;
+            case 128: ICD_TRY(launch<128>(tmA, tmB, k, units, s)); break;
+            default:  ICD_TRY(launch<64>(tmA, tmB, k, units, s)); break;
+        }
     }
     if (pl.splits > 1) {
         const long long work = ((long long)M * N + 3) / 4;

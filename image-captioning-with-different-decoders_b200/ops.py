@@ -232,6 +232,11 @@ def cross_entropy_fwd_bwd(logits, targets, inv_count, want_grad=True):
     return row_loss, d_logits
 
 
+def gemm_set_pair_mode(mode):
+    """0 single-CTA tiles, 1 CTA pairs + TMA multicast of B, 2 cta_group::2 pairs (default); returns the previous mode"""
+    return int(lib().icd_gemm_set_pair_mode(int(mode)))
+
+
 def launch_count():
     """Kernels launched by libicd_b200.so in this process so far."""
     return int(lib().icd_launch_count())

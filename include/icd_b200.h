@@ -45,6 +45,9 @@ ICD_API int icd_sizeof_att_desc(void);               /* sizeof(icd_att_desc_t)  
 ICD_API int icd_sizeof_base_desc(void);
 ICD_API int icd_sizeof_beam_desc(void);
 ICD_API int icd_has_tensor_core_gemm(void);          /* 1 if the tcgen05/TMA GEMM path was compiled in     */
+/* Tile pairing of the tensor-core contraction (also env ICD_GEMM_PAIR): 0 single-CTA tiles, 1 CTA pairs sharing the B tile
+ * by TMA multicast, 2 CTA pairs on one 256-row tile with tcgen05.mma.cta_group::2 (default).  Returns the previous mode. */
+ICD_API int icd_gemm_set_pair_mode(int mode);
 ICD_API int64_t icd_launch_count(void);              /* kernels launched by this library so far (process-wide) */
 
 /* Optional device-side timing of the attention-step kernels (bench.py's roofline line).  When enabled every

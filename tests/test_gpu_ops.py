@@ -278,10 +278,20 @@ def test_attention_step_bf16_features_matches_oracle_on_rounded_features(cuda, R
     H.assert_close_norm(d_wf, wf64.grad, 2e-5, "d_w_full")
 
 
+@pytest.fixture(params=[2, 1, 0], ids=["cta_group2_pairs", "multicast_pairs", "single_cta"])
+def pair_mode(request):
+    """Run under every tile-pairing mode of the tensor-core contraction (icd_gemm_set_pair_mode)."""
+    ops = _ops()
+    old = ops.gemm_set_pair_mode(request.param)
+    yield request.param
+    ops.gemm_set_pair_mode(old)
+
+
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 0), (0, 1), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(512, 2048, 2048), (512, 512, 4608), (300, 200, 1000), (128, 64, 64),
-                                   (2048, 520, 12288), (96, 9490, 136), (512, 2048, 40000)])
-def test_gemm_bf16_operand_majors_tiles_and_split_k(cuda, M, N, K, a_mn, b_mn):
+                                   (2048, 520, 12288), (96, 9490, 136), (512, 2048, 40000), (1000, 4608, 512),
+                                   (640, 9490, 512)])
+def test_gemm_bf16_operand_majors_tiles_and_split_k(cuda, pair_mode, M, N, K, a_mn, b_mn):
     """Every operand-major combination of the tcgen05 kernel (K-major = rows of K, MN-major = rows of M/N, consumed
     without a transpose), across the BN = 256/128/64 tile plans and the deterministic split-K plans the shapes select
     (per-step contractions with M = batch, weight-gradient contractions with K = tokens)."""
