@@ -855,8 +855,12 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const KArgs& k, int 
 //   0 = single-CTA tiles only; 1 = CTA pairs sharing the B tile by TMA multicast (cta_group::1 MMAs);
 //   2 = CTA pairs computing one 256 x BN tile with tcgen05.mma.cta_group::2 (default where the shape allows it)
 int g_pair_mode = -1;
+bool g_pair_forced = false;               // set through icd_gemm_set_pair_mode / ICD_GEMM_PAIR: apply the mode to every eligible shape
 int pair_mode() {
-    if (g_pair_mode < 0) { const char* e = getenv("ICD_GEMM_PAIR"); g_pair_mode = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }
+    if (g_pair_mode < 0) {
+        const char* e = getenv("ICD_GEMM_PAIR");
+        if (e && e[0] >= '0' && e[0] <= '2') { g_pair_mode = e[0] - '0'; g_pair_forced = true; } else g_pair_mode = 2;
+    }
     return g_pair_mode;
 }
 
@@ -894,7 +898,13 @@ Plan make_plan(int M, int N, int K, bool allow_split) {
 }  // namespace
 
 extern "C" int icd_has_tensor_core_gemm(void) { return 1; }
-extern "C" int icd_gemm_set_pair_mode(int mode) { const int old = pair_mode(); if (mode >= 0 && mode <= 2) g_pair_mode = mode; return old; }
+extern "C" int icd_gemm_set_pair_mode(int mode) {
+    const int old = g_pair_forced ? pair_mode() : -1;
+    pair_mode();
+    if (mode >= 0 && mode <= 2) { g_pair_mode = mode; g_pair_forced = true; }
+    else { g_pair_mode = 2; g_pair_forced = false; }          // any other value: back to the built-in policy
+    return old;
+}
 
 int icd_convert_bf16(const float* src, int64_t s_r, int64_t s_c, int rows, int cols, void* dst, int64_t ldd,
                      cudaStream_t s) {
@@ -935,7 +945,10 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
         pl.splits = 1; pl.kb_per_split = (K + BK - 1) / BK;
     }
     const int tiles_m = (M + BM - 1) / BM;
-    const int mode = (pl.bn >= 128 && tiles_m >= 2) ? pair_mode() : 0;
+    // pairing pays on long-K contractions (deeper ring: 6 stages of 32 KB instead of 4 of 48 KB, half the B traffic per SM);
+    // the K = 512 shapes are epilogue / store bound and run slightly better on independent CTAs
+    int mode = (pl.bn >= 128 && tiles_m >= 2) ? pair_mode() : 0;
+    if (mode == 2 && !g_pair_forced && (K + BK - 1) / BK < 16) mode = 0;
     const int cluster = mode ? 2 : 1;
     CUtensorMap tmA, tmB;
     ICD_TRY(make_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(A16), lda, M, K, BM, a_mn));

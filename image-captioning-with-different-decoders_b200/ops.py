@@ -233,7 +233,8 @@ def cross_entropy_fwd_bwd(logits, targets, inv_count, want_grad=True):
 
 
 def gemm_set_pair_mode(mode):
-    """0 single-CTA tiles, 1 CTA pairs + TMA multicast of B, 2 cta_group::2 pairs (default); returns the previous mode"""
+    """Force a tile-pairing mode for every eligible shape: 0 single-CTA tiles, 1 CTA pairs + TMA multicast of B,
+    2 tcgen05.mma.cta_group::2 pairs; -1 restores the built-in policy.  Returns the previous forced mode (or -1)."""
     return int(lib().icd_gemm_set_pair_mode(int(mode)))
 
 

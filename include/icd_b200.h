@@ -46,7 +46,8 @@ ICD_API int icd_sizeof_base_desc(void);
 ICD_API int icd_sizeof_beam_desc(void);
 ICD_API int icd_has_tensor_core_gemm(void);          /* 1 if the tcgen05/TMA GEMM path was compiled in     */
 /* Tile pairing of the tensor-core contraction (also env ICD_GEMM_PAIR): 0 single-CTA tiles, 1 CTA pairs sharing the B tile
- * by TMA multicast, 2 CTA pairs on one 256-row tile with tcgen05.mma.cta_group::2 (default).  Returns the previous mode. */
+ * by TMA multicast, 2 CTA pairs on one 256-row tile with tcgen05.mma.cta_group::2; any other value restores the built-in
+ * policy (cta_group::2 pairs for long-K shapes, single CTAs otherwise).  Returns the previous forced mode or -1. */
 ICD_API int icd_gemm_set_pair_mode(int mode);
 ICD_API int64_t icd_launch_count(void);              /* kernels launched by this library so far (process-wide) */
 
