@@ -1,0 +1,40 @@
+"""Attention-step kernel timing vs number of rows per launch (HBM efficiency at reduced grid sizes)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+import __graft_entry__  # noqa: E402
+
+__graft_entry__.build()
+from icd_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+P, C, A = 196, 2048, 512
+B = 1184
+enc16 = torch.randn(B, P, C, device=dev).clamp_min_(0).bfloat16()
+att16 = (torch.randn(B, P, A, device=dev) * 0.5).bfloat16()
+att_dec = torch.randn(B, A, device=dev) * 0.5
+wf = torch.randn(A, device=dev) * 0.2
+bf = torch.zeros(1, device=dev)
+fb = torch.randn(B, C, device=dev)
+for rows in (592, 512, 444, 296, 256, 148):
+    def run(lo):
+        return ops.attention_step_fwd_bf16(enc16[lo:lo + rows], att16[lo:lo + rows], att_dec[lo:lo + rows], wf, bf, fb[lo:lo + rows])
+    los = [lo for lo in range(0, B, rows) if lo + rows <= B]
+    for _ in range(3):
+        for lo in los:
+            run(lo)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 0
+    e0.record()
+    for _ in range(10):
+        for lo in los:
+            run(lo); n += 1
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / n
+    print("fwd rows=%3d  %.1f us per launch  %.0f GB/s" % (rows, us, rows * 1022736 / us / 1e3))
