@@ -24,6 +24,8 @@ from ..vocabulary import Vocabulary
 class SoftAttention(nn.Module):
     """Attention network (models/attention.py:18-61)."""
 
+    precision = "fp32"      # class-level default: instances unpickled from a reference checkpoint carry no such attribute
+
     def __init__(self, encoder_dim=2048, decoder_dim=512, attention_dim=512):
         super(SoftAttention, self).__init__()
         self.enc_att = nn.Linear(encoder_dim, attention_dim)      # :32
@@ -92,6 +94,10 @@ class AttentionDecoderParams:
 
 class AttentionDecoder(nn.Module):
     """Teacher-forced soft-attention LSTM decoder (models/attention.py:72-284)."""
+
+    # class-level defaults of the B200 additions (instances unpickled from a reference checkpoint do not have them)
+    precision = "fp32"
+    _dropout_mask_override = None
 
     def __init__(self, device, params):
         super(AttentionDecoder, self).__init__()

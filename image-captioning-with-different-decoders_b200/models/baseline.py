@@ -21,6 +21,8 @@ class BaselineDecoderParams:
 
 
 class BaselineDecoder(nn.Module):
+    precision = "fp32"      # class-level default (instances unpickled from a reference checkpoint do not carry it)
+
     def __init__(self, params):
         super().__init__()
 

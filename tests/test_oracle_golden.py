@@ -10,6 +10,7 @@ import torch
 
 import helpers as H
 from oracle import decoders as O
+from oracle import reference_import
 
 import icd_b200.models.attention as my_att
 import icd_b200.models.baseline as my_base
@@ -149,3 +150,48 @@ def test_pinning_report_present():
     rep = json.load(open(os.path.join(H.GOLDEN_DIR, "PINNING.json")))
     for name in list(H.ATT_CASES) + list(H.BASE_CASES) + list(H.BEAM_CASES):
         assert name in rep
+
+
+@pytest.mark.skipif(not reference_import.reference_available(), reason="needs the reference tree (build container only)")
+def test_reference_whole_module_checkpoint_loads_as_drop_in(tmp_path):
+    """The reference pickles whole modules (checkpoint.py:51-59).  icd_b200.checkpoint maps the pickled class paths
+    (models.attention.*, models.baseline.*, vocabulary.Vocabulary) onto the drop-in classes: same weights, same keys."""
+    import sys
+    import icd_b200.models.attention as my_att
+    import icd_b200.models.baseline as my_base
+    from icd_b200 import checkpoint as ckpt
+    from icd_b200.vocabulary import Vocabulary as MyVocab
+    ns = reference_import.load_reference()
+    case = H.ATT_CASES["att_small_ragged"]
+    ref_dec = H.build_attention_module(case, ns.AttentionDecoder, ns.AttentionDecoderParams,
+                                       reference_import.make_reference_vocab(ns, case["V"]))
+    bcase = H.BASE_CASES["base_small"]
+    ref_base = H.build_baseline_module(bcase, ns.BaselineDecoder, ns.BaselineDecoderParams)
+    opt = torch.optim.Adam(ref_dec.parameters(), lr=1e-4)
+    path = tmp_path / "basic_att_0.pth.tar"
+    # pickling needs the reference modules importable under their own names (they are parked under _icd_ref.* otherwise)
+    names = ["models", "models.attention", "models.baseline", "vocabulary"]
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        for k in names:
+            sys.modules[k] = sys.modules["_icd_ref." + k]
+        torch.save({"epoch": 0, "metrics": {"loss": [1.0]}, "encoder": None, "decoder": ref_dec,
+                    "encoder_optimizer": None, "decoder_optimizer": opt, "baseline": ref_base}, str(path))
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    chk = ckpt.load_checkpoint_file(str(path))
+    epoch, enc, dec, enc_opt, dec_opt, metrics = ckpt.unpack_checkpoint(chk)
+    assert epoch == 0 and metrics == {"loss": [1.0]}
+    assert type(dec) is my_att.AttentionDecoder and type(dec.attention) is my_att.SoftAttention
+    assert type(dec.vocab) is MyVocab and len(dec.vocab) == case["V"] and dec.vocab("<end>") == case["V"] - 2
+    assert dec.precision == "fp32" and dec._dropout_mask_override is None
+    sd_ref, sd = ref_dec.state_dict(), dec.state_dict()
+    assert list(sd) == list(sd_ref) and all(torch.equal(sd[k], sd_ref[k]) for k in sd)
+    base = chk["baseline"]
+    assert type(base) is my_base.BaselineDecoder and base.precision == "fp32"
+    assert all(torch.equal(v, ref_base.state_dict()[k]) for k, v in base.state_dict().items())
+    assert isinstance(dec_opt, torch.optim.Adam)
