@@ -44,6 +44,7 @@ extern "C" int icd_init_hidden_state(int B, int P, int C, int D, int precision, 
                                      const float* c_lin_w, const float* c_lin_b,
                                      float* mean_enc, float* h, float* c, void* stream) {
     cudaStream_t s = icd_stream(stream);
+    ICD_CHECK_ARG(precision == ICD_PREC_FP32 || precision == ICD_PREC_FP32X3, "init_hidden_state: precision %d not supported here", precision);
     // mean over pixels (:161) — same streaming kernel as the attention-weighted sum, uniform weights
     ICD_TRY(icd_weighted_pixel_sum(B, P, C, nullptr, enc, nullptr, 0, nullptr, 0, mean_enc, nullptr, nullptr, s));
     ICD_TRY(icd_gemm_simple(precision, mean_enc, C, 1, h_lin_w, C, 1, h, D, B, D, C, h_lin_b, nullptr,

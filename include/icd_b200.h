@@ -289,7 +289,9 @@ ICD_API int64_t icd_attention_decoder_ws_bytes(const icd_att_desc_t* d);
 ICD_API int icd_attention_decoder_fwd(const icd_att_desc_t* d, void* stream);
 ICD_API int icd_attention_decoder_bwd(const icd_att_desc_t* d, void* stream);
 
-/* init_hidden_state (models/attention.py:151-164): mean over pixels, h_lin, c_lin.  h, c: (B,D). */
+/* init_hidden_state (models/attention.py:151-164): mean over pixels, h_lin, c_lin.  h, c: (B,D).
+ * Stand-alone entry point (caption generation): precision must be ICD_PREC_FP32 — the tensor-core tiers need a
+ * workspace and are reached through icd_attention_decoder_fwd / icd_beam_search. */
 ICD_API int icd_init_hidden_state(int B, int P, int C, int D, int precision, const float* enc,
                           const float* h_lin_w, const float* h_lin_b,
                           const float* c_lin_w, const float* c_lin_b,
