@@ -132,7 +132,8 @@ int icd_lstm_pointwise_fwd(int rows, int D, const float* gates_pre, const float*
 int icd_lstm_pointwise_bwd(int rows, int D, const float* dh_in, const float* d_hdrop, int64_t hdrop_row_stride,
                            const uint8_t* mask, float scale, float* dc_inout,
                            const float* gates_act, const float* c_prev, const float* c_new,
-                           float* dgates_pre, int64_t ld_dg, cudaStream_t s, void* dg16 = nullptr, int64_t ld_dg16 = 0);
+                           float* dgates_pre, int64_t ld_dg, cudaStream_t s, void* dg16 = nullptr, int64_t ld_dg16 = 0,
+                           const float* dh_parts = nullptr, int n_parts = 0, int parts_rows = 0);   // deferred split-K planes of dh
 int icd_weighted_pixel_sum(int rows, int P, int C, const int32_t* img_index, const float* enc,
                            const float* alpha, int64_t ld_alpha, const float* fbeta_pre, int64_t ld_fb,
                            float* awe_raw, float* gate, float* gated, cudaStream_t s);

@@ -220,6 +220,9 @@ int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
     ICD_TRY(icd_colsum_bf16(dY16, ldY, (int64_t)BT, V, d->row_valid, d->d_fc_b, u.colsum_ws, s));
 
     // ---- BPTT ----
+    // The dh contraction (M = batch, N = D, K = NZ) runs split-K; its reduce pass is deferred into the next step's LSTM
+    // gate kernel, which sums the K-slice planes while it reads dh anyway (one launch less per step).
+    int dh_splits = 0, dh_rows = 0;            // > 0: dh of the previous iteration lives in u.splitk as dh_splits planes of dh_rows rows
     for (int t = T - 1; t >= 0; --t) {
         const int bt = d->bt_host[t];
         if (bt == 0) continue;
@@ -230,7 +233,8 @@ int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
                                        d->drop_mask ? d->drop_mask + (size_t)t * BD : nullptr, d->drop_scale,
                                        d->dc, d->gates_act + (size_t)t * B * 4 * D,
                                        d->c_all + (size_t)t * BD, d->c_all + (size_t)(t + 1) * BD,
-                                       dzt + A + C, NZ, s, at16(dz16, A + C), NZ));     // dG also emitted as bf16
+                                       dzt + A + C, NZ, s, at16(dz16, A + C), NZ,     // dG also emitted as bf16
+                                       u.splitk, dh_splits, dh_rows));
         // d_gated = dG W_ih[:, E:]           (W_ih[:, E:] stored [4D, C] = MN-major B, N = C, K = 4D)
         MMX(at16(dz16, A + C), NZ, 0, u.WihC, C, 1, d->d_gated, C, bt, C, 4 * D, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
         ICD_TRY(icd_attention_step_bwd_bf16(bt, P, C, A, u.enc, u.att_enc, zt, NZ, d->full_att_w,
@@ -240,9 +244,12 @@ int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
                                             dzt, NZ, dzt + A, NZ, d->d_e + (size_t)t * P, (int64_t)T * P,
                                             dz16, NZ, d->d_enc ? d->d_awe_all + (size_t)t * B * C : nullptr,
                                             (void*)s));                             // d att_dec | d fbeta_pre (+ bf16)
-        // dh_t = dz [W_dec; W_fbeta; W_hh]    (stack stored [NZ, D] = MN-major B, N = D, K = NZ)
-        MMX(dz16, NZ, 0, u.Wcat, D, 1, d->dh, D, bt, D, NZ, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
+        // dh_t = dz [W_dec; W_fbeta; W_hh]    (stack stored [NZ, D] = MN-major B, N = D, K = NZ); reduce deferred (see above)
+        ICD_TRY(icd_gemm_bf16_ex(dz16, NZ, 0, u.Wcat, D, 1, d->dh, D, bt, D, NZ, NF, NF, NF, 0, NF, 0, nullptr, 0.f, s,
+                                 nullptr, 0, u.splitk, u.splitk_floats, &dh_splits));
+        dh_rows = bt;
     }
+    if (dh_splits > 0) ICD_TRY(icd_splitk_finish(u.splitk, dh_splits, dh_rows, D, d->dh, D, nullptr, 0, s));   // d h0
 
     // ---- init_hidden_state (:161-163): dh, dc now hold d h0, d c0 ----
     CVT(d->dh, D, B, D, u.dh, D);

@@ -936,7 +936,8 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
                      float* C, int64_t ldc, int M, int N, int K,
                      const float* bias1, const float* bias2, const float* add1, int64_t ld1,
                      const float* add2, int64_t ld2, const uint8_t* row_mask, float beta, cudaStream_t s,
-                     void* C16, int64_t ldc16, float* splitk_ws, int64_t splitk_ws_floats) {
+                     void* C16, int64_t ldc16, float* splitk_ws, int64_t splitk_ws_floats, int* deferred_splits) {
+    if (deferred_splits) *deferred_splits = 0;
     if (M == 0 || N == 0) return 0;
     ICD_CHECK_ARG(K > 0, "gemm_tc: K must be positive");
     ICD_CHECK_ARG(C != nullptr || C16 != nullptr, "gemm_tc: no output");
@@ -979,7 +980,9 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
             default:  ICD_TRY(launch<64>(tmA, tmB, k, units, s)); break;
         }
     }
-    if (pl.splits > 1) {
+    if (pl.splits > 1 && deferred_splits) {
+        *deferred_splits = pl.splits;          // the consumer sums the [splits][M][N] planes left in splitk_ws
+    } else if (pl.splits > 1) {
         const long long work = ((long long)M * N + 3) / 4;
         long long blocks = (work + 255) / 256;
         if (blocks > ICD_NUM_SMS * 8) blocks = ICD_NUM_SMS * 8;
@@ -990,12 +993,29 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
     return 0;
 }
 
+// C[M,N] = sum of the `splits` planes a deferred contraction left in splitk_ws (fixed order); optional bf16 copy
+int icd_splitk_finish(const float* splitk_ws, int splits, int M, int N, float* C, int64_t ldc, void* C16, int64_t ldc16,
+                      cudaStream_t s) {
+    if (M == 0 || N == 0 || splits <= 0) return 0;
+    EpiArgs e;
+    e.C = C; e.ldc = ldc; e.M = M; e.N = N; e.K = 0; e.bias1 = e.bias2 = e.add1 = e.add2 = nullptr; e.ld1 = e.ld2 = 0;
+    e.row_mask = nullptr; e.beta = 0.f; e.C16 = reinterpret_cast<__nv_bfloat16*>(C16); e.ldc16 = ldc16;
+    auto al = [](const void* q, uintptr_t a) { return (reinterpret_cast<uintptr_t>(q) & (a - 1)) == 0; };
+    e.vec = ((!C || (al(C, 16) && ldc % 4 == 0)) && (!C16 || (al(C16, 8) && ldc16 % 4 == 0)) && N % 4 == 0) ? 4 : 1;
+    const long long work = ((long long)M * N + 3) / 4;
+    long long blocks = (work + 255) / 256;
+    if (blocks > ICD_NUM_SMS * 8) blocks = ICD_NUM_SMS * 8;
+    ICD_CUDA(icd_launch_pdl(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, s, splitk_ws, splits, e));
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
 int icd_gemm_bf16(const void* A16, int64_t lda, const void* B16, int64_t ldb, float* C, int64_t ldc,
                   int M, int N, int K, const float* bias1, const float* bias2, const float* add1, int64_t ld1,
                   const float* add2, int64_t ld2, const uint8_t* row_mask, float beta, cudaStream_t s,
                   void* C16, int64_t ldc16) {
     return icd_gemm_bf16_ex(A16, lda, 0, B16, ldb, 0, C, ldc, M, N, K, bias1, bias2, add1, ld1, add2, ld2, row_mask,
-                            beta, s, C16, ldc16, nullptr, 0);
+                            beta, s, C16, ldc16, nullptr, 0, nullptr);
 }
 
 namespace {
@@ -1090,5 +1110,5 @@ int icd_gemm_x3_launch(const icd_gemm_desc_t* d, cudaStream_t s) {
     else { ldb = up8(N); ICD_TRY(split_mn(d->B, d->sbk, N, b16, ldb, 1)); }
     return icd_gemm_bf16_ex(a16, lda, a_mn, b16, ldb, b_mn, d->C, d->ldc, M, N, Kx, d->bias1, d->bias2, d->add1, d->ld1,
                             d->add2, d->ld2, d->row_mask, d->beta, s, nullptr, 0, sk,
-                            icd_gemm_bf16_splitk_floats(M, N, Kx));
+                            icd_gemm_bf16_splitk_floats(M, N, Kx), nullptr);
 }

@@ -18,7 +18,13 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
                      float* C, int64_t ldc, int M, int N, int K,
                      const float* bias1, const float* bias2, const float* add1, int64_t ld1,
                      const float* add2, int64_t ld2, const uint8_t* row_mask, float beta, cudaStream_t s,
-                     void* C16, int64_t ldc16, float* splitk_ws, int64_t splitk_ws_floats);
+                     void* C16, int64_t ldc16, float* splitk_ws, int64_t splitk_ws_floats,
+                     int* deferred_splits = nullptr);
+// deferred_splits != NULL: when the plan splits K, the reduce pass is LEFT TO THE CONSUMER — the raw K-slice partials stay in
+// splitk_ws as [*deferred_splits][M][N] fp32 planes and C is not written (*deferred_splits = 0: C was written normally,
+// epilogue included).  Only for calls whose epilogue is empty (no bias / add / mask / beta / C16).
+int icd_splitk_finish(const float* splitk_ws, int splits, int M, int N, float* C, int64_t ldc, void* C16, int64_t ldc16,
+                      cudaStream_t s);
 int64_t icd_gemm_bf16_splitk_floats(int M, int N, int K);
 int64_t icd_gemm_tc_ws_bytes(int M, int N, int K);
 // fp32-grade tier (ICD_PREC_FP32X3): 3-term bf16 split laid out along K (A pattern which = 0, B pattern which = 1):

@@ -48,7 +48,8 @@ __global__ void lstm_pointwise_bwd_kernel(int rows, int D, const float* __restri
                                           float* __restrict__ dc_inout, const float* __restrict__ gates_act,
                                           const float* __restrict__ c_prev, const float* __restrict__ c_new,
                                           float* __restrict__ dgates_pre, long long ld_dg,
-                                          __nv_bfloat16* __restrict__ dg16, long long ld_dg16) {
+                                          __nv_bfloat16* __restrict__ dg16, long long ld_dg16,
+                                          const float* __restrict__ dh_parts, int n_parts, int parts_rows) {
     pdl_trigger();
     pdl_wait();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -56,7 +57,12 @@ __global__ void lstm_pointwise_bwd_kernel(int rows, int D, const float* __restri
     const int r = (int)(idx / D), d = (int)(idx % D);
     const float* ga = gates_act + (long long)r * 4 * D;
     const float i = ga[d], f = ga[D + d], g = ga[2 * D + d], o = ga[3 * D + d];
-    float dh = dh_in ? dh_in[idx] : 0.f;
+    float dh;
+    if (n_parts > 0 && r < parts_rows) {       // deferred split-K: sum the K-slice planes of the dh contraction here
+        dh = 0.f;
+        const long long stride = (long long)parts_rows * D;
+        for (int sp = 0; sp < n_parts; ++sp) dh += dh_parts[sp * stride + idx];
+    } else dh = dh_in ? dh_in[idx] : 0.f;
     if (d_hdrop) {
         float u = d_hdrop[(long long)r * hdrop_row_stride + d];
         if (mask) u = mask[idx] ? u * scale : 0.f;
@@ -327,12 +333,14 @@ int icd_lstm_pointwise_fwd(int rows, int D, const float* gates_pre, const float*
 int icd_lstm_pointwise_bwd(int rows, int D, const float* dh_in, const float* d_hdrop, int64_t hdrop_row_stride,
                            const uint8_t* mask, float scale, float* dc_inout,
                            const float* gates_act, const float* c_prev, const float* c_new,
-                           float* dgates_pre, int64_t ld_dg, cudaStream_t s, void* dg16, int64_t ld_dg16) {
+                           float* dgates_pre, int64_t ld_dg, cudaStream_t s, void* dg16, int64_t ld_dg16,
+                           const float* dh_parts, int n_parts, int parts_rows) {
     if (rows == 0) return 0;
     const long long n = (long long)rows * D;
     ICD_CUDA(icd_launch_pdl(lstm_pointwise_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, s, rows, D,
                             dh_in, d_hdrop, (long long)hdrop_row_stride, (const unsigned char*)mask, scale, dc_inout, gates_act,
-                            c_prev, c_new, dgates_pre, (long long)ld_dg, (__nv_bfloat16*)dg16, (long long)ld_dg16));
+                            c_prev, c_new, dgates_pre, (long long)ld_dg, (__nv_bfloat16*)dg16, (long long)ld_dg16,
+                            dh_parts, n_parts, parts_rows));
     ICD_LAUNCH_CHECK();
     return 0;
 }
