@@ -517,8 +517,9 @@ def main():
                     copy_stream.wait_event(done[i % 2])            # buffer free again?
                     e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e_a.record(copy_stream)
-                    bufs[i % 2][0].copy_(enc_host, non_blocking=True)
-                    bufs[i % 2][1].copy_(caps_h, non_blocking=True)
+                    if not os.environ.get("ICD_BENCH_E2E_NOCOPY"):      # diagnostic only: isolates the cost of the H2D stream
+                        bufs[i % 2][0].copy_(enc_host, non_blocking=True)
+                        bufs[i % 2][1].copy_(caps_h, non_blocking=True)
                     e_b.record(copy_stream)
                     h2d_ev.append((e_a, e_b))
                     ready[i % 2].record(copy_stream)

@@ -105,7 +105,6 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
         int* __restrict__ parent_s, int* __restrict__ word_s, int* __restrict__ trace_s,
         float* __restrict__ best_score, int* __restrict__ best_step, int* __restrict__ best_parent) {
     __shared__ float s_red[40];
-    __shared__ float s_off[KMAX];            // per-row additive constant: score_i - max_i - log(sum_i)
     __shared__ float s_max[KMAX], s_lsum[KMAX], s_score[KMAX];
     __shared__ float s_cv[256 * KMAX];
     __shared__ int s_ci[256 * KMAX];

@@ -27,7 +27,7 @@ __global__ void row_valid_kernel(int B, int T, const BtPack bt, unsigned char* _
 int check_common(const icd_att_desc_t* d) {
     ICD_CHECK_ARG(d != nullptr, "attention_decoder: null descriptor");
     ICD_CHECK_ARG(d->B > 0 && d->T > 0 && d->T <= ICD_MAX_STEPS, "attention_decoder: B=%d T=%d out of range", d->B, d->T);
-    ICD_CHECK_ARG(d->L > d->T - 1 + 0 && d->L >= d->T, "attention_decoder: captions need at least T columns (L=%d T=%d)", d->L, d->T);
+    ICD_CHECK_ARG(d->L >= d->T, "attention_decoder: captions need at least T columns (L=%d T=%d)", d->L, d->T);
     ICD_CHECK_ARG(d->A % 4 == 0 && d->C % 4 == 0 && d->D % 4 == 0 && d->E % 4 == 0,
                   "attention_decoder: A,C,D,E must be multiples of 4 (A=%d C=%d D=%d E=%d)", d->A, d->C, d->D, d->E);
     for (int t = 0; t < d->T; ++t) {
