@@ -16,7 +16,34 @@ long long g_icd_launches = 0;
 namespace {
 constexpr int PROF_MAX = 8192;
 struct ProfRec { cudaEvent_t a, b; int dir, rows; };
-bool g_prof_on = false;
+int g_prof_stride = 0;               // 0 = off; n = every n-th attention launch of each direction is timed
+int g_prof_seen[2] = {0, 0};
+}  // namespace
+
+// Which kernel classes are launched with the programmatic-stream-serialization attribute (bit = ICD_PDL_* class).
+unsigned icd_pdl_mask() {
+    static const unsigned mask = [] {
+        const char* e = getenv("ICD_PDL_MASK");
+        // default: contractions, LSTM gate math and split-K reductions start early; the attention-step kernels do NOT —
+        // their CTAs would be placed while the previous contraction still holds part of the SMs, and the uneven placement
+        // costs the HBM-bound kernel 15-60 us per launch (measured: tools/e2e_diag.py)
+        return e ? (unsigned)strtoul(e, nullptr, 0) : ((1u << ICD_PDL_GEMM) | (1u << ICD_PDL_POINTWISE) | (1u << ICD_PDL_REDUCE));
+    }();
+    return mask;
+}
+// ... and behind which predecessor classes (env ICD_PDL_PRED_MASK); tracks the previous launch of this thread
+unsigned icd_pdl_allowed(int cls) {
+    static const unsigned pred_mask = [] {
+        const char* e = getenv("ICD_PDL_PRED_MASK");
+        return e ? (unsigned)strtoul(e, nullptr, 0) : 0xffffffffu;
+    }();
+    static thread_local int last_cls = -1;
+    const unsigned ok = ((icd_pdl_mask() >> cls) & 1u) && (last_cls < 0 || ((pred_mask >> last_cls) & 1u));
+    last_cls = cls;
+    return ok;
+}
+
+namespace {
 ProfRec g_prof[PROF_MAX];
 int g_prof_n = 0, g_prof_created = 0;
 bool g_prof_open = false;
@@ -24,7 +51,8 @@ bool g_prof_open = false;
 
 void icd_prof_mark_begin(int dir, int rows, cudaStream_t s) {
     g_prof_open = false;
-    if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+    if (g_prof_stride <= 0 || g_prof_n >= PROF_MAX) return;
+    if (g_prof_seen[dir & 1]++ % g_prof_stride != 0) return;
     if (g_prof_n >= g_prof_created) {
         if (cudaEventCreate(&g_prof[g_prof_n].a) != cudaSuccess || cudaEventCreate(&g_prof[g_prof_n].b) != cudaSuccess) return;
         g_prof_created = g_prof_n + 1;
@@ -45,7 +73,11 @@ void icd_prof_mark_end(int dir, cudaStream_t s) {
 extern "C" {
 int64_t icd_launch_count(void) { return (int64_t)g_icd_launches; }
 
-int icd_prof_enable(int on) { g_prof_on = on != 0; if (!on) g_prof_n = 0; return 0; }
+int icd_prof_enable(int on) {
+    g_prof_stride = on > 0 ? on : 0; g_prof_seen[0] = g_prof_seen[1] = 0;
+    if (!on) g_prof_n = 0;
+    return 0;
+}
 
 int icd_prof_collect(double* fwd_ms, int64_t* fwd_launches, int64_t* fwd_rows,
                      double* bwd_ms, int64_t* bwd_launches, int64_t* bwd_rows) {

@@ -627,7 +627,7 @@ extern "C" int icd_attention_step_fwd_bf16(int rows, int P, int C, int A, const 
         configured = smem;
     }
     icd_prof_mark_begin(0, rows, s);
-    ICD_CUDA(icd_launch_pdl(att_step_fwd_bf16_kernel, dim3(rows), dim3(256), smem, s, P, C, A, (const int*)img_index,
+    ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_FWD, att_step_fwd_bf16_kernel, dim3(rows), dim3(256), smem, s, P, C, A, (const int*)img_index,
                             reinterpret_cast<const __nv_bfloat16*>(enc16), reinterpret_cast<const __nv_bfloat16*>(att_enc16),
                             att_dec, (long long)ld_dec, w_full, b_full, fbeta_pre, (long long)ld_fb, alpha, (long long)ld_alpha,
                             awe_raw, gate, gated, reinterpret_cast<__nv_bfloat16*>(gated16)));
@@ -662,7 +662,7 @@ extern "C" int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
         configured = smem;
     }
     icd_prof_mark_begin(1, rows, s);
-    ICD_CUDA(icd_launch_pdl(att_step_bwd_bf16_kernel, dim3(rows), dim3(256), smem, s, P, C, A,
+    ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_BWD, att_step_bwd_bf16_kernel, dim3(rows), dim3(256), smem, s, P, C, A,
                             reinterpret_cast<const __nv_bfloat16*>(enc16), reinterpret_cast<const __nv_bfloat16*>(att_enc16),
                             att_dec, (long long)ld_dec, w_full, alpha, (long long)ld_alpha, d_alpha_ext, (long long)ld_dalpha,
                             gate, awe_raw, d_gated, d_att_dec, (long long)ld_ddec, d_fbeta_pre, (long long)ld_dfb,

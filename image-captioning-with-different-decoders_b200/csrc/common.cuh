@@ -28,27 +28,32 @@ extern long long g_icd_launches;      // api.cu: kernels launched by this librar
 static inline cudaStream_t icd_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 #ifdef __CUDACC__
+// kernel classes for the programmatic-dependent-launch policy (bit index into icd_pdl_mask())
+enum { ICD_PDL_GEMM = 0, ICD_PDL_ATT_FWD = 1, ICD_PDL_ATT_BWD = 2, ICD_PDL_POINTWISE = 3, ICD_PDL_REDUCE = 4 };
+unsigned icd_pdl_mask();             // api.cu: which classes may start early (env ICD_PDL_MASK overrides the default)
+unsigned icd_pdl_allowed(int cls);   // api.cu: 1 if a launch of class `cls` may start early behind the previous launch
+
 // launch with the programmatic-stream-serialization attribute (see pdl_trigger / pdl_wait below)
 template <typename... KArgs, typename... Args>
-static inline cudaError_t icd_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+static inline cudaError_t icd_launch_pdl(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                          Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = icd_pdl_allowed(cls);
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 // the same, as thread-block clusters of `cluster_x` CTAs (grid.x must be a multiple of cluster_x)
 template <typename... KArgs, typename... Args>
-static inline cudaError_t icd_launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
-                                                 unsigned cluster_x, Args... args) {
+static inline cudaError_t icd_launch_pdl_cluster(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                                 cudaStream_t s, unsigned cluster_x, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[0].val.programmaticStreamSerializationAllowed = icd_pdl_allowed(cls);
     attr[1].id = cudaLaunchAttributeClusterDimension;
     attr[1].val.clusterDim.x = cluster_x; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 2;

@@ -827,11 +827,11 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KArgs& k, int u
     }
     if (k.cluster > 1) {                       // units = super tiles x slices; one CTA pair per unit slot
         const int pairs = units < ICD_NUM_SMS / 2 ? units : ICD_NUM_SMS / 2;
-        ICD_CUDA(icd_launch_pdl_cluster(gemm_tc_kernel<BN>, dim3(2 * pairs), dim3(NUM_THREADS), (size_t)Cfg<BN>::SMEM, s, 2u,
+        ICD_CUDA(icd_launch_pdl_cluster(ICD_PDL_GEMM, gemm_tc_kernel<BN>, dim3(2 * pairs), dim3(NUM_THREADS), (size_t)Cfg<BN>::SMEM, s, 2u,
                                         tmA, tmB, k));
     } else {
         const int grid = units < ICD_NUM_SMS ? units : ICD_NUM_SMS;
-        ICD_CUDA(icd_launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), (size_t)Cfg<BN>::SMEM, s, tmA, tmB, k));
+        ICD_CUDA(icd_launch_pdl(ICD_PDL_GEMM, gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), (size_t)Cfg<BN>::SMEM, s, tmA, tmB, k));
     }
     ICD_LAUNCH_CHECK();
     return 0;
@@ -845,7 +845,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const KArgs& k, int 
         attr_set = true;
     }
     const int pairs = units < ICD_NUM_SMS / 2 ? units : ICD_NUM_SMS / 2;
-    ICD_CUDA(icd_launch_pdl_cluster(gemm_tc2_kernel<BN>, dim3(2 * pairs), dim3(NUM_THREADS), (size_t)Cfg2<BN>::SMEM, s, 2u,
+    ICD_CUDA(icd_launch_pdl_cluster(ICD_PDL_GEMM, gemm_tc2_kernel<BN>, dim3(2 * pairs), dim3(NUM_THREADS), (size_t)Cfg2<BN>::SMEM, s, 2u,
                                     tmA, tmB, k));
     ICD_LAUNCH_CHECK();
     return 0;
@@ -986,7 +986,7 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
         const long long work = ((long long)M * N + 3) / 4;
         long long blocks = (work + 255) / 256;
         if (blocks > ICD_NUM_SMS * 8) blocks = ICD_NUM_SMS * 8;
-        ICD_CUDA(icd_launch_pdl(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, s,
+        ICD_CUDA(icd_launch_pdl(ICD_PDL_REDUCE, splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, s,
                                 (const float*)splitk_ws, pl.splits, e));
         ICD_LAUNCH_CHECK();
     }
@@ -1005,7 +1005,7 @@ int icd_splitk_finish(const float* splitk_ws, int splits, int M, int N, float* C
     const long long work = ((long long)M * N + 3) / 4;
     long long blocks = (work + 255) / 256;
     if (blocks > ICD_NUM_SMS * 8) blocks = ICD_NUM_SMS * 8;
-    ICD_CUDA(icd_launch_pdl(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, s, splitk_ws, splits, e));
+    ICD_CUDA(icd_launch_pdl(ICD_PDL_REDUCE, splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, s, splitk_ws, splits, e));
     ICD_LAUNCH_CHECK();
     return 0;
 }

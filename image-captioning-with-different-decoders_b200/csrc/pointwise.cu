@@ -323,7 +323,7 @@ int icd_lstm_pointwise_fwd(int rows, int D, const float* gates_pre, const float*
                            cudaStream_t s, void* h16, void* hdrop16) {
     if (rows == 0) return 0;
     const long long n = (long long)rows * D;
-    ICD_CUDA(icd_launch_pdl(lstm_pointwise_fwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, s, rows, D,
+    ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, lstm_pointwise_fwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, s, rows, D,
                             gates_pre, c_prev, gates_act, c_new, h_new, hdrop, (long long)hdrop_row_stride,
                             (const unsigned char*)mask, scale, (__nv_bfloat16*)h16, (__nv_bfloat16*)hdrop16));
     ICD_LAUNCH_CHECK();
@@ -337,7 +337,7 @@ int icd_lstm_pointwise_bwd(int rows, int D, const float* dh_in, const float* d_h
                            const float* dh_parts, int n_parts, int parts_rows) {
     if (rows == 0) return 0;
     const long long n = (long long)rows * D;
-    ICD_CUDA(icd_launch_pdl(lstm_pointwise_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, s, rows, D,
+    ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, lstm_pointwise_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, s, rows, D,
                             dh_in, d_hdrop, (long long)hdrop_row_stride, (const unsigned char*)mask, scale, dc_inout, gates_act,
                             c_prev, c_new, dgates_pre, (long long)ld_dg, (__nv_bfloat16*)dg16, (long long)ld_dg16,
                             dh_parts, n_parts, parts_rows));

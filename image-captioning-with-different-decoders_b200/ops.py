@@ -244,7 +244,8 @@ def launch_count():
 
 
 def prof_enable(on):
-    check(lib().icd_prof_enable(int(bool(on))), "icd_prof_enable")
+    """on: False/0 = off, True/1 = time every attention-step launch, n > 1 = every n-th launch of each direction."""
+    check(lib().icd_prof_enable(int(on)), "icd_prof_enable")
 
 
 def prof_collect():

@@ -51,9 +51,11 @@ ICD_API int icd_has_tensor_core_gemm(void);          /* 1 if the tcgen05/TMA GEM
 ICD_API int icd_gemm_set_pair_mode(int mode);
 ICD_API int64_t icd_launch_count(void);              /* kernels launched by this library so far (process-wide) */
 
-/* Optional device-side timing of the attention-step kernels (bench.py's roofline line).  When enabled every
- * icd_attention_step_fwd / _bwd launch is bracketed by a cudaEvent pair on its own stream; icd_prof_collect
- * waits for the recorded events, sums elapsed milliseconds / launches / rows per direction and resets. */
+/* Optional device-side timing of the attention-step kernels (bench.py's roofline line).  icd_prof_enable(n), n >= 1:
+ * every n-th icd_attention_step_fwd / _bwd launch (per direction) is bracketed by a cudaEvent pair on its own stream
+ * (an event record between two kernels costs a few microseconds and suppresses their programmatic overlap, so a
+ * timed region samples with n > 1); icd_prof_enable(0) switches it off.  icd_prof_collect waits for the recorded
+ * events, sums elapsed milliseconds / launches / rows per direction over the SAMPLED launches and resets. */
 ICD_API int icd_prof_enable(int on);
 ICD_API int icd_prof_collect(double* fwd_ms, int64_t* fwd_launches, int64_t* fwd_rows,
                      double* bwd_ms, int64_t* bwd_launches, int64_t* bwd_rows);
