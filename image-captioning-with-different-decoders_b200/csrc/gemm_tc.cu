@@ -869,28 +869,37 @@ int pair_mode() {
 struct Plan { int bn, splits, kb_per_split; };
 
 Plan make_plan(int M, int N, int K, bool allow_split) {
+    // Cost model in SM clocks, fitted to CUDA-graph replays of the train-step shapes (tools/gemm_bench.py --graph):
+    //   one k-block costs 560 + 7.1 clk per KB of operands the CTA pulls from L2 (the per-SM L2->smem path, ~46 B/clk, bounds
+    //   these tiles, not the tensor pipe); launch + prologue + epilogue ~4500; a split-K pass 6000 + ~1.05 clk per KB of
+    //   partial planes (written by the contraction, read back by the reduce pass or the deferred consumer).
     const int tm = (M + BM - 1) / BM, nkb = (K + BK - 1) / BK;
     const int cand[3] = {256, 128, 64};
-    const double clk_per_kb[3] = {512.0, 256.0 * 1.15, 192.0 * 1.3};
     Plan best; best.bn = 64; best.splits = 1; best.kb_per_split = nkb;
     double best_cost = 1e300;
+    const double plane_kb = (double)M * N * 4.0 / 1024.0;
     for (int i = 0; i < 3; ++i) {
         const int bn = cand[i];
         if (i < 2 && N <= cand[i + 1]) continue;                 // a narrower tile already covers N
         const int tiles = tm * ((N + bn - 1) / bn);
-        int splits = 1, kbs = nkb;
-        if (allow_split && tiles * 2 <= ICD_NUM_SMS && nkb >= 8) {
-            int s = ICD_NUM_SMS / tiles;
-            if (s > nkb / 4) s = nkb / 4;
-            if (s > 32) s = 32;
-            if (s >= 2) { kbs = (nkb + s - 1) / s; splits = (nkb + kbs - 1) / kbs; }
+        const double clk_kb = 560.0 + 7.1 * ((BM + bn) * BK * 2 / 1024.0);
+        int smax = 1;
+        if (allow_split && nkb >= 8) {
+            smax = ICD_NUM_SMS / tiles;
+            if (smax > nkb / 4) smax = nkb / 4;
+            if (smax > 32) smax = 32;
+            if (smax < 1) smax = 1;
         }
-        const double units = (double)tiles * splits;
-        double waves = units / ICD_NUM_SMS;                      // static round-robin: the busiest CTA does ceil() units,
-        if (waves < 1.0) waves = 1.0;                            // but short tiles overlap their epilogues: blend
-        else waves = 0.5 * (waves + std::ceil(waves));
-        const double cost = waves * kbs * clk_per_kb[i] + 3000.0 + (splits > 1 ? 6000.0 : 0.0);
-        if (cost < best_cost) { best_cost = cost; best.bn = bn; best.splits = splits; best.kb_per_split = kbs; }
+        for (int sp = 1; sp <= smax; ++sp) {
+            const int kbs = (nkb + sp - 1) / sp;
+            if ((nkb + kbs - 1) / kbs != sp) continue;           // this slice length leaves an empty slice
+            const double units = (double)tiles * sp;
+            double waves = units / ICD_NUM_SMS;                  // static round-robin: the busiest CTA does ceil() units,
+            if (waves < 1.0) waves = 1.0;                        // but short tiles overlap their epilogues: blend
+            else waves = 0.5 * (waves + std::ceil(waves));
+            const double cost = waves * kbs * clk_kb + 4500.0 + (sp > 1 ? 6000.0 + sp * plane_kb * 1.05 : 0.0);
+            if (cost < best_cost) { best_cost = cost; best.bn = bn; best.splits = sp; best.kb_per_split = kbs; }
+        }
     }
     return best;
 }
@@ -942,6 +951,13 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
     ICD_CHECK_ARG(K > 0, "gemm_tc: K must be positive");
     ICD_CHECK_ARG(C != nullptr || C16 != nullptr, "gemm_tc: no output");
     Plan pl = make_plan(M, N, K, splitk_ws != nullptr);
+    if (const char* f = getenv("ICD_GEMM_FORCE_PLAN")) {           // diagnostic: "bn,splits" (tools/gemm_bench.py)
+        int bn = 0, sp = 0;
+        if (sscanf(f, "%d,%d", &bn, &sp) == 2 && (bn == 64 || bn == 128 || bn == 256) && sp >= 1 && (sp == 1 || splitk_ws)) {
+            const int nkb = (K + BK - 1) / BK;
+            pl.bn = bn; pl.kb_per_split = (nkb + sp - 1) / sp; pl.splits = (nkb + pl.kb_per_split - 1) / pl.kb_per_split;
+        }
+    }
     if (pl.splits > 1 && (int64_t)pl.splits * M * N > splitk_ws_floats) {
         pl.splits = 1; pl.kb_per_split = (K + BK - 1) / BK;
     }

@@ -4,6 +4,7 @@ torch is used here only for device memory, the current stream and dtype bookkeep
 kernel of libicd_b200.so.  All functions require CUDA tensors and raise otherwise — there is no CPU path.
 """
 import ctypes
+import os
 
 import torch
 
@@ -80,6 +81,8 @@ def gemm_bf16(a16, b16, M, N, K, *, a_mn=False, b_mn=False, out=None, out16=None
     ws, nws = None, 0
     if split_k:
         nws = int(lib().icd_gemm_bf16_splitk_ws_floats(M, N, K))
+        if os.environ.get("ICD_GEMM_FORCE_PLAN"):        # diagnostic plan override (tools/gemm_bench.py): room for any split
+            nws = 32 * M * N
         if nws:
             ws = torch.empty(nws, device=dev, dtype=torch.float32)
     check(lib().icd_gemm_bf16_operands(ptr(a16), ctypes.c_int64(a16.stride(0)), int(a_mn), ptr(b16),

@@ -14,6 +14,7 @@ __graft_entry__.build()
 from icd_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda:0")
+GRAPH = "--graph" in sys.argv              # time a CUDA-graph replay of the launch chain (removes the Python launch cost)
 PROFILE = "--profile" in sys.argv          # one warm-up + one launch per shape (for ncu --set full)
 B, T, P, C, A, D, E, V = 512, 24, 196, 2048, 512, 512, 512, 9490
 NZ = A + C + 4 * D
@@ -35,15 +36,34 @@ def run(name, M, N, K, a_mn=False, b_mn=False, fp32=True, bf16=False, mask=False
         ops.gemm_bf16(a, b, M, N, K, **kw)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        ops.gemm_bf16(a, b, M, N, K, **kw)
-    e1.record()
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / iters
+    if GRAPH:                                   # replay a captured chain: no host launch overhead between the kernels
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                ops.gemm_bf16(a, b, M, N, K, **kw)
+        g.replay(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (5 * iters)
+    else:
+        e0.record()
+        for _ in range(iters):
+            ops.gemm_bf16(a, b, M, N, K, **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / iters
     print("%-34s M=%6d N=%5d K=%6d  %8.1f us  %7.1f TF/s" % (name, M, N, K, us, 2.0 * M * N * K / us / 1e6), flush=True)
 
 
+if "--dh" in sys.argv:
+    run("dh (step)", B, D, NZ, b_mn=True, iters=200)
+    run("d_gated (step)", B, C, 4 * D, b_mn=True, iters=200)
+    run("K4 gates (step)", B, 4 * D, C, add=True, iters=200)
+    run("K2 z (step)", B, NZ, D, bias=True, iters=200)
+    sys.exit(0)
 run("K1 enc_att (bf16 out)", B * P, A, C, fp32=False, bf16=True, bias=True)
 run("K5 emb*W_ih (fp32 out)", T * B, 4 * D, E, bias=True)
 run("K6 fc fwd (ldc=V, mask)", B * T, V, D, bias=True, mask=True)
