@@ -73,7 +73,7 @@ int baseline_fwd_bf16(const icd_base_desc_t* d, cudaStream_t s) {
     const size_t BH = (size_t)B * H;
     const int LB = L * B;
     ICD_CUDA(cudaMemcpyAsync(d->x, d->img_features, sizeof(float) * (size_t)B * E, cudaMemcpyDeviceToDevice, s));      // :101
-    if (L > 1) ICD_TRY(icd_embed_gather(d->emb_w, d->emb_is_f64, d->captions, B, L, L - 1, E, d->x + (size_t)B * E, s));
+    if (L > 1) ICD_TRY(icd_embed_gather(d->emb_w, d->emb_is_f64, d->captions, B, L, L - 1, E, V, d->x + (size_t)B * E, s));
     BCVT(d->w_ih, E, 4 * H, E, u.Wih, u.ldE);
     BCVT(d->w_hh, H, 4 * H, H, u.Whh, H);
     BCVT(d->lin_w, H, V, H, u.Wlin, H);
@@ -162,7 +162,7 @@ extern "C" int icd_baseline_decoder_fwd(const icd_base_desc_t* d, void* stream) 
     const size_t BH = (size_t)B * H;
     // x[0] = img_features, x[t] = embedding(captions[:, t-1])   (:93-101)
     ICD_CUDA(cudaMemcpyAsync(d->x, d->img_features, sizeof(float) * (size_t)B * E, cudaMemcpyDeviceToDevice, s));
-    if (L > 1) ICD_TRY(icd_embed_gather(d->emb_w, d->emb_is_f64, d->captions, B, L, L - 1, E, d->x + (size_t)B * E, s));
+    if (L > 1) ICD_TRY(icd_embed_gather(d->emb_w, d->emb_is_f64, d->captions, B, L, L - 1, E, V, d->x + (size_t)B * E, s));
     ICD_TRY(icd_gemm_simple(prec, d->x, E, 1, d->w_ih, E, 1, d->xg, 4 * H, L * B, 4 * H, E, d->b_ih, d->b_hh,
                             nullptr, 0, nullptr, 0, nullptr, 0.f, s));
     ICD_CUDA(cudaMemsetAsync(d->h_all, 0, sizeof(float) * BH, s));                           // zero (h0, c0) (:106)

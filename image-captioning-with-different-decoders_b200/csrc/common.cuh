@@ -70,6 +70,12 @@ __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
     return r;
 }
 
+__device__ __forceinline__ float2 ld_stream_f2(const float2* p) {
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -126,7 +132,7 @@ int icd_colsum(const float* X, int64_t ld, int64_t M, int N, const uint8_t* row_
 int64_t icd_colsum_bf16_ws_floats(int64_t M, int N);
 int icd_colsum_bf16(const void* X16, int64_t ld, int64_t M, int N, const uint8_t* row_mask, float* out, float* ws,
                     cudaStream_t s);
-int icd_embed_gather(const void* table, int is_f64, const int64_t* captions, int B, int L, int T, int E,
+int icd_embed_gather(const void* table, int is_f64, const int64_t* captions, int B, int L, int T, int E, int V,
                      float* out /* (T,B,E) */, cudaStream_t s);
 int icd_embed_scatter_add(void* d_table, int is_f64, const int64_t* captions, int B, int L, int T, int E,
                           const int32_t* bt_host, const float* d_x /* (T,B,E) */, cudaStream_t s);

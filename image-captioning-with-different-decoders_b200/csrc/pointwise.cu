@@ -143,10 +143,11 @@ __global__ void __launch_bounds__(128) colsum_bf16_partial_kernel(const __nv_bfl
 
 template <typename TT>
 __global__ void embed_gather_kernel(const TT* __restrict__ table, const long long* __restrict__ captions,
-                                    int B, int L, int T, int E, float* __restrict__ out) {
+                                    int B, int L, int T, int E, int V, float* __restrict__ out) {
     const int row = blockIdx.x;                  // row = t*B + b
     const int t = row / B, b = row % B;
     const long long tok = captions[(long long)b * L + t];
+    if (tok < 0 || tok >= V) __trap();           // nn.Embedding raises on an out-of-range id; never read outside the table
     const TT* src = table + tok * E;
     float* dst = out + (long long)row * E;
     for (int e = threadIdx.x; e < E; e += blockDim.x) dst[e] = (float)src[e];
@@ -286,26 +287,36 @@ __global__ void __launch_bounds__(256) cross_entropy_bwd_kernel(int V, const flo
     float* dx = d_logits ? d_logits + r * V : nullptr;
     __nv_bfloat16* d16r = d16 ? d16 + r * ld16 : nullptr;
     if (d16r) for (int v = V + threadIdx.x; v < ld16; v += blockDim.x) d16r[v] = __float2bfloat16_rn(0.f);
-    if (tgt < 0) {
-        for (int v = threadIdx.x; v < V; v += blockDim.x) {
-            if (dx) dx[v] = 0.f;
-            if (d16r) d16r[v] = __float2bfloat16_rn(0.f);
+    if (tgt < 0) {                                   // ignored row: zeros (the bf16 row is 16-byte aligned, ld16 % 8 == 0)
+        if (dx) for (int v = threadIdx.x; v < V; v += blockDim.x) dx[v] = 0.f;
+        if (d16r) {
+            uint4* z = reinterpret_cast<uint4*>(d16r);
+            for (int v = threadIdx.x; v < (int)(ld16 >> 3); v += blockDim.x) z[v] = make_uint4(0u, 0u, 0u, 0u);
         }
         return;
     }
     const float lse = lse_in[r];
     const float scale = inv_count * (upstream ? upstream[0] : 1.f);
-    // V even and rows 8-byte aligned (V = 9490): 64-bit loads / stores; otherwise scalar
+    // V even and rows 8-byte aligned (V = 9490): 64-bit loads / stores, four loads in flight per thread; otherwise scalar
     if ((V & 1) == 0) {
         const int V2 = V >> 1;
-        for (int j = threadIdx.x; j < V2; j += blockDim.x) {
-            const float2 xv = *reinterpret_cast<const float2*>(x + 2 * j);
+        const float2* x2 = reinterpret_cast<const float2*>(x);
+        auto emit = [&](int j, float2 xv) {
             float2 g;
             g.x = (expf(xv.x - lse) - ((2 * j) == tgt ? 1.f : 0.f)) * scale;
             g.y = (expf(xv.y - lse) - ((2 * j + 1) == tgt ? 1.f : 0.f)) * scale;
             if (dx) *reinterpret_cast<float2*>(dx + 2 * j) = g;
             if (d16r) *reinterpret_cast<__nv_bfloat162*>(d16r + 2 * j) = __floats2bfloat162_rn(g.x, g.y);
+        };
+        int j = threadIdx.x;
+        for (; j + 3 * 256 < V2; j += 4 * 256) {
+            float2 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = ld_stream_f2(x2 + j + u * 256);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) emit(j + u * 256, v[u]);
         }
+        for (; j < V2; j += 256) emit(j, x2[j]);
     } else {
         for (int v = threadIdx.x; v < V; v += blockDim.x) {
             const float g = (expf(x[v] - lse) - (v == tgt ? 1.f : 0.f)) * scale;
@@ -371,11 +382,11 @@ int icd_colsum_bf16(const void* X16, int64_t ld, int64_t M, int N, const uint8_t
     return icd_colsum(ws, N, chunks, N, nullptr, out, s);
 }
 
-int icd_embed_gather(const void* table, int is_f64, const int64_t* captions, int B, int L, int T, int E,
+int icd_embed_gather(const void* table, int is_f64, const int64_t* captions, int B, int L, int T, int E, int V,
                      float* out, cudaStream_t s) {
     if (B * T == 0) return 0;
-    if (is_f64) embed_gather_kernel<double><<<B * T, 128, 0, s>>>((const double*)table, (const long long*)captions, B, L, T, E, out);
-    else        embed_gather_kernel<float><<<B * T, 128, 0, s>>>((const float*)table, (const long long*)captions, B, L, T, E, out);
+    if (is_f64) embed_gather_kernel<double><<<B * T, 128, 0, s>>>((const double*)table, (const long long*)captions, B, L, T, E, V, out);
+    else        embed_gather_kernel<float><<<B * T, 128, 0, s>>>((const float*)table, (const long long*)captions, B, L, T, E, V, out);
     ICD_LAUNCH_CHECK();
     return 0;
 }
