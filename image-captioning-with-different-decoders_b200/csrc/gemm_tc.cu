@@ -196,6 +196,35 @@ __device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ s
                 *reinterpret_cast<uint2*>(e.C16 + (long long)m * e.ldc16 + n) = pk;
             }
         }
+    } else if (e.vec == 3 && nb + 32 <= e.N) {
+        // fp32 rows that are only 8-byte aligned on odd m (ldc % 4 == 2, e.g. the (B*T, V = 9490) logits): a lane still owns 4
+        // columns of 4 rows, but on odd rows its columns are shifted by 2 so the 128-bit store is aligned again; the last lane
+        // of an odd row writes the two 64-bit leftovers (columns 0-1 and 30-31).  bias + row mask only (no add / beta / C16).
+        const int j = lane & 7;
+        const bool odd = ((lane >> 3) & 1) != 0;                      // mrow0 is even: parity of the row == parity of lane >> 3
+        const bool edge = odd && j == 7;
+        int col[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) col[q] = edge ? (q < 2 ? q : 28 + q) : 4 * j + (odd ? 2 : 0) + q;
+        float b[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) b[q] = (e.bias1 ? __ldg(e.bias1 + nb + col[q]) : 0.f) + (e.bias2 ? __ldg(e.bias2 + nb + col[q]) : 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + (lane >> 3), m = mrow0 + rr;
+            if (!((rows_in >> rr) & 1u)) continue;
+            const float* sr = sE + rr * EPI_LD;
+            const bool keep_row = ((rows_keep >> rr) & 1u) != 0;
+            float x[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[q] = keep_row ? sr[col[q]] + b[q] : 0.f;
+            float* dst = e.C + (long long)m * e.ldc + nb;
+            if (!edge) *reinterpret_cast<float4*>(dst + col[0]) = make_float4(x[0], x[1], x[2], x[3]);
+            else {
+                *reinterpret_cast<float2*>(dst) = make_float2(x[0], x[1]);
+                *reinterpret_cast<float2*>(dst + 30) = make_float2(x[2], x[3]);
+            }
+        }
     } else if (e.vec >= 2 && nb + 32 <= e.N) {
         const int cc = (lane & 15) * 2, n = nb + cc;
         float2 bsum = make_float2(0.f, 0.f);
@@ -981,7 +1010,8 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
                (!add2 || (al(add2, 4 * v) && ld2 % v == 0)) && (!C16 || (al(C16, 2 * v) && ldc16 % v == 0)) &&
                (!bias1 || al(bias1, 4 * v)) && (!bias2 || al(bias2, 4 * v));
     };
-    e.vec = fits(4) ? 4 : (fits(2) ? 2 : 1);
+    const bool shifted = C && !C16 && !add1 && !add2 && beta == 0.f && al(C, 16) && (ldc & 3) == 2;   // see epilogue_store_chunk
+    e.vec = fits(4) ? 4 : (shifted ? 3 : (fits(2) ? 2 : 1));
     k.a_mn = a_mn ? 1 : 0; k.b_mn = b_mn ? 1 : 0;
     k.splits = pl.splits; k.kb_per_split = pl.kb_per_split; k.partial = splitk_ws;
     k.cluster = cluster;

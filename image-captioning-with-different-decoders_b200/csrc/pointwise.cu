@@ -226,7 +226,7 @@ __device__ __forceinline__ void online_merge(float& m, float& s, float m2, float
     s = a + b; m = mn;
 }
 
-// single pass over the row: online log-sum-exp, 64-bit loads (rows are 8-byte aligned when V is even), 4 loads in flight
+// single pass over the row: online log-sum-exp, 128-bit loads (scalar head / tail around the 16-byte aligned body), 4 loads in flight
 __global__ void __launch_bounds__(256) cross_entropy_fwd_kernel(int V, const float* __restrict__ logits,
                                                                 const long long* __restrict__ targets,
                                                                 float* __restrict__ row_loss, float* __restrict__ lse_out) {
@@ -239,24 +239,28 @@ __global__ void __launch_bounds__(256) cross_entropy_fwd_kernel(int V, const flo
         return;
     }
     float m = -INFINITY, s = 0.f;
-    if ((V & 1) == 0) {
-        const int V2 = V >> 1;
-        const float2* x2 = reinterpret_cast<const float2*>(x);
-        int j = threadIdx.x;
-        for (; j + 3 * 256 < V2; j += 4 * 256) {
-            float2 v[4];
+    // scalar head up to the first 16-byte boundary of the row (rows of V = 9490 floats start 8-byte aligned on odd r),
+    // 128-bit body with four loads in flight per thread, scalar tail
+    const int head = min(V, (int)((4 - ((reinterpret_cast<uintptr_t>(x) >> 2) & 3)) & 3));
+    const int V4 = (V - head) >> 2;
+    if ((int)threadIdx.x < head) online_add(m, s, x[threadIdx.x]);
+    for (int v = head + 4 * V4 + threadIdx.x; v < V; v += 256) online_add(m, s, x[v]);
+    const float* xb = x + head;
+    int j = threadIdx.x;
+    for (; j + 3 * 256 < V4; j += 4 * 256) {
+        float4 v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = x2[j + u * 256];
+        for (int u = 0; u < 4; ++u) v[u] = ld_stream_f4(xb + 4 * (j + u * 256));
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float mx = fmaxf(v[u].x, v[u].y), mn = fmaxf(m, mx);
-                s = s * __expf(m - mn) + __expf(v[u].x - mn) + __expf(v[u].y - mn);
-                m = mn;
-            }
+        for (int u = 0; u < 4; ++u) {
+            const float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)), mn = fmaxf(m, mx);
+            s = s * __expf(m - mn) + __expf(v[u].x - mn) + __expf(v[u].y - mn) + __expf(v[u].z - mn) + __expf(v[u].w - mn);
+            m = mn;
         }
-        for (; j < V2; j += 256) { const float2 v = x2[j]; online_add(m, s, v.x); online_add(m, s, v.y); }
-    } else {
-        for (int v = threadIdx.x; v < V; v += 256) online_add(m, s, x[v]);
+    }
+    for (; j < V4; j += 256) {
+        const float4 v = ld_stream_f4(xb + 4 * j);
+        online_add(m, s, v.x); online_add(m, s, v.y); online_add(m, s, v.z); online_add(m, s, v.w);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -297,33 +301,48 @@ __global__ void __launch_bounds__(256) cross_entropy_bwd_kernel(int V, const flo
     }
     const float lse = lse_in[r];
     const float scale = inv_count * (upstream ? upstream[0] : 1.f);
-    // V even and rows 8-byte aligned (V = 9490): 64-bit loads / stores, four loads in flight per thread; otherwise scalar
-    if ((V & 1) == 0) {
-        const int V2 = V >> 1;
-        const float2* x2 = reinterpret_cast<const float2*>(x);
-        auto emit = [&](int j, float2 xv) {
-            float2 g;
-            g.x = (expf(xv.x - lse) - ((2 * j) == tgt ? 1.f : 0.f)) * scale;
-            g.y = (expf(xv.y - lse) - ((2 * j + 1) == tgt ? 1.f : 0.f)) * scale;
-            if (dx) *reinterpret_cast<float2*>(dx + 2 * j) = g;
-            if (d16r) *reinterpret_cast<__nv_bfloat162*>(d16r + 2 * j) = __floats2bfloat162_rn(g.x, g.y);
-        };
-        int j = threadIdx.x;
-        for (; j + 3 * 256 < V2; j += 4 * 256) {
-            float2 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = ld_stream_f2(x2 + j + u * 256);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) emit(j + u * 256, v[u]);
+    // scalar head up to the row's first 16-byte boundary, 128-bit body with four loads in flight per thread, scalar tail
+    // (the fp32 gradient rows share the alignment of the logit rows when both buffers are 16-byte aligned)
+    auto grad = [&](float xv, int v) { return (expf(xv - lse) - (v == tgt ? 1.f : 0.f)) * scale; };
+    auto emit1 = [&](int v) {
+        const float g = grad(x[v], v);
+        if (dx) dx[v] = g;
+        if (d16r) d16r[v] = __float2bfloat16_rn(g);
+    };
+    const int head = min(V, (int)((4 - ((reinterpret_cast<uintptr_t>(x) >> 2) & 3)) & 3));
+    const int V4 = (V - head) >> 2;
+    if ((int)threadIdx.x < head) emit1(threadIdx.x);
+    for (int v = head + 4 * V4 + threadIdx.x; v < V; v += 256) emit1(v);
+    const bool dx_vec = dx && ((reinterpret_cast<uintptr_t>(dx + head) & 15) == 0);
+    auto emit4 = [&](int jj, float4 xv) {
+        const int v = head + 4 * jj;
+        const float4 g = make_float4(grad(xv.x, v), grad(xv.y, v + 1), grad(xv.z, v + 2), grad(xv.w, v + 3));
+        if (dx) {
+            if (dx_vec) *reinterpret_cast<float4*>(dx + v) = g;
+            else { dx[v] = g.x; dx[v + 1] = g.y; dx[v + 2] = g.z; dx[v + 3] = g.w; }
         }
-        for (; j < V2; j += 256) emit(j, x2[j]);
-    } else {
-        for (int v = threadIdx.x; v < V; v += blockDim.x) {
-            const float g = (expf(x[v] - lse) - (v == tgt ? 1.f : 0.f)) * scale;
-            if (dx) dx[v] = g;
-            if (d16r) d16r[v] = __float2bfloat16_rn(g);
+        if (d16r) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(g.x, g.y), hi = __floats2bfloat162_rn(g.z, g.w);
+            if ((v & 3) == 0) {                                        // 8-byte aligned in the bf16 row
+                uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                *reinterpret_cast<uint2*>(d16r + v) = pk;
+            } else if ((v & 1) == 0) {
+                *reinterpret_cast<__nv_bfloat162*>(d16r + v) = lo; *reinterpret_cast<__nv_bfloat162*>(d16r + v + 2) = hi;
+            } else {
+                d16r[v] = __low2bfloat16(lo); d16r[v + 1] = __high2bfloat16(lo); d16r[v + 2] = __low2bfloat16(hi); d16r[v + 3] = __high2bfloat16(hi);
+            }
         }
+    };
+    const float* xb = x + head;
+    int j = threadIdx.x;
+    for (; j + 3 * 256 < V4; j += 4 * 256) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld_stream_f4(xb + 4 * (j + u * 256));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) emit4(j + u * 256, v[u]);
     }
+    for (; j < V4; j += 256) emit4(j, ld_stream_f4(xb + 4 * j));
 }
 
 }  // namespace

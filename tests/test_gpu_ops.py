@@ -167,10 +167,12 @@ def test_clip_adam_matches_torch_adam_with_clamp(cuda):
     H.assert_close_norm(p, p_ref.data, 1e-6, "adam params")
 
 
-def test_cross_entropy_matches_torch(cuda):
+@pytest.mark.parametrize("V", [9490, 9491, 9488, 9489, 5, 2])
+def test_cross_entropy_matches_torch(cuda, V):
+    """V = 9490: rows alternate between 16- and 8-byte alignment; odd V: every alignment (scalar head / tail paths)."""
     ops = _ops()
     g = torch.Generator().manual_seed(4)
-    R, V = 37, 9490
+    R = 37
     x = torch.randn(R, V, generator=g) * 3
     t = torch.randint(0, V, (R,), generator=g)
     t[5] = -1
@@ -285,6 +287,23 @@ def pair_mode(request):
     old = ops.gemm_set_pair_mode(request.param)
     yield request.param
     ops.gemm_set_pair_mode(old)
+
+
+@pytest.mark.parametrize("N", [9490, 9494, 70])
+def test_gemm_bf16_masked_rows_with_8_byte_aligned_row_stride(cuda, N):
+    """The vocabulary-layer shape: fp32 output rows of N = 9490 floats (row stride = 2 mod 4) with bias and a row mask —
+    the epilogue's shifted 128-bit store path; masked rows must be exactly 0."""
+    ops = _ops()
+    M, K = 300, 512
+    g = torch.Generator().manual_seed(N)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g)
+    mask = (torch.rand(M, generator=g) > 0.3).to(torch.uint8)
+    c = ops.gemm(a.to(cuda), b.to(cuda), bias1=bias.to(cuda), row_mask=mask.to(cuda), precision="bf16")
+    ref = (a.bfloat16().double() @ b.bfloat16().double().t() + bias.double()) * mask.double()[:, None]
+    H.assert_close_norm(c, ref, 2e-5, "masked tc gemm N=%d" % N)
+    assert torch.all(c[mask.to(cuda) == 0] == 0)
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 0), (0, 1), (1, 1)])
