@@ -160,16 +160,22 @@ __global__ void __launch_bounds__(256, 2) att_step_fwd_grouped_kernel(
         const float* __restrict__ att_dec, long long ld_dec,
         const float* __restrict__ w_full, const float* __restrict__ b_full,
         const float* __restrict__ fbeta_pre, long long ld_fb,
-        float* __restrict__ alpha, long long ld_alpha, float* __restrict__ gated) {
+        float* __restrict__ alpha, long long ld_alpha, float* __restrict__ gated,
+        const int* __restrict__ slot_img, const int* __restrict__ n_slots, const int* __restrict__ row_off) {
     extern __shared__ __align__(16) float sm[];
-    const int img = blockIdx.x;
-    const int kl = k_live ? min(k_live[img], K) : min(k, K);
+    // slot = the live beams of one image: state rows (att_dec / fbeta / gated) row_off[slot] + j, or slot*k + j without a
+    // row map; img = the image whose features the slot decodes (slot == img without a slot map).  alpha rows are
+    // addressed by IMAGE (img*k + j): the caller back-tracks them per image.
+    const int slot = blockIdx.x;
+    if (n_slots && slot >= n_slots[0]) return;
+    const int img = slot_img ? slot_img[slot] : slot;
+    const int kl = k_live ? min(k_live[slot], K) : min(k, K);
     if (kl <= 0) return;
     const int Pp = (P + 3) & ~3;
     float* s_dec = sm;                 // K * A
     float* s_wf = sm + K * A;          // A
     float* s_e = s_wf + A;             // K * Pp
-    const long long r0 = (long long)img * k;
+    const long long r0 = row_off ? (long long)row_off[slot] : (long long)slot * k, ra = (long long)img * k;
     for (int i = threadIdx.x; i < kl * A; i += blockDim.x) s_dec[i] = att_dec[(r0 + i / A) * ld_dec + (i % A)];
     for (int a = threadIdx.x; a < A; a += blockDim.x) s_wf[a] = w_full[a];
     __syncthreads();
@@ -226,7 +232,7 @@ __global__ void __launch_bounds__(256, 2) att_step_fwd_grouped_kernel(
         float sum = 0.f;
         for (int p = lane; p < P; p += 32) { const float ex = expf(e[p] - m); e[p] = ex; sum += ex; }
         sum = warp_sum(sum);
-        float* out = alpha + (r0 + j) * ld_alpha;
+        float* out = alpha + (ra + j) * ld_alpha;
         for (int p = lane; p < P; p += 32) { const float al = e[p] / sum; e[p] = al; out[p] = al; }
     }
     __syncthreads();
@@ -705,7 +711,7 @@ template <int K>
 static int launch_grouped(int n_img, int k, int P, int C, int A, const int* k_live, const float* enc, const float* att_enc,
                           const float* att_dec, int64_t ld_dec, const float* w_full, const float* b_full,
                           const float* fbeta_pre, int64_t ld_fb, float* alpha, int64_t ld_alpha, float* gated,
-                          cudaStream_t s) {
+                          const int* slot_img, const int* n_slots, const int* row_off, cudaStream_t s) {
     const size_t smem = ((size_t)K * A + A + (size_t)K * ((P + 3) & ~3)) * sizeof(float);
     ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_fwd_grouped: K*A too large for shared memory");
     static size_t configured = 48 * 1024;
@@ -714,7 +720,7 @@ static int launch_grouped(int n_img, int k, int P, int C, int A, const int* k_li
         configured = smem;
     }
     att_step_fwd_grouped_kernel<K><<<n_img, 256, smem, s>>>(k, P, C, A, k_live, enc, att_enc, att_dec, ld_dec, w_full, b_full,
-                                                            fbeta_pre, ld_fb, alpha, ld_alpha, gated);
+                                                            fbeta_pre, ld_fb, alpha, ld_alpha, gated, slot_img, n_slots, row_off);
     ICD_LAUNCH_CHECK();
     return 0;
 }
@@ -722,12 +728,13 @@ static int launch_grouped(int n_img, int k, int P, int C, int A, const int* k_li
 int icd_attention_step_fwd_grouped(int n_img, int k, int P, int C, int A, const int* k_live, const float* enc,
                                    const float* att_enc, const float* att_dec, int64_t ld_dec, const float* w_full,
                                    const float* b_full, const float* fbeta_pre, int64_t ld_fb, float* alpha,
-                                   int64_t ld_alpha, float* gated, cudaStream_t s) {
+                                   int64_t ld_alpha, float* gated, const int* slot_img, const int* n_slots, const int* row_off,
+                                   cudaStream_t s) {
     if (n_img == 0) return 0;
     ICD_CHECK_ARG(k >= 1 && k <= 8, "attention_step_fwd_grouped: k=%d (1..8)", k);
     ICD_CHECK_ARG(A % 4 == 0 && C % 4 == 0 && ld_dec % 4 == 0 && ld_fb % 4 == 0, "attention_step_fwd_grouped: misaligned dims");
 #define ICD_GROUPED(KK) return launch_grouped<KK>(n_img, k, P, C, A, k_live, enc, att_enc, att_dec, ld_dec, w_full, b_full, \
-                                                  fbeta_pre, ld_fb, alpha, ld_alpha, gated, s)
+                                                  fbeta_pre, ld_fb, alpha, ld_alpha, gated, slot_img, n_slots, row_off, s)
     switch (k) {
         case 1: ICD_GROUPED(1);
         case 2: ICD_GROUPED(2);

@@ -7,6 +7,12 @@
 // No host synchronisation inside the loop; sequences and alpha frames are reconstructed at the end by
 // back-tracking parent pointers, so no per-step copy of the growing (k, step, 14, 14) alpha tensor (:89).
 //
+// Finished images leave the working set (the reference stops an image's loop at k == 0, :118): the decoder state lives in
+// SLOTS (one per unfinished image) whose live beams occupy consecutive rows; after every step both the slots and the rows
+// of the surviving beams are compacted to the front (device-side scans),
+// and every kernel of the next step — including the tensor-core contractions, which read their row count from device
+// memory — only touches the live slots.  Per-image results (history, alpha frames, winners) stay indexed by image.
+//
 // Reference semantics kept: step 1 candidates come from beam 0 only (:78-79); later steps take the top
 // k_live (= remaining beams) of the flattened (k_live * V) scores, sorted descending (:82); scores are raw
 // summed log-probs (:74-76); beams that emit <end> leave the beam and are never replaced (:93-104); the winner is
@@ -22,6 +28,9 @@ struct BeamWs {
     float *att_enc, *mean, *h0, *c0, *h, *c, *h_tmp, *c_tmp, *w_cat, *b_cat, *emb_x, *z, *gated, *gates_pre,
           *gates_act_unused, *logits, *alpha_steps, *score, *best_score;
     int *img_index, *prev_word, *k_live, *src, *parent, *word, *best_step, *best_parent;
+    int *slot_img, *slot_img_tmp, *k_live_tmp, *new_slot, *n_live, *word_tmp;   // n_live[0] = live slots, [1] = live rows
+    int *row_off[2];                                                            // slot -> first state row (ping-pong per step)
+    float* score_tmp;
     long long* tok64;
     // ICD_PREC_FP32X3: 3-term bf16 splits (gemm_tc.cu) of the weights (once per call) and of the step activations
     void *x3_We, *x3_Wcat, *x3_WihE, *x3_WihC, *x3_Wh, *x3_Wc, *x3_Wfc, *x3_act;
@@ -47,12 +56,16 @@ size_t carve(const icd_beam_desc_t* d, BeamWs* w, char* base) {
     TAKE_F(emb_x, R * E) TAKE_F(z, R * NZ) TAKE_F(gated, R * C) TAKE_F(gates_pre, R * 4 * D)
     TAKE_F(logits, R * V)
     TAKE_F(alpha_steps, S * R * P)
-    TAKE_F(score, R) TAKE_F(best_score, (size_t)d->n_img)
+    TAKE_F(score, R) TAKE_F(score_tmp, R) TAKE_F(best_score, (size_t)d->n_img)
 #undef TAKE_F
     int* ip;
 #define TAKE_I(name, n) ip = (int*)take(sizeof(int) * (n)); if (w) w->name = ip;
     TAKE_I(img_index, R) TAKE_I(prev_word, R) TAKE_I(k_live, (size_t)d->n_img) TAKE_I(src, R)
     TAKE_I(parent, S * R) TAKE_I(word, S * R) TAKE_I(best_step, (size_t)d->n_img) TAKE_I(best_parent, (size_t)d->n_img)
+    TAKE_I(slot_img, (size_t)d->n_img) TAKE_I(slot_img_tmp, (size_t)d->n_img) TAKE_I(k_live_tmp, (size_t)d->n_img)
+    TAKE_I(new_slot, (size_t)d->n_img) TAKE_I(n_live, 4) TAKE_I(word_tmp, R)
+    ip = (int*)take(sizeof(int) * (size_t)d->n_img); if (w) w->row_off[0] = ip;
+    ip = (int*)take(sizeof(int) * (size_t)d->n_img); if (w) w->row_off[1] = ip;
 #undef TAKE_I
     long long* lp = (long long*)take(sizeof(long long) * R); if (w) w->tok64 = lp;
     if (d->precision == ICD_PREC_FP32X3) {
@@ -79,7 +92,8 @@ __global__ void beam_init_kernel(int n_img, int k, int D, int start_id, const fl
                                  const float* __restrict__ c0, float* __restrict__ h, float* __restrict__ c,
                                  int* __restrict__ img_index, int* __restrict__ prev_word, long long* __restrict__ tok64,
                                  float* __restrict__ score, int* __restrict__ k_live, float* __restrict__ best_score,
-                                 int* __restrict__ best_step, int* __restrict__ best_parent) {
+                                 int* __restrict__ best_step, int* __restrict__ best_parent,
+                                 int* __restrict__ slot_img, int* __restrict__ n_live, int* __restrict__ row_off) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long R = (long long)n_img * k;
     if (i < R * D) {
@@ -89,19 +103,24 @@ __global__ void beam_init_kernel(int n_img, int k, int D, int start_id, const fl
         c[i] = c0[img * D + dd];
     }
     if (i < R) { img_index[i] = (int)(i / k); prev_word[i] = start_id; tok64[i] = start_id; score[i] = 0.f; }   // :47-52
-    if (i < n_img) { k_live[i] = k; best_score[i] = -INFINITY; best_step[i] = 0; best_parent[i] = 0; }
+    if (i < n_img) { k_live[i] = k; best_score[i] = -INFINITY; best_step[i] = 0; best_parent[i] = 0; slot_img[i] = (int)i; row_off[i] = (int)i * k; }
+    if (i == 0) { n_live[0] = n_img; n_live[1] = (int)R; }
 }
 
 __device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
     return v > bv || (v == bv && i < bi);
 }
 
-// One CTA per image.  log_softmax over V for each live row, add the running score, top-k_live over the
+// One CTA per live slot.  log_softmax over V for each live row, add the running score, top-k_live over the
 // flattened candidates (ties: lower flat index first), then the beam bookkeeping of gen_captions.py:85-116.
+// State of the surviving beams goes to the *_tmp arrays (slot rows; beam_reorder_kernel moves it to the compacted slots),
+// history (parent / word / trace) and winners are written per IMAGE.
 __global__ void __launch_bounds__(256) beam_topk_kernel(
         int k, int V, int step, int end_id, const float* __restrict__ logits,
-        float* __restrict__ score, int* __restrict__ prev_word, long long* __restrict__ tok64,
-        int* __restrict__ k_live, int* __restrict__ src,
+        const float* __restrict__ score, const int* __restrict__ k_live, const int* __restrict__ slot_img,
+        const int* __restrict__ n_live, const int* __restrict__ row_off,
+        float* __restrict__ score_tmp, int* __restrict__ word_tmp, int* __restrict__ k_live_tmp,
+        int* __restrict__ slot_img_tmp, int* __restrict__ src,
         int* __restrict__ parent_s, int* __restrict__ word_s, int* __restrict__ trace_s,
         float* __restrict__ best_score, int* __restrict__ best_step, int* __restrict__ best_parent) {
     __shared__ float s_red[40];
@@ -110,12 +129,13 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
     __shared__ int s_ci[256 * KMAX];
     __shared__ float s_topv[KMAX];
     __shared__ int s_topi[KMAX];
-    const int img = blockIdx.x;
-    const int kl = k_live[img];
-    if (trace_s) for (int j = threadIdx.x; j < k; j += blockDim.x) trace_s[img * k + j] = -1;
-    if (kl == 0) return;
+    const int slot = blockIdx.x;
+    if (slot >= n_live[0]) return;                                   // trace rows of finished images were preset to -1
+    const int img = slot_img[slot];
+    const int kl = k_live[slot];                                     // > 0: empty slots were compacted away
     const int nrows = (step == 1) ? 1 : kl;                                                  // :78-82
-    const float* lg = logits + (long long)img * k * V;
+    const int row0 = row_off[slot];                                  // first state row of this slot
+    const float* lg = logits + (long long)row0 * V;
     // rows are streamed with 64-bit loads, 4 in flight per thread (rows are 8-byte aligned when V is even)
     const bool even = (V & 1) == 0;
     const int V2 = V >> 1;
@@ -152,7 +172,7 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
             for (int v = threadIdx.x; v < V; v += blockDim.x) sum += expf(x[v] - m);
         }
         sum = block_sum(sum, s_red);
-        if (threadIdx.x == 0) { s_max[i] = m; s_lsum[i] = logf(sum); s_score[i] = score[img * k + i]; }
+        if (threadIdx.x == 0) { s_max[i] = m; s_lsum[i] = logf(sum); s_score[i] = score[row0 + i]; }
     }
     __syncthreads();
     // thread-local top-KMAX over this thread's slice of the flattened (nrows*V) candidates (flat index f = i*V + v)
@@ -231,24 +251,86 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
             if (next == end_id) {                                                            // :93-103
                 if (val > bs) { bs = val; best_score[img] = val; best_step[img] = step; best_parent[img] = prev; }
             } else {                                                                         // :109-116
-                const int r = img * k + nlive;
-                src[r] = prev; parent_s[r] = prev; word_s[r] = next;
-                prev_word[r] = next; tok64[r] = next; score[r] = val;
+                const int r = slot * k + nlive, ri = img * k + nlive;
+                src[r] = prev; score_tmp[r] = val; word_tmp[r] = next;
+                parent_s[ri] = prev; word_s[ri] = next;
                 ++nlive;
             }
         }
-        k_live[img] = nlive;                                                                 // :104
+        k_live_tmp[slot] = nlive;                                                            // :104
+        slot_img_tmp[slot] = img;
     }
 }
 
-__global__ void beam_reorder_kernel(int k, int D, const int* __restrict__ k_live, const int* __restrict__ src,
+// Compaction map after a step: new_slot[s] = rank of slot s among the slots that still have live beams (-1: finished or
+// beyond the previous live count); n_live = {live slots, live rows}.  One CTA, block-wide scan in chunks of 1024 slots.
+__global__ void __launch_bounds__(1024) beam_compact_kernel(int n_img, int k, const int* __restrict__ k_live_tmp,
+                                                            int* __restrict__ new_slot, int* __restrict__ n_live,
+                                                            int* __restrict__ row_off_new) {
+    __shared__ int s_warp[32], s_wrow[32];
+    __shared__ int s_carry, s_rcarry;
+    const int n_prev = n_live[0];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_carry = 0; s_rcarry = 0; }
+    __syncthreads();
+    for (int base = 0; base < n_img; base += 1024) {
+        const int s = base + threadIdx.x;
+        const int kl = (s < n_prev) ? k_live_tmp[s] : 0;
+        const int flag = kl > 0 ? 1 : 0;
+        int incl = flag, rincl = kl;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o), rv = __shfl_up_sync(0xffffffffu, rincl, o);
+            if (lane >= o) { incl += v; rincl += rv; }
+        }
+        if (lane == 31) { s_warp[warp] = incl; s_wrow[warp] = rincl; }
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane], rw = s_wrow[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, w, o), rv = __shfl_up_sync(0xffffffffu, rw, o);
+                if (lane >= o) { w += v; rw += rv; }
+            }
+            s_warp[lane] = w; s_wrow[lane] = rw;
+        }
+        __syncthreads();
+        const int before = s_carry + (warp > 0 ? s_warp[warp - 1] : 0) + incl - flag;
+        const int rbefore = s_rcarry + (warp > 0 ? s_wrow[warp - 1] : 0) + rincl - kl;
+        if (s < n_img) new_slot[s] = flag ? before : -1;
+        if (flag) row_off_new[before] = rbefore;                     // first state row of the compacted slot
+        __syncthreads();
+        if (threadIdx.x == 1023) { s_carry += s_warp[31]; s_rcarry += s_wrow[31]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { n_live[0] = s_carry; n_live[1] = s_rcarry; }
+}
+
+// Move the surviving beams of old slot s to its compacted slot new_slot[s]: h / c rows follow the parent pointers (:109-110),
+// the small per-row state (score, previous word) and the per-slot state (live count, image) move with them.  Reads only
+// *_tmp / h_tmp / c_tmp, writes only the current arrays, so the moves of different slots never collide.
+__global__ void beam_reorder_kernel(int k, int D, const int* __restrict__ new_slot, const int* __restrict__ k_live_tmp,
+                                    const int* __restrict__ slot_img_tmp, const int* __restrict__ src,
+                                    const float* __restrict__ score_tmp, const int* __restrict__ word_tmp,
                                     const float* __restrict__ h_tmp, const float* __restrict__ c_tmp,
-                                    float* __restrict__ h, float* __restrict__ c) {
-    const int r = blockIdx.x;                       // destination row
-    const int img = r / k, j = r % k;
-    if (j >= k_live[img]) return;
-    const long long so = ((long long)img * k + src[r]) * D, dst = (long long)r * D;
+                                    float* __restrict__ h, float* __restrict__ c, float* __restrict__ score,
+                                    int* __restrict__ prev_word, long long* __restrict__ tok64,
+                                    int* __restrict__ k_live, int* __restrict__ slot_img,
+                                    const int* __restrict__ row_off_old, const int* __restrict__ row_off_new) {
+    const int r = blockIdx.x;                       // (old slot, surviving beam j): index into the *_tmp arrays
+    const int s = r / k, j = r % k;
+    const int dslot = new_slot[s];
+    if (dslot < 0) return;
+    const int kl = k_live_tmp[s];
+    if (j >= kl) return;
+    const int dr = row_off_new[dslot] + j;
+    const long long so = ((long long)row_off_old[s] + src[r]) * D, dst = (long long)dr * D;
     for (int dd = threadIdx.x; dd < D; dd += blockDim.x) { h[dst + dd] = h_tmp[so + dd]; c[dst + dd] = c_tmp[so + dd]; }
+    if (threadIdx.x == 0) {
+        score[dr] = score_tmp[r];
+        prev_word[dr] = word_tmp[r]; tok64[dr] = word_tmp[r];
+        if (j == 0) { k_live[dslot] = kl; slot_img[dslot] = slot_img_tmp[s]; }
+    }
 }
 
 // Back-track the winner of each image.
@@ -290,8 +372,10 @@ __global__ void beam_finalize_kernel(int k, int P, int S1 /* max_steps+1 */, lon
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ table_f32, const double* __restrict__ table_f64,
-                                   const long long* __restrict__ tok, int E, float* __restrict__ out) {
+                                   const long long* __restrict__ tok, int E, float* __restrict__ out,
+                                   const int* __restrict__ n_live) {
     const long long r = blockIdx.x;
+    if (r >= n_live[1]) return;
     const long long t = tok[r];
     for (int e = threadIdx.x; e < E; e += blockDim.x)
         out[r * E + e] = table_f64 ? (float)table_f64[t * E + e] : table_f32[t * E + e];
@@ -303,14 +387,16 @@ __global__ void gather_rows_kernel(const float* __restrict__ table_f32, const do
 // activation split on the fly and the weight split `w16x3` prepared once per call.
 int beam_mm(int prec, const BeamWs& w, const float* x, long long ldx, int rows, int K, const float* W, long long ldw,
             const void* w16x3, float* y, long long ldy, int N, const float* bias, const float* add, long long ldadd,
-            float beta, cudaStream_t s) {
+            float beta, cudaStream_t s, const int* m_live = nullptr) {
+    // m_live: device-side count of live rows (compacted to the front).  The tensor-core tier computes only those; the fp32
+    // FMA tier computes all `rows` (rows beyond the live count hold stale, finite state and are never read back).
     if (prec != ICD_PREC_FP32X3)
         return icd_gemm_simple(ICD_PREC_FP32, x, ldx, 1, W, ldw, 1, y, ldy, rows, N, K, bias, nullptr, add, ldadd, nullptr, 0,
                                nullptr, beta, s);
     const long long seg = up8ll(K);
-    ICD_TRY(icd_split3_bf16(x, ldx, rows, K, w.x3_act, 0, s));
+    ICD_TRY(icd_split3_bf16(x, ldx, rows, K, w.x3_act, 0, s, m_live));
     return icd_gemm_bf16_ex(w.x3_act, 6 * seg, 0, w16x3, 6 * seg, 0, y, ldy, rows, N, (int)(6 * seg), bias, nullptr, add, ldadd,
-                            nullptr, 0, nullptr, beta, s, nullptr, 0, w.x3_splitk, w.x3_splitk_floats);
+                            nullptr, 0, nullptr, beta, s, nullptr, 0, w.x3_splitk, w.x3_splitk_floats, nullptr, m_live);
 }
 
 extern "C" int64_t icd_beam_search_ws_bytes(const icd_beam_desc_t* d) {
@@ -365,31 +451,42 @@ extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
         const long long n = R * D;
         beam_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n_img, k, D, d->start_id, w.h0, w.c0, w.h, w.c,
                                                                       w.img_index, w.prev_word, w.tok64, w.score, w.k_live,
-                                                                      w.best_score, w.best_step, w.best_parent);
+                                                                      w.best_score, w.best_step, w.best_parent,
+                                                                      w.slot_img, w.n_live, w.row_off[0]);
         ICD_LAUNCH_CHECK();
     }
+    // candidate words of images that are already finished at a step stay -1 (:91 prints nothing for them)
+    if (d->trace_words) ICD_CUDA(cudaMemsetAsync(d->trace_words, 0xff, sizeof(int32_t) * (size_t)S1 * R, s));
+    const int* live_rows = w.n_live + 1;
     for (int step = 1; step <= S1; ++step) {
         float* alpha_s = w.alpha_steps + (size_t)(step - 1) * R * P;
+        const int* row_off = w.row_off[(step - 1) & 1];
+        int* row_off_next = w.row_off[step & 1];
         gather_rows_kernel<<<(unsigned)R, 128, 0, s>>>(d->emb_is_f64 ? nullptr : (const float*)d->emb_w,
                                                        d->emb_is_f64 ? (const double*)d->emb_w : nullptr,
-                                                       w.tok64, E, w.emb_x);                 // :65
+                                                       w.tok64, E, w.emb_x, w.n_live);       // :65
         ICD_LAUNCH_CHECK();
-        ICD_TRY(beam_mm(prec, w, w.h, D, (int)R, D, w.w_cat, D, w.x3_Wcat, w.z, NZ, NZ, w.b_cat, nullptr, 0, 0.f, s));
-        // :66-69 — one CTA per image serves all of its live beams (features read once per image, finished images skipped)
+        ICD_TRY(beam_mm(prec, w, w.h, D, (int)R, D, w.w_cat, D, w.x3_Wcat, w.z, NZ, NZ, w.b_cat, nullptr, 0, 0.f, s, live_rows));
+        // :66-69 — one CTA per live slot serves all of its live beams (features read once per image and step)
         ICD_TRY(icd_attention_step_fwd_grouped(n_img, k, P, C, A, w.k_live, d->enc, w.att_enc, w.z, NZ, d->full_att_w,
-                                               d->full_att_b, w.z + A, NZ, alpha_s, P, w.gated, s));
+                                               d->full_att_b, w.z + A, NZ, alpha_s, P, w.gated, w.slot_img, w.n_live, row_off, s));
         ICD_TRY(beam_mm(prec, w, w.emb_x, E, (int)R, E, d->w_ih, E + C, w.x3_WihE, w.gates_pre, 4 * D, 4 * D,
-                        d->b_ih, w.z + A + C, NZ, 0.f, s));
+                        d->b_ih, w.z + A + C, NZ, 0.f, s, live_rows));
         ICD_TRY(beam_mm(prec, w, w.gated, C, (int)R, C, d->w_ih + E, E + C, w.x3_WihC, w.gates_pre, 4 * D, 4 * D,
-                        nullptr, nullptr, 0, 1.f, s));                                       // :70-71
+                        nullptr, nullptr, 0, 1.f, s, live_rows));                            // :70-71
         ICD_TRY(icd_lstm_pointwise_fwd((int)R, D, w.gates_pre, w.c, nullptr, w.c_tmp, w.h_tmp, nullptr, 0, nullptr, 1.f, s));
-        ICD_TRY(beam_mm(prec, w, w.h_tmp, D, (int)R, D, d->fc_w, D, w.x3_Wfc, w.logits, V, V, d->fc_b, nullptr, 0, 0.f, s));   // :72
-        beam_topk_kernel<<<n_img, 256, 0, s>>>(k, V, step, d->end_id, w.logits, w.score, w.prev_word, w.tok64, w.k_live,
-                                               w.src, w.parent + (size_t)(step - 1) * R, w.word + (size_t)(step - 1) * R,
+        ICD_TRY(beam_mm(prec, w, w.h_tmp, D, (int)R, D, d->fc_w, D, w.x3_Wfc, w.logits, V, V, d->fc_b, nullptr, 0, 0.f, s, live_rows));   // :72
+        beam_topk_kernel<<<n_img, 256, 0, s>>>(k, V, step, d->end_id, w.logits, w.score, w.k_live, w.slot_img, w.n_live, row_off,
+                                               w.score_tmp, w.word_tmp, w.k_live_tmp, w.slot_img_tmp, w.src,
+                                               w.parent + (size_t)(step - 1) * R, w.word + (size_t)(step - 1) * R,
                                                d->trace_words ? d->trace_words + (size_t)(step - 1) * R : nullptr,
                                                w.best_score, w.best_step, w.best_parent);
         ICD_LAUNCH_CHECK();
-        beam_reorder_kernel<<<(unsigned)R, 128, 0, s>>>(k, D, w.k_live, w.src, w.h_tmp, w.c_tmp, w.h, w.c);
+        beam_compact_kernel<<<1, 1024, 0, s>>>(n_img, k, w.k_live_tmp, w.new_slot, w.n_live, row_off_next);
+        ICD_LAUNCH_CHECK();
+        beam_reorder_kernel<<<(unsigned)R, 128, 0, s>>>(k, D, w.new_slot, w.k_live_tmp, w.slot_img_tmp, w.src, w.score_tmp,
+                                                        w.word_tmp, w.h_tmp, w.c_tmp, w.h, w.c, w.score, w.prev_word, w.tok64,
+                                                        w.k_live, w.slot_img, row_off, row_off_next);
         ICD_LAUNCH_CHECK();
     }
     beam_finalize_kernel<<<n_img, 128, 0, s>>>(k, P, S1, R, d->start_id, d->end_id, w.best_score, w.best_step,

@@ -151,7 +151,9 @@ int icd_weighted_pixel_sum(int rows, int P, int C, const int32_t* img_index, con
 int icd_attention_step_fwd_grouped(int n_img, int k, int P, int C, int A, const int* k_live, const float* enc,
                                    const float* att_enc, const float* att_dec, int64_t ld_dec, const float* w_full,
                                    const float* b_full, const float* fbeta_pre, int64_t ld_fb, float* alpha,
-                                   int64_t ld_alpha, float* gated, cudaStream_t s);
+                                   int64_t ld_alpha, float* gated, const int* slot_img /* slot -> image, or NULL */,
+                                   const int* n_slots /* device: live slots, or NULL */,
+                                   const int* row_off /* slot -> first state row, or NULL (slot*k) */, cudaStream_t s);
 void icd_gemm_simple_set_ws(void* ws, int64_t bytes);
 struct IcdSimpleWsScope {          // RAII: workspace for icd_gemm_simple's tensor-core tiers during one entry-point call
     IcdSimpleWsScope(void* ws, int64_t bytes) { icd_gemm_simple_set_ws(ws, bytes); }

@@ -53,6 +53,8 @@ struct KArgs {
     float* partial;                           // [splits][M][N] raw accumulators when splits > 1
     int cluster;                              // 1, or 2: CTA pairs (thread-block cluster of 2 along M) share every B tile —
                                               // each CTA fetches half of it and TMA-multicasts it into both shared memories
+    const int* m_live;                        // optional DEVICE row count: only rows < min(M, *m_live) are computed / written
+                                              // (beam search: the live rows are compacted to the front, no host round trip)
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -305,11 +307,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // unit sequence, so their pipelines run in lock step through the shared empty barriers
     const int CL = p.cluster;
     const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
-    const int tiles_m = (e.M + BM - 1) / BM, tiles_n = (e.N + BN - 1) / BN;
-    const int tiles_mc = (tiles_m + CL - 1) / CL;
-    const int num_tiles = tiles_mc * tiles_n;                            // super tiles
+    const int tiles_n = (e.N + BN - 1) / BN;
     const int nkb = (e.K + BK - 1) / BK;
-    const int num_units = num_tiles * p.splits;
     const int unit0 = blockIdx.x / CL, unit_stride = gridDim.x / CL;
 
     if (warp == 0 && lane == 0) {
@@ -333,6 +332,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // from here on operands / epilogue inputs produced upstream are read and C is written
     pdl_trigger();
     pdl_wait();
+    const int M_eff = p.m_live ? min(e.M, max(*p.m_live, 0)) : e.M;     // device-side row count (read after the dependency wait)
+    const int tiles_m = (M_eff + BM - 1) / BM;
+    const int tiles_mc = (tiles_m + CL - 1) / CL;
+    const int num_tiles = tiles_mc * tiles_n;                            // super tiles
+    const int num_units = num_tiles * p.splits;
 
     if (warp == 0) {
         // =================================== TMA producer ===================================
@@ -417,6 +421,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int tile = unit % num_tiles, slice = unit / num_tiles;
             const int m0 = ((tile % tiles_mc) * CL + (int)crank) * BM, n0 = (tile / tiles_mc) * BN;
             EpiArgs ee = e;
+            ee.M = M_eff;
             if (p.splits > 1) {                                       // raw partial tile, epilogue deferred
                 ee.C = p.partial + (long long)slice * e.M * e.N; ee.ldc = e.N;
                 ee.bias1 = ee.bias2 = ee.add1 = ee.add2 = nullptr; ee.row_mask = nullptr; ee.beta = 0.f; ee.C16 = nullptr;
@@ -430,7 +435,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c = cg; c < NCHUNK; c += 2) {
                 const int nb = n0 + c * 32;
                 const bool last = (c + 2 >= NCHUNK);
-                if (nb < e.N && mrow0 < e.M) {                        // warp-uniform
+                if (nb < e.N && mrow0 < M_eff) {                        // warp-uniform
                     uint32_t v[32];
                     tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
                     tc_wait_ld();
@@ -530,11 +535,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const EpiArgs& e = p.e;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();                           // 0 = leader
-    const int tiles_m = (e.M + BM - 1) / BM, tiles_n = (e.N + BN - 1) / BN;
-    const int tiles_mc = (tiles_m + 1) / 2;
-    const int num_tiles = tiles_mc * tiles_n;                            // 256 x BN super tiles
+    const int tiles_n = (e.N + BN - 1) / BN;
     const int nkb = (e.K + BK - 1) / BK;
-    const int num_units = num_tiles * p.splits;
     const int unit0 = blockIdx.x / 2, unit_stride = gridDim.x / 2;
 
     if (warp == 0 && lane == 0) {
@@ -556,6 +558,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
     pdl_trigger();
     pdl_wait();
+    const int M_eff = p.m_live ? min(e.M, max(*p.m_live, 0)) : e.M;
+    const int tiles_m = (M_eff + BM - 1) / BM;
+    const int tiles_mc = (tiles_m + 1) / 2;
+    const int num_tiles = tiles_mc * tiles_n;                            // 256 x BN super tiles
+    const int num_units = num_tiles * p.splits;
 
     if (warp == 0) {
         // =================================== TMA producer (both CTAs) ===================================
@@ -628,6 +635,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int tile = unit % num_tiles, slice = unit / num_tiles;
             const int m0 = ((tile % tiles_mc) * 2 + (int)crank) * BM, n0 = (tile / tiles_mc) * BN;
             EpiArgs ee = e;
+            ee.M = M_eff;
             if (p.splits > 1) {
                 ee.C = p.partial + (long long)slice * e.M * e.N; ee.ldc = e.N;
                 ee.bias1 = ee.bias2 = ee.add1 = ee.add2 = nullptr; ee.row_mask = nullptr; ee.beta = 0.f; ee.C16 = nullptr;
@@ -642,7 +650,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int c = cg; c < NCHUNK; c += 2) {
                 const int nb = n0 + c * 32;
                 const bool last = (c + 2 >= NCHUNK);
-                if (nb < e.N && mrow0 < e.M) {
+                if (nb < e.N && mrow0 < M_eff) {
                     uint32_t v[32];
                     tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
                     tc_wait_ld();
@@ -784,7 +792,8 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16& b1, __nv_bfloat16
 }
 // K-major source rows: dst[r*ldd + s*seg + c] = term_s(src[r*s_r + c]), c < cols; pad columns [cols, seg) zeroed.
 __global__ void split3_rows_kernel(const float* __restrict__ src, long long s_r, int rows, int cols, int seg,
-                                   __nv_bfloat16* __restrict__ dst, long long ldd, int which) {
+                                   __nv_bfloat16* __restrict__ dst, long long ldd, int which, const int* __restrict__ m_live) {
+    if (m_live) rows = min(rows, max(*m_live, 0));              // device-side row count (beam search)
     const long long total = (long long)rows * seg;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / seg; const int c = (int)(i % seg);
@@ -974,15 +983,16 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
                      float* C, int64_t ldc, int M, int N, int K,
                      const float* bias1, const float* bias2, const float* add1, int64_t ld1,
                      const float* add2, int64_t ld2, const uint8_t* row_mask, float beta, cudaStream_t s,
-                     void* C16, int64_t ldc16, float* splitk_ws, int64_t splitk_ws_floats, int* deferred_splits) {
+                     void* C16, int64_t ldc16, float* splitk_ws, int64_t splitk_ws_floats, int* deferred_splits,
+                     const int* m_live) {
     if (deferred_splits) *deferred_splits = 0;
     if (M == 0 || N == 0) return 0;
     ICD_CHECK_ARG(K > 0, "gemm_tc: K must be positive");
     ICD_CHECK_ARG(C != nullptr || C16 != nullptr, "gemm_tc: no output");
-    Plan pl = make_plan(M, N, K, splitk_ws != nullptr);
+    Plan pl = make_plan(M, N, K, splitk_ws != nullptr && m_live == nullptr);   // a device-side row count excludes split-K
     if (const char* f = getenv("ICD_GEMM_FORCE_PLAN")) {           // diagnostic: "bn,splits" (tools/gemm_bench.py)
         int bn = 0, sp = 0;
-        if (sscanf(f, "%d,%d", &bn, &sp) == 2 && (bn == 64 || bn == 128 || bn == 256) && sp >= 1 && (sp == 1 || splitk_ws)) {
+        if (sscanf(f, "%d,%d", &bn, &sp) == 2 && (bn == 64 || bn == 128 || bn == 256) && sp >= 1 && (sp == 1 || (splitk_ws && !m_live))) {
             const int nkb = (K + BK - 1) / BK;
             pl.bn = bn; pl.kb_per_split = (nkb + sp - 1) / sp; pl.splits = (nkb + pl.kb_per_split - 1) / pl.kb_per_split;
         }
@@ -1015,6 +1025,7 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
     k.a_mn = a_mn ? 1 : 0; k.b_mn = b_mn ? 1 : 0;
     k.splits = pl.splits; k.kb_per_split = pl.kb_per_split; k.partial = splitk_ws;
     k.cluster = cluster;
+    k.m_live = m_live;
     const int tiles = ((tiles_m + cluster - 1) / cluster) * ((N + pl.bn - 1) / pl.bn);      // super tiles when paired
     const int units = tiles * pl.splits;
     if (mode == 2) {
@@ -1102,14 +1113,14 @@ int icd_gemm_tc_launch(const icd_gemm_desc_t* d, cudaStream_t s) {
 
 // ---------------------------------------------------------------------------------------------- fp32-grade (3-term) tier
 // K-major operand [rows][K] -> bf16 [rows][6*seg], seg = up8(K); returns the leading dimension.
-int icd_split3_bf16(const float* src, int64_t s_r, int rows, int cols, void* dst, int which, cudaStream_t s) {
+int icd_split3_bf16(const float* src, int64_t s_r, int rows, int cols, void* dst, int which, cudaStream_t s, const int* m_live) {
     if (rows == 0 || cols == 0) return 0;
     const int seg = (int)up8(cols);
     const long long total = (long long)rows * seg;
     long long blocks = (total + 255) / 256;
     if (blocks > ICD_NUM_SMS * 16) blocks = ICD_NUM_SMS * 16;
     split3_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, s_r, rows, cols, seg, reinterpret_cast<__nv_bfloat16*>(dst),
-                                                        6LL * seg, which);
+                                                        6LL * seg, which, m_live);
     ICD_LAUNCH_CHECK();
     return 0;
 }

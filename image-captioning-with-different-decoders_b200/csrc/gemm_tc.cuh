@@ -19,15 +19,18 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
                      const float* bias1, const float* bias2, const float* add1, int64_t ld1,
                      const float* add2, int64_t ld2, const uint8_t* row_mask, float beta, cudaStream_t s,
                      void* C16, int64_t ldc16, float* splitk_ws, int64_t splitk_ws_floats,
-                     int* deferred_splits = nullptr);
+                     int* deferred_splits = nullptr, const int* m_live = nullptr);
 // deferred_splits != NULL: when the plan splits K, the reduce pass is LEFT TO THE CONSUMER — the raw K-slice partials stay in
 // splitk_ws as [*deferred_splits][M][N] fp32 planes and C is not written (*deferred_splits = 0: C was written normally,
 // epilogue included).  Only for calls whose epilogue is empty (no bias / add / mask / beta / C16).
+// m_live != NULL: DEVICE-side row count — only rows < min(M, *m_live) are computed and written (tile loop bounds are
+// derived in the kernel, after its dependency wait); the plan then never splits K.
 int icd_splitk_finish(const float* splitk_ws, int splits, int M, int N, float* C, int64_t ldc, void* C16, int64_t ldc16,
                       cudaStream_t s);
 int64_t icd_gemm_bf16_splitk_floats(int M, int N, int K);
 int64_t icd_gemm_tc_ws_bytes(int M, int N, int K);
 // fp32-grade tier (ICD_PREC_FP32X3): 3-term bf16 split laid out along K (A pattern which = 0, B pattern which = 1):
 // K-major fp32 [rows][cols] (row stride s_r) -> bf16 [rows][6 * up8(cols)]
-int icd_split3_bf16(const float* src, int64_t s_r, int rows, int cols, void* dst, int which, cudaStream_t s);
+int icd_split3_bf16(const float* src, int64_t s_r, int rows, int cols, void* dst, int which, cudaStream_t s,
+                    const int* m_live = nullptr);   // m_live: optional device-side row count (rows beyond it are skipped)
 int64_t icd_gemm_x3_ws_bytes(int M, int N, int K);
