@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256, 4) att_step_fwd_kernel(
 // smem: K*A (att_dec) + A (w_full) + K*Ppad (scores / alpha) floats.
 // ------------------------------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(256, 2) att_step_fwd_grouped_kernel(
+__global__ void __launch_bounds__(256, 3) att_step_fwd_grouped_kernel(
         int k, int P, int C, int A, const int* __restrict__ k_live,
         const float* __restrict__ enc, const float* __restrict__ att_enc,
         const float* __restrict__ att_dec, long long ld_dec,
@@ -183,42 +183,50 @@ __global__ void __launch_bounds__(256, 2) att_step_fwd_grouped_kernel(
     const float bfull = b_full ? b_full[0] : 0.f;
     const int A4 = A >> 2;
     const float* ae = att_enc + (long long)img * P * A;
-    for (int p = warp; p < P; p += nwarp) {
-        float acc[K];
+    // GROUPED_ROWS pixel rows per warp iteration: a lane loads the same float4 column q of all of them, so one shared-memory
+    // read of att_dec[j][q] / w_full[q] feeds GROUPED_ROWS rows (the score phase is shared-memory-bound otherwise).  Per row
+    // the summation order (q = lane, lane + 32, ...; x, y, z, w) is that of the per-row kernel: bit-identical scores.
+    constexpr int GROUPED_ROWS = 4;
+    for (int p0 = warp; p0 < P; p0 += GROUPED_ROWS * nwarp) {
+        float acc[GROUPED_ROWS][K];
 #pragma unroll
-        for (int j = 0; j < K; ++j) acc[j] = 0.f;
-        const float* row = ae + (long long)p * A;
-        for (int q0 = lane; q0 < A4; q0 += 4 * 32) {                 // 4 independent 128-bit loads in flight per lane
-            float4 xs[4];
+        for (int u = 0; u < GROUPED_ROWS; ++u)
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int q = q0 + 32 * u;
-                xs[u] = (q < A4) ? ld_stream_f4(row + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < K; ++j) acc[u][j] = 0.f;
+        for (int q = lane; q < A4; q += 32) {
+            float4 xs[GROUPED_ROWS];
+#pragma unroll
+            for (int u = 0; u < GROUPED_ROWS; ++u) {
+                const int p = p0 + u * nwarp;                        // warp-uniform
+                xs[u] = (p < P) ? ld_stream_f4(ae + (long long)p * A + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            const float4 w = *reinterpret_cast<const float4*>(s_wf + 4 * q);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int q = q0 + 32 * u;
-                if (q < A4) {
-                    const float4 x = xs[u];
-                    const float4 w = *reinterpret_cast<const float4*>(s_wf + 4 * q);
+            for (int j = 0; j < K; ++j) {
+                if (j < kl) {
+                    const float4 d = *reinterpret_cast<const float4*>(s_dec + j * A + 4 * q);
 #pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        if (j < kl) {
-                            const float4 d = *reinterpret_cast<const float4*>(s_dec + j * A + 4 * q);
-                            acc[j] = fmaf(fmaxf(x.x + d.x, 0.f), w.x, acc[j]);
-                            acc[j] = fmaf(fmaxf(x.y + d.y, 0.f), w.y, acc[j]);
-                            acc[j] = fmaf(fmaxf(x.z + d.z, 0.f), w.z, acc[j]);
-                            acc[j] = fmaf(fmaxf(x.w + d.w, 0.f), w.w, acc[j]);
-                        }
+                    for (int u = 0; u < GROUPED_ROWS; ++u) {
+                        const float4 x = xs[u];
+                        acc[u][j] = fmaf(fmaxf(x.x + d.x, 0.f), w.x, acc[u][j]);
+                        acc[u][j] = fmaf(fmaxf(x.y + d.y, 0.f), w.y, acc[u][j]);
+                        acc[u][j] = fmaf(fmaxf(x.z + d.z, 0.f), w.z, acc[u][j]);
+                        acc[u][j] = fmaf(fmaxf(x.w + d.w, 0.f), w.w, acc[u][j]);
                     }
                 }
             }
         }
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            if (j < kl) {
-                const float v = warp_sum(acc[j]);
-                if (lane == 0) s_e[j * Pp + p] = v + bfull;
+        for (int u = 0; u < GROUPED_ROWS; ++u) {
+            const int p = p0 + u * nwarp;
+            if (p < P) {
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    if (j < kl) {
+                        const float v = warp_sum(acc[u][j]);
+                        if (lane == 0) s_e[j * Pp + p] = v + bfull;
+                    }
+                }
             }
         }
     }
@@ -248,13 +256,16 @@ __global__ void __launch_bounds__(256, 2) att_step_fwd_grouped_kernel(
 #pragma unroll
             for (int u = 0; u < 8; ++u) x[u] = ld_stream_f4(eb + (long long)(p + u) * C + c);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int j = 0; j < K; ++j) {
+                if (j < kl) {
+                    // p is a multiple of 8 and Pp of 4: two 128-bit broadcast reads serve the 8 rows (same order of adds)
+                    const float4 a0 = *reinterpret_cast<const float4*>(s_e + j * Pp + p);
+                    const float4 a1 = *reinterpret_cast<const float4*>(s_e + j * Pp + p + 4);
+                    const float al8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    if (j < kl) {
-                        const float al = s_e[j * Pp + p + u];
-                        acc[j].x = fmaf(al, x[u].x, acc[j].x); acc[j].y = fmaf(al, x[u].y, acc[j].y);
-                        acc[j].z = fmaf(al, x[u].z, acc[j].z); acc[j].w = fmaf(al, x[u].w, acc[j].w);
+                    for (int u = 0; u < 8; ++u) {
+                        acc[j].x = fmaf(al8[u], x[u].x, acc[j].x); acc[j].y = fmaf(al8[u], x[u].y, acc[j].y);
+                        acc[j].z = fmaf(al8[u], x[u].z, acc[j].z); acc[j].w = fmaf(al8[u], x[u].w, acc[j].w);
                     }
                 }
             }

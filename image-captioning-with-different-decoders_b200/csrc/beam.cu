@@ -474,7 +474,8 @@ extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
                         d->b_ih, w.z + A + C, NZ, 0.f, s, live_rows));
         ICD_TRY(beam_mm(prec, w, w.gated, C, (int)R, C, d->w_ih + E, E + C, w.x3_WihC, w.gates_pre, 4 * D, 4 * D,
                         nullptr, nullptr, 0, 1.f, s, live_rows));                            // :70-71
-        ICD_TRY(icd_lstm_pointwise_fwd((int)R, D, w.gates_pre, w.c, nullptr, w.c_tmp, w.h_tmp, nullptr, 0, nullptr, 1.f, s));
+        ICD_TRY(icd_lstm_pointwise_fwd((int)R, D, w.gates_pre, w.c, nullptr, w.c_tmp, w.h_tmp, nullptr, 0, nullptr, 1.f, s,
+                                       nullptr, nullptr, live_rows));
         ICD_TRY(beam_mm(prec, w, w.h_tmp, D, (int)R, D, d->fc_w, D, w.x3_Wfc, w.logits, V, V, d->fc_b, nullptr, 0, 0.f, s, live_rows));   // :72
         beam_topk_kernel<<<n_img, 256, 0, s>>>(k, V, step, d->end_id, w.logits, w.score, w.k_live, w.slot_img, w.n_live, row_off,
                                                w.score_tmp, w.word_tmp, w.k_live_tmp, w.slot_img_tmp, w.src,

@@ -139,7 +139,8 @@ int icd_embed_scatter_add(void* d_table, int is_f64, const int64_t* captions, in
 int icd_lstm_pointwise_fwd(int rows, int D, const float* gates_pre, const float* c_prev,
                            float* gates_act, float* c_new, float* h_new,
                            float* hdrop, int64_t hdrop_row_stride, const uint8_t* mask, float scale,
-                           cudaStream_t s, void* h16 = nullptr, void* hdrop16 = nullptr);
+                           cudaStream_t s, void* h16 = nullptr, void* hdrop16 = nullptr,
+                           const int* m_live = nullptr /* optional device-side row count */);
 int icd_lstm_pointwise_bwd(int rows, int D, const float* dh_in, const float* d_hdrop, int64_t hdrop_row_stride,
                            const uint8_t* mask, float scale, float* dc_inout,
                            const float* gates_act, const float* c_prev, const float* c_new,

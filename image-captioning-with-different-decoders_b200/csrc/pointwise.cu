@@ -14,9 +14,11 @@ __global__ void lstm_pointwise_fwd_kernel(int rows, int D, const float* __restri
                                           float* __restrict__ c_new, float* __restrict__ h_new,
                                           float* __restrict__ hdrop, long long hdrop_row_stride,
                                           const unsigned char* __restrict__ mask, float scale,
-                                          __nv_bfloat16* __restrict__ h16, __nv_bfloat16* __restrict__ hdrop16) {
+                                          __nv_bfloat16* __restrict__ h16, __nv_bfloat16* __restrict__ hdrop16,
+                                          const int* __restrict__ m_live) {
     pdl_trigger();
     pdl_wait();
+    if (m_live) rows = min(rows, max(*m_live, 0));        // device-side row count (beam search: live rows only)
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)rows * D) return;
     const int r = (int)(idx / D), d = (int)(idx % D);
@@ -350,12 +352,12 @@ __global__ void __launch_bounds__(256) cross_entropy_bwd_kernel(int V, const flo
 int icd_lstm_pointwise_fwd(int rows, int D, const float* gates_pre, const float* c_prev,
                            float* gates_act, float* c_new, float* h_new,
                            float* hdrop, int64_t hdrop_row_stride, const uint8_t* mask, float scale,
-                           cudaStream_t s, void* h16, void* hdrop16) {
+                           cudaStream_t s, void* h16, void* hdrop16, const int* m_live) {
     if (rows == 0) return 0;
     const long long n = (long long)rows * D;
     ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, lstm_pointwise_fwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, s, rows, D,
                             gates_pre, c_prev, gates_act, c_new, h_new, hdrop, (long long)hdrop_row_stride,
-                            (const unsigned char*)mask, scale, (__nv_bfloat16*)h16, (__nv_bfloat16*)hdrop16));
+                            (const unsigned char*)mask, scale, (__nv_bfloat16*)h16, (__nv_bfloat16*)hdrop16, m_live));
     ICD_LAUNCH_CHECK();
     return 0;
 }
