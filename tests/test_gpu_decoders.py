@@ -568,3 +568,38 @@ def test_beam_search_edge_beam_widths_match_oracle(cuda, k, n_img):
         got = [[x for x in row if x >= 0] for row in res["trace"][:len(tr32), i].cpu().tolist()]
         assert got == tr32
     assert checked >= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "fp32x3"])
+def test_beam_search_batch_equals_single_images_under_compaction(cuda, precision):
+    """Finished beams / images leave the working set (slot and row compaction on the device).  An image's caption,
+    score, alpha frames and per-step candidate words must not depend on which other images share the batch: the batched
+    call equals one call per image, for a mix of images that finish at different steps (<end> bias varied per run)."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.gen_captions import beam_search_batched
+    from icd_b200.vocabulary import synthetic_vocab
+    case = dict(H.BEAM_CASES["beam_small"], dropout=0.5, train=False, fine_tune_embedding=True, k=4)
+    vocab = synthetic_vocab(case["V"])
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams, vocab)
+    H.apply_beam_recipe(dec, case)
+    dec = dec.to(cuda)
+    V, k = case["V"], 4
+    base = H.beam_features(case)
+    g = torch.Generator().manual_seed(11)
+    feats = torch.cat([base, base.flip(0) * 0.7 + 0.1, torch.rand(base.shape, generator=g) * base.max()], dim=0).to(cuda)
+    n = feats.shape[0]
+    with torch.no_grad():
+        full = beam_search_batched(dec, feats, k, V - 3, V - 2, max_steps=30, want_alphas=True, want_trace=True,
+                                   precision=precision)
+        lens = full["len"].cpu().tolist()
+        assert len(set(lens)) > 1, "the test needs images that finish at different steps"
+        for i in range(n):
+            one = beam_search_batched(dec, feats[i:i + 1], k, V - 3, V - 2, max_steps=30, want_alphas=True,
+                                      want_trace=True, precision=precision)
+            assert one["len"].cpu().tolist()[0] == lens[i]
+            L = lens[i]
+            assert torch.equal(one["seq"][0, :L], full["seq"][i, :L])
+            assert torch.equal(one["score"][0], full["score"][i])
+            assert torch.equal(one["alpha"][0, :L], full["alpha"][i, :L])
+            assert torch.equal(one["trace"][:, 0], full["trace"][:, i])
