@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
 // ------------------------------------------------------------------------------------------------
 // after the loop: d_att_enc + full_att / enc_att-bias parameter gradients, att_enc stored as bf16.
 //   d_att_enc[b,p,a] = w_full[a] * sum_t d_e[b,t,p] * [att_enc[b,p,a] + att_dec[t,b,a] > 0]
-// grid = (ceil(P/PROJ_PB), B), block = A/4 threads (each 4 consecutive a), 4 pixels per pass so that one 128-bit
+// grid = (ceil(P/PROJ_PB), B), block = 2 x A/4 threads (each 4 consecutive a; the halves alternate over groups of 4 pixels), 4 pixels per pass so that one 128-bit
 // shared-memory read of att_dec[t, a..a+3] feeds 16 updates.  smem: T*A (att_dec) + T*PROJ_PB (d_e).
 // Outputs: d_att_enc fp32 and / or bf16 (either may be NULL: the bf16 tier only needs the bf16 copy, which is the
 // MN-major A operand of the enc_att weight-gradient contraction) and per-CTA partials
@@ -442,11 +442,14 @@ __global__ void att_proj_bwd_bf16_kernel(int B, int T, int P, int A, const int* 
         de_sum += v;
     }
     __syncthreads();
-    const int a = threadIdx.x * 4;
+    // two thread halves share the staged att_dec / d_e and take alternate groups of 4 pixels (twice the warps per byte of
+    // shared memory: the loop is latency-bound at 4 warps per scheduler)
+    const int th = blockDim.x >> 1, half = threadIdx.x / th;
+    const int a = (threadIdx.x - half * th) * 4;
     float4 wacc = make_float4(0.f, 0.f, 0.f, 0.f), bacc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (a < A) {
         const float4 w = *reinterpret_cast<const float4*>(w_full + a);
-        for (int pq = 0; pq < np; pq += 4) {                          // PROJ_PB is a multiple of 4; rows >= np carry d_e = 0
+        for (int pq = half * 4; pq < np; pq += 8) {                   // PROJ_PB is a multiple of 4; rows >= np carry d_e = 0
             float x[4][4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
@@ -489,7 +492,14 @@ __global__ void att_proj_bwd_bf16_kernel(int B, int T, int P, int A, const int* 
         }
     }
     float* mine = partial + ((long long)b * gridDim.x + blockIdx.x) * (2 * A + 4);
-    if (a < A) { *reinterpret_cast<float4*>(mine + a) = wacc; *reinterpret_cast<float4*>(mine + A + a) = bacc; }
+    __syncthreads();                                                  // everyone is done with s_dec: reuse it to add the halves
+    if (half == 1 && a < A) { *reinterpret_cast<float4*>(s_dec + a) = wacc; *reinterpret_cast<float4*>(s_dec + A + a) = bacc; }
+    __syncthreads();
+    if (half == 0 && a < A) {
+        const float4 w1 = *reinterpret_cast<const float4*>(s_dec + a), b1 = *reinterpret_cast<const float4*>(s_dec + A + a);
+        *reinterpret_cast<float4*>(mine + a) = make_float4(wacc.x + w1.x, wacc.y + w1.y, wacc.z + w1.z, wacc.w + w1.w);
+        *reinterpret_cast<float4*>(mine + A + a) = make_float4(bacc.x + b1.x, bacc.y + b1.y, bacc.z + b1.z, bacc.w + b1.w);
+    }
     const float tot = block_sum(de_sum, s_red);
     if (threadIdx.x == 0) { mine[2 * A] = tot; mine[2 * A + 1] = 0.f; mine[2 * A + 2] = 0.f; mine[2 * A + 3] = 0.f; }
 }
@@ -680,7 +690,7 @@ extern "C" int icd_attention_proj_bwd_bf16(int B, int T, int P, int A, const int
                                            float* d_b_enc, float* partial, void* stream) {
     cudaStream_t s = icd_stream(stream);
     ICD_CHECK_ARG(T > 0 && T <= ICD_MAX_STEPS, "attention_proj_bwd_bf16: T=%d out of range", T);
-    ICD_CHECK_ARG(A % 4 == 0 && A / 4 <= 1024, "attention_proj_bwd_bf16: A=%d unsupported", A);
+    ICD_CHECK_ARG(A % 4 == 0 && A / 4 <= 512, "attention_proj_bwd_bf16: A=%d unsupported", A);
     ICD_CHECK_ARG(ld_dec % 4 == 0, "attention_proj_bwd_bf16: ld_dec must be a multiple of 4");
     ICD_CHECK_ARG(B <= 65535, "attention_proj_bwd_bf16: B too large");
     const int chunks = (P + PROJ_PB - 1) / PROJ_PB;
@@ -690,14 +700,15 @@ extern "C" int icd_attention_proj_bwd_bf16(int B, int T, int P, int A, const int
     for (int t = 0; t < ICD_MAX_STEPS; ++t) pack.v[t] = t < T ? bt_host[t] : 0;
     row_len_from_pack_kernel16<<<(B + 127) / 128, 128, 0, s>>>(B, T, pack, row_len);
     ICD_LAUNCH_CHECK();
-    const size_t smem = ((size_t)T * A + (size_t)T * PROJ_PB + 40) * sizeof(float);
+    // (the first 2*A floats are reused to add the two thread halves' partials: at least 2 rows of att_dec are allocated)
+    const size_t smem = ((size_t)(T > 2 ? T : 2) * A + (size_t)T * PROJ_PB + 40) * sizeof(float);
     ICD_CHECK_ARG(smem <= 220 * 1024, "attention_proj_bwd_bf16: T*A too large for shared memory");
     static size_t configured = 48 * 1024;
     if (smem > configured) {
         ICD_CUDA(cudaFuncSetAttribute(att_proj_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    int threads = ((A / 4 + 31) / 32) * 32;
+    const int threads = 2 * (((A / 4 + 31) / 32) * 32);              // two halves, see the kernel
     dim3 grid(chunks, B);
     att_proj_bwd_bf16_kernel<<<grid, threads, smem, s>>>(B, T, P, A, row_len,
                                                           reinterpret_cast<const __nv_bfloat16*>(att_enc16),
