@@ -471,7 +471,7 @@ def main():
     ops.prof_enable(True)                               # the library creates its timing events lazily: do that during warm-up
     for _ in range(n_warm):
         train_step(enc_d, caps_d)
-    barrier()
+    torch.cuda.synchronize()
     ops.prof_collect()                                  # discard the warm-up samples (the events stay allocated)
     import gc
     gc.collect()
@@ -480,6 +480,8 @@ def main():
     launches0 = ops.launch_count()  # record between two kernels costs ~4 us and suppresses their programmatic overlap)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()                       # LAST thing before the clock starts: the ranks leave it together (a gc.collect() between
+                                    # the barrier and the first step skews them by milliseconds, paid in the first all-reduce)
     t_wall0 = time.perf_counter()
     ev0.record()
     for i in range(args.steps):
