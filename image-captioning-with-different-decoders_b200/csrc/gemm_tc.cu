@@ -791,9 +791,39 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16& b1, __nv_bfloat16
     b3 = __float2bfloat16_rn(r2);
 }
 // K-major source rows: dst[r*ldd + s*seg + c] = term_s(src[r*s_r + c]), c < cols; pad columns [cols, seg) zeroed.
+// vec8 = 1 (cols % 8 == 0, 16-byte aligned rows): a thread splits 8 consecutive columns — two 128-bit loads, six 128-bit stores.
 __global__ void split3_rows_kernel(const float* __restrict__ src, long long s_r, int rows, int cols, int seg,
-                                   __nv_bfloat16* __restrict__ dst, long long ldd, int which, const int* __restrict__ m_live) {
+                                   __nv_bfloat16* __restrict__ dst, long long ldd, int which, const int* __restrict__ m_live,
+                                   int vec8) {
     if (m_live) rows = min(rows, max(*m_live, 0));              // device-side row count (beam search)
+    if (vec8) {
+        const int seg8 = seg >> 3;
+        const long long total = (long long)rows * seg8;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const long long r = i / seg8; const int c = (int)(i % seg8) * 8;
+            const float4 x0 = *reinterpret_cast<const float4*>(src + r * s_r + c);
+            const float4 x1 = *reinterpret_cast<const float4*>(src + r * s_r + c + 4);
+            const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            uint32_t t[3][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                __nv_bfloat16 a[3], b[3];
+                split3(xs[2 * q], a[0], a[1], a[2]);
+                split3(xs[2 * q + 1], b[0], b[1], b[2]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    t[k][q] = (uint32_t)__bfloat16_as_ushort(a[k]) | ((uint32_t)__bfloat16_as_ushort(b[k]) << 16);
+            }
+            const int pa[6] = {0, 0, 1, 0, 2, 1}, pb[6] = {0, 1, 0, 2, 0, 1};
+            __nv_bfloat16* d = dst + r * ldd + c;
+#pragma unroll
+            for (int sgm = 0; sgm < 6; ++sgm) {
+                const int k = which == 0 ? pa[sgm] : pb[sgm];
+                *reinterpret_cast<uint4*>(d + (long long)sgm * seg) = make_uint4(t[k][0], t[k][1], t[k][2], t[k][3]);
+            }
+        }
+        return;
+    }
     const long long total = (long long)rows * seg;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / seg; const int c = (int)(i % seg);
@@ -1116,11 +1146,13 @@ int icd_gemm_tc_launch(const icd_gemm_desc_t* d, cudaStream_t s) {
 int icd_split3_bf16(const float* src, int64_t s_r, int rows, int cols, void* dst, int which, cudaStream_t s, const int* m_live) {
     if (rows == 0 || cols == 0) return 0;
     const int seg = (int)up8(cols);
-    const long long total = (long long)rows * seg;
+    const int vec8 = (cols % 8 == 0) && (s_r % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+    const long long total = vec8 ? (long long)rows * (seg / 8) : (long long)rows * seg;
     long long blocks = (total + 255) / 256;
     if (blocks > ICD_NUM_SMS * 16) blocks = ICD_NUM_SMS * 16;
     split3_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, s_r, rows, cols, seg, reinterpret_cast<__nv_bfloat16*>(dst),
-                                                        6LL * seg, which, m_live);
+                                                        6LL * seg, which, m_live, vec8);
     ICD_LAUNCH_CHECK();
     return 0;
 }
