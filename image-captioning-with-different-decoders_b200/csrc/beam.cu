@@ -124,7 +124,6 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
         int* __restrict__ parent_s, int* __restrict__ word_s, int* __restrict__ trace_s,
         float* __restrict__ best_score, int* __restrict__ best_step, int* __restrict__ best_parent) {
     __shared__ float s_red[40];
-    __shared__ float s_max[KMAX], s_lsum[KMAX], s_score[KMAX];
     __shared__ float s_cv[256 * KMAX];
     __shared__ int s_ci[256 * KMAX];
     __shared__ float s_topv[KMAX];
@@ -139,6 +138,24 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
     // rows are streamed with 64-bit loads, 4 in flight per thread (rows are 8-byte aligned when V is even)
     const bool even = (V & 1) == 0;
     const int V2 = V >> 1;
+    // thread-local top-KMAX over this thread's slice of the flattened (nrows*V) candidates (flat index f = i*V + v)
+    float tv[KMAX]; int ti[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
+    auto consider = [&](float xv, float rmax, float rlsum, float rscore, int f) {
+        const float lp = (xv - rmax) - rlsum;                       // log_softmax value
+        const float v = rscore + lp;                                // :76
+        if (better(v, f, tv[KMAX - 1], ti[KMAX - 1])) {
+            tv[KMAX - 1] = v; ti[KMAX - 1] = f;
+#pragma unroll
+            for (int j = KMAX - 1; j > 0; --j) {
+                if (better(tv[j], ti[j], tv[j - 1], ti[j - 1])) {
+                    const float a = tv[j]; tv[j] = tv[j - 1]; tv[j - 1] = a;
+                    const int b = ti[j]; ti[j] = ti[j - 1]; ti[j - 1] = b;
+                }
+            }
+        }
+    };
     for (int i = 0; i < nrows; ++i) {                                                        // :74 log_softmax
         const float* x = lg + (long long)i * V;
         const float2* x2 = reinterpret_cast<const float2*>(x);
@@ -172,31 +189,8 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
             for (int v = threadIdx.x; v < V; v += blockDim.x) sum += expf(x[v] - m);
         }
         sum = block_sum(sum, s_red);
-        if (threadIdx.x == 0) { s_max[i] = m; s_lsum[i] = logf(sum); s_score[i] = score[row0 + i]; }
-    }
-    __syncthreads();
-    // thread-local top-KMAX over this thread's slice of the flattened (nrows*V) candidates (flat index f = i*V + v)
-    float tv[KMAX]; int ti[KMAX];
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
-    auto consider = [&](float xv, float rmax, float rlsum, float rscore, int f) {
-        const float lp = (xv - rmax) - rlsum;                       // log_softmax value
-        const float v = rscore + lp;                                // :76
-        if (better(v, f, tv[KMAX - 1], ti[KMAX - 1])) {
-            tv[KMAX - 1] = v; ti[KMAX - 1] = f;
-#pragma unroll
-            for (int j = KMAX - 1; j > 0; --j) {
-                if (better(tv[j], ti[j], tv[j - 1], ti[j - 1])) {
-                    const float a = tv[j]; tv[j] = tv[j - 1]; tv[j - 1] = a;
-                    const int b = ti[j]; ti[j] = ti[j - 1]; ti[j - 1] = b;
-                }
-            }
-        }
-    };
-    for (int i = 0; i < nrows; ++i) {
-        const float* x = lg + (long long)i * V;
-        const float2* x2 = reinterpret_cast<const float2*>(x);
-        const float rmax = s_max[i], rlsum = s_lsum[i], rscore = s_score[i];
+        // candidate pass for this row right away: its 38 KB are still in L1 from the two softmax passes
+        const float rmax = m, rlsum = logf(sum), rscore = score[row0 + i];
         const int f0 = i * V;
         if (even) {
             int j = threadIdx.x;
