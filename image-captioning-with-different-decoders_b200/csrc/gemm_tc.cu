@@ -934,7 +934,7 @@ int pair_mode() {
 
 // tile width / split-K plan from a small cost model (SM clocks): one persistent wave of work units should cover the
 // 148 SMs; narrower tiles pay more shared-memory / L2 traffic per flop, split-K pays a second (reduce) kernel.
-struct Plan { int bn, splits, kb_per_split; };
+struct Plan { int bn, splits, kb_per_split; double cost; };
 
 Plan make_plan(int M, int N, int K, bool allow_split) {
     // Cost model in SM clocks, fitted to CUDA-graph replays of the train-step shapes (tools/gemm_bench.py --graph):
@@ -943,7 +943,7 @@ Plan make_plan(int M, int N, int K, bool allow_split) {
     //   partial planes (written by the contraction, read back by the reduce pass or the deferred consumer).
     const int tm = (M + BM - 1) / BM, nkb = (K + BK - 1) / BK;
     const int cand[3] = {256, 128, 64};
-    Plan best; best.bn = 64; best.splits = 1; best.kb_per_split = nkb;
+    Plan best; best.bn = 64; best.splits = 1; best.kb_per_split = nkb; best.cost = 1e300;
     double best_cost = 1e300;
     const double plane_kb = (double)M * N * 4.0 / 1024.0;
     for (int i = 0; i < 3; ++i) {
@@ -966,10 +966,20 @@ Plan make_plan(int M, int N, int K, bool allow_split) {
             if (waves < 1.0) waves = 1.0;                        // but short tiles overlap their epilogues: blend
             else waves = 0.5 * (waves + std::ceil(waves));
             const double cost = waves * kbs * clk_kb + 4500.0 + (sp > 1 ? 6000.0 + sp * plane_kb * 1.05 : 0.0);
-            if (cost < best_cost) { best_cost = cost; best.bn = bn; best.splits = sp; best.kb_per_split = kbs; }
+            if (cost < best_cost) { best_cost = cost; best.bn = bn; best.splits = sp; best.kb_per_split = kbs; best.cost = cost; }
         }
     }
     return best;
+}
+
+// A last m-tile with only a few rows can cost a whole extra wave (d fc.weight: M = 9490 = 74 * 128 + 18 -> 150 tiles on 148
+// SMs).  Returns the number of tail rows to run as a second, split-K contraction when the model says that is cheaper.
+int tail_rows_to_split(int M, int N, int K, bool allow_split) {
+    const int rem = M % BM;
+    if (!allow_split || M <= BM || rem == 0 || rem > 32) return 0;
+    const double c_full = make_plan(M, N, K, true).cost;
+    const double c_two = make_plan(M - rem, N, K, true).cost + make_plan(rem, N, K, true).cost;
+    return c_two < 0.9 * c_full ? rem : 0;
 }
 
 }  // namespace
@@ -1005,8 +1015,9 @@ int icd_convert_bf16(const float* src, int64_t s_r, int64_t s_c, int rows, int c
 }
 
 int64_t icd_gemm_bf16_splitk_floats(int M, int N, int K) {
-    const Plan p = make_plan(M, N, K, true);
-    return p.splits > 1 ? (int64_t)p.splits * M * N : 0;
+    auto need = [&](int m) { const Plan p = make_plan(m, N, K, true); return p.splits > 1 ? (int64_t)p.splits * m * N : (int64_t)0; };
+    const int rem = tail_rows_to_split(M, N, K, true);
+    return rem ? std::max(need(M - rem), need(rem)) : need(M);
 }
 
 int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, int64_t ldb, int b_mn,
@@ -1019,6 +1030,23 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
     if (M == 0 || N == 0) return 0;
     ICD_CHECK_ARG(K > 0, "gemm_tc: K must be positive");
     ICD_CHECK_ARG(C != nullptr || C16 != nullptr, "gemm_tc: no output");
+    if (!m_live && !deferred_splits) {
+        // few rows in the last m-tile and an extra wave because of them: run them as a second (split-K) contraction
+        const int rem = tail_rows_to_split(M, N, K, splitk_ws != nullptr);
+        if (rem && icd_gemm_bf16_splitk_floats(M, N, K) <= splitk_ws_floats) {
+            const int Mm = M - rem;
+            auto offA = [&](int m) { return reinterpret_cast<const char*>(A16) + 2 * (a_mn ? (int64_t)m : (int64_t)m * lda); };
+            for (int part = 0; part < 2; ++part) {
+                const int m0 = part ? Mm : 0, mm = part ? rem : Mm;
+                ICD_TRY(icd_gemm_bf16_ex(offA(m0), lda, a_mn, B16, ldb, b_mn, C ? C + (int64_t)m0 * ldc : nullptr, ldc, mm, N, K,
+                                         bias1, bias2, add1 ? add1 + (int64_t)m0 * ld1 : nullptr, ld1,
+                                         add2 ? add2 + (int64_t)m0 * ld2 : nullptr, ld2, row_mask ? row_mask + m0 : nullptr, beta, s,
+                                         C16 ? reinterpret_cast<char*>(C16) + 2 * (int64_t)m0 * ldc16 : nullptr, ldc16,
+                                         splitk_ws, splitk_ws_floats, nullptr, nullptr));
+            }
+            return 0;
+        }
+    }
     Plan pl = make_plan(M, N, K, splitk_ws != nullptr && m_live == nullptr);   // a device-side row count excludes split-K
     if (const char* f = getenv("ICD_GEMM_FORCE_PLAN")) {           // diagnostic: "bn,splits" (tools/gemm_bench.py)
         int bn = 0, sp = 0;

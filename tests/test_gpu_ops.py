@@ -309,11 +309,12 @@ def test_gemm_bf16_masked_rows_with_8_byte_aligned_row_stride(cuda, N):
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 0), (0, 1), (1, 1)])
 @pytest.mark.parametrize("M,N,K", [(512, 2048, 2048), (512, 512, 4608), (300, 200, 1000), (128, 64, 64),
                                    (2048, 520, 12288), (96, 9490, 136), (512, 2048, 40000), (1000, 4608, 512),
-                                   (640, 9490, 512)])
+                                   (640, 9490, 512), (9490, 512, 4096)])
 def test_gemm_bf16_operand_majors_tiles_and_split_k(cuda, pair_mode, M, N, K, a_mn, b_mn):
     """Every operand-major combination of the tcgen05 kernel (K-major = rows of K, MN-major = rows of M/N, consumed
     without a transpose), across the BN = 256/128/64 tile plans and the deterministic split-K plans the shapes select
-    (per-step contractions with M = batch, weight-gradient contractions with K = tokens)."""
+    (per-step contractions with M = batch, weight-gradient contractions with K = tokens); 9490 x 512 x 4096 is the shape
+    whose 18-row last m-tile is split off into a second, split-K contraction (150 tiles would need two waves)."""
     ops = _ops()
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K + a_mn * 2 + b_mn)
     a = torch.randn(M, K, generator=g)
