@@ -467,3 +467,59 @@ extern "C" int icd_cross_entropy_bwd(int64_t R, int V, const float* logits, cons
     ICD_LAUNCH_CHECK();
     return 0;
 }
+
+// ---- doubly stochastic attention regulariser (models/attention.py:413-414) -------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) alpha_reg_fwd_kernel(int T, int P, long long BP, const float* __restrict__ alphas,
+                                                            float alpha_c, float inv_bp, float* __restrict__ resid,
+                                                            float* __restrict__ partial) {
+    __shared__ float s_red[40];
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;           // i = b*P + p
+    float sq = 0.f;
+    if (i < BP) {
+        const long long b = i / P; const int p = (int)(i % P);
+        const float* a = alphas + b * T * P + p;
+        float s = 0.f;
+        for (int t = 0; t < T; ++t) s += a[(long long)t * P];                // t = 0, 1, ...: torch's sum(dim=1) order per (b,p)
+        const float r = alpha_c - s;
+        resid[i] = r;
+        sq = r * r * inv_bp;
+    }
+    const float tot = block_sum(sq, s_red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(256) alpha_reg_bwd_kernel(int T, int P, long long BP, const float* __restrict__ resid,
+                                                            const float* __restrict__ upstream, float scale,
+                                                            float* __restrict__ d_alphas) {
+    const long long n = BP * T;
+    const float g = scale * (upstream ? upstream[0] : 1.f);
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const long long b = i / ((long long)T * P); const int p = (int)(i % P);
+        d_alphas[i] = g * resid[b * P + p];
+    }
+}
+}  // namespace
+
+extern "C" int icd_alpha_regulariser_fwd(int B, int T, int P, const float* alphas, float alpha_c, float* resid,
+                                         float* partial, float* reg, void* stream) {
+    ICD_CHECK_ARG(B > 0 && T > 0 && P > 0, "alpha_regulariser_fwd: empty shape");
+    ICD_CHECK_ARG(alphas && resid && partial && reg, "alpha_regulariser_fwd: null pointer");
+    cudaStream_t s = icd_stream(stream);
+    const long long BP = (long long)B * P;
+    const unsigned blocks = (unsigned)((BP + 255) / 256);
+    alpha_reg_fwd_kernel<<<blocks, 256, 0, s>>>(T, P, BP, alphas, alpha_c, 1.f / (float)BP, resid, partial);
+    ICD_LAUNCH_CHECK();
+    return icd_colsum(partial, 1, (int64_t)blocks, 1, nullptr, reg, s);
+}
+
+extern "C" int icd_alpha_regulariser_bwd(int B, int T, int P, const float* resid, const float* upstream, float* d_alphas,
+                                         void* stream) {
+    ICD_CHECK_ARG(B > 0 && T > 0 && P > 0, "alpha_regulariser_bwd: empty shape");
+    ICD_CHECK_ARG(resid && d_alphas, "alpha_regulariser_bwd: null pointer");
+    const long long BP = (long long)B * P, n = BP * T;
+    long long blocks = (n + 255) / 256;
+    if (blocks > ICD_NUM_SMS * 16) blocks = ICD_NUM_SMS * 16;
+    alpha_reg_bwd_kernel<<<(unsigned)blocks, 256, 0, icd_stream(stream)>>>(T, P, BP, resid, upstream, -2.f / (float)BP, d_alphas);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}

@@ -13,7 +13,7 @@ per-row loss + log-sum-exp; icd_cross_entropy_bwd: gradient, scaled by the upstr
 a bf16 copy for the tensor-core tier); rows with t >= batch_size_t carry target -1 and are skipped
 (they are the rows pack_padded_sequence drops).  ``baseline_caption_loss`` == models/baseline.py:194-195,224-225
 (CrossEntropyLoss(ignore_index=<pad>) over all (b, t)).
-The doubly-stochastic regulariser touches only the (B,T,196) alphas and stays a torch expression.
+The doubly-stochastic regulariser over the (B,T,196) alphas is one forward and one backward kernel (``alpha_regulariser``).
 """
 import numpy as np
 import torch
@@ -61,6 +61,27 @@ class _FusedCE(torch.autograd.Function):
         return d_logits, None, None, None
 
 
+class _AlphaReg(torch.autograd.Function):
+    """((alpha_c - alphas.sum(dim=1)) ** 2).mean() as one forward and one backward kernel (the torch expression is eight)."""
+
+    @staticmethod
+    def forward(ctx, alphas, alpha_c):
+        reg, resid = ops.alpha_regulariser_fwd(alphas, alpha_c)
+        ctx.save_for_backward(resid)
+        ctx.T = alphas.shape[1]
+        return reg
+
+    @staticmethod
+    def backward(ctx, g):
+        (resid,) = ctx.saved_tensors
+        return ops.alpha_regulariser_bwd(resid, ctx.T, upstream=g.reshape(1).float().contiguous()), None
+
+
+def alpha_regulariser(alphas, alpha_c=1.0):
+    """Doubly stochastic attention regulariser of models/attention.py:413-414."""
+    return _AlphaReg.apply(alphas.float().contiguous(), float(alpha_c))        # CUDA only, like every op of this package
+
+
 def packed_targets(encoded_captions, decode_lengths, T, row_valid=None):
     """targets[b, t] = captions[b, t+1] where row b is active at step t (b < batch_size_t), else -1.
     ``row_valid``: the (B*T) uint8 activity mask the decoder forward already built on the device (no host->device
@@ -82,7 +103,7 @@ def attention_caption_loss(predictions, encoded_captions, decode_lengths, alphas
     tgt, n_valid = packed_targets(encoded_captions, decode_lengths, T, getattr(predictions, "_icd_row_valid", None))
     want_bf16 = bool(getattr(predictions, "_icd_bf16_tier", False))
     ce = _FusedCE.apply(predictions.reshape(B * T, V), tgt.reshape(-1).contiguous(), n_valid, want_bf16)
-    return ce + ((alpha_c - alphas.sum(dim=1)) ** 2).mean()
+    return ce + alpha_regulariser(alphas, alpha_c)
 
 
 def baseline_caption_loss(outputs, captions, pad_id=0):

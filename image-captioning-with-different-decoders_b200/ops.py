@@ -228,6 +228,27 @@ def cross_entropy_bwd(logits, targets, lse, inv_count, upstream=None, want_bf16=
     return d_logits, d16
 
 
+def alpha_regulariser_fwd(alphas, alpha_c):
+    """models/attention.py:413-414 -> (reg 0-dim = mean_{b,p} (alpha_c - sum_t alphas)^2, resid (B,P) saved for the backward)"""
+    _need_cuda(alphas)
+    B, T, P = alphas.shape
+    resid = torch.empty(B, P, device=alphas.device, dtype=torch.float32)
+    partial = torch.empty((B * P + 255) // 256, device=alphas.device, dtype=torch.float32)
+    reg = torch.empty(1, device=alphas.device, dtype=torch.float32)
+    check(lib().icd_alpha_regulariser_fwd(B, T, P, ptr(alphas), ctypes.c_float(alpha_c), ptr(resid), ptr(partial), ptr(reg),
+                                          stream_ptr()), "icd_alpha_regulariser_fwd")
+    return reg.reshape(()), resid
+
+
+def alpha_regulariser_bwd(resid, T, upstream=None):
+    """-> d_alphas (B,T,P) = -2 resid / (B*P) * upstream (``upstream``: 1-element CUDA fp32 tensor read on the device)"""
+    _need_cuda(resid)
+    B, P = resid.shape
+    d = torch.empty(B, T, P, device=resid.device, dtype=torch.float32)
+    check(lib().icd_alpha_regulariser_bwd(B, T, P, ptr(resid), ptr(upstream), ptr(d), stream_ptr()), "icd_alpha_regulariser_bwd")
+    return d
+
+
 def cross_entropy_fwd_bwd(logits, targets, inv_count, want_grad=True):
     """Convenience: -> (row_loss (R), d_logits (R,V) = (softmax - onehot) * inv_count)"""
     row_loss, lse = cross_entropy_fwd(logits, targets)

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ICD_B200_ABI_VERSION 10
+#define ICD_B200_ABI_VERSION 11
 #define ICD_MAX_STEPS 256
 
 ICD_API int icd_version(void);                       /* ICD_B200_ABI_VERSION the library was built with */
@@ -393,6 +393,15 @@ ICD_API int icd_cross_entropy_fwd(int64_t R, int V, const float* logits, const i
 ICD_API int icd_cross_entropy_bwd(int64_t R, int V, const float* logits, const int64_t* targets, const float* lse,
                           const float* upstream, float inv_count, float* d_logits, void* d_logits16, int64_t ld16,
                           void* stream);
+
+/* Doubly stochastic attention regulariser (models/attention.py:413-414): reg = mean_{b,p} (alpha_c - sum_t alphas[b,t,p])^2.
+ * forward : resid[b,p] = alpha_c - sum_t alphas[b,t,p] (saved for the backward); reg[0] = the mean (summed in a fixed order:
+ *           per-block partials in `partial`, ceil(B*P/256) floats, then one reduction);
+ * backward: d_alphas[b,t,p] = -2 * resid[b,p] / (B*P) * (*upstream) for every t; `upstream` is a DEVICE scalar. */
+ICD_API int icd_alpha_regulariser_fwd(int B, int T, int P, const float* alphas, float alpha_c, float* resid,
+                              float* partial, float* reg, void* stream);
+ICD_API int icd_alpha_regulariser_bwd(int B, int T, int P, const float* resid, const float* upstream, float* d_alphas,
+                              void* stream);
 
 #ifdef __cplusplus
 }

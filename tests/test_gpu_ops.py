@@ -359,3 +359,36 @@ def test_gemm_fp32x3_is_fp32_grade(cuda, M, N, K, a_mn, b_mn):
     c16 = ops.gemm(a_dev, b_dev, **dict(kw, precision="bf16"))
     assert H.rel_err(c, ref) * 50 < H.rel_err(c16, ref), "fp32x3 must be far tighter than bf16 operands"
     print("fp32x3 rel err %.2e, bf16 rel err %.2e" % (H.rel_err(c, ref), H.rel_err(c16, ref)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,P,V", [(5, 7, 196, 300), (64, 24, 196, 9490), (1, 1, 3, 11)])
+def test_fused_loss_glue_matches_reference_expression(cuda, B, T, P, V):
+    """icd_b200.losses.attention_caption_loss == models/attention.py:401-414 (pack_padded_sequence + CrossEntropyLoss +
+    doubly stochastic regulariser), value and gradients w.r.t. the logits and the alphas, in fp64 torch on the CPU."""
+    from torch.nn.utils.rnn import pack_padded_sequence
+    from icd_b200.losses import attention_caption_loss, alpha_regulariser
+    g = torch.Generator().manual_seed(B * 31 + T)
+    lens = sorted((int(x) for x in torch.randint(1, T + 1, (B,), generator=g)), reverse=True)
+    lens[0] = T
+    caps = torch.randint(0, V, (B, T + 1), generator=g)
+    preds = torch.randn(B, T, V, generator=g) * 2
+    alphas = torch.rand(B, T, P, generator=g) / P
+    for b, l in enumerate(lens):                          # the decoder leaves inactive rows at exactly 0
+        preds[b, l:] = 0
+        alphas[b, l:] = 0
+    p64 = preds.double().requires_grad_(True)
+    a64 = alphas.double().requires_grad_(True)
+    scores = pack_padded_sequence(p64, lens, batch_first=True).data
+    targets = pack_padded_sequence(caps[:, 1:], lens, batch_first=True).data
+    ref = torch.nn.CrossEntropyLoss()(scores, targets) + ((1.0 - a64.sum(dim=1)) ** 2).mean()
+    ref.backward()
+    pd = preds.to(cuda).requires_grad_(True)
+    ad = alphas.to(cuda).requires_grad_(True)
+    loss = attention_caption_loss(pd, caps.to(cuda), lens, ad, alpha_c=1.0)
+    (loss * 0.5).backward()                               # a non-trivial upstream gradient, read on the device
+    assert abs(loss.item() - ref.item()) < 2e-6 * max(1.0, abs(ref.item()))
+    H.assert_close_norm(pd.grad, p64.grad * 0.5, 1e-5, "d_logits")
+    H.assert_close_norm(ad.grad, a64.grad * 0.5, 1e-5, "d_alphas")
+    reg = alpha_regulariser(alphas.to(cuda), 0.7)
+    assert abs(reg.item() - ((0.7 - alphas.double().sum(dim=1)) ** 2).mean().item()) < 1e-6
