@@ -29,7 +29,10 @@ namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
-constexpr int EPI_LD = 33;                           // padded row of the per-warp 32x32 transpose buffer
+constexpr int EPI_LD = 32;                           // row of the per-warp 32x32 transpose buffer; the eight float4 groups of a
+                                                     // row are XOR-swizzled with (row & 7) so that both the 128-bit row writes
+                                                     // (lane = row) and the 128-bit tile reads (8 lanes = one row) are
+                                                     // bank-conflict free without padding
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS; // 320
 constexpr int MN_BLOCK_BYTES = BK * 128;             // one 64-element MN block of an MN-major tile: BK rows x 128 B
@@ -151,7 +154,11 @@ struct Cfg {
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 };
 
-// One 32x32 sub-tile of the accumulator, already transposed into sE (row stride EPI_LD): apply the fused epilogue and
+__device__ __forceinline__ int epi_off4(int r, int g) { return r * EPI_LD + ((g ^ (r & 7)) << 2); }        // float4 group g of row r
+__device__ __forceinline__ int epi_off(int r, int c) { return epi_off4(r, c >> 2) + (c & 3); }             // element (r, c)
+__device__ __forceinline__ float4 epi_ld4(const float* sE, int r, int g) { return *reinterpret_cast<const float4*>(sE + epi_off4(r, g)); }
+
+// One 32x32 sub-tile of the accumulator, already transposed into sE (swizzled, see EPI_LD): apply the fused epilogue and
 // write it out with coalesced accesses.  rowbits: bit r set <=> row mrow0 + r is inside M and not masked out (the row
 // mask is read ONCE per sub-tile, one coalesced byte load + a warp ballot, never in the store loop).
 //   vec4 : lane -> 4 consecutive columns, 8 lanes per row, 4 rows per instruction (128-bit accesses)
@@ -168,34 +175,58 @@ __device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ s
         float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
         if (e.bias1) { const float4 b = *reinterpret_cast<const float4*>(e.bias1 + n); bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w; }
         if (e.bias2) { const float4 b = *reinterpret_cast<const float4*>(e.bias2 + n); bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w; }
-        float4 a1[8], a2[8];
+        if (!e.add1 && !e.add2 && e.beta == 0.f) {
+            // plain store (bias + row mask only): no operand prefetch, the loop is one shared-memory read and one store per row
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + (lane >> 3), m = mrow0 + rr;
-            a1[i] = make_float4(0.f, 0.f, 0.f, 0.f); a2[i] = a1[i];
-            if ((rows_keep >> rr) & 1u) {
-                if (e.add1) a1[i] = *reinterpret_cast<const float4*>(e.add1 + (long long)m * e.ld1 + n);
-                if (e.add2) a2[i] = *reinterpret_cast<const float4*>(e.add2 + (long long)m * e.ld2 + n);
-                if (e.beta != 0.f && e.C) {
-                    const float4 o = *reinterpret_cast<const float4*>(e.C + (long long)m * e.ldc + n);
-                    a1[i].x += e.beta * o.x; a1[i].y += e.beta * o.y; a1[i].z += e.beta * o.z; a1[i].w += e.beta * o.w;
+            for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + (lane >> 3), m = mrow0 + rr;
+                if (!((rows_in >> rr) & 1u)) continue;
+                const float4 sv = epi_ld4(sE, rr, lane & 7);
+                float4 x = make_float4(sv.x + bsum.x, sv.y + bsum.y, sv.z + bsum.z, sv.w + bsum.w);
+                if (!((rows_keep >> rr) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e.C) *reinterpret_cast<float4*>(e.C + (long long)m * e.ldc + n) = x;
+                if (e.C16) {
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(e.C16 + (long long)m * e.ldc16 + n) = pk;
                 }
             }
+            return;
         }
+        // general path: the add / beta operands of four rows are fetched before those rows are stored (two halves keep the
+        // register footprint of the operand prefetch at 32 instead of 64)
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            float4 a1[4], a2[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + (lane >> 3), m = mrow0 + rr;
-            if (!((rows_in >> rr) & 1u)) continue;
-            const float* s = sE + rr * EPI_LD + cc;
-            float4 x = make_float4(s[0] + bsum.x + a1[i].x + a2[i].x, s[1] + bsum.y + a1[i].y + a2[i].y,
-                                   s[2] + bsum.z + a1[i].z + a2[i].z, s[3] + bsum.w + a1[i].w + a2[i].w);
-            if (!((rows_keep >> rr) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e.C) *reinterpret_cast<float4*>(e.C + (long long)m * e.ldc + n) = x;
-            if (e.C16) {
-                const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
-                uint2 pk;
-                pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-                *reinterpret_cast<uint2*>(e.C16 + (long long)m * e.ldc16 + n) = pk;
+            for (int i = 0; i < 4; ++i) {
+                const int rr = (h * 4 + i) * 4 + (lane >> 3), m = mrow0 + rr;
+                a1[i] = make_float4(0.f, 0.f, 0.f, 0.f); a2[i] = a1[i];
+                if ((rows_keep >> rr) & 1u) {
+                    if (e.add1) a1[i] = *reinterpret_cast<const float4*>(e.add1 + (long long)m * e.ld1 + n);
+                    if (e.add2) a2[i] = *reinterpret_cast<const float4*>(e.add2 + (long long)m * e.ld2 + n);
+                    if (e.beta != 0.f && e.C) {
+                        const float4 o = *reinterpret_cast<const float4*>(e.C + (long long)m * e.ldc + n);
+                        a1[i].x += e.beta * o.x; a1[i].y += e.beta * o.y; a1[i].z += e.beta * o.z; a1[i].w += e.beta * o.w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int rr = (h * 4 + i) * 4 + (lane >> 3), m = mrow0 + rr;
+                if (!((rows_in >> rr) & 1u)) continue;
+                const float4 sv = epi_ld4(sE, rr, lane & 7);
+                float4 x = make_float4(sv.x + bsum.x + a1[i].x + a2[i].x, sv.y + bsum.y + a1[i].y + a2[i].y,
+                                       sv.z + bsum.z + a1[i].z + a2[i].z, sv.w + bsum.w + a1[i].w + a2[i].w);
+                if (!((rows_keep >> rr) & 1u)) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (e.C) *reinterpret_cast<float4*>(e.C + (long long)m * e.ldc + n) = x;
+                if (e.C16) {
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(e.C16 + (long long)m * e.ldc16 + n) = pk;
+                }
             }
         }
     } else if (e.vec == 3 && nb + 32 <= e.N) {
@@ -215,11 +246,16 @@ __device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ s
         for (int i = 0; i < 8; ++i) {
             const int rr = i * 4 + (lane >> 3), m = mrow0 + rr;
             if (!((rows_in >> rr) & 1u)) continue;
-            const float* sr = sE + rr * EPI_LD;
             const bool keep_row = ((rows_keep >> rr) & 1u) != 0;
+            // 128-bit reads of the aligned groups that hold this lane's four (possibly shifted) columns
+            const float4 ga = epi_ld4(sE, rr, edge ? 0 : j), gb = epi_ld4(sE, rr, edge ? 7 : (j < 7 ? j + 1 : 7));
+            float sv[4];
+            if (!odd) { sv[0] = ga.x; sv[1] = ga.y; sv[2] = ga.z; sv[3] = ga.w; }
+            else if (!edge) { sv[0] = ga.z; sv[1] = ga.w; sv[2] = gb.x; sv[3] = gb.y; }
+            else { sv[0] = ga.x; sv[1] = ga.y; sv[2] = gb.z; sv[3] = gb.w; }
             float x[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) x[q] = keep_row ? sr[col[q]] + b[q] : 0.f;
+            for (int q = 0; q < 4; ++q) x[q] = keep_row ? sv[q] + b[q] : 0.f;
             float* dst = e.C + (long long)m * e.ldc + nb;
             if (!edge) *reinterpret_cast<float4*>(dst + col[0]) = make_float4(x[0], x[1], x[2], x[3]);
             else {
@@ -249,8 +285,8 @@ __device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ s
             for (int u = 0; u < 8; ++u) {
                 const int rr = (i0 + u) * 2 + (lane >> 4), m = mrow0 + rr;
                 if (!((rows_in >> rr) & 1u)) continue;
-                const float* s = sE + rr * EPI_LD + cc;
-                float2 x = make_float2(s[0] + bsum.x + a[u].x, s[1] + bsum.y + a[u].y);
+                const float2 sv = *reinterpret_cast<const float2*>(sE + epi_off(rr, cc));
+                float2 x = make_float2(sv.x + bsum.x + a[u].x, sv.y + bsum.y + a[u].y);
                 if (!((rows_keep >> rr) & 1u)) x = make_float2(0.f, 0.f);
                 if (e.C) *reinterpret_cast<float2*>(e.C + (long long)m * e.ldc + n) = x;
                 if (e.C16) *reinterpret_cast<__nv_bfloat162*>(e.C16 + (long long)m * e.ldc16 + n) = __floats2bfloat162_rn(x.x, x.y);
@@ -278,7 +314,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ s
             for (int u = 0; u < 8; ++u) {
                 const int rr = r0 + u, m = mrow0 + rr;
                 if (!nok || !((rows_in >> rr) & 1u)) continue;
-                float x = sE[rr * EPI_LD + lane] + bsum + a[u];
+                float x = sE[epi_off(rr, lane)] + bsum + a[u];
                 if (!((rows_keep >> rr) & 1u)) x = 0.f;
                 if (e.C) e.C[(long long)m * e.ldc + n] = x;
                 if (e.C16) e.C16[(long long)m * e.ldc16 + n] = __float2bfloat16_rn(x);
@@ -445,7 +481,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         released = true;
                     }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sE[lane * EPI_LD + j] = __uint_as_float(v[j]);
+                    for (int g4 = 0; g4 < 8; ++g4)
+                        *reinterpret_cast<float4*>(sE + epi_off4(lane, g4)) =
+                            make_float4(__uint_as_float(v[4 * g4]), __uint_as_float(v[4 * g4 + 1]),
+                                        __uint_as_float(v[4 * g4 + 2]), __uint_as_float(v[4 * g4 + 3]));
                     __syncwarp();
                     epilogue_store_chunk(sE, lane, mrow0, nb, ee);
                     __syncwarp();
@@ -660,7 +699,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         released = true;
                     }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sE[lane * EPI_LD + j] = __uint_as_float(v[j]);
+                    for (int g4 = 0; g4 < 8; ++g4)
+                        *reinterpret_cast<float4*>(sE + epi_off4(lane, g4)) =
+                            make_float4(__uint_as_float(v[4 * g4]), __uint_as_float(v[4 * g4 + 1]),
+                                        __uint_as_float(v[4 * g4 + 2]), __uint_as_float(v[4 * g4 + 3]));
                     __syncwarp();
                     epilogue_store_chunk(sE, lane, mrow0, nb, ee);
                     __syncwarp();
