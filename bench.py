@@ -30,7 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 V, A, D, E, P, C, MAXLEN = 9490, 512, 512, 512, 196, 2048, 25
-PROF_STRIDE = 5          # attention-step launches per direction per step = MAXLEN - 1 = 24: stride 5 visits every time step
+PROF_STRIDE = 11         # attention-step launches per direction per step = MAXLEN - 1 = 24: stride 11 (coprime) visits every time step
 B_PER_GPU = 512
 CPU_SAMPLE_B = 32
 # fused attention step, forward, fp32 features: P*C*4 + P*A*4 + (A + C + C + P)*4 per (image, step)
