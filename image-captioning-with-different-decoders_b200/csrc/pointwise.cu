@@ -106,41 +106,51 @@ __global__ void colsum_kernel(const float* __restrict__ X, long long ld, long lo
 }
 
 // partial[chunk][n] = sum over the rows of `chunk` of mask[m] * X16[m*ld + n]   (bf16 source, fp32 accumulate).
-// grid = (ceil(N/256), chunks), block = 128 threads x 2 columns; rows of a chunk are streamed with 32-bit loads.
+// grid = (ceil(N/1024), chunks), block = 128 threads x 8 columns; 8 rows in flight per thread with 128-bit loads when the
+// rows are 16-byte aligned (vec), element loads otherwise; masked rows are not read.  Rows are added in index order.
+constexpr int COLSUM16_ROWS = 128;          // rows per chunk (partial row); also the workspace contract below
 __global__ void __launch_bounds__(128) colsum_bf16_partial_kernel(const __nv_bfloat16* __restrict__ X, long long ld,
                                                                   long long M, int N, int rows_per_chunk,
                                                                   const unsigned char* __restrict__ row_mask,
-                                                                  float* __restrict__ partial) {
-    const int n = blockIdx.x * 256 + threadIdx.x * 2;
+                                                                  float* __restrict__ partial, int vec) {
+    const int n = blockIdx.x * 1024 + threadIdx.x * 8;
+    if (n >= N) return;
     const long long m0 = (long long)blockIdx.y * rows_per_chunk;
     const long long m1 = min(M, m0 + rows_per_chunk);
-    float a0 = 0.f, a1 = 0.f;
-    if (n < N) {
-        const bool pair = (n + 1 < N);
-        long long m = m0;
-        for (; m + 3 < m1; m += 4) {
-            uint32_t v[4];
+    const int nc = min(8, N - n);                          // valid columns of this thread
+    float acc[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const __nv_bfloat16* p = X + (m + u) * ld + n;
-                v[u] = pair ? *reinterpret_cast<const uint32_t*>(p) : (uint32_t)(*reinterpret_cast<const unsigned short*>(p));
-            }
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    auto load_row = [&](long long m) -> uint4 {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (row_mask && !row_mask[m]) return v;            // masked row: contributes +0, not read
+        const __nv_bfloat16* p = X + m * ld + n;
+        if (vec && nc == 8) return *reinterpret_cast<const uint4*>(p);
+        unsigned short e[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (row_mask && !row_mask[m + u]) continue;
-                a0 += __uint_as_float(v[u] << 16); a1 += __uint_as_float(v[u] & 0xffff0000u);
-            }
-        }
-        for (; m < m1; ++m) {
-            if (row_mask && !row_mask[m]) continue;
-            const __nv_bfloat16* p = X + m * ld + n;
-            const uint32_t v = pair ? *reinterpret_cast<const uint32_t*>(p) : (uint32_t)(*reinterpret_cast<const unsigned short*>(p));
-            a0 += __uint_as_float(v << 16); a1 += __uint_as_float(v & 0xffff0000u);
-        }
-        float* o = partial + (long long)blockIdx.y * N + n;
-        o[0] = a0;
-        if (pair) o[1] = a1;
+        for (int j = 0; j < 8; ++j) e[j] = (j < nc) ? *reinterpret_cast<const unsigned short*>(p + j) : (unsigned short)0;
+        v.x = e[0] | ((uint32_t)e[1] << 16); v.y = e[2] | ((uint32_t)e[3] << 16);
+        v.z = e[4] | ((uint32_t)e[5] << 16); v.w = e[6] | ((uint32_t)e[7] << 16);
+        return v;
+    };
+    auto add_row = [&](const uint4& v) {
+        acc[0] += __uint_as_float(v.x << 16); acc[1] += __uint_as_float(v.x & 0xffff0000u);
+        acc[2] += __uint_as_float(v.y << 16); acc[3] += __uint_as_float(v.y & 0xffff0000u);
+        acc[4] += __uint_as_float(v.z << 16); acc[5] += __uint_as_float(v.z & 0xffff0000u);
+        acc[6] += __uint_as_float(v.w << 16); acc[7] += __uint_as_float(v.w & 0xffff0000u);
+    };
+    long long m = m0;
+    for (; m + 7 < m1; m += 8) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = load_row(m + u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) add_row(v[u]);
     }
+    for (; m < m1; ++m) add_row(load_row(m));
+    float* o = partial + (long long)blockIdx.y * N + n;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (j < nc) o[j] = acc[j];
 }
 
 template <typename TT>
@@ -385,7 +395,7 @@ int icd_colsum(const float* X, int64_t ld, int64_t M, int N, const uint8_t* row_
 }
 
 int64_t icd_colsum_bf16_ws_floats(int64_t M, int N) {
-    const int64_t chunks = (M + 511) / 512;
+    const int64_t chunks = (M + COLSUM16_ROWS - 1) / COLSUM16_ROWS;
     return chunks * N;
 }
 
@@ -394,11 +404,13 @@ int icd_colsum_bf16(const void* X16, int64_t ld, int64_t M, int N, const uint8_t
                     cudaStream_t s) {
     if (N == 0) return 0;
     ICD_CHECK_ARG(ld % 2 == 0, "colsum_bf16: ld must be even");
-    const int rows_per_chunk = 512;
+    const int rows_per_chunk = COLSUM16_ROWS;
     const int chunks = (int)((M + rows_per_chunk - 1) / rows_per_chunk);
-    dim3 grid((N + 255) / 256, chunks);
+    ICD_CHECK_ARG(chunks <= 65535, "colsum_bf16: too many rows");
+    const int vec = (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(X16) & 15) == 0);
+    dim3 grid((N + 1023) / 1024, chunks);
     colsum_bf16_partial_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(X16), ld, M, N, rows_per_chunk,
-                                                    row_mask, ws);
+                                                    row_mask, ws, vec);
     ICD_LAUNCH_CHECK();
     return icd_colsum(ws, N, chunks, N, nullptr, out, s);
 }
