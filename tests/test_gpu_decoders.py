@@ -603,3 +603,36 @@ def test_beam_search_batch_equals_single_images_under_compaction(cuda, precision
             assert torch.equal(one["score"][0], full["score"][i])
             assert torch.equal(one["alpha"][0, :L], full["alpha"][i, :L])
             assert torch.equal(one["trace"][:, 0], full["trace"][:, i])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,tol,gtol", [("fp32", 1e-4, 2e-3), ("fp32x3", 1e-4, 3e-3), ("bf16", 8e-3, 1.5e-1)])
+def test_attention_decoder_real_vocabulary_size_odd_v(cuda, precision, tol, gtol):
+    """V = 8111 (the reference's real COCO vocabulary): an ODD row length, so the logits rows take every
+    4-byte alignment and the vocabulary-layer kernels run their scalar / shifted paths, at the full model dimensions."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.vocabulary import synthetic_vocab
+    case = dict(B=3, V=8111, A=512, D=512, E=512, max_len=6, lengths=[6, 5, 3], wseed=5, iseed=77,
+                dropout=0.0, train=False, fine_tune_embedding=True)
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams,
+                                   synthetic_vocab(case["V"]))
+    w = {k: v.detach().clone().requires_grad_(True) for k, v in dec.state_dict().items()}
+    dec = dec.to(cuda)
+    dec.precision = precision
+    enc = synthetic_features(case["B"], case["iseed"])
+    caps, lens = synthetic_caps(case)
+    preds, cs, dl, alphas = dec(enc.to(cuda), caps.to(cuda), lens)
+    o_preds, _, o_dl, o_alphas = O.attention_decoder_forward(w, enc, caps, lens)
+    assert dl == o_dl
+    H.assert_close_norm(preds, o_preds, tol, "predictions")
+    H.assert_close_norm(alphas, o_alphas, tol, "alphas")
+    from icd_b200.losses import attention_caption_loss
+    loss = attention_caption_loss(preds, cs, dl, alphas)
+    o_loss = O.attention_loss(o_preds, caps, o_dl, o_alphas)
+    assert abs(loss.item() - o_loss.item()) < max(tol, 1e-5) * abs(o_loss.item())
+    loss.backward()
+    o_loss.backward()
+    for k, p in dec.named_parameters():
+        if k == "attention.full_att.bias":
+            continue
+        H.assert_close_norm(p.grad, w[k].grad, gtol, "grad " + k, atol=1e-6)
