@@ -126,7 +126,10 @@ def workload_config(n, precision, batch):
                         "V=9490, A=D=E=512, 14x14x2048 synthetic features, embedding frozen, dropout 0.5" % batch,
             "global_batch": batch * n, "per_gpu_batch": batch, "decode_steps": 24, "vocab": V,
             "gemm_precision": precision, "parallelism": "dp%d" % n,
-            "l2": "inputs_exceed_l2 (822 MB of features per step vs 126 MB L2; no explicit flush)"}
+            "l2": "inputs_exceed_l2 (822 MB of features per step vs 126 MB L2; no explicit flush)",
+            "loss_gradient": ("bf16 tier: attention_caption_loss(bf16_grad_only=True) - the logit gradient reaches the decoder "
+                              "backward as its bf16 copy only (the fp32 copy is not materialised)")
+                             if precision == "bf16" else "fp32"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -447,7 +450,7 @@ def main():
 
     def train_step(enc, caps):
         preds, caps_sorted, dl, alphas = dec(enc, caps, lens)
-        loss = attention_caption_loss(preds, caps_sorted, dl, alphas, alpha_c=1.0)
+        loss = attention_caption_loss(preds, caps_sorted, dl, alphas, alpha_c=1.0, bf16_grad_only=True)
         opt.zero_grad()
         loss.backward()
         opt.step()

@@ -30,23 +30,32 @@ _BF16_SIDECAR = {}
 
 
 def take_bf16_sidecar(grad):
-    """-> bf16 tensor (R, ld16) matching the fp32 gradient ``grad`` if the fused loss produced one, else None."""
+    """-> bf16 tensor (R, ld16) matching the fp32 gradient ``grad`` if the fused loss produced one, else None.
+    Raises if ``grad`` is a HOLLOW fp32 gradient (``bf16_grad_only=True``) whose bf16 copy can no longer be trusted."""
     ent = _BF16_SIDECAR.pop(grad.data_ptr(), None)
+    orphan_hollow = any(e[3] and e[1].numel() == grad.numel() for e in _BF16_SIDECAR.values())
     _BF16_SIDECAR.clear()
     if ent is None:
+        if orphan_hollow:            # autograd summed the hollow gradient with another one into a new tensor
+            raise RuntimeError("attention_caption_loss(bf16_grad_only=True): the logit gradient reaching the decoder is "
+                               "not the one the loss produced (predictions feed something else too); use "
+                               "bf16_grad_only=False")
         return None
-    d16, d32, version = ent
+    d16, d32, version, hollow = ent
     if d32.numel() != grad.numel() or d32._version != version or grad._version != version:
+        if hollow:
+            raise RuntimeError("attention_caption_loss(bf16_grad_only=True): the logit gradient was modified before it "
+                               "reached the decoder (predictions feed something else too); use bf16_grad_only=False")
         return None
     return d16
 
 
 class _FusedCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits2d, targets, n_valid, want_bf16):
+    def forward(ctx, logits2d, targets, n_valid, want_bf16, bf16_only=False):
         row_loss, lse = ops.cross_entropy_fwd(logits2d, targets)
         ctx.save_for_backward(logits2d, targets, lse)
-        ctx.n_valid, ctx.want_bf16 = n_valid, want_bf16
+        ctx.n_valid, ctx.want_bf16, ctx.bf16_only = n_valid, want_bf16, bool(bf16_only and want_bf16)
         return row_loss.sum() / n_valid
 
     @staticmethod
@@ -54,11 +63,11 @@ class _FusedCE(torch.autograd.Function):
         logits2d, targets, lse = ctx.saved_tensors
         g = g.reshape(1).float().contiguous()
         d_logits, d16 = ops.cross_entropy_bwd(logits2d, targets, lse, 1.0 / ctx.n_valid, upstream=g,
-                                              want_bf16=ctx.want_bf16)
+                                              want_bf16=ctx.want_bf16, want_fp32=not ctx.bf16_only)
         _BF16_SIDECAR.clear()
         if d16 is not None:
-            _BF16_SIDECAR[d_logits.data_ptr()] = (d16, d_logits, d_logits._version)
-        return d_logits, None, None, None
+            _BF16_SIDECAR[d_logits.data_ptr()] = (d16, d_logits, d_logits._version, ctx.bf16_only)
+        return d_logits, None, None, None, None
 
 
 class _AlphaReg(torch.autograd.Function):
@@ -98,11 +107,15 @@ def packed_targets(encoded_captions, decode_lengths, T, row_valid=None):
     return torch.where(active, tgt, torch.full_like(tgt, -1)), int(sum(decode_lengths))
 
 
-def attention_caption_loss(predictions, encoded_captions, decode_lengths, alphas, alpha_c=1.0):
+def attention_caption_loss(predictions, encoded_captions, decode_lengths, alphas, alpha_c=1.0, bf16_grad_only=False):
+    """bf16_grad_only (bf16 tier only): the loss backward writes ONLY the bf16 copy of d(loss)/d(logits) that the decoder
+    backward consumes and leaves the 466 MB fp32 gradient tensor hollow.  Valid when ``predictions`` feeds nothing but this
+    loss in the autograd graph — the reference train loop (models/attention.py:401-414; its top-5 accuracy is computed
+    without a graph).  If the gradient is modified on its way to the decoder the backward raises instead of reading it."""
     B, T, V = predictions.shape
     tgt, n_valid = packed_targets(encoded_captions, decode_lengths, T, getattr(predictions, "_icd_row_valid", None))
     want_bf16 = bool(getattr(predictions, "_icd_bf16_tier", False))
-    ce = _FusedCE.apply(predictions.reshape(B * T, V), tgt.reshape(-1).contiguous(), n_valid, want_bf16)
+    ce = _FusedCE.apply(predictions.reshape(B * T, V), tgt.reshape(-1).contiguous(), n_valid, want_bf16, bf16_grad_only)
     return ce + alpha_regulariser(alphas, alpha_c)
 
 

@@ -212,18 +212,22 @@ def cross_entropy_fwd(logits, targets):
     return row_loss, lse
 
 
-def cross_entropy_bwd(logits, targets, lse, inv_count, upstream=None, want_bf16=False):
+def cross_entropy_bwd(logits, targets, lse, inv_count, upstream=None, want_bf16=False, want_fp32=True):
     """-> (d_logits (R,V) fp32 = (softmax - onehot) * inv_count * upstream, d_logits16 (R, up8(V)) bf16 or None);
-    ``upstream`` is a 0-dim / 1-element CUDA fp32 tensor read on the device (no host sync)."""
+    ``upstream`` is a 0-dim / 1-element CUDA fp32 tensor read on the device (no host sync).
+    want_fp32=False (needs want_bf16): the fp32 gradient is NOT written — the returned fp32 tensor is allocated but
+    hollow (its contents are undefined); only for callers that hand the bf16 copy on (see losses._FusedCE)."""
     _need_cuda(logits, targets, lse)
     R, V = logits.shape
+    assert want_fp32 or want_bf16
     d_logits = torch.empty_like(logits)
     d16, ld16 = None, 0
     if want_bf16:
         ld16 = (V + 7) // 8 * 8
         d16 = torch.empty(R, ld16, device=logits.device, dtype=torch.bfloat16)
     check(lib().icd_cross_entropy_bwd(ctypes.c_int64(R), V, ptr(logits), ptr(targets), ptr(lse), ptr(upstream),
-                                      ctypes.c_float(inv_count), ptr(d_logits), ptr(d16), ctypes.c_int64(ld16),
+                                      ctypes.c_float(inv_count), ptr(d_logits) if want_fp32 else None, ptr(d16),
+                                      ctypes.c_int64(ld16),
                                       stream_ptr()), "icd_cross_entropy_bwd")
     return d_logits, d16
 

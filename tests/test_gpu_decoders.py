@@ -636,3 +636,36 @@ def test_attention_decoder_real_vocabulary_size_odd_v(cuda, precision, tol, gtol
         if k == "attention.full_att.bias":
             continue
         H.assert_close_norm(p.grad, w[k].grad, gtol, "grad " + k, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_bf16_grad_only_loss_is_identical_and_refuses_misuse(cuda):
+    """attention_caption_loss(bf16_grad_only=True) skips the fp32 copy of d(loss)/d(logits): the decoder gradients are
+    bit-identical (the bf16 tier consumes the bf16 copy either way), and a graph in which ``predictions`` also feeds
+    something else is refused with an error instead of silently reading the hollow fp32 tensor."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.losses import attention_caption_loss
+    from icd_b200.vocabulary import synthetic_vocab
+    case = dict(B=6, V=310, A=64, D=64, E=64, max_len=9, lengths=[9, 8, 8, 5, 3, 2], wseed=2, iseed=41,
+                dropout=0.0, train=False, fine_tune_embedding=True)
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams,
+                                   synthetic_vocab(case["V"])).to(cuda)
+    dec.precision = "bf16"
+    enc = synthetic_features(case["B"], case["iseed"]).to(cuda)
+    caps, lens = synthetic_caps(case)
+    caps = caps.to(cuda)
+    grads = []
+    for only in (False, True):
+        dec.zero_grad()
+        preds, cs, dl, alphas = dec(enc, caps, lens)
+        attention_caption_loss(preds, cs, dl, alphas, bf16_grad_only=only).backward()
+        grads.append({k: p.grad.clone() for k, p in dec.named_parameters()})
+    for k in grads[0]:
+        if k == "embedding.weight":           # scatter-add with atomics: run-to-run summation order differs
+            H.assert_close_norm(grads[1][k], grads[0][k], 1e-5, "grad " + k)
+        else:
+            assert torch.equal(grads[0][k], grads[1][k]), k
+    preds, cs, dl, alphas = dec(enc, caps, lens)
+    loss = attention_caption_loss(preds, cs, dl, alphas, bf16_grad_only=True) + 1e-3 * preds.sum()
+    with pytest.raises(RuntimeError, match="bf16_grad_only"):
+        loss.backward()
