@@ -195,3 +195,26 @@ def test_reference_whole_module_checkpoint_loads_as_drop_in(tmp_path):
     assert type(base) is my_base.BaselineDecoder and base.precision == "fp32"
     assert all(torch.equal(v, ref_base.state_dict()[k]) for k, v in base.state_dict().items())
     assert isinstance(dec_opt, torch.optim.Adam)
+
+
+def test_oracle_loss_glue_equals_pack_padded_sequence_expression():
+    """The oracle restates models/attention.py:401-414 without pack_padded_sequence (explicit time-major gather of the
+    first batch_size_t rows); check it against the reference's literal expression on random ragged, sorted lengths,
+    and the teacher-forced ids against torch.max(dim=2) truncated to decode_lengths (:544-553)."""
+    from torch.nn.utils.rnn import pack_padded_sequence
+    g = torch.Generator().manual_seed(3)
+    for trial in range(6):
+        B, T, V, P = 2 + trial, 3 + 2 * trial, 37 + trial, 11
+        dl = sorted((int(x) for x in torch.randint(1, T + 1, (B,), generator=g)), reverse=True)
+        dl[0] = T
+        preds = torch.randn(B, T, V, generator=g, dtype=torch.float64)
+        alphas = torch.rand(B, T, P, generator=g, dtype=torch.float64)
+        caps = torch.randint(0, V, (B, T + 1), generator=g)
+        scores = pack_padded_sequence(preds, dl, batch_first=True).data
+        targets = pack_padded_sequence(caps[:, 1:], dl, batch_first=True).data
+        ref = torch.nn.CrossEntropyLoss()(scores, targets) + ((1.0 - alphas.sum(dim=1)) ** 2).mean()
+        got = O.attention_loss(preds, caps, dl, alphas, alpha_c=1.0)
+        assert abs(float(ref) - float(got)) < 1e-12 * max(1.0, abs(float(ref)))
+        ids = O.teacher_forced_ids(preds, dl)
+        _, top = torch.max(preds, dim=2)
+        assert [list(map(int, r)) for r in ids] == [top[j, :dl[j]].tolist() for j in range(B)]
