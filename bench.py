@@ -13,9 +13,13 @@ all-reduce (N > 1) + clamp(+-5) + Adam(1e-4).  Weak scaling: per-GPU work is fix
 
 Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM; `e2e`: the same step driven from pinned HOST
 buffers through the public module API, H2D copies of features+captions and the D2H read of the loss inside the timed
-region.  `roofline`: the fused attention-step forward kernel (HBM-bound), algorithmic bytes / live CUDA-event time.
-`cpu_baseline` / `--impl reference`: the reference algorithm (oracle/decoders.py, per-step enc_att recompute as at
-models/attention.py:54) on the host cores, on a bounded sample of the same workload.
+region (+ the box's copy-only H2D ceiling measured in the same run).  `roofline`: the DOMINANT kernel of the step, the
+fused attention-step backward (HBM-bound), algorithmic bytes / live CUDA-event time; the forward kernel nested under
+`roofline.fwd`.  `beam5`: configs[4], image-sharded over all ranks with the final gather.  At N = 1 the line also carries
+`other_configs` (configs[1] baseline decoder, configs[3] glove_att, the fp32x3 / fp32 tiers of configs[2], the unmodified
+reference run by eager PyTorch on the same GPU, a parity check of the timed path against the fp64 oracle) and
+`cpu_baseline` / `cpu_baseline_configs0`.  `--impl reference` (and `cpu_baseline`): the UNMODIFIED reference modules from
+baseline/_ref (baseline/install_ref.py) on the host cores, on a bounded 32-caption slice of the same workload.
 """
 import argparse
 import json
@@ -46,61 +50,109 @@ def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="icd_b200", choices=["icd_b200", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp32x3", "bf16"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="captions per GPU (default: the benchmark config)")
-    ap.add_argument("--workload", default="train", choices=["train", "beam", "baseline", "glove"],
+    ap.add_argument("--workload", default="train", choices=["train", "beam", "baseline", "glove", "tier"],
                     help="train = BASELINE.json configs[2] (the metric's configuration, default); the others time the "
                          "remaining configs and print their own JSON line")
     ap.add_argument("--beam-images", type=int, default=1024, help="images per GPU for the beam-search measurement")
     ap.add_argument("--no-beam", action="store_true", help="skip the beam-5 side measurement of the default run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other configs / context figures / parity check of the N=1 line")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
 # ---------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the reference algorithm on the host cores (oracle port)
+# reference arm / cpu_baseline: the reference's own CPU implementation on the host cores
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_steps(steps, warmup, sample_b=CPU_SAMPLE_B):
-    """Time `steps` train steps of the reference algorithm on a `sample_b`-caption slice of the benchmark batch."""
+REF_INSTALL = os.path.join(ROOT, "baseline", "_ref")
+
+
+def _reference_namespace():
+    """The UNMODIFIED reference, imported from its verbatim install under baseline/_ref (baseline/install_ref.py; git-ignored,
+    shipped to the GPU box with the snapshot).  None when the install is absent."""
+    if not os.path.isfile(os.path.join(REF_INSTALL, "models", "attention.py")):
+        return None
+    from oracle import reference_import
+    return reference_import.load_reference(REF_INSTALL), reference_import
+
+
+def cpu_reference_steps(steps, warmup, sample_b=CPU_SAMPLE_B, want="auto"):
+    """Time `steps` train steps of the reference on a `sample_b`-caption slice of the benchmark batch, all host cores.
+    kind "reference": the reference's own modules (models/attention.py:72-284, train_utils.py:2-12) driven by the body of its
+    train loop (models/attention.py:396-430) restated literally; kind "port": oracle/decoders.py (only when the install is
+    missing)."""
     import torch
+    from torch.nn.utils.rnn import pack_padded_sequence
     from icd_b200 import synthetic
-    from icd_b200.vocabulary import synthetic_vocab
-    import icd_b200.models.attention as my_att
-    from oracle import decoders as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    p = my_att.AttentionDecoderParams()
-    p.vocab = synthetic_vocab(V)
-    torch.manual_seed(0)
-    dec = my_att.AttentionDecoder(torch.device("cpu"), p)       # used as a seeded weight container only
-    dec.fine_tune_embeddings(False)
-    w = {k: v.detach().clone().requires_grad_(k != "embedding.weight") for k, v in dec.state_dict().items()}
-    params = [t for t in w.values() if t.requires_grad]
-    opt = torch.optim.Adam(params, lr=1e-4)
     enc = synthetic.features(sample_b)
     caps, lens = synthetic.captions(sample_b, V, max_len=MAXLEN)
+    ref = _reference_namespace() if want in ("auto", "reference") else None
     times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        dl = [l - 1 for l in lens]
-        masks = [(torch.rand(sum(x > t for x in dl), D) >= 0.5).float() for t in range(max(dl))]
-        preds, _, dl, alphas = O.attention_decoder_forward(w, enc, caps, lens, dropout_p=0.5, dropout_masks=masks)
-        loss = O.attention_loss(preds, caps, dl, alphas)
-        opt.zero_grad()
-        loss.backward()
-        for t in params:
-            t.grad.clamp_(-5.0, 5.0)
-        opt.step()
-        loss.item()
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
+    if ref is not None:
+        ns, reference_import = ref
+        kind = "reference"
+        p = ns.AttentionDecoderParams()
+        p.vocab = reference_import.make_reference_vocab(ns, V)
+        torch.manual_seed(0)
+        dec = ns.AttentionDecoder(torch.device("cpu"), p)
+        dec.fine_tune_embeddings(False)                           # train.py:41 default
+        dec.train()
+        opt = torch.optim.Adam(params=filter(lambda q: q.requires_grad, dec.parameters()), lr=1e-4)   # :352-355
+        criterion = torch.nn.CrossEntropyLoss()                   # :371
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            scores, caps_sorted, decode_lengths, alphas = dec(enc, caps, lens)                         # :396
+            targets = caps_sorted[:, 1:]                                                               # :401
+            scores = pack_padded_sequence(scores, decode_lengths, batch_first=True).data               # :405-406
+            targets = pack_padded_sequence(targets, decode_lengths, batch_first=True).data             # :407-408
+            loss = criterion(scores, targets)                                                          # :411
+            loss += 1.0 * ((1. - alphas.sum(dim=1)) ** 2).mean()                                       # :414
+            opt.zero_grad()                                                                            # :417
+            loss.backward()                                                                            # :420
+            ns.clip_gradient(opt, 5.0)                                                                 # :423
+            opt.step()                                                                                 # :428
+            loss.item()                                                                                # :433
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    else:
+        kind = "port"
+        from icd_b200.vocabulary import synthetic_vocab
+        import icd_b200.models.attention as my_att
+        from oracle import decoders as O
+        p = my_att.AttentionDecoderParams()
+        p.vocab = synthetic_vocab(V)
+        torch.manual_seed(0)
+        dec = my_att.AttentionDecoder(torch.device("cpu"), p)       # used as a seeded weight container only
+        dec.fine_tune_embeddings(False)
+        w = {k: v.detach().clone().requires_grad_(k != "embedding.weight") for k, v in dec.state_dict().items()}
+        params = [t for t in w.values() if t.requires_grad]
+        opt = torch.optim.Adam(params, lr=1e-4)
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            dl = [l - 1 for l in lens]
+            masks = [(torch.rand(sum(x > t for x in dl), D) >= 0.5).float() for t in range(max(dl))]
+            preds, _, dl, alphas = O.attention_decoder_forward(w, enc, caps, lens, dropout_p=0.5, dropout_masks=masks)
+            loss = O.attention_loss(preds, caps, dl, alphas)
+            opt.zero_grad()
+            loss.backward()
+            for t in params:
+                t.grad.clamp_(-5.0, 5.0)
+            opt.step()
+            loss.item()
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
     total = sum(times)
-    return dict(value=sample_b * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores,
-                sample="%d-caption slice of the %d-caption batch, T=24, V=%d, %d timed steps" %
-                       (sample_b, B_PER_GPU, V, len(times)))
+    return dict(value=sample_b * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores, kind=kind,
+                sample="%d-caption slice of the %d-caption batch (the reference's per-step enc_att recompute makes B=512 "
+                       "a >10 s CPU step), T=24, V=%d, %d timed steps, %s" %
+                       (sample_b, B_PER_GPU, V, len(times),
+                        "unmodified reference modules from baseline/_ref" if kind == "reference" else "oracle port"))
 
 
 def run_reference_arm(args):
@@ -108,13 +160,16 @@ def run_reference_arm(args):
     if rank != 0:
         return
     r = cpu_reference_steps(args.steps, args.warmup)
+    cfg = workload_config(args.gpus, "fp32", B_PER_GPU)
+    cfg["reference_arm_sample"] = r["sample"]
+    cfg["reference_arm_batch"] = CPU_SAMPLE_B
     line = {
         "impl": "reference", "metric": "attention-decoder train-step captions/s", "value": r["value"],
         "unit": "captions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus, "fp32", B_PER_GPU),
-        "cpu_baseline": {"value": r["value"], "unit": "captions/s", "cores": r["cores"], "kind": "port",
+        "config": cfg,
+        "cpu_baseline": {"value": r["value"], "unit": "captions/s", "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -233,22 +288,53 @@ def measured_peak_hbm():
 
 
 def ncu_traffic():
-    """dram bytes read+write per launch of the fused attention-step forward kernel from the committed ncu capture."""
+    """ncu `dram__bytes_read.sum + dram__bytes_write.sum` per launch of the two attention-step kernels, from the committed
+    `ncu --set full` capture (profiles/roofline_traffic.json).  It cannot be measured inside a timed run (ncu replays every
+    kernel ~40 times), so the bench line carries the committed figure and says where it comes from."""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(path):
         try:
-            return json.load(open(path)).get("att_step_fwd_kernel_dram_bytes_per_launch")
+            return json.load(open(path))
         except Exception:
-            return None
-    return None
+            return {}
+    return {}
 
 
-def beam_measure(dev, n_img, k=5, max_steps=24, reps=2):
+def roofline_block(precision, prof, ms_total, peak, peak_src):
+    """`roofline` of the bench line: the DOMINANT kernel of the step — the fused attention-step BACKWARD (largest share of
+    the step) — with the forward kernel nested under "fwd".  achieved = algorithmic bytes per row x rows /
+    live CUDA-event time of the sampled launches."""
+    fwd_b, bwd_b = att_bytes_per_row(precision)
+    tr = ncu_traffic()
+    sfx = "_bf16_kernel" if precision == "bf16" else "_kernel"
+
+    def one(direction, nbytes):
+        ms, n, rows = prof[direction + "_ms"], prof[direction + "_launches"], prof[direction + "_rows"]
+        ach = (nbytes * rows / (ms / 1e3) / 1e9) if ms > 0 else None
+        return {"kernel": "att_step_%s%s (fused additive-attention step, %s)" % (direction, sfx, "backward" if direction == "bwd" else "forward"),
+                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+                "traffic": tr.get("att_step_%s_kernel_dram_bytes_per_launch" % direction),
+                "traffic_source": tr.get("source", "profiles/roofline_traffic.json (committed ncu --set full capture, not this run)"),
+                "algorithmic_bytes_per_row": nbytes, "rows_per_launch": (rows / n) if n else None,
+                "launches": n, "avg_launch_ms": (ms / n) if n else None,
+                "share_of_step": (PROF_STRIDE * ms / ms_total) if ms_total else None}
+    blk = one("bwd", bwd_b)
+    blk.update({"feature_storage": "bf16" if precision == "bf16" else "fp32", "peak_source": peak_src,
+                "sampling": "every %d-th launch of the timed region is event-timed; share_of_step scales the sample back up" % PROF_STRIDE,
+                "fwd": one("fwd", fwd_b)})
+    return blk
+
+
+def beam_measure(dev, n_img, k=5, max_steps=24, reps=2, world=1, rank=0):
     """BASELINE.json configs[4]: beam search k = 5 over synthetic features, caption cap 25 tokens (loop body runs for step
-    = 1 .. max_steps + 1), weights from the beam fixture recipe so that captions terminate.  Timed region:
-    the whole batched decode (icd_beam_search, fp32 tier) + the device->host read of lengths and token ids."""
+    = 1 .. max_steps + 1), weights from the beam fixture recipe so that captions terminate; `n_img` images
+    PER GPU, image-sharded over `world` ranks with no collective until the final gather (gen_captions.beam_search_sharded).
+    Timed region (CUDA events, max over ranks): the whole batched decode on every rank + the gather of lengths / token ids /
+    scores to rank 0 + the device->host read there.  Afterwards (untimed) rank 0 re-decodes another rank's shard alone and
+    checks the gathered captions are identical to that single-GPU run."""
     import torch
-    from icd_b200.gen_captions import beam_search_batched
+    import torch.distributed as dist
+    from icd_b200.gen_captions import beam_search_batched, beam_search_sharded
     from icd_b200.vocabulary import synthetic_vocab
     import icd_b200.models.attention as my_att
     p = my_att.AttentionDecoderParams()
@@ -260,106 +346,218 @@ def beam_measure(dev, n_img, k=5, max_steps=24, reps=2):
         dec.fc.weight[V - 2] *= 30.0
         dec.fc.bias[V - 2] = -4.0
     dec = dec.to(dev).eval()
-    g = torch.Generator().manual_seed(77)
-    feats = torch.randn(n_img, 14, 14, C, generator=g).abs_().to(dev)
-    times, res = [], None
+
+    def shard(r):
+        g = torch.Generator().manual_seed(77 + r)
+        return torch.randn(n_img, 14, 14, C, generator=g).abs_().to(dev)
+    feats = shard(rank)
+    times, lens, seqs = [], None, None
     with torch.no_grad():
         for i in range(reps + 1):
+            if world > 1:
+                dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            res = beam_search_batched(dec, feats, k, V - 3, V - 2, max_steps=max_steps, want_alphas=False)
-            lens = res["len"].cpu()
-            seqs = res["seq"].cpu()
+            res = beam_search_sharded(dec, feats, k, V - 3, V - 2, max_steps=max_steps)
+            if rank == 0:
+                lens = res["len"].cpu()
+                seqs = res["seq"].cpu()
             e1.record()
             torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if i > 0:
-                times.append(e0.elapsed_time(e1))
+                times.append(float(t.item()))
+        check = None
+        if rank == 0 and world > 1:                     # the gathered shard of the LAST rank == that shard decoded on one GPU
+            r = world - 1
+            one = beam_search_batched(dec, shard(r), k, V - 3, V - 2, max_steps=max_steps, want_alphas=False)
+            check = bool(torch.equal(one["len"].cpu(), lens[r * n_img:(r + 1) * n_img]) and
+                         torch.equal(one["seq"].cpu(), seqs[r * n_img:(r + 1) * n_img]))
+    if rank != 0:
+        return None
     ms = min(times)
     done = int((lens > 0).sum())
-    return {"metric": "beam-5 captions/s", "value": n_img / (ms / 1e3), "unit": "captions/s", "images": n_img, "beam": k,
-            "max_caption_tokens": max_steps + 1, "ms": ms, "completed": done,
+    total = n_img * world
+    return {"metric": "beam-5 captions/s", "value": total / (ms / 1e3), "unit": "captions/s", "images": total,
+            "images_per_gpu": n_img, "n_gpus": world, "beam": k,
+            "max_caption_tokens": max_steps + 1, "ms": ms, "completed": done, "data": "synthetic",
+            "gathered_equals_single_gpu_run": check,
             "precision": "fp32x3 (3-term bf16 split on tcgen05, fp32-grade logits; captions identical to the reference on the goldens)",
-            "mean_len": float(lens[lens > 0].float().mean()) if done else 0.0}
+            "mean_len": float(lens[lens > 0].float().mean()) if done else 0.0,
+            "config": {"workload": "configs[4]: beam search k=5, cap 25 tokens, %d images sharded over %d GPU(s), final gather of "
+                                   "lengths + token ids + scores to rank 0 inside the timed region" % (total, world)}}
 
 
-def side_workload(args):
-    """configs[1] (baseline LSTM decoder B=128, L=25), configs[3] (glove_att: E=300, fp64 fine-tuned table, B=512) and
-    configs[4] (beam search) on one GPU: fwd + loss + bwd + clamp + Adam, CUDA-event timed."""
+def _time_steps(step, steps, warmup):
     import torch
-    import __graft_entry__
-    __graft_entry__.build()
-    from icd_b200 import synthetic
-    from icd_b200.losses import attention_caption_loss, baseline_caption_loss
-    from icd_b200.parallel import DataParallelClipAdam
-    from icd_b200.vocabulary import synthetic_vocab
-    import icd_b200.models.attention as my_att
-    import icd_b200.models.baseline as my_base
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    torch.cuda.set_device(dev)
-    if args.workload == "beam":
-        line = beam_measure(dev, args.beam_images)
-        line.update({"n_gpus": 1, "data": "synthetic", "config": {"workload": "configs[4]: beam search k=5, %d images" % args.beam_images}})
-        print(json.dumps(line), flush=True)
-        return
-    if args.workload == "baseline":
-        Bb, L = 128, MAXLEN
-        p = my_base.BaselineDecoderParams()
-        p.vocab_size = V
-        torch.manual_seed(0)
-        dec = my_base.BaselineDecoder(p).to(dev)
-        dec.precision = "bf16" if args.precision in ("auto", "bf16") else args.precision
-        opt = DataParallelClipAdam(dec, lr=1e-4, grad_clip=5.0)
-        img = torch.randn(Bb, E, device=dev, requires_grad=True)
-        caps, _ = synthetic.captions(Bb, V, max_len=L)
-        caps = caps.to(dev)
-
-        def step():
-            out = dec(img, caps)
-            loss = baseline_caption_loss(out, caps)
-            opt.zero_grad()
-            loss.backward()
-            opt.step()
-            return loss
-        name, batch = "configs[1]: baseline LSTM decoder, batch 128, L=25, V=9490, E=H=512", Bb
-    else:
-        Bb = args.batch
-        p = my_att.AttentionDecoderParams()
-        p.vocab = synthetic_vocab(V)
-        p.embed_size = 300
-        torch.manual_seed(0)
-        dec = my_att.AttentionDecoder(dev, p)
-        dec.load_pretrained_embeddins(synthetic.glove_like_table(V, 300))
-        dec.fine_tune_embeddings(True)
-        dec = dec.to(dev)
-        dec.precision = "bf16" if args.precision in ("auto", "bf16") else args.precision
-        dec.train()
-        opt = DataParallelClipAdam(dec, lr=1e-4, grad_clip=5.0)
-        enc = synthetic.features(Bb).to(dev)
-        caps, lens = synthetic.captions(Bb, V, max_len=MAXLEN)
-        caps = caps.to(dev)
-
-        def step():
-            preds, cs, dl, alphas = dec(enc, caps, lens)
-            loss = attention_caption_loss(preds, cs, dl, alphas)
-            opt.zero_grad()
-            loss.backward()
-            opt.step()
-            return loss
-        name, batch = "configs[3]: glove_att, embed 300, fp64 fine-tuned embedding table, batch %d, T=24, V=9490" % Bb, Bb
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss = step()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    print(json.dumps({"metric": "train-step captions/s", "value": batch / (ms / 1e3), "unit": "captions/s", "n_gpus": 1,
-                      "steps": args.steps, "ms_per_step": ms, "loss": float(loss.item()), "data": "synthetic",
-                      "dtype": dec.precision, "config": {"workload": name}}), flush=True)
+    return e0.elapsed_time(e1) / steps, float(loss.item())
+
+
+def measure_baseline(dev, precision="bf16", steps=20, warmup=5, world=1):
+    """BASELINE.json configs[1]: baseline LSTM decoder, batch 128 (per GPU), L = 25, V = 9490, E = H = 512:
+    fwd + loss + bwd + (gradient all-reduce) + clamp + Adam."""
+    import torch
+    from icd_b200 import synthetic
+    from icd_b200.losses import baseline_caption_loss
+    from icd_b200.parallel import DataParallelClipAdam
+    import icd_b200.models.baseline as my_base
+    Bb, L = 128, MAXLEN
+    p = my_base.BaselineDecoderParams()
+    p.vocab_size = V
+    torch.manual_seed(0)
+    dec = my_base.BaselineDecoder(p).to(dev)
+    dec.precision = precision
+    opt = DataParallelClipAdam(dec, lr=1e-4, grad_clip=5.0)
+    img = torch.randn(Bb, E, device=dev, requires_grad=True)
+    caps, _ = synthetic.captions(Bb, V, max_len=L)
+    caps = caps.to(dev)
+
+    def step():
+        out = dec(img, caps)
+        loss = baseline_caption_loss(out, caps)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+    ms, loss = _time_steps(step, steps, warmup)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"metric": "baseline-decoder train-step captions/s", "value": Bb * world / (ms / 1e3), "unit": "captions/s",
+            "n_gpus": world, "ms_per_step": ms, "steps": steps, "loss": loss, "dtype": precision, "data": "synthetic",
+            "config": {"workload": "configs[1]: baseline LSTM decoder, batch 128/GPU, L=25, V=9490, E=H=512"}}
+
+
+def measure_attention(dev, precision, batch, steps, warmup, glove=False):
+    """The attention train step on one GPU in a given tier: configs[3] (glove_att: E = 300, fp64 fine-tuned table) when
+    glove=True, else configs[2] in another precision tier (fp32x3 = the tier that meets the 1e-3 bar, fp32 = FMA tier)."""
+    import torch
+    from icd_b200 import synthetic
+    from icd_b200.losses import attention_caption_loss
+    from icd_b200.parallel import DataParallelClipAdam
+    from icd_b200.vocabulary import synthetic_vocab
+    import icd_b200.models.attention as my_att
+    p = my_att.AttentionDecoderParams()
+    p.vocab = synthetic_vocab(V)
+    if glove:
+        p.embed_size = 300
+    torch.manual_seed(0)
+    dec = my_att.AttentionDecoder(dev, p)
+    if glove:
+        dec.load_pretrained_embeddins(synthetic.glove_like_table(V, 300))
+    dec.fine_tune_embeddings(bool(glove))
+    dec = dec.to(dev)
+    dec.precision = precision
+    dec.train()
+    opt = DataParallelClipAdam(dec, lr=1e-4, grad_clip=5.0)
+    enc = synthetic.features(batch).to(dev)
+    caps, lens = synthetic.captions(batch, V, max_len=MAXLEN)
+    caps = caps.to(dev)
+
+    def step():
+        preds, cs, dl, alphas = dec(enc, caps, lens)
+        loss = attention_caption_loss(preds, cs, dl, alphas, bf16_grad_only=(precision == "bf16"))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        return loss
+    ms, loss = _time_steps(step, steps, warmup)
+    name = ("configs[3]: glove_att, embed 300, fp64 fine-tuned embedding table, batch %d, T=24, V=9490" % batch) if glove else \
+           ("configs[2] in the %s tier: basic_att train step, batch %d, T=24, V=9490" % (precision, batch))
+    return {"metric": "attention-decoder train-step captions/s", "value": batch / (ms / 1e3), "unit": "captions/s", "n_gpus": 1,
+            "ms_per_step": ms, "steps": steps, "loss": loss, "dtype": precision, "data": "synthetic", "config": {"workload": name}}
+
+
+def measure_eager_torch_reference(dev, batch=B_PER_GPU, steps=2, warmup=1):
+    """Context figure ("the bar to beat is eager PyTorch on the same B200"): the UNMODIFIED reference modules
+    (baseline/_ref; the oracle port when the install is missing) run by eager PyTorch / cuBLAS on this GPU, same batch, same
+    train-step body as the reference loop (models/attention.py:396-430).  Not a product path; nothing of icd_b200 runs here."""
+    import torch
+    from torch.nn.utils.rnn import pack_padded_sequence
+    from icd_b200 import synthetic
+    torch.backends.cuda.matmul.allow_tf32 = False          # the reference's defaults (SURVEY.md 8c caution vi)
+    enc = synthetic.features(batch).to(dev)
+    caps, lens = synthetic.captions(batch, V, max_len=MAXLEN)
+    caps = caps.to(dev)
+    ref = _reference_namespace()
+    if ref is not None:
+        ns, reference_import = ref
+        p = ns.AttentionDecoderParams()
+        p.vocab = reference_import.make_reference_vocab(ns, V)
+        torch.manual_seed(0)
+        dec = ns.AttentionDecoder(dev, p).to(dev)
+        dec.fine_tune_embeddings(False)
+        dec.train()
+        opt = torch.optim.Adam(params=filter(lambda q: q.requires_grad, dec.parameters()), lr=1e-4)
+        criterion = torch.nn.CrossEntropyLoss().to(dev)
+
+        def step():
+            scores, caps_sorted, decode_lengths, alphas = dec(enc, caps, lens)
+            targets = caps_sorted[:, 1:]
+            scores = pack_padded_sequence(scores, decode_lengths, batch_first=True).data
+            targets = pack_padded_sequence(targets, decode_lengths, batch_first=True).data
+            loss = criterion(scores, targets)
+            loss += 1.0 * ((1. - alphas.sum(dim=1)) ** 2).mean()
+            opt.zero_grad()
+            loss.backward()
+            ns.clip_gradient(opt, 5.0)
+            opt.step()
+            return loss
+        kind = "unmodified reference modules (baseline/_ref), eager PyTorch fp32 on this GPU"
+    else:
+        return {"unavailable": "baseline/_ref not installed"}
+    ms, loss = _time_steps(step, steps, warmup)
+    return {"metric": "attention-decoder train-step captions/s", "value": batch / (ms / 1e3), "unit": "captions/s",
+            "ms_per_step": ms, "steps": steps, "loss": loss, "dtype": "f32", "kind": kind,
+            "config": {"workload": "configs[2] shape, batch %d, run by the reference's own code on the GPU" % batch}}
+
+
+def side_workload(args):
+    """`--workload baseline|glove|beam|tier`: the other BASELINE.json configs as their own JSON line (1 GPU, or N ranks
+    under torchrun for baseline / beam: batch- resp. image-sharded)."""
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+    prec = "bf16" if args.precision in ("auto", "bf16") else args.precision
+    if args.workload == "beam":
+        line = beam_measure(dev, args.beam_images, world=world, rank=rank)
+    elif args.workload == "baseline":
+        line = measure_baseline(dev, prec, args.steps, max(args.warmup, 3), world=world)
+    elif args.workload == "glove":
+        line = measure_attention(dev, prec, args.batch, args.steps, max(args.warmup, 3), glove=True)
+    else:
+        line = measure_attention(dev, prec, args.batch, args.steps, max(args.warmup, 3))
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def bind_to_gpu_numa_node(device_index):
@@ -410,8 +608,8 @@ def main():
     numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("ICD_BENCH_KEEP_NCCL_DEBUG") is None:
-            os.environ["NCCL_DEBUG"] = "WARN"       # the NCCL version banner goes to stdout: keep stdout = ONE JSON line
+        # NCCL_DEBUG is left exactly as the caller set it (the driver reads the NCCL INFO lines to count the ranks of the
+        # communicator); the JSON result is the LAST line rank 0 prints, written with one flush after the final barrier
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
         __graft_entry__.build()
@@ -470,7 +668,7 @@ def main():
     sampler = ClockSampler(local_rank, uuid) if (rank == 0 and os.environ.get("ICD_BENCH_SAMPLER", "on") != "off") else None
     if sampler:
         sampler.wait_ready()
-    n_warm = max(args.warmup, 6)                        # >= 3 required; 6 lets the caching allocator reach its steady state
+    n_warm = args.warmup                                # exactly as asked (the timing rules want >= 3; the default is 3)
     ops.prof_enable(True)                               # the library creates its timing events lazily: do that during warm-up
     for _ in range(n_warm):
         train_step(enc_d, caps_d)
@@ -507,6 +705,7 @@ def main():
     # ---- end-to-end timing: host buffers -> H2D -> step -> D2H loss, copies inside the timed region,
     #      next batch prefetched on a side stream while the current step computes ----
     e2e = None
+    host16, enc_h16 = precision == "bf16", None
     if not args.no_e2e:
         copy_stream = torch.cuda.Stream()
 
@@ -607,18 +806,47 @@ def main():
             e2e["fp32_host_features"] = {"value": B * world * args.steps / (ms_f32 / 1e3), "ms_per_step": ms_f32 / args.steps,
                                          "h2d_bytes_per_step": int(enc_h.numel() * 4 + caps_h.numel() * 8)}
 
+    # ---- host -> device ceiling of this box: the SAME pinned buffers copied with nothing else running, all ranks at once ----
+    if e2e is not None:
+        src = enc_h16 if host16 else enc_h
+        dst = torch.empty(src.shape, dtype=src.dtype, device=dev)
+        dst.copy_(src, non_blocking=True)
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(5):
+            dst.copy_(src, non_blocking=True)
+        h1.record()
+        barrier()
+        t = torch.tensor([h0.elapsed_time(h1) / 5], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        h2d_ms = float(t.item())
+        nbytes = src.numel() * src.element_size()
+        ceil = B * world / (h2d_ms / 1e3)
+        e2e["h2d_ceiling"] = {"ms_per_batch_copy_alone": h2d_ms, "gbs_per_gpu": nbytes / (h2d_ms / 1e3) / 1e9,
+                              "gbs_aggregate": world * nbytes / (h2d_ms / 1e3) / 1e9, "captions_per_s": ceil,
+                              "note": "copy-only rate of the same pinned feature buffers, all %d rank(s) concurrently, max over "
+                                      "ranks: an upper bound for any end-to-end number on this box" % world}
+        e2e["frac_of_h2d_ceiling"] = e2e["value"] / ceil
+        e2e["frac_of_resident"] = e2e["value"] / (B * world * args.steps / (ms_total / 1e3))
+        del dst
+
     gc.enable()
     clocks = sampler.window(t_wall0, t_wall1) if sampler else None
     if sampler:
         sampler.stop()
 
+    # ---- configs[4]: beam search, image-sharded over ALL ranks with the final gather (collective: every rank takes part) ----
+    beam5 = None
+    if not args.no_beam:
+        try:
+            beam5 = beam_measure(dev, args.beam_images, world=world, rank=rank)
+        except Exception as ex:              # never lose the headline line over the side measurement
+            beam5 = {"error": repr(ex)[:200]}
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
-        ATT_FWD_BYTES_PER_ROW, ATT_BWD_BYTES_PER_ROW = att_bytes_per_row(precision)
-        fwd_s = prof["fwd_ms"] / 1e3
-        achieved = (ATT_FWD_BYTES_PER_ROW * prof["fwd_rows"] / fwd_s / 1e9) if fwd_s > 0 else None
-        bwd_s = prof["bwd_ms"] / 1e3
-        achieved_bwd = (ATT_BWD_BYTES_PER_ROW * prof["bwd_rows"] / bwd_s / 1e9) if bwd_s > 0 else None
         line = {
             "metric": "attention-decoder train-step captions/s",
             "value": B * world * args.steps / (ms_total / 1e3), "unit": "captions/s",
@@ -630,39 +858,74 @@ def main():
             "per_step_ms": per_step_ms, "host_issue_ms_per_step": 1e3 * t_issue / args.steps,
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {
-                "kernel": ("att_step_fwd_bf16_kernel" if precision == "bf16" else "att_step_fwd_kernel") +
-                          " (fused additive-attention step, forward)",
-                "feature_storage": "bf16" if precision == "bf16" else "fp32",
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": ncu_traffic(),
-                "peak_source": peak_src,
-                "algorithmic_bytes_per_row": ATT_FWD_BYTES_PER_ROW,
-                "launches": prof["fwd_launches"], "avg_launch_ms": (prof["fwd_ms"] / prof["fwd_launches"]) if prof["fwd_launches"] else None,
-                "sampling": "every %d-th launch of the timed region is event-timed; share_of_step scales the sample back up" % PROF_STRIDE,
-                "share_of_step": (PROF_STRIDE * prof["fwd_ms"] / ms_total) if ms_total else None,
-                "bwd": {"kernel": "att_step_bwd_bf16_kernel" if precision == "bf16" else "att_step_bwd_kernel", "achieved": achieved_bwd,
-                        "frac": (achieved_bwd / peak) if achieved_bwd else None,
-                        "algorithmic_bytes_per_row": ATT_BWD_BYTES_PER_ROW,
-                        "share_of_step": (PROF_STRIDE * prof["bwd_ms"] / ms_total) if ms_total else None},
-            },
+            "roofline": roofline_block(precision, prof, ms_total, peak, peak_src),
         }
         if e2e:
             line["e2e"] = e2e
-        if not args.no_beam:
-            try:
-                line["beam5"] = beam_measure(dev, args.beam_images)
-                line["beam5"]["note"] = "configs[4] on this GPU alone (images shard over GPUs with no collective)"
-            except Exception as ex:          # never lose the headline line over the side measurement
-                line["beam5"] = {"error": repr(ex)[:200]}
+        if beam5 is not None:
+            line["beam5"] = beam5
+        if world == 1 and not args.no_extras:
+            # the other BASELINE.json configs and context figures, one GPU, short runs (each guarded: the headline survives)
+            extras = {}
+
+            def guarded(name, fn):
+                try:
+                    extras[name] = fn()
+                except Exception as ex:
+                    extras[name] = {"error": repr(ex)[:300]}
+                torch.cuda.empty_cache()
+            guarded("parity_check", lambda: parity_check(dec, enc_d, caps_d, lens, dev))
+            guarded("configs[1]_baseline_bf16", lambda: measure_baseline(dev, "bf16", steps=20, warmup=5))
+            guarded("configs[1]_baseline_fp32x3", lambda: measure_baseline(dev, "fp32x3", steps=10, warmup=3))
+            guarded("configs[3]_glove_bf16", lambda: measure_attention(dev, "bf16", B, steps=10, warmup=3, glove=True))
+            guarded("configs[2]_fp32x3_tier", lambda: measure_attention(dev, "fp32x3", B, steps=5, warmup=3))
+            guarded("configs[2]_fp32_tier", lambda: measure_attention(dev, "fp32", B, steps=3, warmup=2))
+            guarded("eager_pytorch_reference_on_this_gpu", lambda: measure_eager_torch_reference(dev, B))
+            line["other_configs"] = extras
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_reference_steps(steps=2, warmup=1)
-            line["cpu_baseline"] = {"value": r["value"], "unit": "captions/s", "cores": r["cores"], "kind": "port",
+            line["cpu_baseline"] = {"value": r["value"], "unit": "captions/s", "cores": r["cores"], "kind": r["kind"],
                                     "sample": r["sample"]}
+            r0 = cpu_reference_steps(steps=3, warmup=1, sample_b=4)
+            line["cpu_baseline_configs0"] = {"value": r0["value"], "unit": "captions/s", "cores": r0["cores"], "kind": r0["kind"],
+                                             "ms_per_step": r0["ms_per_step"],
+                                             "sample": "configs[0] itself: basic_att, batch 4, 25 tokens, fwd + loss + bwd + clip + Adam "
+                                                       "on the host cores (README.md:7), 3 timed steps"}
+        sys.stdout.flush()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def parity_check(dec, enc_d, caps_d, lens, dev, rows=32):
+    """Checker, OUTSIDE every timed region: the exact module / tier / loss path that was just timed (current weights, train
+    mode, a fixed dropout keep-mask) on the resident B-row batch, rows 0..31 compared with the fp64 oracle evaluated on the
+    same 32 rows (rows are independent).  Full per-tensor gradient parity at this configuration: tests/test_gpu_timed_config.py."""
+    import torch
+    from oracle import decoders as O
+    B, T, Dd = enc_d.shape[0], MAXLEN - 1, dec.decoder_dim
+    g = torch.Generator().manual_seed(4321)
+    keep = (torch.rand(T, B, Dd, generator=g) >= 0.5).to(torch.uint8)
+    dec._dropout_mask_override = keep
+    try:
+        with torch.no_grad():
+            preds, _, dl, alphas = dec(enc_d, caps_d, lens)
+    finally:
+        dec._dropout_mask_override = None
+    w64 = {k: v.detach().cpu().double() for k, v in dec.state_dict().items()}
+    masks = [keep[t, :rows].double() for t in range(T)]
+    p64, _, dl64, a64 = O.attention_decoder_forward(w64, enc_d[:rows].cpu().double(), caps_d[:rows].cpu(), lens[:rows],
+                                                    dropout_p=0.5, dropout_masks=masks, hoist=True)
+    pr, al = preds[:rows].cpu().double(), alphas[:rows].cpu().double()
+    top2 = p64.topk(2, dim=2).values
+    flips = pr.argmax(2) != p64.argmax(2)
+    return {"rows": rows, "of_batch": B, "tier": dec.precision,
+            "logits_rel_err": float((pr - p64).norm() / p64.norm()), "alphas_rel_err": float((al - a64).norm() / a64.norm()),
+            "greedy_id_flips": int(flips.sum()), "positions": int(flips.numel()),
+            "greedy_id_flips_where_margin_gt_2e-2": int((flips & ((top2[..., 0] - top2[..., 1]) > 2e-2)).sum()),
+            "stated_tolerance": {"logits": 5e-3, "alphas": 5e-3} if dec.precision == "bf16" else {"logits": 1e-4, "alphas": 1e-4},
+            "oracle": "oracle/decoders.py in fp64 on the same rows (checker only)"}
 
 
 if __name__ == "__main__":

@@ -250,6 +250,7 @@ __global__ void __launch_bounds__(256) cross_entropy_fwd_kernel(int V, const flo
         if (threadIdx.x == 0) { row_loss[r] = 0.f; lse_out[r] = 0.f; }
         return;
     }
+    if (tgt >= V) __trap();                          // nn.CrossEntropyLoss raises on a class index >= V; never read outside the row
     float m = -INFINITY, s = 0.f;
     // scalar head up to the first 16-byte boundary of the row (rows of V = 9490 floats start 8-byte aligned on odd r),
     // 128-bit body with four loads in flight per thread, scalar tail
@@ -302,6 +303,7 @@ __global__ void __launch_bounds__(256) cross_entropy_bwd_kernel(int V, const flo
     const long long tgt = targets[r];
     float* dx = d_logits ? d_logits + r * V : nullptr;
     __nv_bfloat16* d16r = d16 ? d16 + r * ld16 : nullptr;
+    if (tgt >= V) __trap();
     if (d16r) for (int v = V + threadIdx.x; v < ld16; v += blockDim.x) d16r[v] = __float2bfloat16_rn(0.f);
     if (tgt < 0) {                                   // ignored row: zeros (the bf16 row is 16-byte aligned, ld16 % 8 == 0)
         if (dx) for (int v = threadIdx.x; v < V; v += blockDim.x) dx[v] = 0.f;

@@ -78,6 +78,30 @@ def beam_search_batched(decoder, features, beam_size, start_id, end_id, max_step
     return out
 
 
+def beam_search_sharded(decoder, features_local, beam_size, start_id, end_id, max_steps=50, group=None, dst=0,
+                        precision="fp32x3"):
+    """BASELINE.json configs[4] / SURVEY.md 8e row 3: images are independent units, so every rank decodes its own shard
+    with ``beam_search_batched`` (no collective during the decode) and ONE final gather brings caption lengths, token ids
+    and scores to rank ``dst``.  All ranks must hold the same number of images.  Works unchanged in a single process.
+    -> on ``dst``: dict(len (world*n,), seq (world*n, max_steps+2), score (world*n,)) in rank order (CUDA tensors);
+       elsewhere: None."""
+    import torch.distributed as dist
+    res = beam_search_batched(decoder, features_local, beam_size, start_id, end_id, max_steps=max_steps,
+                              want_alphas=False, want_trace=False, precision=precision)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return {k: res[k] for k in ("len", "seq", "score")}
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n, S2 = res["seq"].shape
+    # one packed int32 message per rank: [len | score bits | seq]
+    packed = torch.cat([res["len"].view(n, 1), res["score"].view(torch.int32).view(n, 1), res["seq"]], dim=1).contiguous()
+    parts = [torch.empty_like(packed) for _ in range(world)] if rank == dst else None
+    dist.gather(packed, parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    allp = torch.cat(parts, dim=0)
+    return {"len": allp[:, 0].contiguous(), "score": allp[:, 1].contiguous().view(torch.float32), "seq": allp[:, 2:].contiguous()}
+
+
 def attention_caption_image_beam_search(device, args, img, encoder, decoder, vocab):
     """Reads an image and captions it with beam search (gen_captions.py:16-131).
 

@@ -21,41 +21,52 @@ import torch
 from . import ops
 
 
-# bf16 side-channel between the fused loss and the bf16 tier of the decoder backward: the loss backward already streams
-# every logit once, so it also emits the bf16 copy of d(loss)/d(logits) that the vocabulary-layer backward contractions
-# consume — the decoder backward then skips its own fp32 -> bf16 pass over the (B*T, V) gradient.  Keyed by the device
-# address of the fp32 gradient, consumed once, and only honoured if that tensor has not been modified in place since
-# (autograd accumulating a second gradient into it bumps its version counter).
-_BF16_SIDECAR = {}
+# bf16 hand-off between the fused loss and the bf16 tier of the decoder backward: the loss backward already streams every
+# logit once, so it also emits the bf16 copy of d(loss)/d(logits) that the vocabulary-layer backward contractions consume —
+# the decoder backward then skips its own fp32 -> bf16 pass over the (B*T, V) gradient.  The copy travels in a small box
+# that belongs to ONE decoder forward: the decoder's autograd node and the `predictions` tensor it returned both hold it
+# (`predictions._icd_box`), the loss stores it in its own node, so two decoder / loss pairs in one graph (micro-batches,
+# two models) never see each other's gradient, nothing is process-global, and the box dies with the graph.
+class GradBox:
+    """Per-decoder-forward mailbox: filled by _FusedCE.backward, emptied by the decoder backward."""
+    __slots__ = ("d16", "d32", "version", "hollow", "hollow_expected")
 
+    def __init__(self):
+        self.d16 = self.d32 = None
+        self.version = -1
+        self.hollow = False              # the fp32 gradient that was sent is hollow (bf16_grad_only=True)
+        self.hollow_expected = False     # a bf16_grad_only loss was built on this forward: fp32 d_predictions is NOT to be trusted
 
-def take_bf16_sidecar(grad):
-    """-> bf16 tensor (R, ld16) matching the fp32 gradient ``grad`` if the fused loss produced one, else None.
-    Raises if ``grad`` is a HOLLOW fp32 gradient (``bf16_grad_only=True``) whose bf16 copy can no longer be trusted."""
-    ent = _BF16_SIDECAR.pop(grad.data_ptr(), None)
-    orphan_hollow = any(e[3] and e[1].numel() == grad.numel() for e in _BF16_SIDECAR.values())
-    _BF16_SIDECAR.clear()
-    if ent is None:
-        if orphan_hollow:            # autograd summed the hollow gradient with another one into a new tensor
-            raise RuntimeError("attention_caption_loss(bf16_grad_only=True): the logit gradient reaching the decoder is "
-                               "not the one the loss produced (predictions feed something else too); use "
-                               "bf16_grad_only=False")
+    def put(self, d16, d32, hollow):
+        self.d16, self.d32, self.version, self.hollow = d16, d32, d32._version, hollow
+
+    def take(self, grad):
+        """-> the bf16 gradient matching the fp32 tensor ``grad`` that reached the decoder backward, or None when the
+        loss produced none.  Raises when only a HOLLOW fp32 gradient exists and it is not exactly what arrived (autograd
+        summed it with another gradient, or something modified it in place) — never reads undefined memory."""
+        d16, d32, version, hollow = self.d16, self.d32, self.version, self.hollow
+        self.d16 = self.d32 = None
+        ok = (d16 is not None and d32 is not None and d32.data_ptr() == grad.data_ptr() and d32.numel() == grad.numel()
+              and d32._version == version and grad._version == version)
+        if ok:
+            return d16
+        if hollow or self.hollow_expected:
+            raise RuntimeError("attention_caption_loss(bf16_grad_only=True): the logit gradient reaching the decoder is not "
+                               "the one the loss produced (predictions feed something else too, or the gradient was "
+                               "modified on its way); use bf16_grad_only=False")
         return None
-    d16, d32, version, hollow = ent
-    if d32.numel() != grad.numel() or d32._version != version or grad._version != version:
-        if hollow:
-            raise RuntimeError("attention_caption_loss(bf16_grad_only=True): the logit gradient was modified before it "
-                               "reached the decoder (predictions feed something else too); use bf16_grad_only=False")
-        return None
-    return d16
 
 
 class _FusedCE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits2d, targets, n_valid, want_bf16, bf16_only=False):
+    def forward(ctx, logits2d, targets, n_valid, want_bf16, bf16_only=False, box=None):
         row_loss, lse = ops.cross_entropy_fwd(logits2d, targets)
         ctx.save_for_backward(logits2d, targets, lse)
-        ctx.n_valid, ctx.want_bf16, ctx.bf16_only = n_valid, want_bf16, bool(bf16_only and want_bf16)
+        ctx.n_valid, ctx.want_bf16 = n_valid, bool(want_bf16 and box is not None)
+        ctx.bf16_only = bool(bf16_only and ctx.want_bf16)
+        ctx.box = box
+        if ctx.bf16_only:
+            box.hollow_expected = True
         return row_loss.sum() / n_valid
 
     @staticmethod
@@ -64,10 +75,9 @@ class _FusedCE(torch.autograd.Function):
         g = g.reshape(1).float().contiguous()
         d_logits, d16 = ops.cross_entropy_bwd(logits2d, targets, lse, 1.0 / ctx.n_valid, upstream=g,
                                               want_bf16=ctx.want_bf16, want_fp32=not ctx.bf16_only)
-        _BF16_SIDECAR.clear()
         if d16 is not None:
-            _BF16_SIDECAR[d_logits.data_ptr()] = (d16, d_logits, d_logits._version, ctx.bf16_only)
-        return d_logits, None, None, None, None
+            ctx.box.put(d16, d_logits, ctx.bf16_only)
+        return d_logits, None, None, None, None, None
 
 
 class _AlphaReg(torch.autograd.Function):
@@ -107,20 +117,59 @@ def packed_targets(encoded_captions, decode_lengths, T, row_valid=None):
     return torch.where(active, tgt, torch.full_like(tgt, -1)), int(sum(decode_lengths))
 
 
-def attention_caption_loss(predictions, encoded_captions, decode_lengths, alphas, alpha_c=1.0, bf16_grad_only=False):
+def _dp_token_scale(n_valid, device, group=None):
+    """n_local * world / n_global as a DEVICE scalar (one tiny all-reduce, no host sync): with it the mean over ranks of the
+    per-rank mean losses is the mean over ALL packed tokens, i.e. the reference's single-process (N*B)-caption step, also
+    when the ranks hold different numbers of packed tokens (ragged COCO batches).  Exactly 1 for equal-length batches."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    cnt = torch.tensor([float(n_valid)], device=device, dtype=torch.float64)
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+    return (float(n_valid) * dist.get_world_size(group) / cnt).float().reshape(())
+
+
+def attention_caption_loss(predictions, encoded_captions, decode_lengths, alphas, alpha_c=1.0, bf16_grad_only=False,
+                           dp_token_weighting=False, dp_group=None):
     """bf16_grad_only (bf16 tier only): the loss backward writes ONLY the bf16 copy of d(loss)/d(logits) that the decoder
     backward consumes and leaves the 466 MB fp32 gradient tensor hollow.  Valid when ``predictions`` feeds nothing but this
     loss in the autograd graph — the reference train loop (models/attention.py:401-414; its top-5 accuracy is computed
-    without a graph).  If the gradient is modified on its way to the decoder the backward raises instead of reading it."""
+    without a graph).  If the gradient is modified on its way to the decoder the backward raises instead of reading it.
+    dp_token_weighting (data parallel, ragged batches): weight this rank's cross-entropy by n_local * world / n_global so
+    that the 1/world-averaged gradient equals the single-process big-batch gradient (see _dp_token_scale)."""
     B, T, V = predictions.shape
     tgt, n_valid = packed_targets(encoded_captions, decode_lengths, T, getattr(predictions, "_icd_row_valid", None))
-    want_bf16 = bool(getattr(predictions, "_icd_bf16_tier", False))
-    ce = _FusedCE.apply(predictions.reshape(B * T, V), tgt.reshape(-1).contiguous(), n_valid, want_bf16, bf16_grad_only)
+    box = getattr(predictions, "_icd_box", None)
+    want_bf16 = bool(getattr(predictions, "_icd_bf16_tier", False)) and box is not None
+    ce = _FusedCE.apply(predictions.reshape(B * T, V), tgt.reshape(-1).contiguous(), n_valid, want_bf16, bf16_grad_only, box)
+    if dp_token_weighting:
+        scale = _dp_token_scale(n_valid, predictions.device, dp_group)
+        if scale is not None:
+            ce = ce * scale
     return ce + alpha_regulariser(alphas, alpha_c)
 
 
+class _MaskedMeanCE(torch.autograd.Function):
+    """mean over the rows with target >= 0 of the row cross-entropy, the count staying ON THE DEVICE (no host sync):
+    forward = sum(row_loss) / count; backward scales the upstream gradient by 1 / count before the streaming kernel."""
+
+    @staticmethod
+    def forward(ctx, logits2d, targets):
+        row_loss, lse = ops.cross_entropy_fwd(logits2d, targets)
+        inv = 1.0 / (targets >= 0).sum().clamp_min(1).float()
+        ctx.save_for_backward(logits2d, targets, lse, inv)
+        return row_loss.sum() * inv
+
+    @staticmethod
+    def backward(ctx, g):
+        logits2d, targets, lse, inv = ctx.saved_tensors
+        up = (g.reshape(1).float() * inv).contiguous()
+        return ops.cross_entropy_bwd(logits2d, targets, lse, 1.0, upstream=up)[0], None
+
+
 def baseline_caption_loss(outputs, captions, pad_id=0):
+    """CrossEntropyLoss(ignore_index=<pad>)(scores.reshape(-1, V), captions.reshape(-1)) — models/baseline.py:194-195,
+    224-225 — as the two streaming kernels; the number of non-pad targets never leaves the device."""
     B, L, V = outputs.shape
     tgt = torch.where(captions == pad_id, torch.full_like(captions, -1), captions).reshape(-1).contiguous()
-    n_valid = int((tgt >= 0).sum().item())
-    return _FusedCE.apply(outputs.reshape(B * L, V), tgt, max(n_valid, 1), False)
+    return _MaskedMeanCE.apply(outputs.reshape(B * L, V), tgt)

@@ -227,6 +227,7 @@ class _AttentionDecoderFn(torch.autograd.Function):
         emb_is_f64 = emb_w.dtype == torch.float64
         assert emb_w.dtype in (torch.float32, torch.float64)
         weights = [w.contiguous() for w in weights]
+        emb_c = emb_w.contiguous()           # kept in ctx.keep: a non-contiguous table would otherwise leave a dangling pointer
         f32 = dict(device=dev, dtype=torch.float32)
         bufs = dict(
             predictions=torch.empty(B, T, V, **f32), alphas=torch.empty(B, T, P, **f32),
@@ -241,7 +242,7 @@ class _AttentionDecoderFn(torch.autograd.Function):
         fill(d, B=B, T=T, L=L, P=P, C=C, A=A, D=D, E=E, V=V, precision=ops.precision_id(precision),
              emb_is_f64=int(emb_is_f64), enc=enc, enc16=enc16, captions=captions, drop_mask=mask,
              drop_scale=float(drop_scale),
-             emb_w=emb_w.contiguous(), **dict(zip(_W_NAMES, weights)), **bufs)
+             emb_w=emb_c, **dict(zip(_W_NAMES, weights)), **bufs)
         for t in range(T):
             d.bt_host[t] = bt[t]
         need = int(lib().icd_attention_decoder_ws_bytes(ctypes.byref(d)))
@@ -254,11 +255,13 @@ class _AttentionDecoderFn(torch.autograd.Function):
         # leak ~3 GB of activations per step until the cyclic GC runs) — keep a detached alias of alphas instead
         bufs["alphas_saved"] = alphas.detach()
         ctx.desc = d
-        ctx.keep = (enc if enc is not None else enc16, captions, emb_w, weights, mask, bufs)   # keeps buffers alive
+        ctx.keep = (enc if enc is not None else enc16, captions, emb_c, weights, mask, bufs)   # keeps buffers alive
         ctx.dims = (B, T, L, P, C, A, D, E, V, NZ, emb_is_f64)
         ctx.row_valid = bufs["row_valid"]
         predictions._icd_row_valid = bufs["row_valid"]               # (B*T) uint8, reused by the fused loss
         predictions._icd_bf16_tier = precision == "bf16"             # the fused loss then also emits a bf16 gradient
+        from ..losses import GradBox
+        ctx.box = predictions._icd_box = GradBox()                   # per-forward mailbox for that bf16 gradient
         ctx.precision = precision
         return predictions, alphas
 
@@ -276,8 +279,7 @@ class _AttentionDecoderFn(torch.autograd.Function):
         d_pred = d_pred.contiguous().float()
         d_pred16 = None
         if ctx.precision == "bf16":
-            from ..losses import take_bf16_sidecar
-            d_pred16 = take_bf16_sidecar(d_pred)
+            d_pred16 = ctx.box.take(d_pred)          # raises if only a hollow fp32 gradient exists and it is not this tensor
         if d_alphas is not None:
             d_alphas = d_alphas.contiguous().float()
         want_emb = ctx.needs_input_grad[2]

@@ -68,6 +68,7 @@ class _BaselineDecoderFn(torch.autograd.Function):
         assert img.shape == (B, E)
         emb_is_f64 = emb_w.dtype == torch.float64
         ws = [w.contiguous() for w in (w_ih, w_hh, b_ih, b_hh, lin_w, lin_b)]
+        emb_c = emb_w.contiguous()           # kept in ctx.keep (a non-contiguous table must not leave a dangling pointer)
         f32 = dict(device=dev, dtype=torch.float32)
         bufs = dict(outputs=torch.empty(B, L, V, **f32), x=torch.empty(L, B, E, **f32),
                     xg=torch.empty(L, B, 4 * H, **f32), gates_act=torch.empty(L, B, 4 * H, **f32),
@@ -75,7 +76,7 @@ class _BaselineDecoderFn(torch.autograd.Function):
                     hout=torch.empty(B, L, H, **f32), gates_pre=torch.empty(B, 4 * H, **f32))
         d = _lib.BaseDesc()
         fill(d, B=B, L=L, E=E, H=H, V=V, precision=ops.precision_id(precision), emb_is_f64=int(emb_is_f64),
-             img_features=img, captions=captions, emb_w=emb_w.contiguous(), w_ih=ws[0], w_hh=ws[1], b_ih=ws[2],
+             img_features=img, captions=captions, emb_w=emb_c, w_ih=ws[0], w_hh=ws[1], b_ih=ws[2],
              b_hh=ws[3], lin_w=ws[4], lin_b=ws[5], **bufs)
         need = int(lib().icd_baseline_decoder_ws_bytes(ctypes.byref(d)))
         tc_ws = torch.empty(need, device=dev, dtype=torch.uint8) if need else None
@@ -84,7 +85,7 @@ class _BaselineDecoderFn(torch.autograd.Function):
         check(lib().icd_baseline_decoder_fwd(ctypes.byref(d), stream_ptr()), "icd_baseline_decoder_fwd")
         outputs = bufs.pop("outputs")          # not kept in ctx: it carries this node as grad_fn (reference cycle)
         ctx.desc = d
-        ctx.keep = (img, captions, emb_w, ws, bufs)
+        ctx.keep = (img, captions, emb_c, ws, bufs)
         ctx.dims = (B, L, E, H, V)
         return outputs
 

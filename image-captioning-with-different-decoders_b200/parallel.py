@@ -49,8 +49,10 @@ class FlatParamBuffer:
 
 
 def all_reduce_gradients(buf, group=None):
-    """Sum the flat gradient (and any float64 gradients) over the ranks.  No-op when not initialised / 1 rank."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    """Sum the flat gradient (and any float64 gradients) over the ranks.  No-op when not initialised / 1 rank, or when
+    ``group is False`` (a deliberately local optimiser inside a distributed job, e.g. the single-process reference step of
+    tests/test_gpu_dist.py)."""
+    if group is False or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return 1
     dist.all_reduce(buf.flat_grad, op=dist.ReduceOp.SUM, group=group)
     for p in buf.other:
@@ -65,6 +67,7 @@ class DataParallelClipAdam:
     scale(1/world) + clamp(+-c) + Adam kernel over the flat buffers."""
 
     def __init__(self, module, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, grad_clip=5.0, group=None):
+        self._module_params = list(module.parameters())
         self.buf = FlatParamBuffer(module)
         self.lr, self.betas, self.eps, self.grad_clip, self.group = lr, betas, eps, grad_clip, group
         self.exp_avg = torch.zeros_like(self.buf.flat)
@@ -75,6 +78,52 @@ class DataParallelClipAdam:
     def zero_grad(self):
         for p in self.buf.params + self.buf.other:
             p.grad = None
+
+    # -- torch.optim.Adam-shaped state (checkpoints the reference can resume from, checkpoint.py:51-59) --------------
+    def as_torch_adam(self, module=None):
+        """A real ``torch.optim.Adam`` with this optimiser's hyper-parameters, step count and moments.  ``module``: a copy
+        of the optimised module (same parameter order) whose parameters the new optimiser should own; default: the
+        module's own parameters."""
+        params = self.buf.params + self.buf.other
+        if module is not None:
+            mine = {id(p): i for i, p in enumerate(self._module_params)}
+            theirs = [p for p in module.parameters()]
+            params = [theirs[mine[id(p)]] for p in params]
+        opt = torch.optim.Adam(params, lr=self.lr, betas=self.betas, eps=self.eps)
+        if self.step_count > 0:
+            off = 0
+            for p, q in zip(self.buf.params, params):
+                k = p.numel()
+                opt.state[q] = {"step": torch.tensor(float(self.step_count)),
+                                "exp_avg": self.exp_avg[off:off + k].view_as(p).clone(),
+                                "exp_avg_sq": self.exp_avg_sq[off:off + k].view_as(p).clone()}
+                off += k
+            if self._other_opt is not None:
+                for p, q in zip(self.buf.other, params[len(self.buf.params):]):
+                    st = self._other_opt.state.get(p)
+                    if st:
+                        opt.state[q] = {k_: (v.clone() if torch.is_tensor(v) else v) for k_, v in st.items()}
+        return opt
+
+    def load_torch_adam(self, opt):
+        """Adopt step count and moments of a ``torch.optim.Adam`` over the same parameters in the same order (e.g. the
+        ``decoder_optimizer`` of a reference checkpoint)."""
+        theirs = [p for g in opt.param_groups for p in g["params"]]
+        assert len(theirs) == len(self.buf.params) + len(self.buf.other), "optimiser covers a different parameter set"
+        off, steps = 0, []
+        for p, q in zip(self.buf.params, theirs):
+            k = p.numel()
+            st = opt.state.get(q)
+            if st:
+                self.exp_avg[off:off + k].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.append(int(st["step"]))
+            off += k
+        self.step_count = max(steps) if steps else 0
+        if opt.param_groups:
+            self.lr = opt.param_groups[0]["lr"]
+            self.betas = tuple(opt.param_groups[0]["betas"])
+            self.eps = opt.param_groups[0]["eps"]
 
     @torch.no_grad()
     def step(self):

@@ -20,8 +20,8 @@ import types
 REFERENCE_ROOT = os.environ.get("ICD_REFERENCE_ROOT", "/root/reference")
 
 
-def reference_available():
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "attention.py"))
+def reference_available(root=None):
+    return os.path.isfile(os.path.join(root or REFERENCE_ROOT, "models", "attention.py"))
 
 
 def _stub(name, **attrs):
@@ -38,16 +38,20 @@ class _Namespace(types.SimpleNamespace):
     pass
 
 
-def load_reference():
+def load_reference(root=None):
     """Return a namespace with the reference's hot-path classes/functions.
+
+    ``root``: where the unmodified reference lives — ``/root/reference`` in the build container (default), or the verbatim
+    install under ``baseline/_ref`` (baseline/install_ref.py) that travels to the GPU box for ``bench.py --impl reference``.
 
     The reference uses top-level module names (``models``, ``vocabulary`` ...) that
     would shadow/be shadowed by other packages, so its modules are imported with
     ``/root/reference`` at the front of ``sys.path`` and then *renamed* in
     ``sys.modules`` under a ``_icd_ref.`` prefix to keep the import state clean.
     """
-    if not reference_available():
-        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    root = root or REFERENCE_ROOT
+    if not reference_available(root):
+        raise RuntimeError("reference tree not present at %s" % root)
     if "_icd_ref" in sys.modules:
         return sys.modules["_icd_ref"].ns
 
@@ -63,7 +67,7 @@ def load_reference():
                 "embed", "dataset", "metric", "train_utils", "checkpoint", "gen_captions",
                 "pathconf", "eval_func", "eval_func.bleu", "eval_func.bleu.bleu"]
     saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k in shadowed or k.startswith("eval_func")}
-    sys.path.insert(0, REFERENCE_ROOT)
+    sys.path.insert(0, root)
     cwd = os.getcwd()
     try:
         import models.attention as ref_att      # noqa
@@ -73,7 +77,7 @@ def load_reference():
         import train_utils as ref_tu            # noqa
     finally:
         os.chdir(cwd)
-        sys.path.remove(REFERENCE_ROOT)
+        sys.path.remove(root)
     ns = _Namespace(
         attention=ref_att, baseline=ref_base, gen_captions=ref_gen, vocabulary=ref_vocab,
         train_utils=ref_tu,

@@ -166,3 +166,77 @@ def assert_digest_close(name, t, dg, tol, atol=0.0):
     err = float((t64[idx] - s).abs().max())
     assert err <= 20 * tol * rms + atol + tol * float(s.abs().max()), \
         "%s: sampled entries differ by %.3e (rms %.3e)" % (name, err, rms)
+
+
+# --------------------------------------------------------------------------------------------
+# fp64 oracle over a LARGE batch, evaluated in row chunks (rows are independent; only the parameters are shared), so
+# the timed configuration (B = 512, V = 9490, full dimensions) can be checked tensor by tensor in about a minute.
+# --------------------------------------------------------------------------------------------
+def oracle_fp64_chunked(sd, enc, caps, lens, keep_mask=None, p=0.0, frozen=(), chunk=64, cuda_preds=None,
+                        cuda_alphas=None, alpha_c=1.0):
+    """Full-batch loss and parameter gradients of the reference train step (models/attention.py:396-420) from the fp64
+    oracle, accumulated over row chunks:  loss = sum_rows CE / n_packed + sum_{b,p} (alpha_c - sum_t alpha)^2 / (B*P).
+    Lengths must be equal or sorted descending (then "first batch_size_t rows" == "rows with l > t" in every chunk).
+    keep_mask: (T, B, D) uint8 dropout keep-mask (train mode) or None.
+    cuda_preds / cuda_alphas: optional CPU fp32 copies of the CUDA outputs (or dicts name -> tensor for several candidates);
+    their squared errors against the oracle are accumulated chunk by chunk.  -> dict(loss, grads{name: fp64}, err{predictions, alphas} norm-wise relative)"""
+    from oracle import decoders as O
+    import torch.nn.functional as F
+    B = enc.shape[0]
+    dl = [l - 1 for l in lens]
+    assert all(dl[i] >= dl[i + 1] for i in range(B - 1)), "chunked oracle needs equal or descending lengths"
+    T = max(dl)
+    n_packed = sum(dl)
+    P = enc.reshape(B, -1, enc.shape[-1]).shape[1]
+    w64 = {k: v.detach().cpu().double().clone().requires_grad_(k not in frozen) for k, v in sd.items()}
+    loss_total = 0.0
+    outputs = {}                      # candidate name -> (predictions, alphas) CPU tensors to be compared with the oracle
+    if isinstance(cuda_preds, dict):
+        outputs = {k: (cuda_preds[k], cuda_alphas[k]) for k in cuda_preds}
+    elif cuda_preds is not None:
+        outputs = {"": (cuda_preds, cuda_alphas)}
+    acc = {k: {"predictions": [0.0, 0.0], "alphas": [0.0, 0.0]} for k in outputs}
+    margins, ids = [], []
+    for r0 in range(0, B, chunk):
+        r1 = min(B, r0 + chunk)
+        if dl[r0] == 0:
+            break
+        ls = lens[r0:r1]
+        masks = None
+        if keep_mask is not None:
+            masks = [keep_mask[t, r0:r0 + sum(1 for l in dl[r0:r1] if l > t)].double() for t in range(max(dl[r0:r1]))]
+        pr, _, dls, al = O.attention_decoder_forward(w64, enc[r0:r1].double(), caps[r0:r1], ls, dropout_p=p,
+                                                     dropout_masks=masks, hoist=True)
+        Tc = max(dls)
+        active = torch.tensor([[t < d for t in range(Tc)] for d in dls])
+        tgt = caps[r0:r1, 1:Tc + 1]
+        ce = F.cross_entropy(pr[active], tgt[active], reduction="sum") / n_packed
+        reg = ((alpha_c - al.sum(dim=1)) ** 2).sum() / (B * P)
+        (ce + reg).backward()
+        loss_total += float(ce) + float(reg)
+        with torch.no_grad():
+            for cand, (c_pr, c_al) in outputs.items():
+                for name, ref, got in (("predictions", pr, c_pr), ("alphas", al, c_al)):
+                    gsl = got[r0:r1, :Tc].double()
+                    acc[cand][name][0] += float(((gsl - ref) ** 2).sum())
+                    acc[cand][name][1] += float((ref ** 2).sum())
+            top2 = pr.detach().topk(2, dim=2)
+            mg = torch.zeros(r1 - r0, T)
+            ii = torch.zeros(r1 - r0, T, dtype=torch.int64)
+            mg[:, :Tc] = (top2.values[..., 0] - top2.values[..., 1]).float()
+            ii[:, :Tc] = top2.indices[..., 0]
+            margins.append(mg)
+            ids.append(ii)
+    # rows of all-padding chunks contribute alpha_c^2 each to the regulariser (alphas stay 0)
+    done_rows = min(B, ((max(i for i in range(B) if dl[i] > 0) // chunk) + 1) * chunk)
+    loss_total += (B - done_rows) * P * alpha_c ** 2 / (B * P)
+    err = {c: {k: ((v[0] ** 0.5) / (v[1] ** 0.5) if v[1] > 0 else None) for k, v in a.items()} for c, a in acc.items()}
+    if list(err) == [""]:
+        err = err[""]
+    return dict(loss=loss_total, grads={k: v.grad for k, v in w64.items() if v.grad is not None}, err=err,
+                margin=torch.cat(margins, 0), ids=torch.cat(ids, 0), decode_lengths=dl)
+
+
+def seeded_keep_mask(T, B, D, p, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(T, B, D, generator=g) >= p).to(torch.uint8)

@@ -189,3 +189,26 @@ def test_contraction_plan_host_logic():
     assert f(100352, 512, 2048) == 0 and f(12288, 9490, 512) == 0 and f(512, 4608, 512) == 0
     assert f(9490, 512, 12288) == 32 * 18 * 512
     assert f(9472, 512, 12288) == 0
+
+
+def test_reference_install_is_a_verbatim_copy():
+    """baseline/_ref (bench.py's reference arm) holds the UNMODIFIED reference: every installed file hashes like its source
+    (when the source tree is present) and like the manifest written at install time."""
+    import hashlib
+    import json
+    import os
+    ref = os.path.join(H.ROOT, "baseline", "_ref")
+    man_path = os.path.join(ref, "MANIFEST.json")
+    if not os.path.exists(man_path):
+        pytest.skip("baseline/_ref not installed here")
+    man = json.load(open(man_path))
+    assert "models/attention.py" in man["files"] and "gen_captions.py" in man["files"]
+    for rel, sha in man["files"].items():
+        assert hashlib.sha256(open(os.path.join(ref, rel), "rb").read()).hexdigest() == sha, rel
+        src = os.path.join("/root/reference", rel)
+        if os.path.exists(src):
+            assert hashlib.sha256(open(src, "rb").read()).hexdigest() == sha, "installed copy differs from the reference: " + rel
+    # nothing of it is tracked by git
+    import subprocess
+    out = subprocess.run(["git", "ls-files", "baseline/_ref"], cwd=H.ROOT, capture_output=True, text=True).stdout.strip()
+    assert out == "", "baseline/_ref must stay out of the repository history"

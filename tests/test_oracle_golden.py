@@ -197,6 +197,81 @@ def test_reference_whole_module_checkpoint_loads_as_drop_in(tmp_path):
     assert isinstance(dec_opt, torch.optim.Adam)
 
 
+@pytest.mark.skipif(not reference_import.reference_available(), reason="needs the reference tree (build container only)")
+def test_saved_checkpoint_loads_in_the_unmodified_reference(tmp_path, monkeypatch):
+    """The other direction: a checkpoint written by icd_b200.checkpoint.save_checkpoint — decoder whose parameters
+    live in a FlatParamBuffer, fused DataParallelClipAdam optimiser with two steps of state — is read by a plain
+    ``torch.load`` with only the REFERENCE's modules importable, comes back as the reference's own classes, computes the
+    reference forward, and its ``decoder_optimizer`` is a torch.optim.Adam that steps."""
+    import sys
+    import icd_b200.models.attention as my_att
+    from icd_b200 import checkpoint as ckpt
+    from icd_b200.parallel import DataParallelClipAdam
+    from icd_b200.vocabulary import synthetic_vocab
+    ns = reference_import.load_reference()
+    case = H.ATT_CASES["att_small_ragged"]
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams, synthetic_vocab(case["V"]))
+    opt = DataParallelClipAdam(dec, lr=1e-3, grad_clip=5.0)          # re-points the parameters into one flat buffer
+    g = torch.Generator().manual_seed(1)
+    opt.step_count = 2                                               # two steps of (synthetic) optimiser state
+    opt.exp_avg.copy_(torch.randn(opt.exp_avg.shape, generator=g) * 1e-3)
+    opt.exp_avg_sq.copy_(torch.rand(opt.exp_avg_sq.shape, generator=g) * 1e-6)
+    monkeypatch.setattr(ckpt, "CHECKPOINTS_DIR", str(tmp_path))
+
+    class Args:
+        model_name = "basic_att"
+        checkpoint = "basic_att_3.pth.tar"
+    ckpt.save_checkpoint(Args, 3, None, dec, None, opt, {"loss": [2.5]}, verbose=False)
+    assert my_att.AttentionDecoder.__module__ == my_att.__name__ and my_att.AttentionDecoder.__qualname__ == "AttentionDecoder"
+    path = tmp_path / "basic_att_3.pth.tar"
+    names = ["models", "models.attention", "models.baseline", "vocabulary"]
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        for k in names:
+            sys.modules[k] = sys.modules["_icd_ref." + k]
+        chk = torch.load(str(path), map_location="cpu", weights_only=False)     # the reference's call (checkpoint.py:18)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    rdec = chk["decoder"]
+    assert type(rdec) is ns.AttentionDecoder and type(rdec.attention) is ns.SoftAttention
+    assert type(rdec.vocab) is ns.Vocabulary and len(rdec.vocab) == case["V"]
+    assert chk["epoch"] == 3 and chk["metrics"] == {"loss": [2.5]}
+    sd, rsd = dec.state_dict(), rdec.state_dict()
+    assert list(sd) == list(rsd) and all(torch.equal(sd[k], rsd[k]) for k in sd)
+    storages = {p_.untyped_storage().data_ptr() for p_ in rdec.parameters()}
+    assert len(storages) == len(list(rdec.parameters())), "saved parameters must own their storage (not views of a flat buffer)"
+    enc, caps, lens = H.att_inputs(case)
+    rdec.eval()
+    with torch.no_grad():
+        preds, _, dl, alphas = rdec(enc, caps, lens)                             # the reference's own forward
+        o_preds, _, o_dl, o_alphas = O.attention_decoder_forward(O.cast_weights(sd, torch.float32), enc, caps, lens)
+    assert torch.equal(preds, o_preds) and torch.equal(alphas, o_alphas) and dl == o_dl
+    ropt = chk["decoder_optimizer"]
+    assert type(ropt) is torch.optim.Adam and ropt.param_groups[0]["lr"] == 1e-3
+    rparams = [p_ for p_ in rdec.parameters() if p_.requires_grad]
+    assert [id(p_) for p_ in ropt.param_groups[0]["params"]] == [id(p_) for p_ in rparams]
+    off = 0
+    for p_ in rparams:
+        st = ropt.state[p_]
+        assert int(st["step"]) == 2
+        assert torch.equal(st["exp_avg"].reshape(-1), opt.exp_avg[off:off + p_.numel()])
+        off += p_.numel()
+    rdec.train()
+    preds, cs, dl, alphas = rdec(enc, caps, lens)
+    O.attention_loss(preds, cs, dl, alphas).backward()
+    ropt.step()                                                                  # resumes like models/attention.py:359-364
+    # and back: this package reads its own file as drop-in modules; the Adam state moves into the fused optimiser
+    chk2 = ckpt.load_checkpoint(torch.device("cpu"), Args, verbose=False)
+    assert type(chk2["decoder"]) is my_att.AttentionDecoder
+    opt2 = DataParallelClipAdam(chk2["decoder"], lr=1.0)
+    opt2.load_torch_adam(chk2["decoder_optimizer"])
+    assert opt2.step_count == 2 and opt2.lr == 1e-3 and torch.equal(opt2.exp_avg, opt.exp_avg)
+
+
 def test_oracle_loss_glue_equals_pack_padded_sequence_expression():
     """The oracle restates models/attention.py:401-414 without pack_padded_sequence (explicit time-major gather of the
     first batch_size_t rows); check it against the reference's literal expression on random ragged, sorted lengths,
