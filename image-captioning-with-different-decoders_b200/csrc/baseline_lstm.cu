@@ -36,6 +36,7 @@ struct Arena16 {
 struct BaseBufs {
     void *Wih, *Whh, *Wlin, *x, *h, *hout, *dY, *dg;
     float *splitk, *colsum_ws; int64_t splitk_floats, ldE, ldV;
+    unsigned int* bar;                                   // grid-barrier counter of the persistent recurrent kernels
 };
 void carve_base(const icd_base_desc_t* d, Arena16& a, BaseBufs& b) {
     const int64_t B = d->B, L = d->L, E = d->E, H = d->H, V = d->V, LB = L * B;
@@ -51,6 +52,7 @@ void carve_base(const icd_base_desc_t* d, Arena16& a, BaseBufs& b) {
     b.splitk_floats = f;
     b.splitk = reinterpret_cast<float*>(a.take_bytes(f * 4));
     b.colsum_ws = reinterpret_cast<float*>(a.take_bytes(icd_colsum_bf16_ws_floats(LB, (int)V) * 4));
+    b.bar = reinterpret_cast<unsigned int*>(a.take_bytes(256));
 }
 int check_base16(const icd_base_desc_t* d, Arena16& a, BaseBufs& b) {
     ICD_CHECK_ARG(d->H % 8 == 0 && d->E % 4 == 0, "baseline_decoder(bf16): H must be a multiple of 8 and E of 4");
@@ -74,15 +76,21 @@ int baseline_fwd_bf16(const icd_base_desc_t* d, cudaStream_t s) {
     const int LB = L * B;
     ICD_CUDA(cudaMemcpyAsync(d->x, d->img_features, sizeof(float) * (size_t)B * E, cudaMemcpyDeviceToDevice, s));      // :101
     if (L > 1) ICD_TRY(icd_embed_gather(d->emb_w, d->emb_is_f64, d->captions, B, L, L - 1, E, V, d->x + (size_t)B * E, s));
+    // K8: the recurrence as ONE persistent kernel (W_hh slices resident in shared memory, grid barrier per step, gate math
+    // in the tcgen05 epilogue; lstm_persistent.cu) whenever the shape allows it, else the per-step launch chain below
+    const bool persistent = icd_lstm_seq_persistent_ok(B, L, H) != 0;
     BCVT(d->w_ih, E, 4 * H, E, u.Wih, u.ldE);
-    BCVT(d->w_hh, H, 4 * H, H, u.Whh, H);
+    if (!persistent) BCVT(d->w_hh, H, 4 * H, H, u.Whh, H);
     BCVT(d->lin_w, H, V, H, u.Wlin, H);
     BCVT(d->x, E, LB, E, u.x, u.ldE);
     BMM(u.x, u.ldE, 0, u.Wih, u.ldE, 0, d->xg, 4 * H, LB, 4 * H, E, d->b_ih, d->b_hh, nullptr, 0, nullptr, 0);
     ICD_CUDA(cudaMemsetAsync(d->h_all, 0, sizeof(float) * BH, s));                           // zero (h0, c0) (:106)
     ICD_CUDA(cudaMemsetAsync(d->c_all, 0, sizeof(float) * BH, s));
     ICD_CUDA(cudaMemsetAsync(u.h, 0, BH * 2, s));
-    for (int t = 0; t < L; ++t) {
+    if (persistent)
+        ICD_TRY(icd_lstm_seq_fwd_persistent(B, L, H, d->w_hh, d->xg, d->gates_act, d->c_all, d->h_all, d->hout, u.h, u.hout,
+                                            u.bar, s));
+    for (int t = 0; t < L && !persistent; ++t) {
         BMM(at16(u.h, (int64_t)t * BH), H, 0, u.Whh, H, 0, d->gates_pre, 4 * H, B, 4 * H, H, nullptr, nullptr,
             d->xg + (size_t)t * B * 4 * H, 4 * H, nullptr, 0);
         ICD_TRY(icd_lstm_pointwise_fwd(B, H, d->gates_pre, d->c_all + t * BH, d->gates_act + (size_t)t * B * 4 * H,
@@ -107,7 +115,11 @@ int baseline_bwd_bf16(const icd_base_desc_t* d, cudaStream_t s) {
     ICD_TRY(icd_colsum_bf16(u.dY, u.ldV, (int64_t)LB, V, nullptr, d->d_lin_b, u.colsum_ws, s));
     ICD_CUDA(cudaMemsetAsync(d->dh, 0, sizeof(float) * BH, s));
     ICD_CUDA(cudaMemsetAsync(d->dc, 0, sizeof(float) * BH, s));
-    for (int t = L - 1; t >= 0; --t) {
+    const bool persistent = icd_lstm_seq_persistent_ok(B, L, H) != 0;
+    if (persistent)
+        ICD_TRY(icd_lstm_seq_bwd_persistent(B, L, H, d->w_hh, d->d_hout, d->gates_act, d->c_all, d->dc, d->dg, u.dg, u.bar, s));
+    else BCVT(d->w_hh, H, 4 * H, H, u.Whh, H);       // (the forward of a persistent step did not stage it)
+    for (int t = L - 1; t >= 0 && !persistent; --t) {
         float* dgt = d->dg + (size_t)t * B * 4 * H;
         char* dg16 = at16(u.dg, (int64_t)t * B * 4 * H);
         ICD_TRY(icd_lstm_pointwise_bwd(B, H, d->dh, d->d_hout + (size_t)t * H, (int64_t)L * H, nullptr, 1.f, d->dc,

@@ -34,3 +34,12 @@ int64_t icd_gemm_tc_ws_bytes(int M, int N, int K);
 int icd_split3_bf16(const float* src, int64_t s_r, int rows, int cols, void* dst, int which, cudaStream_t s,
                     const int* m_live = nullptr);   // m_live: optional device-side row count (rows beyond it are skipped)
 int64_t icd_gemm_x3_ws_bytes(int M, int N, int K);
+
+// Persistent recurrent LSTM kernels (lstm_persistent.cu): the whole h -> gates -> (c, h) recurrence of nn.LSTM, resp. its
+// adjoint, as ONE cooperative launch.  icd_lstm_seq_persistent_ok: 1 if the shape is covered (else keep a launch chain).
+// h16: ((L+1)*B, H) bf16 with row block 0 zeroed (h_0), c_all / h_all row block 0 zeroed by the caller; bar: 4 bytes.
+int icd_lstm_seq_persistent_ok(int B, int L, int H);
+int icd_lstm_seq_fwd_persistent(int B, int L, int H, const float* w_hh, const float* xg, float* gates_act, float* c_all,
+                                float* h_all, float* hout, void* h16, void* hout16, unsigned int* bar, cudaStream_t s);
+int icd_lstm_seq_bwd_persistent(int B, int L, int H, const float* w_hh, const float* d_hout, const float* gates_act,
+                                const float* c_all, float* dc, float* dg, void* dg16, unsigned int* bar, cudaStream_t s);

