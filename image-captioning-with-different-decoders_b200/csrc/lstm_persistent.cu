@@ -6,7 +6,8 @@
 // Backward, step t:  dh_t = dg_{t+1} W_hh + d_hout_t ;  LSTM cell adjoint -> dg_t, dc_{t-1}
 //
 // Decomposition (weight-stationary — it pays here because the per-step activation is only B x H):
-//   * the grid is H/4 CTAs (forward: 4 hidden units = 16 gate columns each) or H/16 CTAs (backward: 16 hidden units each);
+//   * the grid is H/4 CTAs: forward, 4 hidden units = 16 gate columns each; backward, clusters of 4 CTAs own 16 hidden units and
+//     each rank contracts a quarter of the 4H-long K dimension (partial sums exchanged through distributed shared memory);
 //     a CTA keeps ITS slice of W_hh (16 rows of the B operand x K, bf16, 128B-swizzled K-major UMMA tiles) in shared memory
 //     for all L steps — converted from the fp32 weight once, by the kernel itself;
 //   * per step the whole CTA grid streams the same small A operand (h_{t-1} or dg_{t+1}, bf16, B x K) through a TMA ring and
@@ -59,6 +60,11 @@ __device__ __forceinline__ void tc_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[1
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ uint32_t lp_mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -91,8 +97,99 @@ __device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) 
     return pk;
 }
 
-// BWD = 0: forward recurrence, CTA c owns hidden units [4c, 4c+4)   (accumulator column n = gate * 4 + unit)
-// BWD = 1: backward recurrence, CTA c owns hidden units [16c, 16c+16) (accumulator column n = unit)
+struct Cell4 { float4 a, b, c, d, e, f, g, h; };          // the per-row operands of one 4-unit LSTM cell update
+
+// operands of the forward cell update of (row, units u0..u0+3) at step t: xg_i, xg_f, xg_g, xg_o, c_{t-1}
+__device__ __forceinline__ void cell_fwd_load(const LstmSeqArgs& p, int t, int row, int u0, Cell4& o) {
+    const size_t g_off = ((size_t)t * p.B + row) * 4 * p.H + u0;
+    o.a = *reinterpret_cast<const float4*>(p.xg + g_off);
+    o.b = *reinterpret_cast<const float4*>(p.xg + g_off + p.H);
+    o.c = *reinterpret_cast<const float4*>(p.xg + g_off + 2 * p.H);
+    o.d = *reinterpret_cast<const float4*>(p.xg + g_off + 3 * p.H);
+    o.e = *reinterpret_cast<const float4*>(p.c_all + ((size_t)t * p.B + row) * p.H + u0);
+}
+// hh: h_{t-1} W_hh^T for the 4 units, [gate][unit]
+__device__ __forceinline__ void cell_fwd_apply(const LstmSeqArgs& p, int t, int row, int u0, const Cell4& o, const float (&hh)[16]) {
+    const int H = p.H, B = p.B, L = p.L;
+    const size_t g_off = ((size_t)t * B + row) * 4 * H + u0;
+    const size_t s_off = (size_t)row * H + u0;
+    const size_t BH = (size_t)B * H;
+    const float xi_[4] = {o.a.x, o.a.y, o.a.z, o.a.w}, xf_[4] = {o.b.x, o.b.y, o.b.z, o.b.w};
+    const float xc_[4] = {o.c.x, o.c.y, o.c.z, o.c.w}, xo_[4] = {o.d.x, o.d.y, o.d.z, o.d.w};
+    const float cp_[4] = {o.e.x, o.e.y, o.e.z, o.e.w};
+    float gi[4], gf[4], gg[4], go[4], cn[4], hn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        gi[u] = sigmoidf_(hh[u] + xi_[u]);
+        gf[u] = sigmoidf_(hh[4 + u] + xf_[u]);
+        gg[u] = tanhf(hh[8 + u] + xc_[u]);
+        go[u] = sigmoidf_(hh[12 + u] + xo_[u]);
+        cn[u] = gf[u] * cp_[u] + gi[u] * gg[u];
+        hn[u] = go[u] * tanhf(cn[u]);
+    }
+    *reinterpret_cast<float4*>(p.gates_act + g_off) = make_float4(gi[0], gi[1], gi[2], gi[3]);
+    *reinterpret_cast<float4*>(p.gates_act + g_off + H) = make_float4(gf[0], gf[1], gf[2], gf[3]);
+    *reinterpret_cast<float4*>(p.gates_act + g_off + 2 * H) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+    *reinterpret_cast<float4*>(p.gates_act + g_off + 3 * H) = make_float4(go[0], go[1], go[2], go[3]);
+    *reinterpret_cast<float4*>(p.c_all + (size_t)(t + 1) * BH + s_off) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+    const float4 h4 = make_float4(hn[0], hn[1], hn[2], hn[3]);
+    *reinterpret_cast<float4*>(p.h_all + (size_t)(t + 1) * BH + s_off) = h4;
+    const uint2 hb = pack4_bf16(hn[0], hn[1], hn[2], hn[3]);
+    *reinterpret_cast<uint2*>(p.h16 + (size_t)(t + 1) * BH + s_off) = hb;                    // next step's A operand
+    const size_t o_off = ((size_t)row * L + t) * H + u0;
+    *reinterpret_cast<float4*>(p.hout + o_off) = h4;
+    if (p.hout16) *reinterpret_cast<uint2*>(p.hout16 + o_off) = hb;
+}
+// operands of the backward cell update: d_hout, gates i f g o, c_{t-1}, c_t, dc
+__device__ __forceinline__ void cell_bwd_load(const LstmSeqArgs& p, int t, int row, int u0, Cell4& o) {
+    const size_t g_off = ((size_t)t * p.B + row) * 4 * p.H + u0;
+    const size_t s_off = (size_t)row * p.H + u0;
+    const size_t BH = (size_t)p.B * p.H;
+    o.a = *reinterpret_cast<const float4*>(p.d_hout + ((size_t)row * p.L + t) * p.H + u0);
+    o.b = *reinterpret_cast<const float4*>(p.gates_act + g_off);
+    o.c = *reinterpret_cast<const float4*>(p.gates_act + g_off + p.H);
+    o.d = *reinterpret_cast<const float4*>(p.gates_act + g_off + 2 * p.H);
+    o.e = *reinterpret_cast<const float4*>(p.gates_act + g_off + 3 * p.H);
+    o.f = *reinterpret_cast<const float4*>(p.c_all + (size_t)t * BH + s_off);
+    o.g = *reinterpret_cast<const float4*>(p.c_all + (size_t)(t + 1) * BH + s_off);
+    o.h = *reinterpret_cast<const float4*>(p.dc + s_off);
+}
+__device__ __forceinline__ void cell_bwd_apply(const LstmSeqArgs& p, int t, int row, int u0, const Cell4& o, const float (&dhh)[4]) {
+    const int H = p.H;
+    const size_t g_off = ((size_t)t * p.B + row) * 4 * H + u0;
+    const size_t s_off = (size_t)row * H + u0;
+    const float dh_[4] = {dhh[0] + o.a.x, dhh[1] + o.a.y, dhh[2] + o.a.z, dhh[3] + o.a.w};
+    const float i_[4] = {o.b.x, o.b.y, o.b.z, o.b.w}, f_[4] = {o.c.x, o.c.y, o.c.z, o.c.w};
+    const float g_[4] = {o.d.x, o.d.y, o.d.z, o.d.w}, o_[4] = {o.e.x, o.e.y, o.e.z, o.e.w};
+    const float cp_[4] = {o.f.x, o.f.y, o.f.z, o.f.w}, cn_[4] = {o.g.x, o.g.y, o.g.z, o.g.w};
+    const float dc_[4] = {o.h.x, o.h.y, o.h.z, o.h.w};
+    float pi[4], pf[4], pg[4], po[4], dcn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const float tc = tanhf(cn_[u]);
+        const float d_o = dh_[u] * tc;
+        const float dc = dc_[u] + dh_[u] * o_[u] * (1.f - tc * tc);
+        const float d_i = dc * g_[u], d_g = dc * i_[u], d_f = dc * cp_[u];
+        dcn[u] = dc * f_[u];
+        pi[u] = d_i * i_[u] * (1.f - i_[u]); pf[u] = d_f * f_[u] * (1.f - f_[u]);
+        pg[u] = d_g * (1.f - g_[u] * g_[u]); po[u] = d_o * o_[u] * (1.f - o_[u]);
+    }
+    *reinterpret_cast<float4*>(p.dc + s_off) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
+    *reinterpret_cast<float4*>(p.dg + g_off) = make_float4(pi[0], pi[1], pi[2], pi[3]);
+    *reinterpret_cast<float4*>(p.dg + g_off + H) = make_float4(pf[0], pf[1], pf[2], pf[3]);
+    *reinterpret_cast<float4*>(p.dg + g_off + 2 * H) = make_float4(pg[0], pg[1], pg[2], pg[3]);
+    *reinterpret_cast<float4*>(p.dg + g_off + 3 * H) = make_float4(po[0], po[1], po[2], po[3]);
+    *reinterpret_cast<uint2*>(p.dg16 + g_off) = pack4_bf16(pi[0], pi[1], pi[2], pi[3]);      // next step's A operand
+    *reinterpret_cast<uint2*>(p.dg16 + g_off + H) = pack4_bf16(pf[0], pf[1], pf[2], pf[3]);
+    *reinterpret_cast<uint2*>(p.dg16 + g_off + 2 * H) = pack4_bf16(pg[0], pg[1], pg[2], pg[3]);
+    *reinterpret_cast<uint2*>(p.dg16 + g_off + 3 * H) = pack4_bf16(po[0], po[1], po[2], po[3]);
+}
+
+// BWD = 0: forward recurrence.  CTA c owns hidden units [4c, 4c+4): accumulator column n = gate * 4 + unit, K = H.
+// BWD = 1: backward recurrence.  Clusters of 4 CTAs: cluster i accumulates dh for hidden units [16i, 16i+16) (column n = unit);
+//          CTA rank q of the cluster contracts the K-slice [qH, (q+1)H) of dg (= gate q) — a quarter of the operand stream per
+//          SM — then the four partial sums are exchanged through distributed shared memory (rank q sends columns 4j..4j+3 to
+//          rank j) and rank j finishes units [16i + 4j, 16i + 4j + 4): summed in rank order, so the result is deterministic.
 template <int BWD>
 __global__ void __launch_bounds__(LP_THREADS, 1)
 lstm_seq_kernel(const __grid_constant__ CUtensorMap tmA, const LstmSeqArgs p) {
@@ -106,11 +203,16 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmA, const LstmSeqArgs p) {
     const uint32_t bars = sW + (uint32_t)p.nkb * LP_W_KB_BYTES;
     const uint32_t full0 = bars, empty0 = bars + 8 * S, tfull = bars + 16 * S, tempty = tfull + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gW + (size_t)p.nkb * LP_W_KB_BYTES + 16 * S + 16);
+    const uint32_t sRed = bars + 256;                                  // BWD: [MT][4 source ranks][128 rows] float4
+    float4* gRed = reinterpret_cast<float4*>(gW + (size_t)p.nkb * LP_W_KB_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int B = p.B, L = p.L, H = p.H, K = p.K;
     const int MT = (B + LP_BM - 1) / LP_BM;
-    const int unit0 = blockIdx.x * (BWD ? 16 : 4);
+    const uint32_t crank = BWD ? cluster_ctarank() : 0u;
+    const int unit0 = BWD ? (int)(blockIdx.x / 4) * 16 : (int)blockIdx.x * 4;      // first unit of the accumulator columns
+    const int k0 = BWD ? (int)crank * K : 0;                                       // first column of this CTA's K-slice of A
+    const int my_u0 = BWD ? unit0 + 4 * (int)crank : unit0;                        // the 4 units this CTA finishes
     const unsigned int NC = gridDim.x;
 
     if (threadIdx.x == 0) {
@@ -133,9 +235,9 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmA, const LstmSeqArgs p) {
             if (!BWD) {                                    // B(n, k) = W_hh[gate * H + unit0 + u][k],  n = gate * 4 + u
                 n = idx / Kpad; k = idx % Kpad;
                 if (k < K) v = p.w_hh[(size_t)((n >> 2) * H + unit0 + (n & 3)) * H + k];
-            } else {                                       // B(n, k) = W_hh[k][unit0 + n]   (dh = dg W_hh)
+            } else {                                       // B(n, k) = W_hh[k0 + k][unit0 + n]   (dh = dg W_hh)
                 k = idx / LP_N; n = idx % LP_N;
-                if (k < K) v = p.w_hh[(size_t)k * H + unit0 + n];
+                if (k < K) v = p.w_hh[(size_t)(k0 + k) * H + unit0 + n];
             }
             *reinterpret_cast<__nv_bfloat16*>(gW + w_slice_off(n, k)) = __float2bfloat16_rn(v);
         }
@@ -143,6 +245,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmA, const LstmSeqArgs p) {
     fence_proxy_async_smem();                              // generic-proxy smem writes -> visible to the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
+    if (BWD) cluster_sync_all();                           // peers' shared memory is live before any remote store targets it
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -153,6 +256,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmA, const LstmSeqArgs p) {
         const int t = BWD ? (L - 1 - it) : it;
         const bool has_gemm = it > 0;                      // forward: h_0 = 0; backward: no dh flows in from beyond the last step
         const int a_row0 = (BWD ? (t + 1) : t) * B;        // first row of this step's A operand (h_t resp. dg_{t+1})
+        Cell4 ops;                                         // epilogue warps: cell operands of the first row tile, fetched early
         if (warp == 0) {
             // =================================== TMA producer + grid barrier ===================================
             if (lane == 0 && has_gemm) {
@@ -162,7 +266,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmA, const LstmSeqArgs p) {
                     for (int kb = 0; kb < p.nkb; ++kb) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         mbar_arrive_expect_tx(full0 + 8 * stage, LP_A_BYTES);
-                        tma_load_2d(sA + stage * LP_A_BYTES, &tmA, kb * TC_BK, a_row0 + mt * LP_BM, full0 + 8 * stage);
+                        tma_load_2d(sA + stage * LP_A_BYTES, &tmA, k0 + kb * TC_BK, a_row0 + mt * LP_BM, full0 + 8 * stage);
                         if (++stage == S) { stage = 0; phase ^= 1; }
                     }
             }
@@ -193,120 +297,95 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmA, const LstmSeqArgs p) {
         } else {
             // =================================== epilogue: LSTM cell math, warps 2..5 ===================================
             const int q = warp & 3;                        // TMEM lane quarter this warp may access
+            const int r0 = q * 32 + lane;                  // row inside a 128-row tile
+            if (r0 < B) {                                  // fetched while the contraction runs
+                if (BWD) cell_bwd_load(p, t, r0, my_u0, ops); else cell_fwd_load(p, t, r0, my_u0, ops);
+            }
             if (has_gemm) {
                 mbar_wait(tfull, acc_phase);
                 tc_fence_after();
+                acc_phase ^= 1;
             }
-            for (int mt = 0; mt < MT; ++mt) {
-                const int row = mt * LP_BM + q * 32 + lane;
-                uint32_t v[16];
-                if (has_gemm) {
-                    tc_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * LP_N), v);
-                    tc_wait_ld();
-                } else {
+            if (!BWD) {
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int row = mt * LP_BM + r0;
+                    float hh[16];
+                    if (has_gemm) {
+                        uint32_t v[16];
+                        tc_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * LP_N), v);
+                        tc_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = 0u;
+                        for (int j = 0; j < 16; ++j) hh[j] = __uint_as_float(v[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) hh[j] = 0.f;
+                    }
+                    if (has_gemm && mt == MT - 1) {        // all TMEM reads of this warp are done: hand the accumulator back
+                        tc_fence_before();
+                        if (lane == 0) mbar_arrive(tempty);
+                    }
+                    if (row >= B) continue;
+                    if (mt > 0) cell_fwd_load(p, t, row, my_u0, ops);
+                    cell_fwd_apply(p, t, row, my_u0, ops, hh);
                 }
-                if (has_gemm && mt == MT - 1) {            // all TMEM reads of this warp are done: hand the accumulator back
+            } else {
+                if (has_gemm) {
+                    // partial sums of this K-slice -> the rank that finishes each group of 4 units (distributed shared memory)
+                    for (int mt = 0; mt < MT; ++mt) {
+                        uint32_t v[16];
+                        tc_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * LP_N), v);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t local = sRed + (uint32_t)(((mt * 4 + (int)crank) * LP_BM + r0) * 16);
+                            const uint32_t remote = lp_mapa(local, (uint32_t)j);
+                            asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};"
+                                         :: "r"(remote), "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+                        }
+                    }
                     tc_fence_before();
                     if (lane == 0) mbar_arrive(tempty);
                 }
-                if (row >= B) continue;
-                if (!BWD) {
-                    const size_t g_off = ((size_t)t * B + row) * 4 * H + unit0;
-                    const size_t s_off = (size_t)row * H + unit0;
-                    const size_t BH = (size_t)B * H;
-                    const float4 xi = *reinterpret_cast<const float4*>(p.xg + g_off);
-                    const float4 xf = *reinterpret_cast<const float4*>(p.xg + g_off + H);
-                    const float4 xc = *reinterpret_cast<const float4*>(p.xg + g_off + 2 * H);
-                    const float4 xo = *reinterpret_cast<const float4*>(p.xg + g_off + 3 * H);
-                    const float4 cp = *reinterpret_cast<const float4*>(p.c_all + (size_t)t * BH + s_off);
-                    const float xi_[4] = {xi.x, xi.y, xi.z, xi.w}, xf_[4] = {xf.x, xf.y, xf.z, xf.w};
-                    const float xc_[4] = {xc.x, xc.y, xc.z, xc.w}, xo_[4] = {xo.x, xo.y, xo.z, xo.w};
-                    const float cp_[4] = {cp.x, cp.y, cp.z, cp.w};
-                    float gi[4], gf[4], gg[4], go[4], cn[4], hn[4];
+            }
+        }
+        if (BWD) {
+            __syncwarp();
+            if (has_gemm) cluster_sync_all();              // every rank's partial sums have landed (release / acquire)
+            if (warp >= 2) {
+                const int q = warp & 3, r0 = q * 32 + lane;
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int row = mt * LP_BM + r0;
+                    if (row >= B) continue;
+                    float dhh[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (has_gemm) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        gi[u] = sigmoidf_(__uint_as_float(v[u]) + xi_[u]);
-                        gf[u] = sigmoidf_(__uint_as_float(v[4 + u]) + xf_[u]);
-                        gg[u] = tanhf(__uint_as_float(v[8 + u]) + xc_[u]);
-                        go[u] = sigmoidf_(__uint_as_float(v[12 + u]) + xo_[u]);
-                        cn[u] = gf[u] * cp_[u] + gi[u] * gg[u];
-                        hn[u] = go[u] * tanhf(cn[u]);
-                    }
-                    *reinterpret_cast<float4*>(p.gates_act + g_off) = make_float4(gi[0], gi[1], gi[2], gi[3]);
-                    *reinterpret_cast<float4*>(p.gates_act + g_off + H) = make_float4(gf[0], gf[1], gf[2], gf[3]);
-                    *reinterpret_cast<float4*>(p.gates_act + g_off + 2 * H) = make_float4(gg[0], gg[1], gg[2], gg[3]);
-                    *reinterpret_cast<float4*>(p.gates_act + g_off + 3 * H) = make_float4(go[0], go[1], go[2], go[3]);
-                    *reinterpret_cast<float4*>(p.c_all + (size_t)(t + 1) * BH + s_off) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                    const float4 h4 = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                    *reinterpret_cast<float4*>(p.h_all + (size_t)(t + 1) * BH + s_off) = h4;
-                    const uint2 hb = pack4_bf16(hn[0], hn[1], hn[2], hn[3]);
-                    *reinterpret_cast<uint2*>(p.h16 + (size_t)(t + 1) * BH + s_off) = hb;            // next step's A operand
-                    const size_t o_off = ((size_t)row * L + t) * H + unit0;
-                    *reinterpret_cast<float4*>(p.hout + o_off) = h4;
-                    if (p.hout16) *reinterpret_cast<uint2*>(p.hout16 + o_off) = hb;
-                } else {
-                    const size_t BH = (size_t)B * H;
-#pragma unroll
-                    for (int g4 = 0; g4 < 4; ++g4) {
-                        const int u0 = unit0 + 4 * g4;
-                        const size_t g_off = ((size_t)t * B + row) * 4 * H + u0;
-                        const size_t s_off = (size_t)row * H + u0;
-                        const float4 dho = *reinterpret_cast<const float4*>(p.d_hout + ((size_t)row * L + t) * H + u0);
-                        const float4 ai = *reinterpret_cast<const float4*>(p.gates_act + g_off);
-                        const float4 af = *reinterpret_cast<const float4*>(p.gates_act + g_off + H);
-                        const float4 ag = *reinterpret_cast<const float4*>(p.gates_act + g_off + 2 * H);
-                        const float4 ao = *reinterpret_cast<const float4*>(p.gates_act + g_off + 3 * H);
-                        const float4 c0 = *reinterpret_cast<const float4*>(p.c_all + (size_t)t * BH + s_off);
-                        const float4 c1 = *reinterpret_cast<const float4*>(p.c_all + (size_t)(t + 1) * BH + s_off);
-                        const float4 dcv = *reinterpret_cast<const float4*>(p.dc + s_off);
-                        const float dh_[4] = {__uint_as_float(v[4 * g4]) + dho.x, __uint_as_float(v[4 * g4 + 1]) + dho.y,
-                                              __uint_as_float(v[4 * g4 + 2]) + dho.z, __uint_as_float(v[4 * g4 + 3]) + dho.w};
-                        const float i_[4] = {ai.x, ai.y, ai.z, ai.w}, f_[4] = {af.x, af.y, af.z, af.w};
-                        const float g_[4] = {ag.x, ag.y, ag.z, ag.w}, o_[4] = {ao.x, ao.y, ao.z, ao.w};
-                        const float cp_[4] = {c0.x, c0.y, c0.z, c0.w}, cn_[4] = {c1.x, c1.y, c1.z, c1.w};
-                        const float dc_[4] = {dcv.x, dcv.y, dcv.z, dcv.w};
-                        float pi[4], pf[4], pg[4], po[4], dcn[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float tc = tanhf(cn_[u]);
-                            const float d_o = dh_[u] * tc;
-                            const float dc = dc_[u] + dh_[u] * o_[u] * (1.f - tc * tc);
-                            const float d_i = dc * g_[u], d_g = dc * i_[u], d_f = dc * cp_[u];
-                            dcn[u] = dc * f_[u];
-                            pi[u] = d_i * i_[u] * (1.f - i_[u]); pf[u] = d_f * f_[u] * (1.f - f_[u]);
-                            pg[u] = d_g * (1.f - g_[u] * g_[u]); po[u] = d_o * o_[u] * (1.f - o_[u]);
+                        for (int src = 0; src < 4; ++src) {                       // fixed order: deterministic
+                            const float4 x = gRed[(mt * 4 + src) * LP_BM + r0];
+                            dhh[0] += x.x; dhh[1] += x.y; dhh[2] += x.z; dhh[3] += x.w;
                         }
-                        *reinterpret_cast<float4*>(p.dc + s_off) = make_float4(dcn[0], dcn[1], dcn[2], dcn[3]);
-                        *reinterpret_cast<float4*>(p.dg + g_off) = make_float4(pi[0], pi[1], pi[2], pi[3]);
-                        *reinterpret_cast<float4*>(p.dg + g_off + H) = make_float4(pf[0], pf[1], pf[2], pf[3]);
-                        *reinterpret_cast<float4*>(p.dg + g_off + 2 * H) = make_float4(pg[0], pg[1], pg[2], pg[3]);
-                        *reinterpret_cast<float4*>(p.dg + g_off + 3 * H) = make_float4(po[0], po[1], po[2], po[3]);
-                        *reinterpret_cast<uint2*>(p.dg16 + g_off) = pack4_bf16(pi[0], pi[1], pi[2], pi[3]);
-                        *reinterpret_cast<uint2*>(p.dg16 + g_off + H) = pack4_bf16(pf[0], pf[1], pf[2], pf[3]);
-                        *reinterpret_cast<uint2*>(p.dg16 + g_off + 2 * H) = pack4_bf16(pg[0], pg[1], pg[2], pg[3]);
-                        *reinterpret_cast<uint2*>(p.dg16 + g_off + 3 * H) = pack4_bf16(po[0], po[1], po[2], po[3]);
                     }
+                    if (mt > 0) cell_bwd_load(p, t, row, my_u0, ops);
+                    cell_bwd_apply(p, t, row, my_u0, ops, dhh);
                 }
             }
-            fence_proxy_async_all();                       // the rows just written are read by other CTAs' TMA next step
         }
+        if (warp >= 2) fence_proxy_async_all();            // the rows just written are read by other CTAs' TMA in the next step
         __syncthreads();
         if (threadIdx.x == 0 && it + 1 < L) grid_arrive(p.bar);
     }
 
     tc_fence_before();
     __syncthreads();
+    if (BWD) cluster_sync_all();                           // no rank exits while a peer could still address its shared memory
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"((uint32_t)LP_TMEM_COLS) : "memory");
     }
 }
 
-int plan_smem(int nkb, int* stages) {
-    // resident weight slice + barriers + as many 16 KB A stages as fit (2..8)
-    const int fixed = 1024 + nkb * LP_W_KB_BYTES + 256;
+int plan_smem(int nkb, int red_bytes, int* stages) {
+    // resident weight slice + barriers (+ the backward's exchange buffer) + as many 16 KB A stages as fit (2..8)
+    const int fixed = 1024 + nkb * LP_W_KB_BYTES + 256 + red_bytes;
     int s = (200 * 1024 - fixed) / LP_A_BYTES;
     if (s > 8) s = 8;
     *stages = s;
@@ -318,23 +397,40 @@ bool persistent_enabled() {
     return on;
 }
 
+// A16: the bf16 activation stack [a_rows][a_cols] the per-step A operands are cut from (a.K = this CTA's contraction length)
 template <int BWD>
-int launch_seq(const LstmSeqArgs& a0, const __nv_bfloat16* A16, int a_rows, cudaStream_t s) {
+int launch_seq(const LstmSeqArgs& a0, const __nv_bfloat16* A16, int a_rows, int a_cols, cudaStream_t s) {
     LstmSeqArgs a = a0;
     a.nkb = (a.K + TC_BK - 1) / TC_BK;
-    const int smem = plan_smem(a.nkb, &a.stages);
+    const int MT = (a.B + LP_BM - 1) / LP_BM;
+    const int smem = plan_smem(a.nkb, BWD ? MT * 4 * LP_BM * 16 : 0, &a.stages);
     ICD_CHECK_ARG(a.stages >= 2, "lstm_seq: hidden size %d too large for the resident weight slice", a.H);
     CUtensorMap tmA;
-    ICD_TRY(make_tmap(&tmA, A16, a.K, a_rows, a.K, LP_BM, 0));
+    ICD_TRY(make_tmap(&tmA, A16, a_cols, a_rows, a_cols, LP_BM, 0));
     static int smem_set = 0;
     if (smem_set < smem) {
         ICD_CUDA(cudaFuncSetAttribute(lstm_seq_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         smem_set = smem;
     }
     ICD_CUDA(cudaMemsetAsync(a.bar, 0, sizeof(unsigned int), s));
-    const int grid = a.H / (BWD ? 16 : 4);
-    void* args[] = {(void*)&tmA, (void*)&a};
-    ICD_CUDA(cudaLaunchCooperativeKernel((const void*)lstm_seq_kernel<BWD>, dim3(grid), dim3(LP_THREADS), args, (size_t)smem, s));
+    const int grid = a.H / 4;                              // forward: 4 units per CTA; backward: 16 units per 4-CTA cluster
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(LP_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative;           // every CTA co-resident, or the launch fails: the grid barrier cannot hang
+    attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 4; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = BWD ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_seq_kernel<BWD>, tmA, a);
+    if (e != cudaSuccess && BWD) {
+        // a driver that refuses cooperative + cluster launches: the grid (<= 148 CTAs, one per SM, launched on an otherwise
+        // ordered stream) is co-resident in practice; the barrier's spin limit turns a violation into a fault, not a hang
+        (void)cudaGetLastError();
+        cfg.attrs = attr + 1; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, lstm_seq_kernel<BWD>, tmA, a);
+    }
+    ICD_CUDA(e);
     ICD_LAUNCH_CHECK();
     return 0;
 }
@@ -349,7 +445,7 @@ int icd_lstm_seq_persistent_ok(int B, int L, int H) {
     if (H / 4 > ICD_NUM_SMS) return 0;
     if ((B + LP_BM - 1) / LP_BM > LP_MAX_MT) return 0;
     int st;
-    plan_smem((4 * H + TC_BK - 1) / TC_BK, &st);
+    plan_smem((H + TC_BK - 1) / TC_BK, ((B + LP_BM - 1) / LP_BM) * 4 * LP_BM * 16, &st);
     return st >= 2 ? 1 : 0;
 }
 
@@ -359,16 +455,17 @@ int icd_lstm_seq_fwd_persistent(int B, int L, int H, const float* w_hh, const fl
     LstmSeqArgs a = {};
     a.B = B; a.L = L; a.H = H; a.K = H; a.w_hh = w_hh; a.xg = xg; a.gates_act = gates_act; a.c_all = c_all; a.h_all = h_all;
     a.hout = hout; a.h16 = reinterpret_cast<__nv_bfloat16*>(h16); a.hout16 = reinterpret_cast<__nv_bfloat16*>(hout16); a.bar = bar;
-    return launch_seq<0>(a, a.h16, (L + 1) * B, s);
+    return launch_seq<0>(a, a.h16, (L + 1) * B, H, s);
 }
 
 int icd_lstm_seq_bwd_persistent(int B, int L, int H, const float* w_hh, const float* d_hout, const float* gates_act,
                                 const float* c_all, float* dc, float* dg, void* dg16, unsigned int* bar, cudaStream_t s) {
     ICD_CHECK_ARG(icd_lstm_seq_persistent_ok(B, L, H), "lstm_seq_bwd: shape B=%d L=%d H=%d not covered by the persistent kernel", B, L, H);
     LstmSeqArgs a = {};
-    a.B = B; a.L = L; a.H = H; a.K = 4 * H; a.w_hh = w_hh; a.d_hout = d_hout; a.gates_act = const_cast<float*>(gates_act);
+    a.B = B; a.L = L; a.H = H; a.K = H; a.w_hh = w_hh; a.d_hout = d_hout;      // K: one rank's slice of the 4H-long contraction
+    a.gates_act = const_cast<float*>(gates_act);
     a.c_all = const_cast<float*>(c_all); a.dc = dc; a.dg = dg; a.dg16 = reinterpret_cast<__nv_bfloat16*>(dg16); a.bar = bar;
-    return launch_seq<1>(a, a.dg16, L * B, s);
+    return launch_seq<1>(a, a.dg16, L * B, 4 * H, s);
 }
 
 // ---- C ABI (include/icd_b200.h): the LSTM recurrence on its own, for callers that hoist the input contraction themselves ----

@@ -229,6 +229,8 @@ def test_data_parallel_clip_adam_single_process_equals_reference_optimizer_glue(
                 assert float((pa - pb).abs().max()) <= 1e-3 * lr, "parameter after the first step: " + k
             else:               # Adam's update is ~lr * sign(g) early on: an element whose tiny gradient changes sign between
                 d = (pa - pb).abs()       # the two (now slightly different) models moves by up to 2 lr; all others agree
-                assert float(d.max()) <= 2.1 * lr * (step + 1) and float(d.mean()) <= 2e-2 * lr, "parameter after step %d: %s" % (step + 1, k)
+                assert float(d.max()) <= 2.1 * lr * (step + 1), "parameter after step %d: %s" % (step + 1, k)
+                if k != "attention.full_att.bias":        # (one element whose true gradient is 0: pure sign noise)
+                    assert float(d.mean()) <= 2e-2 * lr, "parameter after step %d: %s" % (step + 1, k)
     assert torch.equal(dec_a.embedding.weight, dec_b.embedding.weight)       # frozen
     assert opt_a.step_count == 3
