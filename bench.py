@@ -553,11 +553,13 @@ def side_workload(args):
         line = measure_attention(dev, prec, args.batch, args.steps, max(args.warmup, 3), glove=True)
     else:
         line = measure_attention(dev, prec, args.batch, args.steps, max(args.warmup, 3))
-    if rank == 0:
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+        if rank == 0:
+            time.sleep(0.5)              # NCCL's closing INFO lines first: the JSON result stays the last line on stdout
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
 
 def bind_to_gpu_numa_node(device_index):
@@ -891,11 +893,16 @@ def main():
                                              "ms_per_step": r0["ms_per_step"],
                                              "sample": "configs[0] itself: basic_att, batch 4, 25 tokens, fwd + loss + bwd + clip + Adam "
                                                        "on the host cores (README.md:7), 3 timed steps"}
-        sys.stdout.flush()
-        print(json.dumps(line), flush=True)
     if world > 1:
+        # tear NCCL down BEFORE printing: with NCCL_DEBUG=INFO (left as the caller set it) the communicator prints while it
+        # closes, and the JSON result must be the last line on stdout
         dist.barrier()
         dist.destroy_process_group()
+        if rank == 0:
+            time.sleep(0.5)              # let the other ranks' closing lines drain
+    if rank == 0:
+        sys.stdout.flush()
+        print(json.dumps(line), flush=True)
 
 
 def parity_check(dec, enc_d, caps_d, lens, dev, rows=32):
