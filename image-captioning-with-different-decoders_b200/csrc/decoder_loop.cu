@@ -172,6 +172,7 @@ extern "C" int icd_attention_decoder_bwd(const icd_att_desc_t* d, void* stream) 
     ICD_TRY(icd_gemm_simple(prec, d->d_predictions, 1, V, d->hdrop, 1, D, d->d_fc_w, D, V, D, B * T,
                             nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s, ICD_GEMM_ALLOW_SPLITK));
     ICD_TRY(icd_colsum(d->d_predictions, V, (int64_t)B * T, V, d->row_valid, d->d_fc_b, s));
+    if (d->ev_fc_ready) ICD_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_fc_ready), s));
 
     // ---- BPTT ----
     for (int t = T - 1; t >= 0; --t) {
@@ -226,6 +227,7 @@ extern "C" int icd_attention_decoder_bwd(const icd_att_desc_t* d, void* stream) 
         ICD_CUDA(cudaMemsetAsync(d->d_emb_w, 0, (d->emb_is_f64 ? sizeof(double) : sizeof(float)) * (size_t)V * E, s));
         ICD_TRY(icd_embed_scatter_add(d->d_emb_w, d->emb_is_f64, d->captions, B, d->L, T, E, d->bt_host, d->d_emb_x, s));
     }
+    if (d->ev_rec_ready) ICD_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_rec_ready), s));
     // attention projections: d_att_enc for all steps at once, full_att grads, then enc_att grads (:54)
     ICD_TRY(icd_attention_proj_bwd(B, T, P, A, d->bt_host, d->att_enc, d->z, NZ, d->full_att_w, d->d_e,
                                    d->d_att_enc, d->d_full_att_w, d->d_full_att_b, d->d_enc_att_b, d->proj_partial,

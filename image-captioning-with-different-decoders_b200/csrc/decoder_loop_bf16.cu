@@ -218,6 +218,7 @@ int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
     MMX(dY16, ldY, 0, u.Wfc, D, 1, d->d_hdrop, D, BT, D, V, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
     MMX(dY16, ldY, 1, u.hdrop, D, 1, d->d_fc_w, D, V, D, BT, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
     ICD_TRY(icd_colsum_bf16(dY16, ldY, (int64_t)BT, V, d->row_valid, d->d_fc_b, u.colsum_ws, s));
+    if (d->ev_fc_ready) ICD_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_fc_ready), s));   // fc gradients final
 
     // ---- BPTT ----
     // The dh contraction (M = batch, N = D, K = NZ) runs split-K; its reduce pass is deferred into the next step's LSTM
@@ -270,6 +271,7 @@ int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
         ICD_CUDA(cudaMemsetAsync(d->d_emb_w, 0, (d->emb_is_f64 ? sizeof(double) : sizeof(float)) * (size_t)V * E, s));
         ICD_TRY(icd_embed_scatter_add(d->d_emb_w, d->emb_is_f64, d->captions, B, d->L, T, E, d->bt_host, d->d_emb_x, s));
     }
+    if (d->ev_rec_ready) ICD_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_rec_ready), s)); // recurrent gradients final
     // attention projections: d_att_enc for all steps at once (bf16 only: it is just the A operand of the next
     // contraction), full_att grads and the enc_att bias grad from the same pass, then the enc_att weight grad (:54)
     ICD_TRY(icd_attention_proj_bwd_bf16(B, T, P, A, d->bt_host, u.att_enc, d->z, NZ, d->full_att_w, d->d_e,

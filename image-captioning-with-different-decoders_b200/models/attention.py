@@ -185,7 +185,8 @@ class AttentionDecoder(nn.Module):
             self.decode_step.weight_ih, self.decode_step.weight_hh, self.decode_step.bias_ih, self.decode_step.bias_hh,
             self.h_lin.weight, self.h_lin.bias, self.c_lin.weight, self.c_lin.bias,
             self.f_beta.weight, self.f_beta.bias, self.fc.weight, self.fc.bias,
-            bt, mask, (1.0 / (1.0 - p)) if mask is not None else 1.0, self.precision)
+            bt, mask, (1.0 / (1.0 - p)) if mask is not None else 1.0, self.precision,
+            getattr(self, "_icd_grad_sink", None))
         return predictions, encoded_captions, decode_lengths, alphas
 
 
@@ -200,7 +201,8 @@ class _AttentionDecoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, enc, captions, emb_w, *rest):
         weights = rest[:18]
-        bt, mask, drop_scale, precision = rest[18:]
+        bt, mask, drop_scale, precision, sink = rest[18:]
+        ctx.sink = sink                  # DataParallelClipAdam in overlap mode: gradients go straight into its flat buffer
         if not enc.is_cuda:
             raise _lib.IcdError("AttentionDecoder.forward needs CUDA tensors; there is no CPU fallback")
         dev = enc.device
@@ -284,15 +286,45 @@ class _AttentionDecoderFn(torch.autograd.Function):
             d_alphas = d_alphas.contiguous().float()
         want_emb = ctx.needs_input_grad[2]
         want_enc = ctx.needs_input_grad[0]           # encoder_out.requires_grad (--fine_tune_encoder, train.py:39)
-        g = dict(
-            d_enc_att_w=torch.empty(A, C, **f32), d_enc_att_b=torch.empty(A, **f32),
-            d_w_cat=torch.empty(NZ, D, **f32), d_b_cat=torch.empty(NZ, **f32),
-            d_full_att_w=torch.empty(A, **f32), d_full_att_b=torch.empty(1, **f32),
-            d_w_ih=torch.empty(4 * D, E + C, **f32),
-            d_h_lin_w=torch.empty(D, C, **f32), d_h_lin_b=torch.empty(D, **f32),
-            d_c_lin_w=torch.empty(D, C, **f32), d_c_lin_b=torch.empty(D, **f32),
-            d_fc_w=torch.empty(V, D, **f32), d_fc_b=torch.empty(V, **f32),
-            d_emb_w=(torch.empty(V, E, device=dev, dtype=emb_w.dtype) if want_emb else None))
+        # gradient buffers: fresh tensors, or (data-parallel overlap mode) views of the optimiser's flat gradient buffer laid out
+        # in completion order, so that no gather copy is needed and finished buckets can be all-reduced mid-backward
+        sink = ctx.sink if (ctx.sink is not None and ctx.sink.sink_ready() and all(ctx.needs_input_grad[3:21])) else None
+        sunk = []
+        if sink is not None:
+            buf = sink.buf
+            wcat = buf.group_view(("attention.dec_att.weight", "f_beta.weight", "decode_step.weight_hh"), (NZ, D))
+            bcat = buf.group_view(("attention.dec_att.bias", "f_beta.bias", "decode_step.bias_hh"), (NZ,))
+            if wcat is None or bcat is None or (want_emb and emb_w.dtype == torch.float32 and "embedding.weight" not in buf.offsets):
+                sink = None
+        if sink is not None:
+            def gv(name, shape):
+                sunk.append(name)
+                return buf.grad_view(name, shape)
+            sunk += ["attention.dec_att.weight", "f_beta.weight", "decode_step.weight_hh",
+                     "attention.dec_att.bias", "f_beta.bias", "decode_step.bias_hh"]
+            emb_sunk = want_emb and emb_w.dtype == torch.float32
+            g = dict(
+                d_enc_att_w=gv("attention.enc_att.weight", (A, C)), d_enc_att_b=gv("attention.enc_att.bias", (A,)),
+                d_w_cat=wcat, d_b_cat=bcat,
+                d_full_att_w=gv("attention.full_att.weight", (A,)), d_full_att_b=gv("attention.full_att.bias", (1,)),
+                d_w_ih=gv("decode_step.weight_ih", (4 * D, E + C)),
+                d_h_lin_w=gv("h_lin.weight", (D, C)), d_h_lin_b=gv("h_lin.bias", (D,)),
+                d_c_lin_w=gv("c_lin.weight", (D, C)), d_c_lin_b=gv("c_lin.bias", (D,)),
+                d_fc_w=gv("fc.weight", (V, D)), d_fc_b=gv("fc.bias", (V,)),
+                d_emb_w=(gv("embedding.weight", (V, E)) if emb_sunk else
+                         (torch.empty(V, E, device=dev, dtype=emb_w.dtype) if want_emb else None)))
+            ev_fc, ev_rec = sink.bucket_events() if sink._world() > 1 else (None, None)
+        else:
+            ev_fc = ev_rec = None
+            g = dict(
+                d_enc_att_w=torch.empty(A, C, **f32), d_enc_att_b=torch.empty(A, **f32),
+                d_w_cat=torch.empty(NZ, D, **f32), d_b_cat=torch.empty(NZ, **f32),
+                d_full_att_w=torch.empty(A, **f32), d_full_att_b=torch.empty(1, **f32),
+                d_w_ih=torch.empty(4 * D, E + C, **f32),
+                d_h_lin_w=torch.empty(D, C, **f32), d_h_lin_b=torch.empty(D, **f32),
+                d_c_lin_w=torch.empty(D, C, **f32), d_c_lin_b=torch.empty(D, **f32),
+                d_fc_w=torch.empty(V, D, **f32), d_fc_b=torch.empty(V, **f32),
+                d_emb_w=(torch.empty(V, E, device=dev, dtype=emb_w.dtype) if want_emb else None))
         scratch = dict(
             d_hdrop=torch.empty(B, T, D, **f32), dz=torch.empty(T, B, NZ, **f32), d_e=torch.empty(B, T, P, **f32),
             dh=torch.empty(B, D, **f32), dc=torch.empty(B, D, **f32), d_gated=torch.empty(B, C, **f32),
@@ -305,6 +337,7 @@ class _AttentionDecoderFn(torch.autograd.Function):
         d = ctx.desc
         fill(d, d_predictions=d_pred, d_predictions16=d_pred16,
              ld_dpred16=(d_pred16.stride(0) if d_pred16 is not None else 0), d_alphas=d_alphas, **g, **scratch)
+        d.ev_fc_ready, d.ev_rec_ready = ev_fc, ev_rec
         check(lib().icd_attention_decoder_bwd(ctypes.byref(d), stream_ptr()), "icd_attention_decoder_bwd")
         # release the ~GBs of saved activations now (stream-ordered: the caching allocator only hands them to later
         # work on this stream), not when the last reference to the loss tensor dies — otherwise two steps' worth of
@@ -313,12 +346,22 @@ class _AttentionDecoderFn(torch.autograd.Function):
         ctx.desc = None
         dwc, dbc = g["d_w_cat"], g["d_b_cat"]
         d_b_lstm = dbc[A + C:]
+        if sink is not None:
+            # bias_ih receives the same gradient as bias_hh: one small copy inside the flat buffer, then the buckets that are
+            # already final start their all-reduce behind the events the C call recorded
+            d_b_ih = sink.buf.grad_view("decode_step.bias_ih", (4 * D,))
+            d_b_ih.copy_(d_b_lstm)
+            sunk.append("decode_step.bias_ih")
+        else:
+            d_b_ih = d_b_lstm.clone()
         grads = [
             g["d_enc_att_w"], g["d_enc_att_b"], dwc[:A], dbc[:A], g["d_full_att_w"].view(1, A), g["d_full_att_b"],
-            g["d_w_ih"], dwc[A + C:], d_b_lstm, d_b_lstm.clone(),
+            g["d_w_ih"], dwc[A + C:], d_b_lstm, d_b_ih,
             g["d_h_lin_w"], g["d_h_lin_b"], g["d_c_lin_w"], g["d_c_lin_b"],
             dwc[A:A + C], dbc[A:A + C], g["d_fc_w"], g["d_fc_b"]]
         d_enc = scratch["d_enc"]
         if d_enc is not None and ctx.in_dtype != torch.float32:
             d_enc = d_enc.to(ctx.in_dtype)
-        return (d_enc, None, g["d_emb_w"], *grads, None, None, None, None)
+        if sink is not None:
+            sink.backward_issued(sunk)
+        return (d_enc, None, g["d_emb_w"], *grads, None, None, None, None, None)

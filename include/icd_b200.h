@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ICD_B200_ABI_VERSION 12
+#define ICD_B200_ABI_VERSION 13
 #define ICD_MAX_STEPS 256
 
 ICD_API int icd_version(void);                       /* ICD_B200_ABI_VERSION the library was built with */
@@ -285,6 +285,12 @@ typedef struct {
     float* proj_partial;          /* icd_attention_proj_bwd_ws_floats(B,P,A) floats */
     /* ICD_PREC_BF16 only: arena for the bf16 operand copies, shared by fwd and bwd of the same step */
     void* tc_ws; int64_t tc_ws_bytes;   /* >= icd_attention_decoder_ws_bytes(desc) */
+    /* backward only, optional (NULL = not recorded): cudaEvent_t handles recorded on `stream` as soon as a group of weight
+     * gradients is final, so that a data-parallel caller can start all-reducing them while the rest of the backward runs:
+     *   ev_fc_ready  — d_fc_w, d_fc_b (right after the vocabulary-layer contractions, BEFORE the time loop);
+     *   ev_rec_ready — d_h_lin_*, d_c_lin_*, d_w_cat, d_b_cat, d_w_ih, d_emb_w (after the hoisted recurrent weight gradients,
+     *                  before the attention-projection pass that produces d_full_att_*, d_enc_att_*). */
+    void* ev_fc_ready; void* ev_rec_ready;
 } icd_att_desc_t;
 
 ICD_API int64_t icd_attention_decoder_ws_bytes(const icd_att_desc_t* d);

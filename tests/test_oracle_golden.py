@@ -254,12 +254,12 @@ def test_saved_checkpoint_loads_in_the_unmodified_reference(tmp_path, monkeypatc
     assert type(ropt) is torch.optim.Adam and ropt.param_groups[0]["lr"] == 1e-3
     rparams = [p_ for p_ in rdec.parameters() if p_.requires_grad]
     assert [id(p_) for p_ in ropt.param_groups[0]["params"]] == [id(p_) for p_ in rparams]
-    off = 0
-    for p_ in rparams:
+    rnames = [k for k, p_ in rdec.named_parameters() if p_.requires_grad]
+    for k, p_ in zip(rnames, rparams):
         st = ropt.state[p_]
-        assert int(st["step"]) == 2
-        assert torch.equal(st["exp_avg"].reshape(-1), opt.exp_avg[off:off + p_.numel()])
-        off += p_.numel()
+        off, n = opt.buf.offsets[k]
+        assert int(st["step"]) == 2 and n == p_.numel()
+        assert torch.equal(st["exp_avg"].reshape(-1), opt.exp_avg[off:off + n])
     rdec.train()
     preds, cs, dl, alphas = rdec(enc, caps, lens)
     O.attention_loss(preds, cs, dl, alphas).backward()
@@ -269,7 +269,11 @@ def test_saved_checkpoint_loads_in_the_unmodified_reference(tmp_path, monkeypatc
     assert type(chk2["decoder"]) is my_att.AttentionDecoder
     opt2 = DataParallelClipAdam(chk2["decoder"], lr=1.0)
     opt2.load_torch_adam(chk2["decoder_optimizer"])
-    assert opt2.step_count == 2 and opt2.lr == 1e-3 and torch.equal(opt2.exp_avg, opt.exp_avg)
+    assert opt2.step_count == 2 and opt2.lr == 1e-3
+    for k, (off, n) in opt.buf.offsets.items():
+        off2, n2 = opt2.buf.offsets[k]
+        assert n == n2 and torch.equal(opt2.exp_avg[off2:off2 + n], opt.exp_avg[off:off + n]), k
+        assert torch.equal(opt2.exp_avg_sq[off2:off2 + n], opt.exp_avg_sq[off:off + n]), k
 
 
 def test_oracle_loss_glue_equals_pack_padded_sequence_expression():
