@@ -115,7 +115,9 @@ extern "C" int icd_attention_decoder_fwd(const icd_att_desc_t* d, void* stream) 
     ICD_TRY(icd_init_hidden_state(B, P, C, D, prec, d->enc, d->h_lin_w, d->h_lin_b, d->c_lin_w, d->c_lin_b,
                                   d->mean_enc, d->h_all, d->c_all, s));
     // K5: embedding lookup (:247) + hoisted input contraction
-    ICD_TRY(icd_embed_gather(d->emb_w, d->emb_is_f64, d->captions, B, d->L, T, E, V, d->emb_x, s));
+    // emb_w == NULL: emb_x (T,B,E) was filled by the caller with pre-computed embeddings (the reference's use_bert branch,
+    // models/attention.py:242-244: (B,L,768) BERT vectors instead of the table lookup); they carry no gradient
+    if (d->emb_w) ICD_TRY(icd_embed_gather(d->emb_w, d->emb_is_f64, d->captions, B, d->L, T, E, V, d->emb_x, s));
     ICD_TRY(icd_gemm_simple(prec, d->emb_x, E, 1, d->w_ih, E + C, 1, d->xg, 4 * D, T * B, 4 * D, E,
                             d->b_ih, d->b_hh, nullptr, 0, nullptr, 0, nullptr, 0.f, s));
 

@@ -166,7 +166,9 @@ int icd_attention_decoder_fwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
     MMX(u.mean, C, 0, u.Wh, C, 0, d->h_all, D, B, D, C, d->h_lin_b, nullptr, nullptr, 0, nullptr, 0, nullptr, u.h, D);
     MMX(u.mean, C, 0, u.Wc, C, 0, d->c_all, D, B, D, C, d->c_lin_b, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, 0);
     // K5: embedding lookup (:247) + hoisted input contraction
-    ICD_TRY(icd_embed_gather(d->emb_w, d->emb_is_f64, d->captions, B, d->L, T, E, V, d->emb_x, s));
+    // emb_w == NULL: emb_x (T,B,E) was filled by the caller with pre-computed embeddings (the reference's use_bert branch,
+    // models/attention.py:242-244: (B,L,768) BERT vectors instead of the table lookup); they carry no gradient
+    if (d->emb_w) ICD_TRY(icd_embed_gather(d->emb_w, d->emb_is_f64, d->captions, B, d->L, T, E, V, d->emb_x, s));
     CVT(d->emb_x, E, TB, E, u.embx, u.ldE);
     MMX(u.embx, u.ldE, 0, u.WihE, u.ldE, 0, d->xg, 4 * D, TB, 4 * D, E, d->b_ih, d->b_hh, nullptr, 0, nullptr, 0, nullptr, nullptr, 0);
 

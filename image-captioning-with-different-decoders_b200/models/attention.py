@@ -6,7 +6,10 @@ reference (models/attention.py:18-284); same parameter initialisation order, so 
 ``nn.Embedding``) are kept as parameter containers for ``state_dict`` / attribute compatibility; ``forward``
 never calls them — it runs the CUDA kernels through the C ABI (include/icd_b200.h).
 
-Out of scope: the BERT-embedding branch (``use_bert=True``, models/attention.py:166-215).
+``use_bert=True`` (models/attention.py:96-100, 166-215, 242-244): the decoder consumes (B, L, 768) pre-computed caption
+embeddings instead of its table lookup and runs the same kernels with E = 768.  Computing them (a BERT forward per caption +
+word-piece merging) needs ``pytorch_pretrained_bert`` and downloaded weights, neither available offline: plug any callable
+``captions -> (B, L, embed_size)`` in as ``decoder.bert_embedder``, or pass ``embeddings=`` to ``forward``.
 ``encoder_out.requires_grad`` (``--fine_tune_encoder``, train.py:39) is honoured: the backward also returns the gradient
 w.r.t. the encoder features (attention-weighted sum, ``enc_att`` projection and initial-state mean paths).
 """
@@ -116,9 +119,9 @@ class AttentionDecoder(nn.Module):
         self.dropout = params.dropout
 
         self.use_bert = params.use_bert
-        if self.use_bert:
-            raise NotImplementedError(
-                "icd_b200: the BERT-embedding branch (models/attention.py:166-215) is out of scope")
+        # (:96-100) the reference loads BertTokenizer / BertModel here; this package takes the embeddings from a pluggable
+        # callable instead (see _create_bert_embeddings) — the decoder arithmetic downstream is identical
+        self.bert_embedder = None
 
         # construction order = reference order (:103-117) so that seeded init is bit-identical
         self.attention = SoftAttention(self.encoder_dim, self.decoder_dim, self.attention_dim)
@@ -159,8 +162,22 @@ class AttentionDecoder(nn.Module):
                                         self.c_lin.bias, precision="fp32")
         return h, c
 
-    def forward(self, encoder_out, encoded_captions, caption_lengths):
-        """(:218-284) -> (predictions (B,T,V), encoded_captions, decode_lengths, attention_weights (B,T,P))"""
+    def _create_bert_embeddings(self, encoded_captions):
+        """(:166-215) -> (B, L, embed_size) caption embeddings, no gradient.  The reference runs bert-base-uncased per caption
+        and sums word pieces back into vocabulary tokens; here ``self.bert_embedder`` (any callable doing that, or a cache of
+        its results — train.py:83-85 notes the BERT pass costs hours) supplies them."""
+        if self.bert_embedder is None:
+            raise NotImplementedError(
+                "icd_b200: use_bert=True needs decoder.bert_embedder = callable(encoded_captions) -> (B, L, %d) embeddings, "
+                "or forward(..., embeddings=...); pytorch_pretrained_bert and its weights are not available offline"
+                % self.embed_size)
+        with torch.no_grad():
+            return self.bert_embedder(encoded_captions)
+
+    def forward(self, encoder_out, encoded_captions, caption_lengths, embeddings=None):
+        """(:218-284) -> (predictions (B,T,V), encoded_captions, decode_lengths, attention_weights (B,T,P)).
+        ``embeddings`` (extension): pre-computed (B, L, embed_size) caption embeddings used instead of the table lookup —
+        what the reference's ``use_bert`` branch feeds the loop (:242-244, :273)."""
         batch_size = encoder_out.size(0)
         encoder_dim = encoder_out.size(-1)
         enc = encoder_out.reshape(batch_size, -1, encoder_dim)                         # :230
@@ -178,9 +195,16 @@ class AttentionDecoder(nn.Module):
             else:
                 seed = int(torch.randint(0, 2 ** 62, (1,)).item())   # consumes torch's CPU generator: seedable
                 mask = ops.dropout_mask((T, batch_size, D), p, seed, device=enc.device)
+        if embeddings is None and self.use_bert:                                       # :242-244
+            embeddings = self._create_bert_embeddings(encoded_captions)
+        emb_source = self.embedding.weight                                             # :247
+        if embeddings is not None:
+            assert embeddings.shape[0] == batch_size and embeddings.shape[1] >= T and embeddings.shape[2] == self.embed_size, \
+                "embeddings must be (batch, >= %d caption positions, %d)" % (T, self.embed_size)
+            emb_source = _PrecomputedEmbeddings(embeddings.detach())
         a = self.attention
         predictions, alphas = _AttentionDecoderFn.apply(
-            enc, encoded_captions, self.embedding.weight,
+            enc, encoded_captions, emb_source,
             a.enc_att.weight, a.enc_att.bias, a.dec_att.weight, a.dec_att.bias, a.full_att.weight, a.full_att.bias,
             self.decode_step.weight_ih, self.decode_step.weight_hh, self.decode_step.bias_ih, self.decode_step.bias_hh,
             self.h_lin.weight, self.h_lin.bias, self.c_lin.weight, self.c_lin.bias,
@@ -193,6 +217,14 @@ class AttentionDecoder(nn.Module):
 _W_NAMES = ["enc_att_w", "enc_att_b", "dec_att_w", "dec_att_b", "full_att_w", "full_att_b",
             "w_ih", "w_hh", "b_ih", "b_hh", "h_lin_w", "h_lin_b", "c_lin_w", "c_lin_b",
             "f_beta_w", "f_beta_b", "fc_w", "fc_b"]
+
+
+class _PrecomputedEmbeddings:
+    """Marks (B, L, E) caption embeddings handed to the decoder in place of the embedding table (not a tensor: autograd
+    must not track it — the reference computes them under torch.no_grad(), :179-180)."""
+
+    def __init__(self, t):
+        self.t = t
 
 
 class _AttentionDecoderFn(torch.autograd.Function):
@@ -222,19 +254,23 @@ class _AttentionDecoderFn(torch.autograd.Function):
         L = captions.shape[1]
         A = weights[0].shape[0]
         D = weights[7].shape[1]
-        E = emb_w.shape[1]
+        pre = None
+        if isinstance(emb_w, _PrecomputedEmbeddings):       # use_bert branch: (B, L, E) vectors, step-major for the kernels
+            pre = emb_w.t[:, :T].to(device=dev).permute(1, 0, 2).contiguous().float()
+            emb_w = None
+        E = pre.shape[2] if pre is not None else emb_w.shape[1]
         V = weights[16].shape[0]
         NZ = A + C + 4 * D
         assert T <= _lib.MAX_STEPS
-        emb_is_f64 = emb_w.dtype == torch.float64
-        assert emb_w.dtype in (torch.float32, torch.float64)
+        emb_is_f64 = emb_w is not None and emb_w.dtype == torch.float64
+        assert emb_w is None or emb_w.dtype in (torch.float32, torch.float64)
         weights = [w.contiguous() for w in weights]
-        emb_c = emb_w.contiguous()           # kept in ctx.keep: a non-contiguous table would otherwise leave a dangling pointer
+        emb_c = emb_w.contiguous() if emb_w is not None else None   # kept in ctx.keep (no dangling pointer to a temporary)
         f32 = dict(device=dev, dtype=torch.float32)
         bufs = dict(
             predictions=torch.empty(B, T, V, **f32), alphas=torch.empty(B, T, P, **f32),
             att_enc=torch.empty(B, P, A, **f32), mean_enc=torch.empty(B, C, **f32),
-            emb_x=torch.empty(T, B, E, **f32), xg=torch.empty(T, B, 4 * D, **f32),
+            emb_x=(pre if pre is not None else torch.empty(T, B, E, **f32)), xg=torch.empty(T, B, 4 * D, **f32),
             w_cat=torch.empty(NZ, D, **f32), b_cat=torch.empty(NZ, **f32), z=torch.empty(T, B, NZ, **f32),
             awe_raw=torch.empty(T, B, C, **f32), gate=torch.empty(T, B, C, **f32), gated=torch.empty(T, B, C, **f32),
             gates_act=torch.empty(T, B, 4 * D, **f32), h_all=torch.empty(T + 1, B, D, **f32),
@@ -284,7 +320,7 @@ class _AttentionDecoderFn(torch.autograd.Function):
             d_pred16 = ctx.box.take(d_pred)          # raises if only a hollow fp32 gradient exists and it is not this tensor
         if d_alphas is not None:
             d_alphas = d_alphas.contiguous().float()
-        want_emb = ctx.needs_input_grad[2]
+        want_emb = ctx.needs_input_grad[2] and emb_w is not None
         want_enc = ctx.needs_input_grad[0]           # encoder_out.requires_grad (--fine_tune_encoder, train.py:39)
         # gradient buffers: fresh tensors, or (data-parallel overlap mode) views of the optimiser's flat gradient buffer laid out
         # in completion order, so that no gather copy is needed and finished buckets can be all-reduced mid-backward

@@ -176,8 +176,8 @@ class DataParallelClipAdam:
         and 1 behind their events, on NCCL's own stream, while the tail of the backward still runs on the compute stream."""
         self.buf.in_place = set(names)
         self._reduced = set()
-        if self._world() == 1:
-            return
+        if self._world() == 1 or set(self.buf.names) - self.buf.in_place:
+            return          # (a parameter without an in-place gradient, e.g. the unused table under use_bert: step() reduces all)
         if self._comm_stream is None:
             self._comm_stream = torch.cuda.Stream()
         for i, ev in enumerate(self._events):

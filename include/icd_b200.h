@@ -235,7 +235,8 @@ typedef struct {
     const float *w_ih, *w_hh, *b_ih, *b_hh;
     const float *h_lin_w, *h_lin_b, *c_lin_w, *c_lin_b;
     const float *f_beta_w, *f_beta_b, *fc_w, *fc_b;
-    const void* emb_w;            /* (V,E) fp32 or fp64 */
+    const void* emb_w;            /* (V,E) fp32 or fp64; NULL => emb_x below already holds pre-computed embeddings (T,B,E)
+                                     (use_bert branch, models/attention.py:242-244), no embedding gradient */
     /* outputs */
     float* predictions;           /* (B,T,V) rows >= batch_size_t are exactly 0 (:253,280)        */
     float* alphas;                /* (B,T,P)                                    (:257,281)        */

@@ -87,13 +87,15 @@ def lstm_cell(x, h, c, w_ih, w_hh, b_ih, b_hh):
 # AttentionDecoder.forward — models/attention.py:218-284
 # --------------------------------------------------------------------------------------
 def attention_decoder_forward(w, encoder_out, encoded_captions, caption_lengths,
-                              dropout_p=0.0, dropout_masks=None, hoist=False):
+                              dropout_p=0.0, dropout_masks=None, hoist=False, embeddings=None):
     """Returns (predictions, encoded_captions, decode_lengths, attention_weights).
 
     dropout_masks: optional list (one per step) of 0/1 keep-masks of shape (batch_size_t, D);
       the activations are multiplied by mask/(1-p) exactly like nn.Dropout in train mode
       (models/attention.py:107,279).  None => no dropout (eval mode / p = 0).
     hoist: compute enc_att once instead of once per step (numerically the same op).
+    embeddings: optional (B, L, E) pre-computed caption embeddings — what ``_create_bert_embeddings`` returns in the
+      reference's use_bert branch (models/attention.py:242-244); they replace the table lookup of :247.
     """
     dtype = w["fc.weight"].dtype
     B = encoder_out.size(0)
@@ -103,7 +105,10 @@ def attention_decoder_forward(w, encoder_out, encoded_captions, caption_lengths,
     P = enc.size(1)
     decode_lengths = [l - 1 for l in caption_lengths]                          # :236
     T = max(decode_lengths)
-    emb = F.embedding(encoded_captions, w["embedding.weight"])                 # :247 (may be fp64 table)
+    if embeddings is not None:
+        emb = embeddings                                                       # :244 (use_bert)
+    else:
+        emb = F.embedding(encoded_captions, w["embedding.weight"])             # :247 (may be fp64 table)
     h, c = init_hidden_state(w, enc)                                           # :250
     predictions = torch.zeros(B, T, V, dtype=dtype)                            # :253
     alphas = torch.zeros(B, T, P, dtype=dtype)                                 # :257
@@ -255,3 +260,26 @@ def beam_search(w, encoder_out, beam_size, start_id, end_id, max_steps=50, trace
         return [start_id, end_id], [], caption_end
     idx = complete_scores.index(max(complete_scores))                          # :127 first max
     return complete_seqs[idx], complete_alpha[idx], caption_end
+
+
+# --------------------------------------------------------------------------------------
+# evaluate() — models/attention.py:516-553, the reference's batch-size-1 validation loop
+# --------------------------------------------------------------------------------------
+def evaluate_reference_style(w, encoder_out, captions, caption_lengths, special_ids):
+    """One decoder call PER IMAGE like the reference's val_loader (batch_size=1, :489-494): -> (losses, hypotheses,
+    references) exactly as the loop appends them (:533, :536-553)."""
+    losses, hypotheses, references = [], [], []
+    for j in range(encoder_out.size(0)):
+        L = caption_lengths[j]
+        caps = captions[j:j + 1, :L]                      # pad_sequence over a single caption adds no padding (:481-483)
+        scores, caps_sorted, decode_lengths, alphas = attention_decoder_forward(w, encoder_out[j:j + 1], caps, [L])
+        loss = attention_loss(scores, caps_sorted, decode_lengths, alphas)                          # :526-531
+        losses.append(float(loss))
+        targets = caps_sorted[:, 1:]
+        img_captions = targets[0].tolist()
+        cleaned = [x for x in img_captions if x not in special_ids]                                 # :539
+        references.append([cleaned for _ in img_captions])                                          # :540
+        _, preds = torch.max(scores, dim=2)                                                         # :544
+        pred = preds.tolist()[0][:decode_lengths[0]]                                                # :548
+        hypotheses.append([x for x in pred if x not in special_ids])                                # :550
+    return losses, hypotheses, references

@@ -669,3 +669,93 @@ def test_bf16_grad_only_loss_is_identical_and_refuses_misuse(cuda):
     loss = attention_caption_loss(preds, cs, dl, alphas, bf16_grad_only=True) + 1e-3 * preds.sum()
     with pytest.raises(RuntimeError, match="bf16_grad_only"):
         loss.backward()
+
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,tol,gtol", [("fp32", 1e-4, 2e-3), ("bf16", 8e-3, 1.5e-1)])
+def test_precomputed_caption_embeddings_use_bert_branch(cuda, precision, tol, gtol):
+    """use_bert=True (models/attention.py:96-100, 242-244): the decoder takes (B, L, 768) pre-computed caption embeddings from
+    ``bert_embedder`` (or ``forward(embeddings=...)``) and runs the same kernels with E = 768; the embedding table is bypassed
+    and receives no gradient.  Against the fp64 oracle's ``embeddings=`` path (pinned to the reference's branch on the CPU)."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.vocabulary import synthetic_vocab
+    V, B, L = 131, 5, 9
+    p = my_att.AttentionDecoderParams()
+    p.attention_dim, p.decoder_dim, p.embed_size, p.dropout, p.use_bert = 48, 32, 768, 0.0, True
+    p.vocab = synthetic_vocab(V)
+    torch.manual_seed(7)
+    dec = my_att.AttentionDecoder(cuda, p)
+    w64 = {k: v.detach().clone().double().requires_grad_(True) for k, v in dec.state_dict().items()}
+    dec = dec.to(cuda)
+    dec.precision = precision
+    g = torch.Generator().manual_seed(8)
+    emb = torch.randn(B, L, 768, generator=g) * 0.3
+    enc = synthetic_features(B, 17)
+    caps, lens = synthetic_caps(dict(B=B, V=V, max_len=L, iseed=17, lengths=[9, 9, 6, 4, 2]))
+    with pytest.raises(NotImplementedError, match="bert_embedder"):
+        dec(enc.to(cuda), caps.to(cuda), lens)
+    calls = []
+    dec.bert_embedder = lambda c: (calls.append(c.shape), emb.to(cuda))[1]
+    preds, _, dl, alphas = dec(enc.to(cuda), caps.to(cuda), lens)
+    assert calls == [caps.shape]
+    o_preds, _, o_dl, o_alphas = O.attention_decoder_forward(w64, enc.double(), caps, lens, embeddings=emb.double())
+    assert dl == o_dl
+    H.assert_close_norm(preds, o_preds, tol, "predictions")
+    H.assert_close_norm(alphas, o_alphas, tol, "alphas")
+    O.attention_loss(preds, caps.to(cuda), dl, alphas).backward()
+    O.attention_loss(o_preds, caps, o_dl, o_alphas).backward()
+    for k, q in dec.named_parameters():
+        if k == "embedding.weight":
+            assert q.grad is None
+        elif k != "attention.full_att.bias":
+            H.assert_close_norm(q.grad, w64[k].grad, gtol, "grad " + k, atol=1e-7)
+    # the explicit keyword gives the same result as the embedder hook
+    with torch.no_grad():
+        p2, _, _, a2 = dec(enc.to(cuda), caps.to(cuda), lens, embeddings=emb.to(cuda))
+    assert torch.equal(p2, preds) and torch.equal(a2, alphas)
+
+
+@pytest.mark.gpu
+def test_batched_evaluate_equals_reference_per_image_loop(cuda):
+    """icd_b200.evaluation (batched port of evaluate(), models/attention.py:454-567): one call over a ragged batch returns the
+    per-image losses, hypotheses and references the reference's batch-size-1 loop produces (oracle restatement of :516-553)."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.evaluation import evaluate, evaluate_batch
+    from icd_b200.vocabulary import END_TOKEN, PAD_TOKEN, START_TOKEN, synthetic_vocab
+    case = dict(H.ATT_CASES["att_small_ragged"])
+    vocab = synthetic_vocab(case["V"])
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams, vocab)
+    w = O.cast_weights(dec.state_dict(), torch.float64)
+    dec = dec.to(cuda).train()                      # evaluate() must switch it to eval itself (:503)
+    enc, caps, lens = H.att_inputs(case)
+    special = [vocab(START_TOKEN), vocab(END_TOKEN), vocab(PAD_TOKEN)]
+    o_losses, o_hyp, o_ref = O.evaluate_reference_style(w, enc.double(), caps, lens, special)
+    dec.eval()
+    losses, hyp, ref, n = evaluate_batch(dec, enc.to(cuda), caps.to(cuda), lens, vocab)
+    assert n == [l - 1 for l in lens] and ref == o_ref
+    for a, b in zip(losses, o_losses):
+        assert abs(a - b) < 1e-4 * abs(b)
+    # hypotheses: identical wherever the oracle's own top-2 margin is not razor thin
+    p64, _, dl64, _ = O.attention_decoder_forward(w, enc.double(), caps, lens)
+    top2 = p64.topk(2, dim=2).values
+    margin_ok = [(top2[j, :dl64[j], 0] - top2[j, :dl64[j], 1]).min().item() > 1e-4 for j in range(case["B"])]
+    assert any(margin_ok)
+    for j in range(case["B"]):
+        if margin_ok[j]:
+            assert hyp[j] == o_hyp[j]
+
+    class Identity(torch.nn.Module):
+        def forward(self, x):
+            return x
+
+    class Args:
+        print_freq = 1
+    dec.train()
+    loader = [(enc[:3], caps[:3], lens[:3]), (enc[3:], caps[3:, :lens[3]], lens[3:])]
+    m = evaluate(cuda, Args, Identity(), dec, loader, vocab, score_fn=lambda r, h: {"n": len(h)})
+    assert not dec.training and m["n"] == case["B"] and len(m["losses"]) == case["B"]
+    for a, b in zip(m["losses"], o_losses):
+        assert abs(a - b) < 1e-4 * abs(b)
+    tok = [l - 1 for l in lens]
+    assert abs(m["avg_loss"] - sum(a * b for a, b in zip(o_losses, tok)) / sum(tok)) < 1e-4

@@ -276,6 +276,85 @@ def test_saved_checkpoint_loads_in_the_unmodified_reference(tmp_path, monkeypatc
         assert torch.equal(opt2.exp_avg_sq[off2:off2 + n], opt.exp_avg_sq[off:off + n]), k
 
 
+@pytest.mark.skipif(not reference_import.reference_available(), reason="needs the reference tree (build container only)")
+def test_oracle_precomputed_embedding_branch_equals_reference_use_bert_branch(monkeypatch):
+    """models/attention.py:242-244, :273 — with ``use_bert`` the loop consumes (B, L, 768) vectors from
+    ``_create_bert_embeddings`` instead of the table lookup.  BERT itself is unavailable offline, so the reference decoder is
+    built with stand-in tokenizer / model classes and its ``_create_bert_embeddings`` is replaced by a function returning
+    fixed vectors: everything downstream is the reference's own code.  The oracle's ``embeddings=`` path must agree exactly,
+    forward and backward."""
+    ns = reference_import.load_reference()
+
+    class _Fake:
+        @classmethod
+        def from_pretrained(cls, name):
+            return cls()
+
+        def to(self, device):
+            return self
+
+        def eval(self):
+            return self
+    monkeypatch.setattr(ns.attention, "BertTokenizer", _Fake)
+    monkeypatch.setattr(ns.attention, "BertModel", _Fake)
+    V, B, L = 53, 4, 7
+    p = ns.AttentionDecoderParams()
+    p.attention_dim, p.decoder_dim, p.embed_size, p.dropout, p.use_bert = 24, 16, 768, 0.5, True
+    p.vocab = reference_import.make_reference_vocab(ns, V)
+    torch.manual_seed(5)
+    dec = ns.AttentionDecoder(torch.device("cpu"), p)
+    dec.eval()
+    g = torch.Generator().manual_seed(6)
+    emb = torch.randn(B, L, 768, generator=g)
+    dec._create_bert_embeddings = lambda caps: emb
+    case = dict(B=B, V=V, max_len=L, iseed=3, lengths=[7, 6, 6, 3])
+    enc, caps, lens = H.att_inputs(case)
+    preds, _, dl, alphas = dec(enc, caps, lens)
+    O.attention_loss(preds, caps, dl, alphas).backward()
+    w = {k: v.detach().clone().requires_grad_(True) for k, v in dec.state_dict().items()}
+    o_preds, _, o_dl, o_alphas = O.attention_decoder_forward(w, enc, caps, lens, embeddings=emb)
+    O.attention_loss(o_preds, caps, o_dl, o_alphas).backward()
+    assert dl == o_dl and torch.equal(preds, o_preds) and torch.equal(alphas, o_alphas)
+    for k, q in dec.named_parameters():
+        if k == "embedding.weight":
+            assert q.grad is None and w[k].grad is None          # the table is bypassed
+        else:
+            assert torch.equal(q.grad, w[k].grad), k
+
+
+@pytest.mark.skipif(not reference_import.reference_available(), reason="needs the reference tree (build container only)")
+def test_oracle_evaluate_restatement_equals_reference_per_image_calls():
+    """oracle.evaluate_reference_style restates the body of evaluate() (models/attention.py:516-553; the function itself builds
+    a COCO dataset and cannot run offline): checked against the unmodified reference decoder called once per image with the
+    literal loss / argmax / cleaning expressions of those lines."""
+    from torch.nn.utils.rnn import pack_padded_sequence
+    ns = reference_import.load_reference()
+    case = H.ATT_CASES["att_small_ragged"]
+    dec = H.build_attention_module(case, ns.AttentionDecoder, ns.AttentionDecoderParams,
+                                   reference_import.make_reference_vocab(ns, case["V"]))
+    dec.eval()
+    vocab = dec.vocab
+    enc, caps, lens = H.att_inputs(case)
+    special = [vocab(ns.vocabulary.START_TOKEN), vocab(ns.vocabulary.END_TOKEN), vocab(ns.vocabulary.PAD_TOKEN)]
+    losses, hyps, refs = O.evaluate_reference_style(O.cast_weights(dec.state_dict(), torch.float32), enc, caps, lens, special)
+    criterion = torch.nn.CrossEntropyLoss()
+    with torch.no_grad():
+        for j in range(case["B"]):
+            c1 = caps[j:j + 1, :lens[j]]
+            scores, cs, dl, aw = dec(enc[j:j + 1], c1, [lens[j]])
+            targets = cs[:, 1:]
+            sp = pack_padded_sequence(scores, dl, batch_first=True).data
+            tp = pack_padded_sequence(targets, dl, batch_first=True).data
+            loss = criterion(sp, tp)
+            loss += ((1. - aw.sum(dim=1)) ** 2).mean()
+            assert abs(loss.item() - losses[j]) < 1e-6
+            img_captions = targets[0].tolist()
+            cleaned = [x for x in img_captions if x not in special]
+            assert refs[j] == list(map(lambda c: cleaned, img_captions))
+            _, pr = torch.max(scores, dim=2)
+            assert hyps[j] == [x for x in pr.tolist()[0][:dl[0]] if x not in special]
+
+
 def test_oracle_loss_glue_equals_pack_padded_sequence_expression():
     """The oracle restates models/attention.py:401-414 without pack_padded_sequence (explicit time-major gather of the
     first batch_size_t rows); check it against the reference's literal expression on random ragged, sorted lengths,
