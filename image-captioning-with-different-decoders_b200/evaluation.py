@@ -39,8 +39,9 @@ def evaluate_batch(decoder, img_features, captions, caption_lengths, vocab):
     special = [vocab(START_TOKEN), vocab(END_TOKEN), vocab(PAD_TOKEN)]
     references, hypotheses = [], []
     for j in range(B):
-        cleaned = [w for w in tlist[j] if w not in special]                                                # :538-539
-        references.append([cleaned for _ in tlist[j]])                                                     # :540 (sic: one copy per position)
+        row = tlist[j][:caption_lengths[j] - 1]             # the reference's batch of ONE carries no padding (:481-483)
+        cleaned = [w for w in row if w not in special]                                                     # :538-539
+        references.append([cleaned for _ in row])                                                          # :540 (sic: one copy per position)
         hypotheses.append([w for w in preds[j][:decode_lengths[j]] if w not in special])                   # :548-551
     return losses, hypotheses, references, list(decode_lengths)
 
