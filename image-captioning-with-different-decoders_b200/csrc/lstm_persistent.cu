@@ -392,6 +392,8 @@ int plan_smem(int nkb, int red_bytes, int* stages) {
     return fixed + s * LP_A_BYTES;
 }
 
+int g_bwd_launch_mode = 0;      // 0 = not launched yet, 1 = cooperative + cluster launch accepted, 2 = plain cluster launch
+
 bool persistent_enabled() {
     static const bool on = [] { const char* e = getenv("ICD_LSTM_PERSISTENT"); return !(e && e[0] == '0'); }();
     return on;
@@ -423,12 +425,14 @@ int launch_seq(const LstmSeqArgs& a0, const __nv_bfloat16* A16, int a_rows, int 
     attr[1].val.clusterDim.x = 4; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = BWD ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_seq_kernel<BWD>, tmA, a);
+    if (BWD && e == cudaSuccess) g_bwd_launch_mode = 1;
     if (e != cudaSuccess && BWD) {
         // a driver that refuses cooperative + cluster launches: the grid (<= 148 CTAs, one per SM, launched on an otherwise
         // ordered stream) is co-resident in practice; the barrier's spin limit turns a violation into a fault, not a hang
         (void)cudaGetLastError();
         cfg.attrs = attr + 1; cfg.numAttrs = 1;
         e = cudaLaunchKernelEx(&cfg, lstm_seq_kernel<BWD>, tmA, a);
+        if (e == cudaSuccess) g_bwd_launch_mode = 2;
     }
     ICD_CUDA(e);
     ICD_LAUNCH_CHECK();
@@ -470,6 +474,7 @@ int icd_lstm_seq_bwd_persistent(int B, int L, int H, const float* w_hh, const fl
 
 // ---- C ABI (include/icd_b200.h): the LSTM recurrence on its own, for callers that hoist the input contraction themselves ----
 extern "C" int icd_lstm_seq_supported(int B, int L, int H) { return icd_lstm_seq_persistent_ok(B, L, H); }
+extern "C" int icd_lstm_seq_bwd_launch_mode(void) { return g_bwd_launch_mode; }
 
 extern "C" int icd_lstm_seq_fwd(int B, int L, int H, const float* w_hh, const float* xg, float* gates_act, float* c_all,
                                 float* h_all, float* hout, void* h16, void* hout16, void* barrier_ws, void* stream) {

@@ -361,6 +361,9 @@ ICD_API int icd_baseline_decoder_bwd(const icd_base_desc_t* d, void* stream);
  * otherwise callers keep a per-step launch chain (icd_baseline_decoder_fwd does that by itself).
  * ---------------------------------------------------------------------------------------------- */
 ICD_API int icd_lstm_seq_supported(int B, int L, int H);
+/* diagnostic: how the last backward recurrence was launched — 0 not yet, 1 cooperative + 4-CTA clusters (co-residency
+ * guaranteed by the driver), 2 plain cluster launch (a driver that refuses the combination; co-resident in practice) */
+ICD_API int icd_lstm_seq_bwd_launch_mode(void);
 ICD_API int icd_lstm_seq_fwd(int B, int L, int H, const float* w_hh, const float* xg, float* gates_act, float* c_all,
                      float* h_all, float* hout, void* h16, void* hout16, void* barrier_ws, void* stream);
 ICD_API int icd_lstm_seq_bwd(int B, int L, int H, const float* w_hh, const float* d_hout, const float* gates_act,

@@ -431,6 +431,9 @@ def test_persistent_lstm_recurrence_matches_torch(cuda, B, L, H):
     dg, dg16 = ops.lstm_seq_bwd(w_hh.to(cuda), d_hout.to(cuda), out["gates_act"], out["c_all"])
     H_.assert_close_norm(dg, x64.grad, 2e-2, "d gates_pre")            # xg enters the gates additively: d xg == dg
     H_.assert_close_norm(dg16.float().view(L, B, 4 * H), dg, 4e-3, "dg16")
+    from icd_b200._lib import lib
+    print("lstm_seq backward launch mode:", lib().icd_lstm_seq_bwd_launch_mode())
+    assert lib().icd_lstm_seq_bwd_launch_mode() in (1, 2)
     # run-to-run determinism (fixed summation order inside one tcgen05 accumulator)
     out2 = ops.lstm_seq_fwd(w_hh.to(cuda), xg.to(cuda))
     assert torch.equal(out["hout"], out2["hout"]) and torch.equal(out["c_all"], out2["c_all"])
