@@ -139,8 +139,8 @@ int baseline_bwd_bf16(const icd_base_desc_t* d, cudaStream_t s) {
             if (L > 1) {
                 int32_t bt[ICD_MAX_STEPS];
                 for (int t = 0; t < ICD_MAX_STEPS; ++t) bt[t] = B;
-                ICD_TRY(icd_embed_scatter_add(d->d_emb_w, d->emb_is_f64, d->captions, B, L, L - 1, E, bt,
-                                              d->d_x + (size_t)B * E, s));
+                ICD_TRY(icd_embed_scatter_add(d->d_emb_w, d->emb_is_f64, d->captions, B, L, L - 1, E, V, bt,
+                                              d->d_x + (size_t)B * E, s, d->d_hout, (int64_t)sizeof(float) * B * L * H));   // d_hout: free after BPTT
             }
         }
     }
@@ -232,8 +232,8 @@ extern "C" int icd_baseline_decoder_bwd(const icd_base_desc_t* d, void* stream) 
             if (L > 1) {
                 int32_t bt[ICD_MAX_STEPS];
                 for (int t = 0; t < ICD_MAX_STEPS; ++t) bt[t] = B;
-                ICD_TRY(icd_embed_scatter_add(d->d_emb_w, d->emb_is_f64, d->captions, B, L, L - 1, E, bt,
-                                              d->d_x + (size_t)B * E, s));
+                ICD_TRY(icd_embed_scatter_add(d->d_emb_w, d->emb_is_f64, d->captions, B, L, L - 1, E, V, bt,
+                                              d->d_x + (size_t)B * E, s, d->d_hout, (int64_t)sizeof(float) * B * L * H));   // d_hout: free after BPTT
             }
         }
     }

@@ -134,8 +134,13 @@ int icd_colsum_bf16(const void* X16, int64_t ld, int64_t M, int N, const uint8_t
                     cudaStream_t s);
 int icd_embed_gather(const void* table, int is_f64, const int64_t* captions, int B, int L, int T, int E, int V,
                      float* out /* (T,B,E) */, cudaStream_t s);
-int icd_embed_scatter_add(void* d_table, int is_f64, const int64_t* captions, int B, int L, int T, int E,
-                          const int32_t* bt_host, const float* d_x /* (T,B,E) */, cudaStream_t s);
+// d_table (V,E) += rows of d_x scattered by token id.  With a workspace of icd_embed_scatter_ws_bytes(B, T) bytes the sum
+// is DETERMINISTIC (rows sorted by (token, row), one CTA per token adds them in row order); without it (or with
+// ICD_EMBED_ATOMIC=1) atomics accumulate in arrival order.
+int64_t icd_embed_scatter_ws_bytes(int B, int T);
+int icd_embed_scatter_add(void* d_table, int is_f64, const int64_t* captions, int B, int L, int T, int E, int V,
+                          const int32_t* bt_host, const float* d_x /* (T,B,E) */, cudaStream_t s,
+                          void* ws = nullptr, int64_t ws_bytes = 0);
 int icd_lstm_pointwise_fwd(int rows, int D, const float* gates_pre, const float* c_prev,
                            float* gates_act, float* c_new, float* h_new,
                            float* hdrop, int64_t hdrop_row_stride, const uint8_t* mask, float scale,

@@ -227,7 +227,9 @@ extern "C" int icd_attention_decoder_bwd(const icd_att_desc_t* d, void* stream) 
         ICD_TRY(icd_gemm_simple(prec, dG, NZ, 1, d->w_ih, 1, E + C, d->d_emb_x, E, TB, E, 4 * D,
                                 nullptr, nullptr, nullptr, 0, nullptr, 0, nullptr, 0.f, s));
         ICD_CUDA(cudaMemsetAsync(d->d_emb_w, 0, (d->emb_is_f64 ? sizeof(double) : sizeof(float)) * (size_t)V * E, s));
-        ICD_TRY(icd_embed_scatter_add(d->d_emb_w, d->emb_is_f64, d->captions, B, d->L, T, E, d->bt_host, d->d_emb_x, s));
+        // (d_gated is free after the time loop: it serves as the sort workspace of the deterministic scatter)
+        ICD_TRY(icd_embed_scatter_add(d->d_emb_w, d->emb_is_f64, d->captions, B, d->L, T, E, V, d->bt_host, d->d_emb_x, s,
+                                      d->d_gated, (int64_t)sizeof(float) * B * C));
     }
     if (d->ev_rec_ready) ICD_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_rec_ready), s));
     // attention projections: d_att_enc for all steps at once, full_att grads, then enc_att grads (:54)

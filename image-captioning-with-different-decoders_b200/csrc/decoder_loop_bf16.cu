@@ -271,7 +271,9 @@ int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
     if (d->d_emb_w) {
         MMX(dG16, NZ, 0, u.WihE, u.ldE, 1, d->d_emb_x, E, TB, E, 4 * D, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
         ICD_CUDA(cudaMemsetAsync(d->d_emb_w, 0, (d->emb_is_f64 ? sizeof(double) : sizeof(float)) * (size_t)V * E, s));
-        ICD_TRY(icd_embed_scatter_add(d->d_emb_w, d->emb_is_f64, d->captions, B, d->L, T, E, d->bt_host, d->d_emb_x, s));
+        // (d_gated is free after the time loop: it serves as the sort workspace of the deterministic scatter)
+        ICD_TRY(icd_embed_scatter_add(d->d_emb_w, d->emb_is_f64, d->captions, B, d->L, T, E, V, d->bt_host, d->d_emb_x, s,
+                                      d->d_gated, (int64_t)sizeof(float) * B * C));
     }
     if (d->ev_rec_ready) ICD_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_rec_ready), s)); // recurrent gradients final
     // attention projections: d_att_enc for all steps at once (bf16 only: it is just the A operand of the next

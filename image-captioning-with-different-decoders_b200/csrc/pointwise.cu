@@ -6,6 +6,7 @@
 //   row-wise cross-entropy forward+backward (models/attention.py:411).
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace {
 
@@ -178,6 +179,69 @@ __global__ void embed_scatter_add_kernel(TT* __restrict__ d_table, const long lo
     TT* dst = d_table + tok * E;
     const float* src = d_x + (long long)row * E;
     for (int e = threadIdx.x; e < E; e += blockDim.x) atomicAdd(dst + e, (TT)src[e]);
+}
+
+// ---- deterministic embedding gradient: sort the (token, row) pairs, then one CTA per token adds its rows in row order -------
+// (the atomic variant above accumulates in arrival order: run-to-run different in the last bits, and slow in fp64)
+constexpr int EMB_SORT_N = 16384;                   // keys per chunk: 128 KB of shared memory
+constexpr unsigned long long EMB_KEY_NONE = ~0ull;
+
+// chunk c sorts rows [c * EMB_SORT_N, ...) of the (T, B) row space by (token id, row index): key = token << 32 | row; rows
+// that are inactive at their step (b >= batch_size_t) get the sentinel and sink to the end.  Bitonic network in shared memory.
+__global__ void __launch_bounds__(1024) embed_sort_kernel(const long long* __restrict__ captions, int B, int L, int T, int V,
+                                                           const BtPack bt, int n_sort, unsigned long long* __restrict__ keys) {
+    extern __shared__ unsigned long long s_key[];
+    const long long base = (long long)blockIdx.x * EMB_SORT_N;
+    const long long N = (long long)T * B;
+    for (int i = threadIdx.x; i < n_sort; i += blockDim.x) {
+        const long long r = base + i;
+        unsigned long long key = EMB_KEY_NONE;
+        if (r < N) {
+            const int t = (int)(r / B), b = (int)(r % B);
+            if (b < bt.v[t]) {
+                const long long tok = captions[(long long)b * L + t];
+                if (tok < 0 || tok >= V) __trap();
+                key = ((unsigned long long)tok << 32) | (unsigned long long)(unsigned int)r;
+            }
+        }
+        s_key[i] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n_sort; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_sort; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = s_key[i], b2 = s_key[ixj];
+                    const bool asc = (i & k) == 0;
+                    if ((a > b2) == asc) { s_key[i] = b2; s_key[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n_sort; i += blockDim.x) keys[base + i] = s_key[i];
+}
+
+// one CTA per sorted position; only segment heads (first occurrence of a token in the chunk) work: they add the segment's
+// rows in ascending row order and accumulate into the table row (chunks are launched one after the other: no two CTAs ever
+// touch the same table row concurrently, and the order of every sum is fixed)
+template <typename TT>
+__global__ void __launch_bounds__(128) embed_segment_reduce_kernel(const unsigned long long* __restrict__ keys, int n_sort,
+                                                                    const float* __restrict__ d_x, TT* __restrict__ d_table, int E) {
+    const int i = blockIdx.x;
+    const unsigned long long key = keys[i];
+    if (key == EMB_KEY_NONE) return;
+    const unsigned int tok = (unsigned int)(key >> 32);
+    if (i > 0 && (unsigned int)(keys[i - 1] >> 32) == tok) return;
+    int end = i + 1;
+    while (end < n_sort && (unsigned int)(keys[end] >> 32) == tok && keys[end] != EMB_KEY_NONE) ++end;
+    TT* dst = d_table + (long long)tok * E;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        TT acc = (TT)0;
+        for (int j = i; j < end; ++j) acc += (TT)d_x[(long long)(unsigned int)(keys[j] & 0xffffffffull) * E + e];
+        dst[e] += acc;
+    }
 }
 
 // Philox4x32-10 counter-based generator (Salmon et al. 2011).
@@ -426,12 +490,44 @@ int icd_embed_gather(const void* table, int is_f64, const int64_t* captions, int
     return 0;
 }
 
-int icd_embed_scatter_add(void* d_table, int is_f64, const int64_t* captions, int B, int L, int T, int E,
-                          const int32_t* bt_host, const float* d_x, cudaStream_t s) {
+int64_t icd_embed_scatter_ws_bytes(int B, int T) {
+    const int64_t N = (int64_t)B * T;
+    const int64_t chunks = (N + EMB_SORT_N - 1) / EMB_SORT_N;
+    int64_t n_sort = EMB_SORT_N;
+    if (chunks == 1) { n_sort = 32; while (n_sort < N) n_sort <<= 1; }        // one chunk: the next power of two is enough
+    return chunks * n_sort * (int64_t)sizeof(unsigned long long);
+}
+
+int icd_embed_scatter_add(void* d_table, int is_f64, const int64_t* captions, int B, int L, int T, int E, int V,
+                          const int32_t* bt_host, const float* d_x, cudaStream_t s, void* ws, int64_t ws_bytes) {
     if (B * T == 0) return 0;
     ICD_CHECK_ARG(T <= ICD_MAX_STEPS, "embed_scatter_add: T too large");
     BtPack pack;
     for (int t = 0; t < ICD_MAX_STEPS; ++t) pack.v[t] = t < T ? bt_host[t] : 0;
+    static const bool atomic_mode = [] { const char* e = getenv("ICD_EMBED_ATOMIC"); return e && e[0] == '1'; }();
+    if (!atomic_mode && ws && ws_bytes >= icd_embed_scatter_ws_bytes(B, T)) {
+        // deterministic path: sort (token, row) per chunk of 16384 rows, then segment sums in row order, chunk after chunk
+        const long long N = (long long)B * T;
+        const int chunks = (int)((N + EMB_SORT_N - 1) / EMB_SORT_N);
+        int n_sort = EMB_SORT_N;
+        if (chunks == 1) { n_sort = 32; while (n_sort < N) n_sort <<= 1; }
+        const size_t smem = (size_t)n_sort * sizeof(unsigned long long);
+        static size_t configured = 48 * 1024;
+        if (smem > configured) {
+            ICD_CUDA(cudaFuncSetAttribute(embed_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws);
+        embed_sort_kernel<<<chunks, 1024, smem, s>>>((const long long*)captions, B, L, T, V, pack, n_sort, keys);
+        ICD_LAUNCH_CHECK();
+        for (int c = 0; c < chunks; ++c) {
+            const unsigned long long* kc = keys + (size_t)c * EMB_SORT_N;
+            if (is_f64) embed_segment_reduce_kernel<double><<<n_sort, 128, 0, s>>>(kc, n_sort, d_x, (double*)d_table, E);
+            else        embed_segment_reduce_kernel<float><<<n_sort, 128, 0, s>>>(kc, n_sort, d_x, (float*)d_table, E);
+            ICD_LAUNCH_CHECK();
+        }
+        return 0;
+    }
     if (is_f64) embed_scatter_add_kernel<double><<<B * T, 128, 0, s>>>((double*)d_table, (const long long*)captions, B, L, T, E, pack, d_x);
     else        embed_scatter_add_kernel<float><<<B * T, 128, 0, s>>>((float*)d_table, (const long long*)captions, B, L, T, E, pack, d_x);
     ICD_LAUNCH_CHECK();

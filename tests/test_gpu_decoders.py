@@ -759,3 +759,33 @@ def test_batched_evaluate_equals_reference_per_image_loop(cuda):
         assert abs(a - b) < 1e-4 * abs(b)
     tok = [l - 1 for l in lens]
     assert abs(m["avg_loss"] - sum(a * b for a, b in zip(o_losses, tok)) / sum(tok)) < 1e-4
+
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("glove", [False, True])
+def test_embedding_gradient_is_run_to_run_deterministic(cuda, glove):
+    """The embedding-table gradient (models/attention.py:247 backward; fp64 for the GloVe table) is a scatter-add over
+    repeated token ids: rows are sorted by (token, row) and each token's rows are added in row order by one CTA, so two runs
+    give bit-identical gradients (atomics would not), and the values match the fp64 oracle."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.vocabulary import synthetic_vocab
+    V = 23                                                   # few tokens: every id repeats many times
+    case = dict(B=40, V=V, A=48, D=32, E=(300 if glove else 24), max_len=12, lengths=[12] * 40, wseed=4, iseed=9,
+                dropout=0.0, train=False, fine_tune_embedding=True, glove=glove)
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams, synthetic_vocab(V))
+    w64 = {k: v.detach().clone().double().requires_grad_(True) for k, v in dec.state_dict().items()}
+    dec = dec.to(cuda)
+    enc = synthetic_features(case["B"], case["iseed"])
+    caps, lens = synthetic_caps(case)
+    grads = []
+    for _ in range(3):
+        dec.zero_grad()
+        preds, _, dl, alphas = dec(enc.to(cuda), caps.to(cuda), lens)
+        O.attention_loss(preds, caps.to(cuda), dl, alphas).backward()
+        grads.append(dec.embedding.weight.grad.clone())
+    assert grads[0].dtype == (torch.float64 if glove else torch.float32)
+    assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+    p64, _, dl64, a64 = O.attention_decoder_forward(w64, enc.double(), caps, lens)
+    O.attention_loss(p64, caps, dl64, a64).backward()
+    H.assert_close_norm(grads[0], w64["embedding.weight"].grad, 1e-4, "embedding gradient")
