@@ -26,7 +26,7 @@ constexpr int KMAX = 8;          // beam slots per image supported by the top-k 
 
 struct BeamWs {
     float *att_enc, *mean, *h0, *c0, *h, *c, *h_tmp, *c_tmp, *w_cat, *b_cat, *emb_x, *z, *gated, *gates_pre,
-          *gates_act_unused, *logits, *alpha_steps, *score, *best_score;
+          *gates_act_unused, *logits, *alpha_steps, *score, *best_score, *embg;
     int *img_index, *prev_word, *k_live, *src, *parent, *word, *best_step, *best_parent;
     int *slot_img, *slot_img_tmp, *k_live_tmp, *new_slot, *n_live, *word_tmp;   // n_live[0] = live slots, [1] = live rows
     int *row_off[2];                                                            // slot -> first state row (ping-pong per step)
@@ -55,6 +55,7 @@ size_t carve(const icd_beam_desc_t* d, BeamWs* w, char* base) {
     TAKE_F(w_cat, (size_t)NZ * D) TAKE_F(b_cat, (size_t)NZ)
     TAKE_F(emb_x, R * E) TAKE_F(z, R * NZ) TAKE_F(gated, R * C) TAKE_F(gates_pre, R * 4 * D)
     TAKE_F(logits, R * V)
+    TAKE_F(embg, d->emb_is_f64 ? 0 : (size_t)V * 4 * D)       // embedding row x W_ih[:, :E]^T + b_ih for EVERY token, once per call
     TAKE_F(alpha_steps, S * R * P)
     TAKE_F(score, R) TAKE_F(score_tmp, R) TAKE_F(best_score, (size_t)d->n_img)
 #undef TAKE_F
@@ -94,17 +95,18 @@ __global__ void beam_init_kernel(int n_img, int k, int D, int start_id, const fl
                                  float* __restrict__ score, int* __restrict__ k_live, float* __restrict__ best_score,
                                  int* __restrict__ best_step, int* __restrict__ best_parent,
                                  int* __restrict__ slot_img, int* __restrict__ n_live, int* __restrict__ row_off) {
+    // The reference starts every image with k IDENTICAL beams (:44-62) and takes the first top-k from beam 0 only (:78-79).
+    // Here step 1 runs ONE state row per image (k_live = 1); the first top-k still selects k candidates from it, after which
+    // the slot holds up to k distinct rows.  Same results, a fifth of the first (and most expensive) step's work.
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long R = (long long)n_img * k;
-    if (i < R * D) {
-        const long long r = i / D; const int dd = (int)(i % D);
-        const long long img = r / k;
-        h[i] = h0[img * D + dd];
-        c[i] = c0[img * D + dd];
+    if (i < (long long)n_img * D) { h[i] = h0[i]; c[i] = c0[i]; }
+    if (i < R) img_index[i] = (int)(i / k);
+    if (i < n_img) {
+        prev_word[i] = start_id; tok64[i] = start_id; score[i] = 0.f;                                           // :47-52
+        k_live[i] = 1; best_score[i] = -INFINITY; best_step[i] = 0; best_parent[i] = 0; slot_img[i] = (int)i; row_off[i] = (int)i;
     }
-    if (i < R) { img_index[i] = (int)(i / k); prev_word[i] = start_id; tok64[i] = start_id; score[i] = 0.f; }   // :47-52
-    if (i < n_img) { k_live[i] = k; best_score[i] = -INFINITY; best_step[i] = 0; best_parent[i] = 0; slot_img[i] = (int)i; row_off[i] = (int)i * k; }
-    if (i == 0) { n_live[0] = n_img; n_live[1] = (int)R; }
+    if (i == 0) { n_live[0] = n_img; n_live[1] = n_img; }
 }
 
 __device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
@@ -131,86 +133,75 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
     const int slot = blockIdx.x;
     if (slot >= n_live[0]) return;                                   // trace rows of finished images were preset to -1
     const int img = slot_img[slot];
-    const int kl = k_live[slot];                                     // > 0: empty slots were compacted away
-    const int nrows = (step == 1) ? 1 : kl;                                                  // :78-82
+    const int kl = k_live[slot];                                     // live state rows of this slot (> 0; 1 at step 1)
+    const int nrows = kl;                                                                    // :78-82
+    const int ksel = (step == 1) ? k : kl;                           // candidates to select (:79: k from the single first row)
     const int row0 = row_off[slot];                                  // first state row of this slot
     const float* lg = logits + (long long)row0 * V;
-    // rows are streamed with 64-bit loads, 4 in flight per thread (rows are 8-byte aligned when V is even)
     const bool even = (V & 1) == 0;
     const int V2 = V >> 1;
     // thread-local top-KMAX over this thread's slice of the flattened (nrows*V) candidates (flat index f = i*V + v)
     float tv[KMAX]; int ti[KMAX];
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
-    auto consider = [&](float xv, float rmax, float rlsum, float rscore, int f) {
-        const float lp = (xv - rmax) - rlsum;                       // log_softmax value
-        const float v = rscore + lp;                                // :76
-        if (better(v, f, tv[KMAX - 1], ti[KMAX - 1])) {
-            tv[KMAX - 1] = v; ti[KMAX - 1] = f;
-#pragma unroll
-            for (int j = KMAX - 1; j > 0; --j) {
-                if (better(tv[j], ti[j], tv[j - 1], ti[j - 1])) {
-                    const float a = tv[j]; tv[j] = tv[j - 1]; tv[j - 1] = a;
-                    const int b = ti[j]; ti[j] = ti[j - 1]; ti[j - 1] = b;
-                }
-            }
-        }
-    };
-    for (int i = 0; i < nrows; ++i) {                                                        // :74 log_softmax
+    for (int i = 0; i < nrows; ++i) {
+        // ONE streaming pass per row: online log-sum-exp (running max m, sum s of exp(x - m)) and, in the same pass, the
+        // thread's top-KMAX RAW logits of the row.  log_softmax + score is monotone in the logit within a row, so the row's
+        // best candidates are its largest logits; their values v = score + (x - max) - log(sum) (:74-76) are formed once the
+        // row statistics are known and merged into the thread's flat top-KMAX by (v, lower flat index first).  (Selecting by
+        // x instead of v inside a row could only differ if >= KMAX - k + 1 distinct logits of ONE thread's slice collapsed
+        // onto the same fp32 v at the selection boundary.)
         const float* x = lg + (long long)i * V;
         const float2* x2 = reinterpret_cast<const float2*>(x);
-        float m = -INFINITY;
-        if (even) {
-            int j = threadIdx.x;
-            for (; j + 3 * 256 < V2; j += 4 * 256) {
-                float2 a[4];
+        float m = -INFINITY, ssum = 0.f;
+        float rx[KMAX]; int rv[KMAX];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) a[u] = x2[j + u * 256];
+        for (int j = 0; j < KMAX; ++j) { rx[j] = -INFINITY; rv[j] = 0x7fffffff; }
+        auto visit = [&](float xv, int v) {
+            if (xv > m) { ssum = ssum * expf(m - xv) + 1.f; m = xv; } else ssum += expf(xv - m);
+            if (better(xv, v, rx[KMAX - 1], rv[KMAX - 1])) {
+                rx[KMAX - 1] = xv; rv[KMAX - 1] = v;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) m = fmaxf(m, fmaxf(a[u].x, a[u].y));
-            }
-            for (; j < V2; j += 256) { const float2 a = x2[j]; m = fmaxf(m, fmaxf(a.x, a.y)); }
-        } else {
-            for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, x[v]);
-        }
-        m = block_max(m, s_red);
-        float sum = 0.f;
-        if (even) {
-            int j = threadIdx.x;
-            for (; j + 3 * 256 < V2; j += 4 * 256) {
-                float2 a[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) a[u] = x2[j + u * 256];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) sum += expf(a[u].x - m) + expf(a[u].y - m);
-            }
-            for (; j < V2; j += 256) { const float2 a = x2[j]; sum += expf(a.x - m) + expf(a.y - m); }
-        } else {
-            for (int v = threadIdx.x; v < V; v += blockDim.x) sum += expf(x[v] - m);
-        }
-        sum = block_sum(sum, s_red);
-        // candidate pass for this row right away: its 38 KB are still in L1 from the two softmax passes
-        const float rmax = m, rlsum = logf(sum), rscore = score[row0 + i];
-        const int f0 = i * V;
-        if (even) {
-            int j = threadIdx.x;
-            for (; j + 3 * 256 < V2; j += 4 * 256) {
-                float2 a[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) a[u] = x2[j + u * 256];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    consider(a[u].x, rmax, rlsum, rscore, f0 + 2 * (j + u * 256));
-                    consider(a[u].y, rmax, rlsum, rscore, f0 + 2 * (j + u * 256) + 1);
+                for (int j = KMAX - 1; j > 0; --j) {
+                    if (better(rx[j], rv[j], rx[j - 1], rv[j - 1])) {
+                        const float a = rx[j]; rx[j] = rx[j - 1]; rx[j - 1] = a;
+                        const int b2 = rv[j]; rv[j] = rv[j - 1]; rv[j - 1] = b2;
+                    }
                 }
             }
-            for (; j < V2; j += 256) {
-                const float2 a = x2[j];
-                consider(a.x, rmax, rlsum, rscore, f0 + 2 * j);
-                consider(a.y, rmax, rlsum, rscore, f0 + 2 * j + 1);
+        };
+        if (even) {
+            int j = threadIdx.x;
+            for (; j + 3 * 256 < V2; j += 4 * 256) {
+                float2 a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = x2[j + u * 256];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { visit(a[u].x, 2 * (j + u * 256)); visit(a[u].y, 2 * (j + u * 256) + 1); }
             }
+            for (; j < V2; j += 256) { const float2 a = x2[j]; visit(a.x, 2 * j); visit(a.y, 2 * j + 1); }
         } else {
-            for (int v = threadIdx.x; v < V; v += blockDim.x) consider(x[v], rmax, rlsum, rscore, f0 + v);
+            for (int v = threadIdx.x; v < V; v += blockDim.x) visit(x[v], v);
+        }
+        const float rmax = block_max(m, s_red);
+        const float sum = block_sum((m == -INFINITY) ? 0.f : ssum * expf(m - rmax), s_red);
+        const float rlsum = logf(sum), rscore = score[row0 + i];
+        const int f0 = i * V;
+#pragma unroll
+        for (int q = 0; q < KMAX; ++q) {
+            if (rv[q] == 0x7fffffff) continue;
+            const float v = rscore + ((rx[q] - rmax) - rlsum);
+            const int f = f0 + rv[q];
+            if (better(v, f, tv[KMAX - 1], ti[KMAX - 1])) {
+                tv[KMAX - 1] = v; ti[KMAX - 1] = f;
+#pragma unroll
+                for (int j = KMAX - 1; j > 0; --j) {
+                    if (better(tv[j], ti[j], tv[j - 1], ti[j - 1])) {
+                        const float a = tv[j]; tv[j] = tv[j - 1]; tv[j - 1] = a;
+                        const int b2 = ti[j]; ti[j] = ti[j - 1]; ti[j - 1] = b2;
+                    }
+                }
+            }
         }
     }
 #pragma unroll
@@ -218,7 +209,7 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
     __syncthreads();
     if (threadIdx.x < 32) {                                          // warp 0: kl rounds of arg-best
         const int lane = threadIdx.x;
-        for (int round = 0; round < kl; ++round) {
+        for (int round = 0; round < ksel; ++round) {
             float bv = -INFINITY; int bi = 0x7fffffff, bpos = -1;
             for (int q = lane; q < 256 * KMAX; q += 32)
                 if (better(s_cv[q], s_ci[q], bv, bi)) { bv = s_cv[q]; bi = s_ci[q]; bpos = q; }
@@ -237,7 +228,7 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
     if (threadIdx.x == 0) {
         int nlive = 0;
         float bs = best_score[img];
-        for (int j = 0; j < kl; ++j) {
+        for (int j = 0; j < ksel; ++j) {
             const int idx = s_topi[j];
             const float val = s_topv[j];
             const int prev = idx / V, next = idx % V;                                        // :85-86
@@ -375,6 +366,22 @@ __global__ void gather_rows_kernel(const float* __restrict__ table_f32, const do
         out[r * E + e] = table_f64 ? (float)table_f64[t * E + e] : table_f32[t * E + e];
 }
 
+// gates_pre[r, :] = embg[token_r, :] (= embedding(token) W_ih[:, :E]^T + b_ih, precomputed for the whole vocabulary) + the
+// h W_hh^T + b_hh part of z: what the per-step embedding contraction produced, as one gather (:65, :70-71).
+__global__ void beam_gates_init_kernel(const float* __restrict__ embg, const long long* __restrict__ tok, int G,
+                                       const float* __restrict__ zhh, long long ldz, float* __restrict__ gates_pre,
+                                       const int* __restrict__ n_live) {
+    const long long r = blockIdx.x;
+    if (r >= n_live[1]) return;
+    const float4* src = reinterpret_cast<const float4*>(embg + tok[r] * G);
+    const float4* zz = reinterpret_cast<const float4*>(zhh + r * ldz);
+    float4* dst = reinterpret_cast<float4*>(gates_pre + r * G);
+    for (int e = threadIdx.x; e < (G >> 2); e += blockDim.x) {
+        const float4 a = src[e], b = zz[e];
+        dst[e] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+}
+
 }  // namespace
 
 // y[rows, N] = x[rows, K] * W[N, K]^T (+ bias + add + beta*y): fp32 FMA kernel, or the fp32-grade tensor-core tier with the
@@ -432,6 +439,17 @@ extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
         ICD_TRY(icd_split3_bf16(d->c_lin_w, C, D, C, w.x3_Wc, 1, s));
         ICD_TRY(icd_split3_bf16(d->fc_w, D, V, D, w.x3_Wfc, 1, s));
     }
+    // embedding -> gate contribution for the whole vocabulary, once per call: V rows instead of (live rows) x (steps) rows, and
+    // no per-step activation split of the embedding rows (fp32 tables; an fp64 GloVe table keeps the per-step contraction)
+    const bool use_embg = !d->emb_is_f64 && (NZ % 4 == 0) && ((A + C) % 4 == 0);
+    if (use_embg) {
+        const int VC = 4096;                                 // rows per pass: bounds the split scratch (x3_act holds >= 64*P rows of C)
+        for (int v0 = 0; v0 < V; v0 += VC) {
+            const int nv = V - v0 < VC ? V - v0 : VC;
+            ICD_TRY(beam_mm(prec, w, (const float*)d->emb_w + (size_t)v0 * E, E, nv, E, d->w_ih, E + C, w.x3_WihE,
+                            w.embg + (size_t)v0 * 4 * D, 4 * D, 4 * D, d->b_ih, nullptr, 0, 0.f, s));
+        }
+    }
     for (int i0 = 0; i0 < n_img; i0 += X3_IMG_CHUNK) {       // att_enc = enc_att(enc), once per image
         const int ni = n_img - i0 < X3_IMG_CHUNK ? n_img - i0 : X3_IMG_CHUNK;
         ICD_TRY(beam_mm(prec, w, d->enc + (size_t)i0 * P * C, C, ni * P, C, d->enc_att_w, C, w.x3_We,
@@ -456,16 +474,22 @@ extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
         float* alpha_s = w.alpha_steps + (size_t)(step - 1) * R * P;
         const int* row_off = w.row_off[(step - 1) & 1];
         int* row_off_next = w.row_off[step & 1];
-        gather_rows_kernel<<<(unsigned)R, 128, 0, s>>>(d->emb_is_f64 ? nullptr : (const float*)d->emb_w,
-                                                       d->emb_is_f64 ? (const double*)d->emb_w : nullptr,
-                                                       w.tok64, E, w.emb_x, w.n_live);       // :65
-        ICD_LAUNCH_CHECK();
+        if (!use_embg) {
+            gather_rows_kernel<<<(unsigned)R, 128, 0, s>>>(d->emb_is_f64 ? nullptr : (const float*)d->emb_w,
+                                                           d->emb_is_f64 ? (const double*)d->emb_w : nullptr,
+                                                           w.tok64, E, w.emb_x, w.n_live);       // :65
+            ICD_LAUNCH_CHECK();
+        }
         ICD_TRY(beam_mm(prec, w, w.h, D, (int)R, D, w.w_cat, D, w.x3_Wcat, w.z, NZ, NZ, w.b_cat, nullptr, 0, 0.f, s, live_rows));
         // :66-69 — one CTA per live slot serves all of its live beams (features read once per image and step)
         ICD_TRY(icd_attention_step_fwd_grouped(n_img, k, P, C, A, w.k_live, d->enc, w.att_enc, w.z, NZ, d->full_att_w,
                                                d->full_att_b, w.z + A, NZ, alpha_s, P, w.gated, w.slot_img, w.n_live, row_off, s));
-        ICD_TRY(beam_mm(prec, w, w.emb_x, E, (int)R, E, d->w_ih, E + C, w.x3_WihE, w.gates_pre, 4 * D, 4 * D,
-                        d->b_ih, w.z + A + C, NZ, 0.f, s, live_rows));
+        if (use_embg) {
+            beam_gates_init_kernel<<<(unsigned)R, 128, 0, s>>>(w.embg, w.tok64, 4 * D, w.z + A + C, NZ, w.gates_pre, w.n_live);
+            ICD_LAUNCH_CHECK();
+        } else
+            ICD_TRY(beam_mm(prec, w, w.emb_x, E, (int)R, E, d->w_ih, E + C, w.x3_WihE, w.gates_pre, 4 * D, 4 * D,
+                            d->b_ih, w.z + A + C, NZ, 0.f, s, live_rows));
         ICD_TRY(beam_mm(prec, w, w.gated, C, (int)R, C, d->w_ih + E, E + C, w.x3_WihC, w.gates_pre, 4 * D, 4 * D,
                         nullptr, nullptr, 0, 1.f, s, live_rows));                            // :70-71
         ICD_TRY(icd_lstm_pointwise_fwd((int)R, D, w.gates_pre, w.c, nullptr, w.c_tmp, w.h_tmp, nullptr, 0, nullptr, 1.f, s,

@@ -223,24 +223,42 @@ __global__ void __launch_bounds__(1024) embed_sort_kernel(const long long* __res
     for (int i = threadIdx.x; i < n_sort; i += blockDim.x) keys[base + i] = s_key[i];
 }
 
-// one CTA per sorted position; only segment heads (first occurrence of a token in the chunk) work: they add the segment's
-// rows in ascending row order and accumulate into the table row (chunks are launched one after the other: no two CTAs ever
-// touch the same table row concurrently, and the order of every sum is fixed)
+// one CTA (8 warps) per sorted position; only segment heads (first occurrence of a token in the chunk) work.  Warp w adds the
+// segment's rows head + w, head + w + 8, ... in ascending order (lanes own columns e = lane, lane + 32, ...: every row is one
+// coalesced read), then the eight partial sums are added in warp order — a FIXED association, so the result is deterministic —
+// and accumulated into the table row (chunks are launched one after the other: no two CTAs touch a table row concurrently).
+constexpr int EMB_MAX_E = 1024;                     // columns per table row the register accumulators cover (E <= 1024)
 template <typename TT>
-__global__ void __launch_bounds__(128) embed_segment_reduce_kernel(const unsigned long long* __restrict__ keys, int n_sort,
+__global__ void __launch_bounds__(256) embed_segment_reduce_kernel(const unsigned long long* __restrict__ keys, int n_sort,
                                                                     const float* __restrict__ d_x, TT* __restrict__ d_table, int E) {
+    extern __shared__ unsigned char s_raw[];
+    TT* s_part = reinterpret_cast<TT*>(s_raw);                           // [8 warps][E]
     const int i = blockIdx.x;
     const unsigned long long key = keys[i];
     if (key == EMB_KEY_NONE) return;
     const unsigned int tok = (unsigned int)(key >> 32);
     if (i > 0 && (unsigned int)(keys[i - 1] >> 32) == tok) return;
     int end = i + 1;
-    while (end < n_sort && (unsigned int)(keys[end] >> 32) == tok && keys[end] != EMB_KEY_NONE) ++end;
+    while (end < n_sort && keys[end] != EMB_KEY_NONE && (unsigned int)(keys[end] >> 32) == tok) ++end;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NE = EMB_MAX_E / 32;
+    TT acc[NE];
+#pragma unroll
+    for (int q = 0; q < NE; ++q) acc[q] = (TT)0;
+    for (int j = i + warp; j < end; j += 8) {
+        const float* src = d_x + (long long)(unsigned int)(keys[j] & 0xffffffffull) * E;
+#pragma unroll
+        for (int q = 0; q < NE; ++q) { const int e = lane + 32 * q; if (e < E) acc[q] += (TT)src[e]; }
+    }
+#pragma unroll
+    for (int q = 0; q < NE; ++q) { const int e = lane + 32 * q; if (e < E) s_part[(size_t)warp * E + e] = acc[q]; }
+    __syncthreads();
     TT* dst = d_table + (long long)tok * E;
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
-        TT acc = (TT)0;
-        for (int j = i; j < end; ++j) acc += (TT)d_x[(long long)(unsigned int)(keys[j] & 0xffffffffull) * E + e];
-        dst[e] += acc;
+        TT t = s_part[e];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) t += s_part[(size_t)w * E + e];
+        dst[e] += t;
     }
 }
 
@@ -505,7 +523,7 @@ int icd_embed_scatter_add(void* d_table, int is_f64, const int64_t* captions, in
     BtPack pack;
     for (int t = 0; t < ICD_MAX_STEPS; ++t) pack.v[t] = t < T ? bt_host[t] : 0;
     static const bool atomic_mode = [] { const char* e = getenv("ICD_EMBED_ATOMIC"); return e && e[0] == '1'; }();
-    if (!atomic_mode && ws && ws_bytes >= icd_embed_scatter_ws_bytes(B, T)) {
+    if (!atomic_mode && ws && ws_bytes >= icd_embed_scatter_ws_bytes(B, T) && E <= EMB_MAX_E) {
         // deterministic path: sort (token, row) per chunk of 16384 rows, then segment sums in row order, chunk after chunk
         const long long N = (long long)B * T;
         const int chunks = (int)((N + EMB_SORT_N - 1) / EMB_SORT_N);
@@ -522,8 +540,15 @@ int icd_embed_scatter_add(void* d_table, int is_f64, const int64_t* captions, in
         ICD_LAUNCH_CHECK();
         for (int c = 0; c < chunks; ++c) {
             const unsigned long long* kc = keys + (size_t)c * EMB_SORT_N;
-            if (is_f64) embed_segment_reduce_kernel<double><<<n_sort, 128, 0, s>>>(kc, n_sort, d_x, (double*)d_table, E);
-            else        embed_segment_reduce_kernel<float><<<n_sort, 128, 0, s>>>(kc, n_sort, d_x, (float*)d_table, E);
+            const size_t rs = (size_t)8 * E * (is_f64 ? sizeof(double) : sizeof(float));      // <= 64 KB: opted in below
+            static size_t red_configured[2] = {48 * 1024, 48 * 1024};
+            if (rs > red_configured[is_f64 ? 1 : 0]) {
+                if (is_f64) ICD_CUDA(cudaFuncSetAttribute(embed_segment_reduce_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+                else        ICD_CUDA(cudaFuncSetAttribute(embed_segment_reduce_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs));
+                red_configured[is_f64 ? 1 : 0] = rs;
+            }
+            if (is_f64) embed_segment_reduce_kernel<double><<<n_sort, 256, rs, s>>>(kc, n_sort, d_x, (double*)d_table, E);
+            else        embed_segment_reduce_kernel<float><<<n_sort, 256, rs, s>>>(kc, n_sort, d_x, (float*)d_table, E);
             ICD_LAUNCH_CHECK();
         }
         return 0;
