@@ -17,6 +17,7 @@
 // d_att_enc is NOT read-modify-written per step: d_e is saved per step and one kernel after the time
 // loop (attention_proj_bwd) forms d_att_enc and d_w_full for all steps at once.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -161,7 +162,8 @@ __global__ void __launch_bounds__(256, 3) att_step_fwd_grouped_kernel(
         const float* __restrict__ w_full, const float* __restrict__ b_full,
         const float* __restrict__ fbeta_pre, long long ld_fb,
         float* __restrict__ alpha, long long ld_alpha, float* __restrict__ gated,
-        const int* __restrict__ slot_img, const int* __restrict__ n_slots, const int* __restrict__ row_off) {
+        const int* __restrict__ slot_img, const int* __restrict__ n_slots, const int* __restrict__ row_off,
+        unsigned short* __restrict__ gated_x3) {
     extern __shared__ __align__(16) float sm[];
     // slot = the live beams of one image: state rows (att_dec / fbeta / gated) row_off[slot] + j, or slot*k + j without a
     // row map; img = the image whose features the slot decodes (slot == img without a slot map).  alpha rows are
@@ -286,8 +288,31 @@ __global__ void __launch_bounds__(256, 3) att_step_fwd_grouped_kernel(
             if (j < kl) {
                 const float4 f = *reinterpret_cast<const float4*>(fbeta_pre + (r0 + j) * ld_fb + c);
                 const float4 g = make_float4(sigmoidf_(f.x), sigmoidf_(f.y), sigmoidf_(f.z), sigmoidf_(f.w));
-                *reinterpret_cast<float4*>(gated + (r0 + j) * C + c) =
-                    make_float4(g.x * acc[j].x, g.y * acc[j].y, g.z * acc[j].z, g.w * acc[j].w);
+                const float4 o = make_float4(g.x * acc[j].x, g.y * acc[j].y, g.z * acc[j].z, g.w * acc[j].w);
+                if (gated) *reinterpret_cast<float4*>(gated + (r0 + j) * C + c) = o;
+                if (gated_x3) {
+                    // fp32-grade tensor-core tier: emit the 3-term bf16 split of the row right here, in the A-operand layout of
+                    // the next contraction ([a1 | a1 | a2 | a1 | a3 | a2] along K, segment length C; gemm_tc.cu) — the separate
+                    // split pass over the (rows, C) activation disappears
+                    const float xs[4] = {o.x, o.y, o.z, o.w};
+                    unsigned short t[3][4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const __nv_bfloat16 b1 = __float2bfloat16_rn(xs[q]);
+                        const float r1 = xs[q] - __bfloat162float(b1);
+                        const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
+                        const __nv_bfloat16 b3 = __float2bfloat16_rn(r1 - __bfloat162float(b2));
+                        t[0][q] = __bfloat16_as_ushort(b1); t[1][q] = __bfloat16_as_ushort(b2); t[2][q] = __bfloat16_as_ushort(b3);
+                    }
+                    unsigned short* dst = gated_x3 + (r0 + j) * 6 * (long long)C + c;
+                    const int pat[6] = {0, 0, 1, 0, 2, 1};
+#pragma unroll
+                    for (int sg = 0; sg < 6; ++sg) {
+                        const unsigned short* tt = t[pat[sg]];
+                        *reinterpret_cast<uint2*>(dst + (long long)sg * C) =
+                            make_uint2((unsigned)tt[0] | ((unsigned)tt[1] << 16), (unsigned)tt[2] | ((unsigned)tt[3] << 16));
+                    }
+                }
             }
         }
     }
@@ -722,7 +747,7 @@ template <int K>
 static int launch_grouped(int n_img, int k, int P, int C, int A, const int* k_live, const float* enc, const float* att_enc,
                           const float* att_dec, int64_t ld_dec, const float* w_full, const float* b_full,
                           const float* fbeta_pre, int64_t ld_fb, float* alpha, int64_t ld_alpha, float* gated,
-                          const int* slot_img, const int* n_slots, const int* row_off, cudaStream_t s) {
+                          const int* slot_img, const int* n_slots, const int* row_off, cudaStream_t s, void* gated_x3) {
     const size_t smem = ((size_t)K * A + A + (size_t)K * ((P + 3) & ~3)) * sizeof(float);
     ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_fwd_grouped: K*A too large for shared memory");
     static size_t configured = 48 * 1024;
@@ -731,7 +756,8 @@ static int launch_grouped(int n_img, int k, int P, int C, int A, const int* k_li
         configured = smem;
     }
     att_step_fwd_grouped_kernel<K><<<n_img, 256, smem, s>>>(k, P, C, A, k_live, enc, att_enc, att_dec, ld_dec, w_full, b_full,
-                                                            fbeta_pre, ld_fb, alpha, ld_alpha, gated, slot_img, n_slots, row_off);
+                                                            fbeta_pre, ld_fb, alpha, ld_alpha, gated, slot_img, n_slots, row_off,
+                                                            reinterpret_cast<unsigned short*>(gated_x3));
     ICD_LAUNCH_CHECK();
     return 0;
 }
@@ -740,12 +766,13 @@ int icd_attention_step_fwd_grouped(int n_img, int k, int P, int C, int A, const 
                                    const float* att_enc, const float* att_dec, int64_t ld_dec, const float* w_full,
                                    const float* b_full, const float* fbeta_pre, int64_t ld_fb, float* alpha,
                                    int64_t ld_alpha, float* gated, const int* slot_img, const int* n_slots, const int* row_off,
-                                   cudaStream_t s) {
+                                   cudaStream_t s, void* gated_x3) {
     if (n_img == 0) return 0;
+    ICD_CHECK_ARG(!gated_x3 || C % 8 == 0, "attention_step_fwd_grouped: the fused 3-term split needs C % 8 == 0");
     ICD_CHECK_ARG(k >= 1 && k <= 8, "attention_step_fwd_grouped: k=%d (1..8)", k);
     ICD_CHECK_ARG(A % 4 == 0 && C % 4 == 0 && ld_dec % 4 == 0 && ld_fb % 4 == 0, "attention_step_fwd_grouped: misaligned dims");
 #define ICD_GROUPED(KK) return launch_grouped<KK>(n_img, k, P, C, A, k_live, enc, att_enc, att_dec, ld_dec, w_full, b_full, \
-                                                  fbeta_pre, ld_fb, alpha, ld_alpha, gated, slot_img, n_slots, row_off, s)
+                                                  fbeta_pre, ld_fb, alpha, ld_alpha, gated, slot_img, n_slots, row_off, s, gated_x3)
     switch (k) {
         case 1: ICD_GROUPED(1);
         case 2: ICD_GROUPED(2);

@@ -117,6 +117,7 @@ __device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
 // flattened candidates (ties: lower flat index first), then the beam bookkeeping of gen_captions.py:85-116.
 // State of the surviving beams goes to the *_tmp arrays (slot rows; beam_reorder_kernel moves it to the compacted slots),
 // history (parent / word / trace) and winners are written per IMAGE.
+template <int KT>      // KT >= k: length of the per-thread candidate lists (a shorter list = far fewer sorted insertions)
 __global__ void __launch_bounds__(256) beam_topk_kernel(
         int k, int V, int step, int end_id, const float* __restrict__ logits,
         const float* __restrict__ score, const int* __restrict__ k_live, const int* __restrict__ slot_img,
@@ -126,8 +127,8 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
         int* __restrict__ parent_s, int* __restrict__ word_s, int* __restrict__ trace_s,
         float* __restrict__ best_score, int* __restrict__ best_step, int* __restrict__ best_parent) {
     __shared__ float s_red[40];
-    __shared__ float s_cv[256 * KMAX];
-    __shared__ int s_ci[256 * KMAX];
+    __shared__ float s_cv[256 * KT];
+    __shared__ int s_ci[256 * KT];
     __shared__ float s_topv[KMAX];
     __shared__ int s_topi[KMAX];
     const int slot = blockIdx.x;
@@ -140,29 +141,28 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
     const float* lg = logits + (long long)row0 * V;
     const bool even = (V & 1) == 0;
     const int V2 = V >> 1;
-    // thread-local top-KMAX over this thread's slice of the flattened (nrows*V) candidates (flat index f = i*V + v)
-    float tv[KMAX]; int ti[KMAX];
+    // thread-local top-KT over this thread's slice of the flattened (nrows*V) candidates (flat index f = i*V + v)
+    float tv[KT]; int ti[KT];
 #pragma unroll
-    for (int j = 0; j < KMAX; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
+    for (int j = 0; j < KT; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
     for (int i = 0; i < nrows; ++i) {
         // ONE streaming pass per row: online log-sum-exp (running max m, sum s of exp(x - m)) and, in the same pass, the
-        // thread's top-KMAX RAW logits of the row.  log_softmax + score is monotone in the logit within a row, so the row's
+        // thread's top-KT RAW logits of the row.  log_softmax + score is monotone in the logit within a row, so the row's
         // best candidates are its largest logits; their values v = score + (x - max) - log(sum) (:74-76) are formed once the
-        // row statistics are known and merged into the thread's flat top-KMAX by (v, lower flat index first).  (Selecting by
-        // x instead of v inside a row could only differ if >= KMAX - k + 1 distinct logits of ONE thread's slice collapsed
-        // onto the same fp32 v at the selection boundary.)
+        // row statistics are known and merged into the thread's flat top-KT by (v, lower flat index first).  (Selecting by
+        // x instead of v inside a row can only differ if two DISTINCT logits among one thread's best k of a row collapse onto the
+        // same fp32 v exactly at the selection boundary: a tie whose order torch.topk leaves unspecified too.)
         const float* x = lg + (long long)i * V;
         const float2* x2 = reinterpret_cast<const float2*>(x);
         float m = -INFINITY, ssum = 0.f;
-        float rx[KMAX]; int rv[KMAX];
+        float rx[KT]; int rv[KT];
 #pragma unroll
-        for (int j = 0; j < KMAX; ++j) { rx[j] = -INFINITY; rv[j] = 0x7fffffff; }
-        auto visit = [&](float xv, int v) {
-            if (xv > m) { ssum = ssum * expf(m - xv) + 1.f; m = xv; } else ssum += expf(xv - m);
-            if (better(xv, v, rx[KMAX - 1], rv[KMAX - 1])) {
-                rx[KMAX - 1] = xv; rv[KMAX - 1] = v;
+        for (int j = 0; j < KT; ++j) { rx[j] = -INFINITY; rv[j] = 0x7fffffff; }
+        auto keep = [&](float xv, int v) {                            // thread-local top-KT raw logits of this row
+            if (better(xv, v, rx[KT - 1], rv[KT - 1])) {
+                rx[KT - 1] = xv; rv[KT - 1] = v;
 #pragma unroll
-                for (int j = KMAX - 1; j > 0; --j) {
+                for (int j = KT - 1; j > 0; --j) {
                     if (better(rx[j], rv[j], rx[j - 1], rv[j - 1])) {
                         const float a = rx[j]; rx[j] = rx[j - 1]; rx[j - 1] = a;
                         const int b2 = rv[j]; rv[j] = rv[j - 1]; rv[j - 1] = b2;
@@ -176,26 +176,43 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
                 float2 a[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) a[u] = x2[j + u * 256];
+                // the running maximum moves at most once per 8 values: one rescale, then eight plain exp(x - m) terms
+                const float cm = fmaxf(fmaxf(fmaxf(a[0].x, a[0].y), fmaxf(a[1].x, a[1].y)), fmaxf(fmaxf(a[2].x, a[2].y), fmaxf(a[3].x, a[3].y)));
+                if (cm > m) { ssum *= __expf(m - cm); m = cm; }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { visit(a[u].x, 2 * (j + u * 256)); visit(a[u].y, 2 * (j + u * 256) + 1); }
+                for (int u = 0; u < 4; ++u) {
+                    ssum += __expf(a[u].x - m) + __expf(a[u].y - m);
+                    keep(a[u].x, 2 * (j + u * 256)); keep(a[u].y, 2 * (j + u * 256) + 1);
+                }
             }
-            for (; j < V2; j += 256) { const float2 a = x2[j]; visit(a.x, 2 * j); visit(a.y, 2 * j + 1); }
+            for (; j < V2; j += 256) {
+                const float2 a = x2[j];
+                const float cm = fmaxf(a.x, a.y);
+                if (cm > m) { ssum *= __expf(m - cm); m = cm; }
+                ssum += __expf(a.x - m) + __expf(a.y - m);
+                keep(a.x, 2 * j); keep(a.y, 2 * j + 1);
+            }
         } else {
-            for (int v = threadIdx.x; v < V; v += blockDim.x) visit(x[v], v);
+            for (int v = threadIdx.x; v < V; v += blockDim.x) {
+                const float xv = x[v];
+                if (xv > m) { ssum *= __expf(m - xv); m = xv; }
+                ssum += __expf(xv - m);
+                keep(xv, v);
+            }
         }
         const float rmax = block_max(m, s_red);
         const float sum = block_sum((m == -INFINITY) ? 0.f : ssum * expf(m - rmax), s_red);
         const float rlsum = logf(sum), rscore = score[row0 + i];
         const int f0 = i * V;
 #pragma unroll
-        for (int q = 0; q < KMAX; ++q) {
+        for (int q = 0; q < KT; ++q) {
             if (rv[q] == 0x7fffffff) continue;
             const float v = rscore + ((rx[q] - rmax) - rlsum);
             const int f = f0 + rv[q];
-            if (better(v, f, tv[KMAX - 1], ti[KMAX - 1])) {
-                tv[KMAX - 1] = v; ti[KMAX - 1] = f;
+            if (better(v, f, tv[KT - 1], ti[KT - 1])) {
+                tv[KT - 1] = v; ti[KT - 1] = f;
 #pragma unroll
-                for (int j = KMAX - 1; j > 0; --j) {
+                for (int j = KT - 1; j > 0; --j) {
                     if (better(tv[j], ti[j], tv[j - 1], ti[j - 1])) {
                         const float a = tv[j]; tv[j] = tv[j - 1]; tv[j - 1] = a;
                         const int b2 = ti[j]; ti[j] = ti[j - 1]; ti[j - 1] = b2;
@@ -205,13 +222,13 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
         }
     }
 #pragma unroll
-    for (int j = 0; j < KMAX; ++j) { s_cv[threadIdx.x * KMAX + j] = tv[j]; s_ci[threadIdx.x * KMAX + j] = ti[j]; }
+    for (int j = 0; j < KT; ++j) { s_cv[threadIdx.x * KT + j] = tv[j]; s_ci[threadIdx.x * KT + j] = ti[j]; }
     __syncthreads();
     if (threadIdx.x < 32) {                                          // warp 0: kl rounds of arg-best
         const int lane = threadIdx.x;
         for (int round = 0; round < ksel; ++round) {
             float bv = -INFINITY; int bi = 0x7fffffff, bpos = -1;
-            for (int q = lane; q < 256 * KMAX; q += 32)
+            for (int q = lane; q < 256 * KT; q += 32)
                 if (better(s_cv[q], s_ci[q], bv, bi)) { bv = s_cv[q]; bi = s_ci[q]; bpos = q; }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -388,14 +405,14 @@ __global__ void beam_gates_init_kernel(const float* __restrict__ embg, const lon
 // activation split on the fly and the weight split `w16x3` prepared once per call.
 int beam_mm(int prec, const BeamWs& w, const float* x, long long ldx, int rows, int K, const float* W, long long ldw,
             const void* w16x3, float* y, long long ldy, int N, const float* bias, const float* add, long long ldadd,
-            float beta, cudaStream_t s, const int* m_live = nullptr) {
+            float beta, cudaStream_t s, const int* m_live = nullptr, bool pre_split = false) {
     // m_live: device-side count of live rows (compacted to the front).  The tensor-core tier computes only those; the fp32
     // FMA tier computes all `rows` (rows beyond the live count hold stale, finite state and are never read back).
     if (prec != ICD_PREC_FP32X3)
         return icd_gemm_simple(ICD_PREC_FP32, x, ldx, 1, W, ldw, 1, y, ldy, rows, N, K, bias, nullptr, add, ldadd, nullptr, 0,
                                nullptr, beta, s);
     const long long seg = up8ll(K);
-    ICD_TRY(icd_split3_bf16(x, ldx, rows, K, w.x3_act, 0, s, m_live));
+    if (!pre_split) ICD_TRY(icd_split3_bf16(x, ldx, rows, K, w.x3_act, 0, s, m_live));   // (pre_split: the producer wrote w.x3_act)
     return icd_gemm_bf16_ex(w.x3_act, 6 * seg, 0, w16x3, 6 * seg, 0, y, ldy, rows, N, (int)(6 * seg), bias, nullptr, add, ldadd,
                             nullptr, 0, nullptr, beta, s, nullptr, 0, w.x3_splitk, w.x3_splitk_floats, nullptr, m_live);
 }
@@ -482,8 +499,12 @@ extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
         }
         ICD_TRY(beam_mm(prec, w, w.h, D, (int)R, D, w.w_cat, D, w.x3_Wcat, w.z, NZ, NZ, w.b_cat, nullptr, 0, 0.f, s, live_rows));
         // :66-69 — one CTA per live slot serves all of its live beams (features read once per image and step)
+        // fp32-grade tensor-core tier: the attention kernel emits the 3-term bf16 split of `gated` itself (the A operand of the
+        // gate contraction below), so neither the fp32 copy nor a split pass over (rows, C) is needed
+        const bool fused_split = prec == ICD_PREC_FP32X3 && use_embg && (C % 8 == 0);
         ICD_TRY(icd_attention_step_fwd_grouped(n_img, k, P, C, A, w.k_live, d->enc, w.att_enc, w.z, NZ, d->full_att_w,
-                                               d->full_att_b, w.z + A, NZ, alpha_s, P, w.gated, w.slot_img, w.n_live, row_off, s));
+                                               d->full_att_b, w.z + A, NZ, alpha_s, P, fused_split ? nullptr : w.gated, w.slot_img,
+                                               w.n_live, row_off, s, fused_split ? w.x3_act : nullptr));
         if (use_embg) {
             beam_gates_init_kernel<<<(unsigned)R, 128, 0, s>>>(w.embg, w.tok64, 4 * D, w.z + A + C, NZ, w.gates_pre, w.n_live);
             ICD_LAUNCH_CHECK();
@@ -491,15 +512,25 @@ extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
             ICD_TRY(beam_mm(prec, w, w.emb_x, E, (int)R, E, d->w_ih, E + C, w.x3_WihE, w.gates_pre, 4 * D, 4 * D,
                             d->b_ih, w.z + A + C, NZ, 0.f, s, live_rows));
         ICD_TRY(beam_mm(prec, w, w.gated, C, (int)R, C, d->w_ih + E, E + C, w.x3_WihC, w.gates_pre, 4 * D, 4 * D,
-                        nullptr, nullptr, 0, 1.f, s, live_rows));                            // :70-71
+                        nullptr, nullptr, 0, 1.f, s, live_rows, fused_split));               // :70-71
         ICD_TRY(icd_lstm_pointwise_fwd((int)R, D, w.gates_pre, w.c, nullptr, w.c_tmp, w.h_tmp, nullptr, 0, nullptr, 1.f, s,
                                        nullptr, nullptr, live_rows));
         ICD_TRY(beam_mm(prec, w, w.h_tmp, D, (int)R, D, d->fc_w, D, w.x3_Wfc, w.logits, V, V, d->fc_b, nullptr, 0, 0.f, s, live_rows));   // :72
-        beam_topk_kernel<<<n_img, 256, 0, s>>>(k, V, step, d->end_id, w.logits, w.score, w.k_live, w.slot_img, w.n_live, row_off,
-                                               w.score_tmp, w.word_tmp, w.k_live_tmp, w.slot_img_tmp, w.src,
-                                               w.parent + (size_t)(step - 1) * R, w.word + (size_t)(step - 1) * R,
-                                               d->trace_words ? d->trace_words + (size_t)(step - 1) * R : nullptr,
-                                               w.best_score, w.best_step, w.best_parent);
+#define ICD_TOPK(KT) beam_topk_kernel<KT><<<n_img, 256, 0, s>>>(k, V, step, d->end_id, w.logits, w.score, w.k_live, w.slot_img, w.n_live, \
+                                               row_off, w.score_tmp, w.word_tmp, w.k_live_tmp, w.slot_img_tmp, w.src,                   \
+                                               w.parent + (size_t)(step - 1) * R, w.word + (size_t)(step - 1) * R,                      \
+                                               d->trace_words ? d->trace_words + (size_t)(step - 1) * R : nullptr,                      \
+                                               w.best_score, w.best_step, w.best_parent)
+        switch (k) {
+            case 1: ICD_TOPK(1); break;
+            case 2: ICD_TOPK(2); break;
+            case 3: ICD_TOPK(3); break;
+            case 4: ICD_TOPK(4); break;
+            case 5: ICD_TOPK(5); break;
+            case 6: ICD_TOPK(6); break;
+            default: ICD_TOPK(8); break;
+        }
+#undef ICD_TOPK
         ICD_LAUNCH_CHECK();
         beam_compact_kernel<<<1, 1024, 0, s>>>(n_img, k, w.k_live_tmp, w.new_slot, w.n_live, row_off_next);
         ICD_LAUNCH_CHECK();

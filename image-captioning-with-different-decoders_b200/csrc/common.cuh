@@ -159,7 +159,8 @@ int icd_attention_step_fwd_grouped(int n_img, int k, int P, int C, int A, const 
                                    const float* b_full, const float* fbeta_pre, int64_t ld_fb, float* alpha,
                                    int64_t ld_alpha, float* gated, const int* slot_img /* slot -> image, or NULL */,
                                    const int* n_slots /* device: live slots, or NULL */,
-                                   const int* row_off /* slot -> first state row, or NULL (slot*k) */, cudaStream_t s);
+                                   const int* row_off /* slot -> first state row, or NULL (slot*k) */, cudaStream_t s,
+                                   void* gated_x3 = nullptr /* optional: 3-term bf16 split of gated, rows of 6*C (gemm_tc.cu A layout) */);
 void icd_gemm_simple_set_ws(void* ws, int64_t bytes);
 struct IcdSimpleWsScope {          // RAII: workspace for icd_gemm_simple's tensor-core tiers during one entry-point call
     IcdSimpleWsScope(void* ws, int64_t bytes) { icd_gemm_simple_set_ws(ws, bytes); }
