@@ -10,7 +10,8 @@
 //     thread, accumulators in TMEM (2 stages x BN fp32 columns: the epilogue of tile i overlaps the MMAs of tile i+1);
 //   * sync: mbarrier full/empty ring (TMA <-> MMA), tcgen05.commit -> mbarrier (MMA -> TMA slot release and
 //     MMA -> epilogue), tmem_empty barrier (epilogue -> MMA);
-//   * warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-9 epilogue
+//   * warp roles (416 threads): warps 0-3 TMA producers (A / B x even / odd k-blocks), warp 4 TMEM allocator + MMA issuer,
+//     warps 5-12 epilogue
 //     (tcgen05.ld 32x32b.x32 -> registers -> padded smem transpose -> coalesced 128-bit loads/stores with the fused
 //     epilogue: bias1 + bias2 + add1 + add2, row mask, beta, optional bf16 copy of the result);
 //   * persistent: grid = min(#work units, #SMs), static round-robin schedule;
@@ -32,7 +33,13 @@ constexpr int EPI_LD = 32;                           // row of the per-warp 32x3
                                                      // (lane = row) and the 128-bit tile reads (8 lanes = one row) are
                                                      // bank-conflict free without padding
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS; // 320
+// warp roles: warps 0-3 TMA producers (operand A / B x even / odd k-blocks: one UTMALDG costs ~100 issue clocks, a single
+// producer thread caps the ring at ~400 clocks per k-block — twice the MMA time of a 128 x 64 tile), warp 4 TMEM
+// allocator + MMA issuer, warps 5-12 epilogue
+constexpr int NUM_PROD_WARPS = 4;
+constexpr int MMA_WARP = NUM_PROD_WARPS;
+constexpr int EPI_WARP0 = NUM_PROD_WARPS + 1;
+constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);        // 416
 constexpr int MN_BLOCK_BYTES = TC_MN_BLOCK_BYTES;    // one 64-element MN block of an MN-major tile: BK rows x 128 B
 
 struct EpiArgs {
@@ -52,8 +59,10 @@ struct KArgs {
     int a_mn, b_mn;                           // 1: operand is MN-major in memory
     int splits, kb_per_split;                 // split-K: work unit = (tile, slice)
     float* partial;                           // [splits][M][N] raw accumulators when splits > 1
-    int cluster;                              // 1, or 2: CTA pairs (thread-block cluster of 2 along M) share every B tile —
-                                              // each CTA fetches half of it and TMA-multicasts it into both shared memories
+    int cm, cn;                               // thread-block cluster of cm x cn CTAs (cm along M, cn along N; 1 x 1 = none): the cn
+                                              // CTAs of a cluster row share their A tile and the cm CTAs of a cluster column their
+                                              // B tile — every CTA fetches 1/cn of A and 1/cm of B and TMA-multicasts the slice into
+                                              // all shared memories that need it, so each operand byte leaves L2 once per cluster
     const int* m_live;                        // optional DEVICE row count: only rows < min(M, *m_live) are computed / written
                                               // (beam search: the live rows are compacted to the front, no host round trip)
 };
@@ -241,6 +250,13 @@ __device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ s
     }
 }
 
+#ifdef ICD_GEMM_TRACE
+__device__ long long g_trace[6][512];      // [0] producer: empty-wait done, [1] producer: TMA issued, [2] MMA: full-wait done, [3] MMA: issued
+#define TRACE(slot, idx) do { if (blockIdx.x == 0 && (idx) < 512) g_trace[slot][idx] = clock64(); } while (0)
+#else
+#define TRACE(slot, idx) do {} while (0)
+#endif
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KArgs p) {
@@ -256,11 +272,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + STAGES * C_::STAGE_BYTES + C_::EPI_BYTES + 16 * STAGES + 32);
 
     const EpiArgs& e = p.e;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // cluster = 2: the pair works on m-tiles (2*mp, 2*mp + 1) of the same n-tile ("super tile"); both CTAs walk the same
-    // unit sequence, so their pipelines run in lock step through the shared empty barriers
-    const int CL = p.cluster;
+    const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
+    // cluster cm x cn: the cluster works on a "super tile" of cm x cn tiles (m-tiles cm*mp + rm, n-tiles cn*np + rn); all of
+    // its CTAs walk the same unit sequence, so their pipelines run in lock step through the shared empty barriers
+    const int CM = p.cm, CN = p.cn, CL = CM * CN;
     const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0u;
+    const int rm = (int)crank % CM, rn = (int)crank / CM;               // position inside the cluster
+    uint16_t mask_row = 0, mask_col = 0;                                // CTAs sharing this CTA's A tile (same rm) / B tile (same rn)
+    for (int j = 0; j < CN; ++j) mask_row |= (uint16_t)(1u << (rm + CM * j));
+    for (int i = 0; i < CM; ++i) mask_col |= (uint16_t)(1u << (rn * CM + i));
     const int tiles_n = (e.N + BN - 1) / BN;
     const int nkb = (e.K + BK - 1) / BK;
     const int unit0 = blockIdx.x / CL, unit_stride = gridDim.x / CL;
@@ -268,11 +288,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB) : "memory");
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, (uint32_t)CL); }
+        // a slot is free once every CTA this one multicasts into (its cluster row and column) has consumed it
+        // full: one arrive.expect_tx from the A producer and one from the B producer of the stage
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 2); mbar_init(empty0 + 8 * i, (uint32_t)(CM + CN - 1)); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)C_::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -281,58 +303,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     if (CL > 1) cluster_sync_all();          // the peer's barriers must be initialised before any multicast can target them
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
     // PDL: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail;
     // from here on operands / epilogue inputs produced upstream are read and C is written
     pdl_trigger();
     pdl_wait();
-    const int M_eff = p.m_live ? min(e.M, max(*p.m_live, 0)) : e.M;     // device-side row count (read after the dependency wait)
+    const int M_eff = p.m_live ? min(e.M, max((int)uniform_u32((uint32_t)*p.m_live), 0)) : e.M;     // device-side row count (read after the dependency wait)
     const int tiles_m = (M_eff + BM - 1) / BM;
-    const int tiles_mc = (tiles_m + CL - 1) / CL;
-    const int num_tiles = tiles_mc * tiles_n;                            // super tiles
+    const int tiles_mc = (tiles_m + CM - 1) / CM, tiles_nc = (tiles_n + CN - 1) / CN;
+    const int num_tiles = tiles_mc * tiles_nc;                           // super tiles
     const int num_units = num_tiles * p.splits;
 
-    if (warp == 0) {
-        // =================================== TMA producer ===================================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int unit = unit0; unit < num_units; unit += unit_stride) {
-                const int tile = unit % num_tiles, slice = unit / num_tiles;
-                const int m0 = ((tile % tiles_mc) * CL + (int)crank) * BM, n0 = (tile / tiles_mc) * BN;
-                const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(empty0 + 8 * stage, phase ^ 1);        // cluster = 2: BOTH CTAs have consumed this slot
+    if (warp < NUM_PROD_WARPS) {
+        // =================================== TMA producers ===================================
+        // producer warp w: operand (w & 1: 0 = A, 1 = B) of every second k-block (parity w >> 1); whole warp in uniform control
+        // flow, one elected lane issues (see elect_one).  STAGES is even, so a producer always meets stages of one parity.
+        const int which = warp & 1, par = warp >> 1;
+        // slice of the tile this CTA fetches for its cluster row (A) / column (B): rows of a K-major tile, k-rows of an MN-major one
+        const int CS = which ? CM : CN, rs = which ? rm : rn;
+        const uint16_t mc_mask = which ? mask_col : mask_row;
+        const int mn = which ? p.b_mn : p.a_mn;
+        const int tile_rows = which ? BN : BM;
+        const uint32_t tile_bytes = which ? (uint32_t)C_::B_BYTES : (uint32_t)A_BYTES;
+        const uint32_t slice_off = mn ? (uint32_t)(rs * (MN_BLOCK_BYTES / CS)) : (uint32_t)(rs * (int)(tile_bytes / CS));
+        const int slice_row = mn ? 0 : rs * (tile_rows / CS), slice_k = mn ? rs * (BK / CS) : 0;
+        const int n_blk = mn ? (tile_rows + 63) / 64 : 1;                 // TMA boxes per k-block
+        const CUtensorMap* tm = which ? &tmB : &tmA;
+        const uint32_t s_base = which ? sB : sA;
+        int stage = par; uint32_t phase = 0;
+        int it = 0;                                                       // k-blocks seen so far (all units)
+        for (int unit = unit0; unit < num_units; unit += unit_stride) {
+            const int tile = unit % num_tiles, slice = unit / num_tiles;
+            const int m0 = ((tile % tiles_mc) * CM + rm) * BM, n0 = ((tile / tiles_mc) * CN + rn) * BN;
+            const int r0 = (which ? n0 : m0) + slice_row;
+            const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                if ((it & 1) != par) continue;
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);            // every CTA of the cluster row / column has consumed this slot
+                if (elect_one()) {
+                    TRACE(which, kb);
                     const uint32_t fb = full0 + 8 * stage;
-                    mbar_arrive_expect_tx(fb, C_::STAGE_BYTES);
-                    const uint32_t a_dst = sA + stage * A_BYTES, b_dst = sB + stage * C_::B_BYTES;
-                    if (!p.a_mn) tma_load_2d(a_dst, &tmA, kb * BK, m0, fb);
-                    else {
-#pragma unroll
-                        for (int j = 0; j < BM / 64; ++j) tma_load_2d(a_dst + j * MN_BLOCK_BYTES, &tmA, m0 + 64 * j, kb * BK, fb);
-                    }
-                    if (CL == 1) {
-                        if (!p.b_mn) tma_load_2d(b_dst, &tmB, kb * BK, n0, fb);
-                        else {
-#pragma unroll
-                            for (int j = 0; j < (BN + 63) / 64; ++j) tma_load_2d(b_dst + j * MN_BLOCK_BYTES, &tmB, n0 + 64 * j, kb * BK, fb);
-                        }
+                    mbar_arrive_expect_tx(fb, tile_bytes);           // all slices of this operand tile, whoever sends them
+                    const uint32_t dst = s_base + stage * tile_bytes + slice_off;
+                    if (!mn) {
+                        if (CS == 1) tma_load_2d(dst, tm, kb * BK, r0, fb);
+                        else tma_load_2d_mc(dst, tm, kb * BK, r0, fb, mc_mask);
                     } else {
-                        // this CTA fetches its half of the B tile and multicasts it into both CTAs' shared memory; the
-                        // transaction bytes land on the full barrier at the same offset in each CTA
-                        if (!p.b_mn) tma_load_2d_mc(b_dst + crank * (C_::B_BYTES / 2), &tmB, kb * BK, n0 + (int)crank * (BN / 2), fb, (uint16_t)0x3);
-                        else {
-#pragma unroll
-                            for (int j = 0; j < BN / 128; ++j) {
-                                const int blk = (int)crank * (BN / 128) + j;
-                                tma_load_2d_mc(b_dst + blk * MN_BLOCK_BYTES, &tmB, n0 + 64 * blk, kb * BK, fb, (uint16_t)0x3);
-                            }
+                        for (int j = 0; j < n_blk; ++j) {
+                            if (CS == 1) tma_load_2d(dst + j * MN_BLOCK_BYTES, tm, r0 + 64 * j, kb * BK, fb);
+                            else tma_load_2d_mc(dst + j * MN_BLOCK_BYTES, tm, r0 + 64 * j, kb * BK + slice_k, fb, mc_mask);
                         }
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                stage += 2;
+                if (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == MMA_WARP) {
         // =================================== MMA issuer ===================================
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
@@ -346,9 +374,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
             for (int kb = kb0; kb < kb1; ++kb) {
+                TRACE(4, kb);
                 mbar_wait(full0 + 8 * stage, phase);                  // TMA bytes have landed
+                TRACE(5, kb);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
+                    TRACE(2, kb);
                     const uint64_t adesc = make_smem_desc(sA + stage * A_BYTES, p.a_mn);
                     const uint64_t bdesc = make_smem_desc(sB + stage * C_::B_BYTES, p.b_mn);
 #pragma unroll
@@ -356,8 +387,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tc_mma_f16(d_tmem, adesc + (uint64_t)k * a_kstep, bdesc + (uint64_t)k * b_kstep, idesc,
                                    (kb > kb0 || k > 0) ? 1u : 0u);
                     if (CL == 1) tc_commit(empty0 + 8 * stage);       // smem slot reusable once these MMAs retire
-                    else tc_commit_mc(empty0 + 8 * stage, (uint16_t)0x3);   // ... signalled to both producers of the pair
+                    else tc_commit_mc(empty0 + 8 * stage, (uint16_t)(mask_row | mask_col));   // ... signalled to every producer that fills it
                     if (kb == kb1 - 1) tc_commit(tfull0 + 8 * acc);   // accumulator complete -> epilogue
+                    TRACE(3, kb);
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -365,15 +397,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
-        // =================================== epilogue warps 2..9 ===================================
+        // =================================== epilogue warps 5..12 ===================================
         const int q = warp & 3;                                       // TMEM lane quarter this warp may access
-        const int cg = (warp - 2) >> 2;                               // column group: chunks cg, cg+2, ...
-        float* sE = sEpi + (warp - 2) * 32 * EPI_LD;
+        const int cg = (warp - EPI_WARP0) >> 2;                       // column group: chunks cg, cg+2, ...
+        float* sE = sEpi + (warp - EPI_WARP0) * 32 * EPI_LD;
         int acc = 0; uint32_t acc_phase = 0;
         constexpr int NCHUNK = BN / 32;
         for (int unit = unit0; unit < num_units; unit += unit_stride) {
             const int tile = unit % num_tiles, slice = unit / num_tiles;
-            const int m0 = ((tile % tiles_mc) * CL + (int)crank) * BM, n0 = (tile / tiles_mc) * BN;
+            const int m0 = ((tile % tiles_mc) * CM + rm) * BM, n0 = ((tile / tiles_mc) * CN + rn) * BN;
             EpiArgs ee = e;
             ee.M = M_eff;
             if (p.splits > 1) {                                       // raw partial tile, epilogue deferred
@@ -419,7 +451,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     if (CL > 1) cluster_sync_all();          // the peer may still multicast into this CTA's shared memory / barriers
-    if (warp == 1) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
                      :: "r"(tmem_base), "r"((uint32_t)C_::TMEM_COLS) : "memory");
@@ -490,7 +522,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + STAGES * C_::STAGE_BYTES + C_::EPI_BYTES + 16 * STAGES + 32);
 
     const EpiArgs& e = p.e;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
     const uint32_t crank = cluster_ctarank();                           // 0 = leader
     const int tiles_n = (e.N + BN - 1) / BN;
     const int nkb = (e.K + BK - 1) / BK;
@@ -499,11 +531,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB) : "memory");
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 2); mbar_init(empty0 + 8 * i, 1); }   // full: A and B producer of the leader
         for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 2 * NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"(smem_u32(tmem_slot)), "r"((uint32_t)C_::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -512,43 +544,50 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncthreads();
     cluster_sync_all();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
     pdl_trigger();
     pdl_wait();
-    const int M_eff = p.m_live ? min(e.M, max(*p.m_live, 0)) : e.M;
+    const int M_eff = p.m_live ? min(e.M, max((int)uniform_u32((uint32_t)*p.m_live), 0)) : e.M;
     const int tiles_m = (M_eff + BM - 1) / BM;
     const int tiles_mc = (tiles_m + 1) / 2;
     const int num_tiles = tiles_mc * tiles_n;                            // 256 x BN super tiles
     const int num_units = num_tiles * p.splits;
 
-    if (warp == 0) {
-        // =================================== TMA producer (both CTAs) ===================================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int unit = unit0; unit < num_units; unit += unit_stride) {
-                const int tile = unit % num_tiles, slice = unit / num_tiles;
-                const int m0 = ((tile % tiles_mc) * 2 + (int)crank) * BM, n0 = (tile / tiles_mc) * BN + (int)crank * (BN / 2);
-                const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+    if (warp < NUM_PROD_WARPS) {
+        // =================================== TMA producers (both CTAs) ===================================
+        // producer warp w: operand (w & 1: 0 = this CTA's 128 rows of A, 1 = its half of B) of every second k-block (parity
+        // w >> 1); the bytes of both CTAs complete on the LEADER's full barrier, armed by the leader's two producers of the stage
+        const int which = warp & 1, par = warp >> 1;
+        const int mn = which ? p.b_mn : p.a_mn;
+        const uint32_t tile_bytes = which ? (uint32_t)C_::BH_BYTES : (uint32_t)A_BYTES;
+        const int n_blk = mn ? (which ? BN / 128 : BM / 64) : 1;
+        const CUtensorMap* tm = which ? &tmB : &tmA;
+        const uint32_t s_base = which ? sB : sA;
+        int stage = par; uint32_t phase = 0;
+        int it = 0;
+        for (int unit = unit0; unit < num_units; unit += unit_stride) {
+            const int tile = unit % num_tiles, slice = unit / num_tiles;
+            const int m0 = ((tile % tiles_mc) * 2 + (int)crank) * BM, n0 = (tile / tiles_mc) * BN + (int)crank * (BN / 2);
+            const int r0 = which ? n0 : m0;
+            const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
+            for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                if ((it & 1) != par) continue;
+                mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                if (elect_one()) {
                     const uint32_t fb_leader = mapa_u32(full0 + 8 * stage, 0);
-                    if (crank == 0) mbar_arrive_expect_tx(full0 + 8 * stage, 2 * C_::STAGE_BYTES);   // bytes of BOTH CTAs
-                    const uint32_t a_dst = sA + stage * A_BYTES, b_dst = sB + stage * C_::BH_BYTES;
-                    if (!p.a_mn) tma_load_2d_2sm(a_dst, &tmA, kb * BK, m0, fb_leader);
+                    if (crank == 0) mbar_arrive_expect_tx(full0 + 8 * stage, 2 * tile_bytes);   // this operand's bytes of BOTH CTAs
+                    const uint32_t dst = s_base + stage * tile_bytes;
+                    if (!mn) tma_load_2d_2sm(dst, tm, kb * BK, r0, fb_leader);
                     else {
-#pragma unroll
-                        for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(a_dst + j * MN_BLOCK_BYTES, &tmA, m0 + 64 * j, kb * BK, fb_leader);
+                        for (int j = 0; j < n_blk; ++j) tma_load_2d_2sm(dst + j * MN_BLOCK_BYTES, tm, r0 + 64 * j, kb * BK, fb_leader);
                     }
-                    if (!p.b_mn) tma_load_2d_2sm(b_dst, &tmB, kb * BK, n0, fb_leader);
-                    else {
-#pragma unroll
-                        for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(b_dst + j * MN_BLOCK_BYTES, &tmB, n0 + 64 * j, kb * BK, fb_leader);
-                    }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                stage += 2;
+                if (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == MMA_WARP) {
         // =================================== MMA issuer (leader CTA only) ===================================
         if (crank == 0) {
             int stage = 0; uint32_t phase = 0;
@@ -565,7 +604,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full0 + 8 * stage, phase);              // both CTAs' tiles have landed
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (elect_one()) {
                         const uint64_t adesc = make_smem_desc(sA + stage * A_BYTES, p.a_mn);
                         const uint64_t bdesc = make_smem_desc(sB + stage * C_::BH_BYTES, p.b_mn);
 #pragma unroll
@@ -582,10 +621,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else {
-        // =================================== epilogue warps 2..9 (both CTAs, own TMEM half) ===================================
+        // =================================== epilogue warps 5..12 (both CTAs, own TMEM half) ===================================
         const int q = warp & 3;
-        const int cg = (warp - 2) >> 2;
-        float* sE = sEpi + (warp - 2) * 32 * EPI_LD;
+        const int cg = (warp - EPI_WARP0) >> 2;
+        float* sE = sEpi + (warp - EPI_WARP0) * 32 * EPI_LD;
         int acc = 0; uint32_t acc_phase = 0;
         constexpr int NCHUNK = BN / 32;
         for (int unit = unit0; unit < num_units; unit += unit_stride) {
@@ -637,7 +676,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
-    if (warp == 1) {
+    if (warp == MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;"
                      :: "r"(tmem_base), "r"((uint32_t)C_::TMEM_COLS) : "memory");
@@ -816,10 +855,24 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KArgs& k, int u
         ICD_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
         attr_set = true;
     }
-    if (k.cluster > 1) {                       // units = super tiles x slices; one CTA pair per unit slot
-        const int pairs = units < ICD_NUM_SMS / 2 ? units : ICD_NUM_SMS / 2;
-        ICD_CUDA(icd_launch_pdl_cluster(ICD_PDL_GEMM, gemm_tc_kernel<BN>, dim3(2 * pairs), dim3(NUM_THREADS), (size_t)Cfg<BN>::SMEM, s, 2u,
-                                        tmA, tmB, k));
+    if (k.cm * k.cn > 1) {                     // units = super tiles x slices; one cluster per unit slot
+        const int cl = k.cm * k.cn;
+        static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};      // co-resident clusters of this size (queried once)
+        if (max_clusters[cl] == 0) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(cl * (ICD_NUM_SMS / cl)); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = Cfg<BN>::SMEM;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, gemm_tc_kernel<BN>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = ICD_NUM_SMS / cl / 2; }
+            max_clusters[cl] = n < ICD_NUM_SMS / cl ? n : ICD_NUM_SMS / cl;
+            if (getenv("ICD_GEMM_VERBOSE")) fprintf(stderr, "[icd] gemm_tc<%d>: %d co-resident clusters of %d CTAs\n", BN, max_clusters[cl], cl);
+        }
+        const int clusters = units < max_clusters[cl] ? units : max_clusters[cl];
+        ICD_CUDA(icd_launch_pdl_cluster(ICD_PDL_GEMM, gemm_tc_kernel<BN>, dim3(cl * clusters), dim3(NUM_THREADS), (size_t)Cfg<BN>::SMEM, s,
+                                        (unsigned)cl, tmA, tmB, k));
     } else {
         const int grid = units < ICD_NUM_SMS ? units : ICD_NUM_SMS;
         ICD_CUDA(icd_launch_pdl(ICD_PDL_GEMM, gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), (size_t)Cfg<BN>::SMEM, s, tmA, tmB, k));
@@ -905,9 +958,31 @@ int tail_rows_to_split(int M, int N, int K, bool allow_split) {
     return c_two < 0.9 * c_full ? rem : 0;
 }
 
+// Cluster shape (cm x cn) of the multicast kernel.  The in-loop contractions with M = batch are bound by the chip-wide
+// L2 -> shared-memory rate (~6.3 KB/clk): with 128 x 64 tiles every k-block pulls 24 KB per CTA for 1 MFLOP.  In a cm x cn
+// cluster each A byte leaves L2 once per cluster row and each B byte once per cluster column (per CTA and k-block:
+// 16/cn + BN/8/cm KB).  ICD_GEMM_CLUSTER="cm,cn" overrides (diagnostic).
+void cluster_shape(int M, int N, int K, int bn, int splits, bool dev_rows, int* cm, int* cn) {
+    *cm = 1; *cn = 1;
+    const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + bn - 1) / bn;
+    int fm = 0, fn = 0;
+    if (const char* f = getenv("ICD_GEMM_CLUSTER")) {
+        if (sscanf(f, "%d,%d", &fm, &fn) == 2 && fm >= 1 && fn >= 1 && fm * fn <= 8 && (fm & (fm - 1)) == 0 && (fn & (fn - 1)) == 0) {
+            if (tiles_m % fm == 0 && tiles_n % fn == 0 && bn / fm >= 8) { *cm = fm; *cn = fn; }
+            return;
+        }
+    }
+    (void)K; (void)splits; (void)dev_rows;
+}
+
 }  // namespace
 
 extern "C" int icd_has_tensor_core_gemm(void) { return 1; }
+#ifdef ICD_GEMM_TRACE
+extern "C" __attribute__((visibility("default"))) int icd_gemm_trace_read(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 6 * 512);
+}
+#endif
 extern "C" int icd_gemm_set_pair_mode(int mode) {
     const int old = g_pair_forced ? pair_mode() : -1;
     pair_mode();
@@ -986,10 +1061,23 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
     // the K = 512 shapes are epilogue / store bound and run slightly better on independent CTAs
     int mode = (pl.bn >= 128 && tiles_m >= 2) ? pair_mode() : 0;
     if (mode == 2 && !g_pair_forced && (K + BK - 1) / BK < 16) mode = 0;
-    const int cluster = mode ? 2 : 1;
+    // cluster shape of the multicast kernel (mode 1: pairs along M sharing B; small-M contractions: cm x cn, see cluster_shape)
+    int cm = mode ? 2 : 1, cn = 1;
+    if (mode != 2 || !g_pair_forced) {
+        int qm = 1, qn = 1;
+        cluster_shape(M, N, K, pl.bn, pl.splits, m_live != nullptr, &qm, &qn);
+        if (qm * qn > 1) { mode = 1; cm = qm; cn = qn; }
+    }
     CUtensorMap tmA, tmB;
-    ICD_TRY(make_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(A16), lda, M, K, BM, a_mn));
-    ICD_TRY(make_tmap(&tmB, reinterpret_cast<const __nv_bfloat16*>(B16), ldb, N, K, pl.bn / cluster, b_mn));
+    if (mode == 2) {
+        ICD_TRY(make_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(A16), lda, M, K, BM, a_mn));
+        ICD_TRY(make_tmap(&tmB, reinterpret_cast<const __nv_bfloat16*>(B16), ldb, N, K, pl.bn / 2, b_mn));
+    } else {
+        // K-major: the box is the CTA's row slice of the tile; MN-major: all 64-wide MN blocks, the CTA's k-row slice
+        ICD_TRY(make_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(A16), lda, M, K, BM / cn, a_mn, BK / cn));
+        ICD_TRY(make_tmap(&tmB, reinterpret_cast<const __nv_bfloat16*>(B16), ldb, N, K, pl.bn / cm, b_mn, BK / cm));
+    }
+    const int cluster = mode == 2 ? 2 : cm;                    // CTAs along M that form one super tile
     KArgs k;
     EpiArgs& e = k.e;
     e.C = C; e.ldc = ldc; e.M = M; e.N = N; e.K = K; e.bias1 = bias1; e.bias2 = bias2;
@@ -1005,9 +1093,10 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
     e.vec = fits(4) ? 4 : (shifted ? 3 : (fits(2) ? 2 : 1));
     k.a_mn = a_mn ? 1 : 0; k.b_mn = b_mn ? 1 : 0;
     k.splits = pl.splits; k.kb_per_split = pl.kb_per_split; k.partial = splitk_ws;
-    k.cluster = cluster;
+    k.cm = mode == 2 ? 2 : cm; k.cn = mode == 2 ? 1 : cn;
     k.m_live = m_live;
-    const int tiles = ((tiles_m + cluster - 1) / cluster) * ((N + pl.bn - 1) / pl.bn);      // super tiles when paired
+    const int tiles_n = (N + pl.bn - 1) / pl.bn;
+    const int tiles = ((tiles_m + cluster - 1) / cluster) * ((tiles_n + k.cn - 1) / k.cn);  // super tiles when clustered
     const int units = tiles * pl.splits;
     if (mode == 2) {
         if (pl.bn == 256) ICD_TRY(launch2<256>(tmA, tmB, k, units, s)); else ICD_TRY(launch2<128>(tmA, tmB, k, units, s));

@@ -47,6 +47,16 @@ __device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  :: "r"(bar), "h"(mask) : "memory");
 }
+// One lane of a fully converged warp (CUTLASS' elect_one_sync).  The single-thread roles (TMA producer, MMA issuer) run
+// their loops with the WHOLE warp in uniform control flow and issue under this predicate: code under `if (lane == 0)` is
+// divergent for the compiler, which then wraps every UTMALDG / UTCHMMA / UTCBAR in an ELECT + R2UR.BROADCAST "waterfall"
+// loop (~100 clocks per instruction: measured 750 clocks per k-block of four MMAs, i.e. issue-bound at 15 % tensor use).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t x) { return __shfl_sync(0xffffffffu, x, 0); }   // provably warp-uniform copy
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -111,7 +121,10 @@ inline int get_encode(EncodeTiledFn* out) {
 
 // K-major operand:  memory [rows][K] (ld elements between rows)  -> dims {K, rows}, box {BK, box_rows}
 // MN-major operand: memory [K][rows] (ld elements between k rows) -> dims {rows, K}, box {64, BK}
-inline int make_tmap(CUtensorMap* tm, const __nv_bfloat16* p, long long ld, int rows, int K, int box_rows, int mn_major) {
+// box_k: k-extent of the box (a cluster CTA that fetches only a slice of a tile: box_rows rows of a K-major tile, box_k
+// k-rows of an MN-major one)
+inline int make_tmap(CUtensorMap* tm, const __nv_bfloat16* p, long long ld, int rows, int K, int box_rows, int mn_major,
+                     int box_k = TC_BK) {
     EncodeTiledFn enc;
     ICD_TRY(get_encode(&enc));
     ICD_CHECK_ARG((reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld % 8) == 0,
@@ -119,7 +132,7 @@ inline int make_tmap(CUtensorMap* tm, const __nv_bfloat16* p, long long ld, int 
     cuuint64_t dims[2], strides[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2], estr[2] = {1, 1};
     if (!mn_major) { dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows; box[0] = TC_BK; box[1] = (cuuint32_t)box_rows; }
-    else           { dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K; box[0] = 64; box[1] = TC_BK; }
+    else           { dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K; box[0] = 64; box[1] = (cuuint32_t)box_k; }
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(p), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -334,6 +334,37 @@ def test_gemm_bf16_operand_majors_tiles_and_split_k(cuda, pair_mode, M, N, K, a_
     assert torch.equal(c, c2), "tensor-core contraction (incl. split-K) must be run-to-run deterministic"
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("cluster", ["2,1", "1,2", "2,2", "4,2", "2,4", "4,1", "1,4"])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("M,N,K,plan", [(512, 2048, 2048, "64,1"), (512, 4608, 512, "128,1"), (512, 512, 4608, "128,8"),
+                                        (512, 2048, 2048, "128,2"), (1000, 4608, 1000, "256,1")])
+def test_gemm_bf16_cluster_multicast(cuda, monkeypatch, cluster, M, N, K, plan, a_mn, b_mn):
+    """cm x cn thread-block clusters of the multicast contraction: every CTA fetches 1/cn of its A tile and 1/cm of its B tile
+    (row slices of K-major tiles, k-row slices of MN-major ones) and TMA-multicasts them along its cluster row / column.
+    All operand majors, split-K and non-split plans, bit-identical to the un-clustered kernel (same tiles, same k order)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(M + N + K + a_mn * 2 + b_mn)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g).to(cuda)
+    a_dev = (a.t().contiguous() if a_mn else a).to(cuda)
+    b_dev = (b.t().contiguous() if b_mn else b).to(cuda)
+    kw = dict(M=M, N=N, K=K, bias1=bias, precision="bf16")
+    if a_mn:
+        kw["a_strides"] = (1, M)
+    if b_mn:
+        kw["b_strides"] = (1, N)
+    monkeypatch.setenv("ICD_GEMM_FORCE_PLAN", plan)
+    monkeypatch.setenv("ICD_GEMM_CLUSTER", "1,1")
+    c0 = ops.gemm(a_dev, b_dev, **kw)
+    monkeypatch.setenv("ICD_GEMM_CLUSTER", cluster)
+    c = ops.gemm(a_dev, b_dev, **kw)
+    ref = a.bfloat16().double() @ b.bfloat16().double().t() + bias.double().cpu()
+    H.assert_close_norm(c, ref, 2e-5, "clustered tc gemm %s majors (%d,%d) %dx%dx%d" % (cluster, a_mn, b_mn, M, N, K))
+    assert torch.equal(c, c0), "cluster multicast must not change a single bit"
+
+
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (1, 1), (0, 1)])
 @pytest.mark.parametrize("M,N,K", [(200, 9490, 512), (64, 300, 2048), (5120, 2048, 520)])
 def test_gemm_fp32x3_is_fp32_grade(cuda, M, N, K, a_mn, b_mn):

@@ -58,6 +58,48 @@ def run(name, M, N, K, a_mn=False, b_mn=False, fp32=True, bf16=False, mask=False
     print("%-34s M=%6d N=%5d K=%6d  %8.1f us  %7.1f TF/s" % (name, M, N, K, us, 2.0 * M * N * K / us / 1e6), flush=True)
 
 
+if "--clusters" in sys.argv:
+    # sweep of the cm x cn multicast clusters and tile / split-K plans on the in-loop (M = batch) contractions
+    shapes = [("K2 z", B, NZ, D, dict(bias=True), ["128,1", "64,1", "256,1"]),
+              ("K4 gates", B, 4 * D, C, dict(add=True), ["64,1", "128,1", "128,2", "256,2", "256,4"]),
+              ("d_gated", B, C, 4 * D, dict(b_mn=True), ["64,1", "128,1", "128,2", "256,2", "256,4"]),
+              ("dh", B, D, NZ, dict(b_mn=True), ["128,8", "64,4", "128,4", "64,8", "256,8", "256,16"])]
+    for name, M, N, K, kw, plans in shapes:
+        for plan in plans:
+            for cl in ["1,1", "2,1", "1,2", "2,2", "4,1", "4,2", "2,4", "1,4"]:
+                os.environ["ICD_GEMM_FORCE_PLAN"] = plan
+                os.environ["ICD_GEMM_CLUSTER"] = cl
+                os.environ["ICD_GEMM_PAIR"] = "0"
+                run("%s plan %s cluster %s" % (name, plan, cl), M, N, K, iters=100, **kw)
+    sys.exit(0)
+if "--kslope" in sys.argv:
+    # time against K at fixed M x N and plan: slope = cost of one k-block, intercept = launch + prologue + epilogue
+    os.environ["ICD_GEMM_PAIR"] = "0"
+    for plan in ["64,1", "128,1", "256,1"]:
+        os.environ["ICD_GEMM_FORCE_PLAN"] = plan
+        for K in [64, 256, 512, 1024, 2048, 4096, 8192]:
+            run("plan %s" % plan, B, 4 * D, K, iters=100)
+    for K in [64, 256, 512, 1024, 2048, 4096, 8192]:
+        a = torch.randn(B, K, device=dev, dtype=torch.bfloat16); b = torch.randn(4 * D, K, device=dev, dtype=torch.bfloat16)
+        out = torch.empty(B, 4 * D, device=dev, dtype=torch.bfloat16)
+        for _ in range(3):
+            torch.matmul(a, b.t(), out=out)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(100):
+                torch.matmul(a, b.t(), out=out)
+        g.replay(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            g.replay()
+        e1.record(); torch.cuda.synchronize()
+        print("cuBLAS (calibration) K=%5d  %7.1f us" % (K, e0.elapsed_time(e1) * 1e3 / 500), flush=True)
+    sys.exit(0)
+if "--one" in sys.argv:            # one shape, for ncu: python tools/gemm_bench.py --one  (K4 gates, plan from the environment)
+    PROFILE = True
+    run("K4 gates (step)", B, 4 * D, C, add=True)
+    sys.exit(0)
 if "--dh" in sys.argv:
     run("dh (step)", B, D, NZ, b_mn=True, iters=200)
     run("d_gated (step)", B, C, 4 * D, b_mn=True, iters=200)
