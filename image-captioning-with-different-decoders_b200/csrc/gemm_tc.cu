@@ -330,6 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n_blk = mn ? (tile_rows + 63) / 64 : 1;                 // TMA boxes per k-block
         const CUtensorMap* tm = which ? &tmB : &tmA;
         const uint32_t s_base = which ? sB : sA;
+        if (elect_one()) {                                                // one thread runs the whole loop (see the MMA issuer)
         int stage = par; uint32_t phase = 0;
         int it = 0;                                                       // k-blocks seen so far (all units)
         for (int unit = unit0; unit < num_units; unit += unit_stride) {
@@ -340,7 +341,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 if ((it & 1) != par) continue;
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);            // every CTA of the cluster row / column has consumed this slot
-                if (elect_one()) {
+                {
                     TRACE(which, kb);
                     const uint32_t fb = full0 + 8 * stage;
                     mbar_arrive_expect_tx(fb, tile_bytes);           // all slices of this operand tile, whoever sends them
@@ -355,47 +356,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
-                __syncwarp();
                 stage += 2;
                 if (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
             }
         }
+        }
+        __syncwarp();
     } else if (warp == MMA_WARP) {
         // =================================== MMA issuer ===================================
-        int stage = 0; uint32_t phase = 0;
-        int acc = 0; uint32_t acc_phase = 0;
-        const uint32_t idesc = C_::IDESC | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16);
-        const uint64_t a_kstep = p.a_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);   // descriptor units of 16 B
-        const uint64_t b_kstep = p.b_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
-        for (int unit = unit0; unit < num_units; unit += unit_stride) {
-            const int slice = unit / num_tiles;
-            const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
-            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);              // epilogue has drained this accumulator
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-            for (int kb = kb0; kb < kb1; ++kb) {
-                TRACE(4, kb);
-                mbar_wait(full0 + 8 * stage, phase);                  // TMA bytes have landed
-                TRACE(5, kb);
+        // ONE elected thread runs the whole loop: leaving an elect region after every k-block costs ~100 clocks of
+        // reconvergence behind the UTCHMMAs, and a UTCHMMA issues at best every 48 clocks whatever its N — the issuing thread
+        // is the bottleneck of the narrow tiles, so nothing else may sit on its critical path: the barrier of the NEXT ring
+        // slot is probed before the MMAs of the current one are issued (tools/micro/mma_loop.cu)
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            const uint32_t idesc = C_::IDESC | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16);
+            const int a_mn = p.a_mn, b_mn = p.b_mn;
+            const uint64_t a_kstep = a_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);   // descriptor units of 16 B
+            const uint64_t b_kstep = b_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
+            const uint16_t mc_all = (uint16_t)(mask_row | mask_col);
+            uint32_t ready = 0;                                           // the current slot's barrier was already seen complete
+            for (int unit = unit0; unit < num_units; unit += unit_stride) {
+                const int slice = unit / num_tiles;
+                const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);              // epilogue has drained this accumulator
                 tc_fence_after();
-                if (elect_one()) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    TRACE(4, kb);
+                    if (!ready) mbar_wait(full0 + 8 * stage, phase);      // TMA bytes have landed
+                    TRACE(5, kb);
+                    tc_fence_after();
+                    const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
+                    const uint32_t nphase = (stage + 1 == STAGES) ? (phase ^ 1) : phase;
+                    ready = mbar_test(full0 + 8 * nstage, nphase);        // consumed in the next iteration
                     TRACE(2, kb);
-                    const uint64_t adesc = make_smem_desc(sA + stage * A_BYTES, p.a_mn);
-                    const uint64_t bdesc = make_smem_desc(sB + stage * C_::B_BYTES, p.b_mn);
+                    const uint64_t adesc = make_smem_desc(sA + stage * A_BYTES, a_mn);
+                    const uint64_t bdesc = make_smem_desc(sB + stage * C_::B_BYTES, b_mn);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
                         tc_mma_f16(d_tmem, adesc + (uint64_t)k * a_kstep, bdesc + (uint64_t)k * b_kstep, idesc,
                                    (kb > kb0 || k > 0) ? 1u : 0u);
-                    if (CL == 1) tc_commit(empty0 + 8 * stage);       // smem slot reusable once these MMAs retire
-                    else tc_commit_mc(empty0 + 8 * stage, (uint16_t)(mask_row | mask_col));   // ... signalled to every producer that fills it
-                    if (kb == kb1 - 1) tc_commit(tfull0 + 8 * acc);   // accumulator complete -> epilogue
+                    if (CL == 1) tc_commit(empty0 + 8 * stage);           // smem slot reusable once these MMAs retire
+                    else tc_commit_mc(empty0 + 8 * stage, mc_all);        // ... signalled to every producer that fills it
+                    if (kb == kb1 - 1) tc_commit(tfull0 + 8 * acc);       // accumulator complete -> epilogue
                     TRACE(3, kb);
+                    stage = nstage; phase = nphase;
                 }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        __syncwarp();
     } else {
         // =================================== epilogue warps 5..12 ===================================
         const int q = warp & 3;                                       // TMEM lane quarter this warp may access
@@ -563,6 +575,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int n_blk = mn ? (which ? BN / 128 : BM / 64) : 1;
         const CUtensorMap* tm = which ? &tmB : &tmA;
         const uint32_t s_base = which ? sB : sA;
+        if (elect_one()) {
         int stage = par; uint32_t phase = 0;
         int it = 0;
         for (int unit = unit0; unit < num_units; unit += unit_stride) {
@@ -573,7 +586,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int kb = kb0; kb < kb1; ++kb, ++it) {
                 if ((it & 1) != par) continue;
                 mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                if (elect_one()) {
+                {
                     const uint32_t fb_leader = mapa_u32(full0 + 8 * stage, 0);
                     if (crank == 0) mbar_arrive_expect_tx(full0 + 8 * stage, 2 * tile_bytes);   // this operand's bytes of BOTH CTAs
                     const uint32_t dst = s_base + stage * tile_bytes;
@@ -582,19 +595,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         for (int j = 0; j < n_blk; ++j) tma_load_2d_2sm(dst + j * MN_BLOCK_BYTES, tm, r0 + 64 * j, kb * BK, fb_leader);
                     }
                 }
-                __syncwarp();
                 stage += 2;
                 if (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
             }
         }
+        }
+        __syncwarp();
     } else if (warp == MMA_WARP) {
         // =================================== MMA issuer (leader CTA only) ===================================
-        if (crank == 0) {
+        // one elected thread runs the whole loop; the next ring slot's barrier is probed before the current MMAs are issued
+        if (crank == 0 && elect_one()) {
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            const uint32_t idesc = C_::IDESC | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16);
-            const uint64_t a_kstep = p.a_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
-            const uint64_t b_kstep = p.b_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
+            const int a_mn = p.a_mn, b_mn = p.b_mn;
+            const uint32_t idesc = C_::IDESC | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+            const uint64_t a_kstep = a_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
+            const uint64_t b_kstep = b_mn ? (uint64_t)(2048 >> 4) : (uint64_t)(32 >> 4);
+            uint32_t ready = 0;
             for (int unit = unit0; unit < num_units; unit += unit_stride) {
                 const int slice = unit / num_tiles;
                 const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
@@ -602,24 +619,25 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(full0 + 8 * stage, phase);              // both CTAs' tiles have landed
+                    if (!ready) mbar_wait(full0 + 8 * stage, phase);  // both CTAs' tiles have landed
                     tc_fence_after();
-                    if (elect_one()) {
-                        const uint64_t adesc = make_smem_desc(sA + stage * A_BYTES, p.a_mn);
-                        const uint64_t bdesc = make_smem_desc(sB + stage * C_::BH_BYTES, p.b_mn);
+                    const int nstage = (stage + 1 == STAGES) ? 0 : stage + 1;
+                    const uint32_t nphase = (stage + 1 == STAGES) ? (phase ^ 1) : phase;
+                    ready = mbar_test(full0 + 8 * nstage, nphase);
+                    const uint64_t adesc = make_smem_desc(sA + stage * A_BYTES, a_mn);
+                    const uint64_t bdesc = make_smem_desc(sB + stage * C_::BH_BYTES, b_mn);
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k)
-                            tc_mma_f16_2sm(d_tmem, adesc + (uint64_t)k * a_kstep, bdesc + (uint64_t)k * b_kstep, idesc,
-                                           (kb > kb0 || k > 0) ? 1u : 0u);
-                        tc_commit_2sm(empty0 + 8 * stage, (uint16_t)0x3);                 // slot free in both CTAs
-                        if (kb == kb1 - 1) tc_commit_2sm(tfull0 + 8 * acc, (uint16_t)0x3);   // accumulator ready in both
-                    }
-                    __syncwarp();
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        tc_mma_f16_2sm(d_tmem, adesc + (uint64_t)k * a_kstep, bdesc + (uint64_t)k * b_kstep, idesc,
+                                       (kb > kb0 || k > 0) ? 1u : 0u);
+                    tc_commit_2sm(empty0 + 8 * stage, (uint16_t)0x3);                 // slot free in both CTAs
+                    if (kb == kb1 - 1) tc_commit_2sm(tfull0 + 8 * acc, (uint16_t)0x3);   // accumulator ready in both
+                    stage = nstage; phase = nphase;
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
+        __syncwarp();
     } else {
         // =================================== epilogue warps 5..12 (both CTAs, own TMEM half) ===================================
         const int q = warp & 3;
@@ -1078,6 +1096,9 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
         ICD_TRY(make_tmap(&tmB, reinterpret_cast<const __nv_bfloat16*>(B16), ldb, N, K, pl.bn / cm, b_mn, BK / cm));
     }
     const int cluster = mode == 2 ? 2 : cm;                    // CTAs along M that form one super tile
+    static const bool verbose = getenv("ICD_GEMM_VERBOSE") != nullptr;
+    if (verbose) fprintf(stderr, "[icd] gemm %d x %d x %d (a_mn %d b_mn %d): bn %d, splits %d x %d k-blocks, %s, cluster %d x %d\n", M, N, K,
+                         a_mn, b_mn, pl.bn, pl.splits, pl.kb_per_split, mode == 2 ? "cta_group::2 pairs" : "cta_group::1", cm, cn);
     KArgs k;
     EpiArgs& e = k.e;
     e.C = C; e.ldc = ldc; e.M = M; e.N = N; e.K = K; e.bias1 = bias1; e.bias2 = bias2;

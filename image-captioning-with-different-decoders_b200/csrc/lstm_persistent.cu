@@ -206,7 +206,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmA, const LstmSeqArgs p) {
     const uint32_t sRed = bars + 256;                                  // BWD: [MT][4 source ranks][128 rows] float4
     float4* gRed = reinterpret_cast<float4*>(gW + (size_t)p.nkb * LP_W_KB_BYTES + 256);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int B = p.B, L = p.L, H = p.H, K = p.K;
     const int MT = (B + LP_BM - 1) / LP_BM;
     const uint32_t crank = BWD ? cluster_ctarank() : 0u;
@@ -247,7 +247,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmA, const LstmSeqArgs p) {
     __syncthreads();
     if (BWD) cluster_sync_all();                           // peers' shared memory is live before any remote store targets it
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
     int stage = 0; uint32_t phase = 0;                     // A ring (producer and MMA warps keep their own copies)
     uint32_t acc_phase = 0;                                // accumulator hand-off (MMA and epilogue warps)
@@ -259,14 +259,19 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmA, const LstmSeqArgs p) {
         Cell4 ops;                                         // epilogue warps: cell operands of the first row tile, fetched early
         if (warp == 0) {
             // =================================== TMA producer + grid barrier ===================================
-            if (lane == 0 && has_gemm) {
-                grid_wait(p.bar, NC * (unsigned int)it);   // every CTA has published its rows of iteration it-1
-                fence_proxy_async_all();                   // ... and the async proxy (TMA) may now read them
+            // (whole warp in uniform control flow, one elected lane issues: tc_common.cuh elect_one)
+            if (has_gemm) {
+                if (lane == 0) grid_wait(p.bar, NC * (unsigned int)it);   // every CTA has published its rows of iteration it-1
+                __syncwarp();
+                fence_proxy_async_all();                       // ... and the async proxy (TMA) may now read them
                 for (int mt = 0; mt < MT; ++mt)
                     for (int kb = 0; kb < p.nkb; ++kb) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                        mbar_arrive_expect_tx(full0 + 8 * stage, LP_A_BYTES);
-                        tma_load_2d(sA + stage * LP_A_BYTES, &tmA, k0 + kb * TC_BK, a_row0 + mt * LP_BM, full0 + 8 * stage);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(full0 + 8 * stage, LP_A_BYTES);
+                            tma_load_2d(sA + stage * LP_A_BYTES, &tmA, k0 + kb * TC_BK, a_row0 + mt * LP_BM, full0 + 8 * stage);
+                        }
+                        __syncwarp();
                         if (++stage == S) { stage = 0; phase ^= 1; }
                     }
             }
@@ -279,7 +284,7 @@ lstm_seq_kernel(const __grid_constant__ CUtensorMap tmA, const LstmSeqArgs p) {
                     for (int kb = 0; kb < p.nkb; ++kb) {
                         mbar_wait(full0 + 8 * stage, phase);
                         tc_fence_after();
-                        if (lane == 0) {
+                        if (elect_one()) {
                             const uint64_t adesc = make_smem_desc(sA + stage * LP_A_BYTES, 0);
                             const uint64_t bdesc = make_smem_desc(sW + kb * LP_W_KB_BYTES, 0);
 #pragma unroll
