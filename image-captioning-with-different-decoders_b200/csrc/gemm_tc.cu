@@ -930,21 +930,23 @@ int pair_mode() {
 // 148 SMs; narrower tiles pay more shared-memory / L2 traffic per flop, split-K pays a second (reduce) kernel.
 struct Plan { int bn, splits, kb_per_split; double cost; };
 
-Plan make_plan(int M, int N, int K, bool allow_split) {
-    // Cost model in SM clocks, fitted to CUDA-graph replays of the train-step shapes (tools/gemm_bench.py --graph):
-    //   one k-block costs 560 + 7.1 clk per KB of operands the CTA pulls from L2 (the per-SM L2->smem path, ~46 B/clk, bounds
-    //   these tiles, not the tensor pipe); launch + prologue + epilogue ~4500; a split-K pass 6000 + ~1.05 clk per KB of
-    //   partial planes (written by the contraction, read back by the reduce pass or the deferred consumer).
+Plan make_plan(int M, int N, int K, bool allow_split, bool deferred = false) {
+    // Cost model in SM clocks, fitted to CUDA-graph replays of the in-loop shapes (tools/gemm_bench.py --plans / --kslope --graph,
+    // profiles/r02_gemm_plans.txt) AFTER the issue path was fixed (one elected thread per role, four producer warps):
+    //   one k-block costs 295 / 362 / 567 clk at BN = 64 / 128 / 256 — a UTCHMMA issues at best every 48 clk whatever its N, so the
+    //   narrow tiles are bound by the issuing thread, the 256-wide one by the tensor pipe (4 x 128 clk);
+    //   launch + prologue + epilogue 7400 / 8500 / 12000; a split-K reduce pass 3900 + 500 clk per MB of partial planes, or — when
+    //   the consumer sums the planes itself (deferred) — only the extra plane traffic, 300 clk per MB.
     const int tm = (M + BM - 1) / BM, nkb = (K + BK - 1) / BK;
     const int cand[3] = {256, 128, 64};
+    const double kb_clk[3] = {567.0, 362.0, 295.0}, fixed_clk[3] = {12000.0, 8500.0, 7400.0};
     Plan best; best.bn = 64; best.splits = 1; best.kb_per_split = nkb; best.cost = 1e300;
     double best_cost = 1e300;
-    const double plane_kb = (double)M * N * 4.0 / 1024.0;
+    const double plane_mb = (double)M * N * 4.0 / 1048576.0;
     for (int i = 0; i < 3; ++i) {
         const int bn = cand[i];
         if (i < 2 && N <= cand[i + 1]) continue;                 // a narrower tile already covers N
         const int tiles = tm * ((N + bn - 1) / bn);
-        const double clk_kb = 560.0 + 7.1 * ((BM + bn) * BK * 2 / 1024.0);
         int smax = 1;
         if (allow_split && nkb >= 8) {
             smax = ICD_NUM_SMS / tiles;
@@ -959,7 +961,8 @@ Plan make_plan(int M, int N, int K, bool allow_split) {
             double waves = units / ICD_NUM_SMS;                  // static round-robin: the busiest CTA does ceil() units,
             if (waves < 1.0) waves = 1.0;                        // but short tiles overlap their epilogues: blend
             else waves = 0.5 * (waves + std::ceil(waves));
-            const double cost = waves * kbs * clk_kb + 4500.0 + (sp > 1 ? 6000.0 + sp * plane_kb * 1.05 : 0.0);
+            const double split_cost = sp > 1 ? (deferred ? 300.0 * sp * plane_mb : 3900.0 + 500.0 * sp * plane_mb) : 0.0;
+            const double cost = waves * kbs * kb_clk[i] + fixed_clk[i] + split_cost;
             if (cost < best_cost) { best_cost = cost; best.bn = bn; best.splits = sp; best.kb_per_split = kbs; best.cost = cost; }
         }
     }
@@ -1031,7 +1034,11 @@ int icd_convert_bf16(const float* src, int64_t s_r, int64_t s_c, int rows, int c
 }
 
 int64_t icd_gemm_bf16_splitk_floats(int M, int N, int K) {
-    auto need = [&](int m) { const Plan p = make_plan(m, N, K, true); return p.splits > 1 ? (int64_t)p.splits * m * N : (int64_t)0; };
+    auto need = [&](int m) {                                   // either flavour of the plan (reduce pass / deferred to the consumer)
+        const Plan p = make_plan(m, N, K, true, false), q = make_plan(m, N, K, true, true);
+        const int sp = p.splits > q.splits ? p.splits : q.splits;
+        return sp > 1 ? (int64_t)sp * m * N : (int64_t)0;
+    };
     const int rem = tail_rows_to_split(M, N, K, true);
     return rem ? std::max(need(M - rem), need(rem)) : need(M);
 }
@@ -1063,7 +1070,7 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
             return 0;
         }
     }
-    Plan pl = make_plan(M, N, K, splitk_ws != nullptr && m_live == nullptr);   // a device-side row count excludes split-K
+    Plan pl = make_plan(M, N, K, splitk_ws != nullptr && m_live == nullptr, deferred_splits != nullptr);   // a device-side row count excludes split-K
     if (const char* f = getenv("ICD_GEMM_FORCE_PLAN")) {           // diagnostic: "bn,splits" (tools/gemm_bench.py)
         int bn = 0, sp = 0;
         if (sscanf(f, "%d,%d", &bn, &sp) == 2 && (bn == 64 || bn == 128 || bn == 256) && sp >= 1 && (sp == 1 || (splitk_ws && !m_live))) {

@@ -72,6 +72,20 @@ if "--clusters" in sys.argv:
                 os.environ["ICD_GEMM_PAIR"] = "0"
                 run("%s plan %s cluster %s" % (name, plan, cl), M, N, K, iters=100, **kw)
     sys.exit(0)
+if "--plans" in sys.argv:
+    # tile / split-K / pairing sweep on the in-loop (M = batch) contractions: the data the cost model of make_plan is fitted to
+    pair = os.environ.get("ICD_GEMM_PAIR", "0")
+    shapes = [("K2 z", B, NZ, D, dict(bias=True)), ("K4 gates", B, 4 * D, C, dict(add=True)),
+              ("d_gated", B, C, 4 * D, dict(b_mn=True)), ("dh", B, D, NZ, dict(b_mn=True)), ("h_lin", B, D, C, dict(bias=True, bf16=True))]
+    for name, M, N, K, kw in shapes:
+        for bn in [64, 128, 256]:
+            for sp in [1, 2, 3, 4, 6, 8, 12, 16]:
+                nkb = (K + 63) // 64
+                if sp > 1 and (nkb // sp < 2 or ((M + 127) // 128) * ((N + bn - 1) // bn) * sp > 160):
+                    continue
+                os.environ["ICD_GEMM_FORCE_PLAN"] = "%d,%d" % (bn, sp)
+                run("pair %s %s plan %d,%d" % (pair, name, bn, sp), M, N, K, iters=100, **kw)
+    sys.exit(0)
 if "--kslope" in sys.argv:
     # time against K at fixed M x N and plan: slope = cost of one k-block, intercept = launch + prologue + epilogue
     os.environ["ICD_GEMM_PAIR"] = "0"
