@@ -12,6 +12,7 @@
 // kernel only ever sees K-major operands.
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -43,6 +44,7 @@ struct Arena {
 // No transposed copies exist: the tensor-core kernel consumes MN-major operands directly (gemm_tc.cu).
 struct Bufs {
     void *We, *Wcat, *WihE, *WihC, *Wh, *Wc, *Wfc;                 // weights [out, in] (K-major for y = x W^T, MN-major B for dX = dY W)
+    void *WihCp;                                                   // W_ih[:, E:] with gate-permuted rows (fused LSTMCell epilogue)
     void *enc, *att_enc, *mean, *embx, *h, *gated, *hdrop;         // forward activations [rows, features]
     void *dY, *dz, *dh, *dc, *dae;                                 // backward: [rows, features]
     float* splitk; int64_t splitk_floats;                          // deterministic split-K slices
@@ -56,6 +58,7 @@ void carve(const icd_att_desc_t* d, Arena& a, Bufs& b) {
     b.ldE = up8(E); b.ldV = up8(V);
     b.We = a.take(A, C); b.Wcat = a.take(NZ, D); b.WihE = a.take(4 * D, b.ldE); b.WihC = a.take(4 * D, C);
     b.Wh = a.take(D, C); b.Wc = a.take(D, C); b.Wfc = a.take(V, D);
+    b.WihCp = a.take(4 * D, C);
     b.enc = d->enc16 ? const_cast<void*>(d->enc16) : a.take(B * P, C);      // caller-provided bf16 features are used in place
     b.att_enc = a.take(B * P, A); b.mean = a.take(B, C); b.embx = a.take(TB, b.ldE);
     b.h = a.take(TB + B, D);
@@ -150,6 +153,10 @@ int icd_attention_decoder_fwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
     CVT(d->w_hh, D, 4 * D, D, at16(u.Wcat, (int64_t)(A + C) * D), D);
     CVT(d->w_ih, E + C, 4 * D, E, u.WihE, u.ldE);
     CVT(d->w_ih + E, E + C, 4 * D, C, u.WihC, C);
+    static const bool fused_cell_env = [] { const char* e = getenv("ICD_FUSED_CELL"); return !e || e[0] != '0'; }();
+    const bool fused_cell = fused_cell_env && D % 16 == 0 && (E + C) % 4 == 0 && E % 4 == 0 && NZ % 4 == 0 &&
+                            (!d->drop_mask || D % 8 == 0) && (T * D) % 8 == 0;
+    if (fused_cell) ICD_TRY(icd_convert_bf16_gateperm(d->w_ih + E, E + C, D, C, u.WihCp, C, s));
     CVT(d->h_lin_w, C, D, C, u.Wh, C);
     CVT(d->c_lin_w, C, D, C, u.Wc, C);
     CVT(d->fc_w, D, V, D, u.Wfc, D);
@@ -184,6 +191,14 @@ int icd_attention_decoder_fwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
                                             zt + A, NZ, d->alphas + (size_t)t * P, (int64_t)T * P,
                                             d->awe_raw + (size_t)t * B * C, d->gate + (size_t)t * B * C,
                                             d->gated + (size_t)t * B * C, g16, (void*)s));                         // K3
+        if (fused_cell) {                                                                                           // K4 + LSTMCell
+            ICD_TRY(icd_gemm_bf16_lstm_cell(g16, C, u.WihCp, C, bt, D, C, d->xg + (size_t)t * B * 4 * D, 4 * D, zt + A + C, NZ, c_prev,
+                                            d->gates_act + (size_t)t * B * 4 * D, d->c_all + (size_t)(t + 1) * BD,
+                                            d->h_all + (size_t)(t + 1) * BD, d->hdrop + (size_t)t * D, (int64_t)T * D,
+                                            d->drop_mask ? d->drop_mask + (size_t)t * BD : nullptr, d->drop_scale,
+                                            at16(u.h, (int64_t)(t + 1) * B * D), at16(u.hdrop, (int64_t)t * D), s));
+            continue;
+        }
         MMX(g16, C, 0, u.WihC, C, 0, d->gates_pre, 4 * D, bt, 4 * D, C, nullptr, nullptr,
             d->xg + (size_t)t * B * 4 * D, 4 * D, zt + A + C, NZ, nullptr, nullptr, 0);                            // K4
         ICD_TRY(icd_lstm_pointwise_fwd(bt, D, d->gates_pre, c_prev, d->gates_act + (size_t)t * B * 4 * D,

@@ -54,8 +54,25 @@ struct EpiArgs {
     int vec;                                  // 4 / 2 / 1: widest vector (in floats) every row start of C / add / C16 allows
 };
 
+// Fused LSTMCell epilogue (models/attention.py:277-278 after the K4 contraction): the B operand is the GATE-PERMUTED copy of
+// W_ih[:, E:] (row ug*32 + g*8 + j = natural row g*D + ug*8 + j, icd_convert_bf16_gateperm), so every 32-column chunk of the
+// accumulator holds the four gates (i, f, g, o) of 8 hidden units and the epilogue thread that owns a row can finish the cell
+// for them: pre = acc + xg + z_hh, c = f*c_prev + i*g, h = o*tanh(c), dropout(h) — no gates_pre round trip, no second kernel.
+struct LstmEpi {
+    int on, D;
+    const float* xg; long long ld_xg;         // hoisted input term (+ both biases), natural gate layout [rows][4D]
+    const float* zhh; long long ld_zhh;       // h W_hh^T columns of z, natural gate layout
+    const float* c_prev;                      // [rows][D]
+    float* gates_act;                         // [rows][4D] activated gates (saved for the backward)
+    float* c_new; float* h_new;               // [rows][D]
+    float* hdrop; long long hdrop_stride;     // dropout(h) rows hdrop_stride apart, may be NULL
+    const unsigned char* mask; float scale;   // keep mask [rows][D] or NULL
+    __nv_bfloat16* h16; __nv_bfloat16* hdrop16;
+};
+
 struct KArgs {
     EpiArgs e;
+    LstmEpi lstm;
     int a_mn, b_mn;                           // 1: operand is MN-major in memory
     int splits, kb_per_split;                 // split-K: work unit = (tile, slice)
     float* partial;                           // [splits][M][N] raw accumulators when splits > 1
@@ -250,6 +267,70 @@ __device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ s
     }
 }
 
+__device__ __forceinline__ void ld8(const float* p, float (&x)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&x)[8]) {
+    *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(x[4], x[5], x[6], x[7]);
+}
+__device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const float (&x)[8]) {
+    uint4 pk;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(x[0], x[1]); pk.x = *reinterpret_cast<const uint32_t*>(&t);
+    t = __floats2bfloat162_rn(x[2], x[3]); pk.y = *reinterpret_cast<const uint32_t*>(&t);
+    t = __floats2bfloat162_rn(x[4], x[5]); pk.z = *reinterpret_cast<const uint32_t*>(&t);
+    t = __floats2bfloat162_rn(x[6], x[7]); pk.w = *reinterpret_cast<const uint32_t*>(&t);
+    *reinterpret_cast<uint4*>(p) = pk;
+}
+// One accumulator row of a 32-column chunk = gates (i, f, g, o) x 8 hidden units [8*ug, 8*ug + 8) of row m (see LstmEpi).
+// The row's operands are fetched BEFORE the epilogue warp waits for the accumulator (the loads — lane-strided 32-byte
+// segments, slow to issue — then hide behind the contraction); same arithmetic, in the same order, as the unfused pair
+// (contraction epilogue acc + add1 + add2, then lstm_pointwise_fwd).
+struct LstmRowOps { float a1[4][8], a2[4][8], cp[8]; uint2 mk; };
+__device__ __forceinline__ void lstm_prefetch_row(LstmRowOps& o, int m, int ug, const LstmEpi& L) {
+    const int D = L.D, u0 = ug * 8;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        ld8(L.xg + (long long)m * L.ld_xg + g * D + u0, o.a1[g]);
+        ld8(L.zhh + (long long)m * L.ld_zhh + g * D + u0, o.a2[g]);
+    }
+    ld8(L.c_prev + (long long)m * D + u0, o.cp);
+    o.mk = make_uint2(0x01010101u, 0x01010101u);
+    if (L.hdrop && L.mask) o.mk = *reinterpret_cast<const uint2*>(L.mask + (long long)m * D + u0);
+}
+__device__ __forceinline__ void lstm_epilogue_row(const uint32_t (&v)[32], const LstmRowOps& o, int m, int ug, const LstmEpi& L) {
+    const int D = L.D, u0 = ug * 8;
+    float gi[8], gf[8], gg[8], go[8], c[8], h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        gi[j] = sigmoidf_(__uint_as_float(v[j]) + o.a1[0][j] + o.a2[0][j]);
+        gf[j] = sigmoidf_(__uint_as_float(v[8 + j]) + o.a1[1][j] + o.a2[1][j]);
+        gg[j] = tanhf(__uint_as_float(v[16 + j]) + o.a1[2][j] + o.a2[2][j]);
+        go[j] = sigmoidf_(__uint_as_float(v[24 + j]) + o.a1[3][j] + o.a2[3][j]);
+        c[j] = gf[j] * o.cp[j] + gi[j] * gg[j];
+        h[j] = go[j] * tanhf(c[j]);
+    }
+    if (L.gates_act) {
+        float* ga = L.gates_act + (long long)m * 4 * D + u0;
+        st8(ga, gi); st8(ga + D, gf); st8(ga + 2 * D, gg); st8(ga + 3 * D, go);
+    }
+    st8(L.c_new + (long long)m * D + u0, c);
+    st8(L.h_new + (long long)m * D + u0, h);
+    if (L.h16) st8_bf16(L.h16 + (long long)m * D + u0, h);
+    if (L.hdrop) {
+        float hd[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool keep = (((j < 4 ? o.mk.x : o.mk.y) >> (8 * (j & 3))) & 0xffu) != 0;
+            hd[j] = L.mask ? (keep ? h[j] * L.scale : 0.f) : h[j];
+        }
+        st8(L.hdrop + (long long)m * L.hdrop_stride + u0, hd);
+        if (L.hdrop16) st8_bf16(L.hdrop16 + (long long)m * L.hdrop_stride + u0, hd);
+    }
+}
+
 #ifdef ICD_GEMM_TRACE
 __device__ long long g_trace[6][512];      // [0] producer: empty-wait done, [1] producer: TMA issued, [2] MMA: full-wait done, [3] MMA: issued
 #define TRACE(slot, idx) do { if (blockIdx.x == 0 && (idx) < 512) g_trace[slot][idx] = clock64(); } while (0)
@@ -425,9 +506,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ee.bias1 = ee.bias2 = ee.add1 = ee.add2 = nullptr; ee.row_mask = nullptr; ee.beta = 0.f; ee.C16 = nullptr;
                 ee.vec = (e.N % 4 == 0) ? 4 : ((e.N % 2 == 0) ? 2 : 1);
             }
+            const int mrow0 = m0 + q * 32;
+            LstmRowOps lops;
+            const bool lstm_row = p.lstm.on && (n0 + cg * 32 < e.N) && (mrow0 + lane < M_eff);
+            if (lstm_row) lstm_prefetch_row(lops, mrow0 + lane, (n0 + cg * 32) >> 5, p.lstm);   // hides behind the contraction
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
-            const int mrow0 = m0 + q * 32;
             bool released = false;
 #pragma unroll 1
             for (int c = cg; c < NCHUNK; c += 2) {
@@ -441,6 +525,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tc_fence_before();
                         if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
                         released = true;
+                    }
+                    if (p.lstm.on) {                                  // fused LSTMCell: the thread finishes its row's 8 units
+                        if (lstm_row) lstm_epilogue_row(v, lops, mrow0 + lane, nb >> 5, p.lstm);   // BN = 64: chunk c == cg
+                        continue;
                     }
 #pragma unroll
                     for (int g4 = 0; g4 < 8; ++g4)
@@ -779,6 +867,22 @@ __global__ void convert_rows_kernel(const float* __restrict__ src, long long s_r
     }
 }
 
+// gate-permuting variant for an LSTM weight block [4D][cols] (gate-major rows i|f|g|o): destination row
+// ug*32 + g*8 + j = source row g*D + ug*8 + j, so that 32 consecutive rows hold the four gates of 8 hidden units (LstmEpi).
+__global__ void convert_rows_gateperm_kernel(const float* __restrict__ src, long long s_r, int D, int cols,
+                                             __nv_bfloat16* __restrict__ dst, long long ldd) {
+    const long long n4 = cols >> 2, total = 4LL * D * n4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int rp = (int)(i / n4), c = (int)(i % n4) * 4;          // destination row
+        const int ug = rp >> 5, g = (rp >> 3) & 3, j = rp & 7;
+        const float4 x = ld_stream_f4(src + (long long)(g * D + ug * 8 + j) * s_r + c);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(dst + (long long)rp * ldd + c) = pk;
+    }
+}
+
 // transposing variant: src is contiguous along r (s_r == 1, s_c = source leading dimension).  32x32 smem tiles.
 __global__ void convert_transpose_kernel(const float* __restrict__ src, long long s_c, int rows, int cols,
                                          __nv_bfloat16* __restrict__ dst, long long ldd) {
@@ -1033,6 +1137,44 @@ int icd_convert_bf16(const float* src, int64_t s_r, int64_t s_c, int rows, int c
     return 0;
 }
 
+int icd_convert_bf16_gateperm(const float* src, int64_t s_r, int D, int cols, void* dst, int64_t ldd, cudaStream_t s) {
+    ICD_CHECK_ARG(D % 8 == 0 && cols % 4 == 0 && s_r % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && ldd % 8 == 0,
+                  "convert_bf16_gateperm: D %% 8, cols %% 4 and 16-byte aligned rows required (D=%d cols=%d)", D, cols);
+    const long long total = 4LL * D * (cols / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > ICD_NUM_SMS * 16) blocks = ICD_NUM_SMS * 16;
+    convert_rows_gateperm_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, s_r, D, cols, reinterpret_cast<__nv_bfloat16*>(dst), ldd);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+// gates contraction + LSTMCell in one kernel (see LstmEpi): A16 = gated [rows][K] bf16, Wp16 = gate-permuted W_ih[:, E:] [4D][K]
+int icd_gemm_bf16_lstm_cell(const void* A16, int64_t lda, const void* Wp16, int64_t ldb, int rows, int D, int K,
+                            const float* xg, int64_t ld_xg, const float* zhh, int64_t ld_zhh, const float* c_prev,
+                            float* gates_act, float* c_new, float* h_new, float* hdrop, int64_t hdrop_stride,
+                            const uint8_t* mask, float scale, void* h16, void* hdrop16, cudaStream_t s) {
+    if (rows == 0) return 0;
+    ICD_CHECK_ARG(D % 16 == 0 && K > 0, "gemm_lstm_cell: D must be a multiple of 16 (D=%d)", D);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    ICD_CHECK_ARG(al16(xg) && al16(zhh) && al16(c_prev) && al16(gates_act) && al16(c_new) && al16(h_new) && al16(hdrop) && al16(h16) &&
+                  al16(hdrop16) && (!mask || (reinterpret_cast<uintptr_t>(mask) & 7) == 0) && ld_xg % 4 == 0 && ld_zhh % 4 == 0 &&
+                  hdrop_stride % 8 == 0, "gemm_lstm_cell: operands must be 16-byte aligned");
+    const int N = 4 * D;
+    CUtensorMap tmA, tmB;
+    ICD_TRY(make_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(A16), lda, rows, K, BM, 0));
+    ICD_TRY(make_tmap(&tmB, reinterpret_cast<const __nv_bfloat16*>(Wp16), ldb, N, K, 64, 0));
+    KArgs k = {};
+    EpiArgs& e = k.e;
+    e.C = nullptr; e.ldc = 0; e.M = rows; e.N = N; e.K = K; e.vec = 4; e.beta = 0.f;
+    k.a_mn = 0; k.b_mn = 0; k.splits = 1; k.kb_per_split = (K + BK - 1) / BK; k.partial = nullptr; k.cm = 1; k.cn = 1; k.m_live = nullptr;
+    LstmEpi& L = k.lstm;
+    L.on = 1; L.D = D; L.xg = xg; L.ld_xg = ld_xg; L.zhh = zhh; L.ld_zhh = ld_zhh; L.c_prev = c_prev; L.gates_act = gates_act;
+    L.c_new = c_new; L.h_new = h_new; L.hdrop = hdrop; L.hdrop_stride = hdrop_stride; L.mask = mask; L.scale = scale;
+    L.h16 = reinterpret_cast<__nv_bfloat16*>(h16); L.hdrop16 = reinterpret_cast<__nv_bfloat16*>(hdrop16);
+    const int units = ((rows + BM - 1) / BM) * (N / 64);
+    return launch<64>(tmA, tmB, k, units, s);
+}
+
 int64_t icd_gemm_bf16_splitk_floats(int M, int N, int K) {
     auto need = [&](int m) {                                   // either flavour of the plan (reduce pass / deferred to the consumer)
         const Plan p = make_plan(m, N, K, true, false), q = make_plan(m, N, K, true, true);
@@ -1106,7 +1248,7 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
     static const bool verbose = getenv("ICD_GEMM_VERBOSE") != nullptr;
     if (verbose) fprintf(stderr, "[icd] gemm %d x %d x %d (a_mn %d b_mn %d): bn %d, splits %d x %d k-blocks, %s, cluster %d x %d\n", M, N, K,
                          a_mn, b_mn, pl.bn, pl.splits, pl.kb_per_split, mode == 2 ? "cta_group::2 pairs" : "cta_group::1", cm, cn);
-    KArgs k;
+    KArgs k = {};
     EpiArgs& e = k.e;
     e.C = C; e.ldc = ldc; e.M = M; e.N = N; e.K = K; e.bias1 = bias1; e.bias2 = bias2;
     e.add1 = add1; e.ld1 = ld1; e.add2 = add2; e.ld2 = ld2; e.row_mask = row_mask; e.beta = beta;

@@ -25,6 +25,14 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
 // epilogue included).  Only for calls whose epilogue is empty (no bias / add / mask / beta / C16).
 // m_live != NULL: DEVICE-side row count — only rows < min(M, *m_live) are computed and written (tile loop bounds are
 // derived in the kernel, after its dependency wait); the plan then never splits K.
+// LSTM weight block [4D][cols] -> bf16 with the rows gate-permuted (row ug*32 + g*8 + j = source row g*D + ug*8 + j)
+int icd_convert_bf16_gateperm(const float* src, int64_t s_r, int D, int cols, void* dst, int64_t ldd, cudaStream_t s);
+// gates = A W^T (W gate-permuted) + xg + z_hh followed by the LSTMCell, in ONE kernel: writes gates_act / c_new / h_new /
+// dropout(h) (+ bf16 copies of h and dropout(h)); the arithmetic equals the contraction + icd_lstm_pointwise_fwd pair bit for bit
+int icd_gemm_bf16_lstm_cell(const void* A16, int64_t lda, const void* Wp16, int64_t ldb, int rows, int D, int K,
+                            const float* xg, int64_t ld_xg, const float* zhh, int64_t ld_zhh, const float* c_prev,
+                            float* gates_act, float* c_new, float* h_new, float* hdrop, int64_t hdrop_stride,
+                            const uint8_t* mask, float scale, void* h16, void* hdrop16, cudaStream_t s);
 int icd_splitk_finish(const float* splitk_ws, int splits, int M, int N, float* C, int64_t ldc, void* C16, int64_t ldc16,
                       cudaStream_t s);
 int64_t icd_gemm_bf16_splitk_floats(int M, int N, int K);
