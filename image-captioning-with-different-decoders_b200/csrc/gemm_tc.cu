@@ -10,8 +10,8 @@
 //     thread, accumulators in TMEM (2 stages x BN fp32 columns: the epilogue of tile i overlaps the MMAs of tile i+1);
 //   * sync: mbarrier full/empty ring (TMA <-> MMA), tcgen05.commit -> mbarrier (MMA -> TMA slot release and
 //     MMA -> epilogue), tmem_empty barrier (epilogue -> MMA);
-//   * warp roles (416 threads): warps 0-3 TMA producers (A / B x even / odd k-blocks), warp 4 TMEM allocator + MMA issuer,
-//     warps 5-12 epilogue
+//   * warp roles (384 threads): warps 0-2 TMA producers (k-blocks round-robin), warp 3 TMEM allocator + MMA issuer,
+//     warps 4-11 epilogue
 //     (tcgen05.ld 32x32b.x32 -> registers -> padded smem transpose -> coalesced 128-bit loads/stores with the fused
 //     epilogue: bias1 + bias2 + add1 + add2, row mask, beta, optional bf16 copy of the result);
 //   * persistent: grid = min(#work units, #SMs), static round-robin schedule;
@@ -33,13 +33,13 @@ constexpr int EPI_LD = 32;                           // row of the per-warp 32x3
                                                      // (lane = row) and the 128-bit tile reads (8 lanes = one row) are
                                                      // bank-conflict free without padding
 constexpr int NUM_EPI_WARPS = 8;
-// warp roles: warps 0-3 TMA producers (operand A / B x even / odd k-blocks: one UTMALDG costs ~100 issue clocks, a single
-// producer thread caps the ring at ~400 clocks per k-block — twice the MMA time of a 128 x 64 tile), warp 4 TMEM
-// allocator + MMA issuer, warps 5-12 epilogue
-constexpr int NUM_PROD_WARPS = 4;
+// warp roles: warps 0-2 TMA producers (k-blocks round-robin: one UTMALDG costs ~100 issue clocks, a single producer thread
+// caps the ring at ~400 clocks per k-block — twice the MMA time of a 128 x 64 tile), warp 3 TMEM allocator + MMA issuer,
+// warps 4-11 epilogue.  12 warps = 3 per scheduler: 168 registers per thread (13 warps would put 4 on one scheduler: 128)
+constexpr int NUM_PROD_WARPS = 3;
 constexpr int MMA_WARP = NUM_PROD_WARPS;
 constexpr int EPI_WARP0 = NUM_PROD_WARPS + 1;
-constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);        // 416
+constexpr int NUM_THREADS = 32 * (EPI_WARP0 + NUM_EPI_WARPS);        // 384
 constexpr int MN_BLOCK_BYTES = TC_MN_BLOCK_BYTES;    // one 64-element MN block of an MN-major tile: BK rows x 128 B
 
 struct EpiArgs {
@@ -108,17 +108,45 @@ __device__ __forceinline__ float4 epi_ld4(const float* sE, int r, int g) { retur
 //   vec4 : lane -> 4 consecutive columns, 8 lanes per row, 4 rows per instruction (128-bit accesses)
 //   vec2 : lane -> 2 consecutive columns, 16 lanes per row, 2 rows per instruction (64-bit; row stride even, e.g. V = 9490)
 //   else : lane -> 1 column, 1 row per instruction (still 128 B coalesced); also the N tail of the other two
-__device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ sE, int lane, int mrow0, int nb,
-                                                     const EpiArgs& e) {
+// Row validity of a 32-row strip (bit r: row mrow0 + r inside M / not masked out): ONE coalesced byte load + two ballots per
+// tile, issued before the epilogue warp waits for the accumulator so the load latency hides behind the contraction.
+__device__ __forceinline__ void epi_row_bits(const EpiArgs& e, int lane, int mrow0, unsigned& rows_in, unsigned& rows_keep) {
     unsigned inb = (mrow0 + lane < e.M) ? 1u : 0u;
     unsigned keep = inb;
     if (e.row_mask && inb) keep = e.row_mask[mrow0 + lane] ? 1u : 0u;
-    const unsigned rows_in = __ballot_sync(0xffffffffu, inb != 0), rows_keep = __ballot_sync(0xffffffffu, keep != 0);
+    rows_in = __ballot_sync(0xffffffffu, inb != 0); rows_keep = __ballot_sync(0xffffffffu, keep != 0);
+}
+// bias1 / bias2 of the lane's four columns of chunk nb in the 128-bit store paths (vec 4: columns 4j..4j+3; vec 3: the shifted
+// mapping of the 8-byte-aligned rows), loaded before the accumulator chunk is read and NOT touched until the store loop (the
+// first use is where the load latency would be paid); zero where those paths do not apply.
+struct Bias4 { float4 a, b; };
+__device__ __forceinline__ Bias4 epi_bias4(const EpiArgs& e, int lane, int nb) {
+    Bias4 r; r.a = make_float4(0.f, 0.f, 0.f, 0.f); r.b = r.a;
+    if (nb + 32 > e.N || (!e.bias1 && !e.bias2)) return r;
+    if (e.vec >= 4) {
+        const int n = nb + (lane & 7) * 4;
+        if (e.bias1) r.a = *reinterpret_cast<const float4*>(e.bias1 + n);
+        if (e.bias2) r.b = *reinterpret_cast<const float4*>(e.bias2 + n);
+    } else if (e.vec == 3) {
+        const int j = lane & 7;
+        const bool odd = ((lane >> 3) & 1) != 0, edge = odd && j == 7;
+        float t[4], u[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int col = edge ? (q < 2 ? q : 28 + q) : 4 * j + (odd ? 2 : 0) + q;
+            t[q] = e.bias1 ? __ldg(e.bias1 + nb + col) : 0.f;
+            u[q] = e.bias2 ? __ldg(e.bias2 + nb + col) : 0.f;
+        }
+        r.a = make_float4(t[0], t[1], t[2], t[3]); r.b = make_float4(u[0], u[1], u[2], u[3]);
+    }
+    return r;
+}
+
+__device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ sE, int lane, int mrow0, int nb,
+                                                     const EpiArgs& e, unsigned rows_in, unsigned rows_keep, const Bias4& bias) {
+    const float4 bsum = make_float4(bias.a.x + bias.b.x, bias.a.y + bias.b.y, bias.a.z + bias.b.z, bias.a.w + bias.b.w);
     if (e.vec >= 4 && nb + 32 <= e.N) {
         const int cc = (lane & 7) * 4, n = nb + cc;
-        float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e.bias1) { const float4 b = *reinterpret_cast<const float4*>(e.bias1 + n); bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w; }
-        if (e.bias2) { const float4 b = *reinterpret_cast<const float4*>(e.bias2 + n); bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w; }
         if (!e.add1 && !e.add2 && e.beta == 0.f) {
             // plain store (bias + row mask only): no operand prefetch, the loop is one shared-memory read and one store per row
 #pragma unroll
@@ -183,9 +211,7 @@ __device__ __forceinline__ void epilogue_store_chunk(const float* __restrict__ s
         int col[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) col[q] = edge ? (q < 2 ? q : 28 + q) : 4 * j + (odd ? 2 : 0) + q;
-        float b[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) b[q] = (e.bias1 ? __ldg(e.bias1 + nb + col[q]) : 0.f) + (e.bias2 ? __ldg(e.bias2 + nb + col[q]) : 0.f);
+        const float b[4] = {bsum.x, bsum.y, bsum.z, bsum.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int rr = i * 4 + (lane >> 3), m = mrow0 + rr;
@@ -370,8 +396,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB) : "memory");
         // a slot is free once every CTA this one multicasts into (its cluster row and column) has consumed it
-        // full: one arrive.expect_tx from the A producer and one from the B producer of the stage
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 2); mbar_init(empty0 + 8 * i, (uint32_t)(CM + CN - 1)); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, (uint32_t)(CM + CN - 1)); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -397,50 +422,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp < NUM_PROD_WARPS) {
         // =================================== TMA producers ===================================
-        // producer warp w: operand (w & 1: 0 = A, 1 = B) of every second k-block (parity w >> 1); whole warp in uniform control
-        // flow, one elected lane issues (see elect_one).  STAGES is even, so a producer always meets stages of one parity.
-        const int which = warp & 1, par = warp >> 1;
-        // slice of the tile this CTA fetches for its cluster row (A) / column (B): rows of a K-major tile, k-rows of an MN-major one
-        const int CS = which ? CM : CN, rs = which ? rm : rn;
-        const uint16_t mc_mask = which ? mask_col : mask_row;
-        const int mn = which ? p.b_mn : p.a_mn;
-        const int tile_rows = which ? BN : BM;
-        const uint32_t tile_bytes = which ? (uint32_t)C_::B_BYTES : (uint32_t)A_BYTES;
-        const uint32_t slice_off = mn ? (uint32_t)(rs * (MN_BLOCK_BYTES / CS)) : (uint32_t)(rs * (int)(tile_bytes / CS));
-        const int slice_row = mn ? 0 : rs * (tile_rows / CS), slice_k = mn ? rs * (BK / CS) : 0;
-        const int n_blk = mn ? (tile_rows + 63) / 64 : 1;                 // TMA boxes per k-block
-        const CUtensorMap* tm = which ? &tmB : &tmA;
-        const uint32_t s_base = which ? sB : sA;
-        if (elect_one()) {                                                // one thread runs the whole loop (see the MMA issuer)
-        int stage = par; uint32_t phase = 0;
-        int it = 0;                                                       // k-blocks seen so far (all units)
-        for (int unit = unit0; unit < num_units; unit += unit_stride) {
-            const int tile = unit % num_tiles, slice = unit / num_tiles;
-            const int m0 = ((tile % tiles_mc) * CM + rm) * BM, n0 = ((tile / tiles_mc) * CN + rn) * BN;
-            const int r0 = (which ? n0 : m0) + slice_row;
-            const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
-            for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                if ((it & 1) != par) continue;
-                mbar_wait(empty0 + 8 * stage, phase ^ 1);            // every CTA of the cluster row / column has consumed this slot
-                {
-                    TRACE(which, kb);
+        // producer warp w fetches every NUM_PROD_WARPS-th k-block (both operands); ONE elected thread runs the whole loop (see
+        // the MMA issuer).  A UTMALDG costs ~100 issue clocks: one producer alone caps the ring at ~400 clocks per k-block.
+        // In a cluster this CTA fetches slice rn of its A tile for its cluster row and slice rm of its B tile for its cluster
+        // column (rows of a K-major tile, k-rows of every 64-wide block of an MN-major one) and multicasts them.
+        const int a_mn = p.a_mn, b_mn = p.b_mn;
+        const uint32_t a_off = a_mn ? (uint32_t)(rn * (MN_BLOCK_BYTES / CN)) : (uint32_t)(rn * (A_BYTES / CN));
+        const uint32_t b_off = b_mn ? (uint32_t)(rm * (MN_BLOCK_BYTES / CM)) : (uint32_t)(rm * (C_::B_BYTES / CM));
+        const int a_row = a_mn ? 0 : rn * (BM / CN), a_k = a_mn ? rn * (BK / CN) : 0;
+        const int b_row = b_mn ? 0 : rm * (BN / CM), b_k = b_mn ? rm * (BK / CM) : 0;
+        if (elect_one()) {
+            int stage = warp; uint32_t phase = 0;
+            int it = 0;                                                   // k-blocks seen so far (all units)
+            for (int unit = unit0; unit < num_units; unit += unit_stride) {
+                const int tile = unit % num_tiles, slice = unit / num_tiles;
+                const int m0 = ((tile % tiles_mc) * CM + rm) * BM, n0 = ((tile / tiles_mc) * CN + rn) * BN;
+                const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    if ((it % NUM_PROD_WARPS) != warp) continue;
+                    mbar_wait_backoff(empty0 + 8 * stage, phase ^ 1);   // every CTA of the cluster row / column has consumed this slot
+                    TRACE(0, kb);
                     const uint32_t fb = full0 + 8 * stage;
-                    mbar_arrive_expect_tx(fb, tile_bytes);           // all slices of this operand tile, whoever sends them
-                    const uint32_t dst = s_base + stage * tile_bytes + slice_off;
-                    if (!mn) {
-                        if (CS == 1) tma_load_2d(dst, tm, kb * BK, r0, fb);
-                        else tma_load_2d_mc(dst, tm, kb * BK, r0, fb, mc_mask);
+                    mbar_arrive_expect_tx(fb, C_::STAGE_BYTES);      // all slices of both tiles, whoever sends them
+                    const uint32_t a_dst = sA + stage * A_BYTES + a_off, b_dst = sB + stage * C_::B_BYTES + b_off;
+                    if (!a_mn) {
+                        if (CN == 1) tma_load_2d(a_dst, &tmA, kb * BK, m0 + a_row, fb);
+                        else tma_load_2d_mc(a_dst, &tmA, kb * BK, m0 + a_row, fb, mask_row);
                     } else {
-                        for (int j = 0; j < n_blk; ++j) {
-                            if (CS == 1) tma_load_2d(dst + j * MN_BLOCK_BYTES, tm, r0 + 64 * j, kb * BK, fb);
-                            else tma_load_2d_mc(dst + j * MN_BLOCK_BYTES, tm, r0 + 64 * j, kb * BK + slice_k, fb, mc_mask);
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j) {
+                            if (CN == 1) tma_load_2d(a_dst + j * MN_BLOCK_BYTES, &tmA, m0 + 64 * j, kb * BK, fb);
+                            else tma_load_2d_mc(a_dst + j * MN_BLOCK_BYTES, &tmA, m0 + 64 * j, kb * BK + a_k, fb, mask_row);
                         }
                     }
+                    if (!b_mn) {
+                        if (CM == 1) tma_load_2d(b_dst, &tmB, kb * BK, n0 + b_row, fb);
+                        else tma_load_2d_mc(b_dst, &tmB, kb * BK, n0 + b_row, fb, mask_col);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < (BN + 63) / 64; ++j) {
+                            if (CM == 1) tma_load_2d(b_dst + j * MN_BLOCK_BYTES, &tmB, n0 + 64 * j, kb * BK, fb);
+                            else tma_load_2d_mc(b_dst + j * MN_BLOCK_BYTES, &tmB, n0 + 64 * j, kb * BK + b_k, fb, mask_col);
+                        }
+                    }
+                    TRACE(1, kb);
+                    stage += NUM_PROD_WARPS;
+                    if (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
                 }
-                stage += 2;
-                if (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
             }
-        }
         }
         __syncwarp();
     } else if (warp == MMA_WARP) {
@@ -490,7 +519,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
     } else {
-        // =================================== epilogue warps 5..12 ===================================
+        // =================================== epilogue warps 4..11 ===================================
         const int q = warp & 3;                                       // TMEM lane quarter this warp may access
         const int cg = (warp - EPI_WARP0) >> 2;                       // column group: chunks cg, cg+2, ...
         float* sE = sEpi + (warp - EPI_WARP0) * 32 * EPI_LD;
@@ -510,6 +539,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             LstmRowOps lops;
             const bool lstm_row = p.lstm.on && (n0 + cg * 32 < e.N) && (mrow0 + lane < M_eff);
             if (lstm_row) lstm_prefetch_row(lops, mrow0 + lane, (n0 + cg * 32) >> 5, p.lstm);   // hides behind the contraction
+            unsigned rows_in, rows_keep;                                 // ... and so does the row mask
+            epi_row_bits(ee, lane, mrow0, rows_in, rows_keep);
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             bool released = false;
@@ -518,6 +549,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int nb = n0 + c * 32;
                 const bool last = (c + 2 >= NCHUNK);
                 if (nb < e.N && mrow0 < M_eff) {                        // warp-uniform
+                    const Bias4 bias_c = epi_bias4(ee, lane, nb);    // in flight while the accumulator chunk is read and staged
                     uint32_t v[32];
                     tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
                     tc_wait_ld();
@@ -536,7 +568,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             make_float4(__uint_as_float(v[4 * g4]), __uint_as_float(v[4 * g4 + 1]),
                                         __uint_as_float(v[4 * g4 + 2]), __uint_as_float(v[4 * g4 + 3]));
                     __syncwarp();
-                    epilogue_store_chunk(sE, lane, mrow0, nb, ee);
+                    epilogue_store_chunk(sE, lane, mrow0, nb, ee, rows_in, rows_keep, bias_c);
                     __syncwarp();
                 }
             }
@@ -631,7 +663,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" :: "l"(&tmB) : "memory");
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 2); mbar_init(empty0 + 8 * i, 1); }   // full: A and B producer of the leader
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 2 * NUM_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -655,38 +687,36 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
     if (warp < NUM_PROD_WARPS) {
         // =================================== TMA producers (both CTAs) ===================================
-        // producer warp w: operand (w & 1: 0 = this CTA's 128 rows of A, 1 = its half of B) of every second k-block (parity
-        // w >> 1); the bytes of both CTAs complete on the LEADER's full barrier, armed by the leader's two producers of the stage
-        const int which = warp & 1, par = warp >> 1;
-        const int mn = which ? p.b_mn : p.a_mn;
-        const uint32_t tile_bytes = which ? (uint32_t)C_::BH_BYTES : (uint32_t)A_BYTES;
-        const int n_blk = mn ? (which ? BN / 128 : BM / 64) : 1;
-        const CUtensorMap* tm = which ? &tmB : &tmA;
-        const uint32_t s_base = which ? sB : sA;
+        // producer warp w fetches every NUM_PROD_WARPS-th k-block: this CTA's 128 rows of A and its half of B; the bytes of both
+        // CTAs complete on the LEADER's full barrier, armed by the leader's producer of that k-block
+        const int a_mn = p.a_mn, b_mn = p.b_mn;
         if (elect_one()) {
-        int stage = par; uint32_t phase = 0;
-        int it = 0;
-        for (int unit = unit0; unit < num_units; unit += unit_stride) {
-            const int tile = unit % num_tiles, slice = unit / num_tiles;
-            const int m0 = ((tile % tiles_mc) * 2 + (int)crank) * BM, n0 = (tile / tiles_mc) * BN + (int)crank * (BN / 2);
-            const int r0 = which ? n0 : m0;
-            const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
-            for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                if ((it & 1) != par) continue;
-                mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                {
+            int stage = warp; uint32_t phase = 0;
+            int it = 0;
+            for (int unit = unit0; unit < num_units; unit += unit_stride) {
+                const int tile = unit % num_tiles, slice = unit / num_tiles;
+                const int m0 = ((tile % tiles_mc) * 2 + (int)crank) * BM, n0 = (tile / tiles_mc) * BN + (int)crank * (BN / 2);
+                const int kb0 = slice * p.kb_per_split, kb1 = min(nkb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    if ((it % NUM_PROD_WARPS) != warp) continue;
+                    mbar_wait_backoff(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t fb_leader = mapa_u32(full0 + 8 * stage, 0);
-                    if (crank == 0) mbar_arrive_expect_tx(full0 + 8 * stage, 2 * tile_bytes);   // this operand's bytes of BOTH CTAs
-                    const uint32_t dst = s_base + stage * tile_bytes;
-                    if (!mn) tma_load_2d_2sm(dst, tm, kb * BK, r0, fb_leader);
+                    if (crank == 0) mbar_arrive_expect_tx(full0 + 8 * stage, 2 * C_::STAGE_BYTES);   // bytes of BOTH CTAs
+                    const uint32_t a_dst = sA + stage * A_BYTES, b_dst = sB + stage * C_::BH_BYTES;
+                    if (!a_mn) tma_load_2d_2sm(a_dst, &tmA, kb * BK, m0, fb_leader);
                     else {
-                        for (int j = 0; j < n_blk; ++j) tma_load_2d_2sm(dst + j * MN_BLOCK_BYTES, tm, r0 + 64 * j, kb * BK, fb_leader);
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(a_dst + j * MN_BLOCK_BYTES, &tmA, m0 + 64 * j, kb * BK, fb_leader);
                     }
+                    if (!b_mn) tma_load_2d_2sm(b_dst, &tmB, kb * BK, n0, fb_leader);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(b_dst + j * MN_BLOCK_BYTES, &tmB, n0 + 64 * j, kb * BK, fb_leader);
+                    }
+                    stage += NUM_PROD_WARPS;
+                    if (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
                 }
-                stage += 2;
-                if (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
             }
-        }
         }
         __syncwarp();
     } else if (warp == MMA_WARP) {
@@ -727,7 +757,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         __syncwarp();
     } else {
-        // =================================== epilogue warps 5..12 (both CTAs, own TMEM half) ===================================
+        // =================================== epilogue warps 4..11 (both CTAs, own TMEM half) ===================================
         const int q = warp & 3;
         const int cg = (warp - EPI_WARP0) >> 2;
         float* sE = sEpi + (warp - EPI_WARP0) * 32 * EPI_LD;
@@ -743,9 +773,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 ee.bias1 = ee.bias2 = ee.add1 = ee.add2 = nullptr; ee.row_mask = nullptr; ee.beta = 0.f; ee.C16 = nullptr;
                 ee.vec = (e.N % 4 == 0) ? 4 : ((e.N % 2 == 0) ? 2 : 1);
             }
+            const int mrow0 = m0 + q * 32;
+            unsigned rows_in, rows_keep;                                 // row mask fetched while the contraction runs
+            epi_row_bits(ee, lane, mrow0, rows_in, rows_keep);
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
-            const int mrow0 = m0 + q * 32;
             const uint32_t tempty_leader = mapa_u32(tempty0 + 8 * acc, 0);
             bool released = false;
 #pragma unroll 1
@@ -753,6 +785,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int nb = n0 + c * 32;
                 const bool last = (c + 2 >= NCHUNK);
                 if (nb < e.N && mrow0 < M_eff) {
+                    const Bias4 bias_c = epi_bias4(ee, lane, nb);
                     uint32_t v[32];
                     tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
                     tc_wait_ld();
@@ -767,7 +800,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             make_float4(__uint_as_float(v[4 * g4]), __uint_as_float(v[4 * g4 + 1]),
                                         __uint_as_float(v[4 * g4 + 2]), __uint_as_float(v[4 * g4 + 3]));
                     __syncwarp();
-                    epilogue_store_chunk(sE, lane, mrow0, nb, ee);
+                    epilogue_store_chunk(sE, lane, mrow0, nb, ee, rows_in, rows_keep, bias_c);
                     __syncwarp();
                 }
             }

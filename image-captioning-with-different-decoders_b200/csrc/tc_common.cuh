@@ -35,6 +35,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (++spins > (1ull << 24)) __trap();        // a protocol bug must fault, never hang the GPU
     }
 }
+// the same for a waiter that is not on the critical path (a TMA producer several ring slots ahead of the consumer): sleeps
+// between polls so that its spin does not take issue slots from the epilogue warps of the same scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    unsigned long long spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(64);
+        if (++spins > (1ull << 22)) __trap();
+    }
+}
 // non-blocking probe of a phase (used to start the barrier read of the NEXT ring slot before the MMAs of the current one
 // are issued: the ~150-clock latency of the probe then hides behind the issue of four UTCHMMAs)
 __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {

@@ -110,6 +110,10 @@ if "--kslope" in sys.argv:
         e1.record(); torch.cuda.synchronize()
         print("cuBLAS (calibration) K=%5d  %7.1f us" % (K, e0.elapsed_time(e1) * 1e3 / 500), flush=True)
     sys.exit(0)
+if "--fc" in sys.argv:             # the vocabulary layer's forward contraction only (for ncu)
+    PROFILE = "--profile" in sys.argv
+    run("K6 fc fwd (ldc=V, mask)", B * T, V, D, bias=True, mask=True)
+    sys.exit(0)
 if "--one" in sys.argv:            # one shape, for ncu: python tools/gemm_bench.py --one  (K4 gates, plan from the environment)
     PROFILE = True
     run("K4 gates (step)", B, 4 * D, C, add=True)
