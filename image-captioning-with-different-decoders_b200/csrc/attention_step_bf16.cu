@@ -415,13 +415,52 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
 //   partial[(b*gridDim.x + chunk)*(2A+4)] = { d_w_full[A], colsum_p d_att_enc[A] (-> d enc_att.bias), sum d_e, 0,0,0 }.
 // ------------------------------------------------------------------------------------------------
 constexpr int PROJ_PB = 28;
+constexpr float PROJ_W_MIN = 1e-18f;       // below this |w_full[a]| the split form of d_w_full is not used (see the kernel)
+
+// out[n] = sum_m X[m*ldx + n] * Y[m*ldy + n]   (deterministic; block (32,32) like colsum_kernel)
+__global__ void coldot_kernel(const float* __restrict__ X, long long ldx, const float* __restrict__ Y, long long ldy,
+                              long long M, int N, float* __restrict__ out) {
+    __shared__ float s[32][33];
+    const int n = blockIdx.x * 32 + threadIdx.x;
+    float acc = 0.f;
+    if (n < N) {
+        long long m = threadIdx.y;
+        for (; m + 96 < M; m += 128) {                       // four rows in flight per thread
+            const float x0 = X[m * ldx + n], x1 = X[(m + 32) * ldx + n], x2 = X[(m + 64) * ldx + n], x3 = X[(m + 96) * ldx + n];
+            const float y0 = Y[m * ldy + n], y1 = Y[(m + 32) * ldy + n], y2 = Y[(m + 64) * ldy + n], y3 = Y[(m + 96) * ldy + n];
+            acc = fmaf(x0, y0, acc); acc = fmaf(x1, y1, acc); acc = fmaf(x2, y2, acc); acc = fmaf(x3, y3, acc);
+        }
+        for (; m < M; m += 32) acc = fmaf(X[m * ldx + n], Y[m * ldy + n], acc);
+    }
+    s[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int y = 0; y < 32; ++y) t += s[y][threadIdx.x];
+        out[n] = t;
+    }
+}
+// d_w_full[a] += t2[a] / w_full[a], t2[a] = sum_{t,b} att_dec[t,b,a] * d_att_dec[t,b,a]: since d_att_dec = w_full * sum_p mask * d_e,
+// this is the part of  sum d_e * relu(att_enc + att_dec)  that multiplies att_dec.  Skipped when the projection kernel did not
+// split (same predicate).  One CTA.
+__global__ void proj_wfull_finish_kernel(int A, const float* __restrict__ w_full, const float* __restrict__ t2,
+                                         float* __restrict__ d_w_full) {
+    int bad = 0;
+    for (int a4 = threadIdx.x * 4; a4 < A; a4 += blockDim.x * 4) {
+        const float4 w = *reinterpret_cast<const float4*>(w_full + a4);
+        bad |= (fabsf(w.x) < PROJ_W_MIN) | (fabsf(w.y) < PROJ_W_MIN) | (fabsf(w.z) < PROJ_W_MIN) | (fabsf(w.w) < PROJ_W_MIN);
+    }
+    if (__syncthreads_or(bad)) return;
+    for (int a = threadIdx.x; a < A; a += blockDim.x) d_w_full[a] += t2[a] / w_full[a];
+}
 
 __global__ void att_proj_bwd_bf16_kernel(int B, int T, int P, int A, const int* __restrict__ row_len,
                                          const __nv_bfloat16* __restrict__ att_enc,
                                          const float* __restrict__ att_dec_all, long long ld_dec,
                                          const float* __restrict__ w_full, const float* __restrict__ d_e,
                                          float* __restrict__ d_att_enc, __nv_bfloat16* __restrict__ d_att_enc16,
-                                         float* __restrict__ partial) {
+                                         float* __restrict__ partial, int split_wfull) {
     extern __shared__ __align__(16) float sm[];
     const int b = blockIdx.y, p0 = blockIdx.x * PROJ_PB;
     const int np = min(PROJ_PB, P - p0);
@@ -429,10 +468,24 @@ __global__ void att_proj_bwd_bf16_kernel(int B, int T, int P, int A, const int* 
     float* s_dec = sm;
     float* s_de = sm + (size_t)T * A;
     float* s_red = s_de + (size_t)T * PROJ_PB;
+    // split_wfull (see proj_wfull_finish_kernel): the inner loop only forms the masked sums S = sum_t [att_enc + att_dec_t > 0] d_e_t
+    // — with the NEGATED att_dec staged in shared memory that is one compare and one predicated add per (pixel, channel, step)
+    // instead of add / compare / add / max / fma — and d_w_full = sum att_enc * S here + (sum_t att_dec_t * d_att_dec_t) / w
+    // later.  Needs every |w_full[a]| to be a sane divisor: the predicate is evaluated identically here and in the finish kernel.
+    bool fast = false;
+    if (split_wfull) {
+        int bad = 0;
+        for (int a4 = threadIdx.x * 4; a4 < A; a4 += blockDim.x * 4) {
+            const float4 w = *reinterpret_cast<const float4*>(w_full + a4);
+            bad |= (fabsf(w.x) < PROJ_W_MIN) | (fabsf(w.y) < PROJ_W_MIN) | (fabsf(w.z) < PROJ_W_MIN) | (fabsf(w.w) < PROJ_W_MIN);
+        }
+        fast = __syncthreads_or(bad) == 0;
+    }
+    const float sgn = fast ? -1.f : 1.f;
     for (int i = threadIdx.x; i < Tb * (A >> 2); i += blockDim.x) {
         const int t = i / (A >> 2), a4 = (i % (A >> 2)) * 4;
-        *reinterpret_cast<float4*>(s_dec + (size_t)t * A + a4) =
-            *reinterpret_cast<const float4*>(att_dec_all + ((long long)t * B + b) * ld_dec + a4);
+        const float4 v = *reinterpret_cast<const float4*>(att_dec_all + ((long long)t * B + b) * ld_dec + a4);
+        *reinterpret_cast<float4*>(s_dec + (size_t)t * A + a4) = make_float4(sgn * v.x, sgn * v.y, sgn * v.z, sgn * v.w);
     }
     float de_sum = 0.f;
     for (int i = threadIdx.x; i < Tb * PROJ_PB; i += blockDim.x) {
@@ -463,6 +516,25 @@ __global__ void att_proj_bwd_bf16_kernel(int B, int T, int P, int A, const int* 
             for (int u = 0; u < 4; ++u)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) acc[u][i] = 0.f;
+            if (fast) {
+                for (int t = 0; t < Tb; ++t) {
+                    const float4 de4 = *reinterpret_cast<const float4*>(s_de + t * PROJ_PB + pq);
+                    const float4 d = *reinterpret_cast<const float4*>(s_dec + (size_t)t * A + a);     // -att_dec[t]
+                    const float de[4] = {de4.x, de4.y, de4.z, de4.w};
+                    const float nd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            acc[u][i] += (x[u][i] > nd[i]) ? de[u] : 0.f;       // x + att_dec > 0  <=>  x > -att_dec (exactly, in fp32)
+                }
+                float wl[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) wl[i] = fmaf(x[u][i], acc[u][i], wl[i]);    // rows past np carry S = 0
+                wacc.x += wl[0]; wacc.y += wl[1]; wacc.z += wl[2]; wacc.w += wl[3];
+            } else
             for (int t = 0; t < Tb; ++t) {
                 const float4 de4 = *reinterpret_cast<const float4*>(s_de + t * PROJ_PB + pq);
                 const float4 d = *reinterpret_cast<const float4*>(s_dec + (size_t)t * A + a);
@@ -688,6 +760,18 @@ extern "C" int icd_attention_proj_bwd_bf16(int B, int T, int P, int A, const int
                                            const float* w_full, const float* d_e,
                                            float* d_att_enc, void* d_att_enc16, float* d_w_full, float* d_b_full,
                                            float* d_b_enc, float* partial, void* stream) {
+    return icd_attention_proj_bwd_bf16_ex(B, T, P, A, bt_host, att_enc16, att_dec_all, ld_dec, w_full, d_e, d_att_enc, d_att_enc16,
+                                          d_w_full, d_b_full, d_b_enc, partial, nullptr, 0, stream);
+}
+
+// d_att_dec_all != NULL: the (T*B, A) gradient w.r.t. att_dec that the per-step backward kernels wrote (rows of inactive
+// (t, b) zero, as att_dec_all's): enables the split form of d_w_full (see att_proj_bwd_bf16_kernel).
+extern "C" int icd_attention_proj_bwd_bf16_ex(int B, int T, int P, int A, const int32_t* bt_host,
+                                              const void* att_enc16, const float* att_dec_all, int64_t ld_dec,
+                                              const float* w_full, const float* d_e,
+                                              float* d_att_enc, void* d_att_enc16, float* d_w_full, float* d_b_full,
+                                              float* d_b_enc, float* partial, const float* d_att_dec_all, int64_t ld_ddec,
+                                              void* stream) {
     cudaStream_t s = icd_stream(stream);
     ICD_CHECK_ARG(T > 0 && T <= ICD_MAX_STEPS, "attention_proj_bwd_bf16: T=%d out of range", T);
     ICD_CHECK_ARG(A % 4 == 0 && A / 4 <= 512, "attention_proj_bwd_bf16: A=%d unsupported", A);
@@ -713,9 +797,18 @@ extern "C" int icd_attention_proj_bwd_bf16(int B, int T, int P, int A, const int
     att_proj_bwd_bf16_kernel<<<grid, threads, smem, s>>>(B, T, P, A, row_len,
                                                           reinterpret_cast<const __nv_bfloat16*>(att_enc16),
                                                           att_dec_all, ld_dec, w_full, d_e, d_att_enc,
-                                                          reinterpret_cast<__nv_bfloat16*>(d_att_enc16), partial);
+                                                          reinterpret_cast<__nv_bfloat16*>(d_att_enc16), partial,
+                                                          d_att_dec_all ? 1 : 0);
     ICD_LAUNCH_CHECK();
     ICD_TRY(icd_colsum(partial, W, (int64_t)B * chunks, A, nullptr, d_w_full, s));
+    if (d_att_dec_all) {
+        float* t2 = partial + (int64_t)B * chunks * W + B + 8;       // A floats behind the row lengths (ws_floats reserves them)
+        coldot_kernel<<<(A + 31) / 32, dim3(32, 32), 0, s>>>(att_dec_all, (long long)ld_dec, d_att_dec_all, (long long)ld_ddec,
+                                                             (long long)T * B, A, t2);
+        ICD_LAUNCH_CHECK();
+        proj_wfull_finish_kernel<<<1, 256, 0, s>>>(A, w_full, t2, d_w_full);
+        ICD_LAUNCH_CHECK();
+    }
     if (d_b_enc) ICD_TRY(icd_colsum(partial + A, W, (int64_t)B * chunks, A, nullptr, d_b_enc, s));
     ICD_TRY(icd_colsum(partial + 2 * A, W, (int64_t)B * chunks, 1, nullptr, d_b_full, s));
     return 0;

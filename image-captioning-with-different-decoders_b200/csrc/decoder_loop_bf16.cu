@@ -293,9 +293,9 @@ int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
     if (d->ev_rec_ready) ICD_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(d->ev_rec_ready), s)); // recurrent gradients final
     // attention projections: d_att_enc for all steps at once (bf16 only: it is just the A operand of the next
     // contraction), full_att grads and the enc_att bias grad from the same pass, then the enc_att weight grad (:54)
-    ICD_TRY(icd_attention_proj_bwd_bf16(B, T, P, A, d->bt_host, u.att_enc, d->z, NZ, d->full_att_w, d->d_e,
-                                        nullptr, u.dae, d->d_full_att_w, d->d_full_att_b, d->d_enc_att_b,
-                                        d->proj_partial, (void*)s));
+    ICD_TRY(icd_attention_proj_bwd_bf16_ex(B, T, P, A, d->bt_host, u.att_enc, d->z, NZ, d->full_att_w, d->d_e,
+                                           nullptr, u.dae, d->d_full_att_w, d->d_full_att_b, d->d_enc_att_b,
+                                           d->proj_partial, d->dz, NZ, (void*)s));
     MMX(u.dae, A, 1, u.enc, C, 1, d->d_enc_att_w, C, A, C, BP, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
     // ---- optional: gradient w.r.t. the encoder features (--fine_tune_encoder) ----
     if (d->d_enc) {

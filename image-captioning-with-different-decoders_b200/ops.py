@@ -330,8 +330,9 @@ def attention_step_bwd_bf16(enc16, att_enc16, att_dec, w_full, alpha, gate, awe_
     return d_att_dec, d_fb, d_e, dz16
 
 
-def attention_proj_bwd_bf16(att_enc16, att_dec_all, w_full, d_e, bt):
-    """-> (d_att_enc fp32, d_att_enc16 bf16, d_w_full, d_b_full, d_b_enc)"""
+def attention_proj_bwd_bf16(att_enc16, att_dec_all, w_full, d_e, bt, d_att_dec_all=None):
+    """-> (d_att_enc fp32, d_att_enc16 bf16, d_w_full, d_b_full, d_b_enc).  d_att_dec_all (T, B, A): the gradient w.r.t. att_dec from
+    the per-step backward kernels — switches d_w_full to its split form (icd_attention_proj_bwd_bf16_ex)."""
     B, P, A = att_enc16.shape
     T = len(bt)
     dev = att_enc16.device
@@ -342,11 +343,13 @@ def attention_proj_bwd_bf16(att_enc16, att_dec_all, w_full, d_e, bt):
     d_be = torch.empty(A, device=dev, dtype=torch.float32)
     ws = torch.empty(int(lib().icd_attention_proj_bwd_ws_floats(B, P, A)), device=dev, dtype=torch.float32)
     bt_arr = (ctypes.c_int32 * T)(*bt)
-    check(lib().icd_attention_proj_bwd_bf16(B, T, P, A, bt_arr, ptr(att_enc16), ptr(att_dec_all),
-                                            ctypes.c_int64(att_dec_all.stride(1)), ptr(w_full), ptr(d_e),
-                                            ptr(d_att_enc), ptr(d_att_enc16), ptr(d_wf), ptr(d_bf), ptr(d_be), ptr(ws),
-                                            stream_ptr()),
-          "icd_attention_proj_bwd_bf16")
+    check(lib().icd_attention_proj_bwd_bf16_ex(B, T, P, A, bt_arr, ptr(att_enc16), ptr(att_dec_all),
+                                               ctypes.c_int64(att_dec_all.stride(1)), ptr(w_full), ptr(d_e),
+                                               ptr(d_att_enc), ptr(d_att_enc16), ptr(d_wf), ptr(d_bf), ptr(d_be), ptr(ws),
+                                               ptr(d_att_dec_all) if d_att_dec_all is not None else None,
+                                               ctypes.c_int64(d_att_dec_all.stride(1) if d_att_dec_all is not None else 0),
+                                               stream_ptr()),
+          "icd_attention_proj_bwd_bf16_ex")
     return d_att_enc, d_att_enc16, d_wf, d_bf, d_be
 
 

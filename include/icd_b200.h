@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ICD_B200_ABI_VERSION 13
+#define ICD_B200_ABI_VERSION 14
 #define ICD_MAX_STEPS 256
 
 ICD_API int icd_version(void);                       /* ICD_B200_ABI_VERSION the library was built with */
@@ -211,6 +211,14 @@ ICD_API int icd_attention_proj_bwd_bf16(int B, int T, int P, int A, const int32_
                                 const float* w_full, const float* d_e,
                                 float* d_att_enc, void* d_att_enc16, float* d_w_full, float* d_b_full,
                                 float* d_b_enc, float* partial, void* stream);
+/* the same with d_att_dec_all (T*B, A; leading dimension ld_ddec; rows of inactive (t, b) zero) = the gradient w.r.t. att_dec
+ * written by icd_attention_step_bwd_bf16: d full_att.weight is then formed as  sum att_enc * S + (sum att_dec * d_att_dec) / w
+ * (S = the masked d_e sums the kernel needs anyway) — 2 instead of 5 instructions per (pixel, channel, step).  NULL: as above. */
+ICD_API int icd_attention_proj_bwd_bf16_ex(int B, int T, int P, int A, const int32_t* bt_host,
+                                const void* att_enc16, const float* att_dec_all, int64_t ld_dec,
+                                const float* w_full, const float* d_e,
+                                float* d_att_enc, void* d_att_enc16, float* d_w_full, float* d_b_full,
+                                float* d_b_enc, float* partial, const float* d_att_dec_all, int64_t ld_ddec, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * AttentionDecoder.forward / backward, teacher-forced (models/attention.py:218-284).

@@ -177,17 +177,18 @@ def test_constructor_accepts_a_foreign_vocabulary_class_with_the_reference_surfa
 
 def test_contraction_plan_host_logic():
     """Pure host logic of the tensor-core tier (no GPU needed): the split-K workspace the plan asks for.
-    * the per-step dh contraction (512 x 512 x 4608) runs as 8 K-slices (cost model fitted on graph replays, DESIGN.md 5.2);
+    * the per-step dh contraction (512 x 512 x 4608) runs as 4 K-slices of 64-wide tiles (cost model refitted in round 2 to the
+      fixed issue path, DESIGN.md 5.2);
     * shapes that fill the GPU do not split;
-    * d fc.weight (9490 x 512 x 12288): the 18-row last m-tile is split off into a 32-slice contraction, the 74 full
+    * d fc.weight (9490 x 512 x 12288): the 18-row last m-tile is split off into an 18-slice contraction, the 74 full
       m-tiles x 2 n-tiles = 148 tiles (one wave) need no workspace."""
     from icd_b200._lib import lib
     L = lib()
     L.icd_gemm_bf16_splitk_ws_floats.restype = ctypes.c_int64
     f = lambda M, N, K: int(L.icd_gemm_bf16_splitk_ws_floats(M, N, K))
-    assert f(512, 512, 4608) == 8 * 512 * 512
+    assert f(512, 512, 4608) == 4 * 512 * 512
     assert f(100352, 512, 2048) == 0 and f(12288, 9490, 512) == 0 and f(512, 4608, 512) == 0
-    assert f(9490, 512, 12288) == 32 * 18 * 512
+    assert f(9490, 512, 12288) == 18 * 18 * 512
     assert f(9472, 512, 12288) == 0
 
 

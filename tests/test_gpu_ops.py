@@ -278,6 +278,17 @@ def test_attention_step_bf16_features_matches_oracle_on_rounded_features(cuda, R
     H.assert_close_norm(d_att_enc16.float(), ae64.grad, 4e-3, "d_att_enc16")
     H.assert_close_norm(d_be, ae64.grad.sum(dim=(0, 1)), 2e-5, "d_b_enc")
     H.assert_close_norm(d_wf, wf64.grad, 2e-5, "d_w_full")
+    # split form of d_w_full (masked sums in the kernel + (sum att_dec * d_att_dec) / w afterwards): same results
+    s_att_enc, s_att_enc16, s_wf, s_bf, s_be = ops.attention_proj_bwd_bf16(att_enc16.to(cuda), att_dec.to(cuda).view(1, R, A),
+                                                        wf.to(cuda), d_e.view(R, 1, P), [R], d_att_dec_all=d_att_dec.view(1, R, A))
+    assert torch.equal(s_att_enc, d_att_enc) and torch.equal(s_att_enc16, d_att_enc16) and torch.equal(s_be, d_be)
+    H.assert_close_norm(s_wf, wf64.grad, 2e-5, "d_w_full (split form)")
+    # ... and a w_full with a zero entry falls back to the direct form inside the kernel
+    wf0 = wf.clone(); wf0[3] = 0.0
+    z_ref = ops.attention_proj_bwd_bf16(att_enc16.to(cuda), att_dec.to(cuda).view(1, R, A), wf0.to(cuda), d_e.view(R, 1, P), [R])
+    z_spl = ops.attention_proj_bwd_bf16(att_enc16.to(cuda), att_dec.to(cuda).view(1, R, A), wf0.to(cuda), d_e.view(R, 1, P), [R],
+                                        d_att_dec_all=d_att_dec.view(1, R, A))
+    assert torch.equal(z_ref[2], z_spl[2]) and torch.isfinite(z_spl[2]).all()
 
 
 @pytest.fixture(params=[2, 1, 0], ids=["cta_group2_pairs", "multicast_pairs", "single_cta"])
