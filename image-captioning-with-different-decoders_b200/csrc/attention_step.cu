@@ -702,7 +702,7 @@ extern "C" int64_t icd_attention_proj_bwd_ws_floats(int B, int P, int A) {
     const int64_t chunks = (P + PROJ_PB - 1) / PROJ_PB;
     // per-CTA partials (d_w_full[A] | d_b_enc[A] | sum d_e + pad) + [B] int row lengths (4-byte words at the end)
     // + A floats for the att_dec part of d_w_full (bf16 tier, icd_attention_proj_bwd_bf16_ex)
-    return (int64_t)B * chunks * (2 * A + 4) + B + 8 + A;
+    return (int64_t)B * chunks * (2 * A + 4) + B + 8 + 49 * (int64_t)A;      // 49 = 1 + COLDOT_CHUNKS (attention_step_bf16.cu)
 }
 
 extern "C" int icd_attention_proj_bwd(int B, int T, int P, int A, const int32_t* bt_host,

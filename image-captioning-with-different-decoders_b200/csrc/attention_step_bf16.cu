@@ -417,14 +417,19 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
 constexpr int PROJ_PB = 28;
 constexpr float PROJ_W_MIN = 1e-18f;       // below this |w_full[a]| the split form of d_w_full is not used (see the kernel)
 
-// out[n] = sum_m X[m*ldx + n] * Y[m*ldy + n]   (deterministic; block (32,32) like colsum_kernel)
+// out[blockIdx.y][n] = sum over the rows of chunk blockIdx.y of X[m*ldx + n] * Y[m*ldy + n]   (deterministic; block (32,32) like
+// colsum_kernel; the chunks are added by a colsum pass afterwards)
+constexpr int COLDOT_CHUNKS = 48;
 __global__ void coldot_kernel(const float* __restrict__ X, long long ldx, const float* __restrict__ Y, long long ldy,
-                              long long M, int N, float* __restrict__ out) {
+                              long long M_all, int N, float* __restrict__ out_all) {
     __shared__ float s[32][33];
     const int n = blockIdx.x * 32 + threadIdx.x;
+    const long long per = (M_all + gridDim.y - 1) / gridDim.y, m_lo = per * blockIdx.y;
+    const long long M = min(M_all, m_lo + per);
+    float* out = out_all + (long long)blockIdx.y * N;
     float acc = 0.f;
     if (n < N) {
-        long long m = threadIdx.y;
+        long long m = m_lo + threadIdx.y;
         for (; m + 96 < M; m += 128) {                       // four rows in flight per thread
             const float x0 = X[m * ldx + n], x1 = X[(m + 32) * ldx + n], x2 = X[(m + 64) * ldx + n], x3 = X[(m + 96) * ldx + n];
             const float y0 = Y[m * ldy + n], y1 = Y[(m + 32) * ldy + n], y2 = Y[(m + 64) * ldy + n], y3 = Y[(m + 96) * ldy + n];
@@ -802,10 +807,12 @@ extern "C" int icd_attention_proj_bwd_bf16_ex(int B, int T, int P, int A, const 
     ICD_LAUNCH_CHECK();
     ICD_TRY(icd_colsum(partial, W, (int64_t)B * chunks, A, nullptr, d_w_full, s));
     if (d_att_dec_all) {
-        float* t2 = partial + (int64_t)B * chunks * W + B + 8;       // A floats behind the row lengths (ws_floats reserves them)
-        coldot_kernel<<<(A + 31) / 32, dim3(32, 32), 0, s>>>(att_dec_all, (long long)ld_dec, d_att_dec_all, (long long)ld_ddec,
-                                                             (long long)T * B, A, t2);
+        float* t2 = partial + (int64_t)B * chunks * W + B + 8;       // (1 + COLDOT_CHUNKS) * A floats behind the row lengths
+        float* t2_parts = t2 + A;
+        coldot_kernel<<<dim3((A + 31) / 32, COLDOT_CHUNKS), dim3(32, 32), 0, s>>>(att_dec_all, (long long)ld_dec, d_att_dec_all,
+                                                                                (long long)ld_ddec, (long long)T * B, A, t2_parts);
         ICD_LAUNCH_CHECK();
+        ICD_TRY(icd_colsum(t2_parts, A, COLDOT_CHUNKS, A, nullptr, t2, s));
         proj_wfull_finish_kernel<<<1, 256, 0, s>>>(A, w_full, t2, d_w_full);
         ICD_LAUNCH_CHECK();
     }

@@ -374,6 +374,104 @@ __global__ void __launch_bounds__(256) cross_entropy_fwd_kernel(int V, const flo
     }
 }
 
+// Forward AND gradient in one pass over the logits (training fast path of the bf16 tier): the row is parked in shared memory
+// while its log-sum-exp is formed (exactly as cross_entropy_fwd_kernel does), then the bf16 gradient
+// (exp(x - lse) - onehot) * inv_count is written from the parked copy — every logit is read from HBM once instead of twice.
+// The upstream gradient of the loss is applied afterwards (scale_bf16_by_device_scalar_kernel: a no-op when it is 1).
+__global__ void __launch_bounds__(256) cross_entropy_fwd_grad16_kernel(int V, const float* __restrict__ logits,
+                                                                       const long long* __restrict__ targets, float inv_count,
+                                                                       float* __restrict__ row_loss, float* __restrict__ lse_out,
+                                                                       __nv_bfloat16* __restrict__ d16, long long ld16) {
+    extern __shared__ __align__(16) float s_x[];     // V floats (+ reduction scratch behind them)
+    float* s_m = s_x + ((V + 3) & ~3) + 4;           // behind the row and its alignment pad (see sx below)
+    float* s_s = s_m + 8;
+    const long long r = blockIdx.x;
+    const float* x = logits + r * V;
+    const long long tgt = targets[r];
+    __nv_bfloat16* d16r = d16 + r * ld16;
+    if (tgt >= V) __trap();
+    if (tgt < 0) {                                   // ignored row: loss 0, zero gradient row (16-byte aligned, ld16 % 8 == 0)
+        if (threadIdx.x == 0) { row_loss[r] = 0.f; lse_out[r] = 0.f; }
+        uint4* z = reinterpret_cast<uint4*>(d16r);
+        for (int v = threadIdx.x; v < (int)(ld16 >> 3); v += blockDim.x) z[v] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    float m = -INFINITY, s = 0.f;
+    const int head = min(V, (int)((4 - ((reinterpret_cast<uintptr_t>(x) >> 2) & 3)) & 3));
+    const int V4 = (V - head) >> 2;
+    // the shared copy keeps the row's own alignment phase: element v lives at s_x[v + pad], pad = (4 - head) & 3, so that the
+    // 128-bit body is 16-byte aligned on both sides
+    const int pad = (4 - head) & 3;
+    float* sx = s_x + pad;
+    if ((int)threadIdx.x < head) { const float v = x[threadIdx.x]; sx[threadIdx.x] = v; online_add(m, s, v); }
+    for (int v = head + 4 * V4 + threadIdx.x; v < V; v += 256) { const float t = x[v]; sx[v] = t; online_add(m, s, t); }
+    const float* xb = x + head;
+    float* sb = sx + head;
+    int j = threadIdx.x;
+    for (; j + 3 * 256 < V4; j += 4 * 256) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld_stream_f4(xb + 4 * (j + u * 256));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            *reinterpret_cast<float4*>(sb + 4 * (j + u * 256)) = v[u];
+            const float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)), mn = fmaxf(m, mx);
+            s = s * __expf(m - mn) + __expf(v[u].x - mn) + __expf(v[u].y - mn) + __expf(v[u].z - mn) + __expf(v[u].w - mn);
+            m = mn;
+        }
+    }
+    for (; j < V4; j += 256) {
+        const float4 v = ld_stream_f4(xb + 4 * j);
+        *reinterpret_cast<float4*>(sb + 4 * j) = v;
+        online_add(m, s, v.x); online_add(m, s, v.y); online_add(m, s, v.z); online_add(m, s, v.w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        online_merge(m, s, m2, s2);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { s_m[w] = m; s_s[w] = s; }
+    __syncthreads();                                  // also: the parked row is complete
+    float M = s_m[0], S = s_s[0];
+    for (int i = 1; i < 8; ++i) online_merge(M, S, s_m[i], s_s[i]);      // every thread, same order as cross_entropy_fwd_kernel
+    const float lse = M + logf(S);
+    if (threadIdx.x == 0) { row_loss[r] = lse - sx[tgt]; lse_out[r] = lse; }
+    // gradient, 8 columns (16 bytes of bf16) per thread and pass
+    const int V8 = V >> 3;
+    for (int q = threadIdx.x; q < (int)(ld16 >> 3); q += 256) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const int v = 8 * q + 2 * h;
+            float g0 = 0.f, g1 = 0.f;
+            if (q < V8 || v < V) g0 = (expf(sx[v] - lse) - (v == tgt ? 1.f : 0.f)) * inv_count;
+            if (q < V8 || v + 1 < V) g1 = (expf(sx[v + 1] - lse) - (v + 1 == tgt ? 1.f : 0.f)) * inv_count;
+            const __nv_bfloat162 t = __floats2bfloat162_rn(g0, g1);
+            pk[h] = *reinterpret_cast<const uint32_t*>(&t);
+        }
+        *reinterpret_cast<uint4*>(d16r + 8 * q) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+}
+
+// x[i] *= *scale for a bf16 buffer — unless *scale == 1 (the usual upstream gradient of a loss): then nothing is touched
+__global__ void __launch_bounds__(256) scale_bf16_by_device_scalar_kernel(__nv_bfloat16* __restrict__ x, long long n8,
+                                                                          const float* __restrict__ scale) {
+    const float g = scale[0];
+    if (g == 1.f) return;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
+        uint4 v = reinterpret_cast<uint4*>(x)[i];
+        uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const float lo = __uint_as_float(w[h] << 16) * g, hi = __uint_as_float(w[h] & 0xffff0000u) * g;
+            const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+            w[h] = *reinterpret_cast<const uint32_t*>(&t);
+        }
+        reinterpret_cast<uint4*>(x)[i] = v;
+    }
+}
+
 __global__ void __launch_bounds__(256) cross_entropy_bwd_kernel(int V, const float* __restrict__ logits,
                                                                 const long long* __restrict__ targets,
                                                                 const float* __restrict__ lse_in,
@@ -588,6 +686,35 @@ extern "C" int icd_cross_entropy_fwd(int64_t R, int V, const float* logits, cons
     if (R <= 0) return 0;
     ICD_CHECK_ARG(row_loss && lse, "cross_entropy_fwd: row_loss and lse are required");
     cross_entropy_fwd_kernel<<<(unsigned)R, 256, 0, icd_stream(stream)>>>(V, logits, (const long long*)targets, row_loss, lse);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int icd_cross_entropy_fwd_grad16(int64_t R, int V, const float* logits, const int64_t* targets, float inv_count,
+                                            float* row_loss, float* lse, void* d_logits16, int64_t ld16, void* stream) {
+    if (R <= 0) return 0;
+    ICD_CHECK_ARG(row_loss && lse && d_logits16, "cross_entropy_fwd_grad16: null output");
+    ICD_CHECK_ARG(ld16 % 8 == 0 && ld16 >= V && (reinterpret_cast<uintptr_t>(d_logits16) & 15) == 0,
+                  "cross_entropy_fwd_grad16: ld16=%lld must be a multiple of 8 and >= V, the gradient 16-byte aligned", (long long)ld16);
+    const size_t smem = ((size_t)((V + 3) & ~3) + 4 + 16) * sizeof(float);
+    ICD_CHECK_ARG(smem <= 200 * 1024, "cross_entropy_fwd_grad16: V=%d does not fit in shared memory (use the two-kernel path)", V);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        ICD_CUDA(cudaFuncSetAttribute(cross_entropy_fwd_grad16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    cross_entropy_fwd_grad16_kernel<<<(unsigned)R, 256, smem, icd_stream(stream)>>>(V, logits, (const long long*)targets, inv_count,
+                                                                                    row_loss, lse, (__nv_bfloat16*)d_logits16, ld16);
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int icd_scale_bf16_by_device_scalar(void* x16, int64_t n, const float* scale, void* stream) {
+    if (n <= 0) return 0;
+    ICD_CHECK_ARG(n % 8 == 0 && (reinterpret_cast<uintptr_t>(x16) & 15) == 0 && scale, "scale_bf16: n %% 8 and 16-byte alignment required");
+    long long blocks = (n / 8 + 255) / 256;
+    if (blocks > ICD_NUM_SMS * 16) blocks = ICD_NUM_SMS * 16;
+    scale_bf16_by_device_scalar_kernel<<<(unsigned)blocks, 256, 0, icd_stream(stream)>>>((__nv_bfloat16*)x16, (long long)(n / 8), scale);
     ICD_LAUNCH_CHECK();
     return 0;
 }

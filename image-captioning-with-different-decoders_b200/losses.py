@@ -57,14 +57,23 @@ class GradBox:
         return None
 
 
+_FUSED_CE_MAX_V = 49000          # rows up to this many classes fit the one-pass kernel's shared memory (icd_cross_entropy_fwd_grad16)
+
+
 class _FusedCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits2d, targets, n_valid, want_bf16, bf16_only=False, box=None):
-        row_loss, lse = ops.cross_entropy_fwd(logits2d, targets)
-        ctx.save_for_backward(logits2d, targets, lse)
         ctx.n_valid, ctx.want_bf16 = n_valid, bool(want_bf16 and box is not None)
         ctx.bf16_only = bool(bf16_only and ctx.want_bf16)
         ctx.box = box
+        ctx.d16 = None
+        if ctx.bf16_only and ctx.needs_input_grad[0] and logits2d.shape[1] <= _FUSED_CE_MAX_V:
+            # training fast path: the only gradient anyone will ask for is the bf16 one, so it is formed in the SAME pass over
+            # the logits as the loss (each row parked in shared memory); the backward only applies the upstream scalar
+            row_loss, lse, ctx.d16 = ops.cross_entropy_fwd_grad16(logits2d, targets, 1.0 / n_valid)
+        else:
+            row_loss, lse = ops.cross_entropy_fwd(logits2d, targets)
+        ctx.save_for_backward(logits2d, targets, lse)
         if ctx.bf16_only:
             box.hollow_expected = True
         return row_loss.sum() / n_valid
@@ -73,6 +82,11 @@ class _FusedCE(torch.autograd.Function):
     def backward(ctx, g):
         logits2d, targets, lse = ctx.saved_tensors
         g = g.reshape(1).float().contiguous()
+        if ctx.d16 is not None:
+            d16, ctx.d16 = ops.scale_bf16_by_device_scalar(ctx.d16, g), None
+            d_logits = torch.empty_like(logits2d)            # hollow: never written, never read (GradBox refuses anything else)
+            ctx.box.put(d16, d_logits, True)
+            return d_logits, None, None, None, None, None
         d_logits, d16 = ops.cross_entropy_bwd(logits2d, targets, lse, 1.0 / ctx.n_valid, upstream=g,
                                               want_bf16=ctx.want_bf16, want_fp32=not ctx.bf16_only)
         if d16 is not None:

@@ -232,6 +232,29 @@ def cross_entropy_bwd(logits, targets, lse, inv_count, upstream=None, want_bf16=
     return d_logits, d16
 
 
+def cross_entropy_fwd_grad16(logits, targets, inv_count):
+    """Forward and bf16 gradient in one pass over the logits (icd_cross_entropy_fwd_grad16)
+    -> (row_loss (R,), lse (R,), d_logits16 (R, up8(V)) bf16 = (softmax - onehot) * inv_count, NOT yet times the upstream gradient)"""
+    _need_cuda(logits, targets)
+    R, V = logits.shape
+    ld16 = (V + 7) // 8 * 8
+    row_loss = torch.empty(R, device=logits.device, dtype=torch.float32)
+    lse = torch.empty(R, device=logits.device, dtype=torch.float32)
+    d16 = torch.empty(R, ld16, device=logits.device, dtype=torch.bfloat16)
+    check(lib().icd_cross_entropy_fwd_grad16(ctypes.c_int64(R), V, ptr(logits), ptr(targets), ctypes.c_float(inv_count),
+                                             ptr(row_loss), ptr(lse), ptr(d16), ctypes.c_int64(ld16), stream_ptr()),
+          "icd_cross_entropy_fwd_grad16")
+    return row_loss, lse, d16
+
+
+def scale_bf16_by_device_scalar(x16, scale):
+    """x16 *= scale (1-element CUDA fp32 tensor read on the device); nothing is touched when it is exactly 1."""
+    _need_cuda(x16, scale)
+    check(lib().icd_scale_bf16_by_device_scalar(ptr(x16), ctypes.c_int64(x16.numel()), ptr(scale), stream_ptr()),
+          "icd_scale_bf16_by_device_scalar")
+    return x16
+
+
 def alpha_regulariser_fwd(alphas, alpha_c):
     """models/attention.py:413-414 -> (reg 0-dim = mean_{b,p} (alpha_c - sum_t alphas)^2, resid (B,P) saved for the backward)"""
     _need_cuda(alphas)

@@ -430,6 +430,12 @@ ICD_API int icd_cross_entropy_fwd(int64_t R, int V, const float* logits, const i
 ICD_API int icd_cross_entropy_bwd(int64_t R, int V, const float* logits, const int64_t* targets, const float* lse,
                           const float* upstream, float inv_count, float* d_logits, void* d_logits16, int64_t ld16,
                           void* stream);
+/* training fast path of the bf16 tier: forward AND the bf16 gradient (exp(x - lse) - onehot) * inv_count in ONE pass over the
+ * logits (each row is parked in shared memory between the two; V <= ~50 000) — the upstream gradient of the loss is applied
+ * afterwards with icd_scale_bf16_by_device_scalar (x16[i] *= *scale; returns at once when *scale == 1). */
+ICD_API int icd_cross_entropy_fwd_grad16(int64_t R, int V, const float* logits, const int64_t* targets, float inv_count,
+                          float* row_loss, float* lse, void* d_logits16, int64_t ld16, void* stream);
+ICD_API int icd_scale_bf16_by_device_scalar(void* x16, int64_t n, const float* scale, void* stream);
 
 /* Doubly stochastic attention regulariser (models/attention.py:413-414): reg = mean_{b,p} (alpha_c - sum_t alphas[b,t,p])^2.
  * forward : resid[b,p] = alpha_c - sum_t alphas[b,t,p] (saved for the backward); reg[0] = the mean (summed in a fixed order:

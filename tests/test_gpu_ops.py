@@ -194,6 +194,17 @@ def test_cross_entropy_matches_torch(cuda, V):
     assert d16.shape[1] % 8 == 0 and d16.shape[1] >= x.shape[1]
     H.assert_close_norm(d16[:, :x.shape[1]].float(), x64.grad * 0.37, 4e-3, "d_logits16")
     assert torch.all(d16[:, x.shape[1]:] == 0)
+    # one-pass kernel (forward + bf16 gradient, each row parked in shared memory): same loss and log-sum-exp bit for bit, the same
+    # bf16 gradient as the two-kernel path with upstream 1; the upstream scalar is applied afterwards (untouched when it is 1)
+    rl1, lse1, g16 = ops.cross_entropy_fwd_grad16(x.to(cuda), t.to(cuda), 1.0 / n)
+    assert torch.equal(rl1, rl) and torch.equal(lse1, lse)
+    _, ref16 = ops.cross_entropy_bwd(x.to(cuda), t.to(cuda), lse, 1.0 / n, upstream=torch.ones(1, device=cuda), want_bf16=True)
+    assert torch.equal(g16, ref16)
+    keep = g16.clone()
+    ops.scale_bf16_by_device_scalar(g16, torch.ones(1, device=cuda))
+    assert torch.equal(g16, keep)
+    ops.scale_bf16_by_device_scalar(g16, up)
+    H.assert_close_norm(g16[:, :x.shape[1]].float(), x64.grad * 0.37, 8e-3, "one-pass d_logits16 * upstream")
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 128), (512, 4608, 512), (300, 9490, 512),
