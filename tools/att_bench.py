@@ -20,7 +20,7 @@ att_dec = torch.randn(B, A, device=dev) * 0.5
 wf = torch.randn(A, device=dev) * 0.2
 bf = torch.zeros(1, device=dev)
 fb = torch.randn(B, C, device=dev)
-for rows in (592, 512, 444, 296, 256, 148):
+for rows in (592, 574, 512, 444, 296, 256, 148):
     def run(lo):
         return ops.attention_step_fwd_bf16(enc16[lo:lo + rows], att16[lo:lo + rows], att_dec[lo:lo + rows], wf, bf, fb[lo:lo + rows])
     los = [lo for lo in range(0, B, rows) if lo + rows <= B]
@@ -38,3 +38,26 @@ for rows in (592, 512, 444, 296, 256, 148):
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / n
     print("fwd rows=%3d  %.1f us per launch  %.0f GB/s" % (rows, us, rows * 1022736 / us / 1e3))
+
+# backward kernel at the same row counts
+alpha, awe, gate, gated, gated16 = ops.attention_step_fwd_bf16(enc16, att16, att_dec, wf, bf, fb)
+d_gated = torch.randn(B, C, device=dev)
+for rows in (592, 574, 512, 444, 296, 256, 148):
+    def runb(lo):
+        sl = slice(lo, lo + rows)
+        return ops.attention_step_bwd_bf16(enc16[sl], att16[sl], att_dec[sl], wf, alpha[sl], gate[sl], awe[sl], d_gated[sl], None)
+    los = [lo for lo in range(0, B, rows) if lo + rows <= B]
+    for _ in range(2):
+        for lo in los:
+            runb(lo)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 0
+    e0.record()
+    for _ in range(10):
+        for lo in los:
+            runb(lo); n += 1
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / n
+    print("bwd rows=%3d  %.1f us per launch  %.0f GB/s (incl. the wrapper's output allocations)" % (rows, us, rows * 1042736 / us / 1e3))
