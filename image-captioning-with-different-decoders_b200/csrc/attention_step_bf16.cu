@@ -4,6 +4,7 @@
 // HBM-bound step: 196*2048*2 + 196*512*2 + small = 1 022 736 B per (image, step) forward.
 // Same math and same reference lines as attention_step.cu (models/attention.py:55-60, 270-271).
 #include "common.cuh"
+#include <stdlib.h>
 #include <cuda_bf16.h>
 
 namespace {
@@ -177,6 +178,20 @@ __global__ void __launch_bounds__(256, 4) att_step_fwd_bf16_kernel(
 // ------------------------------------------------------------------------------------------------
 // backward: grid = rows, block = 256.  smem: C + 2*A + 2*Ppad + 40 + 3*8*(A/8) floats
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned mapa_shared(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_shared_cluster_f32(unsigned addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
         int P, int C, int A,
         const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* __restrict__ att_enc,
@@ -187,7 +202,8 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
         float* __restrict__ d_att_dec, long long ld_ddec,
         float* __restrict__ d_fbeta_pre, long long ld_dfb,
         float* __restrict__ d_e, long long ld_de,
-        __nv_bfloat16* __restrict__ dz16, long long ld_dz16, float* __restrict__ d_awe_out, int use_mma) {
+        __nv_bfloat16* __restrict__ dz16, long long ld_dz16, float* __restrict__ d_awe_out, int use_mma,
+        int n_whole /* < 0: plain launch, one CTA per row; >= 0: launched as 2-CTA clusters, the first n_whole CTAs take whole rows */) {
     extern __shared__ __align__(16) float sm[];
     float* s_dawe = sm;                       // C
     float* s_dec = s_dawe + C;                // A
@@ -197,7 +213,23 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
     float* s_part = s_red + 40;               // 3 * A
     float* s_pb = s_part + 3 * A;             // nwarp * Pp16   (tensor-core path: per-warp partial d_alpha)
     __nv_bfloat16* s_hl = reinterpret_cast<__nv_bfloat16*>(s_pb + (blockDim.x >> 5) * (((P + 15) >> 4) << 4));   // 3 * C bf16
-    const int r = blockIdx.x;
+    float* s_xch = reinterpret_cast<float*>(s_hl + 3 * C);      // A floats (split rows: rank 1's d_att_dec partial lands here on rank 0)
+    // Row balance.  This kernel's throughput per SM saturates at ~43 GB/s, its fair share of HBM, so a launch is as slow as its
+    // busiest SM: 512 rows put 4 CTAs on 68 SMs and 3 on the other 80 and take 93.9 us where 592 rows take 98.2
+    // (profiles/r02_att_rows_per_launch.txt).  When the row count is not a multiple of the SM count, the launcher therefore runs
+    // the LAST few rows as TWO half-row CTAs each (a 2-CTA cluster: pixels [0, p_split) / [p_split, P) in the two streaming
+    // phases; the softmax-backward dot product and the d_att_dec partial sums meet through distributed shared memory) so that
+    // whole rows + half rows fill every SM's four CTA slots evenly in ONE wave.  (Splitting every row is slower: cluster barriers
+    // and a second wave cost more than the balance gains — profiles/r02_experiments.md.)
+    int r = blockIdx.x, hrank = 0;
+    bool split = false;
+    if (n_whole >= 0 && (int)blockIdx.x >= n_whole) {
+        split = true;
+        r = n_whole + (((int)blockIdx.x - n_whole) >> 1);
+        hrank = ((int)blockIdx.x - n_whole) & 1;
+    }
+    const int p_split = min(P, (((P >> 1) + 8) >> 4) << 4);
+    const int p_lo = (split && hrank) ? p_split : 0, p_hi = (split && !hrank) ? p_split : P;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     pdl_trigger();
     pdl_wait();
@@ -210,7 +242,8 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
             const float4 g = *reinterpret_cast<const float4*>(gate + o + c);
             const float4 aw = *reinterpret_cast<const float4*>(awe_raw + o + c);
             const float4 da = make_float4(dg.x * g.x, dg.y * g.y, dg.z * g.z, dg.w * g.w);
-            *reinterpret_cast<float4*>(s_dawe + c) = da;
+            *reinterpret_cast<float4*>(s_dawe + c) = da;                           // both CTAs of a split row need all of d_awe
+            if (split && ((c * 2 >= C) ? 1 : 0) != hrank) continue;                // ... but each output element has one owner
             if (d_awe_out) *reinterpret_cast<float4*>(d_awe_out + o + c) = da;     // kept for the encoder gradient
             const float4 df = make_float4(dg.x * aw.x * g.x * (1.f - g.x), dg.y * aw.y * g.y * (1.f - g.y),
                                           dg.z * aw.z * g.z * (1.f - g.z), dg.w * aw.w * g.w * (1.f - g.w));
@@ -250,7 +283,7 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
         const int Pp16 = ((P + 15) >> 4) << 4;
         const __nv_bfloat16* eb = enc + (long long)r * P * C + cb0 + 8 * t;
         const __nv_bfloat16* bsrc = (g < 3) ? (s_hl + g * C + cb0 + 8 * t) : s_hl;
-        for (int pb = 0; pb < (Pp16 >> 4); ++pb) {
+        for (int pb = p_lo >> 4; pb < ((p_hi + 15) >> 4); ++pb) {
             const int p0 = pb * 16 + g, p1 = p0 + 8;
             const __nv_bfloat16* rowA = eb + (long long)min(p0, P - 1) * C;
             const __nv_bfloat16* rowB = eb + (long long)min(p1, P - 1) * C;
@@ -284,7 +317,7 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
             }
         }
         __syncthreads();
-        for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        for (int p = p_lo + threadIdx.x; p < p_hi; p += blockDim.x) {
             float acc = 0.f;
             for (int w = 0; w < nwarp; ++w) acc += s_pb[w * Pp16 + p];
             if (d_alpha_ext) acc += d_alpha_ext[(long long)r * ld_dalpha + p];
@@ -293,7 +326,7 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
     } else {
         const __nv_bfloat16* eb = enc + (long long)r * P * C;
         const int C8 = C >> 3;
-        for (int p = warp; p < P; p += nwarp) {
+        for (int p = p_lo + warp; p < p_hi; p += nwarp) {
             const __nv_bfloat16* row = eb + (long long)p * C;
             float acc = 0.f;
             int j = lane;
@@ -332,10 +365,18 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
     // (C) softmax backward, centred
     {
         float part = 0.f;
-        for (int p = threadIdx.x; p < P; p += blockDim.x) part = fmaf(s_alpha[p], s_de[p], part);
-        const float dot = block_sum(part, s_red);
+        for (int p = p_lo + threadIdx.x; p < p_hi; p += blockDim.x) part = fmaf(s_alpha[p], s_de[p], part);
+        float dot = block_sum(part, s_red);
+        if (split) {                                  // the other half's share of sum_p alpha_p d_alpha_p, through its shared memory
+            if (threadIdx.x == 0) {
+                s_red[34 + hrank] = dot;
+                st_shared_cluster_f32(mapa_shared(smem_addr(s_red + 34 + hrank), (unsigned)(hrank ^ 1)), dot);
+            }
+            cluster_barrier();
+            dot = s_red[34] + s_red[35];              // rank 0's share first on both sides: identical, deterministic
+        }
         float* out = d_e + (long long)r * ld_de;
-        for (int p = threadIdx.x; p < P; p += blockDim.x) {
+        for (int p = p_lo + threadIdx.x; p < p_hi; p += blockDim.x) {
             const float v = s_alpha[p] * (s_de[p] - dot);
             s_de[p] = v;
             out[p] = v;
@@ -358,8 +399,8 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
                 const float4 d0 = *reinterpret_cast<const float4*>(s_dec + 8 * j);
                 const float4 d1 = *reinterpret_cast<const float4*>(s_dec + 8 * j + 4);
                 const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-                int p = grp;
-                for (; p + 6 * 4 < P; p += 7 * 4) {
+                int p = p_lo + grp;
+                for (; p + 6 * 4 < p_hi; p += 7 * 4) {
                     uint4 x[7];
 #pragma unroll
                     for (int u = 0; u < 7; ++u) x[u] = ld_stream_u4(ab + (long long)(p + 4 * u) * A + 8 * j);
@@ -372,7 +413,7 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
                         for (int i = 0; i < 8; ++i) acc[i] += (f[i] + dd[i] > 0.f) ? de : 0.f;
                     }
                 }
-                for (; p < P; p += 4) {
+                for (; p < p_hi; p += 4) {
                     const uint4 x = ld_stream_u4(ab + (long long)p * A + 8 * j);
                     const float de = s_de[p];
                     float f[8];
@@ -387,11 +428,23 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
                 *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
             }
             __syncthreads();
+            if (split) {
+                // rank 1 hands the sum over ITS pixels to rank 0 (its own exchange buffer), which finishes the row
+                if (hrank == 1 && grp == 0 && j < A8) {
+                    const unsigned dst = mapa_shared(smem_addr(s_xch + 8 * j), 0u);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        st_shared_cluster_f32(dst + 4 * i, acc[i] + s_part[8 * j + i] + s_part[A + 8 * j + i] + s_part[2 * A + 8 * j + i]);
+                }
+                cluster_barrier();
+                if (hrank == 1) continue;
+            }
             if (grp == 0 && j < A8) {
                 float res[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    res[i] = (acc[i] + s_part[8 * j + i] + s_part[A + 8 * j + i] + s_part[2 * A + 8 * j + i]) * w_full[8 * j + i];
+                    res[i] = (acc[i] + s_part[8 * j + i] + s_part[A + 8 * j + i] + s_part[2 * A + 8 * j + i] +
+                              (split ? s_xch[8 * j + i] : 0.f)) * w_full[8 * j + i];
                 float* o = d_att_dec + (long long)r * ld_ddec + 8 * j;
                 *reinterpret_cast<float4*>(o) = make_float4(res[0], res[1], res[2], res[3]);
                 *reinterpret_cast<float4*>(o + 4) = make_float4(res[4], res[5], res[6], res[7]);
@@ -740,7 +793,7 @@ extern "C" int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
                   "attention_step_bwd_bf16: row strides misaligned");
     // tensor-core d_alpha path: 8 warps x channel strips of whole 32-channel blocks
     const int use_mma = (C % 256 == 0) ? 1 : 0;
-    const size_t smem = ((size_t)C + 4 * (size_t)A + 2 * ((P + 3) & ~3) + 40 + 8 * (((P + 15) >> 4) << 4)) * sizeof(float)
+    const size_t smem = ((size_t)C + 5 * (size_t)A + 2 * ((P + 3) & ~3) + 40 + 8 * (((P + 15) >> 4) << 4)) * sizeof(float)
                         + 3 * (size_t)C * 2;
     ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_bwd_bf16: dims too large for shared memory");
     static size_t configured = 48 * 1024;
@@ -748,13 +801,36 @@ extern "C" int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
         ICD_CUDA(cudaFuncSetAttribute(att_step_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
+    // row balance (see the kernel): with SLOTS = 4 CTAs on each of the 148 SMs, a launch of `rows` CTAs whose last wave is partly
+    // filled runs its last n_split rows as two half-row CTAs each, so that whole + half rows fill that wave: rows + n_split = a
+    // multiple of SLOTS.  Only when the rows are not already balanced and the split part stays a minority.
+    const char* split_e = getenv("ICD_ATT_BWD_SPLIT");     // 0: never, 2: every row (tests), else: the balance rule
+    const bool split_env = !split_e || split_e[0] != '0';
+    const int SLOTS = 4 * ICD_NUM_SMS;
+    int n_split = 0;
+    if (split_e && split_e[0] == '2' && P >= 32) n_split = rows;
+    else if (split_env && P >= 32) {
+        const int rem = rows % SLOTS;                       // rows of the partly filled wave
+        if (rem > 3 * ICD_NUM_SMS && rem < SLOTS) n_split = SLOTS - rem;         // e.g. 512 rows: 80 split rows -> 432 + 160 CTAs
+        if (n_split > rows) n_split = 0;
+        if ((rows - n_split) & 1) n_split += (n_split < rows) ? 1 : -1;          // the whole rows must pair up (2-CTA clusters)
+        if (n_split < 0 || n_split > rows) n_split = 0;
+    }
     icd_prof_mark_begin(1, rows, s);
-    ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_BWD, att_step_bwd_bf16_kernel, dim3(rows), dim3(256), smem, s, P, C, A,
+    if (n_split > 0)
+        ICD_CUDA(icd_launch_pdl_cluster(ICD_PDL_ATT_BWD, att_step_bwd_bf16_kernel, dim3(rows + n_split), dim3(256), smem, s, 2u, P, C, A,
                             reinterpret_cast<const __nv_bfloat16*>(enc16), reinterpret_cast<const __nv_bfloat16*>(att_enc16),
                             att_dec, (long long)ld_dec, w_full, alpha, (long long)ld_alpha, d_alpha_ext, (long long)ld_dalpha,
                             gate, awe_raw, d_gated, d_att_dec, (long long)ld_ddec, d_fbeta_pre, (long long)ld_dfb,
                             d_e, (long long)ld_de, reinterpret_cast<__nv_bfloat16*>(dz16), (long long)ld_dz16, d_awe_out,
-                            use_mma));
+                            use_mma, rows - n_split));
+    else
+        ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_BWD, att_step_bwd_bf16_kernel, dim3(rows), dim3(256), smem, s, P, C, A,
+                            reinterpret_cast<const __nv_bfloat16*>(enc16), reinterpret_cast<const __nv_bfloat16*>(att_enc16),
+                            att_dec, (long long)ld_dec, w_full, alpha, (long long)ld_alpha, d_alpha_ext, (long long)ld_dalpha,
+                            gate, awe_raw, d_gated, d_att_dec, (long long)ld_ddec, d_fbeta_pre, (long long)ld_dfb,
+                            d_e, (long long)ld_de, reinterpret_cast<__nv_bfloat16*>(dz16), (long long)ld_dz16, d_awe_out,
+                            use_mma, -1));
     icd_prof_mark_end(1, s);
     ICD_LAUNCH_CHECK();
     return 0;

@@ -1,5 +1,7 @@
 """GPU tier, op level: every C-ABI kernel entry point against the oracle / an fp64 torch restatement of the same op.
 Tolerances (fp32 tier): 1e-5 norm-wise for contractions and pointwise ops unless stated."""
+import os
+
 import pytest
 import torch
 
@@ -283,6 +285,18 @@ def test_attention_step_bf16_features_matches_oracle_on_rounded_features(cuda, R
     H.assert_close_norm(d_fb, fb64.grad, 2e-5, "d_fbeta_pre")
     H.assert_close_norm(dz16[:, :A].float(), ad64.grad, 4e-3, "dz16[:, :A]")
     H.assert_close_norm(dz16[:, A:].float(), fb64.grad, 4e-3, "dz16[:, A:]")
+    # row-balance mode of the backward kernel: rows run as two half-row CTAs (2-CTA cluster, halves meet through distributed
+    # shared memory); forced here for every row, the balance rule itself splits only the tail of a launch
+    os.environ["ICD_ATT_BWD_SPLIT"] = "2"
+    try:
+        s_att_dec, s_fb, s_e, s_dz16 = ops.attention_step_bwd_bf16(enc16.to(cuda), att_enc16.to(cuda), att_dec.to(cuda),
+                                                                  wf.to(cuda), alpha, gate, awe, d_gated.to(cuda), d_alpha.to(cuda))
+    finally:
+        del os.environ["ICD_ATT_BWD_SPLIT"]
+    assert torch.equal(s_fb, d_fb) and torch.equal(s_dz16[:, A:], dz16[:, A:])
+    H.assert_close_norm(s_att_dec, ad64.grad, 2e-5, "d_att_dec (split rows)")
+    H.assert_close_norm(s_e, d_e, 1e-5, "d_e (split rows)")
+    H.assert_close_norm(s_dz16[:, :A].float(), ad64.grad, 4e-3, "dz16[:, :A] (split rows)")
     d_att_enc, d_att_enc16, d_wf, d_bf, d_be = ops.attention_proj_bwd_bf16(att_enc16.to(cuda), att_dec.to(cuda).view(1, R, A),
                                                         wf.to(cuda), d_e.view(R, 1, P), [R])
     H.assert_close_norm(d_att_enc, ae64.grad, 2e-5, "d_att_enc")
