@@ -801,18 +801,17 @@ extern "C" int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
         ICD_CUDA(cudaFuncSetAttribute(att_step_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    // row balance (see the kernel): with SLOTS = 4 CTAs on each of the 148 SMs, a launch of `rows` CTAs whose last wave is partly
-    // filled runs its last n_split rows as two half-row CTAs each, so that whole + half rows fill that wave: rows + n_split = a
-    // multiple of SLOTS.  Only when the rows are not already balanced and the split part stays a minority.
+    // row balance (see the kernel): with up to 4 CTAs on each of the 148 SMs, a launch of `rows` CTAs whose last wave is partly
+    // filled runs its last n_split rows as two half-row CTAs each, so that every SM gets the same number of CTAs: rows + n_split = a
+    // multiple of the SM count.  Only when the rows are not already balanced and the split part stays a minority.
     const char* split_e = getenv("ICD_ATT_BWD_SPLIT");     // 0: never, 2: every row (tests), else: the balance rule
     const bool split_env = !split_e || split_e[0] != '0';
-    const int SLOTS = 4 * ICD_NUM_SMS;
     int n_split = 0;
     if (split_e && split_e[0] == '2' && P >= 32) n_split = rows;
     else if (split_env && P >= 32) {
-        const int rem = rows % SLOTS;                       // rows of the partly filled wave
-        if (rem > 3 * ICD_NUM_SMS && rem < SLOTS) n_split = SLOTS - rem;         // e.g. 512 rows: 80 split rows -> 432 + 160 CTAs
-        if (n_split > rows) n_split = 0;
+        const int rem = rows % ICD_NUM_SMS;                 // rows beyond an equal number per SM
+        if (rem) n_split = ICD_NUM_SMS - rem;               // e.g. 512 rows: 80 split rows -> 432 + 160 CTAs = 4 per SM
+        if (n_split > rows / 4) n_split = 0;                // the split part must stay a minority
         if ((rows - n_split) & 1) n_split += (n_split < rows) ? 1 : -1;          // the whole rows must pair up (2-CTA clusters)
         if (n_split < 0 || n_split > rows) n_split = 0;
     }

@@ -42,7 +42,7 @@ for rows in (592, 574, 512, 444, 296, 256, 148):
 # backward kernel at the same row counts
 alpha, awe, gate, gated, gated16 = ops.attention_step_fwd_bf16(enc16, att16, att_dec, wf, bf, fb)
 d_gated = torch.randn(B, C, device=dev)
-for rows in (592, 574, 512, 444, 296, 256, 148):
+for rows in (592, 574, 512, 480, 444, 400, 320, 296, 290, 256, 200, 148):
     def runb(lo):
         sl = slice(lo, lo + rows)
         return ops.attention_step_bwd_bf16(enc16[sl], att16[sl], att_dec[sl], wf, alpha[sl], gate[sl], awe[sl], d_gated[sl], None)
