@@ -86,6 +86,86 @@ __global__ void lstm_pointwise_bwd_kernel(int rows, int D, const float* __restri
     }
 }
 
+// The same adjoint, four hidden units per thread (128-bit loads / stores, 64-bit bf16 stores), element arithmetic identical to
+// the scalar kernel above (results are bit-identical).  Operands that the FORWARD pass produced (gate activations, cell
+// states, keep mask) and the vocabulary-layer gradient are fetched BEFORE griddepcontrol.wait, so their latency hides behind
+// the tail of the dh contraction in front of this launch; dh and dc are written by kernels of the chain itself (dc by the
+// previous adjoint, which in the baseline decoder's chain may still be running when this grid becomes resident) and are
+// read after the wait.
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4_bf16(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 w;
+    w.x = *reinterpret_cast<unsigned*>(&lo); w.y = *reinterpret_cast<unsigned*>(&hi);
+    *reinterpret_cast<uint2*>(p) = w;
+}
+
+__global__ void __launch_bounds__(128) lstm_pointwise_bwd_vec4_kernel(
+        int rows, int D, const float* __restrict__ dh_in, const float* __restrict__ d_hdrop, long long hdrop_row_stride,
+        const unsigned char* __restrict__ mask, float scale, float* __restrict__ dc_inout,
+        const float* __restrict__ gates_act, const float* __restrict__ c_prev, const float* __restrict__ c_new,
+        float* __restrict__ dgates_pre, long long ld_dg, __nv_bfloat16* __restrict__ dg16, long long ld_dg16,
+        const float* __restrict__ dh_parts, int n_parts, int parts_rows) {
+    pdl_trigger();
+    const int D4 = D >> 2;
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = q < (long long)rows * D4;
+    int r = 0, d = 0;
+    long long idx = 0;
+    float4 gi, gf, gg, go, cn, cp, u;
+    gi = gf = gg = go = cn = cp = u = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+        r = (int)(q / D4); d = (int)(q % D4) * 4;
+        idx = (long long)r * D + d;
+        const float* ga = gates_act + (long long)r * 4 * D + d;
+        gi = ld4(ga); gf = ld4(ga + D); gg = ld4(ga + 2 * D); go = ld4(ga + 3 * D);
+        cn = ld4(c_new + idx); cp = ld4(c_prev + idx);
+        if (d_hdrop) {
+            u = ld4(d_hdrop + (long long)r * hdrop_row_stride + d);
+            if (mask) {
+                const uchar4 m = *reinterpret_cast<const uchar4*>(mask + idx);
+                u.x = m.x ? u.x * scale : 0.f; u.y = m.y ? u.y * scale : 0.f;
+                u.z = m.z ? u.z * scale : 0.f; u.w = m.w ? u.w * scale : 0.f;
+            }
+        }
+    }
+    pdl_wait();
+    if (!live) return;
+    float4 dh;
+    if (n_parts > 0 && r < parts_rows) {       // deferred split-K: sum the K-slice planes of the dh contraction here
+        dh = make_float4(0.f, 0.f, 0.f, 0.f);
+        const long long stride = (long long)parts_rows * D;
+        for (int sp = 0; sp < n_parts; ++sp) {
+            const float4 p = ld4(dh_parts + sp * stride + idx);
+            dh.x += p.x; dh.y += p.y; dh.z += p.z; dh.w += p.w;
+        }
+    } else dh = dh_in ? ld4(dh_in + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 dc_old = ld4(dc_inout + idx);
+    float4 pi, pf, pg, po, dcn;
+#define ICD_ADJ(X)                                                                                                    \
+    {                                                                                                                 \
+        const float i = gi.X, f = gf.X, g = gg.X, o = go.X;                                                           \
+        float dhx = dh.X;                                                                                             \
+        if (d_hdrop) dhx += u.X;                                                                                      \
+        const float tc = tanhf(cn.X);                                                                                 \
+        const float d_o = dhx * tc;                                                                                   \
+        const float dc = dc_old.X + dhx * o * (1.f - tc * tc);                                                        \
+        const float d_i = dc * g, d_g = dc * i, d_f = dc * cp.X;                                                      \
+        dcn.X = dc * f;                                                                                               \
+        pi.X = d_i * i * (1.f - i); pf.X = d_f * f * (1.f - f); pg.X = d_g * (1.f - g * g); po.X = d_o * o * (1.f - o); \
+    }
+    ICD_ADJ(x) ICD_ADJ(y) ICD_ADJ(z) ICD_ADJ(w)
+#undef ICD_ADJ
+    st4(dc_inout + idx, dcn);
+    float* dg = dgates_pre + (long long)r * ld_dg + d;
+    st4(dg, pi); st4(dg + D, pf); st4(dg + 2 * D, pg); st4(dg + 3 * D, po);
+    if (dg16) {
+        __nv_bfloat16* q16 = dg16 + (long long)r * ld_dg16 + d;
+        st4_bf16(q16, pi); st4_bf16(q16 + D, pf); st4_bf16(q16 + 2 * D, pg); st4_bf16(q16 + 3 * D, po);
+    }
+}
+
 // out[n] = sum_m mask[m] * X[m*ld + n].  block (32,32): x -> column, y -> row phase.  deterministic.
 __global__ void colsum_kernel(const float* __restrict__ X, long long ld, long long M, int N,
                               const unsigned char* __restrict__ row_mask, float* __restrict__ out) {
@@ -320,8 +400,41 @@ __device__ __forceinline__ void online_merge(float& m, float& s, float m2, float
     s = a + b; m = mn;
 }
 
-// single pass over the row: online log-sum-exp, 128-bit loads (scalar head / tail around the 16-byte aligned body), 4 loads in flight
-__global__ void __launch_bounds__(256) cross_entropy_fwd_kernel(int V, const float* __restrict__ logits,
+// d(loss)/d(logit) of one element: (exp(x - lse) - onehot) * scale.  ONE definition for the streaming backward kernel and the
+// one-pass kernel, so their bf16 gradients agree bit for bit (exp through ex2.approx: 2^-22 relative, far inside every tier's bar).
+__device__ __forceinline__ float ce_grad(float x, bool is_target, float lse, float scale) {
+    return (__expf(x - lse) - (is_target ? 1.f : 0.f)) * scale;
+}
+
+// Running (max, sum exp) of one row over a 256-thread CTA, before the cross-thread merge: scalar head up to the row's first
+// 16-byte boundary (rows of V = 9490 floats start 8-byte aligned on odd r), scalar tail, 128-bit body.  CE_U body loads of a thread are issued
+// before the first one is consumed.  (Measured on the 12288 x 9490 logits: more loads per thread lose more through the lower
+// occupancy than they gain — 3 at eight CTAs per SM for the streaming kernel, 5 at five CTAs per SM for the kernel that parks the row.)  PARK: the row is also copied to shared memory (sx[v] = x[v]).  One definition for
+// cross_entropy_fwd_kernel and the one-pass kernel: their log-sum-exp agrees bit for bit.
+template <bool PARK, int CE_U>
+__device__ __forceinline__ void ce_row_stats(const float* __restrict__ x, int V, int head, int V4, float* sx, float& m, float& s) {
+    if ((int)threadIdx.x < head) { const float v = x[threadIdx.x]; if (PARK) sx[threadIdx.x] = v; online_add(m, s, v); }
+    for (int v = head + 4 * V4 + threadIdx.x; v < V; v += 256) { const float t = x[v]; if (PARK) sx[v] = t; online_add(m, s, t); }
+    const float* xb = x + head;
+    for (int j0 = threadIdx.x; j0 < V4; j0 += CE_U * 256) {
+        float4 v[CE_U];
+#pragma unroll
+        for (int u = 0; u < CE_U; ++u)
+            if (j0 + u * 256 < V4) v[u] = ld_stream_f4(xb + 4 * (j0 + u * 256));
+#pragma unroll
+        for (int u = 0; u < CE_U; ++u) {
+            if (j0 + u * 256 < V4) {
+                if (PARK) *reinterpret_cast<float4*>(sx + head + 4 * (j0 + u * 256)) = v[u];
+                const float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)), mn = fmaxf(m, mx);
+                s = s * __expf(m - mn) + __expf(v[u].x - mn) + __expf(v[u].y - mn) + __expf(v[u].z - mn) + __expf(v[u].w - mn);
+                m = mn;
+            }
+        }
+    }
+}
+
+// single pass over the row: online log-sum-exp, 128-bit loads (scalar head / tail around the 16-byte aligned body)
+__global__ void __launch_bounds__(256, 8) cross_entropy_fwd_kernel(int V, const float* __restrict__ logits,
                                                                 const long long* __restrict__ targets,
                                                                 float* __restrict__ row_loss, float* __restrict__ lse_out) {
     __shared__ float s_m[8], s_s[8];
@@ -334,29 +447,9 @@ __global__ void __launch_bounds__(256) cross_entropy_fwd_kernel(int V, const flo
     }
     if (tgt >= V) __trap();                          // nn.CrossEntropyLoss raises on a class index >= V; never read outside the row
     float m = -INFINITY, s = 0.f;
-    // scalar head up to the first 16-byte boundary of the row (rows of V = 9490 floats start 8-byte aligned on odd r),
-    // 128-bit body with four loads in flight per thread, scalar tail
-    const int head = min(V, (int)((4 - ((reinterpret_cast<uintptr_t>(x) >> 2) & 3)) & 3));
+    const int head = min(V, (int)((4 - ((reinterpret_cast<uintptr_t>(x) >> 2) & 3)) & 3));      // see ce_row_stats
     const int V4 = (V - head) >> 2;
-    if ((int)threadIdx.x < head) online_add(m, s, x[threadIdx.x]);
-    for (int v = head + 4 * V4 + threadIdx.x; v < V; v += 256) online_add(m, s, x[v]);
-    const float* xb = x + head;
-    int j = threadIdx.x;
-    for (; j + 3 * 256 < V4; j += 4 * 256) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ld_stream_f4(xb + 4 * (j + u * 256));
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)), mn = fmaxf(m, mx);
-            s = s * __expf(m - mn) + __expf(v[u].x - mn) + __expf(v[u].y - mn) + __expf(v[u].z - mn) + __expf(v[u].w - mn);
-            m = mn;
-        }
-    }
-    for (; j < V4; j += 256) {
-        const float4 v = ld_stream_f4(xb + 4 * j);
-        online_add(m, s, v.x); online_add(m, s, v.y); online_add(m, s, v.z); online_add(m, s, v.w);
-    }
+    ce_row_stats<false, 3>(x, V, head, V4, nullptr, m, s);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
@@ -378,7 +471,7 @@ __global__ void __launch_bounds__(256) cross_entropy_fwd_kernel(int V, const flo
 // while its log-sum-exp is formed (exactly as cross_entropy_fwd_kernel does), then the bf16 gradient
 // (exp(x - lse) - onehot) * inv_count is written from the parked copy — every logit is read from HBM once instead of twice.
 // The upstream gradient of the loss is applied afterwards (scale_bf16_by_device_scalar_kernel: a no-op when it is 1).
-__global__ void __launch_bounds__(256) cross_entropy_fwd_grad16_kernel(int V, const float* __restrict__ logits,
+__global__ void __launch_bounds__(256, 5) cross_entropy_fwd_grad16_kernel(int V, const float* __restrict__ logits,
                                                                        const long long* __restrict__ targets, float inv_count,
                                                                        float* __restrict__ row_loss, float* __restrict__ lse_out,
                                                                        __nv_bfloat16* __restrict__ d16, long long ld16) {
@@ -403,28 +496,7 @@ __global__ void __launch_bounds__(256) cross_entropy_fwd_grad16_kernel(int V, co
     // 128-bit body is 16-byte aligned on both sides
     const int pad = (4 - head) & 3;
     float* sx = s_x + pad;
-    if ((int)threadIdx.x < head) { const float v = x[threadIdx.x]; sx[threadIdx.x] = v; online_add(m, s, v); }
-    for (int v = head + 4 * V4 + threadIdx.x; v < V; v += 256) { const float t = x[v]; sx[v] = t; online_add(m, s, t); }
-    const float* xb = x + head;
-    float* sb = sx + head;
-    int j = threadIdx.x;
-    for (; j + 3 * 256 < V4; j += 4 * 256) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ld_stream_f4(xb + 4 * (j + u * 256));
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            *reinterpret_cast<float4*>(sb + 4 * (j + u * 256)) = v[u];
-            const float mx = fmaxf(fmaxf(v[u].x, v[u].y), fmaxf(v[u].z, v[u].w)), mn = fmaxf(m, mx);
-            s = s * __expf(m - mn) + __expf(v[u].x - mn) + __expf(v[u].y - mn) + __expf(v[u].z - mn) + __expf(v[u].w - mn);
-            m = mn;
-        }
-    }
-    for (; j < V4; j += 256) {
-        const float4 v = ld_stream_f4(xb + 4 * j);
-        *reinterpret_cast<float4*>(sb + 4 * j) = v;
-        online_add(m, s, v.x); online_add(m, s, v.y); online_add(m, s, v.z); online_add(m, s, v.w);
-    }
+    ce_row_stats<true, 5>(x, V, head, V4, sx, m, s);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
@@ -437,20 +509,31 @@ __global__ void __launch_bounds__(256) cross_entropy_fwd_grad16_kernel(int V, co
     for (int i = 1; i < 8; ++i) online_merge(M, S, s_m[i], s_s[i]);      // every thread, same order as cross_entropy_fwd_kernel
     const float lse = M + logf(S);
     if (threadIdx.x == 0) { row_loss[r] = lse - sx[tgt]; lse_out[r] = lse; }
-    // gradient, 8 columns (16 bytes of bf16) per thread and pass
-    const int V8 = V >> 3;
+    // gradient, 8 columns (16 bytes of bf16) per thread and pass; the parked row is read back with 64-bit accesses when its
+    // alignment phase allows (pad even: every row of an even-V matrix)
+    const int V8 = V >> 3, itgt = (int)tgt;
+    const bool pair_ok = (pad & 1) == 0;
     for (int q = threadIdx.x; q < (int)(ld16 >> 3); q += 256) {
+        float xv[8];
+        const int v0 = 8 * q;
+        if (q < V8 && pair_ok) {
+#pragma unroll
+            for (int h = 0; h < 4; ++h) { const float2 t = *reinterpret_cast<const float2*>(sx + v0 + 2 * h); xv[2 * h] = t.x; xv[2 * h + 1] = t.y; }
+        } else {
+#pragma unroll
+            for (int h = 0; h < 8; ++h) xv[h] = (v0 + h < V) ? sx[v0 + h] : 0.f;
+        }
+        float g[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) g[h] = ce_grad(xv[h], v0 + h == itgt, lse, inv_count);
+        if (q >= V8) {
+#pragma unroll
+            for (int h = 0; h < 8; ++h) if (v0 + h >= V) g[h] = 0.f;                    // pad columns of the bf16 row
+        }
         uint32_t pk[4];
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const int v = 8 * q + 2 * h;
-            float g0 = 0.f, g1 = 0.f;
-            if (q < V8 || v < V) g0 = (expf(sx[v] - lse) - (v == tgt ? 1.f : 0.f)) * inv_count;
-            if (q < V8 || v + 1 < V) g1 = (expf(sx[v + 1] - lse) - (v + 1 == tgt ? 1.f : 0.f)) * inv_count;
-            const __nv_bfloat162 t = __floats2bfloat162_rn(g0, g1);
-            pk[h] = *reinterpret_cast<const uint32_t*>(&t);
-        }
-        *reinterpret_cast<uint4*>(d16r + 8 * q) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        for (int h = 0; h < 4; ++h) { const __nv_bfloat162 t = __floats2bfloat162_rn(g[2 * h], g[2 * h + 1]); pk[h] = *reinterpret_cast<const uint32_t*>(&t); }
+        *reinterpret_cast<uint4*>(d16r + v0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
 }
 
@@ -497,7 +580,8 @@ __global__ void __launch_bounds__(256) cross_entropy_bwd_kernel(int V, const flo
     const float scale = inv_count * (upstream ? upstream[0] : 1.f);
     // scalar head up to the row's first 16-byte boundary, 128-bit body with four loads in flight per thread, scalar tail
     // (the fp32 gradient rows share the alignment of the logit rows when both buffers are 16-byte aligned)
-    auto grad = [&](float xv, int v) { return (expf(xv - lse) - (v == tgt ? 1.f : 0.f)) * scale; };
+    const int itgt = (int)tgt;
+    auto grad = [&](float xv, int v) { return ce_grad(xv, v == itgt, lse, scale); };
     auto emit1 = [&](int v) {
         const float g = grad(x[v], v);
         if (dx) dx[v] = g;
@@ -561,6 +645,19 @@ int icd_lstm_pointwise_bwd(int rows, int D, const float* dh_in, const float* d_h
                            const float* dh_parts, int n_parts, int parts_rows) {
     if (rows == 0) return 0;
     const long long n = (long long)rows * D;
+    auto al = [](const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; };
+    const bool scalar_only = getenv("ICD_LSTM_BWD_SCALAR") != nullptr;        // test hook: the one-unit-per-thread kernel
+    const bool vec4 = !scalar_only && D % 4 == 0 && ld_dg % 4 == 0 && hdrop_row_stride % 4 == 0 && (!dg16 || ld_dg16 % 4 == 0) &&
+                      al(dh_in, 16) && al(d_hdrop, 16) && al(mask, 4) && al(dc_inout, 16) && al(gates_act, 16) && al(c_prev, 16) &&
+                      al(c_new, 16) && al(dgates_pre, 16) && al(dg16, 8) && al(dh_parts, 16);
+    if (vec4) {
+        ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, lstm_pointwise_bwd_vec4_kernel, dim3((unsigned)((n / 4 + 127) / 128)), dim3(128), (size_t)0,
+                                s, rows, D, dh_in, d_hdrop, (long long)hdrop_row_stride, (const unsigned char*)mask, scale, dc_inout,
+                                gates_act, c_prev, c_new, dgates_pre, (long long)ld_dg, (__nv_bfloat16*)dg16, (long long)ld_dg16,
+                                dh_parts, n_parts, parts_rows));
+        ICD_LAUNCH_CHECK();
+        return 0;
+    }
     ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, lstm_pointwise_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), (size_t)0, s, rows, D,
                             dh_in, d_hdrop, (long long)hdrop_row_stride, (const unsigned char*)mask, scale, dc_inout, gates_act,
                             c_prev, c_new, dgates_pre, (long long)ld_dg, (__nv_bfloat16*)dg16, (long long)ld_dg16,

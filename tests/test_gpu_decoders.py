@@ -789,3 +789,40 @@ def test_embedding_gradient_is_run_to_run_deterministic(cuda, glove):
     p64, _, dl64, a64 = O.attention_decoder_forward(w64, enc.double(), caps, lens)
     O.attention_loss(p64, caps, dl64, a64).backward()
     H.assert_close_norm(grads[0], w64["embedding.weight"].grad, 1e-4, "embedding gradient")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32x3", "bf16"])
+def test_lstm_gate_adjoint_vectorised_kernel_is_bit_identical_to_scalar(cuda, precision, monkeypatch):
+    """(The tensor-core tiers: their contractions are run-to-run deterministic; the fp32 FMA tier's split-K weight gradients use atomics.)
+    The LSTMCell adjoint of the BPTT (models/attention.py:277-278 backward) runs four hidden units per thread; the
+    one-unit-per-thread kernel (ICD_LSTM_BWD_SCALAR, also the fallback for D % 4 != 0) must give bit-identical gradients,
+    with train-mode dropout, ragged lengths and the deferred split-K planes of the dh contraction in play."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.vocabulary import synthetic_vocab
+    case = dict(B=37, V=97, A=64, D=64, E=32, max_len=11, lengths=[11] * 9 + [9] * 8 + [6] * 10 + [3] * 10, wseed=6, iseed=41,
+                dropout=0.5, train=True, fine_tune_embedding=True)
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams, synthetic_vocab(case["V"]))
+    dec = dec.to(cuda)
+    dec.train()
+    dec.precision = precision
+    enc = synthetic_features(case["B"], case["iseed"]).to(cuda)
+    caps, lens = synthetic_caps(case)
+    caps = caps.to(cuda)
+    keep = (torch.rand(max(lens) - 1, case["B"], case["D"], generator=torch.Generator().manual_seed(3)) < 0.5).to(cuda)
+
+    def grads():
+        dec.zero_grad()
+        dec._dropout_mask_override = keep
+        preds, _, dl, alphas = dec(enc, caps, lens)
+        O.attention_loss(preds, caps, dl, alphas).backward()
+        return {k: p.grad.clone() for k, p in dec.named_parameters() if p.grad is not None}
+
+    monkeypatch.delenv("ICD_LSTM_BWD_SCALAR", raising=False)
+    g_vec = grads()
+    monkeypatch.setenv("ICD_LSTM_BWD_SCALAR", "1")
+    g_sc = grads()
+    monkeypatch.delenv("ICD_LSTM_BWD_SCALAR", raising=False)
+    assert g_vec.keys() == g_sc.keys() and len(g_vec) > 8
+    for k in g_vec:
+        assert torch.equal(g_vec[k], g_sc[k]), k

@@ -58,6 +58,27 @@ def run(name, M, N, K, a_mn=False, b_mn=False, fp32=True, bf16=False, mask=False
     print("%-34s M=%6d N=%5d K=%6d  %8.1f us  %7.1f TF/s" % (name, M, N, K, us, 2.0 * M * N * K / us / 1e6), flush=True)
 
 
+if "--fc" in sys.argv:
+    # the vocabulary layer (K6) and the hoisted input projection (K5): short K, fp32 output — tile width, pairing, multicast clusters
+    for name, M, N, K, kw in [("K6 fc fwd (ldc=V, mask)", B * T, V, D, dict(bias=True, mask=True)),
+                              ("K6 fc fwd (ldc=9496)", B * T, V, D, dict(bias=True, mask=True, ldc=9496)),
+                              ("K5 emb*W_ih", B * T, 4 * D, E, dict(bias=True))]:
+        for pair, plan, cl in [("0", "256,1", "1,1"), ("0", "128,1", "1,1"), ("2", "256,1", "1,1"), ("2", "128,1", "1,1"),
+                               ("0", "256,1", "2,1"), ("0", "256,1", "1,2"), ("0", "256,1", "2,2"), ("0", "128,1", "2,2"), ("0", "256,1", "4,1"),
+                               ("0", "256,1", "4,2")]:
+            os.environ["ICD_GEMM_FORCE_PLAN"] = plan
+            os.environ["ICD_GEMM_CLUSTER"] = cl
+            ops.gemm_set_pair_mode(int(pair))
+            run("%s pair %s plan %s cluster %s" % (name, pair, plan, cl), M, N, K, iters=20, **kw)
+    sys.exit(0)
+if "--fck" in sys.argv:
+    # K-slope of the vocabulary-layer shape: the K -> 0 intercept is the epilogue + store time of the real kernel
+    for ldc in (V, 9496, 9600):
+        for K_ in (64, 128, 256, 512, 1024):
+            run("fc shape ldc=%d" % ldc, B * T, V, K_, bias=True, mask=True, ldc=ldc, iters=10)
+    for K_ in (64, 256, 512):
+        run("K5 shape", B * T, 4 * D, K_, bias=True, iters=20)
+    sys.exit(0)
 if "--clusters" in sys.argv:
     # sweep of the cm x cn multicast clusters and tile / split-K plans on the in-loop (M = batch) contractions
     shapes = [("K2 z", B, NZ, D, dict(bias=True), ["128,1", "64,1", "256,1"]),
