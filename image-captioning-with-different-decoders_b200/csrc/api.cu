@@ -38,10 +38,21 @@ unsigned icd_pdl_allowed(int cls) {
         return e ? (unsigned)strtoul(e, nullptr, 0) : 0xffffffffu;
     }();
     static thread_local int last_cls = -1;
-    const unsigned ok = ((icd_pdl_mask() >> cls) & 1u) && (last_cls < 0 || ((pred_mask >> last_cls) & 1u));
+    unsigned ok = ((icd_pdl_mask() >> cls) & 1u) && (last_cls < 0 || ((pred_mask >> last_cls) & 1u));
+    if (cls == ICD_PDL_GEMM_LATE) ok = (icd_pdl_mask() >> ICD_PDL_GEMM) & 1u;
+    // an attention-step grid may be STAGED behind a contraction that keeps its dependents back until its last CTA has exited:
+    // every SM is free when the grid is placed (no uneven placement), and the launch latency hides behind the contraction
+    if ((cls == ICD_PDL_ATT_FWD || cls == ICD_PDL_ATT_BWD) && last_cls == ICD_PDL_GEMM_LATE) ok = 1u;
     last_cls = cls;
     return ok;
 }
+
+namespace { thread_local int g_late_hint = 0; }
+void icd_gemm_next_feeds_attention() {
+    static const bool on = [] { const char* e = getenv("ICD_PDL_LATE"); return !e || e[0] != '0'; }();
+    g_late_hint = on ? 1 : 0;
+}
+int icd_gemm_take_late_hint() { const int h = g_late_hint; g_late_hint = 0; return h; }
 
 namespace {
 ProfRec g_prof[PROF_MAX];

@@ -29,7 +29,10 @@ static inline cudaStream_t icd_stream(void* s) { return reinterpret_cast<cudaStr
 
 #ifdef __CUDACC__
 // kernel classes for the programmatic-dependent-launch policy (bit index into icd_pdl_mask())
-enum { ICD_PDL_GEMM = 0, ICD_PDL_ATT_FWD = 1, ICD_PDL_ATT_BWD = 2, ICD_PDL_POINTWISE = 3, ICD_PDL_REDUCE = 4 };
+enum { ICD_PDL_GEMM = 0, ICD_PDL_ATT_FWD = 1, ICD_PDL_ATT_BWD = 2, ICD_PDL_POINTWISE = 3, ICD_PDL_REDUCE = 4,
+       ICD_PDL_GEMM_LATE = 5 };      // a contraction that does NOT release its dependents early (they start when its last CTA exits)
+void icd_gemm_next_feeds_attention();   // api.cu: the next contraction of this thread is followed by an attention-step launch
+int icd_gemm_take_late_hint();          // api.cu: consumes the hint (1 once, then 0)
 unsigned icd_pdl_mask();             // api.cu: which classes may start early (env ICD_PDL_MASK overrides the default)
 unsigned icd_pdl_allowed(int cls);   // api.cu: 1 if a launch of class `cls` may start early behind the previous launch
 

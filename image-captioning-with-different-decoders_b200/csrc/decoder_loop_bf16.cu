@@ -147,19 +147,24 @@ int icd_attention_decoder_fwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
     ICD_CUDA(cudaMemsetAsync(d->b_cat + A + C, 0, sizeof(float) * 4 * D, s));
 
     // ---- bf16 copies of the weights (they change every optimiser step) ----
-    CVT(d->enc_att_w, C, A, C, u.We, C);
-    CVT(d->dec_att_w, D, A, D, u.Wcat, D);                                   // [W_dec; W_fbeta; W_hh]
-    CVT(d->f_beta_w, D, C, D, at16(u.Wcat, (int64_t)A * D), D);
-    CVT(d->w_hh, D, 4 * D, D, at16(u.Wcat, (int64_t)(A + C) * D), D);
-    CVT(d->w_ih, E + C, 4 * D, E, u.WihE, u.ldE);
-    CVT(d->w_ih + E, E + C, 4 * D, C, u.WihC, C);
+    // (one launch for all of them: icd_convert_bf16_batch)
     static const bool fused_cell_env = [] { const char* e = getenv("ICD_FUSED_CELL"); return !e || e[0] != '0'; }();
     const bool fused_cell = fused_cell_env && D % 16 == 0 && (E + C) % 4 == 0 && E % 4 == 0 && NZ % 4 == 0 &&
                             (!d->drop_mask || D % 8 == 0) && (T * D) % 8 == 0;
+    {
+        const IcdCvtSeg segs[9] = {
+            {d->enc_att_w, C, A, C, u.We, C},
+            {d->dec_att_w, D, A, D, u.Wcat, D},                                               // [W_dec; W_fbeta; W_hh]
+            {d->f_beta_w, D, C, D, at16(u.Wcat, (int64_t)A * D), D},
+            {d->w_hh, D, 4 * D, D, at16(u.Wcat, (int64_t)(A + C) * D), D},
+            {d->w_ih, E + C, 4 * D, E, u.WihE, u.ldE},
+            {d->w_ih + E, E + C, 4 * D, C, u.WihC, C},
+            {d->h_lin_w, C, D, C, u.Wh, C},
+            {d->c_lin_w, C, D, C, u.Wc, C},
+            {d->fc_w, D, V, D, u.Wfc, D}};
+        ICD_TRY(icd_convert_bf16_batch(segs, 9, s));
+    }
     if (fused_cell) ICD_TRY(icd_convert_bf16_gateperm(d->w_ih + E, E + C, D, C, u.WihCp, C, s));
-    CVT(d->h_lin_w, C, D, C, u.Wh, C);
-    CVT(d->c_lin_w, C, D, C, u.Wc, C);
-    CVT(d->fc_w, D, V, D, u.Wfc, D);
     // ---- features: fp32 -> bf16 and the pixel mean (:161) in one pass over encoder_out ----
     if (d->enc16) ICD_TRY(icd_feature_mean_bf16(B, P, C, d->enc16, d->mean_enc, u.mean, s));
     else {
@@ -186,6 +191,7 @@ int icd_attention_decoder_fwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
         float* zt = d->z + (size_t)t * B * NZ;
         char* h16 = at16(u.h, (int64_t)t * B * D);
         char* g16 = at16(u.gated, (int64_t)t * B * C);
+        icd_gemm_next_feeds_attention();       // the attention-step grid is staged behind K2 and placed when K2's last CTA exits
         MMX(h16, D, 0, u.Wcat, D, 0, zt, NZ, bt, NZ, D, d->b_cat, nullptr, nullptr, 0, nullptr, 0, nullptr, nullptr, 0);   // K2
         ICD_TRY(icd_attention_step_fwd_bf16(bt, P, C, A, nullptr, u.enc, u.att_enc, zt, NZ, d->full_att_w, d->full_att_b,
                                             zt + A, NZ, d->alphas + (size_t)t * P, (int64_t)T * P,
@@ -254,6 +260,7 @@ int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s) {
                                        dzt + A + C, NZ, s, at16(dz16, A + C), NZ,     // dG also emitted as bf16
                                        u.splitk, dh_splits, dh_rows));
         // d_gated = dG W_ih[:, E:]           (W_ih[:, E:] stored [4D, C] = MN-major B, N = C, K = 4D)
+        icd_gemm_next_feeds_attention();
         MMX(at16(dz16, A + C), NZ, 0, u.WihC, C, 1, d->d_gated, C, bt, C, 4 * D, NF, NF, NF, 0, NF, 0, nullptr, nullptr, 0);
         ICD_TRY(icd_attention_step_bwd_bf16(bt, P, C, A, u.enc, u.att_enc, zt, NZ, d->full_att_w,
                                             d->alphas + (size_t)t * P, (int64_t)T * P,

@@ -83,6 +83,7 @@ struct KArgs {
                                               // CTAs of a cluster row share their A tile and the cm CTAs of a cluster column their
                                               // B tile — every CTA fetches 1/cn of A and 1/cm of B and TMA-multicasts the slice into
                                               // all shared memories that need it, so each operand byte leaves L2 once per cluster
+    int late_trigger;                         // 1: dependents are not released early (an attention-step launch follows, see api.cu)
     int raster_n;                             // 1: consecutive work units walk along N (a wave of CTAs writes whole output rows:
                                               // contiguous DRAM pages) instead of along M
     const int* m_live;                        // optional DEVICE row count: only rows < min(M, *m_live) are computed / written
@@ -460,7 +461,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
     // PDL: everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the previous kernel's tail;
     // from here on operands / epilogue inputs produced upstream are read and C is written
-    pdl_trigger();
+    if (!p.late_trigger) pdl_trigger();
     pdl_wait();
     const int M_eff = p.m_live ? min(e.M, max((int)uniform_u32((uint32_t)*p.m_live), 0)) : e.M;     // device-side row count (read after the dependency wait)
     const int tiles_m = (M_eff + BM - 1) / BM;
@@ -729,7 +730,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = uniform_u32(*tmem_slot);
-    pdl_trigger();
+    if (!p.late_trigger) pdl_trigger();
     pdl_wait();
     const int M_eff = p.m_live ? min(e.M, max((int)uniform_u32((uint32_t)*p.m_live), 0)) : e.M;
     const int tiles_m = (M_eff + BM - 1) / BM;
@@ -956,6 +957,29 @@ __global__ void convert_rows_kernel(const float* __restrict__ src, long long s_r
     }
 }
 
+// up to ICD_CVT_MAX_SEGS conversions of the 128-bit kind in one grid: work item i (one float4) belongs to the segment whose
+// prefix range holds it
+struct CvtBatch {
+    const float* src[ICD_CVT_MAX_SEGS]; __nv_bfloat16* dst[ICD_CVT_MAX_SEGS];
+    long long s_r[ICD_CVT_MAX_SEGS], ldd[ICD_CVT_MAX_SEGS], end[ICD_CVT_MAX_SEGS];      // end: exclusive prefix sum of float4 items
+    int n4[ICD_CVT_MAX_SEGS];                                                           // float4 items per row
+    int n;
+};
+__global__ void __launch_bounds__(256) convert_rows_batch_kernel(const CvtBatch b) {
+    const long long total = b.end[b.n - 1];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int g = 0;
+        while (i >= b.end[g]) ++g;
+        const long long j = i - (g ? b.end[g - 1] : 0);
+        const long long r = j / b.n4[g]; const int c = (int)(j % b.n4[g]) * 4;
+        const float4 x = ld_stream_f4(b.src[g] + r * b.s_r[g] + c);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(b.dst[g] + r * b.ldd[g] + c) = pk;
+    }
+}
+
 // gate-permuting variant for an LSTM weight block [4D][cols] (gate-major rows i|f|g|o): destination row
 // ug*32 + g*8 + j = source row g*D + ug*8 + j, so that 32 consecutive rows hold the four gates of 8 hidden units (LstmEpi).
 __global__ void convert_rows_gateperm_kernel(const float* __restrict__ src, long long s_r, int D, int cols,
@@ -1082,11 +1106,11 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KArgs& k, int u
             if (getenv("ICD_GEMM_VERBOSE")) fprintf(stderr, "[icd] gemm_tc<%d>: %d co-resident clusters of %d CTAs\n", BN, max_clusters[cl], cl);
         }
         const int clusters = units < max_clusters[cl] ? units : max_clusters[cl];
-        ICD_CUDA(icd_launch_pdl_cluster(ICD_PDL_GEMM, gemm_tc_kernel<BN>, dim3(cl * clusters), dim3(NUM_THREADS), (size_t)Cfg<BN>::SMEM, s,
+        ICD_CUDA(icd_launch_pdl_cluster(k.late_trigger ? ICD_PDL_GEMM_LATE : ICD_PDL_GEMM, gemm_tc_kernel<BN>, dim3(cl * clusters), dim3(NUM_THREADS), (size_t)Cfg<BN>::SMEM, s,
                                         (unsigned)cl, tmA, tmB, k));
     } else {
         const int grid = units < ICD_NUM_SMS ? units : ICD_NUM_SMS;
-        ICD_CUDA(icd_launch_pdl(ICD_PDL_GEMM, gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), (size_t)Cfg<BN>::SMEM, s, tmA, tmB, k));
+        ICD_CUDA(icd_launch_pdl(k.late_trigger ? ICD_PDL_GEMM_LATE : ICD_PDL_GEMM, gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), (size_t)Cfg<BN>::SMEM, s, tmA, tmB, k));
     }
     ICD_LAUNCH_CHECK();
     return 0;
@@ -1100,7 +1124,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const KArgs& k, int 
         attr_set = true;
     }
     const int pairs = units < ICD_NUM_SMS / 2 ? units : ICD_NUM_SMS / 2;
-    ICD_CUDA(icd_launch_pdl_cluster(ICD_PDL_GEMM, gemm_tc2_kernel<BN>, dim3(2 * pairs), dim3(NUM_THREADS), (size_t)Cfg2<BN>::SMEM, s, 2u,
+    ICD_CUDA(icd_launch_pdl_cluster(k.late_trigger ? ICD_PDL_GEMM_LATE : ICD_PDL_GEMM, gemm_tc2_kernel<BN>, dim3(2 * pairs), dim3(NUM_THREADS), (size_t)Cfg2<BN>::SMEM, s, 2u,
                                     tmA, tmB, k));
     ICD_LAUNCH_CHECK();
     return 0;
@@ -1222,6 +1246,27 @@ int icd_convert_bf16(const float* src, int64_t s_r, int64_t s_c, int rows, int c
         ICD_CHECK_ARG(grid.y <= 65535, "convert_bf16: too many columns for the transposing path");
         convert_transpose_kernel<<<grid, dim3(32, 8), 0, s>>>(src, s_c, rows, cols, d, ldd);
     }
+    ICD_LAUNCH_CHECK();
+    return 0;
+}
+
+int icd_convert_bf16_batch(const IcdCvtSeg* segs, int n, cudaStream_t s) {
+    CvtBatch b = {};
+    long long total = 0;
+    for (int i = 0; i < n; ++i) {
+        const IcdCvtSeg& g = segs[i];
+        if (g.rows == 0 || g.cols == 0) continue;
+        const bool vec = (g.cols % 4 == 0) && (g.s_r % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.src) & 15) == 0) && g.ldd % 8 == 0 &&
+                         g.ldd >= g.cols && ((reinterpret_cast<uintptr_t>(g.dst) & 7) == 0);
+        if (!vec || b.n == ICD_CVT_MAX_SEGS) { ICD_TRY(icd_convert_bf16(g.src, g.s_r, 1, g.rows, g.cols, g.dst, g.ldd, s)); continue; }
+        total += (long long)g.rows * (g.cols / 4);
+        b.src[b.n] = g.src; b.dst[b.n] = reinterpret_cast<__nv_bfloat16*>(g.dst); b.s_r[b.n] = g.s_r; b.ldd[b.n] = g.ldd;
+        b.n4[b.n] = g.cols / 4; b.end[b.n] = total; ++b.n;
+    }
+    if (b.n == 0) return 0;
+    long long blocks = (total + 255) / 256;
+    if (blocks > ICD_NUM_SMS * 16) blocks = ICD_NUM_SMS * 16;
+    convert_rows_batch_kernel<<<(unsigned)blocks, 256, 0, s>>>(b);
     ICD_LAUNCH_CHECK();
     return 0;
 }
@@ -1354,6 +1399,7 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
     k.splits = pl.splits; k.kb_per_split = pl.kb_per_split; k.partial = splitk_ws;
     k.cm = mode == 2 ? 2 : cm; k.cn = mode == 2 ? 1 : cn;
     k.m_live = m_live;
+    k.late_trigger = icd_gemm_take_late_hint();
     {   // rasterisation of the work units (ICD_GEMM_RASTER=0|1 overrides): see KArgs::raster_n
         static const int raster_env = [] { const char* f = getenv("ICD_GEMM_RASTER"); return f ? atoi(f) : -1; }();
         // default: along N when the operand with the long dimension is A (>= 8 row tiles, several column tiles): the column

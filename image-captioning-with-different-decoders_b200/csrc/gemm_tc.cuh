@@ -26,6 +26,11 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
 // m_live != NULL: DEVICE-side row count — only rows < min(M, *m_live) are computed and written (tile loop bounds are
 // derived in the kernel, after its dependency wait); the plan then never splits K.
 // LSTM weight block [4D][cols] -> bf16 with the rows gate-permuted (row ug*32 + g*8 + j = source row g*D + ug*8 + j)
+// several fp32 -> bf16 row conversions in ONE launch (the weight copies at the top of a decoder step: nine launches of a few
+// microseconds each otherwise).  Segments that the 128-bit path cannot take are converted by icd_convert_bf16 instead.
+constexpr int ICD_CVT_MAX_SEGS = 12;
+struct IcdCvtSeg { const float* src; long long s_r; int rows, cols; void* dst; long long ldd; };
+int icd_convert_bf16_batch(const IcdCvtSeg* segs, int n, cudaStream_t s);
 int icd_convert_bf16_gateperm(const float* src, int64_t s_r, int D, int cols, void* dst, int64_t ldd, cudaStream_t s);
 // gates = A W^T (W gate-permuted) + xg + z_hh followed by the LSTMCell, in ONE kernel: writes gates_act / c_new / h_new /
 // dropout(h) (+ bf16 copies of h and dropout(h)); the arithmetic equals the contraction + icd_lstm_pointwise_fwd pair bit for bit
