@@ -475,6 +475,8 @@ constexpr float PROJ_W_MIN = 1e-18f;       // below this |w_full[a]| the split f
 constexpr int COLDOT_CHUNKS = 48;
 __global__ void coldot_kernel(const float* __restrict__ X, long long ldx, const float* __restrict__ Y, long long ldy,
                               long long M_all, int N, float* __restrict__ out_all) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s[32][33];
     const int n = blockIdx.x * 32 + threadIdx.x;
     const long long per = (M_all + gridDim.y - 1) / gridDim.y, m_lo = per * blockIdx.y;
@@ -504,6 +506,8 @@ __global__ void coldot_kernel(const float* __restrict__ X, long long ldx, const 
 // split (same predicate).  One CTA.
 __global__ void proj_wfull_finish_kernel(int A, const float* __restrict__ w_full, const float* __restrict__ t2,
                                          float* __restrict__ d_w_full) {
+    pdl_trigger();
+    pdl_wait();
     int bad = 0;
     for (int a4 = threadIdx.x * 4; a4 < A; a4 += blockDim.x * 4) {
         const float4 w = *reinterpret_cast<const float4*>(w_full + a4);
@@ -519,6 +523,8 @@ __global__ void att_proj_bwd_bf16_kernel(int B, int T, int P, int A, const int* 
                                          const float* __restrict__ w_full, const float* __restrict__ d_e,
                                          float* __restrict__ d_att_enc, __nv_bfloat16* __restrict__ d_att_enc16,
                                          float* __restrict__ partial, int split_wfull) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) float sm[];
     const int b = blockIdx.y, p0 = blockIdx.x * PROJ_PB;
     const int np = min(PROJ_PB, P - p0);
@@ -641,6 +647,8 @@ __global__ void att_proj_bwd_bf16_kernel(int B, int T, int P, int A, const int* 
 __global__ void __launch_bounds__(256) convert_features_kernel(int P, int C, const float* __restrict__ enc,
                                                                __nv_bfloat16* __restrict__ enc16,
                                                                float* __restrict__ mean, __nv_bfloat16* __restrict__ mean16) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float4 s_part[3 * 64];
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
@@ -681,6 +689,8 @@ __global__ void __launch_bounds__(256) convert_features_kernel(int P, int C, con
 
 struct BtPack { int v[ICD_MAX_STEPS]; };
 __global__ void row_len_from_pack_kernel16(int B, int T, const BtPack bt, int* __restrict__ row_len) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     int n = 0;
@@ -692,6 +702,8 @@ __global__ void row_len_from_pack_kernel16(int B, int T, const BtPack bt, int* _
 // grid = (ceil(C/512), B), block = 256 = 4 pixel groups x 64 lanes of 8 channels (16 B).
 __global__ void __launch_bounds__(256) feature_mean_bf16_kernel(int P, int C, const __nv_bfloat16* __restrict__ enc16,
                                                                 float* __restrict__ mean, __nv_bfloat16* __restrict__ mean16) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_part[3 * 64 * 8];
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
@@ -862,7 +874,7 @@ extern "C" int icd_attention_proj_bwd_bf16_ex(int B, int T, int P, int A, const 
     int* row_len = reinterpret_cast<int*>(partial + (int64_t)B * chunks * W);
     BtPack pack;
     for (int t = 0; t < ICD_MAX_STEPS; ++t) pack.v[t] = t < T ? bt_host[t] : 0;
-    row_len_from_pack_kernel16<<<(B + 127) / 128, 128, 0, s>>>(B, T, pack, row_len);
+    ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, row_len_from_pack_kernel16, dim3((unsigned)((B + 127) / 128)), dim3(128), (size_t)0, s, B, T, pack, row_len));
     ICD_LAUNCH_CHECK();
     // (the first 2*A floats are reused to add the two thread halves' partials: at least 2 rows of att_dec are allocated)
     const size_t smem = ((size_t)(T > 2 ? T : 2) * A + (size_t)T * PROJ_PB + 40) * sizeof(float);
@@ -874,21 +886,19 @@ extern "C" int icd_attention_proj_bwd_bf16_ex(int B, int T, int P, int A, const 
     }
     const int threads = 2 * (((A / 4 + 31) / 32) * 32);              // two halves, see the kernel
     dim3 grid(chunks, B);
-    att_proj_bwd_bf16_kernel<<<grid, threads, smem, s>>>(B, T, P, A, row_len,
-                                                          reinterpret_cast<const __nv_bfloat16*>(att_enc16),
-                                                          att_dec_all, ld_dec, w_full, d_e, d_att_enc,
-                                                          reinterpret_cast<__nv_bfloat16*>(d_att_enc16), partial,
-                                                          d_att_dec_all ? 1 : 0);
+    ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, att_proj_bwd_bf16_kernel, grid, dim3((unsigned)threads), smem, s, B, T, P, A, (const int*)row_len,
+                            reinterpret_cast<const __nv_bfloat16*>(att_enc16), att_dec_all, ld_dec, w_full, d_e, d_att_enc,
+                            reinterpret_cast<__nv_bfloat16*>(d_att_enc16), partial, d_att_dec_all ? 1 : 0));
     ICD_LAUNCH_CHECK();
     ICD_TRY(icd_colsum(partial, W, (int64_t)B * chunks, A, nullptr, d_w_full, s));
     if (d_att_dec_all) {
         float* t2 = partial + (int64_t)B * chunks * W + B + 8;       // (1 + COLDOT_CHUNKS) * A floats behind the row lengths
         float* t2_parts = t2 + A;
-        coldot_kernel<<<dim3((A + 31) / 32, COLDOT_CHUNKS), dim3(32, 32), 0, s>>>(att_dec_all, (long long)ld_dec, d_att_dec_all,
-                                                                                (long long)ld_ddec, (long long)T * B, A, t2_parts);
+        ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, coldot_kernel, dim3((A + 31) / 32, COLDOT_CHUNKS), dim3(32, 32), (size_t)0, s, att_dec_all,
+                                (long long)ld_dec, d_att_dec_all, (long long)ld_ddec, (long long)T * B, A, t2_parts));
         ICD_LAUNCH_CHECK();
         ICD_TRY(icd_colsum(t2_parts, A, COLDOT_CHUNKS, A, nullptr, t2, s));
-        proj_wfull_finish_kernel<<<1, 256, 0, s>>>(A, w_full, t2, d_w_full);
+        ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, proj_wfull_finish_kernel, dim3(1), dim3(256), (size_t)0, s, A, w_full, (const float*)t2, d_w_full));
         ICD_LAUNCH_CHECK();
     }
     if (d_b_enc) ICD_TRY(icd_colsum(partial + A, W, (int64_t)B * chunks, A, nullptr, d_b_enc, s));
@@ -899,8 +909,8 @@ extern "C" int icd_attention_proj_bwd_bf16_ex(int B, int T, int P, int A, const 
 int icd_convert_features_bf16(int B, int P, int C, const float* enc, void* enc16, float* mean, void* mean16, cudaStream_t s) {
     ICD_CHECK_ARG(C % 4 == 0 && B <= 65535, "convert_features: C=%d must be a multiple of 4, B <= 65535", C);
     dim3 grid((C + 255) / 256, B);
-    convert_features_kernel<<<grid, 256, 0, s>>>(P, C, enc, reinterpret_cast<__nv_bfloat16*>(enc16), mean,
-                                                 reinterpret_cast<__nv_bfloat16*>(mean16));
+    ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, convert_features_kernel, grid, dim3(256), (size_t)0, s, P, C, enc,
+                            reinterpret_cast<__nv_bfloat16*>(enc16), mean, reinterpret_cast<__nv_bfloat16*>(mean16)));
     ICD_LAUNCH_CHECK();
     return 0;
 }
@@ -908,8 +918,8 @@ int icd_convert_features_bf16(int B, int P, int C, const float* enc, void* enc16
 int icd_feature_mean_bf16(int B, int P, int C, const void* enc16, float* mean, void* mean16, cudaStream_t s) {
     ICD_CHECK_ARG(C % 8 == 0 && B <= 65535, "feature_mean_bf16: C=%d must be a multiple of 8, B <= 65535", C);
     dim3 grid((C + 511) / 512, B);
-    feature_mean_bf16_kernel<<<grid, 256, 0, s>>>(P, C, reinterpret_cast<const __nv_bfloat16*>(enc16), mean,
-                                                  reinterpret_cast<__nv_bfloat16*>(mean16));
+    ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, feature_mean_bf16_kernel, grid, dim3(256), (size_t)0, s, P, C,
+                            reinterpret_cast<const __nv_bfloat16*>(enc16), mean, reinterpret_cast<__nv_bfloat16*>(mean16)));
     ICD_LAUNCH_CHECK();
     return 0;
 }

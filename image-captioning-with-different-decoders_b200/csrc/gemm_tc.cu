@@ -931,6 +931,8 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // dst[r*ldd + c] = bf16(src[r*s_r + c]), r < rows, c < cols (source rows contiguous).
 __global__ void convert_rows_kernel(const float* __restrict__ src, long long s_r, int rows, int cols,
                                     __nv_bfloat16* __restrict__ dst, long long ldd, int vec) {
+    pdl_trigger();
+    pdl_wait();
     if (vec) {                                          // cols % 4 == 0, rows 16 B aligned: 128-bit loads, 64-bit stores
         const long long n4 = cols >> 2, total = (long long)rows * n4;
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -966,6 +968,8 @@ struct CvtBatch {
     int n;
 };
 __global__ void __launch_bounds__(256) convert_rows_batch_kernel(const CvtBatch b) {
+    pdl_trigger();
+    pdl_wait();
     const long long total = b.end[b.n - 1];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int g = 0;
@@ -984,6 +988,8 @@ __global__ void __launch_bounds__(256) convert_rows_batch_kernel(const CvtBatch 
 // ug*32 + g*8 + j = source row g*D + ug*8 + j, so that 32 consecutive rows hold the four gates of 8 hidden units (LstmEpi).
 __global__ void convert_rows_gateperm_kernel(const float* __restrict__ src, long long s_r, int D, int cols,
                                              __nv_bfloat16* __restrict__ dst, long long ldd) {
+    pdl_trigger();
+    pdl_wait();
     const long long n4 = cols >> 2, total = 4LL * D * n4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int rp = (int)(i / n4), c = (int)(i % n4) * 4;          // destination row
@@ -1240,7 +1246,8 @@ int icd_convert_bf16(const float* src, int64_t s_r, int64_t s_c, int rows, int c
         const long long total = vec ? (long long)rows * (cols / 4) : (long long)rows * ((cols + 1) / 2);
         long long blocks = (total + 255) / 256;
         if (blocks > ICD_NUM_SMS * 16) blocks = ICD_NUM_SMS * 16;
-        convert_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, s_r, rows, cols, d, ldd, vec);
+        ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, convert_rows_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, s, src, (long long)s_r, rows, cols,
+                                d, (long long)ldd, vec));
     } else {
         dim3 grid((rows + 31) / 32, (cols + 31) / 32);
         ICD_CHECK_ARG(grid.y <= 65535, "convert_bf16: too many columns for the transposing path");
@@ -1266,7 +1273,7 @@ int icd_convert_bf16_batch(const IcdCvtSeg* segs, int n, cudaStream_t s) {
     if (b.n == 0) return 0;
     long long blocks = (total + 255) / 256;
     if (blocks > ICD_NUM_SMS * 16) blocks = ICD_NUM_SMS * 16;
-    convert_rows_batch_kernel<<<(unsigned)blocks, 256, 0, s>>>(b);
+    ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, convert_rows_batch_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, s, b));
     ICD_LAUNCH_CHECK();
     return 0;
 }
@@ -1277,7 +1284,8 @@ int icd_convert_bf16_gateperm(const float* src, int64_t s_r, int D, int cols, vo
     const long long total = 4LL * D * (cols / 4);
     long long blocks = (total + 255) / 256;
     if (blocks > ICD_NUM_SMS * 16) blocks = ICD_NUM_SMS * 16;
-    convert_rows_gateperm_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, s_r, D, cols, reinterpret_cast<__nv_bfloat16*>(dst), ldd);
+    ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, convert_rows_gateperm_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, s, src, (long long)s_r, D, cols,
+                            reinterpret_cast<__nv_bfloat16*>(dst), (long long)ldd));
     ICD_LAUNCH_CHECK();
     return 0;
 }

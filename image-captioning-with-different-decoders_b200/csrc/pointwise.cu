@@ -169,6 +169,8 @@ __global__ void __launch_bounds__(128) lstm_pointwise_bwd_vec4_kernel(
 // out[n] = sum_m mask[m] * X[m*ld + n].  block (32,32): x -> column, y -> row phase.  deterministic.
 __global__ void colsum_kernel(const float* __restrict__ X, long long ld, long long M, int N,
                               const unsigned char* __restrict__ row_mask, float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s[32][33];
     const int n = blockIdx.x * 32 + threadIdx.x;
     float acc = 0.f;
@@ -194,6 +196,8 @@ __global__ void __launch_bounds__(128) colsum_bf16_partial_kernel(const __nv_bfl
                                                                   long long M, int N, int rows_per_chunk,
                                                                   const unsigned char* __restrict__ row_mask,
                                                                   float* __restrict__ partial, int vec) {
+    pdl_trigger();
+    pdl_wait();
     const int n = blockIdx.x * 1024 + threadIdx.x * 8;
     if (n >= N) return;
     const long long m0 = (long long)blockIdx.y * rows_per_chunk;
@@ -237,6 +241,8 @@ __global__ void __launch_bounds__(128) colsum_bf16_partial_kernel(const __nv_bfl
 template <typename TT>
 __global__ void embed_gather_kernel(const TT* __restrict__ table, const long long* __restrict__ captions,
                                     int B, int L, int T, int E, int V, float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int row = blockIdx.x;                  // row = t*B + b
     const int t = row / B, b = row % B;
     const long long tok = captions[(long long)b * L + t];
@@ -668,7 +674,8 @@ int icd_lstm_pointwise_bwd(int rows, int D, const float* dh_in, const float* d_h
 
 int icd_colsum(const float* X, int64_t ld, int64_t M, int N, const uint8_t* row_mask, float* out, cudaStream_t s) {
     if (N == 0) return 0;
-    colsum_kernel<<<(N + 31) / 32, dim3(32, 32), 0, s>>>(X, ld, M, N, row_mask, out);
+    ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, colsum_kernel, dim3((unsigned)((N + 31) / 32)), dim3(32, 32), (size_t)0, s, X, (long long)ld,
+                            (long long)M, N, (const unsigned char*)row_mask, out));
     ICD_LAUNCH_CHECK();
     return 0;
 }
@@ -688,8 +695,9 @@ int icd_colsum_bf16(const void* X16, int64_t ld, int64_t M, int N, const uint8_t
     ICD_CHECK_ARG(chunks <= 65535, "colsum_bf16: too many rows");
     const int vec = (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(X16) & 15) == 0);
     dim3 grid((N + 1023) / 1024, chunks);
-    colsum_bf16_partial_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(X16), ld, M, N, rows_per_chunk,
-                                                    row_mask, ws, vec);
+    ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, colsum_bf16_partial_kernel, grid, dim3(128), (size_t)0, s,
+                            reinterpret_cast<const __nv_bfloat16*>(X16), (long long)ld, (long long)M, N, rows_per_chunk,
+                            (const unsigned char*)row_mask, ws, vec));
     ICD_LAUNCH_CHECK();
     return icd_colsum(ws, N, chunks, N, nullptr, out, s);
 }
@@ -697,8 +705,10 @@ int icd_colsum_bf16(const void* X16, int64_t ld, int64_t M, int N, const uint8_t
 int icd_embed_gather(const void* table, int is_f64, const int64_t* captions, int B, int L, int T, int E, int V,
                      float* out, cudaStream_t s) {
     if (B * T == 0) return 0;
-    if (is_f64) embed_gather_kernel<double><<<B * T, 128, 0, s>>>((const double*)table, (const long long*)captions, B, L, T, E, V, out);
-    else        embed_gather_kernel<float><<<B * T, 128, 0, s>>>((const float*)table, (const long long*)captions, B, L, T, E, V, out);
+    if (is_f64) ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, embed_gather_kernel<double>, dim3((unsigned)(B * T)), dim3(128), (size_t)0, s,
+                                        (const double*)table, (const long long*)captions, B, L, T, E, V, out));
+    else        ICD_CUDA(icd_launch_pdl(ICD_PDL_POINTWISE, embed_gather_kernel<float>, dim3((unsigned)(B * T)), dim3(128), (size_t)0, s,
+                                        (const float*)table, (const long long*)captions, B, L, T, E, V, out));
     ICD_LAUNCH_CHECK();
     return 0;
 }
