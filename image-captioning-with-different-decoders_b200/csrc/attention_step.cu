@@ -154,8 +154,11 @@ __global__ void __launch_bounds__(256, 4) att_step_fwd_kernel(
 // order of the weighted sum) is that of att_step_fwd_kernel, so results are bit-identical to the per-row kernel.
 // smem: K*A (att_dec) + A (w_full) + K*Ppad (scores / alpha) floats.
 // ------------------------------------------------------------------------------------------------
+#ifndef ICD_ATT_GROUPED_MINB
+#define ICD_ATT_GROUPED_MINB 3
+#endif
 template <int K>
-__global__ void __launch_bounds__(256, 3) att_step_fwd_grouped_kernel(
+__global__ void __launch_bounds__(256, ICD_ATT_GROUPED_MINB) att_step_fwd_grouped_kernel(
         int k, int P, int C, int A, const int* __restrict__ k_live,
         const float* __restrict__ enc, const float* __restrict__ att_enc,
         const float* __restrict__ att_dec, long long ld_dec,
