@@ -22,6 +22,8 @@
 
 namespace {
 
+constexpr int TOPK_NL = 19;     // 64-bit loads per thread of the register-resident top-k pass: rows of up to 2 * 256 * 19 = 9728 logits
+constexpr int TOPK_CAP = 512;   // shared candidate list of that pass (logits >= tau of one row); more (massive ties): the streaming pass
 constexpr int KMAX = 8;          // beam slots per image supported by the top-k kernel
 
 struct BeamWs {
@@ -113,20 +115,55 @@ __device__ __forceinline__ bool better(float v, int i, float bv, int bi) {
     return v > bv || (v == bv && i < bi);
 }
 
+// A lower bound tau of the KT-th largest value of a row, from the 256 per-thread maxima of the CTA: the KT-th largest of those maxima
+// (KT distinct elements of the row are >= it).  Every thread returns the same value.  scratch: 8 * KT + 1 floats (8 * KT <= 64).
+template <int KT>
+__device__ __forceinline__ float block_kth_of_thread_max(float tm, float* scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float cur = tm;
+#pragma unroll
+    for (int r = 0; r < KT; ++r) {                                    // warp: its KT largest lane maxima, one knocked out per round
+        const float wm = warp_max(cur);
+        const unsigned hit = __ballot_sync(0xffffffffu, cur == wm);
+        if (lane == 0) scratch[w * KT + r] = wm;
+        if (lane == __ffs(hit) - 1) cur = -INFINITY;
+    }
+    __syncthreads();
+    if (w == 0) {                                                      // warp 0: the KT-th largest of the 8 * KT warp candidates
+        float c0 = (lane < 8 * KT) ? scratch[lane] : -INFINITY;
+        float c1 = (lane + 32 < 8 * KT) ? scratch[lane + 32] : -INFINITY;
+        float kth = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < KT; ++r) {
+            const float wm = warp_max(fmaxf(c0, c1));
+            const unsigned hit = __ballot_sync(0xffffffffu, c0 == wm || c1 == wm);
+            if (lane == __ffs(hit) - 1) { if (c0 == wm) c0 = -INFINITY; else c1 = -INFINITY; }
+            kth = wm;
+        }
+        if (lane == 0) scratch[8 * KT] = kth;
+    }
+    __syncthreads();
+    return scratch[8 * KT];
+}
+
 // One CTA per live slot.  log_softmax over V for each live row, add the running score, top-k_live over the
 // flattened candidates (ties: lower flat index first), then the beam bookkeeping of gen_captions.py:85-116.
 // State of the surviving beams goes to the *_tmp arrays (slot rows; beam_reorder_kernel moves it to the compacted slots),
 // history (parent / word / trace) and winners are written per IMAGE.
 template <int KT>      // KT >= k: length of the per-thread candidate lists (a shorter list = far fewer sorted insertions)
-__global__ void __launch_bounds__(256) beam_topk_kernel(
+__global__ void __launch_bounds__(256, 4) beam_topk_kernel(
         int k, int V, int step, int end_id, const float* __restrict__ logits,
         const float* __restrict__ score, const int* __restrict__ k_live, const int* __restrict__ slot_img,
         const int* __restrict__ n_live, const int* __restrict__ row_off,
         float* __restrict__ score_tmp, int* __restrict__ word_tmp, int* __restrict__ k_live_tmp,
         int* __restrict__ slot_img_tmp, int* __restrict__ src,
         int* __restrict__ parent_s, int* __restrict__ word_s, int* __restrict__ trace_s,
-        float* __restrict__ best_score, int* __restrict__ best_step, int* __restrict__ best_parent) {
+        float* __restrict__ best_score, int* __restrict__ best_step, int* __restrict__ best_parent, int stream_only) {
     __shared__ float s_red[40];
+    __shared__ float s_tau[8 * KT + 1];
+    __shared__ float s_candx[TOPK_CAP];
+    __shared__ int s_candi[TOPK_CAP];
+    __shared__ int s_cnt;
     __shared__ float s_cv[256 * KT];
     __shared__ int s_ci[256 * KT];
     __shared__ float s_topv[KMAX];
@@ -145,7 +182,62 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
     float tv[KT]; int ti[KT];
 #pragma unroll
     for (int j = 0; j < KT; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
+    auto flat_insert = [&](float v, int f) {                          // (v, lower flat index first) into the thread's flat top-KT
+        if (better(v, f, tv[KT - 1], ti[KT - 1])) {
+            tv[KT - 1] = v; ti[KT - 1] = f;
+#pragma unroll
+            for (int j = KT - 1; j > 0; --j) {
+                if (better(tv[j], ti[j], tv[j - 1], ti[j - 1])) {
+                    const float a = tv[j]; tv[j] = tv[j - 1]; tv[j - 1] = a;
+                    const int b2 = ti[j]; ti[j] = ti[j - 1]; ti[j - 1] = b2;
+                }
+            }
+        }
+    };
     for (int i = 0; i < nrows; ++i) {
+        if (!stream_only && even && V2 <= TOPK_NL * 256 && 8 * KT <= 64) {
+            // Rows of up to 2 * 256 * TOPK_NL logits (V = 9490): the thread's slice of the row stays in registers.  Pass A: thread
+            // maximum and sum of exp(x - maximum), five instructions per logit.  Then tau, a lower bound of the row's KT-th largest
+            // logit (block_kth_of_thread_max), and pass B puts only the logits >= tau on a shared candidate list; candidate c is
+            // valued and inserted by thread c.  (A thread sees 37 logits of a row: with per-thread sorted lists fed by every logit
+            // — the streaming pass below — SOME lane of each warp inserts on nearly every element and the whole warp walks the
+            // insertion path: 83 instructions per logit measured, the kernel was issue-bound at 190 us per step.)  Every logit that
+            // can be among the row's KT best is >= tau, so the selected candidates are those of the streaming pass.
+            const float2* x2r = reinterpret_cast<const float2*>(lg + (long long)i * V);
+            float2 a[TOPK_NL];
+#pragma unroll
+            for (int u = 0; u < TOPK_NL; ++u) {
+                const int j = threadIdx.x + u * 256;
+                a[u] = (j < V2) ? x2r[j] : make_float2(-INFINITY, -INFINITY);
+            }
+            float tm = -INFINITY, tsum = 0.f;
+#pragma unroll
+            for (int u = 0; u < TOPK_NL; ++u) tm = fmaxf(tm, fmaxf(a[u].x, a[u].y));
+            if (tm > -INFINITY) {
+#pragma unroll
+                for (int u = 0; u < TOPK_NL; ++u) tsum += __expf(a[u].x - tm) + __expf(a[u].y - tm);      // padding: exp(-inf) = 0
+            }
+            if (threadIdx.x == 0) s_cnt = 0;
+            const float tau = block_kth_of_thread_max<KT>(tm, s_tau);      // (its barriers also publish s_cnt = 0)
+#pragma unroll
+            for (int u = 0; u < TOPK_NL; ++u) {
+                const int j = threadIdx.x + u * 256;
+                if (j < V2) {
+                    if (a[u].x >= tau) { const int c = atomicAdd(&s_cnt, 1); if (c < TOPK_CAP) { s_candx[c] = a[u].x; s_candi[c] = 2 * j; } }
+                    if (a[u].y >= tau) { const int c = atomicAdd(&s_cnt, 1); if (c < TOPK_CAP) { s_candx[c] = a[u].y; s_candi[c] = 2 * j + 1; } }
+                }
+            }
+            const float rmax = block_max(tm, s_red);                        // (barriers: the candidate list is complete)
+            const float sum = block_sum((tm == -INFINITY) ? 0.f : tsum * expf(tm - rmax), s_red);
+            const int cnt = s_cnt;
+            __syncthreads();                                                // every thread has read s_cnt before the next row resets it
+            if (cnt <= TOPK_CAP) {
+                const float rlsum = logf(sum), rscore = score[row0 + i];
+                for (int c = threadIdx.x; c < cnt; c += 256) flat_insert(rscore + ((s_candx[c] - rmax) - rlsum), i * V + s_candi[c]);
+                __syncthreads();                                            // the list is free again
+                continue;
+            }
+        }
         // ONE streaming pass per row: online log-sum-exp (running max m, sum s of exp(x - m)) and, in the same pass, the
         // thread's top-KT RAW logits of the row.  log_softmax + score is monotone in the logit within a row, so the row's
         // best candidates are its largest logits; their values v = score + (x - max) - log(sum) (:74-76) are formed once the
@@ -207,18 +299,7 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(
 #pragma unroll
         for (int q = 0; q < KT; ++q) {
             if (rv[q] == 0x7fffffff) continue;
-            const float v = rscore + ((rx[q] - rmax) - rlsum);
-            const int f = f0 + rv[q];
-            if (better(v, f, tv[KT - 1], ti[KT - 1])) {
-                tv[KT - 1] = v; ti[KT - 1] = f;
-#pragma unroll
-                for (int j = KT - 1; j > 0; --j) {
-                    if (better(tv[j], ti[j], tv[j - 1], ti[j - 1])) {
-                        const float a = tv[j]; tv[j] = tv[j - 1]; tv[j - 1] = a;
-                        const int b2 = ti[j]; ti[j] = ti[j - 1]; ti[j - 1] = b2;
-                    }
-                }
-            }
+            flat_insert(rscore + ((rx[q] - rmax) - rlsum), f0 + rv[q]);
         }
     }
 #pragma unroll
@@ -520,7 +601,8 @@ extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
                                                row_off, w.score_tmp, w.word_tmp, w.k_live_tmp, w.slot_img_tmp, w.src,                   \
                                                w.parent + (size_t)(step - 1) * R, w.word + (size_t)(step - 1) * R,                      \
                                                d->trace_words ? d->trace_words + (size_t)(step - 1) * R : nullptr,                      \
-                                               w.best_score, w.best_step, w.best_parent)
+                                               w.best_score, w.best_step, w.best_parent, topk_stream_only)
+        const int topk_stream_only = getenv("ICD_BEAM_TOPK_STREAM") != nullptr;      // test hook: the streaming pass for every row
         switch (k) {
             case 1: ICD_TOPK(1); break;
             case 2: ICD_TOPK(2); break;

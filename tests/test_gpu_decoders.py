@@ -826,3 +826,43 @@ def test_lstm_gate_adjoint_vectorised_kernel_is_bit_identical_to_scalar(cuda, pr
     assert g_vec.keys() == g_sc.keys() and len(g_vec) > 8
     for k in g_vec:
         assert torch.equal(g_vec[k], g_sc[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ties", ["none", "groups", "all_equal"])
+def test_beam_topk_filtered_pass_equals_streaming_pass(cuda, ties, monkeypatch):
+    """The top-k kernel of the beam search keeps a row in registers and offers only the logits >= tau (a lower bound of the row's
+    k-th largest logit) to the candidate lists; rows it cannot take (odd V, V > 9728, more than 512 logits >= tau) go through the
+    streaming pass.  Both must select the same candidates in the same order — also under exact ties (lower flat index first,
+    gen_captions.py:78-82): "groups" gives every logit one of ~9 values (hundreds of exact ties at the top), "all_equal" makes
+    every logit of a row identical (the candidate list overflows and the row falls back to the streaming pass)."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.gen_captions import beam_search_batched
+    from icd_b200.vocabulary import synthetic_vocab
+    case = dict(H.BEAM_CASES["beam_small"], V=1000, dropout=0.5, train=False, fine_tune_embedding=True, k=5)
+    vocab = synthetic_vocab(case["V"])
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams, vocab)
+    H.apply_beam_recipe(dec, case)
+    V = case["V"]
+    with torch.no_grad():
+        if ties != "none":
+            dec.fc.weight.zero_()
+            if ties == "groups":
+                dec.fc.bias.copy_((torch.randn(V, generator=torch.Generator().manual_seed(3)) * 2).round() / 2)
+            else:
+                dec.fc.bias.fill_(0.25)
+    dec = dec.to(cuda)
+    feats = H.beam_features(case).to(cuda)
+    outs = []
+    for stream in (False, True):
+        if stream:
+            monkeypatch.setenv("ICD_BEAM_TOPK_STREAM", "1")
+        else:
+            monkeypatch.delenv("ICD_BEAM_TOPK_STREAM", raising=False)
+        with torch.no_grad():
+            outs.append(beam_search_batched(dec, feats, 5, V - 3, V - 2, max_steps=12, want_alphas=False, want_trace=True,
+                                            precision="fp32x3"))
+    monkeypatch.delenv("ICD_BEAM_TOPK_STREAM", raising=False)
+    a, b = outs
+    assert torch.equal(a["len"], b["len"]) and torch.equal(a["seq"], b["seq"]) and torch.equal(a["trace"], b["trace"])
+    assert torch.equal(a["score"], b["score"])
