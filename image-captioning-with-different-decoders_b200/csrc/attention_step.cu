@@ -17,7 +17,9 @@
 // d_att_enc is NOT read-modify-written per step: d_e is saved per step and one kernel after the time
 // loop (attention_proj_bwd) forms d_att_enc and d_w_full for all steps at once.
 #include "common.cuh"
+#include "tc_common.cuh"
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -318,6 +320,285 @@ __global__ void __launch_bounds__(256, ICD_ATT_GROUPED_MINB) att_step_fwd_groupe
                 }
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Grouped forward, RING variant (the one caption generation runs when the shapes allow): persistent CTAs, two per SM, walk
+// the live slots (slot = blockIdx.x, += gridDim.x); a single producer thread per CTA streams each image's att_enc (P x A) and
+// enc (P x C) tiles through a shared-memory ring with 1-D bulk async copies (cp.async.bulk -> mbarrier complete_tx), eight
+// consumer warps compute from shared memory.  Bytes in flight (3 x 32 KB per CTA) no longer cost registers, the producer keeps
+// fetching across the latency-bound pieces of an image (att_dec staging, softmax, epilogue) and across images, there is no
+// partial last wave of 2 MB work units, and the two CTAs of an SM drift apart so that the issue-bound score phase of one
+// overlaps the HBM-bound weighted sums of the other.  Per row the arithmetic is that of att_step_fwd_grouped_kernel in the
+// same order (lane partition q = lane, lane + 32, ... of the score dot, warp-shuffle tree, ascending pixel order of the
+// weighted sum), so alphas / gated rows are bit-identical to it (tested).
+//   ring slot = RING_ROWS1 (16) pixel rows of att_enc, or RING_ROWS2 (4) pixel rows of enc, each one contiguous copy
+//   score phase: warp w owns rows w and w + 8 of a slot => one shared-memory read of att_dec[j] / w_full feeds two pixel rows
+//   weighted sum: thread t owns channels 4t..4t+3 and 1024+4t..1024+4t+3 (C <= 2048), one slot = 4 pixels per iteration
+// smem: 3 x 32 KB ring + K*A (att_dec) + A (w_full) + K*Ppad (scores / alpha) floats + 6 mbarriers.
+// ------------------------------------------------------------------------------------------------
+#ifndef ICD_RING_SLOTS
+#define ICD_RING_SLOTS 3
+#endif
+constexpr int RING_SLOT_BYTES = 32768, RING_SLOTS = ICD_RING_SLOTS, RING_CONS_WARPS = 8, RING_ROWS1 = 16, RING_ROWS2 = 4;
+constexpr int RING_CONS = RING_CONS_WARPS * 32, RING_THREADS = RING_CONS + 32;
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ring_consumer_sync() { asm volatile("bar.sync 1, %0;" :: "n"(RING_CONS) : "memory"); }
+
+__device__ __forceinline__ void ring_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if (++spins > (1u << 24)) __trap();          // a protocol bug must fault, never hang the GPU
+    }
+}
+
+struct RingArgs {
+    int P, C, A, Pp, n1, n2;
+    const float* att_dec; long long ld_dec;
+    const float* fbeta_pre; long long ld_fb;
+    float* alpha; long long ld_alpha;
+    float* gated; unsigned short* gated_x3;
+    float bfull;
+};
+
+// One image with KL live beams (compile-time: the beam loops are fully unrolled, no per-beam branches in the inner loops —
+// the kernel is issue-bound at five beams, every instruction that is not an FADD / FMNMX / FFMA of the two sums counts).
+template <int KL>
+__device__ __forceinline__ void ring_image(const RingArgs& g, unsigned char* ring_raw, float* s_dec, float* s_wf, float* s_e,
+                                           uint32_t full0, uint32_t empty0, uint32_t& it, long long r0, long long ra) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int A = g.A, C = g.C, P = g.P, Pp = g.Pp, A4 = A >> 2;
+    for (int i = tid; i < KL * A4; i += RING_CONS) {
+        const int j = i / A4, q = i - j * A4;
+        *reinterpret_cast<float4*>(s_dec + j * A + 4 * q) = *reinterpret_cast<const float4*>(g.att_dec + (r0 + j) * g.ld_dec + 4 * q);
+    }
+    ring_consumer_sync();            // s_dec / s_wf staged; everyone has left the previous image's weighted sums (s_e is free)
+    // ---- scores: relu(att_enc + att_dec) . w_full, one ring slot (16 pixel rows) per iteration
+    for (int gi = 0; gi < g.n1; ++gi, ++it) {
+        const uint32_t s = it % RING_SLOTS;
+        ring_wait(full0 + 8 * s, (it / RING_SLOTS) & 1);
+        const int pa = gi * RING_ROWS1 + warp, pb = pa + RING_CONS_WARPS;
+        if (pa < P) {
+            const bool vb = pb < P;
+            const float* xa = reinterpret_cast<const float*>(ring_raw + (size_t)s * RING_SLOT_BYTES) + warp * A;
+            const float* xb = vb ? xa + RING_CONS_WARPS * A : xa;         // row past P: recompute row a, result dropped
+            float acc[2][KL];
+#pragma unroll
+            for (int j = 0; j < KL; ++j) acc[0][j] = acc[1][j] = 0.f;
+            for (int q = lane; q < A4; q += 32) {
+                const float4 x0 = *reinterpret_cast<const float4*>(xa + 4 * q);
+                const float4 x1 = *reinterpret_cast<const float4*>(xb + 4 * q);
+                const float4 w = *reinterpret_cast<const float4*>(s_wf + 4 * q);
+#pragma unroll
+                for (int j = 0; j < KL; ++j) {
+                    const float4 d = *reinterpret_cast<const float4*>(s_dec + j * A + 4 * q);
+                    acc[0][j] = fmaf(fmaxf(x0.x + d.x, 0.f), w.x, acc[0][j]);
+                    acc[1][j] = fmaf(fmaxf(x1.x + d.x, 0.f), w.x, acc[1][j]);
+                    acc[0][j] = fmaf(fmaxf(x0.y + d.y, 0.f), w.y, acc[0][j]);
+                    acc[1][j] = fmaf(fmaxf(x1.y + d.y, 0.f), w.y, acc[1][j]);
+                    acc[0][j] = fmaf(fmaxf(x0.z + d.z, 0.f), w.z, acc[0][j]);
+                    acc[1][j] = fmaf(fmaxf(x1.z + d.z, 0.f), w.z, acc[1][j]);
+                    acc[0][j] = fmaf(fmaxf(x0.w + d.w, 0.f), w.w, acc[0][j]);
+                    acc[1][j] = fmaf(fmaxf(x1.w + d.w, 0.f), w.w, acc[1][j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < KL; ++j) {
+                const float v0 = warp_sum(acc[0][j]);
+                const float v1 = warp_sum(acc[1][j]);
+                if (lane == 0) {
+                    s_e[j * Pp + pa] = v0 + g.bfull;
+                    if (vb) s_e[j * Pp + pb] = v1 + g.bfull;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * s);
+    }
+    ring_consumer_sync();
+    // ---- softmax over pixels: warp j handles row j (KL <= 8 warps)
+    if (warp < KL) {
+        float* e = s_e + warp * Pp;
+        float m = -INFINITY;
+        for (int p = lane; p < P; p += 32) m = fmaxf(m, e[p]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int p = lane; p < P; p += 32) { const float ex = expf(e[p] - m); e[p] = ex; sum += ex; }
+        sum = warp_sum(sum);
+        float* out = g.alpha + (ra + warp) * g.ld_alpha;
+        for (int p = lane; p < P; p += 32) { const float al = e[p] / sum; e[p] = al; out[p] = al; }
+    }
+    ring_consumer_sync();
+    // ---- weighted sums: one ring slot = 4 pixel rows of enc per iteration, thread owns channels c .. c+3 and c+1024 .. c+1027
+    const int c = tid * 4;
+    const bool act0 = c < C, act1 = c + RING_CONS * 4 < C;
+    const int c1off = act1 ? RING_CONS * 4 : 0;              // no second column: re-read the first, result dropped
+    float4 acc[2][KL];
+#pragma unroll
+    for (int j = 0; j < KL; ++j) acc[0][j] = acc[1][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < g.n2; ++i, ++it) {
+        const uint32_t s = it % RING_SLOTS;
+        ring_wait(full0 + 8 * s, (it / RING_SLOTS) & 1);
+        if (act0) {
+            const int rows = min(RING_ROWS2, P - i * RING_ROWS2);
+            const float* xs = reinterpret_cast<const float*>(ring_raw + (size_t)s * RING_SLOT_BYTES) + c;
+            if (rows == RING_ROWS2) {
+                float4 x[2][RING_ROWS2];
+#pragma unroll
+                for (int u = 0; u < RING_ROWS2; ++u) {
+                    x[0][u] = *reinterpret_cast<const float4*>(xs + (size_t)u * C);
+                    x[1][u] = *reinterpret_cast<const float4*>(xs + (size_t)u * C + c1off);
+                }
+#pragma unroll
+                for (int j = 0; j < KL; ++j) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(s_e + j * Pp + i * RING_ROWS2);
+                    const float al[RING_ROWS2] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                    for (int u = 0; u < RING_ROWS2; ++u) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            acc[h][j].x = fmaf(al[u], x[h][u].x, acc[h][j].x); acc[h][j].y = fmaf(al[u], x[h][u].y, acc[h][j].y);
+                            acc[h][j].z = fmaf(al[u], x[h][u].z, acc[h][j].z); acc[h][j].w = fmaf(al[u], x[h][u].w, acc[h][j].w);
+                        }
+                    }
+                }
+            } else {
+                for (int u = 0; u < rows; ++u) {                      // last slot of a P that is not a multiple of 4
+                    const float4 x0 = *reinterpret_cast<const float4*>(xs + (size_t)u * C);
+                    const float4 x1 = *reinterpret_cast<const float4*>(xs + (size_t)u * C + c1off);
+#pragma unroll
+                    for (int j = 0; j < KL; ++j) {
+                        const float al = s_e[j * Pp + i * RING_ROWS2 + u];
+                        acc[0][j].x = fmaf(al, x0.x, acc[0][j].x); acc[0][j].y = fmaf(al, x0.y, acc[0][j].y);
+                        acc[0][j].z = fmaf(al, x0.z, acc[0][j].z); acc[0][j].w = fmaf(al, x0.w, acc[0][j].w);
+                        acc[1][j].x = fmaf(al, x1.x, acc[1][j].x); acc[1][j].y = fmaf(al, x1.y, acc[1][j].y);
+                        acc[1][j].z = fmaf(al, x1.z, acc[1][j].z); acc[1][j].w = fmaf(al, x1.w, acc[1][j].w);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * s);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int ch = c + h * RING_CONS * 4;
+        if (ch >= C) continue;
+#pragma unroll
+        for (int j = 0; j < KL; ++j) {
+            const float4 f = *reinterpret_cast<const float4*>(g.fbeta_pre + (r0 + j) * g.ld_fb + ch);
+            const float4 gt = make_float4(sigmoidf_(f.x), sigmoidf_(f.y), sigmoidf_(f.z), sigmoidf_(f.w));
+            const float4 o = make_float4(gt.x * acc[h][j].x, gt.y * acc[h][j].y, gt.z * acc[h][j].z, gt.w * acc[h][j].w);
+            if (g.gated) *reinterpret_cast<float4*>(g.gated + (r0 + j) * C + ch) = o;
+            if (g.gated_x3) {                // 3-term bf16 split in the A-operand layout of the gate contraction (see the kernel above)
+                const float xs[4] = {o.x, o.y, o.z, o.w};
+                unsigned short t[3][4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const __nv_bfloat16 b1 = __float2bfloat16_rn(xs[q]);
+                    const float r1 = xs[q] - __bfloat162float(b1);
+                    const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
+                    const __nv_bfloat16 b3 = __float2bfloat16_rn(r1 - __bfloat162float(b2));
+                    t[0][q] = __bfloat16_as_ushort(b1); t[1][q] = __bfloat16_as_ushort(b2); t[2][q] = __bfloat16_as_ushort(b3);
+                }
+                unsigned short* dst = g.gated_x3 + (r0 + j) * 6 * (long long)C + ch;
+                const int pat[6] = {0, 0, 1, 0, 2, 1};
+#pragma unroll
+                for (int sg = 0; sg < 6; ++sg) {
+                    const unsigned short* tt = t[pat[sg]];
+                    *reinterpret_cast<uint2*>(dst + (long long)sg * C) =
+                        make_uint2((unsigned)tt[0] | ((unsigned)tt[1] << 16), (unsigned)tt[2] | ((unsigned)tt[3] << 16));
+                }
+            }
+        }
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(RING_THREADS, (K <= 5 ? 2 : 1)) att_step_fwd_grouped_ring_kernel(
+        int n_img, int k, int P, int C, int A, const int* __restrict__ k_live,
+        const float* __restrict__ enc, const float* __restrict__ att_enc,
+        const float* __restrict__ att_dec, long long ld_dec,
+        const float* __restrict__ w_full, const float* __restrict__ b_full,
+        const float* __restrict__ fbeta_pre, long long ld_fb,
+        float* __restrict__ alpha, long long ld_alpha, float* __restrict__ gated,
+        const int* __restrict__ slot_img, const int* __restrict__ n_slots, const int* __restrict__ row_off,
+        unsigned short* __restrict__ gated_x3) {
+    extern __shared__ __align__(128) unsigned char ring_raw[];
+    const int Pp = (P + 3) & ~3;
+    float* s_dec = reinterpret_cast<float*>(ring_raw + (size_t)RING_SLOTS * RING_SLOT_BYTES);   // K * A
+    float* s_wf = s_dec + K * A;                                                                  // A
+    float* s_e = s_wf + A;                                                                        // K * Pp
+    const uint32_t ring0 = smem_u32(ring_raw);
+    const uint32_t full0 = smem_u32(s_e + K * Pp), empty0 = full0 + 8 * RING_SLOTS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < RING_SLOTS; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, RING_CONS_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int nsl = n_slots ? min(n_slots[0], n_img) : n_img;
+    const int n1 = (P + RING_ROWS1 - 1) / RING_ROWS1, n2 = (P + RING_ROWS2 - 1) / RING_ROWS2;
+
+    if (warp == RING_CONS_WARPS) {
+        // ---------------------------------------------------------------- producer: one thread, runs ahead of the consumers
+        if (lane != 0) return;
+        uint32_t it = 0;
+        for (int slot = blockIdx.x; slot < nsl; slot += gridDim.x) {
+            const int kl = k_live ? min(k_live[slot], K) : min(k, K);
+            if (kl <= 0) continue;
+            const int img = slot_img ? slot_img[slot] : slot;
+            const float* ae = att_enc + (long long)img * P * A;
+            const float* eb = enc + (long long)img * P * C;
+            for (int i = 0; i < n1 + n2; ++i, ++it) {
+                const uint32_t s = it % RING_SLOTS, n = it / RING_SLOTS;
+                if (n > 0) mbar_wait_backoff(empty0 + 8 * s, (n - 1) & 1);
+                const float* src;
+                uint32_t bytes;
+                if (i < n1) {
+                    src = ae + (long long)i * RING_ROWS1 * A;
+                    bytes = (uint32_t)min(RING_ROWS1, P - i * RING_ROWS1) * (uint32_t)A * 4u;
+                } else {
+                    const int i2 = i - n1;
+                    src = eb + (long long)i2 * RING_ROWS2 * C;
+                    bytes = (uint32_t)min(RING_ROWS2, P - i2 * RING_ROWS2) * (uint32_t)C * 4u;
+                }
+                mbar_arrive_expect_tx(full0 + 8 * s, bytes);
+                bulk_g2s(ring0 + s * RING_SLOT_BYTES, src, bytes, full0 + 8 * s);
+            }
+        }
+        return;
+    }
+
+    // -------------------------------------------------------------------- consumers: 8 warps
+    RingArgs g;
+    g.P = P; g.C = C; g.A = A; g.Pp = Pp; g.n1 = n1; g.n2 = n2;
+    g.att_dec = att_dec; g.ld_dec = ld_dec; g.fbeta_pre = fbeta_pre; g.ld_fb = ld_fb;
+    g.alpha = alpha; g.ld_alpha = ld_alpha; g.gated = gated; g.gated_x3 = gated_x3;
+    g.bfull = b_full ? b_full[0] : 0.f;
+    for (int a = tid; a < A; a += RING_CONS) s_wf[a] = w_full[a];
+    uint32_t it = 0;
+    for (int slot = blockIdx.x; slot < nsl; slot += gridDim.x) {
+        const int kl = k_live ? min(k_live[slot], K) : min(k, K);
+        if (kl <= 0) continue;
+        const int img = slot_img ? slot_img[slot] : slot;
+        const long long r0 = row_off ? (long long)row_off[slot] : (long long)slot * k, ra = (long long)img * k;
+#define ICD_RING_CASE(KL) case KL: if constexpr (KL <= K) ring_image<KL>(g, ring_raw, s_dec, s_wf, s_e, full0, empty0, it, r0, ra); break
+        switch (kl) {
+            ICD_RING_CASE(1); ICD_RING_CASE(2); ICD_RING_CASE(3); ICD_RING_CASE(4);
+            ICD_RING_CASE(5); ICD_RING_CASE(6); ICD_RING_CASE(7); ICD_RING_CASE(8);
+        }
+#undef ICD_RING_CASE
     }
 }
 
@@ -753,6 +1034,31 @@ static int launch_grouped(int n_img, int k, int P, int C, int A, const int* k_li
                           const float* fbeta_pre, int64_t ld_fb, float* alpha, int64_t ld_alpha, float* gated,
                           const int* slot_img, const int* n_slots, const int* row_off, cudaStream_t s, void* gated_x3) {
     const size_t smem = ((size_t)K * A + A + (size_t)K * ((P + 3) & ~3)) * sizeof(float);
+    // ring variant (persistent CTAs, bulk-async shared-memory ring): needs one ring slot to hold 14 att_enc rows / 4 enc rows,
+    // 16-byte aligned streams, and the ring + the staged rows within the 227 KB of one SM.  ICD_BEAM_ATT_RING=0 keeps the
+    // register-staged kernel (A/B runs, equivalence test).
+    {
+        const char* ring_env = getenv("ICD_BEAM_ATT_RING");      // read per call: the equivalence test toggles it
+        const bool ring_off = ring_env && atoi(ring_env) == 0;
+        const size_t ring_smem = (size_t)RING_SLOTS * RING_SLOT_BYTES + smem + 2 * 8 * RING_SLOTS;
+        const bool aligned = ((reinterpret_cast<uintptr_t>(enc) | reinterpret_cast<uintptr_t>(att_enc) |
+                               reinterpret_cast<uintptr_t>(att_dec) | reinterpret_cast<uintptr_t>(fbeta_pre)) & 15) == 0;
+        if (!ring_off && aligned && (size_t)RING_ROWS1 * A * 4 <= RING_SLOT_BYTES && (size_t)RING_ROWS2 * C * 4 <= RING_SLOT_BYTES &&
+            C <= RING_CONS * 8 && ring_smem <= 227 * 1024) {
+            static size_t ring_configured = 0;
+            if (ring_smem > ring_configured) {
+                ICD_CUDA(cudaFuncSetAttribute(att_step_fwd_grouped_ring_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)ring_smem));
+                ring_configured = ring_smem;
+            }
+            const int per_sm = (ring_smem + 1024) * 2 <= 228 * 1024 ? 2 : 1;
+            att_step_fwd_grouped_ring_kernel<K><<<std::min(n_img, per_sm * ICD_NUM_SMS), RING_THREADS, ring_smem, s>>>(
+                n_img, k, P, C, A, k_live, enc, att_enc, att_dec, ld_dec, w_full, b_full, fbeta_pre, ld_fb, alpha, ld_alpha, gated,
+                slot_img, n_slots, row_off, reinterpret_cast<unsigned short*>(gated_x3));
+            ICD_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_fwd_grouped: K*A too large for shared memory");
     static size_t configured = 48 * 1024;
     if (smem > configured) {

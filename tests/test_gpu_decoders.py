@@ -866,3 +866,34 @@ def test_beam_topk_filtered_pass_equals_streaming_pass(cuda, ties, monkeypatch):
     a, b = outs
     assert torch.equal(a["len"], b["len"]) and torch.equal(a["seq"], b["seq"]) and torch.equal(a["trace"], b["trace"])
     assert torch.equal(a["score"], b["score"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,precision", [(1, "fp32x3"), (3, "fp32"), (5, "fp32x3"), (8, "fp32x3")])
+def test_beam_grouped_attention_ring_equals_register_staged(cuda, k, precision, monkeypatch):
+    """The attention step of caption generation runs as persistent CTAs that stream att_enc / enc through a bulk-async
+    shared-memory ring (att_step_fwd_grouped_ring_kernel); ICD_BEAM_ATT_RING=0 selects the register-staged one-CTA-per-image
+    kernel.  Same per-row arithmetic in the same order: alphas, scores and captions must agree bit for bit — with more live
+    images than SMs (every CTA walks several slots, the ring wraps across images) and while slots die and get compacted."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.gen_captions import beam_search_batched
+    from icd_b200.vocabulary import synthetic_vocab
+    case = dict(H.BEAM_CASES["beam_small"], dropout=0.5, train=False, fine_tune_embedding=True, k=k, n_img=170)
+    vocab = synthetic_vocab(case["V"])
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams, vocab)
+    H.apply_beam_recipe(dec, case)
+    V = case["V"]
+    dec = dec.to(cuda)
+    feats = H.beam_features(case).to(cuda)
+    outs = []
+    for ring in ("1", "0"):
+        monkeypatch.setenv("ICD_BEAM_ATT_RING", ring)
+        with torch.no_grad():
+            outs.append(beam_search_batched(dec, feats, k, V - 3, V - 2, max_steps=20, want_alphas=True, want_trace=True,
+                                            precision=precision))
+    monkeypatch.delenv("ICD_BEAM_ATT_RING", raising=False)
+    a, b = outs
+    assert torch.equal(a["len"], b["len"]) and torch.equal(a["seq"], b["seq"]) and torch.equal(a["trace"], b["trace"])
+    assert torch.equal(a["score"], b["score"])
+    assert torch.equal(a["alpha"], b["alpha"])
+    assert len(set(a["len"].tolist())) > 1          # captions of different lengths (0 = no beam completed): slots did die
