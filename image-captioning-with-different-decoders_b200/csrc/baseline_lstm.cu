@@ -148,6 +148,11 @@ int baseline_bwd_bf16(const icd_base_desc_t* d, cudaStream_t s) {
 }
 }  // namespace
 
+// fp32-grade tier: the split of W_hh (read by every step of the recurrence) is made once per call, kept at the tail of tc_ws
+static int64_t base_x3_cache_bytes(const icd_base_desc_t* d) {
+    return d->precision == ICD_PREC_FP32X3 ? icd_x3_split_bytes(4 * (int64_t)d->H, d->H) + 512 : 0;
+}
+
 extern "C" int64_t icd_baseline_decoder_ws_bytes(const icd_base_desc_t* d) {
     if (d && d->precision == ICD_PREC_FP32X3) {
         const int64_t B = d->B, L = d->L, E = d->E, H = d->H, V = d->V, LB = L * B;
@@ -155,7 +160,7 @@ extern "C" int64_t icd_baseline_decoder_ws_bytes(const icd_base_desc_t* d) {
                                      {4 * H, H, LB}, {4 * H, E, LB}, {LB, E, 4 * H}};
         int64_t need = 0;
         for (const auto& sh : shapes) need = std::max(need, icd_gemm_ws_bytes((int)sh[0], (int)sh[1], (int)sh[2], ICD_PREC_FP32X3));
-        return need;
+        return need + base_x3_cache_bytes(d);
     }
     if (!d || d->precision != ICD_PREC_BF16) return 0;
     Arena16 a; a.base = nullptr; a.cap = 0; a.off = 0; a.ok = true;
@@ -169,7 +174,8 @@ extern "C" int icd_baseline_decoder_fwd(const icd_base_desc_t* d, void* stream) 
     cudaStream_t s = icd_stream(stream);
     if (d->precision == ICD_PREC_BF16) return baseline_fwd_bf16(d, s);
     ICD_CHECK_ARG(d->precision == ICD_PREC_FP32 || d->precision == ICD_PREC_FP32X3, "baseline_decoder: unknown precision %d", d->precision);
-    IcdSimpleWsScope ws_scope(d->tc_ws, d->tc_ws_bytes);
+    IcdSimpleWsScope ws_scope(d->tc_ws, d->tc_ws_bytes, base_x3_cache_bytes(d));
+    icd_x3_cache_mark(d->w_hh);
     const int B = d->B, L = d->L, E = d->E, H = d->H, V = d->V, prec = d->precision;
     const size_t BH = (size_t)B * H;
     // x[0] = img_features, x[t] = embedding(captions[:, t-1])   (:93-101)
@@ -195,7 +201,8 @@ extern "C" int icd_baseline_decoder_bwd(const icd_base_desc_t* d, void* stream) 
     ICD_TRY(check(d));
     cudaStream_t s = icd_stream(stream);
     if (d->precision == ICD_PREC_BF16) return baseline_bwd_bf16(d, s);
-    IcdSimpleWsScope ws_scope(d->tc_ws, d->tc_ws_bytes);
+    IcdSimpleWsScope ws_scope(d->tc_ws, d->tc_ws_bytes, base_x3_cache_bytes(d));
+    icd_x3_cache_mark(d->w_hh);
     const int B = d->B, L = d->L, E = d->E, H = d->H, V = d->V, prec = d->precision;
     const size_t BH = (size_t)B * H;
     const int LB = L * B;

@@ -165,9 +165,26 @@ int icd_attention_step_fwd_grouped(int n_img, int k, int P, int C, int A, const 
                                    const int* row_off /* slot -> first state row, or NULL (slot*k) */, cudaStream_t s,
                                    void* gated_x3 = nullptr /* optional: 3-term bf16 split of gated, rows of 6*C (gemm_tc.cu A layout) */);
 void icd_gemm_simple_set_ws(void* ws, int64_t bytes);
+// ICD_PREC_FP32X3: the 3-term bf16 split of an operand that stays constant during one entry-point call (a weight matrix read by
+// every step of the time loop) is made ONCE and kept in a cache region at the tail of the caller's arena.  Only operands whose
+// base pointer was marked are cached (activation buffers are rewritten in place between steps); the cache dies with the scope.
+void icd_x3_cache_begin(void* mem, int64_t bytes);
+void icd_x3_cache_end();
+void icd_x3_cache_mark(const float* base);
+void* icd_x3_cache_lookup(const float* p, int64_t stride, int mn, int K, int mn_major, int seg, int which, int64_t bytes, bool* fresh);
+inline int64_t icd_x3_split_bytes(int64_t mn, int64_t K) {          // == the operand regions of icd_gemm_x3_ws_bytes
+    const int64_t b = ((mn + 7) / 8 * 8) * 6 * ((K + 7) / 8 * 8) * 2;
+    return (b + 255) / 256 * 256;
+}
 struct IcdSimpleWsScope {          // RAII: workspace for icd_gemm_simple's tensor-core tiers during one entry-point call
-    IcdSimpleWsScope(void* ws, int64_t bytes) { icd_gemm_simple_set_ws(ws, bytes); }
-    ~IcdSimpleWsScope() { icd_gemm_simple_set_ws(nullptr, 0); }
+    IcdSimpleWsScope(void* ws, int64_t bytes, int64_t cache_bytes = 0) {
+        if (cache_bytes > 0 && ws && bytes > cache_bytes) {
+            icd_gemm_simple_set_ws(ws, bytes - cache_bytes);
+            icd_x3_cache_begin(reinterpret_cast<char*>(ws) + (bytes - cache_bytes), cache_bytes);
+        } else
+            icd_gemm_simple_set_ws(ws, bytes);
+    }
+    ~IcdSimpleWsScope() { icd_gemm_simple_set_ws(nullptr, 0); icd_x3_cache_end(); }
 };
 int icd_gemm_simple(int prec, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
                     float* C, int64_t ldc, int M, int N, int K, const float* bias1, const float* bias2,

@@ -58,6 +58,15 @@ int64_t icd_att_tc_ws_bytes(const icd_att_desc_t* d);                         //
 int icd_attention_decoder_fwd_bf16(const icd_att_desc_t* d, cudaStream_t s);
 int icd_attention_decoder_bwd_bf16(const icd_att_desc_t* d, cudaStream_t s);
 
+// fp32-grade tier: the splits of the two weight matrices every step of the time loop reads ([W_dec; W_fbeta; W_hh] and
+// W_ih[:, E:], K-major in the forward loop, MN-major in the BPTT) are made once per call and kept at the tail of tc_ws
+// (they were 26 % of the tier's train step when every contraction re-split them: profiles/r02_fp32x3_split_cache.txt)
+static int64_t x3_cache_bytes(const icd_att_desc_t* d) {
+    if (d->precision != ICD_PREC_FP32X3) return 0;
+    const int64_t NZ = (int64_t)d->A + d->C + 4 * (int64_t)d->D;
+    return icd_x3_split_bytes(NZ, d->D) + icd_x3_split_bytes(4 * (int64_t)d->D, d->C) + 512;
+}
+
 extern "C" int64_t icd_attention_decoder_ws_bytes(const icd_att_desc_t* d) {
     if (!d) return 0;
     if (d->precision == ICD_PREC_BF16) return icd_att_tc_ws_bytes(d);
@@ -70,7 +79,7 @@ extern "C" int64_t icd_attention_decoder_ws_bytes(const icd_att_desc_t* d) {
         {TB, E, 4 * D}, {A, C, B * P}, {B, C, D}, {B * P, C, A}};
     int64_t need = 0;
     for (const auto& sh : shapes) need = std::max(need, icd_gemm_ws_bytes((int)sh[0], (int)sh[1], (int)sh[2], ICD_PREC_FP32X3));
-    return need;
+    return need + x3_cache_bytes(d);
 }
 
 extern "C" int icd_attention_decoder_fwd(const icd_att_desc_t* d, void* stream) {
@@ -79,7 +88,9 @@ extern "C" int icd_attention_decoder_fwd(const icd_att_desc_t* d, void* stream) 
     if (d->precision == ICD_PREC_BF16) return icd_attention_decoder_fwd_bf16(d, s);
     ICD_CHECK_ARG(d->precision == ICD_PREC_FP32 || d->precision == ICD_PREC_FP32X3, "attention_decoder: unknown precision %d", d->precision);
     ICD_CHECK_ARG(d->enc != nullptr, "attention_decoder(fp32): enc is required (bf16-stored features need ICD_PREC_BF16)");
-    IcdSimpleWsScope ws_scope(d->tc_ws, d->tc_ws_bytes);        // ICD_PREC_FP32X3: operand splits live in the caller's arena
+    IcdSimpleWsScope ws_scope(d->tc_ws, d->tc_ws_bytes, x3_cache_bytes(d));   // ICD_PREC_FP32X3: operand splits live in the caller's arena
+    icd_x3_cache_mark(d->w_cat);
+    icd_x3_cache_mark(d->w_ih + d->E);
     const int B = d->B, T = d->T, P = d->P, C = d->C, A = d->A, D = d->D, E = d->E, V = d->V;
     const int NZ = A + C + 4 * D;
     const int prec = d->precision;
@@ -156,7 +167,9 @@ extern "C" int icd_attention_decoder_bwd(const icd_att_desc_t* d, void* stream) 
     ICD_TRY(check_common(d));
     cudaStream_t s = icd_stream(stream);
     if (d->precision == ICD_PREC_BF16) return icd_attention_decoder_bwd_bf16(d, s);
-    IcdSimpleWsScope ws_scope(d->tc_ws, d->tc_ws_bytes);
+    IcdSimpleWsScope ws_scope(d->tc_ws, d->tc_ws_bytes, x3_cache_bytes(d));
+    icd_x3_cache_mark(d->w_cat);
+    icd_x3_cache_mark(d->w_ih + d->E);
     const int B = d->B, T = d->T, P = d->P, C = d->C, A = d->A, D = d->D, E = d->E, V = d->V;
     const int NZ = A + C + 4 * D;
     const int prec = d->precision;

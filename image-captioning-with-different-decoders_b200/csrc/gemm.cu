@@ -1,5 +1,6 @@
 // Dispatcher for the dense contraction entry point icd_gemm (include/icd_b200.h).
 #include "common.cuh"
+#include <stdlib.h>
 #include "gemm_tc.cuh"
 
 int icd_gemm_f32_launch(const icd_gemm_desc_t* d, cudaStream_t s);   // gemm_f32.cu
@@ -26,6 +27,46 @@ extern "C" int icd_gemm(const icd_gemm_desc_t* d, void* stream) {
 static thread_local void* g_simple_ws = nullptr;
 static thread_local int64_t g_simple_ws_bytes = 0;
 void icd_gemm_simple_set_ws(void* ws, int64_t bytes) { g_simple_ws = ws; g_simple_ws_bytes = bytes; }
+
+// ---- stationary-operand split cache of the fp32-grade tier (see common.cuh)
+namespace {
+struct X3Entry { const float* p; int64_t stride; int mn, K, mn_major, seg, which; void* dst; };
+struct X3Cache {
+    char* base = nullptr; int64_t cap = 0, used = 0;
+    const float* marked[8]; int n_marked = 0;
+    X3Entry e[16]; int n = 0;
+};
+thread_local X3Cache g_x3;
+}  // namespace
+void icd_x3_cache_begin(void* mem, int64_t bytes) {
+    g_x3 = X3Cache();
+    const char* off = getenv("ICD_X3_CACHE");                 // ICD_X3_CACHE=0: every contraction re-splits both operands (test / A-B hook)
+    if (off && atoi(off) == 0) return;
+    const uintptr_t a = (reinterpret_cast<uintptr_t>(mem) + 255) & ~uintptr_t(255);
+    g_x3.base = reinterpret_cast<char*>(a);
+    g_x3.cap = bytes - (int64_t)(a - reinterpret_cast<uintptr_t>(mem));
+}
+void icd_x3_cache_end() { g_x3 = X3Cache(); }
+void icd_x3_cache_mark(const float* base) { if (g_x3.base && g_x3.n_marked < 8) g_x3.marked[g_x3.n_marked++] = base; }
+void* icd_x3_cache_lookup(const float* p, int64_t stride, int mn, int K, int mn_major, int seg, int which, int64_t bytes, bool* fresh) {
+    *fresh = true;
+    if (!g_x3.base) return nullptr;
+    bool ok = false;
+    for (int i = 0; i < g_x3.n_marked; ++i) ok |= (g_x3.marked[i] == p);
+    if (!ok) return nullptr;
+    for (int i = 0; i < g_x3.n; ++i) {
+        const X3Entry& x = g_x3.e[i];
+        if (x.p == p && x.stride == stride && x.mn == mn && x.K == K && x.mn_major == mn_major && x.seg == seg && x.which == which) {
+            *fresh = false;
+            return x.dst;
+        }
+    }
+    if (g_x3.n >= 16 || g_x3.used + bytes > g_x3.cap) return nullptr;
+    void* dst = g_x3.base + g_x3.used;
+    g_x3.used += bytes;
+    g_x3.e[g_x3.n++] = X3Entry{p, stride, mn, K, mn_major, seg, which, dst};
+    return dst;
+}
 
 int icd_gemm_simple(int prec, const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbn, int64_t sbk,
                     float* C, int64_t ldc, int M, int N, int K, const float* bias1, const float* bias2,

@@ -897,3 +897,49 @@ def test_beam_grouped_attention_ring_equals_register_staged(cuda, k, precision, 
     assert torch.equal(a["score"], b["score"])
     assert torch.equal(a["alpha"], b["alpha"])
     assert len(set(a["len"].tolist())) > 1          # captions of different lengths (0 = no beam completed): slots did die
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["attention", "baseline"])
+def test_fp32x3_stationary_weight_split_cache_is_bit_identical(cuda, which, monkeypatch):
+    """fp32-grade tensor-core tier: the 3-term bf16 splits of the weights every step of the time loop reads ([W_dec; W_fbeta; W_hh],
+    W_ih[:, E:], the baseline decoder's W_hh) are made once per forward / backward call and reused by the following steps
+    (ICD_X3_CACHE=0: every contraction re-splits its operands, the round-1 behaviour).  Same split values, same contraction:
+    outputs and gradients must agree bit for bit — ragged lengths, so the row count of the contractions changes between steps."""
+    import icd_b200.models.attention as my_att
+    import icd_b200.models.baseline as my_base
+    from icd_b200.vocabulary import synthetic_vocab
+    if which == "attention":
+        case = dict(B=21, V=97, A=64, D=64, E=32, max_len=9, lengths=[9] * 6 + [7] * 5 + [4] * 10, wseed=6, iseed=41,
+                    dropout=0.5, train=False, fine_tune_embedding=True)
+        dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams, synthetic_vocab(case["V"]))
+        enc = synthetic_features(case["B"], case["iseed"]).to(cuda)
+    else:
+        case = dict(H.BASE_CASES["base_small"])
+        dec = H.build_baseline_module(case, my_base.BaselineDecoder, my_base.BaselineDecoderParams)
+        enc = None
+    dec = dec.to(cuda)
+    dec.eval()
+    dec.precision = "fp32x3"
+
+    def run():
+        dec.zero_grad()
+        if which == "attention":
+            caps, lens = synthetic_caps(case)
+            preds, _, dl, alphas = dec(enc, caps.to(cuda), lens)
+            O.attention_loss(preds, caps.to(cuda), dl, alphas).backward()
+        else:
+            img, caps, lens = H.base_inputs(case)
+            preds = dec(img.to(cuda), caps.to(cuda))
+            O.baseline_loss(preds, caps.to(cuda)).backward()
+        return preds.detach().clone(), {k: p.grad.clone() for k, p in dec.named_parameters() if p.grad is not None}
+
+    monkeypatch.delenv("ICD_X3_CACHE", raising=False)
+    p1, g1 = run()
+    monkeypatch.setenv("ICD_X3_CACHE", "0")
+    p0, g0 = run()
+    monkeypatch.delenv("ICD_X3_CACHE", raising=False)
+    assert torch.equal(p1, p0)
+    assert g1.keys() == g0.keys() and len(g1) >= 4
+    for k in g1:
+        assert torch.equal(g1[k], g0[k]), k
