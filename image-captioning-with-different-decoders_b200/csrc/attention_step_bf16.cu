@@ -517,6 +517,15 @@ __global__ void proj_wfull_finish_kernel(int A, const float* __restrict__ w_full
     for (int a = threadIdx.x; a < A; a += blockDim.x) d_w_full[a] += t2[a] / w_full[a];
 }
 
+// 1.0f where a > b, else 0.0f, as ONE instruction (FSET.BF): with the FFMA that consumes it the masked accumulation
+// `acc += (a > b) ? v : 0` is two instructions, one per pipe (ALU + FMA) — FSETP + FSEL + FADD puts two of three on the
+// half-rate ALU pipe.  fma(1, v, acc) and fma(0, v, acc) round exactly like acc + v and acc (v finite).
+__device__ __forceinline__ float gt_mask(float a, float b) {
+    float m;
+    asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(m) : "f"(a), "f"(b));
+    return m;
+}
+
 __global__ void att_proj_bwd_bf16_kernel(int B, int T, int P, int A, const int* __restrict__ row_len,
                                          const __nv_bfloat16* __restrict__ att_enc,
                                          const float* __restrict__ att_dec_all, long long ld_dec,
@@ -590,7 +599,7 @@ __global__ void att_proj_bwd_bf16_kernel(int B, int T, int P, int A, const int* 
                     for (int u = 0; u < 4; ++u)
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            acc[u][i] += (x[u][i] > nd[i]) ? de[u] : 0.f;       // x + att_dec > 0  <=>  x > -att_dec (exactly, in fp32)
+                            acc[u][i] = fmaf(gt_mask(x[u][i], nd[i]), de[u], acc[u][i]);   // x + att_dec > 0  <=>  x > -att_dec (exactly, in fp32)
                 }
                 float wl[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
