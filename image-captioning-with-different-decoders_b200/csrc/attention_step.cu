@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(RING_THREADS, (K <= 5 ? 2 : 1)) att_step_fwd_g
         const float* __restrict__ fbeta_pre, long long ld_fb,
         float* __restrict__ alpha, long long ld_alpha, float* __restrict__ gated,
         const int* __restrict__ slot_img, const int* __restrict__ n_slots, const int* __restrict__ row_off,
-        unsigned short* __restrict__ gated_x3) {
+        unsigned short* __restrict__ gated_x3, int* __restrict__ ticket, int stagger_ns_per_beam) {
     extern __shared__ __align__(128) unsigned char ring_raw[];
     const int Pp = (P + 3) & ~3;
     float* s_dec = reinterpret_cast<float*>(ring_raw + (size_t)RING_SLOTS * RING_SLOT_BYTES);   // K * A
@@ -541,6 +541,7 @@ __global__ void __launch_bounds__(RING_THREADS, (K <= 5 ? 2 : 1)) att_step_fwd_g
     float* s_e = s_wf + A;                                                                        // K * Pp
     const uint32_t ring0 = smem_u32(ring_raw);
     const uint32_t full0 = smem_u32(s_e + K * Pp), empty0 = full0 + 8 * RING_SLOTS;
+    volatile int* s_slot = reinterpret_cast<volatile int*>(s_e + K * Pp) + 4 * RING_SLOTS;   // RING_SLOTS ints behind the 2 * RING_SLOTS mbarriers
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int i = 0; i < RING_SLOTS; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, RING_CONS_WARPS); }
@@ -552,17 +553,30 @@ __global__ void __launch_bounds__(RING_THREADS, (K <= 5 ? 2 : 1)) att_step_fwd_g
 
     if (warp == RING_CONS_WARPS) {
         // ---------------------------------------------------------------- producer: one thread, runs ahead of the consumers
+        // Work distribution: with a ticket counter the CTAs draw their slots dynamically (no tail of uneven image counts, and
+        // the late start of the second CTA per SM costs nothing); the slot id travels to the consumers in s_slot[ring stage of the image's first tile],
+        // published before the arrive on the image's first ring stage.  -1 = no more work (a stage without bytes).
         if (lane != 0) return;
         uint32_t it = 0;
-        for (int slot = blockIdx.x; slot < nsl; slot += gridDim.x) {
-            const int kl = k_live ? min(k_live[slot], K) : min(k, K);
-            if (kl <= 0) continue;
+        for (int n_done = 0;; ++n_done) {
+            const int slot = ticket ? atomicAdd(ticket, 1) : (int)blockIdx.x + n_done * (int)gridDim.x;
+            const uint32_t s0 = it % RING_SLOTS, n0 = it / RING_SLOTS;
+            if (n0 > 0) mbar_wait_backoff(empty0 + 8 * s0, (n0 - 1) & 1);
+            const bool valid = slot < nsl;
+            const int kl = !valid ? 0 : (k_live ? min(k_live[slot], K) : min(k, K));
+            s_slot[s0] = valid ? slot : -1;
+            if (kl <= 0) {                                            // end of work, or a slot without live beams: an empty stage
+                mbar_arrive(full0 + 8 * s0);
+                ++it;
+                if (!valid) break;
+                continue;
+            }
             const int img = slot_img ? slot_img[slot] : slot;
             const float* ae = att_enc + (long long)img * P * A;
             const float* eb = enc + (long long)img * P * C;
             for (int i = 0; i < n1 + n2; ++i, ++it) {
                 const uint32_t s = it % RING_SLOTS, n = it / RING_SLOTS;
-                if (n > 0) mbar_wait_backoff(empty0 + 8 * s, (n - 1) & 1);
+                if (i > 0 && n > 0) mbar_wait_backoff(empty0 + 8 * s, (n - 1) & 1);
                 const float* src;
                 uint32_t bytes;
                 if (i < n1) {
@@ -588,9 +602,27 @@ __global__ void __launch_bounds__(RING_THREADS, (K <= 5 ? 2 : 1)) att_step_fwd_g
     g.bfull = b_full ? b_full[0] : 0.f;
     for (int a = tid; a < A; a += RING_CONS) s_wf[a] = w_full[a];
     uint32_t it = 0;
-    for (int slot = blockIdx.x; slot < nsl; slot += gridDim.x) {
+    for (int n_done = 0;; ++n_done) {
+        const uint32_t s0 = it % RING_SLOTS;
+        ring_wait(full0 + 8 * s0, (it / RING_SLOTS) & 1);             // the image's first stage (or an empty stage): s_slot is valid
+        const int slot = s_slot[s0];          // read before this stage is released: the producer cannot overwrite it
+        if (slot < 0) break;
         const int kl = k_live ? min(k_live[slot], K) : min(k, K);
-        if (kl <= 0) continue;
+        if (kl <= 0) {                                                // empty stage of a slot without live beams
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * s0);
+            ++it;
+            continue;
+        }
+        // Every image costs the same, so all CTAs would walk through the issue-bound score phase and the HBM-bound weighted
+        // sums in lockstep (HBM idle, then oversubscribed).  The second CTA of every SM starts its first image half an image
+        // late: the two halves of the grid then run in anti-phase.  Free with the ticket counter (late CTAs draw fewer slots).
+        if (n_done == 0 && stagger_ns_per_beam > 0 && blockIdx.x >= ICD_NUM_SMS && 2 * kl > K) {      // few live beams: HBM-bound in both phases
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            const unsigned long long wait_ns = (unsigned long long)stagger_ns_per_beam * (unsigned)kl;
+            do { __nanosleep(256); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < wait_ns);
+        }
         const int img = slot_img ? slot_img[slot] : slot;
         const long long r0 = row_off ? (long long)row_off[slot] : (long long)slot * k, ra = (long long)img * k;
 #define ICD_RING_CASE(KL) case KL: if constexpr (KL <= K) ring_image<KL>(g, ring_raw, s_dec, s_wf, s_e, full0, empty0, it, r0, ra); break
@@ -1032,7 +1064,7 @@ template <int K>
 static int launch_grouped(int n_img, int k, int P, int C, int A, const int* k_live, const float* enc, const float* att_enc,
                           const float* att_dec, int64_t ld_dec, const float* w_full, const float* b_full,
                           const float* fbeta_pre, int64_t ld_fb, float* alpha, int64_t ld_alpha, float* gated,
-                          const int* slot_img, const int* n_slots, const int* row_off, cudaStream_t s, void* gated_x3) {
+                          const int* slot_img, const int* n_slots, const int* row_off, cudaStream_t s, void* gated_x3, int* ticket) {
     const size_t smem = ((size_t)K * A + A + (size_t)K * ((P + 3) & ~3)) * sizeof(float);
     // ring variant (persistent CTAs, bulk-async shared-memory ring): needs one ring slot to hold 14 att_enc rows / 4 enc rows,
     // 16-byte aligned streams, and the ring + the staged rows within the 227 KB of one SM.  ICD_BEAM_ATT_RING=0 keeps the
@@ -1040,7 +1072,7 @@ static int launch_grouped(int n_img, int k, int P, int C, int A, const int* k_li
     {
         const char* ring_env = getenv("ICD_BEAM_ATT_RING");      // read per call: the equivalence test toggles it
         const bool ring_off = ring_env && atoi(ring_env) == 0;
-        const size_t ring_smem = (size_t)RING_SLOTS * RING_SLOT_BYTES + smem + 2 * 8 * RING_SLOTS;
+        const size_t ring_smem = (size_t)RING_SLOTS * RING_SLOT_BYTES + smem + 2 * 8 * RING_SLOTS + 16;
         const bool aligned = ((reinterpret_cast<uintptr_t>(enc) | reinterpret_cast<uintptr_t>(att_enc) |
                                reinterpret_cast<uintptr_t>(att_dec) | reinterpret_cast<uintptr_t>(fbeta_pre)) & 15) == 0;
         if (!ring_off && aligned && (size_t)RING_ROWS1 * A * 4 <= RING_SLOT_BYTES && (size_t)RING_ROWS2 * C * 4 <= RING_SLOT_BYTES &&
@@ -1052,9 +1084,12 @@ static int launch_grouped(int n_img, int k, int P, int C, int A, const int* k_li
                 ring_configured = ring_smem;
             }
             const int per_sm = (ring_smem + 1024) * 2 <= 228 * 1024 ? 2 : 1;
+            // anti-phase start of the second CTA per SM: only with dynamic slot tickets (else the late CTAs would finish late)
+            const char* stag_env = getenv("ICD_RING_STAGGER_NS");
+            const int stagger = (ticket && per_sm == 2 && n_img > ICD_NUM_SMS && k > 1) ? (stag_env ? atoi(stag_env) : 10000) : 0;
             att_step_fwd_grouped_ring_kernel<K><<<std::min(n_img, per_sm * ICD_NUM_SMS), RING_THREADS, ring_smem, s>>>(
                 n_img, k, P, C, A, k_live, enc, att_enc, att_dec, ld_dec, w_full, b_full, fbeta_pre, ld_fb, alpha, ld_alpha, gated,
-                slot_img, n_slots, row_off, reinterpret_cast<unsigned short*>(gated_x3));
+                slot_img, n_slots, row_off, reinterpret_cast<unsigned short*>(gated_x3), ticket, stagger);
             ICD_LAUNCH_CHECK();
             return 0;
         }
@@ -1076,13 +1111,13 @@ int icd_attention_step_fwd_grouped(int n_img, int k, int P, int C, int A, const 
                                    const float* att_enc, const float* att_dec, int64_t ld_dec, const float* w_full,
                                    const float* b_full, const float* fbeta_pre, int64_t ld_fb, float* alpha,
                                    int64_t ld_alpha, float* gated, const int* slot_img, const int* n_slots, const int* row_off,
-                                   cudaStream_t s, void* gated_x3) {
+                                   cudaStream_t s, void* gated_x3, int* ticket) {
     if (n_img == 0) return 0;
     ICD_CHECK_ARG(!gated_x3 || C % 8 == 0, "attention_step_fwd_grouped: the fused 3-term split needs C % 8 == 0");
     ICD_CHECK_ARG(k >= 1 && k <= 8, "attention_step_fwd_grouped: k=%d (1..8)", k);
     ICD_CHECK_ARG(A % 4 == 0 && C % 4 == 0 && ld_dec % 4 == 0 && ld_fb % 4 == 0, "attention_step_fwd_grouped: misaligned dims");
 #define ICD_GROUPED(KK) return launch_grouped<KK>(n_img, k, P, C, A, k_live, enc, att_enc, att_dec, ld_dec, w_full, b_full, \
-                                                  fbeta_pre, ld_fb, alpha, ld_alpha, gated, slot_img, n_slots, row_off, s, gated_x3)
+                                                  fbeta_pre, ld_fb, alpha, ld_alpha, gated, slot_img, n_slots, row_off, s, gated_x3, ticket)
     switch (k) {
         case 1: ICD_GROUPED(1);
         case 2: ICD_GROUPED(2);

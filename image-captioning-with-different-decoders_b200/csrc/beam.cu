@@ -31,6 +31,7 @@ struct BeamWs {
           *gates_act_unused, *logits, *alpha_steps, *score, *best_score, *embg;
     int *img_index, *prev_word, *k_live, *src, *parent, *word, *best_step, *best_parent;
     int *slot_img, *slot_img_tmp, *k_live_tmp, *new_slot, *n_live, *word_tmp;   // n_live[0] = live slots, [1] = live rows
+    int* ring_ticket;                                                           // one slot-ticket counter per step (attention ring kernel)
     int *row_off[2];                                                            // slot -> first state row (ping-pong per step)
     float* score_tmp;
     long long* tok64;
@@ -66,7 +67,7 @@ size_t carve(const icd_beam_desc_t* d, BeamWs* w, char* base) {
     TAKE_I(img_index, R) TAKE_I(prev_word, R) TAKE_I(k_live, (size_t)d->n_img) TAKE_I(src, R)
     TAKE_I(parent, S * R) TAKE_I(word, S * R) TAKE_I(best_step, (size_t)d->n_img) TAKE_I(best_parent, (size_t)d->n_img)
     TAKE_I(slot_img, (size_t)d->n_img) TAKE_I(slot_img_tmp, (size_t)d->n_img) TAKE_I(k_live_tmp, (size_t)d->n_img)
-    TAKE_I(new_slot, (size_t)d->n_img) TAKE_I(n_live, 4) TAKE_I(word_tmp, R)
+    TAKE_I(new_slot, (size_t)d->n_img) TAKE_I(n_live, 4) TAKE_I(word_tmp, R) TAKE_I(ring_ticket, S + 2)
     ip = (int*)take(sizeof(int) * (size_t)d->n_img); if (w) w->row_off[0] = ip;
     ip = (int*)take(sizeof(int) * (size_t)d->n_img); if (w) w->row_off[1] = ip;
 #undef TAKE_I
@@ -568,6 +569,7 @@ extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
     // candidate words of images that are already finished at a step stay -1 (:91 prints nothing for them)
     if (d->trace_words) ICD_CUDA(cudaMemsetAsync(d->trace_words, 0xff, sizeof(int32_t) * (size_t)S1 * R, s));
     const int* live_rows = w.n_live + 1;
+    ICD_CUDA(cudaMemsetAsync(w.ring_ticket, 0, sizeof(int) * (size_t)(S1 + 2), s));
     for (int step = 1; step <= S1; ++step) {
         float* alpha_s = w.alpha_steps + (size_t)(step - 1) * R * P;
         const int* row_off = w.row_off[(step - 1) & 1];
@@ -585,7 +587,7 @@ extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
         const bool fused_split = prec == ICD_PREC_FP32X3 && use_embg && (C % 8 == 0);
         ICD_TRY(icd_attention_step_fwd_grouped(n_img, k, P, C, A, w.k_live, d->enc, w.att_enc, w.z, NZ, d->full_att_w,
                                                d->full_att_b, w.z + A, NZ, alpha_s, P, fused_split ? nullptr : w.gated, w.slot_img,
-                                               w.n_live, row_off, s, fused_split ? w.x3_act : nullptr));
+                                               w.n_live, row_off, s, fused_split ? w.x3_act : nullptr, w.ring_ticket + step));
         if (use_embg) {
             beam_gates_init_kernel<<<(unsigned)R, 128, 0, s>>>(w.embg, w.tok64, 4 * D, w.z + A + C, NZ, w.gates_pre, w.n_live);
             ICD_LAUNCH_CHECK();
