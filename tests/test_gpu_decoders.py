@@ -874,11 +874,12 @@ def test_beam_grouped_attention_ring_equals_register_staged(cuda, k, precision, 
     """The attention step of caption generation runs as persistent CTAs that stream att_enc / enc through a bulk-async
     shared-memory ring (att_step_fwd_grouped_ring_kernel); ICD_BEAM_ATT_RING=0 selects the register-staged one-CTA-per-image
     kernel.  Same per-row arithmetic in the same order: alphas, scores and captions must agree bit for bit — with more live
-    images than SMs (every CTA walks several slots, the ring wraps across images) and while slots die and get compacted."""
+    images than resident CTAs (every CTA draws several slot tickets, the ring wraps across images) and while slots die and get
+    compacted."""
     import icd_b200.models.attention as my_att
     from icd_b200.gen_captions import beam_search_batched
     from icd_b200.vocabulary import synthetic_vocab
-    case = dict(H.BEAM_CASES["beam_small"], dropout=0.5, train=False, fine_tune_embedding=True, k=k, n_img=170)
+    case = dict(H.BEAM_CASES["beam_small"], dropout=0.5, train=False, fine_tune_embedding=True, k=k, n_img=330)   # > 2 CTAs x 148 SMs
     vocab = synthetic_vocab(case["V"])
     dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams, vocab)
     H.apply_beam_recipe(dec, case)
