@@ -41,7 +41,21 @@ struct BeamWs {
 };
 
 inline long long up8ll(long long x) { return (x + 7) / 8 * 8; }
-constexpr int X3_IMG_CHUNK = 64;          // images per enc_att projection pass (bounds the split activation scratch)
+constexpr int X3_IMG_CHUNK = 64;          // most images per enc_att projection pass (bounds the split activation scratch)
+// Images per pass: the projection runs as 256 x 256 super tiles on 74 CTA pairs, so a pass costs ceil(super tiles / 74) rounds whatever
+// its row count.  64 images x 196 pixels are 98 super tiles = 2 rounds for 1.3 rounds of work; 48 images are 74 = exactly one.
+// Pick the count (<= X3_IMG_CHUNK) with the most images per round.
+inline int x3_img_chunk(int P, int A) {
+    int best = X3_IMG_CHUNK;
+    double best_score = 0.0;
+    for (int ni = X3_IMG_CHUNK; ni >= 8; --ni) {
+        const long long tiles_m = ((long long)ni * P + 127) / 128, st = ((tiles_m + 1) / 2) * ((A + 255) / 256);
+        const long long rounds = (st + ICD_NUM_SMS / 2 - 1) / (ICD_NUM_SMS / 2);
+        const double score = (double)ni / (double)rounds;
+        if (score > best_score * 1.0001) { best_score = score; best = ni; }
+    }
+    return best;
+}
 
 size_t carve(const icd_beam_desc_t* d, BeamWs* w, char* base) {
     const size_t R = (size_t)d->n_img * d->k, S = (size_t)d->max_steps + 1;
@@ -549,8 +563,9 @@ extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
                             w.embg + (size_t)v0 * 4 * D, 4 * D, 4 * D, d->b_ih, nullptr, 0, 0.f, s));
         }
     }
-    for (int i0 = 0; i0 < n_img; i0 += X3_IMG_CHUNK) {       // att_enc = enc_att(enc), once per image
-        const int ni = n_img - i0 < X3_IMG_CHUNK ? n_img - i0 : X3_IMG_CHUNK;
+    const int img_chunk = prec == ICD_PREC_FP32X3 ? x3_img_chunk(P, A) : X3_IMG_CHUNK;
+    for (int i0 = 0; i0 < n_img; i0 += img_chunk) {          // att_enc = enc_att(enc), once per image
+        const int ni = n_img - i0 < img_chunk ? n_img - i0 : img_chunk;
         ICD_TRY(beam_mm(prec, w, d->enc + (size_t)i0 * P * C, C, ni * P, C, d->enc_att_w, C, w.x3_We,
                         w.att_enc + (size_t)i0 * P * A, A, A, d->enc_att_b, nullptr, 0, 0.f, s));
     }
