@@ -19,6 +19,8 @@
 // the first completed beam with the maximal score (:127); the loop body runs for step = 1..max_steps+1 (:119).
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -495,6 +497,64 @@ __global__ void beam_gates_init_kernel(const float* __restrict__ embg, const lon
     }
 }
 
+// fp32-grade tier, once per call: ONE pass over a chunk of feature maps writes the 3-term bf16 split of every pixel row (the A
+// operand of the enc_att projection, layout [a1 | a1 | a2 | a1 | a3 | a2] along K with segment length C, gemm_tc.cu) AND the pixel
+// mean of init_hidden_state (gen_captions.py:62 -> models/attention.py:161) — the features are read once instead of twice.
+// grid = (ceil(C/256), images), block = 256 = 4 pixel groups x 64 float4 lanes; the mean is summed exactly like
+// weighted_pixel_sum_kernel (pixels p = g, g+4, ... per group, then g0 + g1 + g2 + g3, then / P): bit-identical to it.
+__global__ void __launch_bounds__(256) split3_mean_kernel(int P, int C, const float* __restrict__ enc,
+                                                          unsigned short* __restrict__ x3, float* __restrict__ mean) {
+    __shared__ float4 s_part[3 * 64];
+    const int img = blockIdx.y;
+    const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int c = blockIdx.x * 256 + lane * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) {
+        const float* base = enc + (long long)img * P * C + c;
+        unsigned short* ob = x3 + (long long)img * P * 6 * C + c;
+        const int pat[6] = {0, 0, 1, 0, 2, 1};
+        for (int p0 = grp; p0 < P; p0 += 16) {
+            float4 x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                x[u] = (p0 + 4 * u < P) ? ld_stream_f4(base + (long long)(p0 + 4 * u) * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int p = p0 + 4 * u;
+                if (p >= P) break;
+                acc.x = fmaf(1.f, x[u].x, acc.x); acc.y = fmaf(1.f, x[u].y, acc.y);
+                acc.z = fmaf(1.f, x[u].z, acc.z); acc.w = fmaf(1.f, x[u].w, acc.w);
+                const float xs[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+                unsigned short t[3][4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const __nv_bfloat16 b1 = __float2bfloat16_rn(xs[q]);
+                    const float r1 = xs[q] - __bfloat162float(b1);
+                    const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
+                    const __nv_bfloat16 b3 = __float2bfloat16_rn(r1 - __bfloat162float(b2));
+                    t[0][q] = __bfloat16_as_ushort(b1); t[1][q] = __bfloat16_as_ushort(b2); t[2][q] = __bfloat16_as_ushort(b3);
+                }
+                unsigned short* dst = ob + (long long)p * 6 * C;
+#pragma unroll
+                for (int sg = 0; sg < 6; ++sg) {
+                    const unsigned short* tt = t[pat[sg]];
+                    *reinterpret_cast<uint2*>(dst + (long long)sg * C) =
+                        make_uint2((unsigned)tt[0] | ((unsigned)tt[1] << 16), (unsigned)tt[2] | ((unsigned)tt[3] << 16));
+                }
+            }
+        }
+    }
+    if (grp > 0) s_part[(grp - 1) * 64 + lane] = acc;
+    __syncthreads();
+    if (grp == 0 && c < C) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) { const float4 o = s_part[g * 64 + lane]; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+        const float inv = (float)P;
+        acc.x /= inv; acc.y /= inv; acc.z /= inv; acc.w /= inv;
+        *reinterpret_cast<float4*>(mean + (long long)img * C + c) = acc;
+    }
+}
+
 }  // namespace
 
 // y[rows, N] = x[rows, K] * W[N, K]^T (+ bias + add + beta*y): fp32 FMA kernel, or the fp32-grade tensor-core tier with the
@@ -564,13 +624,21 @@ extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
         }
     }
     const int img_chunk = prec == ICD_PREC_FP32X3 ? x3_img_chunk(P, A) : X3_IMG_CHUNK;
+    const bool fused_mean = prec == ICD_PREC_FP32X3 && C % 8 == 0 && (reinterpret_cast<uintptr_t>(d->enc) & 15) == 0 &&
+                            getenv("ICD_BEAM_FUSED_MEAN_OFF") == nullptr;
     for (int i0 = 0; i0 < n_img; i0 += img_chunk) {          // att_enc = enc_att(enc), once per image
         const int ni = n_img - i0 < img_chunk ? n_img - i0 : img_chunk;
+        if (fused_mean) {                 // split of the chunk's pixel rows + the pixel mean of its images in one pass over the features
+            split3_mean_kernel<<<dim3((unsigned)((C + 255) / 256), (unsigned)ni), 256, 0, s>>>(
+                P, C, d->enc + (size_t)i0 * P * C, reinterpret_cast<unsigned short*>(w.x3_act), w.mean + (size_t)i0 * C);
+            ICD_LAUNCH_CHECK();
+        }
         ICD_TRY(beam_mm(prec, w, d->enc + (size_t)i0 * P * C, C, ni * P, C, d->enc_att_w, C, w.x3_We,
-                        w.att_enc + (size_t)i0 * P * A, A, A, d->enc_att_b, nullptr, 0, 0.f, s));
+                        w.att_enc + (size_t)i0 * P * A, A, A, d->enc_att_b, nullptr, 0, 0.f, s, nullptr, fused_mean));
     }
     // initial state (:62): pixel mean, h_lin, c_lin
-    ICD_TRY(icd_weighted_pixel_sum(n_img, P, C, nullptr, d->enc, nullptr, 0, nullptr, 0, w.mean, nullptr, nullptr, s));
+    if (!fused_mean)
+        ICD_TRY(icd_weighted_pixel_sum(n_img, P, C, nullptr, d->enc, nullptr, 0, nullptr, 0, w.mean, nullptr, nullptr, s));
     ICD_TRY(beam_mm(prec, w, w.mean, C, n_img, C, d->h_lin_w, C, w.x3_Wh, w.h0, D, D, d->h_lin_b, nullptr, 0, 0.f, s));
     ICD_TRY(beam_mm(prec, w, w.mean, C, n_img, C, d->c_lin_w, C, w.x3_Wc, w.c0, D, D, d->c_lin_b, nullptr, 0, 0.f, s));
     {

@@ -944,3 +944,32 @@ def test_fp32x3_stationary_weight_split_cache_is_bit_identical(cuda, which, monk
     assert g1.keys() == g0.keys() and len(g1) >= 4
     for k in g1:
         assert torch.equal(g1[k], g0[k]), k
+
+
+@pytest.mark.gpu
+def test_beam_prologue_fused_split_and_pixel_mean_is_bit_identical(cuda, monkeypatch):
+    """fp32-grade caption generation reads the features once in its prologue: one kernel writes the 3-term bf16 split of the
+    pixel rows (A operand of the enc_att projection) and the pixel mean of init_hidden_state (gen_captions.py:62).
+    ICD_BEAM_FUSED_MEAN_OFF=1 restores the two separate passes; the mean is summed in the same order, so every output must
+    agree bit for bit (70 images: the projection runs in two passes of different size)."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.gen_captions import beam_search_batched
+    from icd_b200.vocabulary import synthetic_vocab
+    case = dict(H.BEAM_CASES["beam_small"], dropout=0.5, train=False, fine_tune_embedding=True, k=3, n_img=70)
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams, synthetic_vocab(case["V"]))
+    H.apply_beam_recipe(dec, case)
+    dec = dec.to(cuda)
+    V = case["V"]
+    feats = H.beam_features(case).to(cuda)
+    outs = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("ICD_BEAM_FUSED_MEAN_OFF", "1")
+        else:
+            monkeypatch.delenv("ICD_BEAM_FUSED_MEAN_OFF", raising=False)
+        with torch.no_grad():
+            outs.append(beam_search_batched(dec, feats, 3, V - 3, V - 2, max_steps=20, want_alphas=True, want_trace=True))
+    monkeypatch.delenv("ICD_BEAM_FUSED_MEAN_OFF", raising=False)
+    a, b = outs
+    for key in ("len", "seq", "score", "alpha", "trace"):
+        assert torch.equal(a[key], b[key]), key
