@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256, ICD_ATT_GROUPED_MINB) att_step_fwd_groupe
         const float* __restrict__ fbeta_pre, long long ld_fb,
         float* __restrict__ alpha, long long ld_alpha, float* __restrict__ gated,
         const int* __restrict__ slot_img, const int* __restrict__ n_slots, const int* __restrict__ row_off,
-        unsigned short* __restrict__ gated_x3) {
+        unsigned short* __restrict__ gated_x3, int x3_nseg) {
     extern __shared__ __align__(16) float sm[];
     // slot = the live beams of one image: state rows (att_dec / fbeta / gated) row_off[slot] + j, or slot*k + j without a
     // row map; img = the image whose features the slot decodes (slot == img without a slot map).  alpha rows are
@@ -309,11 +309,12 @@ __global__ void __launch_bounds__(256, ICD_ATT_GROUPED_MINB) att_step_fwd_groupe
                         const __nv_bfloat16 b3 = __float2bfloat16_rn(r1 - __bfloat162float(b2));
                         t[0][q] = __bfloat16_as_ushort(b1); t[1][q] = __bfloat16_as_ushort(b2); t[2][q] = __bfloat16_as_ushort(b3);
                     }
-                    unsigned short* dst = gated_x3 + (r0 + j) * 6 * (long long)C + c;
+                    unsigned short* dst = gated_x3 + (r0 + j) * x3_nseg * (long long)C + c;
                     const int pat[6] = {0, 0, 1, 0, 2, 1};
 #pragma unroll
                     for (int sg = 0; sg < 6; ++sg) {
-                        const unsigned short* tt = t[pat[sg]];
+                        if (sg >= x3_nseg) break;
+                        const unsigned short* tt = t[x3_nseg == 3 ? sg : pat[sg]];
                         *reinterpret_cast<uint2*>(dst + (long long)sg * C) =
                             make_uint2((unsigned)tt[0] | ((unsigned)tt[1] << 16), (unsigned)tt[2] | ((unsigned)tt[3] << 16));
                     }
@@ -367,7 +368,7 @@ struct RingArgs {
     const float* att_dec; long long ld_dec;
     const float* fbeta_pre; long long ld_fb;
     float* alpha; long long ld_alpha;
-    float* gated; unsigned short* gated_x3;
+    float* gated; unsigned short* gated_x3; int x3_nseg;
     float bfull;
 };
 
@@ -511,11 +512,12 @@ __device__ __forceinline__ void ring_image(const RingArgs& g, unsigned char* rin
                     const __nv_bfloat16 b3 = __float2bfloat16_rn(r1 - __bfloat162float(b2));
                     t[0][q] = __bfloat16_as_ushort(b1); t[1][q] = __bfloat16_as_ushort(b2); t[2][q] = __bfloat16_as_ushort(b3);
                 }
-                unsigned short* dst = g.gated_x3 + (r0 + j) * 6 * (long long)C + ch;
+                unsigned short* dst = g.gated_x3 + (r0 + j) * g.x3_nseg * (long long)C + ch;
                 const int pat[6] = {0, 0, 1, 0, 2, 1};
 #pragma unroll
                 for (int sg = 0; sg < 6; ++sg) {
-                    const unsigned short* tt = t[pat[sg]];
+                    if (sg >= g.x3_nseg) break;
+                    const unsigned short* tt = t[g.x3_nseg == 3 ? sg : pat[sg]];
                     *reinterpret_cast<uint2*>(dst + (long long)sg * C) =
                         make_uint2((unsigned)tt[0] | ((unsigned)tt[1] << 16), (unsigned)tt[2] | ((unsigned)tt[3] << 16));
                 }
@@ -533,7 +535,7 @@ __global__ void __launch_bounds__(RING_THREADS, (K <= 5 ? 2 : 1)) att_step_fwd_g
         const float* __restrict__ fbeta_pre, long long ld_fb,
         float* __restrict__ alpha, long long ld_alpha, float* __restrict__ gated,
         const int* __restrict__ slot_img, const int* __restrict__ n_slots, const int* __restrict__ row_off,
-        unsigned short* __restrict__ gated_x3, int* __restrict__ ticket, int stagger_ns_per_beam) {
+        unsigned short* __restrict__ gated_x3, int* __restrict__ ticket, int stagger_ns_per_beam, int x3_nseg) {
     extern __shared__ __align__(128) unsigned char ring_raw[];
     const int Pp = (P + 3) & ~3;
     float* s_dec = reinterpret_cast<float*>(ring_raw + (size_t)RING_SLOTS * RING_SLOT_BYTES);   // K * A
@@ -598,7 +600,7 @@ __global__ void __launch_bounds__(RING_THREADS, (K <= 5 ? 2 : 1)) att_step_fwd_g
     RingArgs g;
     g.P = P; g.C = C; g.A = A; g.Pp = Pp; g.n1 = n1; g.n2 = n2;
     g.att_dec = att_dec; g.ld_dec = ld_dec; g.fbeta_pre = fbeta_pre; g.ld_fb = ld_fb;
-    g.alpha = alpha; g.ld_alpha = ld_alpha; g.gated = gated; g.gated_x3 = gated_x3;
+    g.alpha = alpha; g.ld_alpha = ld_alpha; g.gated = gated; g.gated_x3 = gated_x3; g.x3_nseg = x3_nseg;
     g.bfull = b_full ? b_full[0] : 0.f;
     for (int a = tid; a < A; a += RING_CONS) s_wf[a] = w_full[a];
     uint32_t it = 0;
@@ -1064,7 +1066,7 @@ template <int K>
 static int launch_grouped(int n_img, int k, int P, int C, int A, const int* k_live, const float* enc, const float* att_enc,
                           const float* att_dec, int64_t ld_dec, const float* w_full, const float* b_full,
                           const float* fbeta_pre, int64_t ld_fb, float* alpha, int64_t ld_alpha, float* gated,
-                          const int* slot_img, const int* n_slots, const int* row_off, cudaStream_t s, void* gated_x3, int* ticket) {
+                          const int* slot_img, const int* n_slots, const int* row_off, cudaStream_t s, void* gated_x3, int* ticket, int x3_nseg) {
     const size_t smem = ((size_t)K * A + A + (size_t)K * ((P + 3) & ~3)) * sizeof(float);
     // ring variant (persistent CTAs, bulk-async shared-memory ring): needs one ring slot to hold 14 att_enc rows / 4 enc rows,
     // 16-byte aligned streams, and the ring + the staged rows within the 227 KB of one SM.  ICD_BEAM_ATT_RING=0 keeps the
@@ -1089,7 +1091,7 @@ static int launch_grouped(int n_img, int k, int P, int C, int A, const int* k_li
             const int stagger = (ticket && per_sm == 2 && n_img > ICD_NUM_SMS && k > 1) ? (stag_env ? atoi(stag_env) : 10000) : 0;
             att_step_fwd_grouped_ring_kernel<K><<<std::min(n_img, per_sm * ICD_NUM_SMS), RING_THREADS, ring_smem, s>>>(
                 n_img, k, P, C, A, k_live, enc, att_enc, att_dec, ld_dec, w_full, b_full, fbeta_pre, ld_fb, alpha, ld_alpha, gated,
-                slot_img, n_slots, row_off, reinterpret_cast<unsigned short*>(gated_x3), ticket, stagger);
+                slot_img, n_slots, row_off, reinterpret_cast<unsigned short*>(gated_x3), ticket, stagger, x3_nseg);
             ICD_LAUNCH_CHECK();
             return 0;
         }
@@ -1102,7 +1104,7 @@ static int launch_grouped(int n_img, int k, int P, int C, int A, const int* k_li
     }
     att_step_fwd_grouped_kernel<K><<<n_img, 256, smem, s>>>(k, P, C, A, k_live, enc, att_enc, att_dec, ld_dec, w_full, b_full,
                                                             fbeta_pre, ld_fb, alpha, ld_alpha, gated, slot_img, n_slots, row_off,
-                                                            reinterpret_cast<unsigned short*>(gated_x3));
+                                                            reinterpret_cast<unsigned short*>(gated_x3), x3_nseg);
     ICD_LAUNCH_CHECK();
     return 0;
 }
@@ -1111,13 +1113,13 @@ int icd_attention_step_fwd_grouped(int n_img, int k, int P, int C, int A, const 
                                    const float* att_enc, const float* att_dec, int64_t ld_dec, const float* w_full,
                                    const float* b_full, const float* fbeta_pre, int64_t ld_fb, float* alpha,
                                    int64_t ld_alpha, float* gated, const int* slot_img, const int* n_slots, const int* row_off,
-                                   cudaStream_t s, void* gated_x3, int* ticket) {
+                                   cudaStream_t s, void* gated_x3, int* ticket, int x3_nseg) {
     if (n_img == 0) return 0;
     ICD_CHECK_ARG(!gated_x3 || C % 8 == 0, "attention_step_fwd_grouped: the fused 3-term split needs C % 8 == 0");
     ICD_CHECK_ARG(k >= 1 && k <= 8, "attention_step_fwd_grouped: k=%d (1..8)", k);
     ICD_CHECK_ARG(A % 4 == 0 && C % 4 == 0 && ld_dec % 4 == 0 && ld_fb % 4 == 0, "attention_step_fwd_grouped: misaligned dims");
 #define ICD_GROUPED(KK) return launch_grouped<KK>(n_img, k, P, C, A, k_live, enc, att_enc, att_dec, ld_dec, w_full, b_full, \
-                                                  fbeta_pre, ld_fb, alpha, ld_alpha, gated, slot_img, n_slots, row_off, s, gated_x3, ticket)
+                                                  fbeta_pre, ld_fb, alpha, ld_alpha, gated, slot_img, n_slots, row_off, s, gated_x3, ticket, x3_nseg)
     switch (k) {
         case 1: ICD_GROUPED(1);
         case 2: ICD_GROUPED(2);

@@ -503,7 +503,8 @@ __global__ void beam_gates_init_kernel(const float* __restrict__ embg, const lon
 // grid = (ceil(C/256), images), block = 256 = 4 pixel groups x 64 float4 lanes; the mean is summed exactly like
 // weighted_pixel_sum_kernel (pixels p = g, g+4, ... per group, then g0 + g1 + g2 + g3, then / P): bit-identical to it.
 __global__ void __launch_bounds__(256) split3_mean_kernel(int P, int C, const float* __restrict__ enc,
-                                                          unsigned short* __restrict__ x3, float* __restrict__ mean) {
+                                                          unsigned short* __restrict__ x3, float* __restrict__ mean,
+                                                          int nseg /* 6: K-concatenated segments, 3: stored planes [a1 | a2 | a3] */) {
     __shared__ float4 s_part[3 * 64];
     const int img = blockIdx.y;
     const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(256) split3_mean_kernel(int P, int C, const fl
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < C) {
         const float* base = enc + (long long)img * P * C + c;
-        unsigned short* ob = x3 + (long long)img * P * 6 * C + c;
+        unsigned short* ob = x3 + (long long)img * P * nseg * C + c;
         const int pat[6] = {0, 0, 1, 0, 2, 1};
         for (int p0 = grp; p0 < P; p0 += 16) {
             float4 x[4];
@@ -534,10 +535,11 @@ __global__ void __launch_bounds__(256) split3_mean_kernel(int P, int C, const fl
                     const __nv_bfloat16 b3 = __float2bfloat16_rn(r1 - __bfloat162float(b2));
                     t[0][q] = __bfloat16_as_ushort(b1); t[1][q] = __bfloat16_as_ushort(b2); t[2][q] = __bfloat16_as_ushort(b3);
                 }
-                unsigned short* dst = ob + (long long)p * 6 * C;
+                unsigned short* dst = ob + (long long)p * nseg * C;
 #pragma unroll
                 for (int sg = 0; sg < 6; ++sg) {
-                    const unsigned short* tt = t[pat[sg]];
+                    if (sg >= nseg) break;
+                    const unsigned short* tt = t[nseg == 3 ? sg : pat[sg]];
                     *reinterpret_cast<uint2*>(dst + (long long)sg * C) =
                         make_uint2((unsigned)tt[0] | ((unsigned)tt[1] << 16), (unsigned)tt[2] | ((unsigned)tt[3] << 16));
                 }
@@ -567,10 +569,17 @@ int beam_mm(int prec, const BeamWs& w, const float* x, long long ldx, int rows, 
     if (prec != ICD_PREC_FP32X3)
         return icd_gemm_simple(ICD_PREC_FP32, x, ldx, 1, W, ldw, 1, y, ldy, rows, N, K, bias, nullptr, add, ldadd, nullptr, 0,
                                nullptr, beta, s);
+    // three stored planes per operand where a segment is a whole number of k-blocks (gemm_tc.cuh), else the six-segment layout;
+    // the weight splits of the call (w16x3) and the fused producers of w.x3_act follow the same rule
     const long long seg = up8ll(K);
-    if (!pre_split) ICD_TRY(icd_split3_bf16(x, ldx, rows, K, w.x3_act, 0, s, m_live));   // (pre_split: the producer wrote w.x3_act)
-    return icd_gemm_bf16_ex(w.x3_act, 6 * seg, 0, w16x3, 6 * seg, 0, y, ldy, rows, N, (int)(6 * seg), bias, nullptr, add, ldadd,
-                            nullptr, 0, nullptr, beta, s, nullptr, 0, w.x3_splitk, w.x3_splitk_floats, nullptr, m_live);
+    const bool p3 = icd_x3_three_planes(K);
+    const long long ld3 = (p3 ? 3 : 6) * seg;
+    if (!pre_split) ICD_TRY(icd_split3_bf16(x, ldx, rows, K, w.x3_act, p3 ? 2 : 0, s, m_live));   // (pre_split: the producer wrote w.x3_act)
+    if (p3) icd_gemm_x3_planes((int)(seg / 64), (int)(seg / 64));
+    const int rc = icd_gemm_bf16_ex(w.x3_act, ld3, 0, w16x3, ld3, 0, y, ldy, rows, N, (int)(6 * seg), bias, nullptr, add, ldadd,
+                                    nullptr, 0, nullptr, beta, s, nullptr, 0, w.x3_splitk, w.x3_splitk_floats, nullptr, m_live);
+    icd_gemm_x3_planes(0, 0);
+    return rc;
 }
 
 extern "C" int64_t icd_beam_search_ws_bytes(const icd_beam_desc_t* d) {
@@ -604,13 +613,13 @@ extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
     // once per image: enc_att projection and the initial state (:62)
     ICD_CHECK_ARG(prec == ICD_PREC_FP32 || prec == ICD_PREC_FP32X3, "beam_search: precision must be ICD_PREC_FP32 or ICD_PREC_FP32X3");
     if (prec == ICD_PREC_FP32X3) {            // weights are constant over the whole search: split them once
-        ICD_TRY(icd_split3_bf16(d->enc_att_w, C, A, C, w.x3_We, 1, s));
-        ICD_TRY(icd_split3_bf16(w.w_cat, D, NZ, D, w.x3_Wcat, 1, s));
-        ICD_TRY(icd_split3_bf16(d->w_ih, E + C, 4 * D, E, w.x3_WihE, 1, s));
-        ICD_TRY(icd_split3_bf16(d->w_ih + E, E + C, 4 * D, C, w.x3_WihC, 1, s));
-        ICD_TRY(icd_split3_bf16(d->h_lin_w, C, D, C, w.x3_Wh, 1, s));
-        ICD_TRY(icd_split3_bf16(d->c_lin_w, C, D, C, w.x3_Wc, 1, s));
-        ICD_TRY(icd_split3_bf16(d->fc_w, D, V, D, w.x3_Wfc, 1, s));
+        ICD_TRY(icd_split3_bf16(d->enc_att_w, C, A, C, w.x3_We, icd_x3_three_planes(C) ? 2 : 1, s));
+        ICD_TRY(icd_split3_bf16(w.w_cat, D, NZ, D, w.x3_Wcat, icd_x3_three_planes(D) ? 2 : 1, s));
+        ICD_TRY(icd_split3_bf16(d->w_ih, E + C, 4 * D, E, w.x3_WihE, icd_x3_three_planes(E) ? 2 : 1, s));
+        ICD_TRY(icd_split3_bf16(d->w_ih + E, E + C, 4 * D, C, w.x3_WihC, icd_x3_three_planes(C) ? 2 : 1, s));
+        ICD_TRY(icd_split3_bf16(d->h_lin_w, C, D, C, w.x3_Wh, icd_x3_three_planes(C) ? 2 : 1, s));
+        ICD_TRY(icd_split3_bf16(d->c_lin_w, C, D, C, w.x3_Wc, icd_x3_three_planes(C) ? 2 : 1, s));
+        ICD_TRY(icd_split3_bf16(d->fc_w, D, V, D, w.x3_Wfc, icd_x3_three_planes(D) ? 2 : 1, s));
     }
     // embedding -> gate contribution for the whole vocabulary, once per call: V rows instead of (live rows) x (steps) rows, and
     // no per-step activation split of the embedding rows (fp32 tables; an fp64 GloVe table keeps the per-step contraction)
@@ -630,7 +639,8 @@ extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
         const int ni = n_img - i0 < img_chunk ? n_img - i0 : img_chunk;
         if (fused_mean) {                 // split of the chunk's pixel rows + the pixel mean of its images in one pass over the features
             split3_mean_kernel<<<dim3((unsigned)((C + 255) / 256), (unsigned)ni), 256, 0, s>>>(
-                P, C, d->enc + (size_t)i0 * P * C, reinterpret_cast<unsigned short*>(w.x3_act), w.mean + (size_t)i0 * C);
+                P, C, d->enc + (size_t)i0 * P * C, reinterpret_cast<unsigned short*>(w.x3_act), w.mean + (size_t)i0 * C,
+                icd_x3_three_planes(C) ? 3 : 6);
             ICD_LAUNCH_CHECK();
         }
         ICD_TRY(beam_mm(prec, w, d->enc + (size_t)i0 * P * C, C, ni * P, C, d->enc_att_w, C, w.x3_We,
@@ -670,7 +680,8 @@ extern "C" int icd_beam_search(const icd_beam_desc_t* d, void* stream) {
         const bool fused_split = prec == ICD_PREC_FP32X3 && use_embg && (C % 8 == 0);
         ICD_TRY(icd_attention_step_fwd_grouped(n_img, k, P, C, A, w.k_live, d->enc, w.att_enc, w.z, NZ, d->full_att_w,
                                                d->full_att_b, w.z + A, NZ, alpha_s, P, fused_split ? nullptr : w.gated, w.slot_img,
-                                               w.n_live, row_off, s, fused_split ? w.x3_act : nullptr, w.ring_ticket + step));
+                                               w.n_live, row_off, s, fused_split ? w.x3_act : nullptr, w.ring_ticket + step,
+                                               icd_x3_three_planes(C) ? 3 : 6));
         if (use_embg) {
             beam_gates_init_kernel<<<(unsigned)R, 128, 0, s>>>(w.embg, w.tok64, 4 * D, w.z + A + C, NZ, w.gates_pre, w.n_live);
             ICD_LAUNCH_CHECK();

@@ -164,7 +164,8 @@ int icd_attention_step_fwd_grouped(int n_img, int k, int P, int C, int A, const 
                                    const int* n_slots /* device: live slots, or NULL */,
                                    const int* row_off /* slot -> first state row, or NULL (slot*k) */, cudaStream_t s,
                                    void* gated_x3 = nullptr /* optional: 3-term bf16 split of gated, rows of 6*C (gemm_tc.cu A layout) */,
-                                   int* ticket = nullptr /* optional: ONE zeroed device int per launch: the ring kernel's CTAs draw slots dynamically */);
+                                   int* ticket = nullptr /* optional: ONE zeroed device int per launch: the ring kernel's CTAs draw slots dynamically */,
+                                   int x3_nseg = 6 /* layout of gated_x3: 6 K-concatenated segments, or 3 stored planes (gemm_tc.cuh) */);
 void icd_gemm_simple_set_ws(void* ws, int64_t bytes);
 // ICD_PREC_FP32X3: the 3-term bf16 split of an operand that stays constant during one entry-point call (a weight matrix read by
 // every step of the time loop) is made ONCE and kept in a cache region at the tail of the caller's arena.  Only operands whose

@@ -19,6 +19,7 @@
 //     (work unit = tile x K-slice, raw partial tiles to workspace, a second kernel sums the slices in fixed order
 //     and applies the epilogue) so that one wave still covers the 148 SMs.
 #include "common.cuh"
+#include <stdlib.h>
 #include "gemm_tc.cuh"
 #include "tc_common.cuh"
 #include <cmath>
@@ -88,7 +89,19 @@ struct KArgs {
                                               // contiguous DRAM pages) instead of along M
     const int* m_live;                        // optional DEVICE row count: only rows < min(M, *m_live) are computed / written
                                               // (beam search: the live rows are compacted to the front, no host round trip)
+    int x3_kb_a, x3_kb_b;                     // fp32-grade tier, THREE stored planes per operand ([t1 | t2 | t3] along K, segment = x3_kb
+                                              // k-blocks) instead of the six-segment K-concatenation: the producer maps k-block kb of the
+                                              // 6-segment loop to the plane its segment uses (x3_kcoord); 0 = operand stored as it is walked
 };
+
+// k coordinate (elements) of k-block kb.  Six-term product of 3-term splits, segment order (a1 b1, a1 b2, a2 b1, a1 b3, a3 b1, a2 b2):
+// A walks planes 0,0,1,0,2,1 and B planes 0,1,0,2,0,1 (one nibble per segment in `pat`).
+constexpr uint32_t X3_PAT_A = 0x120100u, X3_PAT_B = 0x102010u;
+__device__ __forceinline__ int x3_kcoord(int kb, int seg_kb, uint32_t pat) {
+    if (seg_kb == 0) return kb * BK;
+    const int sg = kb / seg_kb, kk = kb - sg * seg_kb;
+    return ((int)((pat >> (4 * sg)) & 3u) * seg_kb + kk) * BK;
+}
 
 template <int BN>
 struct Cfg {
@@ -495,24 +508,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t fb = full0 + 8 * stage;
                     mbar_arrive_expect_tx(fb, C_::STAGE_BYTES);      // all slices of both tiles, whoever sends them
                     const uint32_t a_dst = sA + stage * A_BYTES + a_off, b_dst = sB + stage * C_::B_BYTES + b_off;
+                    const int ka = x3_kcoord(kb, p.x3_kb_a, X3_PAT_A), kbn = x3_kcoord(kb, p.x3_kb_b, X3_PAT_B);
                     if (!a_mn) {
-                        if (CN == 1) tma_load_2d(a_dst, &tmA, kb * BK, m0 + a_row, fb);
-                        else tma_load_2d_mc(a_dst, &tmA, kb * BK, m0 + a_row, fb, mask_row);
+                        if (CN == 1) tma_load_2d(a_dst, &tmA, ka, m0 + a_row, fb);
+                        else tma_load_2d_mc(a_dst, &tmA, ka, m0 + a_row, fb, mask_row);
                     } else {
 #pragma unroll
                         for (int j = 0; j < BM / 64; ++j) {
-                            if (CN == 1) tma_load_2d(a_dst + j * MN_BLOCK_BYTES, &tmA, m0 + 64 * j, kb * BK, fb);
-                            else tma_load_2d_mc(a_dst + j * MN_BLOCK_BYTES, &tmA, m0 + 64 * j, kb * BK + a_k, fb, mask_row);
+                            if (CN == 1) tma_load_2d(a_dst + j * MN_BLOCK_BYTES, &tmA, m0 + 64 * j, ka, fb);
+                            else tma_load_2d_mc(a_dst + j * MN_BLOCK_BYTES, &tmA, m0 + 64 * j, ka + a_k, fb, mask_row);
                         }
                     }
                     if (!b_mn) {
-                        if (CM == 1) tma_load_2d(b_dst, &tmB, kb * BK, n0 + b_row, fb);
-                        else tma_load_2d_mc(b_dst, &tmB, kb * BK, n0 + b_row, fb, mask_col);
+                        if (CM == 1) tma_load_2d(b_dst, &tmB, kbn, n0 + b_row, fb);
+                        else tma_load_2d_mc(b_dst, &tmB, kbn, n0 + b_row, fb, mask_col);
                     } else {
 #pragma unroll
                         for (int j = 0; j < (BN + 63) / 64; ++j) {
-                            if (CM == 1) tma_load_2d(b_dst + j * MN_BLOCK_BYTES, &tmB, n0 + 64 * j, kb * BK, fb);
-                            else tma_load_2d_mc(b_dst + j * MN_BLOCK_BYTES, &tmB, n0 + 64 * j, kb * BK + b_k, fb, mask_col);
+                            if (CM == 1) tma_load_2d(b_dst + j * MN_BLOCK_BYTES, &tmB, n0 + 64 * j, kbn, fb);
+                            else tma_load_2d_mc(b_dst + j * MN_BLOCK_BYTES, &tmB, n0 + 64 * j, kbn + b_k, fb, mask_col);
                         }
                     }
                     TRACE(1, kb);
@@ -757,15 +771,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const uint32_t fb_leader = mapa_u32(full0 + 8 * stage, 0);
                     if (crank == 0) mbar_arrive_expect_tx(full0 + 8 * stage, 2 * C_::STAGE_BYTES);   // bytes of BOTH CTAs
                     const uint32_t a_dst = sA + stage * A_BYTES, b_dst = sB + stage * C_::BH_BYTES;
-                    if (!a_mn) tma_load_2d_2sm(a_dst, &tmA, kb * BK, m0, fb_leader);
+                    const int ka = x3_kcoord(kb, p.x3_kb_a, X3_PAT_A), kbn = x3_kcoord(kb, p.x3_kb_b, X3_PAT_B);
+                    if (!a_mn) tma_load_2d_2sm(a_dst, &tmA, ka, m0, fb_leader);
                     else {
 #pragma unroll
-                        for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(a_dst + j * MN_BLOCK_BYTES, &tmA, m0 + 64 * j, kb * BK, fb_leader);
+                        for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(a_dst + j * MN_BLOCK_BYTES, &tmA, m0 + 64 * j, ka, fb_leader);
                     }
-                    if (!b_mn) tma_load_2d_2sm(b_dst, &tmB, kb * BK, n0, fb_leader);
+                    if (!b_mn) tma_load_2d_2sm(b_dst, &tmB, kbn, n0, fb_leader);
                     else {
 #pragma unroll
-                        for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(b_dst + j * MN_BLOCK_BYTES, &tmB, n0 + 64 * j, kb * BK, fb_leader);
+                        for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(b_dst + j * MN_BLOCK_BYTES, &tmB, n0 + 64 * j, kbn, fb_leader);
                     }
                     stage += NUM_PROD_WARPS;
                     if (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
@@ -1056,6 +1071,12 @@ __global__ void split3_rows_kernel(const float* __restrict__ src, long long s_r,
             }
             const int pa[6] = {0, 0, 1, 0, 2, 1}, pb[6] = {0, 1, 0, 2, 0, 1};
             __nv_bfloat16* d = dst + r * ldd + c;
+            if (which == 2) {                                     // three stored planes [t1 | t2 | t3]
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    *reinterpret_cast<uint4*>(d + (long long)k * seg) = make_uint4(t[k][0], t[k][1], t[k][2], t[k][3]);
+                continue;
+            }
 #pragma unroll
             for (int sgm = 0; sgm < 6; ++sgm) {
                 const int k = which == 0 ? pa[sgm] : pb[sgm];
@@ -1071,8 +1092,9 @@ __global__ void split3_rows_kernel(const float* __restrict__ src, long long s_r,
         if (c < cols) split3(src[r * s_r + c], t[0], t[1], t[2]);
         else t[0] = t[1] = t[2] = __float2bfloat16_rn(0.f);
         __nv_bfloat16* d = dst + r * ldd + c;
-        if (which == 0) { d[0] = t[0]; d[seg] = t[0]; d[2 * seg] = t[1]; d[3 * seg] = t[0]; d[4 * seg] = t[2]; d[5 * seg] = t[1]; }
-        else            { d[0] = t[0]; d[seg] = t[1]; d[2 * seg] = t[0]; d[3 * seg] = t[2]; d[4 * seg] = t[0]; d[5 * seg] = t[1]; }
+        if (which == 2)      { d[0] = t[0]; d[seg] = t[1]; d[2 * seg] = t[2]; }
+        else if (which == 0) { d[0] = t[0]; d[seg] = t[0]; d[2 * seg] = t[1]; d[3 * seg] = t[0]; d[4 * seg] = t[2]; d[5 * seg] = t[1]; }
+        else                 { d[0] = t[0]; d[seg] = t[1]; d[2 * seg] = t[0]; d[3 * seg] = t[2]; d[4 * seg] = t[0]; d[5 * seg] = t[1]; }
     }
 }
 // MN-major source ([K][MN] rows): dst[(s*seg + k)*ldd + m] = term_s(src[k*s_k + m])   (seg >= K: rows per segment)
@@ -1084,6 +1106,11 @@ __global__ void split3_mn_kernel(const float* __restrict__ src, long long s_k, i
         __nv_bfloat16 t[3];
         split3(src[k * s_k + m], t[0], t[1], t[2]);
         const int pa[6] = {0, 0, 1, 0, 2, 1}, pb[6] = {0, 1, 0, 2, 0, 1};
+        if (which == 2) {
+#pragma unroll
+            for (int sgm = 0; sgm < 3; ++sgm) dst[((long long)sgm * seg + k) * ldd + m] = t[sgm];
+            continue;
+        }
 #pragma unroll
         for (int sgm = 0; sgm < 6; ++sgm) dst[((long long)sgm * seg + k) * ldd + m] = t[which == 0 ? pa[sgm] : pb[sgm]];
     }
@@ -1327,6 +1354,9 @@ int64_t icd_gemm_bf16_splitk_floats(int M, int N, int K) {
     return rem ? std::max(need(M - rem), need(rem)) : need(M);
 }
 
+static thread_local int g_x3_planes[2] = {0, 0};
+void icd_gemm_x3_planes(int seg_kb_a, int seg_kb_b) { g_x3_planes[0] = seg_kb_a; g_x3_planes[1] = seg_kb_b; }
+
 int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, int64_t ldb, int b_mn,
                      float* C, int64_t ldc, int M, int N, int K,
                      const float* bias1, const float* bias2, const float* add1, int64_t ld1,
@@ -1377,14 +1407,19 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
         cluster_shape(M, N, K, pl.bn, pl.splits, m_live != nullptr, &qm, &qn);
         if (qm * qn > 1) { mode = 1; cm = qm; cn = qn; }
     }
+    // fp32-grade tier with three stored planes per operand (icd_gemm_x3_planes): K = 6 segments are walked, 3 are stored
+    const int x3a = g_x3_planes[0], x3b = g_x3_planes[1];
+    ICD_CHECK_ARG((!x3a || (int64_t)x3a * 6 * BK == K) && (!x3b || (int64_t)x3b * 6 * BK == K),
+                  "gemm_tc: three-plane operands need K = 6 * 64 * segment k-blocks (K=%d, %d / %d)", K, x3a, x3b);
+    const int Ka = x3a ? K / 2 : K, Kb = x3b ? K / 2 : K;
     CUtensorMap tmA, tmB;
     if (mode == 2) {
-        ICD_TRY(make_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(A16), lda, M, K, BM, a_mn));
-        ICD_TRY(make_tmap(&tmB, reinterpret_cast<const __nv_bfloat16*>(B16), ldb, N, K, pl.bn / 2, b_mn));
+        ICD_TRY(make_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(A16), lda, M, Ka, BM, a_mn));
+        ICD_TRY(make_tmap(&tmB, reinterpret_cast<const __nv_bfloat16*>(B16), ldb, N, Kb, pl.bn / 2, b_mn));
     } else {
         // K-major: the box is the CTA's row slice of the tile; MN-major: all 64-wide MN blocks, the CTA's k-row slice
-        ICD_TRY(make_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(A16), lda, M, K, BM / cn, a_mn, BK / cn));
-        ICD_TRY(make_tmap(&tmB, reinterpret_cast<const __nv_bfloat16*>(B16), ldb, N, K, pl.bn / cm, b_mn, BK / cm));
+        ICD_TRY(make_tmap(&tmA, reinterpret_cast<const __nv_bfloat16*>(A16), lda, M, Ka, BM / cn, a_mn, BK / cn));
+        ICD_TRY(make_tmap(&tmB, reinterpret_cast<const __nv_bfloat16*>(B16), ldb, N, Kb, pl.bn / cm, b_mn, BK / cm));
     }
     const int cluster = mode == 2 ? 2 : cm;                    // CTAs along M that form one super tile
     static const bool verbose = getenv("ICD_GEMM_VERBOSE") != nullptr;
@@ -1407,6 +1442,7 @@ int icd_gemm_bf16_ex(const void* A16, int64_t lda, int a_mn, const void* B16, in
     k.splits = pl.splits; k.kb_per_split = pl.kb_per_split; k.partial = splitk_ws;
     k.cm = mode == 2 ? 2 : cm; k.cn = mode == 2 ? 1 : cn;
     k.m_live = m_live;
+    k.x3_kb_a = x3a; k.x3_kb_b = x3b;
     k.late_trigger = icd_gemm_take_late_hint();
     {   // rasterisation of the work units (ICD_GEMM_RASTER=0|1 overrides): see KArgs::raster_n
         static const int raster_env = [] { const char* f = getenv("ICD_GEMM_RASTER"); return f ? atoi(f) : -1; }();
@@ -1512,7 +1548,7 @@ int icd_split3_bf16(const float* src, int64_t s_r, int rows, int cols, void* dst
     long long blocks = (total + 255) / 256;
     if (blocks > ICD_NUM_SMS * 16) blocks = ICD_NUM_SMS * 16;
     split3_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, s_r, rows, cols, seg, reinterpret_cast<__nv_bfloat16*>(dst),
-                                                        6LL * seg, which, m_live, vec8);
+                                                        (which == 2 ? 3LL : 6LL) * seg, which, m_live, vec8);
     ICD_LAUNCH_CHECK();
     return 0;
 }
@@ -1543,9 +1579,15 @@ int icd_gemm_x3_launch(const icd_gemm_desc_t* d, cudaStream_t s) {
     const bool mixed = (a_mn != b_mn);
     const int mn_seg = mixed ? seg : K;
     const int Kx = (a_mn && b_mn) ? 6 * K : 6 * seg;
+    // Three stored planes per operand instead of six K-segments whenever a segment is a whole number of k-blocks: the split
+    // passes write half the bytes, the contraction is the same sequence of MMAs on the same values (bit-identical results).
+    const int seg_len = (a_mn && b_mn) ? K : seg;                 // elements of K per segment, the same for both operands
+    const bool p3 = (seg_len % BK) == 0 && getenv("ICD_X3_PLANES6") == nullptr;
+    const int nseg = p3 ? 3 : 6;
     int64_t lda, ldb;
     auto split_mn = [&](const float* src, int64_t s_k, int mn, void* dst, int64_t ldd, int which) -> int {
-        if (mn_seg != K) ICD_CUDA(cudaMemsetAsync(dst, 0, (size_t)6 * mn_seg * ldd * 2, s));
+        if (p3) which = 2;
+        if (mn_seg != K) ICD_CUDA(cudaMemsetAsync(dst, 0, (size_t)nseg * mn_seg * ldd * 2, s));
         const long long total = (long long)K * mn;
         long long blocks = (total + 255) / 256;
         if (blocks > ICD_NUM_SMS * 16) blocks = ICD_NUM_SMS * 16;
@@ -1555,13 +1597,16 @@ int icd_gemm_x3_launch(const icd_gemm_desc_t* d, cudaStream_t s) {
     };
     // an operand that stays constant during the enclosing entry-point call (a marked weight matrix) is split once and reused
     bool a_fresh = true, b_fresh = true;
-    if (void* c = icd_x3_cache_lookup(d->A, a_mn ? d->sak : d->sam, M, K, a_mn, a_mn ? mn_seg : seg, 0, a_bytes, &a_fresh)) a16 = reinterpret_cast<char*>(c);
-    if (void* c = icd_x3_cache_lookup(d->B, b_mn ? d->sbk : d->sbn, N, K, b_mn, b_mn ? mn_seg : seg, 1, b_bytes, &b_fresh)) b16 = reinterpret_cast<char*>(c);
-    if (!a_mn) { lda = 6LL * seg; if (a_fresh) ICD_TRY(icd_split3_bf16(d->A, d->sam, M, K, a16, 0, s)); }
+    if (void* c = icd_x3_cache_lookup(d->A, a_mn ? d->sak : d->sam, M, K, a_mn, a_mn ? mn_seg : seg, p3 ? 2 : 0, a_bytes, &a_fresh)) a16 = reinterpret_cast<char*>(c);
+    if (void* c = icd_x3_cache_lookup(d->B, b_mn ? d->sbk : d->sbn, N, K, b_mn, b_mn ? mn_seg : seg, p3 ? 2 : 1, b_bytes, &b_fresh)) b16 = reinterpret_cast<char*>(c);
+    if (!a_mn) { lda = (int64_t)nseg * seg; if (a_fresh) ICD_TRY(icd_split3_bf16(d->A, d->sam, M, K, a16, p3 ? 2 : 0, s)); }
     else { lda = up8(M); if (a_fresh) ICD_TRY(split_mn(d->A, d->sak, M, a16, lda, 0)); }
-    if (!b_mn) { ldb = 6LL * seg; if (b_fresh) ICD_TRY(icd_split3_bf16(d->B, d->sbn, N, K, b16, 1, s)); }
+    if (!b_mn) { ldb = (int64_t)nseg * seg; if (b_fresh) ICD_TRY(icd_split3_bf16(d->B, d->sbn, N, K, b16, p3 ? 2 : 1, s)); }
     else { ldb = up8(N); if (b_fresh) ICD_TRY(split_mn(d->B, d->sbk, N, b16, ldb, 1)); }
-    return icd_gemm_bf16_ex(a16, lda, a_mn, b16, ldb, b_mn, d->C, d->ldc, M, N, Kx, d->bias1, d->bias2, d->add1, d->ld1,
-                            d->add2, d->ld2, d->row_mask, d->beta, s, nullptr, 0, sk,
-                            icd_gemm_bf16_splitk_floats(M, N, Kx), nullptr);
+    if (p3) icd_gemm_x3_planes(seg_len / BK, seg_len / BK);
+    const int rc = icd_gemm_bf16_ex(a16, lda, a_mn, b16, ldb, b_mn, d->C, d->ldc, M, N, Kx, d->bias1, d->bias2, d->add1, d->ld1,
+                                    d->add2, d->ld2, d->row_mask, d->beta, s, nullptr, 0, sk,
+                                    icd_gemm_bf16_splitk_floats(M, N, Kx), nullptr);
+    icd_gemm_x3_planes(0, 0);
+    return rc;
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 // dst[r*ldd + c] = bf16(src[r*s_r + c*s_c]);  one of s_r / s_c must be 1; ldd multiple of 8.
 int icd_convert_bf16(const float* src, int64_t s_r, int64_t s_c, int rows, int cols, void* dst, int64_t ldd,
@@ -47,6 +48,13 @@ int64_t icd_gemm_tc_ws_bytes(int M, int N, int K);
 int icd_split3_bf16(const float* src, int64_t s_r, int rows, int cols, void* dst, int which, cudaStream_t s,
                     const int* m_live = nullptr);   // m_live: optional device-side row count (rows beyond it are skipped)
 int64_t icd_gemm_x3_ws_bytes(int M, int N, int K);
+// which = 2: THREE stored planes [t1 | t2 | t3] (row of 3 * up8(cols)) instead of the six-segment patterns; the contraction then walks
+// them through icd_gemm_x3_planes(segment k-blocks of A, of B): applies to the icd_gemm_bf16_ex calls of this thread until reset with
+// (0, 0).  Needs up8(cols) % 64 == 0.  Same MMAs on the same values as the six-segment layout: bit-identical results, half the split bytes.
+void icd_gemm_x3_planes(int seg_kb_a, int seg_kb_b);
+inline bool icd_x3_three_planes(long long K) {          // K-major operand of K columns: three stored planes possible?
+    return ((K + 7) / 8 * 8) % 64 == 0 && getenv("ICD_X3_PLANES6") == nullptr;
+}
 
 // Persistent recurrent LSTM kernels (lstm_persistent.cu): the whole h -> gates -> (c, h) recurrence of nn.LSTM, resp. its
 // adjoint, as ONE cooperative launch.  icd_lstm_seq_persistent_ok: 1 if the shape is covered (else keep a launch chain).

@@ -973,3 +973,61 @@ def test_beam_prologue_fused_split_and_pixel_mean_is_bit_identical(cuda, monkeyp
     a, b = outs
     for key in ("len", "seq", "score", "alpha", "trace"):
         assert torch.equal(a[key], b[key]), key
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["train", "beam"])
+def test_fp32x3_three_stored_planes_equal_six_segments(cuda, which, monkeypatch):
+    """fp32-grade tier: where a K segment is a whole number of 64-wide k-blocks each operand is stored as THREE bf16 planes
+    [t1 | t2 | t3] and the contraction's TMA producer walks them in the order of the six cross terms; ICD_X3_PLANES6=1 restores the
+    six-segment K-concatenated copies.  Same MMAs on the same values in the same order: bit-identical outputs and gradients
+    (train: D = A = E = 64 and C = 2048 take the three-plane path, K-major and MN-major operands, cached weight splits and
+    split-K included; beam: the full-size decoder of the golden case, fused producers of the split activations included)."""
+    import icd_b200.models.attention as my_att
+    from icd_b200.gen_captions import beam_search_batched
+    from icd_b200.vocabulary import synthetic_vocab
+
+    def both(fn):
+        monkeypatch.delenv("ICD_X3_PLANES6", raising=False)
+        a = fn()
+        monkeypatch.setenv("ICD_X3_PLANES6", "1")
+        b = fn()
+        monkeypatch.delenv("ICD_X3_PLANES6", raising=False)
+        return a, b
+
+    if which == "train":
+        case = dict(B=21, V=97, A=64, D=64, E=64, max_len=9, lengths=[9] * 6 + [7] * 5 + [4] * 10, wseed=6, iseed=41,
+                    dropout=0.5, train=False, fine_tune_embedding=True)
+        dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams, synthetic_vocab(case["V"]))
+        dec = dec.to(cuda)
+        dec.eval()
+        dec.precision = "fp32x3"
+        enc = synthetic_features(case["B"], case["iseed"]).to(cuda).requires_grad_(True)
+        caps, lens = synthetic_caps(case)
+        caps = caps.to(cuda)
+
+        def run():
+            dec.zero_grad()
+            enc.grad = None
+            preds, _, dl, alphas = dec(enc, caps, lens)
+            O.attention_loss(preds, caps, dl, alphas).backward()
+            out = {k: p.grad.clone() for k, p in dec.named_parameters() if p.grad is not None}
+            out["predictions"], out["alphas"], out["d_enc"] = preds.detach().clone(), alphas.detach().clone(), enc.grad.clone()
+            return out
+        a, b = both(run)
+        assert a.keys() == b.keys() and len(a) > 10
+    else:
+        case = dict(H.BEAM_CASES["beam_cfg"], dropout=0.5, train=False, fine_tune_embedding=True)
+        vocab = synthetic_vocab(case["V"])
+        dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams, vocab)
+        H.apply_beam_recipe(dec, case)
+        dec = dec.to(cuda)
+        feats = H.beam_features(case).to(cuda)
+        V, k = case["V"], case["k"]
+
+        def run():
+            with torch.no_grad():
+                return beam_search_batched(dec, feats, k, V - 3, V - 2, max_steps=30, want_alphas=True, want_trace=True)
+        a, b = both(run)
+    for key in a:
+        assert torch.equal(a[key], b[key]), key
