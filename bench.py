@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--impl", default="icd_b200", choices=["icd_b200", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "fp32x3", "bf16"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="captions per GPU (default: the benchmark config)")
-    ap.add_argument("--workload", default="train", choices=["train", "beam", "baseline", "glove", "tier"],
+    ap.add_argument("--workload", default="train", choices=["train", "beam", "baseline", "glove", "tier", "ragged"],
                     help="train = BASELINE.json configs[2] (the metric's configuration, default); the others time the "
                          "remaining configs and print their own JSON line")
     ap.add_argument("--beam-images", type=int, default=1024, help="images per GPU for the beam-search measurement")
@@ -442,9 +442,11 @@ def measure_baseline(dev, precision="bf16", steps=20, warmup=5, world=1):
             "config": {"workload": "configs[1]: baseline LSTM decoder, batch 128/GPU, L=25, V=9490, E=H=512"}}
 
 
-def measure_attention(dev, precision, batch, steps, warmup, glove=False):
+def measure_attention(dev, precision, batch, steps, warmup, glove=False, ragged=False):
     """The attention train step on one GPU in a given tier: configs[3] (glove_att: E = 300, fp64 fine-tuned table) when
-    glove=True, else configs[2] in another precision tier (fp32x3 = the tier that meets the 1e-3 bar, fp32 = FMA tier)."""
+    glove=True, else configs[2] in another precision tier (fp32x3 = the tier that meets the 1e-3 bar, fp32 = FMA tier).
+    ragged=True: SURVEY.md section 8(d)'s length regime B (caption lengths U{8..25}, sorted descending: batch_size_t shrinks from B
+    to a few rows over the 24 steps) instead of regime A (all captions 25 tokens, the reference's own training regime)."""
     import torch
     from icd_b200 import synthetic
     from icd_b200.losses import attention_caption_loss
@@ -465,7 +467,7 @@ def measure_attention(dev, precision, batch, steps, warmup, glove=False):
     dec.train()
     opt = DataParallelClipAdam(dec, lr=1e-4, grad_clip=5.0)
     enc = synthetic.features(batch).to(dev)
-    caps, lens = synthetic.captions(batch, V, max_len=MAXLEN)
+    caps, lens = synthetic.captions(batch, V, max_len=MAXLEN, lengths=("ragged" if ragged else None))
     caps = caps.to(dev)
 
     def step():
@@ -478,8 +480,16 @@ def measure_attention(dev, precision, batch, steps, warmup, glove=False):
     ms, loss = _time_steps(step, steps, warmup)
     name = ("configs[3]: glove_att, embed 300, fp64 fine-tuned embedding table, batch %d, T=24, V=9490" % batch) if glove else \
            ("configs[2] in the %s tier: basic_att train step, batch %d, T=24, V=9490" % (precision, batch))
-    return {"metric": "attention-decoder train-step captions/s", "value": batch / (ms / 1e3), "unit": "captions/s", "n_gpus": 1,
-            "ms_per_step": ms, "steps": steps, "loss": loss, "dtype": precision, "data": "synthetic", "config": {"workload": name}}
+    out = {"metric": "attention-decoder train-step captions/s", "value": batch / (ms / 1e3), "unit": "captions/s", "n_gpus": 1,
+           "ms_per_step": ms, "steps": steps, "loss": loss, "dtype": precision, "data": "synthetic", "config": {"workload": name}}
+    if ragged:
+        tokens = sum(l - 1 for l in lens)
+        out["config"]["workload"] = ("configs[2], length regime B (SURVEY.md 8d): caption lengths U{8..25} sorted descending, batch %d, "
+                                     "V=9490, %s tier" % (batch, precision))
+        out["decode_tokens_per_step"] = tokens
+        out["decode_tokens_per_s"] = tokens / (ms / 1e3)
+        out["fraction_of_regime_A_tokens"] = tokens / float(batch * (MAXLEN - 1))
+    return out
 
 
 def measure_eager_torch_reference(dev, batch=B_PER_GPU, steps=2, warmup=1):
@@ -551,6 +561,8 @@ def side_workload(args):
         line = measure_baseline(dev, prec, args.steps, max(args.warmup, 3), world=world)
     elif args.workload == "glove":
         line = measure_attention(dev, prec, args.batch, args.steps, max(args.warmup, 3), glove=True)
+    elif args.workload == "ragged":
+        line = measure_attention(dev, prec, args.batch, args.steps, max(args.warmup, 3), ragged=True)
     else:
         line = measure_attention(dev, prec, args.batch, args.steps, max(args.warmup, 3))
     if world > 1:
@@ -880,6 +892,7 @@ def main():
             guarded("configs[1]_baseline_bf16", lambda: measure_baseline(dev, "bf16", steps=20, warmup=5))
             guarded("configs[1]_baseline_fp32x3", lambda: measure_baseline(dev, "fp32x3", steps=10, warmup=3))
             guarded("configs[3]_glove_bf16", lambda: measure_attention(dev, "bf16", B, steps=10, warmup=3, glove=True))
+            guarded("configs[2]_regime_B_ragged_bf16", lambda: measure_attention(dev, "bf16", B, steps=10, warmup=3, ragged=True))
             guarded("configs[2]_fp32x3_tier", lambda: measure_attention(dev, "fp32x3", B, steps=5, warmup=3))
             guarded("configs[2]_fp32_tier", lambda: measure_attention(dev, "fp32", B, steps=3, warmup=2))
             guarded("eager_pytorch_reference_on_this_gpu", lambda: measure_eager_torch_reference(dev, B))

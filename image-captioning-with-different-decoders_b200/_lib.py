@@ -143,3 +143,18 @@ def fill(desc, **kw):
         else:
             setattr(desc, k, v)
     return desc
+
+
+def remember_versions(ctx, named):
+    """Record the autograd version counters of the tensors a custom Function's backward will read through raw pointers
+    ((name, tensor) pairs; None tensors skipped) — the stand-in for save_for_backward's in-place-modification check."""
+    ctx._icd_versions = [(n, t, t._version) for n, t in named if hasattr(t, "_version")]
+
+
+def check_versions(ctx, what):
+    """Raise like autograd does when a tensor saved for backward was modified in place after the forward."""
+    for n, t, v in getattr(ctx, "_icd_versions", ()):
+        if t._version != v:
+            raise RuntimeError("icd_b200: %s: '%s' needed for the backward was modified by an in-place operation after the forward "
+                               "(is at version %d, expected %d); the backward reads it in place, like autograd's saved tensors"
+                               % (what, n, t._version, v))

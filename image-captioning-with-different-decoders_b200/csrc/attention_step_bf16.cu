@@ -46,29 +46,18 @@ __device__ __forceinline__ void mma_bf16_16816(float& d0, float& d1, float& d2, 
 // ------------------------------------------------------------------------------------------------
 constexpr int FW16_ROWS = 4;      // pixel rows per warp iteration in the score phase
 constexpr int FW16_UNROLL = 8;    // pixel rows in flight per thread in the weighted-sum phase
+// rows per launch at or below which a row is shared by 4 / 2 CTAs (att_step_fwd_bf16_split_kernel); fitted on att_bench.py
+constexpr int ICD_ATT_FWD_SPLIT4_ROWS = 48;      // 16-32 rows: 35 -> 27 us; 100 rows: two CTAs per row are better (33 us vs 34)
+constexpr int ICD_ATT_FWD_SPLIT2_ROWS = 222;     // = 1.5 x 148 (three CTAs per SM when shared by two): 200 rows 45.7 -> 43.5 us, 256 rows lose
+// rows per launch at or below which the backward runs EVERY row as two half-row CTAs (its row-balance machinery, see the kernel)
+constexpr int ICD_ATT_BWD_SPLIT_ALL_ROWS = 222;  // 32 rows 43 -> 34 us, 148 rows 46 -> 37, 200 rows 51.5 -> 44; 256 rows: no gain
 
-__global__ void __launch_bounds__(256, 4) att_step_fwd_bf16_kernel(
-        int P, int C, int A, const int* __restrict__ img_index,
-        const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* __restrict__ att_enc,
-        const float* __restrict__ att_dec, long long ld_dec,
-        const float* __restrict__ w_full, const float* __restrict__ b_full,
-        const float* __restrict__ fbeta_pre, long long ld_fb,
-        float* __restrict__ alpha, long long ld_alpha,
-        float* __restrict__ awe_raw, float* __restrict__ gate, float* __restrict__ gated,
-        __nv_bfloat16* __restrict__ gated16) {
-    extern __shared__ __align__(16) float sm[];
-    float* s_dec = sm;
-    float* s_wf = sm + A;
-    float* s_e = sm + 2 * A;
-    float* s_red = s_e + ((P + 3) & ~3);
-    const int r = blockIdx.x;
-    pdl_trigger();
-    pdl_wait();
-    const int img = img_index ? img_index[r] : r;
-    const __nv_bfloat16* ae = att_enc + (long long)img * P * A;
-    const float* dec = att_dec + (long long)r * ld_dec;
-    for (int a = threadIdx.x; a < A; a += blockDim.x) { s_dec[a] = dec[a]; s_wf[a] = w_full[a]; }
-    __syncthreads();
+// phases 1 + 2 of the forward step for ONE row: scores e_p = w_full . relu(att_enc[p, :] + att_dec) + b_full over the row's pixels
+// (att_enc streamed once), softmax over the pixels; alpha is left in s_e and, when `out` is given, written to global memory.
+template <bool HAS_OUT>     // true: `out` is known to be non-null (no test in the whole-row kernel)
+__device__ __forceinline__ void fwd16_scores_softmax(int P, int A, const __nv_bfloat16* ae,
+                                                     const float* b_full, float* s_dec, float* s_wf, float* s_e,
+                                                     float* s_red, float* out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const float bfull = b_full ? b_full[0] : 0.f;
     const int A8 = A >> 3;
@@ -113,11 +102,37 @@ __global__ void __launch_bounds__(256, 4) att_step_fwd_bf16_kernel(
     float sum = 0.f;
     for (int p = threadIdx.x; p < P; p += blockDim.x) { const float ex = expf(s_e[p] - m); s_e[p] = ex; sum += ex; }
     sum = block_sum(sum, s_red);
-    {
-        float* out = alpha + (long long)r * ld_alpha;
+    if (HAS_OUT || out) {
         for (int p = threadIdx.x; p < P; p += blockDim.x) { const float al = s_e[p] / sum; s_e[p] = al; out[p] = al; }
+    } else {
+        for (int p = threadIdx.x; p < P; p += blockDim.x) s_e[p] = s_e[p] / sum;
     }
     __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 4) att_step_fwd_bf16_kernel(
+        int P, int C, int A, const int* __restrict__ img_index,
+        const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* __restrict__ att_enc,
+        const float* __restrict__ att_dec, long long ld_dec,
+        const float* __restrict__ w_full, const float* __restrict__ b_full,
+        const float* __restrict__ fbeta_pre, long long ld_fb,
+        float* __restrict__ alpha, long long ld_alpha,
+        float* __restrict__ awe_raw, float* __restrict__ gate, float* __restrict__ gated,
+        __nv_bfloat16* __restrict__ gated16) {
+    extern __shared__ __align__(16) float sm[];
+    float* s_dec = sm;
+    float* s_wf = sm + A;
+    float* s_e = sm + 2 * A;
+    float* s_red = s_e + ((P + 3) & ~3);
+    const int r = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    const int img = img_index ? img_index[r] : r;
+    const __nv_bfloat16* ae = att_enc + (long long)img * P * A;
+    const float* dec = att_dec + (long long)r * ld_dec;
+    for (int a = threadIdx.x; a < A; a += blockDim.x) { s_dec[a] = dec[a]; s_wf[a] = w_full[a]; }
+    __syncthreads();
+    fwd16_scores_softmax<true>(P, A, ae, b_full, s_dec, s_wf, s_e, s_red, alpha + (long long)r * ld_alpha);
     // phase 3: alpha-weighted sum; thread owns 8 consecutive channels (16 B), FW16_UNROLL pixel rows in flight
     const __nv_bfloat16* eb = enc + (long long)img * P * C;
     for (int c = threadIdx.x * 8; c < C; c += blockDim.x * 8) {
@@ -170,6 +185,116 @@ __global__ void __launch_bounds__(256, 4) att_step_fwd_bf16_kernel(
             if (gated16) {
                 uint4 pk = make_uint4(pack2(gd[0], gd[1]), pack2(gd[2], gd[3]), pack2(gd[4], gd[5]), pack2(gd[6], gd[7]));
                 *reinterpret_cast<uint4*>(gated16 + o) = pk;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward, FEW rows per launch (ragged batches late in the caption, small batches): a row is shared by S = 8 / CH CTAs so that a launch
+// of fewer rows than the GPU has CTA slots still keeps every SM streaming.  CTA (r, s) forms ALL scores of row r (the S readers of the
+// row's att_enc, 20 % of its bytes, meet in L2) and the weighted sum of channels [s C / S, (s + 1) C / S); a thread owns CH consecutive
+// channels and keeps FW16_UNROLL * S pixel rows in flight (the same bytes per thread as the whole-row kernel).  Every output element is
+// formed by the same operations in the same order as in the whole-row kernel: the results are bit-identical (tested).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_stream_u1(const void* p) {
+    unsigned r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+template <int CH> struct StreamChunk;
+template <> struct StreamChunk<4> {
+    uint2 v;
+    __device__ __forceinline__ void load(const void* p) { v = ld_stream_u2(p); }
+    __device__ __forceinline__ void unpack(float (&f)[4]) const {
+        f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+        f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+    }
+};
+template <> struct StreamChunk<2> {
+    unsigned v;
+    __device__ __forceinline__ void load(const void* p) { v = ld_stream_u1(p); }
+    __device__ __forceinline__ void unpack(float (&f)[2]) const {
+        f[0] = __uint_as_float(v << 16); f[1] = __uint_as_float(v & 0xffff0000u);
+    }
+};
+
+template <int CH>
+__global__ void __launch_bounds__(256, 4) att_step_fwd_bf16_split_kernel(
+        int P, int C, int A, const int* __restrict__ img_index,
+        const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* __restrict__ att_enc,
+        const float* __restrict__ att_dec, long long ld_dec,
+        const float* __restrict__ w_full, const float* __restrict__ b_full,
+        const float* __restrict__ fbeta_pre, long long ld_fb,
+        float* __restrict__ alpha, long long ld_alpha,
+        float* __restrict__ awe_raw, float* __restrict__ gate, float* __restrict__ gated,
+        __nv_bfloat16* __restrict__ gated16) {
+    constexpr int S = 8 / CH;
+    constexpr int UN = FW16_UNROLL * S;
+    extern __shared__ __align__(16) float sm[];
+    float* s_dec = sm;
+    float* s_wf = sm + A;
+    float* s_e = sm + 2 * A;
+    float* s_red = s_e + ((P + 3) & ~3);
+    const int r = blockIdx.x / S, part = blockIdx.x % S;
+    pdl_trigger();
+    pdl_wait();
+    const int img = img_index ? img_index[r] : r;
+    const __nv_bfloat16* ae = att_enc + (long long)img * P * A;
+    const float* dec = att_dec + (long long)r * ld_dec;
+    for (int a = threadIdx.x; a < A; a += blockDim.x) { s_dec[a] = dec[a]; s_wf[a] = w_full[a]; }
+    __syncthreads();
+    fwd16_scores_softmax<false>(P, A, ae, b_full, s_dec, s_wf, s_e, s_red, part == 0 ? alpha + (long long)r * ld_alpha : nullptr);
+    // phase 3: this CTA's channel range, CH channels per thread
+    const __nv_bfloat16* eb = enc + (long long)img * P * C;
+    const int cw = C / S;                                         // C % 8 == 0: cw is a multiple of CH
+    for (int c = part * cw + threadIdx.x * CH; c < (part + 1) * cw; c += blockDim.x * CH) {
+        float acc[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) acc[i] = 0.f;
+        int p = 0;
+        for (; p + UN <= P; p += UN) {
+            StreamChunk<CH> x[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) x[u].load(eb + (long long)(p + u) * C + c);
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const float al = s_e[p + u];
+                float f[CH];
+                x[u].unpack(f);
+#pragma unroll
+                for (int i = 0; i < CH; ++i) acc[i] = fmaf(al, f[i], acc[i]);
+            }
+        }
+        for (; p < P; ++p) {
+            StreamChunk<CH> x;
+            x.load(eb + (long long)p * C + c);
+            const float al = s_e[p];
+            float f[CH];
+            x.unpack(f);
+#pragma unroll
+            for (int i = 0; i < CH; ++i) acc[i] = fmaf(al, f[i], acc[i]);
+        }
+        const long long o = (long long)r * C + c;
+        if (awe_raw) {
+#pragma unroll
+            for (int i = 0; i < CH; i += 2) *reinterpret_cast<float2*>(awe_raw + o + i) = make_float2(acc[i], acc[i + 1]);
+        }
+        if (fbeta_pre) {
+            float g[CH], gd[CH];
+#pragma unroll
+            for (int i = 0; i < CH; i += 2) {
+                const float2 f = *reinterpret_cast<const float2*>(fbeta_pre + (long long)r * ld_fb + c + i);
+                g[i] = sigmoidf_(f.x);
+                g[i + 1] = sigmoidf_(f.y);
+            }
+#pragma unroll
+            for (int i = 0; i < CH; ++i) gd[i] = g[i] * acc[i];
+#pragma unroll
+            for (int i = 0; i < CH; i += 2) {
+                if (gate) *reinterpret_cast<float2*>(gate + o + i) = make_float2(g[i], g[i + 1]);
+                if (gated) *reinterpret_cast<float2*>(gated + o + i) = make_float2(gd[i], gd[i + 1]);
+                if (gated16) *reinterpret_cast<uint32_t*>(gated16 + o + i) = pack2(gd[i], gd[i + 1]);
             }
         }
     }
@@ -787,11 +912,24 @@ extern "C" int icd_attention_step_fwd_bf16(int rows, int P, int C, int A, const 
         ICD_CUDA(cudaFuncSetAttribute(att_step_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
+    // few rows per launch (ragged batches late in the caption, small batches): 2 or 4 CTAs per row (channel split, bit-identical
+    // results) so that the launch still fills the CTA slots of the GPU.  ICD_ATT_FWD_SPLIT = 1 | 2 | 4 forces a variant (tests, tools).
+    const char* fsplit_e = getenv("ICD_ATT_FWD_SPLIT");
+    const int split_env = fsplit_e ? atoi(fsplit_e) : 0;
+    int nsplit = split_env == 1 || split_env == 2 || split_env == 4 ? split_env
+                 : (rows <= ICD_ATT_FWD_SPLIT4_ROWS ? 4 : rows <= ICD_ATT_FWD_SPLIT2_ROWS ? 2 : 1);
+    if (smem > 48 * 1024) nsplit = 1;          // (only the whole-row kernel is configured for large shared memory)
     icd_prof_mark_begin(0, rows, s);
-    ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_FWD, att_step_fwd_bf16_kernel, dim3(rows), dim3(256), smem, s, P, C, A, (const int*)img_index,
-                            reinterpret_cast<const __nv_bfloat16*>(enc16), reinterpret_cast<const __nv_bfloat16*>(att_enc16),
-                            att_dec, (long long)ld_dec, w_full, b_full, fbeta_pre, (long long)ld_fb, alpha, (long long)ld_alpha,
-                            awe_raw, gate, gated, reinterpret_cast<__nv_bfloat16*>(gated16)));
+#define ICD_FWD16_ARGS P, C, A, (const int*)img_index, reinterpret_cast<const __nv_bfloat16*>(enc16),                      \
+                       reinterpret_cast<const __nv_bfloat16*>(att_enc16), att_dec, (long long)ld_dec, w_full, b_full, fbeta_pre, \
+                       (long long)ld_fb, alpha, (long long)ld_alpha, awe_raw, gate, gated, reinterpret_cast<__nv_bfloat16*>(gated16)
+    if (nsplit == 4)
+        ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_FWD, att_step_fwd_bf16_split_kernel<2>, dim3(rows * 4), dim3(256), smem, s, ICD_FWD16_ARGS));
+    else if (nsplit == 2)
+        ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_FWD, att_step_fwd_bf16_split_kernel<4>, dim3(rows * 2), dim3(256), smem, s, ICD_FWD16_ARGS));
+    else
+        ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_FWD, att_step_fwd_bf16_kernel, dim3(rows), dim3(256), smem, s, ICD_FWD16_ARGS));
+#undef ICD_FWD16_ARGS
     icd_prof_mark_end(0, s);
     ICD_LAUNCH_CHECK();
     return 0;
@@ -828,7 +966,12 @@ extern "C" int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
     const char* split_e = getenv("ICD_ATT_BWD_SPLIT");     // 0: never, 2: every row (tests), else: the balance rule
     const bool split_env = !split_e || split_e[0] != '0';
     int n_split = 0;
+    // few rows per launch (ragged batches late in the caption, small batches): EVERY row as two half-row CTAs, twice the CTAs
+    // streaming.  ICD_ATT_BWD_SPLIT_ROWS overrides the row count at or below which that happens (tools/att_bench.py fits it).
+    const char* few_e = getenv("ICD_ATT_BWD_SPLIT_ROWS");
+    const int few_rows = few_e ? atoi(few_e) : ICD_ATT_BWD_SPLIT_ALL_ROWS;
     if (split_e && split_e[0] == '2' && P >= 32) n_split = rows;
+    else if (split_env && P >= 32 && rows <= few_rows) n_split = rows;
     else if (split_env && P >= 32) {
         const int rem = rows % ICD_NUM_SMS;                 // rows beyond an equal number per SM
         if (rem) n_split = ICD_NUM_SMS - rem;               // e.g. 512 rows: 80 split rows -> 432 + 160 CTAs = 4 per SM

@@ -234,6 +234,7 @@ class _AttentionDecoderFn(torch.autograd.Function):
     def forward(ctx, enc, captions, emb_w, *rest):
         weights = rest[:18]
         bt, mask, drop_scale, precision, sink = rest[18:]
+        _lib.remember_versions(ctx, list(zip(_W_NAMES, weights)) + [("embedding.weight", emb_w), ("encoder_out", enc)])
         ctx.sink = sink                  # DataParallelClipAdam in overlap mode: gradients go straight into its flat buffer
         if not enc.is_cuda:
             raise _lib.IcdError("AttentionDecoder.forward needs CUDA tensors; there is no CPU fallback")
@@ -309,6 +310,7 @@ class _AttentionDecoderFn(torch.autograd.Function):
         if ctx.keep is None:
             raise RuntimeError("icd_b200: AttentionDecoder backward called a second time; its saved activations were "
                                "released after the first backward (like autograd's saved tensors without retain_graph)")
+        _lib.check_versions(ctx, "AttentionDecoder")
         enc, captions, emb_w, weights, mask, bufs = ctx.keep
         dev = enc.device
         f32 = dict(device=dev, dtype=torch.float32)

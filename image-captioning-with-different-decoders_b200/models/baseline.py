@@ -60,6 +60,9 @@ class _BaselineDecoderFn(torch.autograd.Function):
         if not img.is_cuda:
             raise _lib.IcdError("BaselineDecoder.forward needs CUDA tensors; there is no CPU fallback")
         dev = img.device
+        _lib.remember_versions(ctx, [("embedding.weight", emb_w), ("lstm.weight_ih_l0", w_ih), ("lstm.weight_hh_l0", w_hh),
+                                     ("lstm.bias_ih_l0", b_ih), ("lstm.bias_hh_l0", b_hh), ("linear.weight", lin_w),
+                                     ("linear.bias", lin_b), ("img_features", img)])
         img = img.contiguous().float()                                               # :101 .float()
         captions = captions.contiguous()
         assert captions.dtype == torch.int64
@@ -95,6 +98,7 @@ class _BaselineDecoderFn(torch.autograd.Function):
         if ctx.keep is None:
             raise RuntimeError("icd_b200: BaselineDecoder backward called a second time; its saved activations were "
                                "released after the first backward")
+        _lib.check_versions(ctx, "BaselineDecoder")
         img, captions, emb_w, ws, bufs = ctx.keep
         dev = img.device
         f32 = dict(device=dev, dtype=torch.float32)

@@ -829,6 +829,40 @@ def test_lstm_gate_adjoint_vectorised_kernel_is_bit_identical_to_scalar(cuda, pr
 
 
 @pytest.mark.gpu
+def test_in_place_weight_update_between_forward_and_backward_raises(cuda):
+    """The decoders' autograd Functions read the weights through raw pointers in the backward; like autograd's saved-tensor check
+    they must refuse a backward when a parameter was modified in place after the forward (the reference, built from nn modules,
+    raises "modified by an inplace operation" in the same situation) — and run normally when nothing was touched."""
+    import icd_b200.models.attention as my_att
+    import icd_b200.models.baseline as my_base
+    from icd_b200.vocabulary import synthetic_vocab
+    case = H.ATT_CASES["att_small_ragged"]
+    dec = H.build_attention_module(case, my_att.AttentionDecoder, my_att.AttentionDecoderParams, synthetic_vocab(case["V"])).to(cuda)
+    enc, caps, lens = H.att_inputs(case)
+    preds, cs, dl, alphas = dec(enc.to(cuda), caps.to(cuda), lens)
+    loss = O.attention_loss(preds, caps.to(cuda), dl, alphas)
+    with torch.no_grad():
+        dec.fc.weight.mul_(1.0)
+    with pytest.raises(RuntimeError, match="modified by an in-place operation"):
+        loss.backward()
+    dec.zero_grad()
+    preds, cs, dl, alphas = dec(enc.to(cuda), caps.to(cuda), lens)
+    O.attention_loss(preds, caps.to(cuda), dl, alphas).backward()
+    assert dec.fc.weight.grad is not None and torch.isfinite(dec.fc.weight.grad).all()
+    p = my_base.BaselineDecoderParams()
+    p.vocab_size, p.embed_size, p.hidden_size = 50, 16, 16
+    torch.manual_seed(0)
+    base = my_base.BaselineDecoder(p).to(cuda)
+    img = torch.randn(3, 16, device=cuda)
+    bcaps = torch.randint(1, 47, (3, 7), device=cuda)
+    out = base(img, bcaps)
+    with torch.no_grad():
+        base.lstm.weight_hh_l0.add_(0.0)
+    with pytest.raises(RuntimeError, match="modified by an in-place operation"):
+        out.sum().backward()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("ties", ["none", "groups", "all_equal"])
 def test_beam_topk_filtered_pass_equals_streaming_pass(cuda, ties, monkeypatch):
     """The top-k kernel of the beam search keeps a row in registers and offers only the logits >= tau (a lower bound of the row's

@@ -316,6 +316,45 @@ def test_attention_step_bf16_features_matches_oracle_on_rounded_features(cuda, R
     assert torch.equal(z_ref[2], z_spl[2]) and torch.isfinite(z_spl[2]).all()
 
 
+@pytest.mark.parametrize("R,P,A,Cdim,use_index", [(5, 196, 512, 2048, False), (7, 196, 512, 2048, True), (3, 50, 64, 264, False),
+                                                  (150, 196, 64, 512, False), (300, 37, 48, 256, False)])
+def test_attention_step_fwd_bf16_rows_shared_by_2_or_4_ctas_is_bit_identical(cuda, R, P, A, Cdim, use_index):
+    """Few rows per launch: a row is shared by 2 / 4 CTAs (channel split, att_step_fwd_bf16_split_kernel).  Every output
+    element is formed by the same operations in the same order as in the whole-row kernel, so all five outputs must be
+    bit-identical under ICD_ATT_FWD_SPLIT = 1 / 2 / 4 and under the row-count rule (R = 5: four CTAs per row,
+    R = 150: two, R = 300: one); pixel counts with and without an unrolled remainder, C / 4 not a multiple of the block."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(R * 7 + P)
+    n_img = 4 if use_index else R
+    enc16 = torch.randn(n_img, P, Cdim, generator=g).clamp_min_(0).bfloat16().to(cuda)
+    att_enc16 = (torch.randn(n_img, P, A, generator=g) * 0.5).bfloat16().to(cuda)
+    att_dec = (torch.randn(R, A, generator=g) * 0.5).to(cuda)
+    wf = (torch.randn(A, generator=g) * 0.2).to(cuda)
+    bf = torch.randn(1, generator=g).to(cuda)
+    fb = torch.randn(R, Cdim, generator=g).to(cuda)
+    idx = torch.randint(0, n_img, (R,), generator=g).to(torch.int32).to(cuda) if use_index else None
+    outs = {}
+    for mode in ("1", "2", "4", None):
+        if mode is None:
+            os.environ.pop("ICD_ATT_FWD_SPLIT", None)
+        else:
+            os.environ["ICD_ATT_FWD_SPLIT"] = mode
+        try:
+            outs[mode] = ops.attention_step_fwd_bf16(enc16, att_enc16, att_dec, wf, bf, fb, idx)
+        finally:
+            os.environ.pop("ICD_ATT_FWD_SPLIT", None)
+    for mode in ("2", "4", None):
+        for name, a, b in zip(("alpha", "awe", "gate", "gated", "gated16"), outs["1"], outs[mode]):
+            assert torch.equal(a, b), "%s differs between the whole-row kernel and ICD_ATT_FWD_SPLIT=%s" % (name, mode)
+    # ... and without the gate inputs (SoftAttention.forward on its own): alpha + awe only
+    os.environ["ICD_ATT_FWD_SPLIT"] = "4"
+    try:
+        a4 = ops.attention_step_fwd_bf16(enc16, att_enc16, att_dec, wf, bf, None, idx)
+    finally:
+        os.environ.pop("ICD_ATT_FWD_SPLIT", None)
+    assert torch.equal(a4[0], outs["1"][0]) and torch.equal(a4[1], outs["1"][1])
+
+
 @pytest.fixture(params=[2, 1, 0], ids=["cta_group2_pairs", "multicast_pairs", "single_cta"])
 def pair_mode(request):
     """Run under every tile-pairing mode of the tensor-core contraction (icd_gemm_set_pair_mode)."""

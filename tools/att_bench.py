@@ -20,6 +20,48 @@ att_dec = torch.randn(B, A, device=dev) * 0.5
 wf = torch.randn(A, device=dev) * 0.2
 bf = torch.zeros(1, device=dev)
 fb = torch.randn(B, C, device=dev)
+FEW = "--few-rows" in sys.argv      # rows-per-launch sweep under the row-sharing variants (ICD_ATT_FWD_SPLIT / ICD_ATT_BWD_SPLIT)
+
+
+def timed(fn, los, reps=10, warm=2):
+    for _ in range(warm):
+        for lo in los:
+            fn(lo)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        for lo in los:
+            fn(lo)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (reps * len(los))
+
+
+if FEW:
+    alpha, awe, gate, gated, gated16 = ops.attention_step_fwd_bf16(enc16, att16, att_dec, wf, bf, fb)
+    d_gated = torch.randn(B, C, device=dev)
+    print("rows | fwd us: 1 CTA/row, 2, 4 | bwd us: whole rows, balance rule, 2 CTAs/row")
+    for rows in (16, 32, 64, 100, 148, 200, 256, 296, 350, 400, 444, 512):
+        los = [lo for lo in range(0, B, rows) if lo + rows <= B]
+        out = []
+        for mode in ("1", "2", "4"):
+            os.environ["ICD_ATT_FWD_SPLIT"] = mode
+            out.append(timed(lambda lo: ops.attention_step_fwd_bf16(enc16[lo:lo + rows], att16[lo:lo + rows], att_dec[lo:lo + rows],
+                                                                    wf, bf, fb[lo:lo + rows]), los))
+        os.environ.pop("ICD_ATT_FWD_SPLIT", None)
+        for mode in ("0", None, "2"):
+            if mode is None:
+                os.environ.pop("ICD_ATT_BWD_SPLIT", None)
+            else:
+                os.environ["ICD_ATT_BWD_SPLIT"] = mode
+            out.append(timed(lambda lo: ops.attention_step_bwd_bf16(enc16[lo:lo + rows], att16[lo:lo + rows], att_dec[lo:lo + rows], wf,
+                                                                    alpha[lo:lo + rows], gate[lo:lo + rows], awe[lo:lo + rows],
+                                                                    d_gated[lo:lo + rows], None), los))
+        os.environ.pop("ICD_ATT_BWD_SPLIT", None)
+        print("%4d | %6.1f %6.1f %6.1f | %6.1f %6.1f %6.1f" % (rows, *out), flush=True)
+    sys.exit(0)
+
 for rows in (592, 574, 512, 444, 296, 256, 148):
     def run(lo):
         return ops.attention_step_fwd_bf16(enc16[lo:lo + rows], att16[lo:lo + rows], att_dec[lo:lo + rows], wf, bf, fb[lo:lo + rows])
