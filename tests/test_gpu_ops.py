@@ -355,6 +355,37 @@ def test_attention_step_fwd_bf16_rows_shared_by_2_or_4_ctas_is_bit_identical(cud
     assert torch.equal(a4[0], outs["1"][0]) and torch.equal(a4[1], outs["1"][1])
 
 
+@pytest.mark.parametrize("R", [20, 150, 300, 320, 470, 512])
+def test_attention_step_bwd_bf16_row_sharing_rules_match_whole_rows(cuda, R):
+    """The backward launcher's rules — every row as two half-row CTAs at few rows (R = 20, 150), the minimal balance form (R = 300,
+    320, 470: only the rows beyond an equal number per SM), the full balance form (R = 512) — against the plain one-CTA-per-row
+    launch (ICD_ATT_BWD_SPLIT=0): the channel-wise outputs are bit-identical, the pixel-split sums agree to fp32 rounding."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(R)
+    P, A, Cdim = 196, 64, 256
+    enc16 = torch.randn(R, P, Cdim, generator=g).clamp_min_(0).bfloat16().to(cuda)
+    att_enc16 = (torch.randn(R, P, A, generator=g) * 0.5).bfloat16().to(cuda)
+    att_dec = (torch.randn(R, A, generator=g) * 0.5).to(cuda)
+    wf = (torch.randn(A, generator=g) * 0.2).to(cuda)
+    bf = torch.randn(1, generator=g).to(cuda)
+    fb = torch.randn(R, Cdim, generator=g).to(cuda)
+    d_gated = torch.randn(R, Cdim, generator=g).to(cuda)
+    d_alpha = torch.randn(R, P, generator=g).to(cuda)
+    alpha, awe, gate, gated, gated16 = ops.attention_step_fwd_bf16(enc16, att_enc16, att_dec, wf, bf, fb)
+    os.environ["ICD_ATT_BWD_SPLIT"] = "0"
+    try:
+        w_att_dec, w_fb, w_e, w_dz16 = ops.attention_step_bwd_bf16(enc16, att_enc16, att_dec, wf, alpha, gate, awe, d_gated, d_alpha)
+    finally:
+        del os.environ["ICD_ATT_BWD_SPLIT"]
+    s_att_dec, s_fb, s_e, s_dz16 = ops.attention_step_bwd_bf16(enc16, att_enc16, att_dec, wf, alpha, gate, awe, d_gated, d_alpha)
+    assert torch.equal(s_fb, w_fb) and torch.equal(s_dz16[:, A:], w_dz16[:, A:])
+    H.assert_close_norm(s_att_dec, w_att_dec, 2e-5, "d_att_dec")
+    H.assert_close_norm(s_e, w_e, 1e-5, "d_e")
+    H.assert_close_norm(s_dz16[:, :A].float(), w_att_dec, 4e-3, "dz16[:, :A]")
+    if R in (20, 150, 300, 512):         # (the rules must actually have taken the shared form: some row differs in the last bits)
+        assert not (torch.equal(s_att_dec, w_att_dec) and torch.equal(s_e, w_e))
+
+
 @pytest.fixture(params=[2, 1, 0], ids=["cta_group2_pairs", "multicast_pairs", "single_cta"])
 def pair_mode(request):
     """Run under every tile-pairing mode of the tensor-core contraction (icd_gemm_set_pair_mode)."""

@@ -42,7 +42,7 @@ if FEW:
     alpha, awe, gate, gated, gated16 = ops.attention_step_fwd_bf16(enc16, att16, att_dec, wf, bf, fb)
     d_gated = torch.randn(B, C, device=dev)
     print("rows | fwd us: 1 CTA/row, 2, 4 | bwd us: whole rows, balance rule, 2 CTAs/row")
-    for rows in (16, 32, 64, 100, 148, 200, 256, 296, 350, 400, 444, 512):
+    for rows in (16, 32, 64, 100, 148, 200, 222, 256, 296, 298, 320, 338, 370, 400, 444, 468, 480, 512):
         los = [lo for lo in range(0, B, rows) if lo + rows <= B]
         out = []
         for mode in ("1", "2", "4"):
