@@ -54,41 +54,52 @@ constexpr int ICD_ATT_BWD_SPLIT_ALL_ROWS = 222;  // 32 rows 43 -> 34 us, 148 row
 
 // phases 1 + 2 of the forward step for ONE row: scores e_p = w_full . relu(att_enc[p, :] + att_dec) + b_full over the row's pixels
 // (att_enc streamed once), softmax over the pixels; alpha is left in s_e and, when `out` is given, written to global memory.
-template <bool HAS_OUT>     // true: `out` is known to be non-null (no test in the whole-row kernel)
+template <bool HAS_OUT,      // true: `out` is known to be non-null (no test in the whole-row kernel)
+          int ROWS = FW16_ROWS, int JU = 1>   // pixel rows per warp iteration x 16-byte chunks per lane in flight (the few-rows kernels, which
+                                              // have the register file of an SM almost to themselves, keep 16 loads in flight per lane)
 __device__ __forceinline__ void fwd16_scores_softmax(int P, int A, const __nv_bfloat16* ae,
                                                      const float* b_full, float* s_dec, float* s_wf, float* s_e,
                                                      float* s_red, float* out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const float bfull = b_full ? b_full[0] : 0.f;
     const int A8 = A >> 3;
-    // phase 1: scores; FW16_ROWS pixel rows per warp iteration, 16 B per lane per row chunk
-    for (int p0 = warp; p0 < P; p0 += FW16_ROWS * nwarp) {
-        float acc[FW16_ROWS];
+    // phase 1: scores; ROWS pixel rows per warp iteration, 16 B per lane per row chunk
+    for (int p0 = warp; p0 < P; p0 += ROWS * nwarp) {
+        float acc[ROWS];
 #pragma unroll
-        for (int u = 0; u < FW16_ROWS; ++u) acc[u] = 0.f;
-        for (int j = lane; j < A8; j += 32) {
-            uint4 x[FW16_ROWS];
+        for (int u = 0; u < ROWS; ++u) acc[u] = 0.f;
+        for (int j0 = lane; j0 < A8; j0 += 32 * JU) {
+            uint4 x[JU][ROWS];
 #pragma unroll
-            for (int u = 0; u < FW16_ROWS; ++u) {
-                const int p = p0 + u * nwarp;                     // warp-uniform: rows past P are not loaded at all
-                x[u] = (p < P) ? ld_stream_u4(ae + (long long)p * A + 8 * j) : make_uint4(0u, 0u, 0u, 0u);
+            for (int ju = 0; ju < JU; ++ju) {
+                const int j = j0 + 32 * ju;
+#pragma unroll
+                for (int u = 0; u < ROWS; ++u) {
+                    const int p = p0 + u * nwarp;                 // warp-uniform: rows past P are not loaded at all
+                    x[ju][u] = (p < P && (JU == 1 || j < A8)) ? ld_stream_u4(ae + (long long)p * A + 8 * j) : make_uint4(0u, 0u, 0u, 0u);
+                }
             }
-            const float4 d0 = *reinterpret_cast<const float4*>(s_dec + 8 * j);
-            const float4 d1 = *reinterpret_cast<const float4*>(s_dec + 8 * j + 4);
-            const float4 w0 = *reinterpret_cast<const float4*>(s_wf + 8 * j);
-            const float4 w1 = *reinterpret_cast<const float4*>(s_wf + 8 * j + 4);
-            const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-            const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-            for (int u = 0; u < FW16_ROWS; ++u) {
-                float f[8];
-                unpack8(x[u], f);
+            for (int ju = 0; ju < JU; ++ju) {
+                const int j = j0 + 32 * ju;
+                if (JU > 1 && j >= A8) break;                     // (the chunks of a lane are added in the same order for every JU)
+                const float4 d0 = *reinterpret_cast<const float4*>(s_dec + 8 * j);
+                const float4 d1 = *reinterpret_cast<const float4*>(s_dec + 8 * j + 4);
+                const float4 w0 = *reinterpret_cast<const float4*>(s_wf + 8 * j);
+                const float4 w1 = *reinterpret_cast<const float4*>(s_wf + 8 * j + 4);
+                const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+                const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[u] = fmaf(fmaxf(f[i] + dd[i], 0.f), ww[i], acc[u]);
+                for (int u = 0; u < ROWS; ++u) {
+                    float f[8];
+                    unpack8(x[ju][u], f);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[u] = fmaf(fmaxf(f[i] + dd[i], 0.f), ww[i], acc[u]);
+                }
             }
         }
 #pragma unroll
-        for (int u = 0; u < FW16_ROWS; ++u) {
+        for (int u = 0; u < ROWS; ++u) {
             const float v = warp_sum(acc[u]);
             const int p = p0 + u * nwarp;
             if (lane == 0 && p < P) s_e[p] = v + bfull;
@@ -219,8 +230,9 @@ template <> struct StreamChunk<2> {
     }
 };
 
-template <int CH>
-__global__ void __launch_bounds__(256, 4) att_step_fwd_bf16_split_kernel(
+template <int CH, bool DEEP>   // DEEP (at most two CTAs per SM: <= 148 rows shared by two, <= 48 by four): 128 registers, 16 score-phase loads
+                               // per lane in flight instead of 4 — a launch of few rows is bound by the chain of dependent load batches
+__global__ void __launch_bounds__(256, DEEP ? 2 : 4) att_step_fwd_bf16_split_kernel(
         int P, int C, int A, const int* __restrict__ img_index,
         const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* __restrict__ att_enc,
         const float* __restrict__ att_dec, long long ld_dec,
@@ -244,7 +256,8 @@ __global__ void __launch_bounds__(256, 4) att_step_fwd_bf16_split_kernel(
     const float* dec = att_dec + (long long)r * ld_dec;
     for (int a = threadIdx.x; a < A; a += blockDim.x) { s_dec[a] = dec[a]; s_wf[a] = w_full[a]; }
     __syncthreads();
-    fwd16_scores_softmax<false>(P, A, ae, b_full, s_dec, s_wf, s_e, s_red, part == 0 ? alpha + (long long)r * ld_alpha : nullptr);
+    fwd16_scores_softmax<false, DEEP ? 8 : FW16_ROWS, DEEP ? 2 : 1>(P, A, ae, b_full, s_dec, s_wf, s_e, s_red,
+                                                                     part == 0 ? alpha + (long long)r * ld_alpha : nullptr);
     // phase 3: this CTA's channel range, CH channels per thread
     const __nv_bfloat16* eb = enc + (long long)img * P * C;
     const int cw = C / S;                                         // C % 8 == 0: cw is a multiple of CH
@@ -266,14 +279,31 @@ __global__ void __launch_bounds__(256, 4) att_step_fwd_bf16_split_kernel(
                 for (int i = 0; i < CH; ++i) acc[i] = fmaf(al, f[i], acc[i]);
             }
         }
-        for (; p < P; ++p) {
-            StreamChunk<CH> x;
-            x.load(eb + (long long)p * C + c);
-            const float al = s_e[p];
-            float f[CH];
-            x.unpack(f);
+        if (!DEEP) {                                              // (at 64 registers a second batched block costs the main loop its batching)
+            for (; p < P; ++p) {
+                StreamChunk<CH> x;
+                x.load(eb + (long long)p * C + c);
+                const float al = s_e[p];
+                float f[CH];
+                x.unpack(f);
 #pragma unroll
-            for (int i = 0; i < CH; ++i) acc[i] = fmaf(al, f[i], acc[i]);
+                for (int i = 0; i < CH; ++i) acc[i] = fmaf(al, f[i], acc[i]);
+            }
+        } else if (p < P) {                                       // the remaining pixel rows as ONE batch of loads (not one round trip each)
+            StreamChunk<CH> x[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u)
+                if (p + u < P) x[u].load(eb + (long long)(p + u) * C + c);
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                if (p + u < P) {
+                    const float al = s_e[p + u];
+                    float f[CH];
+                    x[u].unpack(f);
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) acc[i] = fmaf(al, f[i], acc[i]);
+                }
+            }
         }
         const long long o = (long long)r * C + c;
         if (awe_raw) {
@@ -923,10 +953,14 @@ extern "C" int icd_attention_step_fwd_bf16(int rows, int P, int C, int A, const 
 #define ICD_FWD16_ARGS P, C, A, (const int*)img_index, reinterpret_cast<const __nv_bfloat16*>(enc16),                      \
                        reinterpret_cast<const __nv_bfloat16*>(att_enc16), att_dec, (long long)ld_dec, w_full, b_full, fbeta_pre, \
                        (long long)ld_fb, alpha, (long long)ld_alpha, awe_raw, gate, gated, reinterpret_cast<__nv_bfloat16*>(gated16)
-    if (nsplit == 4)
-        ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_FWD, att_step_fwd_bf16_split_kernel<2>, dim3(rows * 4), dim3(256), smem, s, ICD_FWD16_ARGS));
+    if (nsplit == 4 && rows * 4 <= 2 * ICD_NUM_SMS)
+        ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_FWD, att_step_fwd_bf16_split_kernel<2, true>, dim3(rows * 4), dim3(256), smem, s, ICD_FWD16_ARGS));
+    else if (nsplit == 4)
+        ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_FWD, att_step_fwd_bf16_split_kernel<2, false>, dim3(rows * 4), dim3(256), smem, s, ICD_FWD16_ARGS));
+    else if (nsplit == 2 && rows * 2 <= 2 * ICD_NUM_SMS)
+        ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_FWD, att_step_fwd_bf16_split_kernel<4, true>, dim3(rows * 2), dim3(256), smem, s, ICD_FWD16_ARGS));
     else if (nsplit == 2)
-        ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_FWD, att_step_fwd_bf16_split_kernel<4>, dim3(rows * 2), dim3(256), smem, s, ICD_FWD16_ARGS));
+        ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_FWD, att_step_fwd_bf16_split_kernel<4, false>, dim3(rows * 2), dim3(256), smem, s, ICD_FWD16_ARGS));
     else
         ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_FWD, att_step_fwd_bf16_kernel, dim3(rows), dim3(256), smem, s, ICD_FWD16_ARGS));
 #undef ICD_FWD16_ARGS

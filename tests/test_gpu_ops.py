@@ -316,7 +316,7 @@ def test_attention_step_bf16_features_matches_oracle_on_rounded_features(cuda, R
     assert torch.equal(z_ref[2], z_spl[2]) and torch.isfinite(z_spl[2]).all()
 
 
-@pytest.mark.parametrize("R,P,A,Cdim,use_index", [(5, 196, 512, 2048, False), (7, 196, 512, 2048, True), (3, 50, 64, 264, False),
+@pytest.mark.parametrize("R,P,A,Cdim,use_index", [(5, 196, 512, 2048, False), (7, 196, 512, 2048, True), (3, 50, 64, 264, False), (100, 196, 512, 2048, False), (9, 61, 328, 520, False),
                                                   (150, 196, 64, 512, False), (300, 37, 48, 256, False)])
 def test_attention_step_fwd_bf16_rows_shared_by_2_or_4_ctas_is_bit_identical(cuda, R, P, A, Cdim, use_index):
     """Few rows per launch: a row is shared by 2 / 4 CTAs (channel split, att_step_fwd_bf16_split_kernel).  Every output
