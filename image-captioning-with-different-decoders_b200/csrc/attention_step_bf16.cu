@@ -347,7 +347,10 @@ __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
+template <bool DEEP>     // DEEP (launches of at most two CTAs per SM: few rows, every row shared by two CTAs): 128 registers, twice the loads
+                         // in flight in the two streaming phases — such a launch is bound by its chain of dependent load batches.
+                         // Same operations in the same order as the 64-register instantiation: bit-identical (tested).
+__global__ void __launch_bounds__(256, DEEP ? 2 : 4) att_step_bwd_bf16_kernel(
         int P, int C, int A,
         const __nv_bfloat16* __restrict__ enc, const __nv_bfloat16* __restrict__ att_enc,
         const float* __restrict__ att_dec, long long ld_dec, const float* __restrict__ w_full,
@@ -443,17 +446,18 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
             const __nv_bfloat16* rowA = eb + (long long)min(p0, P - 1) * C;
             const __nv_bfloat16* rowB = eb + (long long)min(p1, P - 1) * C;
             float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-            for (int nb0 = 0; nb0 < NB; nb0 += 4) {
-                uint4 xa[4], xb[4];
+            constexpr int UB = DEEP ? 8 : 4;
+            for (int nb0 = 0; nb0 < NB; nb0 += UB) {
+                uint4 xa[UB], xb[UB];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < UB; ++u) {
                     if (nb0 + u < NB) {                           // rows past P (last pixel block) are zero, not re-read
                         xa[u] = (p0 < P) ? ld_stream_u4(rowA + 32 * (nb0 + u)) : make_uint4(0u, 0u, 0u, 0u);
                         xb[u] = (p1 < P) ? ld_stream_u4(rowB + 32 * (nb0 + u)) : make_uint4(0u, 0u, 0u, 0u);
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < UB; ++u) {
                     if (nb0 + u < NB) {
                         uint4 bq = make_uint4(0u, 0u, 0u, 0u);
                         if (g < 3) bq = *reinterpret_cast<const uint4*>(bsrc + 32 * (nb0 + u));
@@ -555,17 +559,21 @@ __global__ void __launch_bounds__(256, 4) att_step_bwd_bf16_kernel(
                 const float4 d1 = *reinterpret_cast<const float4*>(s_dec + 8 * j + 4);
                 const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
                 int p = p_lo + grp;
-                for (; p + 6 * 4 < p_hi; p += 7 * 4) {
-                    uint4 x[7];
+                constexpr int UD = DEEP ? 13 : 7;                 // (a half row = 24-25 pixels per group: two batches of <= 13)
+                for (; DEEP ? (p < p_hi) : (p + (UD - 1) * 4 < p_hi); p += UD * 4) {
+                    uint4 x[UD];
 #pragma unroll
-                    for (int u = 0; u < 7; ++u) x[u] = ld_stream_u4(ab + (long long)(p + 4 * u) * A + 8 * j);
+                    for (int u = 0; u < UD; ++u)
+                        if (!DEEP || p + 4 * u < p_hi) x[u] = ld_stream_u4(ab + (long long)(p + 4 * u) * A + 8 * j);
 #pragma unroll
-                    for (int u = 0; u < 7; ++u) {
-                        const float de = s_de[p + 4 * u];
-                        float f[8];
-                        unpack8(x[u], f);
+                    for (int u = 0; u < UD; ++u) {
+                        if (!DEEP || p + 4 * u < p_hi) {
+                            const float de = s_de[p + 4 * u];
+                            float f[8];
+                            unpack8(x[u], f);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[i] += (f[i] + dd[i] > 0.f) ? de : 0.f;
+                            for (int i = 0; i < 8; ++i) acc[i] += (f[i] + dd[i] > 0.f) ? de : 0.f;
+                        }
                     }
                 }
                 for (; p < p_hi; p += 4) {
@@ -991,7 +999,8 @@ extern "C" int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
     ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_bwd_bf16: dims too large for shared memory");
     static size_t configured = 48 * 1024;
     if (smem > configured) {
-        ICD_CUDA(cudaFuncSetAttribute(att_step_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ICD_CUDA(cudaFuncSetAttribute(att_step_bwd_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ICD_CUDA(cudaFuncSetAttribute(att_step_bwd_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     // row balance (see the kernel): with up to 4 CTAs on each of the 148 SMs, a launch of `rows` CTAs whose last wave is partly
@@ -1016,20 +1025,29 @@ extern "C" int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
         if (n_split < 0 || n_split > rows) n_split = 0;
     }
     icd_prof_mark_begin(1, rows, s);
-    if (n_split > 0)
-        ICD_CUDA(icd_launch_pdl_cluster(ICD_PDL_ATT_BWD, att_step_bwd_bf16_kernel, dim3(rows + n_split), dim3(256), smem, s, 2u, P, C, A,
+#define ICD_BWD16_ARGS P, C, A, reinterpret_cast<const __nv_bfloat16*>(enc16), reinterpret_cast<const __nv_bfloat16*>(att_enc16),           \
+                       att_dec, (long long)ld_dec, w_full, alpha, (long long)ld_alpha, d_alpha_ext, (long long)ld_dalpha,                   \
+                       gate, awe_raw, d_gated, d_att_dec, (long long)ld_ddec, d_fbeta_pre, (long long)ld_dfb,                               \
+                       d_e, (long long)ld_de, reinterpret_cast<__nv_bfloat16*>(dz16), (long long)ld_dz16, d_awe_out, use_mma
+    const char* deep_e = getenv("ICD_ATT_BWD_DEEP");         // 0: never the 128-register instantiation (A/B and test hook)
+    if (n_split == rows && 2 * rows <= 2 * ICD_NUM_SMS && smem <= 100 * 1024 && !(deep_e && deep_e[0] == '0'))
+        ICD_CUDA(icd_launch_pdl_cluster(ICD_PDL_ATT_BWD, att_step_bwd_bf16_kernel<true>, dim3(2 * rows), dim3(256), smem, s, 2u,
+                                        ICD_BWD16_ARGS, 0));
+    else if (n_split > 0)
+        ICD_CUDA(icd_launch_pdl_cluster(ICD_PDL_ATT_BWD, att_step_bwd_bf16_kernel<false>, dim3(rows + n_split), dim3(256), smem, s, 2u, P, C, A,
                             reinterpret_cast<const __nv_bfloat16*>(enc16), reinterpret_cast<const __nv_bfloat16*>(att_enc16),
                             att_dec, (long long)ld_dec, w_full, alpha, (long long)ld_alpha, d_alpha_ext, (long long)ld_dalpha,
                             gate, awe_raw, d_gated, d_att_dec, (long long)ld_ddec, d_fbeta_pre, (long long)ld_dfb,
                             d_e, (long long)ld_de, reinterpret_cast<__nv_bfloat16*>(dz16), (long long)ld_dz16, d_awe_out,
                             use_mma, rows - n_split));
     else
-        ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_BWD, att_step_bwd_bf16_kernel, dim3(rows), dim3(256), smem, s, P, C, A,
+        ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_BWD, att_step_bwd_bf16_kernel<false>, dim3(rows), dim3(256), smem, s, P, C, A,
                             reinterpret_cast<const __nv_bfloat16*>(enc16), reinterpret_cast<const __nv_bfloat16*>(att_enc16),
                             att_dec, (long long)ld_dec, w_full, alpha, (long long)ld_alpha, d_alpha_ext, (long long)ld_dalpha,
                             gate, awe_raw, d_gated, d_att_dec, (long long)ld_ddec, d_fbeta_pre, (long long)ld_dfb,
                             d_e, (long long)ld_de, reinterpret_cast<__nv_bfloat16*>(dz16), (long long)ld_dz16, d_awe_out,
                             use_mma, -1));
+#undef ICD_BWD16_ARGS
     icd_prof_mark_end(1, s);
     ICD_LAUNCH_CHECK();
     return 0;

@@ -386,6 +386,33 @@ def test_attention_step_bwd_bf16_row_sharing_rules_match_whole_rows(cuda, R):
         assert not (torch.equal(s_att_dec, w_att_dec) and torch.equal(s_e, w_e))
 
 
+@pytest.mark.parametrize("R,P,A,Cdim", [(40, 196, 512, 2048), (20, 196, 64, 256), (7, 61, 328, 512), (148, 50, 64, 256)])
+def test_attention_step_bwd_bf16_128_register_instantiation_is_bit_identical(cuda, R, P, A, Cdim):
+    """Launches of at most two CTAs per SM (<= 148 rows, every row as two half-row CTAs) use the 128-register instantiation of the
+    backward kernel (twice the loads in flight in both streaming phases, batched pixel remainder): same operations in the same
+    order, so all outputs must equal the 64-register instantiation's (ICD_ATT_BWD_DEEP=0) bit for bit."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(R + P)
+    enc16 = torch.randn(R, P, Cdim, generator=g).clamp_min_(0).bfloat16().to(cuda)
+    att_enc16 = (torch.randn(R, P, A, generator=g) * 0.5).bfloat16().to(cuda)
+    att_dec = (torch.randn(R, A, generator=g) * 0.5).to(cuda)
+    wf = (torch.randn(A, generator=g) * 0.2).to(cuda)
+    bf = torch.randn(1, generator=g).to(cuda)
+    fb = torch.randn(R, Cdim, generator=g).to(cuda)
+    d_gated = torch.randn(R, Cdim, generator=g).to(cuda)
+    d_alpha = torch.randn(R, P, generator=g).to(cuda)
+    alpha, awe, gate, gated, gated16 = ops.attention_step_fwd_bf16(enc16, att_enc16, att_dec, wf, bf, fb)
+    deep = ops.attention_step_bwd_bf16(enc16, att_enc16, att_dec, wf, alpha, gate, awe, d_gated, d_alpha)
+    os.environ["ICD_ATT_BWD_DEEP"] = "0"
+    try:
+        shallow = ops.attention_step_bwd_bf16(enc16, att_enc16, att_dec, wf, alpha, gate, awe, d_gated, d_alpha)
+    finally:
+        del os.environ["ICD_ATT_BWD_DEEP"]
+    for name, a, b in zip(("d_att_dec", "d_fbeta_pre", "d_e", "dz16"), deep, shallow):
+        assert torch.equal(a, b), name
+    assert torch.isfinite(deep[0]).all() and torch.isfinite(deep[2]).all()
+
+
 @pytest.fixture(params=[2, 1, 0], ids=["cta_group2_pairs", "multicast_pairs", "single_cta"])
 def pair_mode(request):
     """Run under every tile-pairing mode of the tensor-core contraction (icd_gemm_set_pair_mode)."""
