@@ -6,9 +6,11 @@ nvcc cross-compiles without a GPU.  The library is written next to this file so 
 repo snapshot to the GPU box (it is git-ignored, not gpurun-ignored).
 """
 import hashlib
+import json
 import os
 import subprocess
 import sys
+import time
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -41,7 +43,9 @@ def build(force=False, verbose=False):
     stamp_path = os.path.join(OBJ, "stamp.txt")
     stamp = _digest([os.path.join(CSRC, s) for s in srcs] + hdrs)
     if not force and os.path.exists(LIB) and os.path.exists(stamp_path) and open(stamp_path).read() == stamp:
+        _record(stamp, rebuilt=False, seconds=0.0)
         return LIB
+    t0 = time.time()
 
     def compile_one(src):
         obj = os.path.join(OBJ, src[:-3] + ".o")
@@ -61,7 +65,22 @@ def build(force=False, verbose=False):
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
     with open(stamp_path, "w") as f:
         f.write(stamp)
+    _record(stamp, rebuilt=True, seconds=time.time() - t0)
     return LIB
+
+
+def _record(stamp, rebuilt, seconds):
+    """build/last_build.json: what the last build() call did — compiled every source (and with which nvcc) or found the
+    library up to date with the digest of sources + headers + flags.  Evidence only; nothing reads it."""
+    try:
+        with open(LIB, "rb") as f:
+            lib_sha = hashlib.sha256(f.read()).hexdigest()
+        ver = subprocess.run([NVCC, "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-1] if rebuilt else None
+        with open(os.path.join(OBJ, "last_build.json"), "w") as f:
+            json.dump({"rebuilt_from_source": rebuilt, "seconds": round(seconds, 1), "sources": _sources(), "arch": ARCH, "flags": FLAGS,
+                       "nvcc": ver, "sources_digest": stamp, "lib_sha256": lib_sha, "unix_time": int(time.time())}, f, indent=1)
+    except OSError:
+        pass
 
 
 if __name__ == "__main__":
