@@ -931,6 +931,73 @@ __global__ void __launch_bounds__(256) feature_mean_bf16_kernel(int P, int C, co
 
 }  // namespace
 
+// ---- launch forms (pure host logic, also exported for the CPU tests: icd_attention_step_launch_plan_bf16) ---------------
+struct AttLaunchPlan {
+    int per_row;        // CTAs per row of the rows that are shared (1: none are)
+    int shared_rows;    // rows that run shared (forward: 0 or all; backward: the last n_split rows)
+    int grid;           // CTAs of the launch
+    int deep;           // 1: the 128-register instantiation (at most two CTAs per SM)
+};
+
+// forward: few rows per launch (ragged batches late in the caption, small batches) -> 2 or 4 CTAs per row (channel split, bit-identical
+// results) so that the launch still fills the CTA slots of the GPU.  ICD_ATT_FWD_SPLIT = 1 | 2 | 4 forces a variant (tests, tools).
+static AttLaunchPlan att_fwd16_plan(int rows, size_t smem) {
+    const char* fsplit_e = getenv("ICD_ATT_FWD_SPLIT");
+    const int split_env = fsplit_e ? atoi(fsplit_e) : 0;
+    int nsplit = split_env == 1 || split_env == 2 || split_env == 4 ? split_env
+                 : (rows <= ICD_ATT_FWD_SPLIT4_ROWS ? 4 : rows <= ICD_ATT_FWD_SPLIT2_ROWS ? 2 : 1);
+    if (smem > 48 * 1024) nsplit = 1;          // (only the whole-row kernel is configured for large shared memory)
+    AttLaunchPlan pl;
+    pl.per_row = nsplit;
+    pl.shared_rows = nsplit > 1 ? rows : 0;
+    pl.grid = rows * nsplit;
+    pl.deep = (nsplit > 1 && rows * nsplit <= 2 * ICD_NUM_SMS) ? 1 : 0;
+    return pl;
+}
+
+static AttLaunchPlan att_bwd16_plan(int rows, int P, size_t smem) {
+    // row balance (see the kernel): with up to 4 CTAs on each of the 148 SMs, a launch of `rows` CTAs whose last wave is partly
+    // filled runs its last n_split rows as two half-row CTAs each, so that every SM gets the same number of CTAs: rows + n_split = a
+    // multiple of the SM count.  Only when the rows are not already balanced and the split part stays a minority.
+    const char* split_e = getenv("ICD_ATT_BWD_SPLIT");     // 0: never, 2: every row (tests), else: the balance rule
+    const bool split_env = !split_e || split_e[0] != '0';
+    int n_split = 0;
+    // few rows per launch (ragged batches late in the caption, small batches): EVERY row as two half-row CTAs, twice the CTAs
+    // streaming.  ICD_ATT_BWD_SPLIT_ROWS overrides the row count at or below which that happens (tools/att_bench.py fits it).
+    const char* few_e = getenv("ICD_ATT_BWD_SPLIT_ROWS");
+    const int few_rows = few_e ? atoi(few_e) : ICD_ATT_BWD_SPLIT_ALL_ROWS;
+    if (split_e && split_e[0] == '2' && P >= 32) n_split = rows;
+    else if (split_env && P >= 32 && rows <= few_rows) n_split = rows;
+    else if (split_env && P >= 32) {
+        const int rem = rows % ICD_NUM_SMS;                 // rows beyond an equal number per SM
+        if (rem) n_split = ICD_NUM_SMS - rem;               // e.g. 512 rows: 80 split rows -> 432 + 160 CTAs = 4 per SM
+        // the split part must stay a minority; where it would not, the minimal form: only the `rem` rows beyond an equal number L per SM
+        // run as halves (2 rem <= 148 half-row CTAs), so that no SM carries more than L + 1/2 rows instead of L + 1 (320 rows: 69 -> 60 us)
+        if (n_split > rows / 4) n_split = (rem <= ICD_NUM_SMS / 2 && rows > ICD_NUM_SMS) ? rem : 0;
+        if ((rows - n_split) & 1) n_split += (n_split < rows) ? 1 : -1;          // the whole rows must pair up (2-CTA clusters)
+        if (n_split < 0 || n_split > rows) n_split = 0;
+    }
+    AttLaunchPlan pl;
+    pl.per_row = n_split > 0 ? 2 : 1;
+    pl.shared_rows = n_split;
+    pl.grid = rows + n_split;
+    const char* deep_e = getenv("ICD_ATT_BWD_DEEP");         // 0: never the 128-register instantiation (A/B and test hook)
+    pl.deep = (n_split == rows && rows > 0 && 2 * rows <= 2 * ICD_NUM_SMS && smem <= 100 * 1024 && !(deep_e && deep_e[0] == '0')) ? 1 : 0;
+    return pl;
+}
+
+static size_t att_fwd16_smem(int P, int A) { return (2 * (size_t)A + ((P + 3) & ~3) + 40) * sizeof(float); }
+static size_t att_bwd16_smem(int P, int C, int A) {
+    return ((size_t)C + 5 * (size_t)A + 2 * ((P + 3) & ~3) + 40 + 8 * (((P + 15) >> 4) << 4)) * sizeof(float) + 3 * (size_t)C * 2;
+}
+
+extern "C" int icd_attention_step_launch_plan_bf16(int direction, int rows, int P, int C, int A, int32_t* out4) {
+    ICD_CHECK_ARG(out4 && rows >= 0 && P > 0 && C > 0 && A > 0 && (direction == 0 || direction == 1), "attention_step_launch_plan_bf16: bad arguments");
+    const AttLaunchPlan pl = direction == 0 ? att_fwd16_plan(rows, att_fwd16_smem(P, A)) : att_bwd16_plan(rows, P, att_bwd16_smem(P, C, A));
+    out4[0] = pl.per_row; out4[1] = pl.shared_rows; out4[2] = pl.grid; out4[3] = pl.deep;
+    return 0;
+}
+
 extern "C" int icd_attention_step_fwd_bf16(int rows, int P, int C, int A, const int32_t* img_index,
                                            const void* enc16, const void* att_enc16,
                                            const float* att_dec, int64_t ld_dec,
@@ -943,29 +1010,24 @@ extern "C" int icd_attention_step_fwd_bf16(int rows, int P, int C, int A, const 
     ICD_CHECK_ARG(rows > 0 && P > 0, "attention_step_fwd_bf16: bad dims");
     ICD_CHECK_ARG(A % 8 == 0 && C % 8 == 0, "attention_step_fwd_bf16: A=%d and C=%d must be multiples of 8", A, C);
     ICD_CHECK_ARG(ld_dec % 4 == 0 && (!fbeta_pre || ld_fb % 4 == 0), "attention_step_fwd_bf16: row strides must be multiples of 4");
-    const size_t smem = (2 * (size_t)A + ((P + 3) & ~3) + 40) * sizeof(float);
+    const size_t smem = att_fwd16_smem(P, A);
     ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_fwd_bf16: A/P too large for shared memory");
     static size_t configured = 48 * 1024;
     if (smem > configured) {
         ICD_CUDA(cudaFuncSetAttribute(att_step_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    // few rows per launch (ragged batches late in the caption, small batches): 2 or 4 CTAs per row (channel split, bit-identical
-    // results) so that the launch still fills the CTA slots of the GPU.  ICD_ATT_FWD_SPLIT = 1 | 2 | 4 forces a variant (tests, tools).
-    const char* fsplit_e = getenv("ICD_ATT_FWD_SPLIT");
-    const int split_env = fsplit_e ? atoi(fsplit_e) : 0;
-    int nsplit = split_env == 1 || split_env == 2 || split_env == 4 ? split_env
-                 : (rows <= ICD_ATT_FWD_SPLIT4_ROWS ? 4 : rows <= ICD_ATT_FWD_SPLIT2_ROWS ? 2 : 1);
-    if (smem > 48 * 1024) nsplit = 1;          // (only the whole-row kernel is configured for large shared memory)
+    const AttLaunchPlan plan = att_fwd16_plan(rows, smem);
+    const int nsplit = plan.per_row;
     icd_prof_mark_begin(0, rows, s);
 #define ICD_FWD16_ARGS P, C, A, (const int*)img_index, reinterpret_cast<const __nv_bfloat16*>(enc16),                      \
                        reinterpret_cast<const __nv_bfloat16*>(att_enc16), att_dec, (long long)ld_dec, w_full, b_full, fbeta_pre, \
                        (long long)ld_fb, alpha, (long long)ld_alpha, awe_raw, gate, gated, reinterpret_cast<__nv_bfloat16*>(gated16)
-    if (nsplit == 4 && rows * 4 <= 2 * ICD_NUM_SMS)
+    if (nsplit == 4 && plan.deep)
         ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_FWD, att_step_fwd_bf16_split_kernel<2, true>, dim3(rows * 4), dim3(256), smem, s, ICD_FWD16_ARGS));
     else if (nsplit == 4)
         ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_FWD, att_step_fwd_bf16_split_kernel<2, false>, dim3(rows * 4), dim3(256), smem, s, ICD_FWD16_ARGS));
-    else if (nsplit == 2 && rows * 2 <= 2 * ICD_NUM_SMS)
+    else if (nsplit == 2 && plan.deep)
         ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_FWD, att_step_fwd_bf16_split_kernel<4, true>, dim3(rows * 2), dim3(256), smem, s, ICD_FWD16_ARGS));
     else if (nsplit == 2)
         ICD_CUDA(icd_launch_pdl(ICD_PDL_ATT_FWD, att_step_fwd_bf16_split_kernel<4, false>, dim3(rows * 2), dim3(256), smem, s, ICD_FWD16_ARGS));
@@ -994,8 +1056,7 @@ extern "C" int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
                   "attention_step_bwd_bf16: row strides misaligned");
     // tensor-core d_alpha path: 8 warps x channel strips of whole 32-channel blocks
     const int use_mma = (C % 256 == 0) ? 1 : 0;
-    const size_t smem = ((size_t)C + 5 * (size_t)A + 2 * ((P + 3) & ~3) + 40 + 8 * (((P + 15) >> 4) << 4)) * sizeof(float)
-                        + 3 * (size_t)C * 2;
+    const size_t smem = att_bwd16_smem(P, C, A);
     ICD_CHECK_ARG(smem <= 200 * 1024, "attention_step_bwd_bf16: dims too large for shared memory");
     static size_t configured = 48 * 1024;
     if (smem > configured) {
@@ -1003,34 +1064,14 @@ extern "C" int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
         ICD_CUDA(cudaFuncSetAttribute(att_step_bwd_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    // row balance (see the kernel): with up to 4 CTAs on each of the 148 SMs, a launch of `rows` CTAs whose last wave is partly
-    // filled runs its last n_split rows as two half-row CTAs each, so that every SM gets the same number of CTAs: rows + n_split = a
-    // multiple of the SM count.  Only when the rows are not already balanced and the split part stays a minority.
-    const char* split_e = getenv("ICD_ATT_BWD_SPLIT");     // 0: never, 2: every row (tests), else: the balance rule
-    const bool split_env = !split_e || split_e[0] != '0';
-    int n_split = 0;
-    // few rows per launch (ragged batches late in the caption, small batches): EVERY row as two half-row CTAs, twice the CTAs
-    // streaming.  ICD_ATT_BWD_SPLIT_ROWS overrides the row count at or below which that happens (tools/att_bench.py fits it).
-    const char* few_e = getenv("ICD_ATT_BWD_SPLIT_ROWS");
-    const int few_rows = few_e ? atoi(few_e) : ICD_ATT_BWD_SPLIT_ALL_ROWS;
-    if (split_e && split_e[0] == '2' && P >= 32) n_split = rows;
-    else if (split_env && P >= 32 && rows <= few_rows) n_split = rows;
-    else if (split_env && P >= 32) {
-        const int rem = rows % ICD_NUM_SMS;                 // rows beyond an equal number per SM
-        if (rem) n_split = ICD_NUM_SMS - rem;               // e.g. 512 rows: 80 split rows -> 432 + 160 CTAs = 4 per SM
-        // the split part must stay a minority; where it would not, the minimal form: only the `rem` rows beyond an equal number L per SM
-        // run as halves (2 rem <= 148 half-row CTAs), so that no SM carries more than L + 1/2 rows instead of L + 1 (320 rows: 69 -> 60 us)
-        if (n_split > rows / 4) n_split = (rem <= ICD_NUM_SMS / 2 && rows > ICD_NUM_SMS) ? rem : 0;
-        if ((rows - n_split) & 1) n_split += (n_split < rows) ? 1 : -1;          // the whole rows must pair up (2-CTA clusters)
-        if (n_split < 0 || n_split > rows) n_split = 0;
-    }
+    const AttLaunchPlan plan = att_bwd16_plan(rows, P, smem);
+    const int n_split = plan.shared_rows;
     icd_prof_mark_begin(1, rows, s);
 #define ICD_BWD16_ARGS P, C, A, reinterpret_cast<const __nv_bfloat16*>(enc16), reinterpret_cast<const __nv_bfloat16*>(att_enc16),           \
                        att_dec, (long long)ld_dec, w_full, alpha, (long long)ld_alpha, d_alpha_ext, (long long)ld_dalpha,                   \
                        gate, awe_raw, d_gated, d_att_dec, (long long)ld_ddec, d_fbeta_pre, (long long)ld_dfb,                               \
                        d_e, (long long)ld_de, reinterpret_cast<__nv_bfloat16*>(dz16), (long long)ld_dz16, d_awe_out, use_mma
-    const char* deep_e = getenv("ICD_ATT_BWD_DEEP");         // 0: never the 128-register instantiation (A/B and test hook)
-    if (n_split == rows && 2 * rows <= 2 * ICD_NUM_SMS && smem <= 100 * 1024 && !(deep_e && deep_e[0] == '0'))
+    if (plan.deep)
         ICD_CUDA(icd_launch_pdl_cluster(ICD_PDL_ATT_BWD, att_step_bwd_bf16_kernel<true>, dim3(2 * rows), dim3(256), smem, s, 2u,
                                         ICD_BWD16_ARGS, 0));
     else if (n_split > 0)

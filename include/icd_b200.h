@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define ICD_B200_ABI_VERSION 14
+#define ICD_B200_ABI_VERSION 15
 #define ICD_MAX_STEPS 256
 
 ICD_API int icd_version(void);                       /* ICD_B200_ABI_VERSION the library was built with */
@@ -205,6 +205,13 @@ ICD_API int icd_attention_step_bwd_bf16(int rows, int P, int C, int A,
                                 float* d_fbeta_pre, int64_t ld_dfb,
                                 float* d_e, int64_t ld_de,
                                 void* dz16, int64_t ld_dz16, float* d_awe_out, void* stream);
+/* Host-only (no GPU needed): the launch form the two entry points above choose for `rows` rows per launch — the shrinking
+ * batch_size_t of models/attention.py:261-265 and small batches ("few rows per launch" / "row balance").
+ * direction 0 = forward, 1 = backward.  out4[0] = CTAs per row of the rows that run shared (1: none), out4[1] = rows that run
+ * shared (forward: 0 or all; backward: the last n rows, as two half-row CTAs each), out4[2] = CTAs of the launch,
+ * out4[3] = 1 if the 128-register instantiation is used (at most two CTAs per SM).  The ICD_ATT_* environment overrides
+ *  are honoured. */
+ICD_API int icd_attention_step_launch_plan_bf16(int direction, int rows, int P, int C, int A, int32_t* out4);
 /* d_att_enc (fp32) and d_att_enc16 (bf16) are both optional outputs (at least one should be given) */
 ICD_API int icd_attention_proj_bwd_bf16(int B, int T, int P, int A, const int32_t* bt_host,
                                 const void* att_enc16, const float* att_dec_all, int64_t ld_dec,

@@ -192,6 +192,52 @@ def test_contraction_plan_host_logic():
     assert f(9472, 512, 12288) == 0
 
 
+def test_attention_step_launch_forms_host_logic(monkeypatch):
+    """Pure host logic of the attention-step launchers (no GPU needed): which form a launch of `rows` rows takes
+    (DESIGN.md 5.1).  148 SMs, at most 4 resident CTAs per SM (2 for the 128-register instantiations)."""
+    from icd_b200._lib import lib, check
+    for v in ("ICD_ATT_FWD_SPLIT", "ICD_ATT_BWD_SPLIT", "ICD_ATT_BWD_SPLIT_ROWS", "ICD_ATT_BWD_DEEP"):
+        monkeypatch.delenv(v, raising=False)
+    L = lib()
+
+    def plan(direction, rows, P=196, C=2048, A=512):
+        out = (ctypes.c_int32 * 4)()
+        check(L.icd_attention_step_launch_plan_bf16(direction, rows, P, C, A, out), "launch_plan")
+        return tuple(out)          # (CTAs per shared row, shared rows, grid, 128-register instantiation)
+    # forward: four CTAs per row up to 48 rows, two up to 222, the deep instantiation while the grid stays within 2 CTAs per SM
+    assert plan(0, 24) == (4, 24, 96, 1) and plan(0, 48) == (4, 48, 192, 1)
+    assert plan(0, 100) == (2, 100, 200, 1) and plan(0, 148) == (2, 148, 296, 1)
+    assert plan(0, 149) == (2, 149, 298, 0) and plan(0, 222) == (2, 222, 444, 0)
+    assert plan(0, 223) == (1, 0, 223, 0) and plan(0, 512) == (1, 0, 512, 0)
+    # backward: every row as two halves up to 222 rows (deep up to 148); above that the row balance over the 148 SMs
+    assert plan(1, 32) == (2, 32, 64, 1) and plan(1, 148) == (2, 148, 296, 1) and plan(1, 200) == (2, 200, 400, 0)
+    assert plan(1, 512) == (2, 80, 592, 0)            # full form: 432 whole + 160 halves = 4 CTAs per SM
+    assert plan(1, 480) == (2, 112, 592, 0)
+    assert plan(1, 320) == (2, 24, 344, 0)            # minimal form: the 24 rows beyond 2 per SM run as halves
+    assert plan(1, 468) == (2, 24, 492, 0)
+    assert plan(1, 296) == (1, 0, 296, 0) and plan(1, 444) == (1, 0, 444, 0) and plan(1, 592) == (1, 0, 592, 0)
+    assert plan(1, 400) == (2, 44, 444, 0)
+    assert plan(1, 256) == (2, 40, 296, 0)            # full form: 216 whole + 80 halves = 2 CTAs per SM
+    assert plan(1, 230) == (1, 0, 230, 0)             # 82 rows beyond one per SM: neither form applies (66 > 230 / 4, 82 > 74)
+    for rows in range(1, 700):                        # whole rows always pair up (2-CTA clusters); never more halves than rows
+        per, shared, grid, deep = plan(1, rows)
+        assert 0 <= shared <= rows and grid == rows + shared and (shared == 0 or (rows - shared) % 2 == 0)
+        assert not deep or grid <= 296
+        per, shared, grid, deep = plan(0, rows)
+        assert grid == rows * per and (not deep or grid <= 296)
+    assert plan(1, 300, P=16) == (1, 0, 300, 0)       # fewer than 32 pixels: rows are never shared
+    # environment overrides (test hooks)
+    monkeypatch.setenv("ICD_ATT_FWD_SPLIT", "1")
+    assert plan(0, 24) == (1, 0, 24, 0)
+    monkeypatch.setenv("ICD_ATT_BWD_SPLIT", "0")
+    assert plan(1, 32) == (1, 0, 32, 0) and plan(1, 512) == (1, 0, 512, 0)
+    monkeypatch.setenv("ICD_ATT_BWD_SPLIT", "2")
+    assert plan(1, 512) == (2, 512, 1024, 0)
+    monkeypatch.delenv("ICD_ATT_BWD_SPLIT")
+    monkeypatch.setenv("ICD_ATT_BWD_DEEP", "0")
+    assert plan(1, 32) == (2, 32, 64, 0)
+
+
 def test_reference_install_is_a_verbatim_copy():
     """baseline/_ref (bench.py's reference arm) holds the UNMODIFIED reference: every installed file hashes like its source
     (when the source tree is present) and like the manifest written at install time."""
