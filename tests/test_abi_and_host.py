@@ -127,6 +127,14 @@ def test_synthetic_inputs_shapes_and_schedule():
     assert bt == [4, 4, 3, 3, 2, 2, 2]
     t = synthetic.glove_like_table(20)
     assert t.dtype == torch.float64 and t.shape == (20, 300)
+    # the regime-B workload of bench.py (`configs[2]_regime_B_ragged_bf16`): lengths U{8..25} sorted descending at
+    # B = 512 -> 8133 decode tokens per step against 12 288 in regime A; batch_size_t falls from 512 to a few dozen rows
+    caps, lens = synthetic.captions(512, 9490, max_len=25, lengths="ragged")
+    assert lens == sorted(lens, reverse=True) and lens[0] == 25 and min(lens) >= 8
+    dl = [l - 1 for l in lens]
+    assert sum(dl) == 8133
+    bt = [sum(l > t for l in dl) for t in range(max(dl))]
+    assert len(bt) == 24 and bt[0] == 512 and bt[6] == 512 and bt[-1] < 48 and bt == sorted(bt, reverse=True)
 
 
 def test_flat_param_buffer_views_share_storage():
