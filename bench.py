@@ -16,7 +16,8 @@ buffers through the public module API, H2D copies of features+captions and the D
 region (+ the box's copy-only H2D ceiling measured in the same run).  `roofline`: the DOMINANT kernel of the step, the
 fused attention-step backward (HBM-bound), algorithmic bytes / live CUDA-event time; the forward kernel nested under
 `roofline.fwd`.  `beam5`: configs[4], image-sharded over all ranks with the final gather.  At N = 1 the line also carries
-`other_configs` (configs[1] baseline decoder, configs[3] glove_att, the fp32x3 / fp32 tiers of configs[2], the unmodified
+`other_configs` (configs[1] baseline decoder, configs[3] glove_att, configs[2] in length regime B = ragged captions with the
+shrinking batch_size_t of models/attention.py:261-265, the fp32x3 / fp32 tiers of configs[2], the unmodified
 reference run by eager PyTorch on the same GPU, a parity check of the timed path against the fp64 oracle) and
 `cpu_baseline` / `cpu_baseline_configs0`.  `--impl reference` (and `cpu_baseline`): the UNMODIFIED reference modules from
 baseline/_ref (baseline/install_ref.py) on the host cores, on a bounded 32-caption slice of the same workload.
