@@ -246,6 +246,24 @@ def test_attention_step_launch_forms_host_logic(monkeypatch):
     assert plan(1, 32) == (2, 32, 64, 0)
 
 
+def test_version_counter_guard_of_the_autograd_functions():
+    """The decoders' backward reads weights through raw pointers; `_lib.remember_versions` / `check_versions` stand in for
+    autograd's saved-tensor check (pure host logic: CPU tensors suffice)."""
+    from icd_b200 import _lib
+
+    class Ctx:
+        pass
+    ctx = Ctx()
+    w, b, other = torch.zeros(3, 3), torch.zeros(3), object()
+    _lib.remember_versions(ctx, [("fc.weight", w), ("fc.bias", b), ("not_a_tensor", other), ("absent", None)])
+    _lib.check_versions(ctx, "Decoder")                      # untouched: passes
+    view = w[0]
+    view.add_(1.0)                                           # an in-place update through a VIEW bumps the base's counter too
+    with pytest.raises(RuntimeError, match="'fc.weight' needed for the backward was modified by an in-place operation"):
+        _lib.check_versions(ctx, "Decoder")
+    _lib.check_versions(Ctx(), "Decoder")                    # a ctx that recorded nothing checks nothing
+
+
 def test_reference_install_is_a_verbatim_copy():
     """baseline/_ref (bench.py's reference arm) holds the UNMODIFIED reference: every installed file hashes like its source
     (when the source tree is present) and like the manifest written at install time."""
